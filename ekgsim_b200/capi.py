@@ -1,0 +1,181 @@
+"""ekgsim_b200/capi.py -- ctypes binding of the C ABI (include/ekgsim_b200.h).
+
+The product is the shared library `libekgsim_b200.so` (hand-written sm_100a CUDA behind an
+extern "C" boundary) plus the host-side C++ facade in ekgsim_b200/host/.  This module is the
+thin Python view of the same ABI used by tests/, bench.py and __graft_entry__.py; it adds no
+compute of its own and has no CPU fallback: if the library is missing or no CUDA device is
+present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libekgsim_b200.so")
+
+NBHD = {"2D4": 0, "2D8": 1, "3D4": 2, "3D8": 3, "cube": 3}
+MODE_DEFAULT, MODE_DIRECT, MODE_HOISTED = 0, 1, 2
+START_FLAG = 0x1000
+
+# every symbol include/ekgsim_b200.h declares: name -> (restype, argtypes)
+_p, _i64, _d, _int = C.c_void_p, C.c_int64, C.c_double, C.c_int
+SYMBOLS = {
+    "ekg_abi_version": (_int, []),
+    "ekg_last_error": (C.c_char_p, []),
+    "ekg_device_count": (_int, []),
+    "ekg_model_create": (_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _int, C.POINTER(_p)]),
+    "ekg_model_destroy": (None, [_p]),
+    "ekg_model_set_slab": (_int, [_p, _i64, _i64]),
+    "ekg_model_num_voxels": (_i64, [_p]),
+    "ekg_model_num_layers": (_i64, [_p]),
+    "ekg_model_activation": (_int, [_p, _p, C.POINTER(_i64)]),
+    "ekg_model_activation_ms": (_d, [_p]),
+    "ekg_model_set_activation": (_int, [_p, _p]),
+    "ekg_model_get_activation": (_int, [_p, _p]),
+    "ekg_model_ap_classes": (_int, [_p, _p, C.POINTER(_i64)]),
+    "ekg_simulate": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p]),
+    "ekg_simulate_device": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _p]),
+    "ekg_last_launch_count": (_i64, [_p]),
+    "ekg_last_kernel_name": (C.c_char_p, [_p]),
+}
+
+_lib = None
+
+
+class EkgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (code %d)" % (msg, code))
+        self.code = code
+
+
+def lib():
+    """Loads libekgsim_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libekgsim_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise EkgError(rc, lib().ekg_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def n_steps(total_time, t_step):
+    return int(np.ceil(total_time / t_step))  # simulator.cpp:471
+
+
+class Model:
+    """Device-resident voxel model (layers + conduction matrix + activation map)."""
+
+    def __init__(self, layers, transfer, device=0):
+        layers = np.ascontiguousarray(layers, dtype=np.uint16)
+        if layers.ndim == 2:
+            layers = layers[None]
+        transfer = np.ascontiguousarray(transfer, dtype=np.float64)
+        self.shape = layers.shape
+        self.device = device
+        self._h = C.c_void_p()
+        Z, Y, X = layers.shape
+        _check(lib().ekg_model_create(_ptr(layers), Z, Y, X, _ptr(transfer), transfer.shape[0], transfer.shape[1],
+                                      device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().ekg_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def num_voxels(self):
+        return int(lib().ekg_model_num_voxels(self._h))
+
+    @property
+    def num_layers(self):
+        return int(lib().ekg_model_num_layers(self._h))
+
+    def set_slab(self, z0, z1):
+        _check(lib().ekg_model_set_slab(self._h, int(z0), int(z1)))
+
+    def activation(self):
+        """Runs the automaton on the GPU; returns (delay[Z,Y,X] f64, sweeps)."""
+        out = np.empty(self.shape, dtype=np.float64)
+        sweeps = C.c_int64(0)
+        _check(lib().ekg_model_activation(self._h, _ptr(out), C.byref(sweeps)))
+        return out, int(sweeps.value)
+
+    @property
+    def activation_ms(self):
+        return float(lib().ekg_model_activation_ms(self._h))
+
+    def set_activation(self, delay):
+        delay = np.ascontiguousarray(delay, dtype=np.float64)
+        assert delay.size == int(np.prod(self.shape))
+        _check(lib().ekg_model_set_activation(self._h, _ptr(delay)))
+
+    def get_activation(self):
+        out = np.empty(self.shape, dtype=np.float64)
+        _check(lib().ekg_model_get_activation(self._h, _ptr(out)))
+        return out
+
+    def ap_classes(self):
+        idx = np.empty(self.shape, dtype=np.int64)
+        K = C.c_int64(0)
+        _check(lib().ekg_model_ap_classes(self._h, _ptr(idx), C.byref(K)))
+        return int(K.value), idx
+
+    def simulate(self, layer_k, leads_zyx, nbhd="3D4", t_start=100.0, t_step=1.0, total_time=400.0, mode=MODE_DEFAULT):
+        """Host buffers in, host ECG [B, L, T] out (the call EkgSim::run maps to)."""
+        layer_k = np.ascontiguousarray(layer_k, dtype=np.float64)
+        if layer_k.ndim == 2:
+            layer_k = layer_k[None]
+        B = layer_k.shape[0]
+        assert layer_k.shape[1:] == (self.num_layers, 9), layer_k.shape
+        leads = np.ascontiguousarray(leads_zyx, dtype=np.float64)
+        if leads.ndim == 2:
+            leads = np.broadcast_to(leads[None], (B,) + leads.shape).copy()
+        L = leads.shape[1]
+        T = n_steps(total_time, t_step)
+        out = np.empty((B, L, T), dtype=np.float64)
+        _check(lib().ekg_simulate(self._h, _ptr(layer_k), _ptr(leads), B, L, NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd),
+                                  float(t_start), float(t_step), float(total_time), int(mode), _ptr(out)))
+        return out
+
+    def simulate_device(self, d_layer_k, d_leads, B, L, d_ecg, nbhd="3D4", t_start=100.0, t_step=1.0, total_time=400.0,
+                        mode=MODE_DEFAULT, stream=0):
+        """Raw device pointers (ints) on this model's device; asynchronous on `stream`."""
+        _check(lib().ekg_simulate_device(self._h, C.c_void_p(d_layer_k), C.c_void_p(d_leads), int(B), int(L),
+                                         NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd), float(t_start), float(t_step),
+                                         float(total_time), int(mode), C.c_void_p(d_ecg), C.c_void_p(stream)))
+
+    @property
+    def last_launch_count(self):
+        return int(lib().ekg_last_launch_count(self._h))
+
+    @property
+    def last_kernel_name(self):
+        return lib().ekg_last_kernel_name(self._h).decode()

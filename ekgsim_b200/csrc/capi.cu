@@ -1,0 +1,356 @@
+// ekgsim_b200/csrc/capi.cu -- the extern "C" entry points of libekgsim_b200.so and the host-side
+// preparation of the device-resident model (compaction, neighbour masks, edge-weight table).
+// Interface and the reference symbols each entry point replaces: include/ekgsim_b200.h.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+
+#include "ekg_internal.cuh"
+
+namespace ekg {
+
+static thread_local std::string g_error;
+
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(int code, const std::string& msg) { g_error = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+	char buf[512];
+	snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+	g_error = buf;
+	cudaGetLastError();  // clear the sticky-less error state
+	return EKG_E_CUDA;
+}
+
+constexpr uint16_t kStartFlag = 0x1000;  // ShapeElement::layerStartingPoint (matrix.h:90)
+
+__global__ void gather_at_kernel(const double* __restrict__ time_pad, const uint32_t* __restrict__ pidx, double* __restrict__ at, int64_t n) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double v = time_pad[pidx[i]];
+	at[i] = isinf(v) ? 0.0 : v;  // never reached -> excitationDelay stays 0 (simulator.cpp:219)
+}
+
+static int64_t pad_index(const ekg_model* m, int64_t z, int64_t y, int64_t x) { return ((z + 1) * m->pY + (y + 1)) * m->pX + (x + 1); }
+
+static void free_model(ekg_model* m) {
+	if (!m) return;
+	cudaSetDevice(m->device);
+	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at,
+	                m->d_segs, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg};
+	for (void* p : ptrs) if (p) cudaFree(p);
+	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
+	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
+	if (m->stream) cudaStreamDestroy(m->stream);
+	delete m;
+}
+
+// (re)build the layer-sorted ECG voxel list for z in [z0, z1)
+static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
+	const int64_t Y = m->Y, X = m->X;
+	const int nl = m->n_layers;
+	std::vector<int64_t> cnt(nl + 2, 0);
+	for (int64_t z = z0; z < z1; ++z) for (int64_t i = z * Y * X; i < (z + 1) * Y * X; ++i) if (m->h_layer[i]) ++cnt[m->h_layer[i]];
+	m->layer_off.assign(nl + 1, 0);
+	for (int l = 1; l <= nl; ++l) m->layer_off[l] = m->layer_off[l - 1] + cnt[l];
+	const int64_t n = m->layer_off[nl];
+	std::vector<uint32_t> pos(n), mask(n), pidx(n);
+	std::vector<int64_t> cur(m->layer_off.begin(), m->layer_off.end());
+
+	// padded layer map for bounds-free neighbour tests
+	std::vector<uint8_t> lp((size_t)(m->pZ * m->pY * m->pX), 0);
+	for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < Y; ++y)
+		memcpy(&lp[pad_index(m, z, y, 0)], &m->h_layer[(z * Y + y) * X], (size_t)X);
+	NbrTable cube;
+	make_nbr_table(EKG_NBHD_3D8, &cube);
+	int64_t off[kMaxNbr];
+	for (int k = 0; k < cube.n; ++k) off[k] = (cube.dz[k] * m->pY + cube.dy[k]) * m->pX + cube.dx[k];
+
+	for (int64_t z = z0; z < z1; ++z) for (int64_t y = 0; y < Y; ++y) for (int64_t x = 0; x < X; ++x) {
+		const uint8_t l = m->h_layer[(z * Y + y) * X + x];
+		if (!l) continue;
+		const int64_t p = pad_index(m, z, y, x);
+		uint32_t mk = 0;
+		for (int k = 0; k < cube.n; ++k) if (lp[p - off[k]]) mk |= 1u << k;  // neighbour = index - dif (simulator.cpp:514)
+		const int64_t j = cur[l - 1]++;
+		pos[j] = (uint32_t)x | ((uint32_t)y << 11) | ((uint32_t)z << 22);
+		mask[j] = mk;
+		pidx[j] = (uint32_t)p;
+	}
+
+	for (void* p : {(void*)m->d_pos, (void*)m->d_mask, (void*)m->d_ecg_pidx, (void*)m->d_at}) if (p) cudaFree(p);
+	m->d_pos = m->d_mask = m->d_ecg_pidx = nullptr; m->d_at = nullptr;
+	const size_t nn = (size_t)std::max<int64_t>(n, 1);
+	EKG_CUDA(cudaMalloc(&m->d_pos, nn * 4));
+	EKG_CUDA(cudaMalloc(&m->d_mask, nn * 4));
+	EKG_CUDA(cudaMalloc(&m->d_ecg_pidx, nn * 4));
+	EKG_CUDA(cudaMalloc(&m->d_at, nn * 8));
+	EKG_CUDA(cudaMemcpy(m->d_pos, pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+	EKG_CUDA(cudaMemcpy(m->d_mask, mask.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+	EKG_CUDA(cudaMemcpy(m->d_ecg_pidx, pidx.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+	m->n_ecg = n;
+	m->slab_z0 = z0; m->slab_z1 = z1;
+	m->n_segs = 0; m->seg_len = 0;  // segment table depends on the list
+	return EKG_OK;
+}
+
+static int gather_at(ekg_model* m) {
+	if (m->n_ecg == 0) return EKG_OK;
+	gather_at_kernel<<<(int)((m->n_ecg + 255) / 256), 256, 0, m->stream>>>(m->d_time_pad, m->d_ecg_pidx, m->d_at, m->n_ecg);
+	EKG_CUDA(cudaGetLastError());
+	EKG_CUDA(cudaStreamSynchronize(m->stream));
+	return EKG_OK;
+}
+
+// after d_time_pad holds a map: refresh the host raster copy, t0 and the ECG-list gather
+static int publish_activation(ekg_model* m, bool download) {
+	const int64_t n = m->Z * m->Y * m->X;
+	if (download) {
+		std::vector<double> padded((size_t)(m->pZ * m->pY * m->pX));
+		EKG_CUDA(cudaMemcpy(padded.data(), m->d_time_pad, padded.size() * 8, cudaMemcpyDeviceToHost));
+		m->h_delay.assign((size_t)n, 0.0);
+		for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < m->Y; ++y) for (int64_t x = 0; x < m->X; ++x) {
+			const int64_t i = (z * m->Y + y) * m->X + x;
+			if (!m->h_layer[i]) continue;
+			const double v = padded[pad_index(m, z, y, x)];
+			m->h_delay[i] = std::isinf(v) ? 0.0 : v;
+		}
+	}
+	double lo = INFINITY, hi = -INFINITY;
+	for (int64_t i = 0; i < n; ++i) if (m->h_layer[i]) { lo = std::min(lo, m->h_delay[i]); hi = std::max(hi, m->h_delay[i]); }
+	m->t0 = (lo <= hi) ? 0.5 * (lo + hi) : 0.0;
+	m->have_activation = true;
+	return gather_at(m);
+}
+
+}  // namespace ekg
+
+using namespace ekg;
+
+extern "C" {
+
+int ekg_abi_version(void) { return EKG_ABI_VERSION; }
+const char* ekg_last_error(void) { return g_error.c_str(); }
+
+int ekg_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
+                     const double* transfer, int64_t t_rows, int64_t t_cols, int device, ekg_model** out) {
+	if (!out) return fail(EKG_E_INVALID, "out is NULL");
+	*out = nullptr;
+	if (!layers || Z <= 0 || Y <= 0 || X <= 0) return fail(EKG_E_INVALID, "bad shape");
+	if (!transfer || t_rows <= 0 || t_cols <= 0) return fail(EKG_E_INVALID, "bad transfer matrix");
+	if (X > 2047 || Y > 2047 || Z > 1023) return fail(EKG_E_UNSUPPORTED, "grid exceeds the packed coordinate layout (X,Y <= 2047, Z <= 1023)");
+	if ((Z + 2) * (Y + 2) * (X + 2) >= (int64_t)1 << 32) return fail(EKG_E_UNSUPPORTED, "grid exceeds 2^32 padded voxels");
+	if (ekg_device_count() <= device || device < 0) return fail(EKG_E_CUDA, "no such CUDA device (libekgsim_b200 has no CPU fallback)");
+
+	ekg_model* m = new ekg_model();
+	m->device = device;
+	m->Z = Z; m->Y = Y; m->X = X;
+	m->pZ = Z + 2; m->pY = Y + 2; m->pX = X + 2;
+	const int64_t n = Z * Y * X;
+	m->h_layer.resize((size_t)n);
+	int max_layer = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		uint16_t l = layers[i];
+		if (l & kStartFlag) { m->h_starts.push_back(i); l = (uint16_t)(l - kStartFlag); }  // simulator.cpp:261-264
+		if (l > 255) { delete m; return fail(EKG_E_UNSUPPORTED, "more than 255 layers"); }
+		m->h_layer[(size_t)i] = (uint8_t)l;
+		if (l) { ++m->n_occ; max_layer = std::max<int>(max_layer, l); }
+	}
+	m->n_layers = max_layer;  // targetNumOfAps = highest layer number (simulator.cpp:186-198)
+	if (t_rows < max_layer || t_cols < max_layer) { delete m; return fail(EKG_E_TRANSFER, "loaded transfer matrix too small"); }  // simulator.cpp:203-205
+	m->h_transfer.assign(transfer, transfer + t_rows * t_cols);
+	m->t_rows = t_rows; m->t_cols = t_cols;
+
+#define EKG_CREATE_CUDA(call)                                                                   \
+	do {                                                                                        \
+		cudaError_t e__ = (call);                                                               \
+		if (e__ != cudaSuccess) { int rc__ = cuda_fail(e__, #call, __FILE__, __LINE__); free_model(m); return rc__; } \
+	} while (0)
+
+	EKG_CREATE_CUDA(cudaSetDevice(device));
+	EKG_CREATE_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+	EKG_CREATE_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
+
+	// padded dense layer map + raster list of occupied voxels (automaton)
+	const int64_t npad = m->pZ * m->pY * m->pX;
+	{
+		std::vector<uint8_t> lp((size_t)npad, 0);
+		std::vector<uint32_t> pidx((size_t)std::max<int64_t>(m->n_occ, 1));
+		int64_t j = 0;
+		for (int64_t z = 0; z < Z; ++z) for (int64_t y = 0; y < Y; ++y) for (int64_t x = 0; x < X; ++x) {
+			const uint8_t l = m->h_layer[(size_t)((z * Y + y) * X + x)];
+			if (!l) continue;
+			const int64_t p = pad_index(m, z, y, x);
+			lp[(size_t)p] = l;
+			pidx[(size_t)j++] = (uint32_t)p;
+		}
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_layer_pad, (size_t)npad));
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_time_pad, (size_t)npad * 8));
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_auto_pidx, pidx.size() * 4));
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_flags, (size_t)(m->max_sweeps + 1) * sizeof(int)));
+		EKG_CREATE_CUDA(cudaMemcpy(m->d_layer_pad, lp.data(), (size_t)npad, cudaMemcpyHostToDevice));
+		EKG_CREATE_CUDA(cudaMemcpy(m->d_auto_pidx, pidx.data(), pidx.size() * 4, cudaMemcpyHostToDevice));
+		EKG_CREATE_CUDA(cudaMemset(m->d_time_pad, 0, (size_t)npad * 8));
+	}
+	// edge weights: lag = T[layer][neighbour layer] * sqrt(sqrLength(dif)) (simulator.cpp:239-240), host IEEE arithmetic
+	{
+		const int nl1 = max_layer + 1;
+		std::vector<double> w((size_t)nl1 * nl1 * 3, INFINITY);
+		for (int lu = 1; lu < nl1; ++lu) for (int lv = 1; lv < nl1; ++lv) {
+			if (lu >= t_rows || lv >= t_cols) continue;
+			for (int s = 1; s <= 3; ++s) {
+				double lag = transfer[(int64_t)lu * t_cols + lv];
+				lag *= std::sqrt((double)s);
+				w[((size_t)lu * nl1 + lv) * 3 + (s - 1)] = lag;
+			}
+		}
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_wtab, w.size() * 8));
+		EKG_CREATE_CUDA(cudaMemcpy(m->d_wtab, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+	}
+	int rc = build_ecg_list(m, 0, Z);
+	if (rc) { free_model(m); return rc; }
+	*out = m;
+	return EKG_OK;
+}
+
+void ekg_model_destroy(ekg_model* m) { free_model(m); }
+
+int ekg_model_set_slab(ekg_model* m, int64_t z_begin, int64_t z_end) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	if (z_begin < 0 || z_end > m->Z || z_begin > z_end) return fail(EKG_E_INVALID, "bad z range");
+	EKG_CUDA(cudaSetDevice(m->device));
+	int rc = build_ecg_list(m, z_begin, z_end);
+	if (rc) return rc;
+	if (m->have_activation) return gather_at(m);
+	return EKG_OK;
+}
+
+int64_t ekg_model_num_voxels(const ekg_model* m) { return m ? m->n_ecg : 0; }
+int64_t ekg_model_num_layers(const ekg_model* m) { return m ? m->n_layers : 0; }
+
+int ekg_model_activation(ekg_model* m, double* delay_out, int64_t* sweeps_out) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	if (m->h_starts.empty()) return fail(EKG_E_NO_START, "Could not find starting point for excitation sequence");  // simulator.cpp:274-277
+	if (m->n_layers >= m->t_cols || m->n_layers >= m->t_rows) {
+		char buf[128];
+		snprintf(buf, sizeof buf, "transfer (conduction) matrix does not define layer %d", m->n_layers);  // simulator.cpp:234-238
+		return fail(EKG_E_TRANSFER, buf);
+	}
+	EKG_CUDA(cudaSetDevice(m->device));
+	cudaEvent_t e0, e1;
+	EKG_CUDA(cudaEventCreate(&e0));
+	EKG_CUDA(cudaEventCreate(&e1));
+	EKG_CUDA(cudaEventRecord(e0, m->stream));
+	int rc = run_automaton(m, sweeps_out);
+	if (rc == EKG_OK) {
+		cudaEventRecord(e1, m->stream);
+		cudaEventSynchronize(e1);
+		cudaEventElapsedTime(&m->activation_ms, e0, e1);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (rc) return rc;
+	rc = publish_activation(m, true);
+	if (rc) return rc;
+	if (delay_out) memcpy(delay_out, m->h_delay.data(), m->h_delay.size() * 8);
+	return EKG_OK;
+}
+
+int ekg_model_set_activation(ekg_model* m, const double* delay) {
+	if (!m || !delay) return fail(EKG_E_INVALID, "NULL argument");
+	EKG_CUDA(cudaSetDevice(m->device));
+	const int64_t n = m->Z * m->Y * m->X;
+	m->h_delay.assign(delay, delay + n);
+	std::vector<double> padded((size_t)(m->pZ * m->pY * m->pX), 0.0);
+	for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < m->Y; ++y)
+		memcpy(&padded[(size_t)pad_index(m, z, y, 0)], &delay[(z * m->Y + y) * m->X], (size_t)m->X * 8);
+	EKG_CUDA(cudaMemcpy(m->d_time_pad, padded.data(), padded.size() * 8, cudaMemcpyHostToDevice));
+	return publish_activation(m, false);
+}
+
+int ekg_model_get_activation(const ekg_model* m, double* delay_out) {
+	if (!m || !delay_out) return fail(EKG_E_INVALID, "NULL argument");
+	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence yet");
+	memcpy(delay_out, m->h_delay.data(), m->h_delay.size() * 8);
+	return EKG_OK;
+}
+
+double ekg_model_activation_ms(const ekg_model* m) { return m ? (double)m->activation_ms : 0.0; }
+
+int ekg_model_ap_classes(const ekg_model* m, int64_t* ap_index_out, int64_t* n_classes_out) {
+	if (!m || !ap_index_out || !n_classes_out) return fail(EKG_E_INVALID, "NULL argument");
+	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence yet");
+	// one (layer, exact delay) -> index map, indices handed out in first-seen raster order
+	// (simulator.cpp:566-590 keeps one std::map<double,size_t> per layer with a shared counter)
+	struct Key { uint64_t bits; uint32_t layer; bool operator==(const Key& o) const { return bits == o.bits && layer == o.layer; } };
+	struct Hash { size_t operator()(const Key& k) const { uint64_t x = k.bits ^ ((uint64_t)k.layer << 52); x ^= x >> 31; x *= 0x9e3779b97f4a7c15ULL; x ^= x >> 29; return (size_t)x; } };
+	std::unordered_map<Key, int64_t, Hash> map;
+	map.reserve((size_t)m->n_occ / 4 + 16);
+	const int64_t n = m->Z * m->Y * m->X;
+	int64_t next = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		if (!m->h_layer[(size_t)i]) { ap_index_out[i] = -1; continue; }
+		Key k; memcpy(&k.bits, &m->h_delay[(size_t)i], 8); k.layer = m->h_layer[(size_t)i];
+		auto it = map.find(k);
+		if (it == map.end()) { map.emplace(k, next); ap_index_out[i] = next++; }
+		else ap_index_out[i] = it->second;
+	}
+	*n_classes_out = next;
+	return EKG_OK;
+}
+
+int ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_leads_zyx, int64_t B, int64_t n_leads, int nbhd,
+                        double t_start, double t_step, double total_time, int flags, double* d_ecg_out, void* stream) {
+	if (!m || !d_layer_k || !d_leads_zyx || !d_ecg_out) return fail(EKG_E_INVALID, "NULL argument");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return run_ecg(m, d_layer_k, d_leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, d_ecg_out,
+	               stream ? (cudaStream_t)stream : m->stream);
+}
+
+int ekg_simulate(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
+                 double t_start, double t_step, double total_time, int flags, double* ecg_out) {
+	if (!m || !layer_k || !leads_zyx || !ecg_out) return fail(EKG_E_INVALID, "NULL argument");
+	if (B <= 0 || n_leads <= 0 || !(t_step > 0) || !(total_time > 0)) return fail(EKG_E_INVALID, "bad sizes");
+	EKG_CUDA(cudaSetDevice(m->device));
+	const int64_t T = (int64_t)ceil(total_time / t_step);
+	const int64_t nk = B * m->n_layers * 9, nlead = B * n_leads * 3, necg = B * n_leads * T;
+	int rc;
+	if ((rc = ensure(&m->d_io_k, &m->io_k_cap, nk))) return rc;
+	if ((rc = ensure(&m->d_io_leads, &m->io_leads_cap, nlead))) return rc;
+	if ((rc = ensure(&m->d_io_ecg, &m->io_ecg_cap, necg))) return rc;
+	if (m->pin_in_cap < nk + nlead) {
+		if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
+		m->h_pin_in = nullptr; m->pin_in_cap = 0;
+		EKG_CUDA(cudaMallocHost(&m->h_pin_in, (size_t)(nk + nlead) * 8));
+		m->pin_in_cap = nk + nlead;
+	}
+	if (m->pin_out_cap < necg) {
+		if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
+		m->h_pin_out = nullptr; m->pin_out_cap = 0;
+		EKG_CUDA(cudaMallocHost(&m->h_pin_out, (size_t)necg * 8));
+		m->pin_out_cap = necg;
+	}
+	memcpy(m->h_pin_in, layer_k, (size_t)nk * 8);
+	memcpy(m->h_pin_in + nk, leads_zyx, (size_t)nlead * 8);
+	EKG_CUDA(cudaMemcpyAsync(m->d_io_k, m->h_pin_in, (size_t)nk * 8, cudaMemcpyHostToDevice, m->stream));
+	EKG_CUDA(cudaMemcpyAsync(m->d_io_leads, m->h_pin_in + nk, (size_t)nlead * 8, cudaMemcpyHostToDevice, m->stream));
+	rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, flags, m->d_io_ecg, m->stream);
+	if (rc) return rc;
+	EKG_CUDA(cudaMemcpyAsync(m->h_pin_out, m->d_io_ecg, (size_t)necg * 8, cudaMemcpyDeviceToHost, m->stream));
+	EKG_CUDA(cudaStreamSynchronize(m->stream));
+	memcpy(ecg_out, m->h_pin_out, (size_t)necg * 8);
+	return EKG_OK;
+}
+
+int64_t ekg_last_launch_count(const ekg_model* m) { return m ? m->last_launches : 0; }
+const char* ekg_last_kernel_name(const ekg_model* m) { return m ? m->last_kernel : "none"; }
+
+}  // extern "C"

@@ -1,0 +1,415 @@
+// ekgsim_b200/csrc/ecg.cu -- fused AP + stencil + lead-reduction kernels (sm_100a).
+//
+// Replaces Simulation::run (reference simlib/simulator.cpp:452-550), which for every occupied
+// voxel c and time sample t evaluates the voxel's action potential V_c(t) and those of its
+// occupied neighbours (WohlfartPlus::operator[], Wohlfart.h:195-203, through
+// ActionPotential::operator(), simulator.cpp:154-170), forms the dipole
+// D_c(t) = sum_dif dif * (V_{c-dif}(t) - V_c(t)) (:511-525) and projects it on every lead with
+// w_{l,c} = (mp_l - p_c)/|mp_l - p_c|^3 (:530-537).
+//
+// Design:
+//  * The double sum is re-associated per voxel:  ECG_l(t) = sum_c G_{l,c} V_c(t) with the
+//    time-invariant lead-field/stencil coefficient
+//        G_{l,c} = - [ (sum_{k in occ(c)} dif_k) . w_{l,c} + sum_{k in occ(c)} dif_k . w_{l,c-dif_k} ]
+//    so each AP is evaluated ONCE per voxel and time sample (the reference evaluates it 8.65x)
+//    and the stencil never touches the time loop.  G is computed on the fly in the kernel's
+//    phase A from the voxel's packed coordinates and its 26-bit neighbour-occupancy mask; the AP
+//    field and G are never materialised in HBM.
+//  * One thread owns one time sample; a CTA owns one segment (a run of voxels of one layer) of
+//    one parameter vector.  Per-layer AP coefficients live in registers, per-voxel data
+//    (activation time, G) is staged through shared memory and read as warp-wide broadcasts, the
+//    per-lead sums stay in registers for the whole voxel loop (fp32 for 32 voxels, then folded
+//    into fp64), and one f64 partial per (segment, vector, lead, sample) is written at the end.
+//    A second tiny kernel adds the partials in a fixed order -> bitwise run-to-run determinism.
+//  * DIRECT variant: the full 9-coefficient AP per voxel and sample = 5 ex2 + 1 lg2 + 1 rcp on
+//    the MUFU pipe (the binding unit) + ~20 FP32 ops.  HOISTED variant: the factors that do not
+//    depend on the voxel (repolarisation sigmoid, exp(-k t)) come from a per-(vector, layer,
+//    sample) table computed in f64, the factors that do not depend on time (exp(+k at)) are
+//    computed once per voxel in phase A; only the depolarisation sigmoid 1/(1+exp(-k1 (t-at)))
+//    remains per voxel and sample (1 ex2 + 1 rcp).
+//
+// Algorithmic traffic: 16 B per voxel (pos, mask, at) per CTA, re-read by the B CTAs of a
+// segment from L2; 0.04 B per voxel-timestep at T = 400 -> MUFU-bound, not HBM-bound.
+
+#include "ekg_internal.cuh"
+
+namespace ekg {
+
+// ---- MUFU wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rsq(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 1/|q|^3 with one Newton step on the reciprocal square root (error ~1 ulp)
+__device__ __forceinline__ float inv_cube(float sq) {
+	float y = mufu_rsq(sq);
+	y = y * fmaf(-0.5f * sq, y * y, 1.5f);
+	return y * y * y;
+}
+
+constexpr int MODE_DIRECT = 1;
+constexpr int MODE_HOISTED = 2;
+
+template <int MODE, int NL>
+struct RowLayout {
+	static constexpr int kUsed = (MODE == MODE_HOISTED ? 3 : 1) + NL;
+	static constexpr int kFloats = kUsed <= 4 ? 4 : 8;
+};
+
+// ---- the fused kernel ---------------------------------------------------------------------------
+template <int MODE, int NL>
+__global__ void __launch_bounds__(kEcgThreadsMax, 2) ecg_kernel(const EcgArgs a) {
+	constexpr int ROW = RowLayout<MODE, NL>::kFloats;
+	__shared__ __align__(16) float s_vox[kChunk * ROW];
+	__shared__ double s_lead[NL * 3];
+
+	const Segment sg = a.segs[blockIdx.x];
+	const int b = blockIdx.y;
+	const int t = blockIdx.z * blockDim.x + threadIdx.x;
+	const bool live = t < a.T;
+
+	if (threadIdx.x < NL * 3) {
+		const int l = a.lead0 + threadIdx.x / 3;
+		s_lead[threadIdx.x] = l < a.L ? a.leads[((int64_t)b * a.L + l) * 3 + threadIdx.x % 3] : 0.0;
+	}
+
+	// per-thread constants of (vector b, layer, sample t)
+	const float* P = a.params + ((int64_t)b * a.n_layers + (sg.layer - 1)) * kParamStride;
+	const float a1 = __ldg(P + 0), a4 = __ldg(P + 1), a5 = __ldg(P + 2), k0 = __ldg(P + 8);
+	float a7 = 0.f, c2 = 0.f, np = 0.f, A = 0.f, Bc = 0.f, k8hi = 0.f, k8lo = 0.f, F1 = 0.f, F2 = 0.f;
+	const float t0 = __ldg(P + 11);  // HOISTED: centre of the activation-time range
+	if (MODE == MODE_DIRECT) {
+		a7 = __ldg(P + 3); c2 = __ldg(P + 4); np = __ldg(P + 5); A = __ldg(P + 6); Bc = __ldg(P + 7);
+		k8hi = __ldg(P + 9); k8lo = __ldg(P + 10);
+	} else if (live) {
+		const float* F = a.ftab + (((int64_t)b * a.n_layers + (sg.layer - 1)) * 2) * a.T + t;
+		F1 = __ldg(F);
+		F2 = __ldg(F + a.T);
+	}
+	const float thi = live ? __ldg(a.t_hi + t) : 0.f;
+	const float tlo = live ? __ldg(a.t_lo + t) : 0.f;
+
+	double acc64[NL];
+#pragma unroll
+	for (int l = 0; l < NL; ++l) acc64[l] = 0.0;
+
+	for (int base = sg.begin; base < sg.end; base += kChunk) {
+		const int n = min(kChunk, sg.end - base);
+		__syncthreads();  // phase B of the previous chunk is done with s_vox; s_lead is visible
+
+		// ---- phase A: per-voxel, time-invariant data -> shared memory ----
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
+			const uint32_t pos = __ldg(a.pos + base + j);
+			const uint32_t mask = __ldg(a.mask + base + j);
+			const float at = (float)__ldg(a.at + base + j);
+			// voxel position = its index in the zero-bordered matrix (simulator.cpp:487, :531)
+			const double pz = (double)((pos >> 22) + 1u), py = (double)(((pos >> 11) & 0x7ffu) + 1u), px = (double)((pos & 0x7ffu) + 1u);
+			float G[NL];
+#pragma unroll
+			for (int l = 0; l < NL; ++l) {
+				const float rz = (float)(s_lead[3 * l] - pz), ry = (float)(s_lead[3 * l + 1] - py), rx = (float)(s_lead[3 * l + 2] - px);
+				float g = 0.f;
+				int sz = 0, sy = 0, sx = 0;
+				for (int k = 0; k < a.nbr.n; ++k) {
+					if ((mask >> a.nbr.bit[k]) & 1u) {
+						const int dz = a.nbr.dz[k], dy = a.nbr.dy[k], dx = a.nbr.dx[k];
+						const float qz = rz + (float)dz, qy = ry + (float)dy, qx = rx + (float)dx;  // mp - p_{c-dif}
+						const float sq = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
+						const float dot = (float)dz * qz + (float)dy * qy + (float)dx * qx;
+						g = fmaf(dot, inv_cube(sq), g);
+						sz += dz; sy += dy; sx += dx;
+					}
+				}
+				const float sqc = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+				g = fmaf((float)sz * rz + (float)sy * ry + (float)sx * rx, inv_cube(sqc), g);
+				G[l] = (a.lead0 + l < a.L) ? -g : 0.f;
+			}
+			float* row = s_vox + j * ROW;
+			if (MODE == MODE_DIRECT) {
+				row[0] = at;
+#pragma unroll
+				for (int l = 0; l < NL; ++l) row[1 + l] = G[l];
+			} else {
+				// time-invariant AP factors exp((k4+k5)(at-t0)), exp(k5 (at-t0)); clamped so that
+				// the products with the (also clamped) table entries can never be inf*0
+				const float da = at - t0;
+				row[0] = at;
+				row[1] = mufu_ex2(fminf(-(a4 + a5) * da, 60.f));
+				row[2] = mufu_ex2(fminf(-a5 * da, 60.f));
+#pragma unroll
+				for (int l = 0; l < NL; ++l) row[3 + l] = G[l];
+			}
+		}
+		__syncthreads();
+
+		// ---- phase B: time loop, one sample per thread, voxels broadcast from shared memory ----
+		if (live) {
+			for (int j0 = 0; j0 < n; j0 += 32) {
+				const int j1 = min(j0 + 32, n);
+				float acc[NL];
+#pragma unroll
+				for (int l = 0; l < NL; ++l) acc[l] = 0.f;
+#pragma unroll 4
+				for (int j = j0; j < j1; ++j) {
+					const float4* rp = reinterpret_cast<const float4*>(s_vox + j * ROW);
+					const float4 r0 = rp[0];
+					float V;
+					float G[NL];
+					const float tau = (thi - r0.x) + tlo;               // t - at   (simulator.cpp:169)
+					const float S = mufu_rcp(1.f + mufu_ex2(a1 * tau));  // 1/(1+exp(-k1 t'))
+					if (MODE == MODE_DIRECT) {
+						const float k8s = k8hi - r0.x;                   // k8 - at  (simulator.cpp:156)
+						const float u = (tau - k8s) - k8lo;              // t' - k8'
+						const float e = mufu_ex2(fmaf(a7, u, c2));       // exp(-k7 (t'-k8') + ln(2^(k7/k6)-1))
+						const float Q = mufu_ex2(np * mufu_lg2(1.f + e)); // (1+e)^(-k6/k7)
+						const float Pp = fmaf(A, mufu_ex2(a4 * tau), Bc); // k2((1-k3) exp(-k4 t') + k3)
+						const float E5 = mufu_ex2(a5 * tau);
+						V = fmaf((S * Pp) * E5, 1.f - Q, k0);
+						G[0] = r0.y;
+						if (NL >= 2) G[1] = r0.z;
+						if (NL >= 3) G[2] = r0.w;
+						if (NL >= 4) G[3] = rp[1].x;
+					} else {
+						const float4 r1 = rp[1];
+						V = fmaf(S, fmaf(F1, r0.y, F2 * r0.z), k0);
+						G[0] = r0.w;
+						if (NL >= 2) G[1] = r1.x;
+						if (NL >= 3) G[2] = r1.y;
+						if (NL >= 4) G[3] = r1.z;
+					}
+#pragma unroll
+					for (int l = 0; l < NL; ++l) acc[l] = fmaf(G[l], V, acc[l]);
+				}
+#pragma unroll
+				for (int l = 0; l < NL; ++l) acc64[l] += (double)acc[l];
+			}
+		}
+	}
+
+	if (live) {
+#pragma unroll
+		for (int l = 0; l < NL; ++l) {
+			const int lead = a.lead0 + l;
+			if (lead < a.L) a.partial[(((int64_t)blockIdx.x * a.B + b) * a.L + lead) * a.T + t] = acc64[l];
+		}
+	}
+}
+
+// ---- partial sums -> ECG, fixed order ------------------------------------------------------------
+__global__ void __launch_bounds__(256) ecg_reduce_kernel(const double* __restrict__ partial, double* __restrict__ ecg, int n_segs, int64_t n_out) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_out) return;
+	double s = 0.0;
+	for (int k = 0; k < n_segs; ++k) s += partial[(int64_t)k * n_out + i];
+	ecg[i] = s;
+}
+
+// ---- per-(vector, layer) coefficient tables, f64 -> f32 -------------------------------------------
+// P[0..11] = -k1 log2e, -k4 log2e, -k5 log2e, -k7 log2e, log2(2^(k7/k6)-1), -k6/k7, k2(1-k3), k2 k3,
+//            k0, hi(k8), lo(k8), t0
+__global__ void ecg_params_kernel(const double* __restrict__ layer_k, float* __restrict__ P, int64_t n, float t0) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double* k = layer_k + i * 9;
+	const double log2e = 1.4426950408889634074;
+	float* p = P + i * kParamStride;
+	p[0] = (float)(-k[1] * log2e);
+	p[1] = (float)(-k[4] * log2e);
+	p[2] = (float)(-k[5] * log2e);
+	p[3] = (float)(-k[7] * log2e);
+	p[4] = (float)(log(pow(2.0, k[7] / k[6]) - 1.0) * log2e);
+	p[5] = (float)(-(k[6] / k[7]));
+	p[6] = (float)(k[2] * (1.0 - k[3]));
+	p[7] = (float)(k[2] * k[3]);
+	p[8] = (float)k[0];
+	const float k8hi = (float)k[8];
+	p[9] = k8hi;
+	p[10] = (float)(k[8] - (double)k8hi);
+	p[11] = t0;
+}
+
+// HOISTED table: F1 = k2(1-k3) R(t) exp(-(k4+k5)(t-t0)),  F2 = k2 k3 R(t) exp(-k5 (t-t0)),
+// R(t) = 1 - (1 + exp(-k7 (t-k8) + ln(2^(k7/k6)-1)))^(-k6/k7)        (Wohlfart.h:199-201; the
+// activation time cancels in t' - k8' = (t-at) - (k8-at), simulator.cpp:156,:169)
+__global__ void ecg_ftab_kernel(const double* __restrict__ layer_k, const double* __restrict__ times, float* __restrict__ F,
+                                int64_t n_bl, int T, double t0) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_bl * T) return;
+	const int64_t bl = i / T;
+	const int t = (int)(i % T);
+	const double* k = layer_k + bl * 9;
+	const double tt = times[t];
+	const double R = 1.0 - pow(1.0 + exp(-k[7] * (tt - k[8]) + log(pow(2.0, k[7] / k[6]) - 1.0)), -(k[6] / k[7]));
+	const double lim = 60.0 * 0.69314718055994530942;  // same clamp as phase A (2^60)
+	const double f1 = k[2] * (1.0 - k[3]) * R * exp(fmin(-(k[4] + k[5]) * (tt - t0), lim));
+	const double f2 = k[2] * k[3] * R * exp(fmin(-k[5] * (tt - t0), lim));
+	F[(bl * 2) * T + t] = (float)f1;
+	F[(bl * 2 + 1) * T + t] = (float)f2;
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+int make_nbr_table(int nbhd, NbrTable* out) {
+	// same enumeration order as Neighbourhood::create (simulator.h:376-384); bit = index in the cube list
+	int n = 0, cube = 0;
+	for (int a0 = 0; a0 < 3; ++a0) for (int a1 = 0; a1 < 3; ++a1) for (int a2 = 0; a2 < 3; ++a2) {
+		const int d0 = abs(a0 - 1), d1 = abs(a1 - 1), d2 = abs(a2 - 1);
+		const int mx3 = std::max(std::max(d0, d1), d2), mn3 = std::min(std::min(d0, d1), d2);
+		const bool in_cube = mx3 == 1;
+		bool keep = false;
+		switch (nbhd) {
+		case EKG_NBHD_2D4: keep = std::min(d1, d2) == 1 && std::max(d1, d2) == 1 && d0 == 0; break;  // callback4N :338
+		case EKG_NBHD_2D8: keep = std::max(d1, d2) == 1 && d0 == 0; break;                            // callback8N :348
+		case EKG_NBHD_3D4: keep = mn3 == 1 && mx3 == 1; break;                                          // callback3x2N :357
+		case EKG_NBHD_3D8: keep = mx3 == 1; break;                                                      // callbackCube :367
+		default: return fail(EKG_E_INVALID, "unknown neighbourhood (only know of these: 2D4, 3D4, 2D8, 3D8 (cube))");
+		}
+		if (keep) {
+			out->dz[n] = (int8_t)(a0 - 1); out->dy[n] = (int8_t)(a1 - 1); out->dx[n] = (int8_t)(a2 - 1);
+			out->bit[n] = (int8_t)cube;
+			++n;
+		}
+		if (in_cube) ++cube;
+	}
+	out->n = n;
+	return EKG_OK;
+}
+
+template <class T>
+int ensure(T** p, int64_t* cap, int64_t need) {
+	if (need <= *cap) return EKG_OK;
+	if (*p) cudaFree(*p);
+	*p = nullptr; *cap = 0;
+	cudaError_t e = cudaMalloc((void**)p, (size_t)need * sizeof(T));
+	if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
+	*cap = need;
+	return EKG_OK;
+}
+template int ensure<float>(float**, int64_t*, int64_t);
+template int ensure<double>(double**, int64_t*, int64_t);
+template int ensure<Segment>(Segment**, int64_t*, int64_t);
+
+static int build_segments(ekg_model* m, int64_t seg_len, cudaStream_t st) {
+	if (m->seg_len == seg_len && m->n_segs > 0) return EKG_OK;
+	std::vector<Segment> segs;
+	for (int l = 1; l <= m->n_layers; ++l) {
+		const int64_t b0 = m->layer_off[l - 1], b1 = m->layer_off[l];
+		const int64_t cnt = b1 - b0;
+		if (cnt <= 0) continue;
+		const int64_t pieces = (cnt + seg_len - 1) / seg_len;
+		for (int64_t p = 0; p < pieces; ++p) {
+			Segment s;
+			s.begin = (int32_t)(b0 + cnt * p / pieces);
+			s.end = (int32_t)(b0 + cnt * (p + 1) / pieces);
+			s.layer = l;
+			s.pad = 0;
+			if (s.end > s.begin) segs.push_back(s);
+		}
+	}
+	int rc = ensure(&m->d_segs, &m->segs_cap, (int64_t)segs.size());
+	if (rc) return rc;
+	// the pageable source is consumed before cudaMemcpyAsync returns
+	EKG_CUDA(cudaMemcpyAsync(m->d_segs, segs.data(), segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, st));
+	EKG_CUDA(cudaStreamSynchronize(st));
+	m->n_segs = (int64_t)segs.size();
+	m->seg_len = seg_len;
+	return EKG_OK;
+}
+
+template <int MODE, int NL>
+static int launch_ecg(const EcgArgs& a, dim3 grid, int threads, cudaStream_t st) {
+	ecg_kernel<MODE, NL><<<grid, threads, 0, st>>>(a);
+	EKG_CUDA(cudaGetLastError());
+	return EKG_OK;
+}
+
+int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
+            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st) {
+	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence: call ekg_model_activation or ekg_model_set_activation first");
+	if (B <= 0 || L <= 0) return fail(EKG_E_INVALID, "B and n_leads must be positive");
+	if (B > 65535) return fail(EKG_E_UNSUPPORTED, "at most 65535 parameter vectors per call");
+	if (!(t_step > 0) || !(total_time > 0)) return fail(EKG_E_INVALID, "t_step and total_time must be positive");
+	const int64_t T = (int64_t)ceil(total_time / t_step);  // simulator.cpp:471
+	if (T <= 0 || T > (1 << 24)) return fail(EKG_E_INVALID, "bad number of time steps");
+	int mode = flags & 0xff;
+	if (mode == EKG_MODE_DEFAULT) mode = EKG_MODE_HOISTED;
+	if (mode != EKG_MODE_DIRECT && mode != EKG_MODE_HOISTED) return fail(EKG_E_INVALID, "unknown ECG mode");
+
+	EcgArgs a{};
+	int rc = make_nbr_table(nbhd, &a.nbr);
+	if (rc) return rc;
+	m->last_launches = 0;
+
+	// time samples by repeated addition (simulator.cpp:496-500), split hi/lo for the fp32 kernel
+	if ((rc = ensure(&m->d_times, &m->times_cap, 2 * T + 2 * T))) return rc;  // [hi | lo | f64 times]
+	double* d_t64 = reinterpret_cast<double*>(m->d_times + 2 * T);
+	if (m->times_T != T || m->times_t_start != t_start || m->times_t_step != t_step) {
+		std::vector<float> h_t(2 * T);
+		std::vector<double> h_t64(T);
+		double st_ = t_start;
+		for (int64_t i = 0; i < T; ++i) {
+			h_t64[i] = st_;
+			h_t[i] = (float)st_;
+			h_t[T + i] = (float)(st_ - (double)h_t[i]);
+			st_ += t_step;
+		}
+		EKG_CUDA(cudaMemcpyAsync(m->d_times, h_t.data(), 2 * T * sizeof(float), cudaMemcpyHostToDevice, st));
+		EKG_CUDA(cudaMemcpyAsync(d_t64, h_t64.data(), T * sizeof(double), cudaMemcpyHostToDevice, st));
+		EKG_CUDA(cudaStreamSynchronize(st));  // pageable sources go out of scope here
+		m->times_T = T; m->times_t_start = t_start; m->times_t_step = t_step;
+	}
+
+	// work decomposition
+	const int tiles = (int)((T + kEcgThreadsMax - 1) / kEcgThreadsMax);
+	const int threads = (int)((((T + tiles - 1) / tiles) + 31) / 32 * 32);
+	const int64_t target_ctas = (int64_t)m->sm_count * 2 * 8;
+	int64_t want_segs = (target_ctas + B * tiles - 1) / (B * tiles);
+	int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
+	seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
+	seg_len = (seg_len + kChunk - 1) / kChunk * kChunk;
+	if ((rc = build_segments(m, seg_len, st))) return rc;
+
+	const int64_t n_out = B * L * T;
+	if ((rc = ensure(&m->d_partial, &m->partial_cap, m->n_segs * n_out))) return rc;
+	if ((rc = ensure(&m->d_params, &m->params_cap, B * m->n_layers * kParamStride))) return rc;
+
+	const int64_t n_bl = B * m->n_layers;
+	ecg_params_kernel<<<(int)((n_bl + 127) / 128), 128, 0, st>>>(d_layer_k, m->d_params, n_bl, (float)m->t0);
+	EKG_CUDA(cudaGetLastError());
+	++m->last_launches;
+	if (mode == EKG_MODE_HOISTED) {
+		if ((rc = ensure(&m->d_ftab, &m->ftab_cap, n_bl * 2 * T))) return rc;
+		ecg_ftab_kernel<<<(int)((n_bl * T + 255) / 256), 256, 0, st>>>(d_layer_k, d_t64, m->d_ftab, n_bl, (int)T, (double)(float)m->t0);
+		EKG_CUDA(cudaGetLastError());
+		++m->last_launches;
+	}
+
+	a.pos = m->d_pos; a.mask = m->d_mask; a.at = m->d_at; a.segs = m->d_segs;
+	a.params = m->d_params; a.ftab = m->d_ftab; a.leads = d_leads;
+	a.t_hi = m->d_times; a.t_lo = m->d_times + T;
+	a.partial = m->d_partial;
+	a.n_segs = (int32_t)m->n_segs; a.B = (int32_t)B; a.L = (int32_t)L; a.T = (int32_t)T; a.n_layers = m->n_layers;
+
+	const dim3 grid((unsigned)m->n_segs, (unsigned)B, (unsigned)tiles);
+	for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
+		a.lead0 = lead0;
+		const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
+		if (mode == EKG_MODE_DIRECT) {
+			if (nl <= 2) rc = launch_ecg<MODE_DIRECT, 2>(a, grid, threads, st);
+			else rc = launch_ecg<MODE_DIRECT, 4>(a, grid, threads, st);
+			m->last_kernel = "ecg_kernel<DIRECT>";
+		} else {
+			if (nl <= 2) rc = launch_ecg<MODE_HOISTED, 2>(a, grid, threads, st);
+			else rc = launch_ecg<MODE_HOISTED, 4>(a, grid, threads, st);
+			m->last_kernel = "ecg_kernel<HOISTED>";
+		}
+		if (rc) return rc;
+		++m->last_launches;
+	}
+	ecg_reduce_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(m->d_partial, d_ecg, (int)m->n_segs, n_out);
+	EKG_CUDA(cudaGetLastError());
+	++m->last_launches;
+	return EKG_OK;
+}
+
+}  // namespace ekg

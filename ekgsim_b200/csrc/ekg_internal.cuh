@@ -1,0 +1,142 @@
+// ekgsim_b200/csrc/ekg_internal.cuh -- internal declarations shared by the CUDA translation
+// units of libekgsim_b200.so.  Nothing here is part of the ABI (see include/ekgsim_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ekgsim_b200.h"
+
+namespace ekg {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define EKG_CUDA(call)                                                             \
+	do {                                                                           \
+		cudaError_t e__ = (call);                                                  \
+		if (e__ != cudaSuccess) return ekg::cuda_fail(e__, #call, __FILE__, __LINE__); \
+	} while (0)
+
+// ---- static layout constants --------------------------------------------------------------------
+constexpr int kMaxNbr = 26;          // full cube (simulator.h:367-373)
+constexpr int kParamStride = 12;     // floats per (individual, layer) in the DIRECT parameter table
+constexpr int kEcgThreadsMax = 512;  // time samples per CTA tile
+constexpr int kChunk = 256;          // voxels staged in shared memory per phase
+constexpr int kMaxLeadsPerPass = 4;
+
+// Neighbour table handed to kernels by value.
+struct NbrTable {
+	int n;
+	int8_t dz[kMaxNbr], dy[kMaxNbr], dx[kMaxNbr];
+	int8_t bit[kMaxNbr];  // position of this neighbour in the 26-bit cube occupancy mask
+};
+
+// One unit of ECG work: a run of voxels of ONE layer in the layer-sorted voxel list.
+struct Segment {
+	int32_t begin, end;  // [begin, end) into the ECG voxel list
+	int32_t layer;       // 1-based layer number
+	int32_t pad;
+};
+
+struct EcgArgs {
+	const uint32_t* pos;    // packed x | y<<11 | z<<22 (unpadded voxel coordinates)
+	const uint32_t* mask;   // 26-bit occupancy of the cube neighbourhood (bit k: voxel c - dif_k occupied)
+	const double* at;       // activation time per ECG-list voxel
+	const Segment* segs;
+	const float* params;    // [B][n_layers][kParamStride]
+	const float* ftab;      // HOISTED: [B][n_layers][2][T]  (F1, F2)
+	const double* leads;    // [B][L][3] (z,y,x)
+	const float* t_hi;      // [T] time samples, hi/lo split of the f64 value
+	const float* t_lo;
+	double* partial;        // [n_segs][B][L][T]
+	int32_t n_segs, B, L, T, n_layers;
+	int32_t lead0;          // first lead handled by this launch (L > kMaxLeadsPerPass -> several passes)
+	NbrTable nbr;
+};
+
+struct AutoArgs {
+	const uint8_t* layer;   // padded dense grid, 0 = empty
+	double* time;           // padded dense grid, +inf = not reached
+	const uint32_t* pidx;   // padded linear index of every occupied voxel, raster order
+	const double* wtab;     // [nl1][nl1][3] edge weight: fl(T[lu][lv] * sqrt(|dif|^2)), |dif|^2 in 1..3
+	int* flags;             // flags[i] != 0 <=> sweep i changed something
+	int* sweeps_out;
+	int64_t n;
+	int32_t nl1;            // n_layers + 1
+	int32_t n_nbr;
+	int32_t off[kMaxNbr];   // padded linear offset of neighbour k (p - off[k])
+	int32_t sq[kMaxNbr];    // |dif|^2 - 1
+	int32_t max_sweeps;
+};
+
+}  // namespace ekg
+
+// The opaque handle of the C ABI.
+struct ekg_model {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	int64_t Z = 0, Y = 0, X = 0;
+	int64_t pZ = 0, pY = 0, pX = 0;  // padded (zero border) dims
+	int n_layers = 0;
+	int64_t n_occ = 0;               // occupied voxels in the whole model
+	int sm_count = 148;
+
+	// host copies
+	std::vector<uint8_t> h_layer;    // raster, start flags stripped
+	std::vector<int64_t> h_starts;   // raster indices of start voxels
+	std::vector<double> h_transfer;
+	int64_t t_rows = 0, t_cols = 0;
+	std::vector<double> h_delay;     // raster activation map (0 = empty / never reached)
+	bool have_activation = false;
+	double t0 = 0.0;                 // centre of the activation-time range (HOISTED kernel)
+	float activation_ms = 0.f;       // device time of the last automaton run
+
+	// automaton state (device)
+	uint8_t* d_layer_pad = nullptr;
+	double* d_time_pad = nullptr;
+	uint32_t* d_auto_pidx = nullptr;
+	double* d_wtab = nullptr;
+	int* d_flags = nullptr;
+	int max_sweeps = 1 << 16;
+
+	// ECG voxel list (layer-sorted, restricted to the slab)
+	int64_t slab_z0 = 0, slab_z1 = 0;
+	int64_t n_ecg = 0;
+	uint32_t* d_pos = nullptr;
+	uint32_t* d_mask = nullptr;
+	uint32_t* d_ecg_pidx = nullptr;  // padded index, for gathering activation times
+	double* d_at = nullptr;
+	std::vector<int64_t> layer_off;  // n_layers + 1 offsets into the ECG list
+
+	// per-call scratch (grown on demand)
+	ekg::Segment* d_segs = nullptr;  int64_t segs_cap = 0;  int64_t n_segs = 0;  int64_t seg_len = 0;
+	float* d_params = nullptr;       int64_t params_cap = 0;
+	float* d_ftab = nullptr;         int64_t ftab_cap = 0;
+	float* d_times = nullptr;        int64_t times_cap = 0;
+	double times_t_start = 0, times_t_step = 0;  int64_t times_T = 0;  // what d_times currently holds
+	double* d_partial = nullptr;     int64_t partial_cap = 0;
+	double* d_io_k = nullptr;        int64_t io_k_cap = 0;     // staging for the host-buffer entry point
+	double* d_io_leads = nullptr;    int64_t io_leads_cap = 0;
+	double* d_io_ecg = nullptr;      int64_t io_ecg_cap = 0;
+	double* h_pin_in = nullptr;      int64_t pin_in_cap = 0;   // pinned host staging
+	double* h_pin_out = nullptr;     int64_t pin_out_cap = 0;
+
+	int64_t last_launches = 0;
+	const char* last_kernel = "none";
+};
+
+namespace ekg {
+// automaton.cu
+int run_automaton(ekg_model* m, int64_t* sweeps_out);
+// ecg.cu
+int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
+            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st);
+int make_nbr_table(int nbhd, NbrTable* out);
+template <class T>
+int ensure(T** p, int64_t* cap, int64_t need);
+}  // namespace ekg

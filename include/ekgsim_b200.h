@@ -1,0 +1,124 @@
+/* include/ekgsim_b200.h -- C ABI of the B200 EkgSim hot path (libekgsim_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The host-side
+ * C++ facade ekgsim_b200/host/sim_lib.h (class SimLib::EkgSim, same surface as the reference's
+ * simlib/sim_lib.h:93-287) is a thin wrapper over these entry points; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * What each entry point replaces in the reference (paths relative to synergy-twinning/ekgsim):
+ *
+ *   ekg_model_create          Simulation::loadShape + loadTransferMatrix   simulator.cpp:181-206
+ *                             (the .matrix text parsing stays on the host: matrix.h:133-248)
+ *   ekg_model_activation      Simulation::calculateExcitationSequence      simulator.cpp:248-286
+ *                             + exciteElement                              simulator.cpp:212-246
+ *   ekg_model_set_activation  Simulation::loadExcitationSequence           simulator.cpp:288-367
+ *   ekg_model_get_activation  EkgSim::getModelShape()[..].excitationDelay  sim_lib.h:276-282
+ *   ekg_model_ap_classes      Simulation::setApIndices (class table)       simulator.cpp:561-621
+ *   ekg_simulate              Simulation::run for B parameter sets at once simulator.cpp:452-550
+ *                             (AP evaluation Wohlfart.h:195-203 via simulator.cpp:154-170)
+ *   ekg_simulate_device       same, device-resident inputs/outputs on a caller stream
+ *
+ * Conventions
+ *   - voxel arrays are raster z,y,x (x fastest): index (z*Y+y)*X+x          (matrix.h:166-173)
+ *   - layers[]: uint16, 0 = empty, 1..n = layer, bit 0x1000 marks an excitation start voxel
+ *     (ShapeElement::layerStartingPoint, matrix.h:90,128)
+ *   - transfer[t_rows][t_cols] row-major, [exciting layer][excited layer], ms per voxel edge
+ *   - lead positions are (z,y,x) triples, voxel units                       (simulator.cpp:376-381)
+ *   - layer_k[b][layer][9]: WohlfartPlus coefficients per layer, activation time 0
+ *   - ecg[b][lead][step], step i is at time t_start + i*t_step (accumulated), n_steps =
+ *     ceil(total_time / t_step)                                             (simulator.cpp:471)
+ *   - every function returns EKG_OK (0) or a negative EKG_E_* code; ekg_last_error() returns
+ *     the message for the calling thread.  The C++ facade turns codes into std::runtime_error,
+ *     the reference's own error convention (main.cpp:405-413).
+ *   - a handle is bound to one CUDA device; calls on one handle must not overlap (the reference
+ *     is single-threaded per process, sim.cpp:444).  Different handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     EKG_E_CUDA.
+ */
+#ifndef EKGSIM_B200_H
+#define EKGSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EKG_ABI_VERSION 1
+
+enum {
+	EKG_OK = 0,
+	EKG_E_INVALID = -1,    /* bad argument */
+	EKG_E_NO_START = -2,   /* "Could not find starting point for excitation sequence" (simulator.cpp:276) */
+	EKG_E_TRANSFER = -3,   /* transfer matrix too small / does not define a layer (simulator.cpp:204, :236) */
+	EKG_E_STATE = -4,      /* call order: e.g. simulate before an activation map exists */
+	EKG_E_CUDA = -5,       /* CUDA runtime error or no device */
+	EKG_E_NOMEM = -6,
+	EKG_E_UNSUPPORTED = -7 /* grid too large for the packed layout, too many leads, ... */
+};
+
+/* neighbourhood ids for the ECG stencil (sim_lib.h:133-141; note 3D4 = the 8 cube corners) */
+enum { EKG_NBHD_2D4 = 0, EKG_NBHD_2D8 = 1, EKG_NBHD_3D4 = 2, EKG_NBHD_3D8 = 3 };
+
+/* ECG kernel selection (flags argument of ekg_simulate*) */
+enum {
+	EKG_MODE_DEFAULT = 0,  /* library picks (currently EKG_MODE_HOISTED when valid, else DIRECT) */
+	EKG_MODE_DIRECT = 1,   /* full 9-coefficient AP evaluated per voxel and time sample */
+	EKG_MODE_HOISTED = 2   /* voxel-invariant and time-invariant factors of the AP hoisted */
+};
+
+typedef struct ekg_model ekg_model;
+
+int         ekg_abi_version(void);
+const char* ekg_last_error(void);
+int         ekg_device_count(void);               /* 0 when no usable CUDA device */
+
+int  ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
+                      const double* transfer, int64_t t_rows, int64_t t_cols,
+                      int device, ekg_model** out);
+void ekg_model_destroy(ekg_model* m);
+
+/* Restrict the ECG sum to voxels with z in [z_begin, z_end): the z-slab shard of one large
+ * model (BASELINE config 4).  Partial ECGs of all slabs add up to the full ECG.  The automaton
+ * always runs on the whole model.  Default range is [0, Z). */
+int  ekg_model_set_slab(ekg_model* m, int64_t z_begin, int64_t z_end);
+
+int64_t ekg_model_num_voxels(const ekg_model* m);   /* occupied voxels (inside the slab) */
+int64_t ekg_model_num_layers(const ekg_model* m);   /* = Simulation::getTargetNumOfAps(), simulator.h:570 */
+
+/* Runs the activation-time automaton on the device; the map stays resident.  delay_out (host,
+ * Z*Y*X doubles, 0.0 for empty / unreached voxels) may be NULL.  sweeps_out (may be NULL)
+ * receives the number of relaxation rounds. */
+int  ekg_model_activation(ekg_model* m, double* delay_out, int64_t* sweeps_out);
+/* Device time (ms, CUDA events) of the last ekg_model_activation call on this handle. */
+double ekg_model_activation_ms(const ekg_model* m);
+int  ekg_model_set_activation(ekg_model* m, const double* delay);
+int  ekg_model_get_activation(const ekg_model* m, double* delay_out);
+
+/* (layer, delay) class table in first-seen raster order: ap_index_out[Z*Y*X] (-1 = empty);
+ * returns K through n_classes_out.  Host-side bookkeeping only (EkgSim::getAps ordering). */
+int  ekg_model_ap_classes(const ekg_model* m, int64_t* ap_index_out, int64_t* n_classes_out);
+
+/* B simulations against the resident model.  Host buffers; blocking. */
+int  ekg_simulate(ekg_model* m, const double* layer_k, const double* leads_zyx,
+                  int64_t B, int64_t n_leads, int nbhd,
+                  double t_start, double t_step, double total_time,
+                  int flags, double* ecg_out);
+
+/* Same with device pointers (on the model's device) and a caller stream (cudaStream_t, may be
+ * NULL = the model's own stream).  Asynchronous with respect to the host. */
+int  ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_leads_zyx,
+                         int64_t B, int64_t n_leads, int nbhd,
+                         double t_start, double t_step, double total_time,
+                         int flags, double* d_ecg_out, void* stream);
+
+/* Number of kernel launches the last ekg_simulate* call on this handle issued. */
+int64_t ekg_last_launch_count(const ekg_model* m);
+/* Name of the ECG kernel variant the last ekg_simulate* call used (static string). */
+const char* ekg_last_kernel_name(const ekg_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKGSIM_B200_H */

@@ -1,0 +1,141 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden
+vectors produced by the compiled reference.  Tolerances are BASELINE.json's: activation times
+bit-exact, ECG traces within 1e-5 of the peak lead amplitude."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ECG_TOL = 1e-5  # relative to peak lead amplitude (north_star)
+
+
+def rel_err(ecg, ref):
+    peak = np.abs(ref).max(axis=-1, keepdims=True)
+    return float((np.abs(ecg - ref) / peak).max())
+
+
+@pytest.fixture(scope="module")
+def gpu_model24(built, model24):
+    m = built.Model(model24["layers"], model24["transfer"], device=0)
+    yield m
+    m.close()
+
+
+def test_activation_model24_bit_exact(gpu_model24, model24_delay):
+    delay, sweeps = gpu_model24.activation()
+    fp = json.load(open(os.path.join(GOLDEN, "golden_activation.json")))
+    assert hashlib.sha256(delay.tobytes()).hexdigest() == fp["sha256_f64_raster"]
+    assert delay.tobytes() == model24_delay.tobytes()
+    assert sweeps > 1
+    K, idx = gpu_model24.ap_classes()
+    assert K == fp["classes"]
+    Ko, idxo = oracle.ap_classes(model24_delay != 0, model24_delay, 24)  # layers>0 mask is enough for -1s
+    print("automaton: %d sweeps, %.3f ms on device" % (sweeps, gpu_model24.activation_ms))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_activation_small_bit_exact(built, seed):
+    layers, transfer, _ = synth.small_heart(seed=seed, shape=(17 + seed, 21, 19 + 2 * seed), n_layers=4 + seed)
+    m = built.Model(layers, transfer)
+    delay, _ = m.activation()
+    assert delay.tobytes() == oracle.activation(layers, transfer).tobytes()
+    m.close()
+
+
+def test_activation_2d_and_unreachable(built):
+    layers, transfer, _ = synth.small_heart(seed=4, shape=(1, 40, 36), n_layers=5, hole=False)
+    layers[0, :, 18] = 0  # cut the ring in two places -> still connected around; then isolate an island
+    layers[0, 2:4, 2:4] = 3
+    m = built.Model(layers, transfer)
+    delay, _ = m.activation()
+    ref = oracle.activation(layers, transfer)
+    assert delay.tobytes() == ref.tobytes()
+    assert (ref[0, 2:4, 2:4] == 0).all()  # island never reached -> delay stays 0 (simulator.cpp:219)
+    m.close()
+
+
+def test_activation_errors(built):
+    layers, transfer, _ = synth.small_heart(seed=0)
+    nostart = layers & 0x0FFF
+    m = built.Model(nostart, transfer)
+    with pytest.raises(built.EkgError) as e:
+        m.activation()
+    assert "starting point" in str(e.value)
+    m.close()
+    with pytest.raises(built.EkgError) as e:
+        built.Model(layers, transfer[:3, :3])
+    assert "transfer matrix too small" in str(e.value)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("nbhd", ["3D4", "3D8"])
+def test_ecg_small_vs_oracle(built, mode, nbhd):
+    layers, transfer, leads = synth.small_heart(seed=7)
+    nl = int((layers & 0xFFF).max())
+    k = synth.layer_params(nl, seed=11, batch=3)
+    delay = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    m.set_activation(delay)
+    for (t0, dt, tot) in [(0.0, 1.0, 128.0), (100.0, 1.0, 400.0), (3.0, 0.5, 50.0)]:
+        ecg = m.simulate(k, leads, nbhd, t0, dt, tot, mode=mode)
+        for b in range(3):
+            ref = oracle.run_direct(layers, delay, k[b], leads, nbhd, t0, dt, tot)
+            assert rel_err(ecg[b], ref) < ECG_TOL, (mode, nbhd, t0, b, rel_err(ecg[b], ref))
+    m.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_ecg_model24_golden_full(gpu_model24, model24_delay, mode):
+    """Full-length model_24 simulations against ECGs dumped from the compiled reference."""
+    g = np.load(os.path.join(GOLDEN, "golden_eval_full.npz"))
+    gpu_model24.set_activation(model24_delay)
+    ecg = gpu_model24.simulate(g["layer_k"], g["leads_zyx"], "3D4", 100.0, 1.0, 400.0, mode=mode)
+    for i in range(ecg.shape[0]):
+        e = rel_err(ecg[i], g["ecg"][i])
+        print("golden %s mode %d: max err %.3g of peak" % (g["name"][i], mode, e))
+        assert e < ECG_TOL
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_ecg_model24_len16_batch(gpu_model24, model24_delay, mode):
+    g = np.load(os.path.join(GOLDEN, "golden_len16.npz"))
+    gpu_model24.set_activation(model24_delay)
+    ecg = gpu_model24.simulate(g["layer_k"], g["leads_zyx"], "3D4", 100.0, 1.0, 16.0, mode=mode)
+    errs = [rel_err(ecg[i], g["ecg"][i]) for i in range(ecg.shape[0])]
+    print("len16 batch of %d, mode %d: worst %.3g of peak" % (len(errs), mode, max(errs)))
+    assert max(errs) < ECG_TOL
+
+
+def test_ecg_slabs_sum_to_whole(built):
+    layers, transfer, leads = synth.small_heart(seed=9)
+    nl = int((layers & 0xFFF).max())
+    k = synth.layer_params(nl, seed=2)
+    delay = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    m.set_activation(delay)
+    whole = m.simulate(k, leads, "3D4", 0.0, 1.0, 64.0, mode=1)
+    Z = layers.shape[0]
+    parts = np.zeros_like(whole)
+    nvox = 0
+    for z0, z1 in [(0, Z // 3), (Z // 3, Z // 2), (Z // 2, Z)]:
+        m.set_slab(z0, z1)
+        nvox += m.num_voxels
+        parts += m.simulate(k, leads, "3D4", 0.0, 1.0, 64.0, mode=1)
+    assert nvox == int(((layers & 0xFFF) > 0).sum())
+    assert rel_err(parts, whole) < 1e-9
+    m.close()
+
+
+def test_determinism(gpu_model24, model24_delay):
+    g = np.load(os.path.join(GOLDEN, "golden_len16.npz"))
+    gpu_model24.set_activation(model24_delay)
+    a = gpu_model24.simulate(g["layer_k"][:4], g["leads_zyx"][:4], "3D4", 100.0, 1.0, 16.0, mode=1)
+    b = gpu_model24.simulate(g["layer_k"][:4], g["leads_zyx"][:4], "3D4", 100.0, 1.0, 16.0, mode=1)
+    assert a.tobytes() == b.tobytes()
