@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libekgsim_b200.so")
 
 NBHD = {"2D4": 0, "2D8": 1, "3D4": 2, "3D8": 3, "cube": 3}
 MODE_DEFAULT, MODE_DIRECT, MODE_HOISTED = 0, 1, 2
+FLAG_TIME_KERNEL = 0x100
 START_FLAG = 0x1000
 
 # every symbol include/ekgsim_b200.h declares: name -> (restype, argtypes)
@@ -38,6 +39,7 @@ SYMBOLS = {
     "ekg_model_ap_classes": (_int, [_p, _p, C.POINTER(_i64)]),
     "ekg_simulate": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p]),
     "ekg_simulate_device": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _p]),
+    "ekg_last_kernel_ms": (_d, [_p]),
     "ekg_last_launch_count": (_i64, [_p]),
     "ekg_last_kernel_name": (C.c_char_p, [_p]),
 }
@@ -171,6 +173,10 @@ class Model:
         _check(lib().ekg_simulate_device(self._h, C.c_void_p(d_layer_k), C.c_void_p(d_leads), int(B), int(L),
                                          NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd), float(t_start), float(t_step),
                                          float(total_time), int(mode), C.c_void_p(d_ecg), C.c_void_p(stream)))
+
+    @property
+    def last_kernel_ms(self):
+        return float(lib().ekg_last_kernel_ms(self._h))
 
     @property
     def last_launch_count(self):

@@ -43,6 +43,8 @@ static void free_model(ekg_model* m) {
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
+	if (m->ev_k0) cudaEventDestroy(m->ev_k0);
+	if (m->ev_k1) cudaEventDestroy(m->ev_k1);
 	if (m->stream) cudaStreamDestroy(m->stream);
 	delete m;
 }
@@ -348,6 +350,13 @@ int ekg_simulate(ekg_model* m, const double* layer_k, const double* leads_zyx, i
 	EKG_CUDA(cudaStreamSynchronize(m->stream));
 	memcpy(ecg_out, m->h_pin_out, (size_t)necg * 8);
 	return EKG_OK;
+}
+
+double ekg_last_kernel_ms(ekg_model* m) {
+	if (!m || !m->ev_recorded) return -1.0;
+	float ms = -1.f;
+	if (cudaEventSynchronize(m->ev_k1) != cudaSuccess || cudaEventElapsedTime(&ms, m->ev_k0, m->ev_k1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+	return (double)ms;
 }
 
 int64_t ekg_last_launch_count(const ekg_model* m) { return m ? m->last_launches : 0; }

@@ -391,6 +391,12 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 	a.n_segs = (int32_t)m->n_segs; a.B = (int32_t)B; a.L = (int32_t)L; a.T = (int32_t)T; a.n_layers = m->n_layers;
 
 	const dim3 grid((unsigned)m->n_segs, (unsigned)B, (unsigned)tiles);
+	const bool timed = (flags & EKG_FLAG_TIME_KERNEL) != 0;
+	m->ev_recorded = false;
+	if (timed) {
+		if (!m->ev_k0) { EKG_CUDA(cudaEventCreate(&m->ev_k0)); EKG_CUDA(cudaEventCreate(&m->ev_k1)); }
+		EKG_CUDA(cudaEventRecord(m->ev_k0, st));
+	}
 	for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
 		a.lead0 = lead0;
 		const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
@@ -406,6 +412,7 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 		if (rc) return rc;
 		++m->last_launches;
 	}
+	if (timed) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
 	ecg_reduce_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(m->d_partial, d_ecg, (int)m->n_segs, n_out);
 	EKG_CUDA(cudaGetLastError());
 	++m->last_launches;

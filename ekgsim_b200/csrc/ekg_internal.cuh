@@ -126,6 +126,7 @@ struct ekg_model {
 	double* h_pin_in = nullptr;      int64_t pin_in_cap = 0;   // pinned host staging
 	double* h_pin_out = nullptr;     int64_t pin_out_cap = 0;
 
+	cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  bool ev_recorded = false;
 	int64_t last_launches = 0;
 	const char* last_kernel = "none";
 };

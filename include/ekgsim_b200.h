@@ -68,6 +68,10 @@ enum {
 	EKG_MODE_HOISTED = 2   /* voxel-invariant and time-invariant factors of the AP hoisted */
 };
 
+/* OR-ed into flags: record CUDA events around the ECG kernel launch(es) on the launching stream
+ * so that ekg_last_kernel_ms() can report the dominant kernel's device time (bench.py roofline). */
+#define EKG_FLAG_TIME_KERNEL 0x100
+
 typedef struct ekg_model ekg_model;
 
 int         ekg_abi_version(void);
@@ -115,6 +119,9 @@ int  ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_
 
 /* Number of kernel launches the last ekg_simulate* call on this handle issued. */
 int64_t ekg_last_launch_count(const ekg_model* m);
+/* Device time (ms) of the ECG kernel launch(es) of the last call made with EKG_FLAG_TIME_KERNEL;
+ * synchronises on the recorded events.  Negative if nothing was recorded. */
+double ekg_last_kernel_ms(ekg_model* m);
 /* Name of the ECG kernel variant the last ekg_simulate* call used (static string). */
 const char* ekg_last_kernel_name(const ekg_model* m);
 

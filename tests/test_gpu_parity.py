@@ -108,7 +108,9 @@ def test_ecg_model24_len16_batch(gpu_model24, model24_delay, mode):
     g = np.load(os.path.join(GOLDEN, "golden_len16.npz"))
     gpu_model24.set_activation(model24_delay)
     ecg = gpu_model24.simulate(g["layer_k"], g["leads_zyx"], "3D4", 100.0, 1.0, 16.0, mode=mode)
-    errs = [rel_err(ecg[i], g["ecg"][i]) for i in range(ecg.shape[0])]
+    # tolerance is relative to the peak amplitude of the lead (north_star), i.e. of the full
+    # 400-sample trace, not of this 16-sample window (peak_full: make_fixtures / oracle)
+    errs = [float((np.abs(ecg[i] - g["ecg"][i]) / g["peak_full"][i][:, None]).max()) for i in range(ecg.shape[0])]
     print("len16 batch of %d, mode %d: worst %.3g of peak" % (len(errs), mode, max(errs)))
     assert max(errs) < ECG_TOL
 
