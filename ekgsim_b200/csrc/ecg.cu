@@ -58,28 +58,41 @@ struct RowLayout {
 };
 
 // ---- the fused kernel ---------------------------------------------------------------------------
+// Work decomposition: grid.x = segment (a run of voxels of ONE layer), grid.y = pair tile.  The
+// (parameter vector b, time sample t) pairs of the whole batch are flattened, p = b*T + t, and cut
+// into tiles of kEcgThreads = 256 consecutive pairs (8 warps = 2 per SM sub-partition, every lane
+// busy; a 400-sample trace is 12.5 warps, which left one sub-partition with 33 % more MUFU work
+// in the first version of this kernel).  A tile therefore spans up to kMaxVecPerTile parameter
+// vectors; phase A computes the lead-field coefficients for each of them.
 template <int MODE, int NL>
-__global__ void __launch_bounds__(kEcgThreadsMax, 2) ecg_kernel(const EcgArgs a) {
+__global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	constexpr int ROW = RowLayout<MODE, NL>::kFloats;
-	__shared__ __align__(16) float s_vox[kChunk * ROW];
-	__shared__ double s_lead[NL * 3];
+	__shared__ __align__(16) float s_vox[kSmemRows * ROW];
+	__shared__ double s_lead[kMaxVecPerTile * NL * 3];
 
 	const Segment sg = a.segs[blockIdx.x];
-	const int b = blockIdx.y;
-	const int t = blockIdx.z * blockDim.x + threadIdx.x;
-	const bool live = t < a.T;
+	const PairTile tile = a.tiles[blockIdx.y];
+	const int b0 = tile.begin / a.T;
+	const int nb = (tile.end - 1) / a.T - b0 + 1;   // parameter vectors touched by this tile (<= kMaxVecPerTile)
+	const int p = tile.begin + threadIdx.x;
+	const bool live = p < tile.end;
+	const int b = live ? p / a.T : b0;
+	const int t = live ? p - b * a.T : 0;
+	const int bl = b - b0;
+	const int chunk = min(kChunk, kSmemRows / nb);
 
-	if (threadIdx.x < NL * 3) {
-		const int l = a.lead0 + threadIdx.x / 3;
-		s_lead[threadIdx.x] = l < a.L ? a.leads[((int64_t)b * a.L + l) * 3 + threadIdx.x % 3] : 0.0;
+	if (threadIdx.x < nb * NL * 3) {
+		const int v = threadIdx.x / (NL * 3), r = threadIdx.x % (NL * 3);
+		const int l = a.lead0 + r / 3;
+		s_lead[threadIdx.x] = l < a.L ? a.leads[((int64_t)(b0 + v) * a.L + l) * 3 + r % 3] : 0.0;
 	}
 
 	// per-thread constants of (vector b, layer, sample t)
 	const float* P = a.params + ((int64_t)b * a.n_layers + (sg.layer - 1)) * kParamStride;
-	const float a1 = __ldg(P + 0), a4 = __ldg(P + 1), a5 = __ldg(P + 2), k0 = __ldg(P + 8);
-	float a7 = 0.f, c2 = 0.f, np = 0.f, A = 0.f, Bc = 0.f, k8hi = 0.f, k8lo = 0.f, F1 = 0.f, F2 = 0.f;
-	const float t0 = __ldg(P + 11);  // HOISTED: centre of the activation-time range
+	const float a1 = __ldg(P + 0), k0 = __ldg(P + 8);
+	float a4 = 0.f, a5 = 0.f, a7 = 0.f, c2 = 0.f, np = 0.f, A = 0.f, Bc = 0.f, k8hi = 0.f, k8lo = 0.f, F1 = 0.f, F2 = 0.f;
 	if (MODE == MODE_DIRECT) {
+		a4 = __ldg(P + 1); a5 = __ldg(P + 2);
 		a7 = __ldg(P + 3); c2 = __ldg(P + 4); np = __ldg(P + 5); A = __ldg(P + 6); Bc = __ldg(P + 7);
 		k8hi = __ldg(P + 9); k8lo = __ldg(P + 10);
 	} else if (live) {
@@ -94,21 +107,23 @@ __global__ void __launch_bounds__(kEcgThreadsMax, 2) ecg_kernel(const EcgArgs a)
 #pragma unroll
 	for (int l = 0; l < NL; ++l) acc64[l] = 0.0;
 
-	for (int base = sg.begin; base < sg.end; base += kChunk) {
-		const int n = min(kChunk, sg.end - base);
+	for (int base = sg.begin; base < sg.end; base += chunk) {
+		const int n = min(chunk, sg.end - base);
 		__syncthreads();  // phase B of the previous chunk is done with s_vox; s_lead is visible
 
-		// ---- phase A: per-voxel, time-invariant data -> shared memory ----
-		for (int j = threadIdx.x; j < n; j += blockDim.x) {
+		// ---- phase A: per-(voxel, vector) time-invariant data -> shared memory ----
+		for (int idx = threadIdx.x; idx < n * nb; idx += kEcgThreads) {
+			const int j = idx / nb, v = idx - j * nb;
 			const uint32_t pos = __ldg(a.pos + base + j);
 			const uint32_t mask = __ldg(a.mask + base + j);
 			const float at = (float)__ldg(a.at + base + j);
 			// voxel position = its index in the zero-bordered matrix (simulator.cpp:487, :531)
 			const double pz = (double)((pos >> 22) + 1u), py = (double)(((pos >> 11) & 0x7ffu) + 1u), px = (double)((pos & 0x7ffu) + 1u);
+			const double* lead = s_lead + v * NL * 3;
 			float G[NL];
 #pragma unroll
 			for (int l = 0; l < NL; ++l) {
-				const float rz = (float)(s_lead[3 * l] - pz), ry = (float)(s_lead[3 * l + 1] - py), rx = (float)(s_lead[3 * l + 2] - px);
+				const float rz = (float)(lead[3 * l] - pz), ry = (float)(lead[3 * l + 1] - py), rx = (float)(lead[3 * l + 2] - px);
 				float g = 0.f;
 				int sz = 0, sy = 0, sx = 0;
 				for (int k = 0; k < a.nbr.n; ++k) {
@@ -125,7 +140,7 @@ __global__ void __launch_bounds__(kEcgThreadsMax, 2) ecg_kernel(const EcgArgs a)
 				g = fmaf((float)sz * rz + (float)sy * ry + (float)sx * rx, inv_cube(sqc), g);
 				G[l] = (a.lead0 + l < a.L) ? -g : 0.f;
 			}
-			float* row = s_vox + j * ROW;
+			float* row = s_vox + idx * ROW;
 			if (MODE == MODE_DIRECT) {
 				row[0] = at;
 #pragma unroll
@@ -133,18 +148,22 @@ __global__ void __launch_bounds__(kEcgThreadsMax, 2) ecg_kernel(const EcgArgs a)
 			} else {
 				// time-invariant AP factors exp((k4+k5)(at-t0)), exp(k5 (at-t0)); clamped so that
 				// the products with the (also clamped) table entries can never be inf*0
+				const float* Pv = a.params + ((int64_t)(b0 + v) * a.n_layers + (sg.layer - 1)) * kParamStride;
+				const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
 				const float da = at - t0;
 				row[0] = at;
-				row[1] = mufu_ex2(fminf(-(a4 + a5) * da, 60.f));
-				row[2] = mufu_ex2(fminf(-a5 * da, 60.f));
+				row[1] = mufu_ex2(fminf(-(v4 + v5) * da, 60.f));
+				row[2] = mufu_ex2(fminf(-v5 * da, 60.f));
 #pragma unroll
 				for (int l = 0; l < NL; ++l) row[3 + l] = G[l];
 			}
 		}
 		__syncthreads();
 
-		// ---- phase B: time loop, one sample per thread, voxels broadcast from shared memory ----
+		// ---- phase B: time loop, one (vector, sample) pair per thread, voxel rows from shared memory ----
 		if (live) {
+			const float* my_rows = s_vox + bl * ROW;
+			const int stride = nb * ROW;
 			for (int j0 = 0; j0 < n; j0 += 32) {
 				const int j1 = min(j0 + 32, n);
 				float acc[NL];
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(kEcgThreadsMax, 2) ecg_kernel(const EcgArgs a)
 				for (int l = 0; l < NL; ++l) acc[l] = 0.f;
 #pragma unroll 4
 				for (int j = j0; j < j1; ++j) {
-					const float4* rp = reinterpret_cast<const float4*>(s_vox + j * ROW);
+					const float4* rp = reinterpret_cast<const float4*>(my_rows + j * stride);
 					const float4 r0 = rp[0];
 					float V;
 					float G[NL];
@@ -288,6 +307,7 @@ int ensure(T** p, int64_t* cap, int64_t need) {
 template int ensure<float>(float**, int64_t*, int64_t);
 template int ensure<double>(double**, int64_t*, int64_t);
 template int ensure<Segment>(Segment**, int64_t*, int64_t);
+template int ensure<PairTile>(PairTile**, int64_t*, int64_t);
 
 static int build_segments(ekg_model* m, int64_t seg_len, cudaStream_t st) {
 	if (m->seg_len == seg_len && m->n_segs > 0) return EKG_OK;
@@ -359,15 +379,30 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 		m->times_T = T; m->times_t_start = t_start; m->times_t_step = t_step;
 	}
 
-	// work decomposition
-	const int tiles = (int)((T + kEcgThreadsMax - 1) / kEcgThreadsMax);
-	const int threads = (int)((((T + tiles - 1) / tiles) + 31) / 32 * 32);
-	const int64_t target_ctas = (int64_t)m->sm_count * 2 * 8;
-	int64_t want_segs = (target_ctas + B * tiles - 1) / (B * tiles);
+	// work decomposition: pair tiles (<= kEcgThreads pairs, <= kMaxVecPerTile vectors each) x segments
+	if (m->tiles_B != B || m->tiles_T != T) {
+		std::vector<PairTile> tiles;
+		const int64_t P = B * T;
+		for (int64_t p = 0; p < P;) {
+			int64_t e = std::min<int64_t>(p + kEcgThreads, P);
+			const int64_t b0 = p / T;
+			if ((e - 1) / T - b0 + 1 > kMaxVecPerTile) e = (b0 + kMaxVecPerTile) * T;
+			tiles.push_back(PairTile{(int32_t)p, (int32_t)e});
+			p = e;
+		}
+		if ((rc = ensure(&m->d_tiles, &m->tiles_cap, (int64_t)tiles.size()))) return rc;
+		EKG_CUDA(cudaMemcpyAsync(m->d_tiles, tiles.data(), tiles.size() * sizeof(PairTile), cudaMemcpyHostToDevice, st));
+		EKG_CUDA(cudaStreamSynchronize(st));
+		m->n_tiles = (int64_t)tiles.size(); m->tiles_B = B; m->tiles_T = T;
+	}
+	if (B * T >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "B * n_steps must be below 2^31");
+	const int64_t target_ctas = (int64_t)m->sm_count * 4 * 8;
+	int64_t want_segs = (target_ctas + m->n_tiles - 1) / m->n_tiles;
 	int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
 	seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
 	seg_len = (seg_len + kChunk - 1) / kChunk * kChunk;
 	if ((rc = build_segments(m, seg_len, st))) return rc;
+	if (m->n_tiles > 65535) return fail(EKG_E_UNSUPPORTED, "too many (vector, sample) pairs for one launch (B * n_steps <= 16.7 M)");
 
 	const int64_t n_out = B * L * T;
 	if ((rc = ensure(&m->d_partial, &m->partial_cap, m->n_segs * n_out))) return rc;
@@ -384,13 +419,14 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 		++m->last_launches;
 	}
 
-	a.pos = m->d_pos; a.mask = m->d_mask; a.at = m->d_at; a.segs = m->d_segs;
+	a.pos = m->d_pos; a.mask = m->d_mask; a.at = m->d_at; a.segs = m->d_segs; a.tiles = m->d_tiles;
 	a.params = m->d_params; a.ftab = m->d_ftab; a.leads = d_leads;
 	a.t_hi = m->d_times; a.t_lo = m->d_times + T;
 	a.partial = m->d_partial;
 	a.n_segs = (int32_t)m->n_segs; a.B = (int32_t)B; a.L = (int32_t)L; a.T = (int32_t)T; a.n_layers = m->n_layers;
 
-	const dim3 grid((unsigned)m->n_segs, (unsigned)B, (unsigned)tiles);
+	const dim3 grid((unsigned)m->n_segs, (unsigned)m->n_tiles, 1);
+	const int threads = kEcgThreads;
 	const bool timed = (flags & EKG_FLAG_TIME_KERNEL) != 0;
 	m->ev_recorded = false;
 	if (timed) {

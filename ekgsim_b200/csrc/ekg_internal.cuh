@@ -25,8 +25,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // ---- static layout constants --------------------------------------------------------------------
 constexpr int kMaxNbr = 26;          // full cube (simulator.h:367-373)
 constexpr int kParamStride = 12;     // floats per (individual, layer) in the DIRECT parameter table
-constexpr int kEcgThreadsMax = 512;  // time samples per CTA tile
-constexpr int kChunk = 256;          // voxels staged in shared memory per phase
+constexpr int kEcgThreads = 256;     // (vector, sample) pairs per CTA: 8 warps, 2 per SM sub-partition
+constexpr int kMaxVecPerTile = 4;    // parameter vectors one pair tile may span
+constexpr int kChunk = 256;          // voxels staged in shared memory per phase (fewer when a tile spans > 2 vectors)
+constexpr int kSmemRows = 512;       // (voxel, vector) rows staged per phase
 constexpr int kMaxLeadsPerPass = 4;
 
 // Neighbour table handed to kernels by value.
@@ -43,11 +45,17 @@ struct Segment {
 	int32_t pad;
 };
 
+// A run of consecutive (vector b, sample t) pairs, p = b*T + t.
+struct PairTile {
+	int32_t begin, end;
+};
+
 struct EcgArgs {
 	const uint32_t* pos;    // packed x | y<<11 | z<<22 (unpadded voxel coordinates)
 	const uint32_t* mask;   // 26-bit occupancy of the cube neighbourhood (bit k: voxel c - dif_k occupied)
 	const double* at;       // activation time per ECG-list voxel
 	const Segment* segs;
+	const PairTile* tiles;
 	const float* params;    // [B][n_layers][kParamStride]
 	const float* ftab;      // HOISTED: [B][n_layers][2][T]  (F1, F2)
 	const double* leads;    // [B][L][3] (z,y,x)
@@ -115,6 +123,7 @@ struct ekg_model {
 
 	// per-call scratch (grown on demand)
 	ekg::Segment* d_segs = nullptr;  int64_t segs_cap = 0;  int64_t n_segs = 0;  int64_t seg_len = 0;
+	ekg::PairTile* d_tiles = nullptr; int64_t tiles_cap = 0; int64_t n_tiles = 0; int64_t tiles_B = 0, tiles_T = 0;
 	float* d_params = nullptr;       int64_t params_cap = 0;
 	float* d_ftab = nullptr;         int64_t ftab_cap = 0;
 	float* d_times = nullptr;        int64_t times_cap = 0;

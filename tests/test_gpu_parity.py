@@ -24,8 +24,13 @@ def rel_err(ecg, ref):
 @pytest.fixture(scope="module")
 def gpu_model24(built, model24):
     m = built.Model(model24["layers"], model24["transfer"], device=0)
+    m._layers = model24["layers"]
     yield m
     m.close()
+
+
+def gpu_model24_layers(m):
+    return m._layers
 
 
 def test_activation_model24_bit_exact(gpu_model24, model24_delay):
@@ -36,7 +41,8 @@ def test_activation_model24_bit_exact(gpu_model24, model24_delay):
     assert sweeps > 1
     K, idx = gpu_model24.ap_classes()
     assert K == fp["classes"]
-    Ko, idxo = oracle.ap_classes(model24_delay != 0, model24_delay, 24)  # layers>0 mask is enough for -1s
+    Ko, idxo = oracle.ap_classes(gpu_model24_layers(gpu_model24), model24_delay, 24)
+    assert Ko == K and (idxo == idx).all()  # same first-seen raster numbering as setApIndices
     print("automaton: %d sweeps, %.3f ms on device" % (sweeps, gpu_model24.activation_ms))
 
 
@@ -131,7 +137,8 @@ def test_ecg_slabs_sum_to_whole(built):
         nvox += m.num_voxels
         parts += m.simulate(k, leads, "3D4", 0.0, 1.0, 64.0, mode=1)
     assert nvox == int(((layers & 0xFFF) > 0).sum())
-    assert rel_err(parts, whole) < 1e-9
+    # same sum, different fp32 grouping of the per-segment partials -> equal to fp32 rounding
+    assert rel_err(parts, whole) < 2e-6
     m.close()
 
 
