@@ -26,11 +26,14 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 constexpr uint16_t kStartFlag = 0x1000;  // ShapeElement::layerStartingPoint (matrix.h:90)
 
-__global__ void gather_at_kernel(const double* __restrict__ time_pad, const uint32_t* __restrict__ pidx, double* __restrict__ at, int64_t n) {
+__global__ void gather_at_kernel(const double* __restrict__ time_pad, const uint32_t* __restrict__ pidx, double* __restrict__ at,
+                                 float* __restrict__ at32, int64_t n) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const double v = time_pad[pidx[i]];
-	at[i] = isinf(v) ? 0.0 : v;  // never reached -> excitationDelay stays 0 (simulator.cpp:219)
+	double v = time_pad[pidx[i]];
+	if (isinf(v)) v = 0.0;  // never reached -> excitationDelay stays 0 (simulator.cpp:219)
+	at[i] = v;
+	at32[i] = (float)v;
 }
 
 static int64_t pad_index(const ekg_model* m, int64_t z, int64_t y, int64_t x) { return ((z + 1) * m->pY + (y + 1)) * m->pX + (x + 1); }
@@ -38,7 +41,7 @@ static int64_t pad_index(const ekg_model* m, int64_t z, int64_t y, int64_t x) { 
 static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
-	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at,
+	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
 	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
@@ -82,13 +85,14 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 		pidx[j] = (uint32_t)p;
 	}
 
-	for (void* p : {(void*)m->d_pos, (void*)m->d_mask, (void*)m->d_ecg_pidx, (void*)m->d_at}) if (p) cudaFree(p);
-	m->d_pos = m->d_mask = m->d_ecg_pidx = nullptr; m->d_at = nullptr;
+	for (void* p : {(void*)m->d_pos, (void*)m->d_mask, (void*)m->d_ecg_pidx, (void*)m->d_at, (void*)m->d_at32}) if (p) cudaFree(p);
+	m->d_pos = m->d_mask = m->d_ecg_pidx = nullptr; m->d_at = nullptr; m->d_at32 = nullptr;
 	const size_t nn = (size_t)std::max<int64_t>(n, 1);
 	EKG_CUDA(cudaMalloc(&m->d_pos, nn * 4));
 	EKG_CUDA(cudaMalloc(&m->d_mask, nn * 4));
 	EKG_CUDA(cudaMalloc(&m->d_ecg_pidx, nn * 4));
 	EKG_CUDA(cudaMalloc(&m->d_at, nn * 8));
+	EKG_CUDA(cudaMalloc(&m->d_at32, nn * 4));
 	EKG_CUDA(cudaMemcpy(m->d_pos, pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
 	EKG_CUDA(cudaMemcpy(m->d_mask, mask.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
 	EKG_CUDA(cudaMemcpy(m->d_ecg_pidx, pidx.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
@@ -100,7 +104,7 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 
 static int gather_at(ekg_model* m) {
 	if (m->n_ecg == 0) return EKG_OK;
-	gather_at_kernel<<<(int)((m->n_ecg + 255) / 256), 256, 0, m->stream>>>(m->d_time_pad, m->d_ecg_pidx, m->d_at, m->n_ecg);
+	gather_at_kernel<<<(int)((m->n_ecg + 255) / 256), 256, 0, m->stream>>>(m->d_time_pad, m->d_ecg_pidx, m->d_at, m->d_at32, m->n_ecg);
 	EKG_CUDA(cudaGetLastError());
 	EKG_CUDA(cudaStreamSynchronize(m->stream));
 	return EKG_OK;

@@ -68,7 +68,7 @@ template <int MODE, int NL>
 __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	constexpr int ROW = RowLayout<MODE, NL>::kFloats;
 	__shared__ __align__(16) float s_vox[kSmemRows * ROW];
-	__shared__ double s_lead[kMaxVecPerTile * NL * 3];
+	__shared__ float2 s_lead[kMaxVecPerTile * NL * 3];  // lead coordinate as fp32 hi + lo
 
 	const Segment sg = a.segs[blockIdx.x];
 	const PairTile tile = a.tiles[blockIdx.y];
@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	if (threadIdx.x < nb * NL * 3) {
 		const int v = threadIdx.x / (NL * 3), r = threadIdx.x % (NL * 3);
 		const int l = a.lead0 + r / 3;
-		s_lead[threadIdx.x] = l < a.L ? a.leads[((int64_t)(b0 + v) * a.L + l) * 3 + r % 3] : 0.0;
+		const double c = l < a.L ? a.leads[((int64_t)(b0 + v) * a.L + l) * 3 + r % 3] : 0.0;
+		const float hi = (float)c;
+		s_lead[threadIdx.x] = make_float2(hi, (float)(c - (double)hi));
 	}
 
 	// per-thread constants of (vector b, layer, sample t)
@@ -103,9 +105,11 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	const float thi = live ? __ldg(a.t_hi + t) : 0.f;
 	const float tlo = live ? __ldg(a.t_lo + t) : 0.f;
 
-	double acc64[NL];
+	// per-lead running sums: fp32 for 32 voxels at a time, folded into an fp32 (sum, compensation)
+	// pair with an error-free TwoSum -- f64-grade accumulation without conversions on the XU pipe
+	float sum[NL], comp[NL];
 #pragma unroll
-	for (int l = 0; l < NL; ++l) acc64[l] = 0.0;
+	for (int l = 0; l < NL; ++l) { sum[l] = 0.f; comp[l] = 0.f; }
 
 	for (int base = sg.begin; base < sg.end; base += chunk) {
 		const int n = min(chunk, sg.end - base);
@@ -116,28 +120,33 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 			const int j = idx / nb, v = idx - j * nb;
 			const uint32_t pos = __ldg(a.pos + base + j);
 			const uint32_t mask = __ldg(a.mask + base + j);
-			const float at = (float)__ldg(a.at + base + j);
-			// voxel position = its index in the zero-bordered matrix (simulator.cpp:487, :531)
-			const double pz = (double)((pos >> 22) + 1u), py = (double)(((pos >> 11) & 0x7ffu) + 1u), px = (double)((pos & 0x7ffu) + 1u);
-			const double* lead = s_lead + v * NL * 3;
+			const float at = __ldg(a.at32 + base + j);
+			// voxel position = its index in the zero-bordered matrix (simulator.cpp:487, :531);
+			// integer -> float through the 2^23 mantissa trick (keeps I2F off the MUFU/XU pipe)
+			const float pz = __uint_as_float(0x4B000000u | ((pos >> 22) + 1u)) - 8388608.f;
+			const float py = __uint_as_float(0x4B000000u | (((pos >> 11) & 0x7ffu) + 1u)) - 8388608.f;
+			const float px = __uint_as_float(0x4B000000u | ((pos & 0x7ffu) + 1u)) - 8388608.f;
+			const float2* lead = s_lead + v * NL * 3;
 			float G[NL];
 #pragma unroll
 			for (int l = 0; l < NL; ++l) {
-				const float rz = (float)(lead[3 * l] - pz), ry = (float)(lead[3 * l + 1] - py), rx = (float)(lead[3 * l + 2] - px);
+				const float rz = (lead[3 * l].x - pz) + lead[3 * l].y;      // mp - p_c, exact difference + low part
+				const float ry = (lead[3 * l + 1].x - py) + lead[3 * l + 1].y;
+				const float rx = (lead[3 * l + 2].x - px) + lead[3 * l + 2].y;
 				float g = 0.f;
-				int sz = 0, sy = 0, sx = 0;
+				float sz = 0.f, sy = 0.f, sx = 0.f;
 				for (int k = 0; k < a.nbr.n; ++k) {
 					if ((mask >> a.nbr.bit[k]) & 1u) {
-						const int dz = a.nbr.dz[k], dy = a.nbr.dy[k], dx = a.nbr.dx[k];
-						const float qz = rz + (float)dz, qy = ry + (float)dy, qx = rx + (float)dx;  // mp - p_{c-dif}
+						const float dz = a.nbr.fz[k], dy = a.nbr.fy[k], dx = a.nbr.fx[k];
+						const float qz = rz + dz, qy = ry + dy, qx = rx + dx;  // mp - p_{c-dif}
 						const float sq = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
-						const float dot = (float)dz * qz + (float)dy * qy + (float)dx * qx;
+						const float dot = fmaf(dz, qz, fmaf(dy, qy, dx * qx));
 						g = fmaf(dot, inv_cube(sq), g);
 						sz += dz; sy += dy; sx += dx;
 					}
 				}
 				const float sqc = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
-				g = fmaf((float)sz * rz + (float)sy * ry + (float)sx * rx, inv_cube(sqc), g);
+				g = fmaf(fmaf(sz, rz, fmaf(sy, ry, sx * rx)), inv_cube(sqc), g);
 				G[l] = (a.lead0 + l < a.L) ? -g : 0.f;
 			}
 			float* row = s_vox + idx * ROW;
@@ -201,7 +210,12 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 					for (int l = 0; l < NL; ++l) acc[l] = fmaf(G[l], V, acc[l]);
 				}
 #pragma unroll
-				for (int l = 0; l < NL; ++l) acc64[l] += (double)acc[l];
+				for (int l = 0; l < NL; ++l) {
+					const float s1 = sum[l] + acc[l];
+					const float bp = s1 - sum[l];
+					comp[l] += (sum[l] - (s1 - bp)) + (acc[l] - bp);
+					sum[l] = s1;
+				}
 			}
 		}
 	}
@@ -210,7 +224,7 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 #pragma unroll
 		for (int l = 0; l < NL; ++l) {
 			const int lead = a.lead0 + l;
-			if (lead < a.L) a.partial[(((int64_t)blockIdx.x * a.B + b) * a.L + lead) * a.T + t] = acc64[l];
+			if (lead < a.L) a.partial[(((int64_t)blockIdx.x * a.B + b) * a.L + lead) * a.T + t] = (double)sum[l] + (double)comp[l];
 		}
 	}
 }
@@ -285,6 +299,7 @@ int make_nbr_table(int nbhd, NbrTable* out) {
 		}
 		if (keep) {
 			out->dz[n] = (int8_t)(a0 - 1); out->dy[n] = (int8_t)(a1 - 1); out->dx[n] = (int8_t)(a2 - 1);
+			out->fz[n] = (float)(a0 - 1); out->fy[n] = (float)(a1 - 1); out->fx[n] = (float)(a2 - 1);
 			out->bit[n] = (int8_t)cube;
 			++n;
 		}
@@ -419,7 +434,7 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 		++m->last_launches;
 	}
 
-	a.pos = m->d_pos; a.mask = m->d_mask; a.at = m->d_at; a.segs = m->d_segs; a.tiles = m->d_tiles;
+	a.pos = m->d_pos; a.mask = m->d_mask; a.at32 = m->d_at32; a.segs = m->d_segs; a.tiles = m->d_tiles;
 	a.params = m->d_params; a.ftab = m->d_ftab; a.leads = d_leads;
 	a.t_hi = m->d_times; a.t_lo = m->d_times + T;
 	a.partial = m->d_partial;

@@ -36,6 +36,7 @@ struct NbrTable {
 	int n;
 	int8_t dz[kMaxNbr], dy[kMaxNbr], dx[kMaxNbr];
 	int8_t bit[kMaxNbr];  // position of this neighbour in the 26-bit cube occupancy mask
+	float fz[kMaxNbr], fy[kMaxNbr], fx[kMaxNbr];  // the same offsets as floats (no I2F in the kernel)
 };
 
 // One unit of ECG work: a run of voxels of ONE layer in the layer-sorted voxel list.
@@ -53,7 +54,7 @@ struct PairTile {
 struct EcgArgs {
 	const uint32_t* pos;    // packed x | y<<11 | z<<22 (unpadded voxel coordinates)
 	const uint32_t* mask;   // 26-bit occupancy of the cube neighbourhood (bit k: voxel c - dif_k occupied)
-	const double* at;       // activation time per ECG-list voxel
+	const float* at32;      // activation time per ECG-list voxel (fp32 copy of the f64 map)
 	const Segment* segs;
 	const PairTile* tiles;
 	const float* params;    // [B][n_layers][kParamStride]
@@ -119,6 +120,7 @@ struct ekg_model {
 	uint32_t* d_mask = nullptr;
 	uint32_t* d_ecg_pidx = nullptr;  // padded index, for gathering activation times
 	double* d_at = nullptr;
+	float* d_at32 = nullptr;
 	std::vector<int64_t> layer_off;  // n_layers + 1 offsets into the ECG list
 
 	// per-call scratch (grown on demand)
