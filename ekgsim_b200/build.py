@@ -10,7 +10,9 @@ SOURCES = ["csrc/capi.cu", "csrc/automaton.cu", "csrc/ecg.cu"]
 HEADERS = ["csrc/ekg_internal.cuh", "../include/ekgsim_b200.h"]
 OUT = os.path.join(HERE, "libekgsim_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+              # the image's g++ links libstdc++ statically: keep that private copy's symbols local
+              "-Xlinker", "--exclude-libs=ALL"]
 
 
 def needs_build():

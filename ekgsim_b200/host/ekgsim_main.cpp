@@ -1,0 +1,187 @@
+// ekgsim_b200/host/ekgsim_main.cpp -- the `ekgSim` command line of the B200 build.
+//
+// Same contract as the reference's main.cpp (synergy-twinning/ekgsim main.cpp:114-277, :367-414):
+//
+//     ekgSim test -sim p1,p2,...,p16 -out result        single simulation in the current directory
+//                                                       (reads simulator.ini and the files it names)
+//
+// with the same console transcript (" parameters for single simulator run: <...>", the u/v lines,
+// the model / neighbourhood / simulation banner, "\reval N  ", " simulation done in X seconds",
+// " criteria = <...>, violation = V", "All done") and the same `result.column`.  Errors are caught
+// and printed to stdout as "runtime error caught: ..."; the process still exits 0 (main.cpp:405-413).
+//
+// Additions of this build (not in the reference):
+//     ekgSim -batch vectors.txt [-batchout criteria.txt]     evaluate many parameter vectors (one per
+//         line, comma/space separated) in one GPU batch; prints one " criteria = <..>, violation = V"
+//         line per vector.  This is what a population-based optimizer should call per generation.
+//     ekgSim -extern <homeDir>     AMS-DEMO ExternalEvaluation protocol (ExternalEvaluation.h:95-151):
+//         reads <homeDir>/input.txt (one gene per line, '#' comments), writes <homeDir>/output.txt
+//         (criteria, then "# violation v").
+// The optimizer itself (`ekgSim` without arguments, AMS-DEMO over MPI) is outside the hot path and is
+// not part of this build; use the reference's optimizer with `-extern` or `-batch` as its evaluator.
+
+#include <cctype>
+#include <map>
+
+#include "ekg_eval.h"
+
+namespace {
+
+struct DashArgs {
+	std::multimap<std::string, std::string> dash;
+	std::vector<std::string> free_args;
+
+	DashArgs(int argc, char** argv) {
+		// "-name value" pairs; "-<digit>..." is a value, not a flag (copyOfLibs/Arguments.cpp:122-137)
+		std::multimap<std::string, std::string>::iterator last = dash.end();
+		for (int i = 1; i < argc; ++i) {
+			const std::string a = argv[i];
+			if (a.size() > 1 && a[0] == '-' && !isdigit((unsigned char)a[1])) last = dash.insert(std::make_pair(a, std::string()));
+			else if (!dash.empty() && last->second.empty()) last->second = a;
+			else free_args.push_back(a);
+		}
+	}
+	bool is_set(const std::string& n) const { return dash.find(n) != dash.end(); }
+	std::string get(const std::string& n) const {
+		std::multimap<std::string, std::string>::const_iterator it = dash.find(n);
+		return it == dash.end() ? std::string() : it->second;
+	}
+	std::vector<std::string> all(const std::string& n) const {
+		std::vector<std::string> v;
+		auto r = dash.equal_range(n);
+		for (auto it = r.first; it != r.second; ++it) v.push_back(it->second);
+		return v;
+	}
+};
+
+std::vector<double> parse_vector(const std::string& s) {
+	std::istringstream in(s);
+	std::vector<double> v;
+	for (double t; in >> t;) {
+		v.push_back(t);
+		const int c = in.peek();
+		if (c == ',' || c == ';') in.ignore(1);
+	}
+	return v;
+}
+
+void parse_outputs(const DashArgs& args, ekg::OutputSettings& out) {
+	for (const std::string& val : args.all("-out")) {
+		std::istringstream st(val);
+		std::string name;
+		st >> name;
+		if (name == "cell_aps") {
+			while (st) {
+				st.ignore(1);
+				size_t n;
+				st >> n;
+				if (st) out.outputCellAps.push_back(n);
+			}
+		} else if (name == "layer_aps") out.layerAps = true;
+		else if (name == "result") out.result = true;
+		else std::cerr << "skipping an unrecognized output opition: " << name << "\n";
+	}
+	if (args.is_set("-out")) std::cout << "\n";
+}
+
+void run_single(const std::vector<double>& params, const ekg::OutputSettings& out) {
+	std::cerr << "##### Running a single simulation experiment ####################\n";
+	ekg::Evaluator ev("simulator.ini");
+	ev.outSettings = out;
+	std::vector<double> result;
+	const double t0 = ekg::wall_seconds();
+	const double violation = ev.eval(params, result);
+	const double secs = ekg::wall_seconds() - t0;
+	std::cout << " simulation done in " << secs << " seconds\n";
+	std::cout << " criteria = " << ekg::angle_list(result) << ", violation = " << violation << "\n";
+}
+
+void run_batch(const std::string& file, const std::string& outfile, int threads) {
+	std::cerr << "##### Running a batch of simulations ############################\n";
+	std::ifstream in(file.c_str());
+	if (!in.is_open()) throw std::runtime_error("could not open " + file);
+	std::vector<std::vector<double>> sols;
+	for (std::string line; std::getline(in, line);) {
+		for (char& c : line) if (c == ',' || c == ';') c = ' ';
+		std::vector<double> v = parse_vector(line);
+		if (!v.empty()) sols.push_back(v);
+	}
+	ekg::Evaluator ev("simulator.ini");
+	std::vector<std::vector<double>> results;
+	std::vector<double> violations;
+	const double t0 = ekg::wall_seconds();
+	ev.evalBatch(sols, results, violations, threads);
+	const double secs = ekg::wall_seconds() - t0;
+	std::ofstream of;
+	if (!outfile.empty()) of.open(outfile.c_str());
+	for (size_t i = 0; i < sols.size(); ++i) {
+		std::cout << " criteria = " << ekg::angle_list(results[i]) << ", violation = " << violations[i] << "\n";
+		if (of.is_open()) {
+			of.precision(17);
+			for (double c : results[i]) of << c << " ";
+			of << violations[i] << "\n";
+		}
+	}
+	std::cout << " batch of " << sols.size() << " simulations done in " << secs << " seconds (GPU part " << ev.simulator().lastRunSeconds() << " s)\n";
+}
+
+void run_extern(const std::string& home) {
+	const std::string dir = home.empty() ? std::string() : home + "/";
+	std::ifstream in((dir + "input.txt").c_str());
+	if (!in.is_open()) throw std::runtime_error("could not open " + dir + "input.txt");
+	std::vector<double> genes;
+	for (std::string line; std::getline(in, line);) {
+		if (line.empty() || line[0] == '#') continue;
+		std::istringstream ls(line);
+		double d;
+		while (ls >> d) genes.push_back(d);
+	}
+	ekg::Evaluator ev("simulator.ini");
+	std::vector<double> result;
+	const double violation = ev.eval(genes, result);
+	std::ofstream out((dir + "output.txt").c_str());
+	out.precision(17);
+	for (double c : result) out << c << "\n";
+	out << "# violation " << violation << "\n";
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+	try {
+		DashArgs args(argc, argv);
+		std::cerr << "***** parsing program arguments ****************************\n";
+		ekg::OutputSettings out;
+		parse_outputs(args, out);
+		if (args.is_set("-?")) {
+			std::cout << "Argument list:\n   -? \tshow this help screen\n   -sim \tjust run single a simulation with parameters provided after -sim\n"
+			             "   -out \tspecify outputs of the program; possible values include result, layer_aps, cell_aps <num> [<num>]*\n"
+			             "   -batch \tevaluate every parameter vector of a text file in one GPU batch [-batchout file] [-threads n]\n"
+			             "   -extern \tAMS-DEMO ExternalEvaluation protocol: <homeDir>/input.txt -> <homeDir>/output.txt\n";
+		} else if (args.is_set("-sim")) {
+			const std::vector<double> params = parse_vector(args.get("-sim"));
+			std::cout << " parameters for single simulator run: " << ekg::angle_list(params) << "\n";
+			if (params.empty()) throw std::runtime_error(" Error: not enough parameters to run simulation: " + args.get("-sim"));
+			std::cerr << "\n";
+			run_single(params, out);
+		} else if (args.is_set("-batch")) {
+			std::cerr << "\n";
+			run_batch(args.get("-batch"), args.get("-batchout"), atoi(args.get("-threads").c_str()));
+		} else if (args.is_set("-extern")) {
+			std::cerr << "\n";
+			run_extern(args.get("-extern"));
+		} else {
+			std::cout << "the optimizer (AMS-DEMO) is not part of the B200 build; use -sim, -batch or -extern as its evaluator\n";
+		}
+		std::cout << "All done\n";
+	} catch (const char* e) {
+		std::cout << "exception caught: " << e << "\n";
+	} catch (std::runtime_error& e) {
+		std::cout << "runtime error caught: " << e.what() << "\n";
+	} catch (std::exception& e) {
+		std::cout << "std exception caught: " << e.what() << "\n";
+	} catch (...) {
+		std::cout << "unknown exception caught, execution halted\n";
+	}
+	return 0;
+}

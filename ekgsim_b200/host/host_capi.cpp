@@ -1,0 +1,64 @@
+// ekgsim_b200/host/host_capi.cpp -- C shim over the host-side evaluation glue (ekg_eval.h) so that
+// tests and tools can drive it without a process boundary.  Not part of the device ABI.
+#include "ekg_eval.h"
+
+extern "C" {
+
+static thread_local std::string g_host_error;
+const char* ekg_host_last_error() { return g_host_error.c_str(); }
+
+/// AP formula (host f64), for cross-checking against the oracle
+double ekg_host_wohlfart_plus(const double* k, double t) {
+	SimLib::WohlfartPlus w(k);
+	return w[t];
+}
+
+double ekg_host_apd90(const double* k) {
+	SimLib::WohlfartPlus w(k);
+	return w.apd90();
+}
+
+/// Evaluator over the simulator.ini of the CURRENT directory (like the CLI).  Needs a GPU.
+void* ekg_host_evaluator_create(const char* ini, int with_device) {
+	try { return new ekg::Evaluator(ini, with_device != 0); }
+	catch (std::exception& e) { g_host_error = e.what(); return nullptr; }
+}
+void ekg_host_evaluator_destroy(void* ev) { delete static_cast<ekg::Evaluator*>(ev); }
+int ekg_host_num_criteria(void* ev) { return (int)static_cast<ekg::Evaluator*>(ev)->deducedNumOfCriteria; }
+
+int ekg_host_eval(void* ev, const double* genes, int n, double* criteria, double* violation) {
+	try {
+		std::vector<double> sol(genes, genes + n), res;
+		*violation = static_cast<ekg::Evaluator*>(ev)->eval(sol, res);
+		std::copy(res.begin(), res.end(), criteria);
+		return 0;
+	} catch (std::exception& e) { g_host_error = e.what(); return -1; }
+}
+
+int ekg_host_eval_batch(void* ev, const double* genes, int n_genes, int B, int threads, double* criteria, double* violations) {
+	try {
+		std::vector<std::vector<double>> sols(B), res;
+		for (int b = 0; b < B; ++b) sols[b].assign(genes + (size_t)b * n_genes, genes + (size_t)(b + 1) * n_genes);
+		std::vector<double> viol;
+		ekg::Evaluator* e = static_cast<ekg::Evaluator*>(ev);
+		e->evalBatch(sols, res, viol, threads);
+		for (int b = 0; b < B; ++b) {
+			std::copy(res[b].begin(), res[b].end(), criteria + (size_t)b * e->deducedNumOfCriteria);
+			violations[b] = viol[b];
+		}
+		return 0;
+	} catch (std::exception& e) { g_host_error = e.what(); return -1; }
+}
+
+/// glue only (no GPU work after construction): genes -> layer coefficients [layers*9], leads [L*3]
+int ekg_host_layer_coefficients(void* ev, const double* genes, int n, double* k_out, double* leads_out, double* violation) {
+	try {
+		std::vector<double> sol(genes, genes + n), k, leads;
+		static_cast<ekg::Evaluator*>(ev)->layerCoefficients(sol, k, leads, *violation);
+		std::copy(k.begin(), k.end(), k_out);
+		std::copy(leads.begin(), leads.end(), leads_out);
+		return 0;
+	} catch (std::exception& e) { g_host_error = e.what(); return -1; }
+}
+
+}  // extern "C"

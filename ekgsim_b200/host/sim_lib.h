@@ -1,0 +1,437 @@
+// ekgsim_b200/host/sim_lib.h -- the "simlib Simulator interface" of the B200 build.
+//
+// Source-compatible stand-in for the reference's simlib/sim_lib.h (class SimLib::EkgSim,
+// sim_lib.h:93-287) and the types its callers touch (Settings simulator.h:83-147, WohlfartPlus
+// Wohlfart.h:167-230, ActionPotential simulator.h:468-480).  Same method names, argument meaning,
+// console output and exceptions (std::runtime_error) -- but where the reference walks the voxel
+// model on the CPU, this class hands the work to libekgsim_b200.so through the C ABI
+// (include/ekgsim_b200.h):
+//
+//     loadShape + loadTransferMatrix  -> ekg_model_create       (device-resident model)
+//     simExcitationSequence           -> ekg_model_activation / ekg_model_set_activation
+//     run                             -> ekg_simulate           (fused AP + stencil + lead kernel)
+//     runBatch (new)                  -> ekg_simulate with B parameter sets in one launch
+//
+// Host-only pieces that stay on the CPU exactly like in the reference: file parsing, the lead
+// displacement plane (u,v) construction, the 2*T-sample "string model" approximation
+// (simulator.cpp:552-559) and the AP formula used by the evaluation glue's layer fitting.
+// There is no CPU fallback for the voxel loops: without a CUDA device the calls throw.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <unordered_map>
+
+#include "../../include/ekgsim_b200.h"
+#include "ekg_support.h"
+
+namespace SimLib {
+
+using ekg::Vec3;
+
+// ---- simulator settings, same ini keys as the reference (simulator.h:107-134) ------------------------
+struct Settings {
+	std::string inputShapeFilename, inputExcitationSequenceFilename, inputPointsFilename, inputTransferFilename;
+	std::string inputActionPotentials, inputActionPotentialsFilter;
+	double inputActionPotentialsFilterParam = 0;
+	double inputActionPotentialsTimeStep = 1;
+	std::string inputActionPotentialsFunction;
+	double inputActionPotentialsScale = 0;
+	std::string outputExcitationSequence, outputApFilename, outputFilename;
+	int simulationLength = 800;
+	int simulationStart = 0;
+	std::string neighbourhoodType;
+	double simulationTimeStep = 10;
+
+	void loadFromIni(const ekg::IniFile& ini) {
+		const int model = ini.section("model");
+		ini.load(inputShapeFilename, "shape", model);
+		ini.load(inputExcitationSequenceFilename, "excitation sequence", model);
+		ini.load(inputPointsFilename, "points", model);
+		ini.load(inputTransferFilename, "transfer", model);
+		const int ap = ini.section("action potentials");
+		ini.load(inputActionPotentials, "input file", ap);
+		ini.load(inputActionPotentialsFilter, "filter", ap);
+		ini.load(inputActionPotentialsTimeStep, "resample time step", ap);
+		ini.load(inputActionPotentialsFilterParam, "filter parameter", ap);
+		ini.load(inputActionPotentialsFunction, "combination function", ap);
+		ini.load(inputActionPotentialsScale, "expected length", ap);
+		const int out = ini.section("output files");
+		ini.load(outputExcitationSequence, "excitation sequence", out);
+		ini.load(outputApFilename, "action potentials filename", out);
+		outputFilename = "result.column";
+		ini.load(outputFilename, "results filename", out);
+		const int sim = ini.section("simulation");
+		ini.load(simulationLength, "length", sim);
+		ini.load(simulationStart, "start", sim);
+		ini.load(neighbourhoodType, "neighbourhood type", sim);
+		simulationTimeStep = 1.0 / 3.0;
+		ini.load(simulationTimeStep, "time step", sim);
+	}
+};
+
+// ---- extended Wohlfart AP, 9 coefficients (Wohlfart.h:167-230) ----------------------------------------
+class WohlfartPlus {
+public:
+	static const size_t numParams = 9;
+
+protected:
+	double k[numParams];
+
+public:
+	WohlfartPlus() {}
+	explicit WohlfartPlus(const double newK[numParams]) { setK(newK); }
+	void setK(const double newK[numParams]) { std::copy(newK, newK + numParams, k); }
+	void setK(const std::vector<double>& newK) { std::copy(newK.begin(), newK.end(), k); }
+	const double* getK() const { return k; }
+	double* getK() { return k; }
+
+	/// value of the AP at time t
+	double operator[](double t) const {
+		return (1.0 / (1.0 + std::exp(-k[1] * t)))
+		     * (k[2] * ((1.0 - k[3]) * std::exp(-k[4] * t) + k[3]))
+		     * (std::exp(-k[5] * t) * (1 - std::pow((1 + std::exp(-k[7] * (t - k[8])
+		            + std::log(std::pow(2, (k[7] / k[6])) - 1))), -(k[6] / k[7]))))
+		     + k[0];
+	}
+
+	/// time at which the AP has repolarised to k0 + 0.1 k2 (last downward crossing on a 1 ms grid
+	/// over [0,1000), linearly interpolated); -1 if it never does
+	double apd90() const {
+		const size_t n = 1000;
+		std::vector<double> d(n);
+		for (size_t i = 0; i < n; ++i) d[i] = (*this)[(double)i];
+		const double target = k[0] + k[2] * 0.1;
+		double time = -1.0;
+		for (size_t i = 1; i < n; ++i)
+			if (d[i - 1] > target && d[i] <= target) {
+				const double wa = d[i - 1] - target, wb = target - d[i];
+				time = (double(i - 1) * wa + double(i) * wb) / (wa + wb);
+			}
+		return time;
+	}
+};
+
+// ---- AP + activation time (simulator.h:468-480, simulator.cpp:154-170) -----------------------------------
+struct ActionPotential {
+	WohlfartPlus wohl;
+	double at;
+
+	void init(const double* wohlK, double newAt) { wohl.setK(wohlK); wohl.getK()[8] -= newAt; at = newAt; }
+	void init(const ActionPotential& ap, double newAt) { wohl.setK(ap.getK()); wohl.getK()[8] -= newAt; at = newAt; }
+	double operator()(double time) const { return wohl[time - at]; }
+	double& operator[](size_t i) { return wohl.getK()[i]; }
+	double operator[](size_t i) const { return wohl.getK()[i]; }
+	const double* getK() const { return wohl.getK(); }
+	size_t size() const { return wohl.numParams; }
+};
+
+typedef ekg::NamedColumn saveVecElement;
+
+template <class Vec>
+void exportVectors(const Vec& vec, const std::string& filename, double startTime, double timeStep = -1.0, const std::string& comment = "") {
+	ekg::export_columns(vec, filename, startTime, timeStep, comment);
+}
+
+/// read-only view of the voxel model for callers of getModelShape()
+struct ShapeElement { size_t layer; double excitationDelay; size_t apIndex; };
+
+class EkgSim {
+public:
+	typedef Vec3 PositionVec;
+
+private:
+	Settings settings;
+	// model on the host (as parsed) and on the device
+	std::vector<uint16_t> layers_;
+	int64_t Z_ = 0, Y_ = 0, X_ = 0;
+	std::vector<double> transfer_;
+	int64_t tRows_ = 0, tCols_ = 0;
+	ekg_model* model_ = nullptr;
+	int device_ = 0;
+	size_t targetNumOfAps_ = 12;   // Simulation::targetNumOfAps default (simulator.h:556)
+	int nbhd_ = -1;
+	double timeStep_ = 0;
+	bool haveActivation_ = false;
+
+	std::vector<ActionPotential> aps_;            // layer APs before run(), per-class APs after (getAps)
+	std::vector<PositionVec> originalMeasuringPositions, measuringPositions, vectorU, vectorV;
+	std::vector<PositionVec> mps_;                // what Simulation::mps holds
+	std::vector<std::vector<double>> measurement_;
+	double startTime_ = 0;
+	int mode_ = EKG_MODE_DEFAULT;
+	double lastRunSeconds_ = 0;
+
+	static void check(int rc) { if (rc != EKG_OK) throw std::runtime_error(ekg_last_error()); }
+
+	void ensureModel() {
+		if (model_) return;
+		if (layers_.empty()) throw std::runtime_error("shape not loaded");
+		if (transfer_.empty()) throw std::runtime_error("transfer matrix not loaded");
+		check(ekg_model_create(layers_.data(), Z_, Y_, X_, transfer_.data(), tRows_, tCols_, device_, &model_));
+	}
+
+	static PositionVec cross(const PositionVec& a, const PositionVec& b) {
+		return PositionVec(a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]);
+	}
+	static void normalize(PositionVec& v) {
+		double s = v[0] * v[0];
+		s += v[1] * v[1];
+		s += v[2] * v[2];
+		const double l = std::sqrt(s);
+		const double f = l != 0 ? 1.0 / l : 0.0;
+		for (int i = 0; i < 3; ++i) v[i] *= f;
+	}
+
+public:
+	EkgSim() {
+		if (const char* d = getenv("EKGSIM_B200_DEVICE")) device_ = atoi(d);
+		if (const char* m = getenv("EKGSIM_B200_MODE")) {
+			const std::string s(m);
+			mode_ = s == "direct" ? EKG_MODE_DIRECT : s == "hoisted" ? EKG_MODE_HOISTED : EKG_MODE_DEFAULT;
+		}
+	}
+	~EkgSim() { if (model_) ekg_model_destroy(model_); }
+
+	void setDevice(int device) { device_ = device; }
+	void setMode(int mode) { mode_ = mode; }
+	double lastRunSeconds() const { return lastRunSeconds_; }
+	ekg_model* handle() { ensureModel(); return model_; }
+
+	void loadSettings(const char* fname = "settings.ini") {
+		ekg::LogTimer tm(std::cerr, "loading settings                            ");
+		ekg::IniFile ini(fname);
+		if (!ini.found()) std::cout << "warning, " << fname << " not found. ";
+		else if (ini.empty()) std::cout << "warning, " << fname << " is empty. ";
+		else settings.loadFromIni(ini);
+	}
+
+	Settings& getSettings() { return settings; }
+
+	/// applies the selected timestep and neighbourhood (sim_lib.h:131-148; note that "3D4" selects the
+	/// 8 cube corners and "2D4" the 4 in-plane diagonals, simulator.h:338-364)
+	void applySettings() {
+		const std::string& t = settings.neighbourhoodType;
+		if (t == "2D4") nbhd_ = EKG_NBHD_2D4;
+		else if (t == "2D8") nbhd_ = EKG_NBHD_2D8;
+		else if (t == "3D4") nbhd_ = EKG_NBHD_3D4;
+		else if (t == "3D8" || t == "cube") nbhd_ = EKG_NBHD_3D8;
+		else throw std::runtime_error("\n   unknown neighbourhood (only know of these: 2D4, 3D4, 2D8, 3D8 (cube))");
+		timeStep_ = settings.simulationTimeStep;
+	}
+
+	/// swaps: the caller's vector receives the previous contents (sim_lib.h:151, simulator.cpp:208-210)
+	void setApsDestructive(std::vector<ActionPotential>& destructible) { aps_.swap(destructible); }
+	const std::vector<ActionPotential>& getAps() const { return aps_; }
+
+	void loadTransferMatrix() {
+		ekg::LogTimer tm(std::cerr, "loading transfer matrix                     ");
+		ekg::load_double_matrix(settings.inputTransferFilename, transfer_, tRows_, tCols_);
+		// Simulation::loadTransferMatrix checks against the default / previously loaded layer count
+		if ((size_t)tRows_ < targetNumOfAps_ || (size_t)tCols_ < targetNumOfAps_) throw std::runtime_error("loaded transfer matrix too small");
+		if (model_) { ekg_model_destroy(model_); model_ = nullptr; haveActivation_ = false; }
+	}
+
+	void loadMeasuringPoints() {
+		ekg::LogTimer tm(std::cerr, "loading measuring points                    ");
+		std::cerr << "measuring points: \n";
+		mps_ = ekg::load_points(settings.inputPointsFilename);
+		for (const PositionVec& p : mps_) std::cerr << " -> " << p[2] << ", " << p[1] << ", " << p[0] << "\n";
+		originalMeasuringPositions = mps_;
+		const size_t n = mps_.size();
+		measuringPositions = mps_;
+		vectorU.resize(n);
+		vectorV.resize(n);
+		measurement_.assign(n, std::vector<double>());
+		// plane of movement of every lead: u = -(x_axis x p), v = (x_axis x p) x p, coordinates are (z,y,x)
+		const PositionVec xAxis(0, 0, 1);
+		for (size_t i = 0; i < n; ++i) {
+			const PositionVec& p = originalMeasuringPositions[i];
+			vectorU[i] = cross(xAxis, p);
+			vectorV[i] = cross(vectorU[i], p);
+			for (int c = 0; c < 3; ++c) vectorU[i][c] *= -1;
+			normalize(vectorU[i]);
+			normalize(vectorV[i]);
+			std::cout << " u" << i << " = " << vectorU[i][2] << "," << vectorU[i][1] << "," << vectorU[i][0] << "\n";
+			std::cout << " v" << i << " = " << vectorV[i][2] << "," << vectorV[i][1] << "," << vectorV[i][0] << "\n";
+		}
+	}
+
+	void moveMeasuringPoints(const std::vector<PositionVec>& uvwDisplacement) {
+		if (uvwDisplacement.size() != measuringPositions.size()) {
+			std::cerr << uvwDisplacement.size() << " != " << measuringPositions.size() << " " << originalMeasuringPositions.size() << std::endl;
+			throw std::runtime_error("invalid vector of measuring point displacements");
+		}
+		for (size_t i = 0; i < originalMeasuringPositions.size(); ++i)
+			measuringPositions[i] = displaced(i, uvwDisplacement[i][0], uvwDisplacement[i][1]);
+		mps_ = measuringPositions;
+		measurement_.assign(mps_.size(), std::vector<double>());
+	}
+
+	/// sets the lead positions directly, (z,y,x) each (Simulation::setMeasuringPoints, simulator.cpp:400-404)
+	void moveMeasuringPointsTo(const std::vector<PositionVec>& positions) {
+		if (positions.size() != measuringPositions.size()) throw std::runtime_error("invalid vector of measuring point displacements");
+		measuringPositions = positions;
+		mps_ = positions;
+		measurement_.assign(mps_.size(), std::vector<double>());
+	}
+
+	/// original position + du * u + dv * v, evaluated left to right like the reference (sim_lib.h:201)
+	PositionVec displaced(size_t i, double du, double dv) const {
+		PositionVec r;
+		for (int c = 0; c < 3; ++c) r[c] = (originalMeasuringPositions[i][c] + du * vectorU[i][c]) + dv * vectorV[i][c];
+		return r;
+	}
+
+	void loadShape() {
+		ekg::LogTimer tm(std::cerr, "loading shape                               ");
+		if (settings.inputShapeFilename == "") throw std::runtime_error("no shape file given (the built-in test shape generator is not part of the B200 build)");
+		ekg::load_shape_matrix(settings.inputShapeFilename, layers_, Z_, Y_, X_);
+		size_t maxLayer = 0;
+		for (uint16_t l : layers_) maxLayer = std::max<size_t>(maxLayer, l & 0x0fff);
+		targetNumOfAps_ = maxLayer;
+		if (model_) { ekg_model_destroy(model_); model_ = nullptr; haveActivation_ = false; }
+	}
+
+	size_t requiredAps() const { return targetNumOfAps_; }
+
+	void simExcitationSequence() {
+		ensureModel();
+		if (settings.inputExcitationSequenceFilename == "") {
+			ekg::LogTimer tm(std::cerr, "calculating excitation sequence             ");
+			check(ekg_model_activation(model_, nullptr, nullptr));
+		} else {
+			ekg::LogTimer tm(std::cerr, "loading excitation sequence                 ");
+			std::vector<double> delay;
+			ekg::load_delay_matrix(settings.inputExcitationSequenceFilename, Z_, Y_, X_, delay);
+			check(ekg_model_set_activation(model_, delay.data()));
+		}
+		haveActivation_ = true;
+		if (settings.outputExcitationSequence != "") {
+			std::vector<double> delay((size_t)(Z_ * Y_ * X_));
+			check(ekg_model_get_activation(model_, delay.data()));
+			ekg::export_delay_matrix(settings.outputExcitationSequence, Z_, Y_, X_, delay);
+		}
+	}
+
+	void printSettings() {
+		std::cout << "model: " << settings.inputShapeFilename << " (" << Z_ << ", " << Y_ << ", " << X_ << ")\n";
+		std::cout << "neighbourhood: ";
+		const std::string& t = settings.neighbourhoodType;
+		if (t == "2D4") std::cout << "2D, 4 neighbours\n";
+		else if (t == "2D8") std::cout << "2D, 8 neighbours\n";
+		else if (t == "3D4") std::cout << "3D, 6 neighbours\n";
+		else if (t == "3D8" || t == "cube") std::cout << "3D, 26 neighbours (full cube)\n";
+		std::cout << "simulation start = " << settings.simulationStart << "\n" << "simulation time step = " << settings.simulationTimeStep << "\n"
+		          << "simulation length = " << settings.simulationLength << "\n" << "total steps = "
+		          << settings.simulationLength / settings.simulationTimeStep << "\n";
+	}
+
+	void printMessages(std::ostream&) {}
+
+	/// full simulation of the current layer APs and lead positions (Simulation::run)
+	void run() {
+		if (aps_.size() != targetNumOfAps_) throw std::runtime_error("run: need exactly one action potential per layer");
+		std::vector<double> k(aps_.size() * 9);
+		for (size_t l = 0; l < aps_.size(); ++l) {
+			std::copy(aps_[l].getK(), aps_[l].getK() + 9, k.begin() + 9 * l);
+			k[9 * l + 8] += aps_[l].at;  // layer APs carry at = 0; undo a shift if a caller set one
+		}
+		std::vector<double> leads(mps_.size() * 3);
+		for (size_t i = 0; i < mps_.size(); ++i) for (int c = 0; c < 3; ++c) leads[3 * i + c] = mps_[i][c];
+		std::vector<double> ecg;
+		runBatch(k.data(), leads.data(), 1, ecg);
+		const size_t T = ecg.size() / std::max<size_t>(mps_.size(), 1);
+		measurement_.assign(mps_.size(), std::vector<double>());
+		for (size_t i = 0; i < mps_.size(); ++i) measurement_[i].assign(ecg.begin() + i * T, ecg.begin() + (i + 1) * T);
+		buildCellAps();
+	}
+
+	/// B parameter sets in one launch: layerK [B][layers][9], leadsZyx [B][leads][3] -> ecg [B][leads][T]
+	void runBatch(const double* layerK, const double* leadsZyx, size_t B, std::vector<double>& ecg) {
+		ensureModel();
+		if (!haveActivation_) throw std::runtime_error("excitation sequence missing: call simExcitationSequence() first");
+		if (nbhd_ < 0) throw std::runtime_error("applySettings() must be called before run()");
+		startTime_ = settings.simulationStart;
+		const size_t T = (size_t)std::ceil(settings.simulationLength / timeStep_);
+		ecg.assign(B * mps_.size() * T, 0.0);
+		const double t0 = ekg::wall_seconds();
+		check(ekg_simulate(model_, layerK, leadsZyx, (int64_t)B, (int64_t)mps_.size(), nbhd_, (double)settings.simulationStart, timeStep_,
+		                   (double)settings.simulationLength, mode_, ecg.data()));
+		lastRunSeconds_ = ekg::wall_seconds() - t0;
+	}
+
+	/// "string model": endo delayed minus epi, layer APs only (Simulation::runApproximation)
+	void runApproximation(double delay, std::vector<double>& result) {
+		result.assign((size_t)(settings.simulationLength / timeStep_), 0.0);
+		for (size_t i = 0; i < result.size(); ++i) {
+			const double simTime = settings.simulationStart + i * timeStep_;
+			result[i] = aps_[0](simTime + delay) - aps_.back()(simTime);
+		}
+	}
+
+	const std::vector<double>& getMeasurement(size_t n) const { return measurement_[n]; }
+	size_t numMeasurements() const { return mps_.size(); }
+	const std::vector<PositionVec>& measuringPoints() const { return mps_; }
+
+	void saveMeasurement(const std::string& comment = "") {
+		ekg::LogTimer tm(std::cerr, "saving measurement                          ");
+		saveMeasurements(settings.outputFilename, comment);
+	}
+	void saveMeasurementAs(const char* fname, const std::string& comment = "") {
+		ekg::LogTimer tm(std::cerr, "saving measurement                          ");
+		saveMeasurements(fname, comment);
+	}
+
+	/// voxel (layer, delay, class index) by raster index, after the excitation sequence exists
+	ShapeElement shapeElementAtIndex(size_t i) {
+		ensureModel();
+		ShapeElement e{(size_t)(layers_[i] & 0x0fff), 0.0, (size_t)(layers_[i] & 0x0fff)};
+		if (haveActivation_) {
+			if (delayCache_.empty()) { delayCache_.resize(layers_.size()); check(ekg_model_get_activation(model_, delayCache_.data())); }
+			e.excitationDelay = delayCache_[i];
+		}
+		return e;
+	}
+	void modelSize(int64_t& Z, int64_t& Y, int64_t& X) const { Z = Z_; Y = Y_; X = X_; }
+
+private:
+	std::vector<double> delayCache_;
+
+	void saveMeasurements(const std::string& filename, const std::string& comment) {
+		std::vector<saveVecElement> v(mps_.size());
+		for (size_t i = 0; i < mps_.size(); ++i) {
+			std::ostringstream name;
+			name << mps_[i][2] << "," << mps_[i][1] << "," << mps_[i][0];
+			v[i].name = name.str();
+			v[i].data = &measurement_[i];
+		}
+		if (!mps_.empty()) exportVectors(v, filename, startTime_, timeStep_, comment);
+	}
+
+	/// after run() the reference's aps hold one AP per (layer, delay) class in first-seen raster
+	/// order (Simulation::setApIndices, simulator.cpp:561-621); `-out cell_aps n` indexes that table
+	void buildCellAps() {
+		std::vector<int64_t> idx(layers_.size());
+		int64_t K = 0;
+		check(ekg_model_ap_classes(model_, idx.data(), &K));
+		if (delayCache_.empty()) { delayCache_.resize(layers_.size()); check(ekg_model_get_activation(model_, delayCache_.data())); }
+		std::vector<ActionPotential> cells((size_t)K);
+		std::vector<char> seen((size_t)K, 0);
+		for (size_t i = 0; i < layers_.size(); ++i) {
+			const int64_t c = idx[i];
+			if (c < 0 || seen[(size_t)c]) continue;
+			seen[(size_t)c] = 1;
+			cells[(size_t)c].init(aps_[(layers_[i] & 0x0fff) - 1], delayCache_[i]);
+		}
+		aps_.swap(cells);
+	}
+
+	EkgSim(const EkgSim&);
+	void operator=(const EkgSim&);
+};
+
+}  // namespace SimLib
+
+typedef SimLib::EkgSim EkgSim;

@@ -1,0 +1,88 @@
+"""tests/hostlib.py -- ctypes view of libekgsim_host.so (the C shim over the host-side C++ glue)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "ekgsim_b200", "libekgsim_host.so")
+CLI = os.path.join(ROOT, "ekgsim_b200", "bin", "ekgSim")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(PATH)
+        L.ekg_host_last_error.restype = C.c_char_p
+        L.ekg_host_wohlfart_plus.restype = C.c_double
+        L.ekg_host_wohlfart_plus.argtypes = [C.c_void_p, C.c_double]
+        L.ekg_host_apd90.restype = C.c_double
+        L.ekg_host_apd90.argtypes = [C.c_void_p]
+        L.ekg_host_evaluator_create.restype = C.c_void_p
+        L.ekg_host_evaluator_create.argtypes = [C.c_char_p, C.c_int]
+        L.ekg_host_evaluator_destroy.argtypes = [C.c_void_p]
+        L.ekg_host_num_criteria.argtypes = [C.c_void_p]
+        L.ekg_host_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ekg_host_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ekg_host_layer_coefficients.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class Evaluator:
+    """Runs in `workdir` (must hold simulator.ini + inputs, like the reference CLI)."""
+
+    def __init__(self, workdir, with_device=True, n_layers=24, n_leads=2):
+        self.workdir, self.n_layers, self.n_leads = workdir, n_layers, n_leads
+        cwd = os.getcwd()
+        os.chdir(workdir)
+        try:
+            self.h = lib().ekg_host_evaluator_create(b"simulator.ini", 1 if with_device else 0)
+        finally:
+            os.chdir(cwd)
+        if not self.h:
+            raise RuntimeError(lib().ekg_host_last_error().decode())
+        self.n_crit = lib().ekg_host_num_criteria(self.h)
+
+    def close(self):
+        if self.h:
+            lib().ekg_host_evaluator_destroy(self.h)
+            self.h = None
+
+    def _in(self, fn):
+        cwd = os.getcwd()
+        os.chdir(self.workdir)
+        try:
+            return fn()
+        finally:
+            os.chdir(cwd)
+
+    def layer_coefficients(self, genes):
+        g = np.ascontiguousarray(genes, dtype=np.float64)
+        k = np.zeros((self.n_layers, 9))
+        leads = np.zeros((self.n_leads, 3))
+        viol = C.c_double(0)
+        rc = lib().ekg_host_layer_coefficients(self.h, g.ctypes.data, len(g), k.ctypes.data, leads.ctypes.data, C.byref(viol))
+        if rc:
+            raise RuntimeError(lib().ekg_host_last_error().decode())
+        return k, leads, viol.value
+
+    def eval(self, genes):
+        g = np.ascontiguousarray(genes, dtype=np.float64)
+        crit = np.zeros(self.n_crit)
+        viol = C.c_double(0)
+        rc = self._in(lambda: lib().ekg_host_eval(self.h, g.ctypes.data, len(g), crit.ctypes.data, C.byref(viol)))
+        if rc:
+            raise RuntimeError(lib().ekg_host_last_error().decode())
+        return crit, viol.value
+
+    def eval_batch(self, genes, threads=0):
+        g = np.ascontiguousarray(genes, dtype=np.float64)
+        B, n = g.shape
+        crit = np.zeros((B, self.n_crit))
+        viol = np.zeros(B)
+        rc = self._in(lambda: lib().ekg_host_eval_batch(self.h, g.ctypes.data, n, B, threads, crit.ctypes.data, viol.ctypes.data))
+        if rc:
+            raise RuntimeError(lib().ekg_host_last_error().decode())
+        return crit, viol

@@ -1,0 +1,88 @@
+"""Host-side C++ (ekgsim_b200/host): ini/format readers, the evaluation glue and the CLI.
+CPU tests compare the newly written glue with the reference's own glue outputs
+(tests/golden/golden_glue256.npz, dumped from the compiled reference by oracle/ref_dump)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import ekgio
+import hostlib
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+README_VECTOR = "0.00035813,0.0890636,0.0632915,226.183,0.000369406,0.0965625,0.0523254,232.278,0.000710767,0.0720323,0.0187579,200.93,23,22,15,13"
+
+
+@pytest.fixture(scope="module")
+def testrun(built, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("testrun"))
+    ekgio.materialise_testrun(d)
+    return d
+
+
+def test_layer_coefficients_bit_identical_to_reference_glue(testrun):
+    """sim.cpp:825-916 + nonlinearFit.h:92-168 restated: 24x9 coefficients, displaced leads, violation."""
+    ev = hostlib.Evaluator(testrun, with_device=False)
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    for i in range(0, 256, 2):
+        k, leads, viol = ev.layer_coefficients(g["params"][i])
+        assert k.tobytes() == g["layer_k"][i].tobytes(), i
+        assert np.abs(leads - g["leads_zyx"][i]).max() < 1e-12
+        assert abs(viol - g["violation"][i]) < 1e-12
+    ev.close()
+
+
+def test_ap_formula_matches_oracle():
+    from oracle import oracle
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        k = np.array([rng.uniform(-90, 0), rng.uniform(1.5, 3.5), 100.0, rng.uniform(0.85, 0.95), rng.uniform(0.05, 0.2),
+                      rng.uniform(3e-4, 1e-3), rng.uniform(0.01, 0.1), rng.uniform(0.01, 0.1), rng.uniform(200, 450)])
+        t = rng.uniform(-20, 700)
+        assert hostlib.lib().ekg_host_wohlfart_plus(k.ctypes.data, float(t)) == oracle.wohlfart_plus(k, t)
+
+
+def test_cli_without_gpu_fails_loudly_like_the_reference(testrun, built):
+    """Errors surface as 'runtime error caught: ...' on stdout and exit code 0 (main.cpp:405-413)."""
+    if built.lib().ekg_device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-out", "result"], cwd=testrun, capture_output=True, text=True)
+    assert r.returncode == 0
+    assert " parameters for single simulator run: <0.00035813,0.0890636" in r.stdout
+    assert " u0 = -0,0.619547,0.78496" in r.stdout          # SURVEY 9 console transcript
+    assert "runtime error caught: " in r.stdout and "no CPU fallback" in r.stdout
+    assert "criteria" not in r.stdout
+
+
+def test_ini_semantics(tmp_path, built):
+    """Last duplicate wins, names are space/case sensitive, unknown neighbourhood throws."""
+    d = str(tmp_path)
+    ekgio.materialise_testrun(d, ini_edit=lambda s: s.replace("neighbourhood type = 3D4", "neighbourhood type = 3D4\nneighbourhood type = 5D9"))
+    with pytest.raises(RuntimeError) as e:
+        hostlib.Evaluator(d, with_device=False)
+    assert "unknown neighbourhood" in str(e.value)
+    ekgio.materialise_testrun(d, ini_edit=lambda s: s.replace("interpolation = endo-mid-epi", "interpolation = sideways"))
+    with pytest.raises(RuntimeError) as e:
+        hostlib.Evaluator(d, with_device=False)
+    assert "unknown interpolation type [sideways]" in str(e.value)
+
+
+def test_missing_files(tmp_path, built):
+    d = str(tmp_path)
+    ekgio.materialise_testrun(d)
+    os.remove(os.path.join(d, "conduction_24.matrix"))
+    with pytest.raises(RuntimeError) as e:
+        hostlib.Evaluator(d, with_device=False)
+    assert "could not open file conduction_24.matrix" in str(e.value)
+
+
+def test_char_matrix_and_2d_model(tmp_path, built):
+    """One-character-per-voxel .matrix (matrix.h:206-218): digits, letters = 10.., X = start in layer 1."""
+    d = str(tmp_path)
+    ekgio.materialise_testrun(d)
+    rows = ["0000000000", "0112233440", "01X2233440", "0112233AB0", "0000000000"]
+    with open(os.path.join(d, "model_24.matrix"), "w") as f:
+        f.write("tiny\n2d 10 x 5\n" + "\n".join(rows) + "\n")
+    ev = hostlib.Evaluator(d, with_device=False, n_layers=11)   # highest layer 'B' = 11
+    ev.close()
