@@ -161,8 +161,8 @@ class Model:
         if leads.ndim == 2:
             leads = np.broadcast_to(leads[None], (B,) + leads.shape).copy()
         L = leads.shape[1]
-        T = n_steps(total_time, t_step)
-        out = np.empty((B, L, T), dtype=np.float64)
+        T = n_steps(total_time, t_step) if t_step > 0 and total_time > 0 else 0
+        out = np.empty((B, L, max(T, 0)), dtype=np.float64)
         _check(lib().ekg_simulate(self._h, _ptr(layer_k), _ptr(leads), B, L, NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd),
                                   float(t_start), float(t_step), float(total_time), int(mode), _ptr(out)))
         return out

@@ -127,7 +127,9 @@ struct ActionPotential {
 	size_t size() const { return wohl.numParams; }
 };
 
-typedef ekg::NamedColumn saveVecElement;
+/// element of the vector handed to exportVectors (simulator.h:488-500); a type of this namespace so
+/// that unqualified exportVectors(...) calls in caller code resolve here by ADL like in the reference
+struct saveVecElement : ekg::NamedColumn {};
 
 template <class Vec>
 void exportVectors(const Vec& vec, const std::string& filename, double startTime, double timeStep = -1.0, const std::string& comment = "") {

@@ -110,3 +110,20 @@ def test_cli_extern_protocol(testrun, golden):
     crit = [float(x) for x in txt[:2]]
     assert np.abs(np.array(crit) - golden["criteria"][i]).max() < 1e-4
     assert txt[2].startswith("# violation 0")
+
+
+def test_reference_glue_on_b200_simlib(testrun, golden):
+    """The reference's UNMODIFIED main.cpp + sim.cpp, compiled from /root/reference against the B200
+    facade (oracle/Makefile target refglue, ekgsim_b200/host/compat/refglue_shim.h): only simlib is
+    swapped, so this isolates the simulator library as a drop-in."""
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "ekgSim_refglue_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ekgSim_refglue_b200 not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "test", "-sim", README_VECTOR, "-out", "result"], cwd=testrun, capture_output=True, text=True)
+    assert r.returncode == 0 and "caught" not in r.stdout, r.stdout[-500:]
+    m = re.search(r" criteria = <([0-9.e+-]+),([0-9.e+-]+)>, violation = ([0-9.e+-]+)\n", r.stdout)
+    i = list(golden["name"]).index("full1")
+    assert abs(float(m.group(1)) - golden["criteria"][i][0]) < 1e-4 and abs(float(m.group(2)) - golden["criteria"][i][1]) < 1e-4
+    assert m.group(3) == "240.609"
+    lines = open(os.path.join(testrun, "result.column")).read().split("\n")
+    assert lines[2] == "#Time[ms]\t69.0145,128.133,-71.8312\t336.761,-112.667,183.886" and len(lines) == 403

@@ -148,3 +148,79 @@ def test_determinism(gpu_model24, model24_delay):
     a = gpu_model24.simulate(g["layer_k"][:4], g["leads_zyx"][:4], "3D4", 100.0, 1.0, 16.0, mode=1)
     b = gpu_model24.simulate(g["layer_k"][:4], g["leads_zyx"][:4], "3D4", 100.0, 1.0, 16.0, mode=1)
     assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("n_leads", [1, 3, 5])
+def test_ecg_lead_counts(built, n_leads):
+    """Lead passes: 1..4 leads per launch, more than 4 in several passes."""
+    layers, transfer, leads2 = synth.small_heart(seed=12)
+    rng = np.random.default_rng(n_leads)
+    leads = np.concatenate([leads2, rng.uniform(-60, 90, size=(4, 3))])[:n_leads]
+    nl = int((layers & 0xFFF).max())
+    k = synth.layer_params(nl, seed=1, batch=2)
+    delay = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    m.set_activation(delay)
+    for mode in (1, 2):
+        ecg = m.simulate(k, leads, "3D4", 0.0, 1.0, 80.0, mode=mode)
+        assert ecg.shape == (2, n_leads, 80)
+        for b in range(2):
+            ref = oracle.run_direct(layers, delay, k[b], leads, "3D4", 0.0, 1.0, 80.0)
+            assert rel_err(ecg[b], ref) < ECG_TOL, (mode, b, rel_err(ecg[b], ref))
+    m.close()
+
+
+@pytest.mark.parametrize("nbhd", ["2D4", "2D8"])
+def test_ecg_2d_model(built, nbhd):
+    layers, transfer, _ = synth.small_heart(seed=4, shape=(1, 40, 36), n_layers=5, hole=False)
+    leads = np.array([[30.0, -20.0, 50.0], [-25.0, 70.0, 10.0]])
+    k = synth.layer_params(5, seed=8)
+    delay = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    m.set_activation(delay)
+    for mode in (1, 2):
+        ecg = m.simulate(k, leads, nbhd, 0.0, 1.0, 60.0, mode=mode)[0]
+        ref = oracle.run_direct(layers, delay, k, leads, nbhd, 0.0, 1.0, 60.0)
+        assert rel_err(ecg, ref) < ECG_TOL, (mode, nbhd, rel_err(ecg, ref))
+    m.close()
+
+
+@pytest.mark.parametrize("B,t0,dt,total", [(10, 0.0, 1.0, 7.0), (37, 5.0, 0.25, 3.0), (3, 0.0, 2.0, 1500.0), (1, 20.0, 1.0, 1.0)])
+def test_ecg_ragged_pair_tiles(built, B, t0, dt, total):
+    """Few samples per vector (one 256-pair tile spans many vectors and is cut at 4), more samples
+    than one tile, a single sample, fractional (exactly representable) time steps."""
+    layers, transfer, leads = synth.small_heart(seed=21, shape=(14, 15, 16), n_layers=4)
+    nl = int((layers & 0xFFF).max())
+    k = synth.layer_params(nl, seed=B, batch=B)
+    if B == 1:
+        k = k.reshape(1, nl, 9)
+    delay = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    m.set_activation(delay)
+    lb = np.stack([leads + i for i in range(B)])  # every vector has its own lead positions
+    full = [oracle.run_direct(layers, delay, k[b], lb[b], "3D4", 0.0, 1.0, 300.0) for b in range(min(B, 4))]
+    for mode in (1, 2):
+        ecg = m.simulate(k, lb, "3D4", t0, dt, total, mode=mode)
+        for b in range(min(B, 4)):
+            ref = oracle.run_direct(layers, delay, k[b], lb[b], "3D4", t0, dt, total)
+            peak = np.abs(full[b]).max(axis=1, keepdims=True)   # peak of the whole trace, not of a short window
+            assert (np.abs(ecg[b] - ref) / peak).max() < ECG_TOL, (mode, b)
+    m.close()
+
+
+def test_simulate_argument_errors(built):
+    layers, transfer, leads = synth.small_heart(seed=1)
+    nl = int((layers & 0xFFF).max())
+    k = synth.layer_params(nl, seed=1)
+    m = built.Model(layers, transfer)
+    with pytest.raises(built.EkgError) as e:   # no activation map yet
+        m.simulate(k, leads, "3D4", 0.0, 1.0, 10.0)
+    assert e.value.code == -4
+    m.activation()
+    with pytest.raises(built.EkgError):
+        m.simulate(k, leads, 9, 0.0, 1.0, 10.0)      # unknown neighbourhood id
+    with pytest.raises(built.EkgError):
+        m.simulate(k, leads, "3D4", 0.0, -1.0, 10.0)  # bad step
+    with pytest.raises(built.EkgError):
+        m.set_slab(5, 2)
+    m.close()
