@@ -256,6 +256,19 @@ int64_t ekg_oracle_run_factored(const uint16_t* layers, const double* delay,
                                 const double* leads, int64_t n_leads, int nbhd,
                                 double t_start, double t_step, double total_time,
                                 double* ecg) {
+	return ekg_oracle_run_factored_slab(layers, delay, Z, Y, X, layer_k, n_layers, leads, n_leads, nbhd,
+	                                    t_start, t_step, total_time, 0, Z, ecg);
+}
+
+/* Partial ECG of the z-slab [z0, z1): only the terms G_c V_c(t) of voxels c inside the slab, with
+ * G_c built from the WHOLE model's neighbourhood.  Slabs partition the voxels, so the partial ECGs
+ * of a partition of [0, Z) add up to the full ECG (multi-GPU sharding of one model). */
+int64_t ekg_oracle_run_factored_slab(const uint16_t* layers, const double* delay,
+                                     int64_t Z, int64_t Y, int64_t X,
+                                     const double* layer_k, int64_t n_layers,
+                                     const double* leads, int64_t n_leads, int nbhd,
+                                     double t_start, double t_step, double total_time,
+                                     int64_t z0, int64_t z1, double* ecg) {
 	int dif[26 * 3];
 	int nn = ekg_oracle_neighbourhood(nbhd, dif);
 	if (nn < 0) return -1;
@@ -293,8 +306,8 @@ int64_t ekg_oracle_run_factored(const uint16_t* layers, const double* delay,
 			if ((layers[j] & ~START_FLAG) == 0) continue;
 			for (int64_t m = 0; m < n_leads; ++m) {
 				double wd = w[3 * m] * dif[3 * k] + w[3 * m + 1] * dif[3 * k + 1] + w[3 * m + 2] * dif[3 * k + 2];
-				G[cls[j] * n_leads + m] += wd;
-				G[cls[c] * n_leads + m] -= wd;
+				if (z2 >= z0 && z2 < z1) G[cls[j] * n_leads + m] += wd;
+				if (z >= z0 && z < z1) G[cls[c] * n_leads + m] -= wd;
 			}
 		}
 	}

@@ -65,6 +65,14 @@ int64_t ekg_oracle_run_factored(const uint16_t* layers, const double* delay,
                                 double t_start, double t_step, double total_time,
                                 double* ecg_out);
 
+/* Partial ECG of the voxels with z in [z0, z1) (see ekg_oracle.c); slabs add up to run_factored. */
+int64_t ekg_oracle_run_factored_slab(const uint16_t* layers, const double* delay,
+                                     int64_t Z, int64_t Y, int64_t X,
+                                     const double* layer_k, int64_t n_layers,
+                                     const double* leads_zyx, int64_t n_leads, int nbhd,
+                                     double t_start, double t_step, double total_time,
+                                     int64_t z0, int64_t z1, double* ecg_out);
+
 /* Simulation::setApIndices (simulator.cpp:561-621): ap_index_out[Z*Y*X] in first-seen raster
  * order (-1 for empty voxels).  Returns the number of classes K. */
 int64_t ekg_oracle_ap_classes(const uint16_t* layers, const double* delay,

@@ -48,6 +48,8 @@ def lib():
         for f in (L.ekg_oracle_run_direct, L.ekg_oracle_run_factored):
             f.restype = i64
             f.argtypes = [p, p, i64, i64, i64, p, i64, p, i64, C.c_int, d, d, d, p]
+        L.ekg_oracle_run_factored_slab.restype = i64
+        L.ekg_oracle_run_factored_slab.argtypes = [p, p, i64, i64, i64, p, i64, p, i64, C.c_int, d, d, d, i64, i64, p]
         L.ekg_oracle_ap_classes.restype = i64
         L.ekg_oracle_ap_classes.argtypes = [p, p, i64, i64, p]
         L.ekg_oracle_run_approximation.restype = i64
@@ -110,6 +112,11 @@ def run_direct(layers, delay, layer_k, leads_zyx, nbhd="3D4", t_start=100.0, t_s
 
 def run_factored(layers, delay, layer_k, leads_zyx, nbhd="3D4", t_start=100.0, t_step=1.0, total_time=400.0):
     return _run(lib().ekg_oracle_run_factored, layers, delay, layer_k, leads_zyx, nbhd, t_start, t_step, total_time)
+
+
+def run_factored_slab(layers, delay, layer_k, leads_zyx, z0, z1, nbhd="3D4", t_start=100.0, t_step=1.0, total_time=400.0):
+    fn = lambda *a: lib().ekg_oracle_run_factored_slab(*a[:-1], int(z0), int(z1), a[-1])
+    return _run(fn, layers, delay, layer_k, leads_zyx, nbhd, t_start, t_step, total_time)
 
 
 def ap_classes(layers, delay, n_layers):

@@ -1,0 +1,86 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU plumbing in ekgsim_b200/dist.py.  The per-rank compute
+is played by the oracle (allowed in tests); what is under test is the sharding arithmetic and the
+collectives: individuals sharded + gathered, z-slabs summed by all-reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import synth
+from ekgsim_b200 import dist as ekdist
+from oracle import oracle
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 256, 1001):
+        for world in (1, 2, 3, 8):
+            r = [ekdist.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_slab_ranges_balance(model24):
+    occ = ((model24["layers"] & 0x0FFF) > 0).sum(axis=(1, 2))
+    for world in (1, 2, 4, 8):
+        slabs = ekdist.slab_ranges(occ, world)
+        assert slabs[0][0] == 0 and slabs[-1][1] == len(occ)
+        assert all(slabs[i][1] == slabs[i + 1][0] for i in range(world - 1))
+        counts = [int(occ[a:b].sum()) for a, b in slabs]
+        assert sum(counts) == 555868
+        assert max(counts) <= 1.1 * 555868 / world + occ.max()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    r, w, _ = ekdist.init("gloo")
+    layers, transfer, leads = synth.small_heart(seed=5, shape=(12, 13, 14), n_layers=4)
+    nl = 4
+    k = synth.layer_params(nl, seed=9, batch=5)
+    delay = oracle.activation(layers, transfer)
+    # (1) individuals sharded over ranks, gathered in rank order
+    b0, b1 = ekdist.shard_range(5, r, w)
+    mine = np.stack([oracle.run_factored(layers, delay, k[b], leads, "3D4", 0.0, 1.0, 24.0) for b in range(b0, b1)]) if b1 > b0 \
+        else np.zeros((0, 2, 24))
+    counts = [ekdist.shard_range(5, i, w)[1] - ekdist.shard_range(5, i, w)[0] for i in range(w)]
+    allv = ekdist.gather_rows(torch.from_numpy(mine), counts).numpy()
+    # (2) one model split into z-slabs, partial ECGs summed
+    occ = ((layers & 0x0FFF) > 0).sum(axis=(1, 2))
+    z0, z1 = ekdist.slab_ranges(occ, w)[r]
+    part = torch.from_numpy(oracle.run_factored_slab(layers, delay, k[0], leads, z0, z1, "3D4", 0.0, 1.0, 24.0))
+    ekdist.allreduce_sum_(part)
+    tmax = ekdist.max_over_ranks(float(r + 1))
+    if r == 0:
+        ref = np.stack([oracle.run_factored(layers, delay, k[b], leads, "3D4", 0.0, 1.0, 24.0) for b in range(5)])
+        q.put((float(np.abs(allv - ref).max()), float(np.abs(part.numpy() - ref[0]).max() / np.abs(ref[0]).max()), tmax))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_sharding_and_collectives(built):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    gathered_err, slab_err, tmax = q.get()
+    assert gathered_err == 0.0       # gather is a pure permutation
+    assert slab_err < 1e-12          # two slabs add up to the whole model
+    assert tmax == 2.0

@@ -224,3 +224,34 @@ def test_simulate_argument_errors(built):
     with pytest.raises(built.EkgError):
         m.set_slab(5, 2)
     m.close()
+
+
+def test_two_gpus_slabs_and_individuals(built, model24, model24_delay):
+    """Needs 2 GPUs (skipped otherwise): z-slab shards of model_24 on two devices add up to the
+    single-device ECG, and individuals split over two devices reproduce the single-device batch."""
+    if built.lib().ekg_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from ekgsim_b200 import dist as ekdist
+    g = np.load(os.path.join(GOLDEN, "golden_len16.npz"))
+    k, leads = g["layer_k"][:6], g["leads_zyx"][:6]
+    m0 = built.Model(model24["layers"], model24["transfer"], device=0)
+    m1 = built.Model(model24["layers"], model24["transfer"], device=1)
+    d0, _ = m0.activation()
+    d1, _ = m1.activation()
+    assert d0.tobytes() == d1.tobytes() == model24_delay.tobytes()
+    whole = m0.simulate(k, leads, "3D4", 100.0, 1.0, 16.0, mode=1)
+    # individuals: 3 + 3
+    split = np.concatenate([m0.simulate(k[:3], leads[:3], "3D4", 100.0, 1.0, 16.0, mode=1),
+                            m1.simulate(k[3:], leads[3:], "3D4", 100.0, 1.0, 16.0, mode=1)])
+    assert (np.abs(split - whole) / g["peak_full"][:6, :, None]).max() < 2e-6
+    # z-slabs balanced by occupied voxels
+    occ = ((model24["layers"] & 0x0FFF) > 0).sum(axis=(1, 2))
+    (a0, a1), (b0, b1) = ekdist.slab_ranges(occ, 2)
+    m0.set_slab(a0, a1)
+    m1.set_slab(b0, b1)
+    assert m0.num_voxels + m1.num_voxels == 555868 and abs(m0.num_voxels - m1.num_voxels) < 0.05 * 555868
+    parts = m0.simulate(k, leads, "3D4", 100.0, 1.0, 16.0, mode=1) + m1.simulate(k, leads, "3D4", 100.0, 1.0, 16.0, mode=1)
+    assert (np.abs(parts - whole) / g["peak_full"][:6, :, None]).max() < 2e-6
+    assert (np.abs(parts - g["ecg"][:6]) / g["peak_full"][:6, :, None]).max() < ECG_TOL
+    m0.close()
+    m1.close()

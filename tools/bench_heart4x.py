@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""tools/bench_heart4x.py -- BASELINE config 4: synthetic 4x-resolution voxel heart
+(np.repeat(model_24, 4) along z, y, x -> 496 x 496 x 372 grid, 35.6 M occupied voxels, one start
+voxel, lead positions x4), ONE simulation, voxels sharded over the ranks as z-slabs, partial ECGs
+summed with one all-reduce.  Run with torchrun (one process per GPU) or as a single process.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/bench_heart4x.py [--check] [--steps K]
+
+--check compares the automaton with the oracle (bit-exact; ~2 min of CPU on rank 0) and the ECG with
+the oracle's class-factored loop on the first 8 samples.  Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import ekgio  # noqa: E402
+import ekgsim_b200 as ek  # noqa: E402
+from ekgsim_b200 import dist as ekdist  # noqa: E402
+
+
+def heart4x(f=4):
+    m = ekgio.load_model24()
+    base = m["layers"]
+    start = np.argwhere(base & ek.START_FLAG)[0]
+    plain = (base & 0x0FFF).astype(np.uint16)
+    big = np.repeat(np.repeat(np.repeat(plain, f, axis=0), f, axis=1), f, axis=2)
+    big[tuple(start * f)] |= ek.START_FLAG   # first replica of the original start voxel in raster order
+    return big, m["transfer"], m["leads_zyx"] * f
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--factor", type=int, default=4)
+    ap.add_argument("--mode", default="direct")
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    rank, world, local = ekdist.init()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    layers, transfer, leads = heart4x(a.factor)
+    n_occ = int(((layers & 0x0FFF) > 0).sum())
+    t0 = time.time()
+    model = ek.Model(layers, transfer, device=local)
+    t_create = time.time() - t0
+    delay, sweeps = model.activation()
+    auto_ms = model.activation_ms
+    occ_z = ((layers & 0x0FFF) > 0).sum(axis=(1, 2))
+    z0, z1 = ekdist.slab_ranges(occ_z, world)[rank]
+    model.set_slab(z0, z1)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_glue256.npz"))
+    k = np.ascontiguousarray(g["layer_k"][:1])
+    lead_b = np.ascontiguousarray(leads[None])
+    T = 400
+    mode = ek.MODE_DIRECT if a.mode == "direct" else ek.MODE_HOISTED
+    d_k = torch.from_numpy(k).to(dev)
+    d_l = torch.from_numpy(lead_b).to(dev)
+    d_e = torch.empty((1, 2, T), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        model.simulate_device(d_k.data_ptr(), d_l.data_ptr(), 1, 2, d_e.data_ptr(), "3D4", 100.0, 1.0, float(T), mode=mode, stream=stream)
+        ekdist.allreduce_sum_(d_e)   # per-lead partial sums of all slabs -> ECG (6.4 kB)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = ekdist.max_over_ranks(e0.elapsed_time(e1) / a.steps, dev)
+    ecg = d_e.cpu().numpy()[0]
+    out = {"workload": "configs[3]: %dx heart, %d occupied voxels, z-slab sharded over %d GPU(s)" % (a.factor, n_occ, world),
+           "n_gpus": world, "ms_per_sim": ms, "voxel_timesteps_per_s": n_occ * T / (ms * 1e-3), "mode": a.mode,
+           "automaton_ms": auto_ms, "automaton_sweeps": sweeps, "model_create_s": t_create,
+           "slab_voxels_rank0": model.num_voxels, "ecg_peak": np.abs(ecg).max(axis=1).tolist()}
+    if a.check and rank == 0:
+        from oracle import oracle
+        t0 = time.time()
+        ref_delay = oracle.activation(layers, transfer)
+        out["automaton_bit_exact"] = bool(ref_delay.tobytes() == delay.tobytes())
+        out["oracle_automaton_s"] = time.time() - t0
+        t0 = time.time()
+        ref = oracle.run_factored(layers, ref_delay, k[0], leads, "3D4", 100.0, 1.0, 8.0)
+        out["oracle_ecg8_s"] = time.time() - t0
+        full_peak = np.abs(ecg).max(axis=1, keepdims=True)
+        out["ecg_err_of_peak_first8"] = float((np.abs(ecg[:, :8] - ref) / full_peak).max())
+    if world > 1:
+        torch.distributed.barrier()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
