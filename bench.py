@@ -204,6 +204,11 @@ def run_b200_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner, the facade's console lines) write to fd 1; keep stdout for the
+    # ONE JSON line by pointing fd 1 at stderr until the result is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -356,7 +361,8 @@ def run_b200_arm(args):
                                               "length %d of 400 samples (%.1f s wall)" % (cores, args.ref_length, wall)}
         except Exception as e:  # the reference binary is a prebuilt artefact; say so instead of failing the bench
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -36,6 +36,16 @@ __global__ void gather_at_kernel(const double* __restrict__ time_pad, const uint
 	at32[i] = (float)v;
 }
 
+// Host -> device upload that is COMPLETE on return.  A plain cudaMemcpy from pageable memory may return
+// while the DMA is still in flight, and kernels on our non-blocking stream do not wait for the legacy
+// default stream -- so uploads go through the model's stream and are synchronised there.
+static int upload(ekg_model* m, void* dst, const void* src, size_t bytes) {
+	if (!bytes) return EKG_OK;
+	EKG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, m->stream));
+	EKG_CUDA(cudaStreamSynchronize(m->stream));
+	return EKG_OK;
+}
+
 static int64_t pad_index(const ekg_model* m, int64_t z, int64_t y, int64_t x) { return ((z + 1) * m->pY + (y + 1)) * m->pX + (x + 1); }
 
 static void free_model(ekg_model* m) {
@@ -93,9 +103,10 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 	EKG_CUDA(cudaMalloc(&m->d_ecg_pidx, nn * 4));
 	EKG_CUDA(cudaMalloc(&m->d_at, nn * 8));
 	EKG_CUDA(cudaMalloc(&m->d_at32, nn * 4));
-	EKG_CUDA(cudaMemcpy(m->d_pos, pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
-	EKG_CUDA(cudaMemcpy(m->d_mask, mask.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
-	EKG_CUDA(cudaMemcpy(m->d_ecg_pidx, pidx.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+	int rc;
+	if ((rc = upload(m, m->d_pos, pos.data(), (size_t)n * 4))) return rc;
+	if ((rc = upload(m, m->d_mask, mask.data(), (size_t)n * 4))) return rc;
+	if ((rc = upload(m, m->d_ecg_pidx, pidx.data(), (size_t)n * 4))) return rc;
 	m->n_ecg = n;
 	m->slab_z0 = z0; m->slab_z1 = z1;
 	m->n_segs = 0; m->seg_len = 0;  // segment table depends on the list
@@ -115,7 +126,8 @@ static int publish_activation(ekg_model* m, bool download) {
 	const int64_t n = m->Z * m->Y * m->X;
 	if (download) {
 		std::vector<double> padded((size_t)(m->pZ * m->pY * m->pX));
-		EKG_CUDA(cudaMemcpy(padded.data(), m->d_time_pad, padded.size() * 8, cudaMemcpyDeviceToHost));
+		EKG_CUDA(cudaMemcpyAsync(padded.data(), m->d_time_pad, padded.size() * 8, cudaMemcpyDeviceToHost, m->stream));
+		EKG_CUDA(cudaStreamSynchronize(m->stream));
 		m->h_delay.assign((size_t)n, 0.0);
 		for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < m->Y; ++y) for (int64_t x = 0; x < m->X; ++x) {
 			const int64_t i = (z * m->Y + y) * m->X + x;
@@ -202,9 +214,9 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_time_pad, (size_t)npad * 8));
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_auto_pidx, pidx.size() * 4));
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_flags, (size_t)(m->max_sweeps + 1) * sizeof(int)));
-		EKG_CREATE_CUDA(cudaMemcpy(m->d_layer_pad, lp.data(), (size_t)npad, cudaMemcpyHostToDevice));
-		EKG_CREATE_CUDA(cudaMemcpy(m->d_auto_pidx, pidx.data(), pidx.size() * 4, cudaMemcpyHostToDevice));
-		EKG_CREATE_CUDA(cudaMemset(m->d_time_pad, 0, (size_t)npad * 8));
+		if (upload(m, m->d_layer_pad, lp.data(), (size_t)npad) || upload(m, m->d_auto_pidx, pidx.data(), pidx.size() * 4)) { free_model(m); return EKG_E_CUDA; }
+		EKG_CREATE_CUDA(cudaMemsetAsync(m->d_time_pad, 0, (size_t)npad * 8, m->stream));
+		EKG_CREATE_CUDA(cudaStreamSynchronize(m->stream));
 	}
 	// edge weights: lag = T[layer][neighbour layer] * sqrt(sqrLength(dif)) (simulator.cpp:239-240), host IEEE arithmetic
 	{
@@ -219,7 +231,7 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 			}
 		}
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_wtab, w.size() * 8));
-		EKG_CREATE_CUDA(cudaMemcpy(m->d_wtab, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+		if (upload(m, m->d_wtab, w.data(), w.size() * 8)) { free_model(m); return EKG_E_CUDA; }
 	}
 	int rc = build_ecg_list(m, 0, Z);
 	if (rc) { free_model(m); return rc; }
@@ -278,7 +290,8 @@ int ekg_model_set_activation(ekg_model* m, const double* delay) {
 	std::vector<double> padded((size_t)(m->pZ * m->pY * m->pX), 0.0);
 	for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < m->Y; ++y)
 		memcpy(&padded[(size_t)pad_index(m, z, y, 0)], &delay[(z * m->Y + y) * m->X], (size_t)m->X * 8);
-	EKG_CUDA(cudaMemcpy(m->d_time_pad, padded.data(), padded.size() * 8, cudaMemcpyHostToDevice));
+	int rc = upload(m, m->d_time_pad, padded.data(), padded.size() * 8);
+	if (rc) return rc;
 	return publish_activation(m, false);
 }
 
@@ -317,8 +330,8 @@ int ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_l
                         double t_start, double t_step, double total_time, int flags, double* d_ecg_out, void* stream) {
 	if (!m || !d_layer_k || !d_leads_zyx || !d_ecg_out) return fail(EKG_E_INVALID, "NULL argument");
 	EKG_CUDA(cudaSetDevice(m->device));
-	return run_ecg(m, d_layer_k, d_leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, d_ecg_out,
-	               stream ? (cudaStream_t)stream : m->stream);
+	// the caller's stream as given: NULL is CUDA's default stream (what torch uses unless told otherwise)
+	return run_ecg(m, d_layer_k, d_leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, d_ecg_out, (cudaStream_t)stream);
 }
 
 int ekg_simulate(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,

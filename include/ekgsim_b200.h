@@ -110,8 +110,9 @@ int  ekg_simulate(ekg_model* m, const double* layer_k, const double* leads_zyx,
                   double t_start, double t_step, double total_time,
                   int flags, double* ecg_out);
 
-/* Same with device pointers (on the model's device) and a caller stream (cudaStream_t, may be
- * NULL = the model's own stream).  Asynchronous with respect to the host. */
+/* Same with device pointers (on the model's device), enqueued on the caller's stream (a
+ * cudaStream_t; NULL = CUDA's default stream).  Asynchronous with respect to the host: the ECGs are
+ * ready when work enqueued on that stream after this call runs. */
 int  ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_leads_zyx,
                          int64_t B, int64_t n_leads, int nbhd,
                          double t_start, double t_step, double total_time,
