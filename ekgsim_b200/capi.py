@@ -34,6 +34,7 @@ SYMBOLS = {
     "ekg_model_num_layers": (_i64, [_p]),
     "ekg_model_activation": (_int, [_p, _p, C.POINTER(_i64)]),
     "ekg_model_activation_ms": (_d, [_p]),
+    "ekg_model_activation_brick_visits": (_i64, [_p]),
     "ekg_model_set_activation": (_int, [_p, _p]),
     "ekg_model_get_activation": (_int, [_p, _p]),
     "ekg_model_ap_classes": (_int, [_p, _p, C.POINTER(_i64)]),
@@ -133,6 +134,10 @@ class Model:
     @property
     def activation_ms(self):
         return float(lib().ekg_model_activation_ms(self._h))
+
+    @property
+    def activation_brick_visits(self):
+        return int(lib().ekg_model_activation_brick_visits(self._h))
 
     def set_activation(self, delay):
         delay = np.ascontiguousarray(delay, dtype=np.float64)

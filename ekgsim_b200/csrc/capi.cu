@@ -51,7 +51,7 @@ static int64_t pad_index(const ekg_model* m, int64_t z, int64_t y, int64_t x) { 
 static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
-	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
+	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
 	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
@@ -165,13 +165,14 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 	if (!layers || Z <= 0 || Y <= 0 || X <= 0) return fail(EKG_E_INVALID, "bad shape");
 	if (!transfer || t_rows <= 0 || t_cols <= 0) return fail(EKG_E_INVALID, "bad transfer matrix");
 	if (X > 2047 || Y > 2047 || Z > 1023) return fail(EKG_E_UNSUPPORTED, "grid exceeds the packed coordinate layout (X,Y <= 2047, Z <= 1023)");
-	if ((Z + 2) * (Y + 2) * (X + 2) >= (int64_t)1 << 32) return fail(EKG_E_UNSUPPORTED, "grid exceeds 2^32 padded voxels");
+	if ((Z + 10) * (Y + 10) * (X + 10) >= (int64_t)1 << 32) return fail(EKG_E_UNSUPPORTED, "grid exceeds 2^32 padded voxels");
 	if (ekg_device_count() <= device || device < 0) return fail(EKG_E_CUDA, "no such CUDA device (libekgsim_b200 has no CPU fallback)");
 
 	ekg_model* m = new ekg_model();
 	m->device = device;
 	m->Z = Z; m->Y = Y; m->X = X;
-	m->pZ = Z + 2; m->pY = Y + 2; m->pX = X + 2;
+	// zero border of one voxel, extents rounded up to whole 8^3 bricks (brick-frontier automaton)
+	m->pZ = (Z + 7) / 8 * 8 + 2; m->pY = (Y + 7) / 8 * 8 + 2; m->pX = (X + 7) / 8 * 8 + 2;
 	const int64_t n = Z * Y * X;
 	m->h_layer.resize((size_t)n);
 	int max_layer = 0;
@@ -232,6 +233,40 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		}
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_wtab, w.size() * 8));
 		if (upload(m, m->d_wtab, w.data(), w.size() * 8)) { free_model(m); return EKG_E_CUDA; }
+	}
+	// live bricks (8^3 tiles holding at least one occupied voxel), their origins and 26 neighbours
+	{
+		const int64_t bZ = (Z + 7) / 8, bY = (Y + 7) / 8, bX = (X + 7) / 8;
+		std::vector<int32_t> index((size_t)(bZ * bY * bX), -1);
+		std::vector<uint32_t> origin;
+		for (int64_t z = 0; z < Z; ++z) for (int64_t y = 0; y < Y; ++y) for (int64_t x = 0; x < X; ++x) {
+			if (!m->h_layer[(size_t)((z * Y + y) * X + x)]) continue;
+			int32_t& bi = index[(size_t)(((z / 8) * bY + y / 8) * bX + x / 8)];
+			if (bi < 0) { bi = (int32_t)origin.size(); origin.push_back((uint32_t)pad_index(m, z / 8 * 8, y / 8 * 8, x / 8 * 8)); }
+		}
+		const int64_t nb = (int64_t)origin.size();
+		std::vector<int32_t> nbr((size_t)std::max<int64_t>(nb, 1) * 26, -1);
+		for (int64_t bz = 0; bz < bZ; ++bz) for (int64_t by = 0; by < bY; ++by) for (int64_t bx = 0; bx < bX; ++bx) {
+			const int32_t bi = index[(size_t)((bz * bY + by) * bX + bx)];
+			if (bi < 0) continue;
+			int k = 0;
+			for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+				if (!dz && !dy && !dx) continue;
+				const int64_t cz = bz + dz, cy = by + dy, cx = bx + dx;
+				if (cz >= 0 && cz < bZ && cy >= 0 && cy < bY && cx >= 0 && cx < bX) nbr[(size_t)bi * 26 + k] = index[(size_t)((cz * bY + cy) * bX + cx)];
+				++k;
+			}
+		}
+		for (int64_t r : m->h_starts) {
+			const int64_t z = r / (Y * X), y = (r / X) % Y, x = r % X;
+			const int32_t bi = index[(size_t)(((z / 8) * bY + y / 8) * bX + x / 8)];
+			if (std::find(m->h_start_bricks.begin(), m->h_start_bricks.end(), bi) == m->h_start_bricks.end()) m->h_start_bricks.push_back(bi);
+		}
+		m->n_bricks = nb;
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_origin, (size_t)std::max<int64_t>(nb, 1) * 4));
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_nbr, nbr.size() * 4));
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, ((size_t)nb * 5 + 8) * sizeof(int)));
+		if (upload(m, m->d_brick_origin, origin.data(), origin.size() * 4) || upload(m, m->d_brick_nbr, nbr.data(), nbr.size() * 4)) { free_model(m); return EKG_E_CUDA; }
 	}
 	int rc = build_ecg_list(m, 0, Z);
 	if (rc) { free_model(m); return rc; }
@@ -302,6 +337,7 @@ int ekg_model_get_activation(const ekg_model* m, double* delay_out) {
 	return EKG_OK;
 }
 
+int64_t ekg_model_activation_brick_visits(const ekg_model* m) { return m ? m->last_brick_visits : 0; }
 double ekg_model_activation_ms(const ekg_model* m) { return m ? (double)m->activation_ms : 0.0; }
 
 int ekg_model_ap_classes(const ekg_model* m, int64_t* ap_index_out, int64_t* n_classes_out) {

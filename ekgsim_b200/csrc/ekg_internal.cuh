@@ -83,6 +83,26 @@ struct AutoArgs {
 	int32_t max_sweeps;
 };
 
+// Brick-frontier automaton (automaton.cu): the padded grid is tiled by 8x8x8 bricks.
+constexpr int kBrick = 8;
+constexpr int kBrickHalo = kBrick + 2;                                // 10
+constexpr int kBrickCells = kBrickHalo * kBrickHalo * kBrickHalo;    // 1000 (brick + one-voxel halo)
+
+struct BrickArgs {
+	const uint8_t* layer;    // padded dense grid
+	double* time;            // padded dense grid
+	const double* wtab;      // [nl1][nl1][3]
+	const uint32_t* origin;  // [n_live] padded linear index of the brick's first voxel
+	const int32_t* nbr;      // [n_live][26] live index of the neighbouring brick in cube direction k, -1 = none
+	int* flag;               // [2][n_live] brick is queued for the round of that parity
+	int* queue;              // [3][n_live] work queues, rotating
+	int* counters;           // [0..2] queue lengths, [3] rounds, [4] brick visits
+	int32_t n_live, nl1, n_nbr, pY, pX, max_rounds, w_in_smem;
+	int32_t loff[kMaxNbr];   // neighbour offset inside the 10^3 shared-memory cell array
+	int32_t sq[kMaxNbr];     // |dif|^2 - 1
+	int8_t dz[kMaxNbr], dy[kMaxNbr], dx[kMaxNbr];
+};
+
 }  // namespace ekg
 
 // The opaque handle of the C ABI.
@@ -112,6 +132,13 @@ struct ekg_model {
 	double* d_wtab = nullptr;
 	int* d_flags = nullptr;
 	int max_sweeps = 1 << 16;
+	// brick-frontier automaton
+	int64_t n_bricks = 0;
+	uint32_t* d_brick_origin = nullptr;
+	int32_t* d_brick_nbr = nullptr;
+	int* d_brick_state = nullptr;        // flag[2][n] | queue[3][n] | counters[8]
+	std::vector<int32_t> h_start_bricks;
+	int64_t last_brick_visits = 0;
 
 	// ECG voxel list (layer-sorted, restricted to the slab)
 	int64_t slab_z0 = 0, slab_z1 = 0;
