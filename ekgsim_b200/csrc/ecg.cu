@@ -31,6 +31,8 @@
 // Algorithmic traffic: 16 B per voxel (pos, mask, at) per CTA, re-read by the B CTAs of a
 // segment from L2; 0.04 B per voxel-timestep at T = 400 -> MUFU-bound, not HBM-bound.
 
+#include <type_traits>
+
 #include "ekg_internal.cuh"
 
 namespace ekg {
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	constexpr int ROW = RowLayout<MODE, NL>::kFloats;
 	__shared__ __align__(16) float s_vox[kSmemRows * ROW];
 	__shared__ float2 s_lead[kMaxVecPerTile * NL * 3];  // lead coordinate as fp32 hi + lo
+	__shared__ int s_atmax[2];                          // HOISTED: latest activation time of the chunk (float bits)
 
 	const Segment sg = a.segs[blockIdx.x];
 	const PairTile tile = a.tiles[blockIdx.y];
@@ -81,6 +84,7 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	const int bl = b - b0;
 	const int chunk = min(kChunk, kSmemRows / nb);
 
+	if (threadIdx.x < 2) s_atmax[threadIdx.x] = 0;
 	if (threadIdx.x < nb * NL * 3) {
 		const int v = threadIdx.x / (NL * 3), r = threadIdx.x % (NL * 3);
 		const int l = a.lead0 + r / 3;
@@ -111,7 +115,8 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 #pragma unroll
 	for (int l = 0; l < NL; ++l) { sum[l] = 0.f; comp[l] = 0.f; }
 
-	for (int base = sg.begin; base < sg.end; base += chunk) {
+	int parity = 0;
+	for (int base = sg.begin; base < sg.end; base += chunk, parity ^= 1) {
 		const int n = min(chunk, sg.end - base);
 		__syncthreads();  // phase B of the previous chunk is done with s_vox; s_lead is visible
 
@@ -160,63 +165,88 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 				const float* Pv = a.params + ((int64_t)(b0 + v) * a.n_layers + (sg.layer - 1)) * kParamStride;
 				const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
 				const float da = at - t0;
-				row[0] = at;
-				row[1] = mufu_ex2(fminf(-(v4 + v5) * da, 60.f));
-				row[2] = mufu_ex2(fminf(-v5 * da, 60.f));
+				// row = (h1, h2, G_0..G_{NL-1}, at): the saturated loop only needs the leading part
+				row[0] = mufu_ex2(fminf(-(v4 + v5) * da, 60.f));
+				row[1] = mufu_ex2(fminf(-v5 * da, 60.f));
 #pragma unroll
-				for (int l = 0; l < NL; ++l) row[3 + l] = G[l];
+				for (int l = 0; l < NL; ++l) row[2 + l] = G[l];
+				row[2 + NL] = at;
+				// activation times are >= 0, so their float bit patterns order like ints
+				const int amax = __reduce_max_sync(__activemask(), __float_as_int(at));
+				if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicMax(&s_atmax[parity], amax);
 			}
 		}
 		__syncthreads();
+		// HOISTED: once every sample of this warp is later than the chunk's last activation by enough
+		// that exp(-k1 (t-at)) < 2^-25, the depolarisation sigmoid is exactly 1 in fp32 and the two
+		// MUFU ops per voxel can be skipped (always the case for T/U-wave runs that start at 100 ms)
+		bool saturated = false;
+		if (MODE == MODE_HOISTED) {
+			const float tau_min = (thi - __int_as_float(s_atmax[parity])) + tlo;
+			saturated = __all_sync(0xffffffffu, !live || a1 * tau_min < -25.f);
+			if (threadIdx.x == 0) s_atmax[parity ^ 1] = 0;  // for the next chunk (written after the barrier above)
+		}
 
 		// ---- phase B: time loop, one (vector, sample) pair per thread, voxel rows from shared memory ----
 		if (live) {
 			const float* my_rows = s_vox + bl * ROW;
 			const int stride = nb * ROW;
-			for (int j0 = 0; j0 < n; j0 += 32) {
-				const int j1 = min(j0 + 32, n);
-				float acc[NL];
+			// SAT = true is the HOISTED loop without the depolarisation sigmoid (see above)
+			auto time_loop = [&](auto sat_tag) {
+				constexpr bool SAT = decltype(sat_tag)::value;
+				for (int j0 = 0; j0 < n; j0 += 32) {
+					const int j1 = min(j0 + 32, n);
+					float acc[NL];
 #pragma unroll
-				for (int l = 0; l < NL; ++l) acc[l] = 0.f;
+					for (int l = 0; l < NL; ++l) acc[l] = 0.f;
+					const float4* rp = reinterpret_cast<const float4*>(my_rows + j0 * stride);
 #pragma unroll 4
-				for (int j = j0; j < j1; ++j) {
-					const float4* rp = reinterpret_cast<const float4*>(my_rows + j * stride);
-					const float4 r0 = rp[0];
-					float V;
-					float G[NL];
-					const float tau = (thi - r0.x) + tlo;               // t - at   (simulator.cpp:169)
-					const float S = mufu_rcp(1.f + mufu_ex2(a1 * tau));  // 1/(1+exp(-k1 t'))
-					if (MODE == MODE_DIRECT) {
-						const float k8s = k8hi - r0.x;                   // k8 - at  (simulator.cpp:156)
-						const float u = (tau - k8s) - k8lo;              // t' - k8'
-						const float e = mufu_ex2(fmaf(a7, u, c2));       // exp(-k7 (t'-k8') + ln(2^(k7/k6)-1))
-						const float Q = mufu_ex2(np * mufu_lg2(1.f + e)); // (1+e)^(-k6/k7)
-						const float Pp = fmaf(A, mufu_ex2(a4 * tau), Bc); // k2((1-k3) exp(-k4 t') + k3)
-						const float E5 = mufu_ex2(a5 * tau);
-						V = fmaf((S * Pp) * E5, 1.f - Q, k0);
-						G[0] = r0.y;
-						if (NL >= 2) G[1] = r0.z;
-						if (NL >= 3) G[2] = r0.w;
-						if (NL >= 4) G[3] = rp[1].x;
-					} else {
-						const float4 r1 = rp[1];
-						V = fmaf(S, fmaf(F1, r0.y, F2 * r0.z), k0);
-						G[0] = r0.w;
-						if (NL >= 2) G[1] = r1.x;
-						if (NL >= 3) G[2] = r1.y;
-						if (NL >= 4) G[3] = r1.z;
+					for (int j = j0; j < j1; ++j, rp += stride / 4) {
+						const float4 r0 = rp[0];
+						float V;
+						float G[NL];
+						if (MODE == MODE_DIRECT) {
+							const float tau = (thi - r0.x) + tlo;               // t - at   (simulator.cpp:169)
+							const float S = mufu_rcp(1.f + mufu_ex2(a1 * tau));  // 1/(1+exp(-k1 t'))
+							const float k8s = k8hi - r0.x;                   // k8 - at  (simulator.cpp:156)
+							const float u = (tau - k8s) - k8lo;              // t' - k8'
+							const float e = mufu_ex2(fmaf(a7, u, c2));       // exp(-k7 (t'-k8') + ln(2^(k7/k6)-1))
+							const float Q = mufu_ex2(np * mufu_lg2(1.f + e)); // (1+e)^(-k6/k7)
+							const float Pp = fmaf(A, mufu_ex2(a4 * tau), Bc); // k2((1-k3) exp(-k4 t') + k3)
+							const float E5 = mufu_ex2(a5 * tau);
+							V = fmaf((S * Pp) * E5, 1.f - Q, k0);
+							G[0] = r0.y;
+							if (NL >= 2) G[1] = r0.z;
+							if (NL >= 3) G[2] = r0.w;
+							if (NL >= 4) G[3] = rp[1].x;
+						} else {
+							G[0] = r0.z;
+							if (NL >= 2) G[1] = r0.w;
+							if (NL >= 3) G[2] = rp[1].x;
+							if (NL >= 4) G[3] = rp[1].y;
+							if (SAT) {
+								V = fmaf(F1, r0.x, fmaf(F2, r0.y, k0));
+							} else {
+								const float at = NL <= 2 ? rp[1].x : rp[1].z;
+								const float tau = (thi - at) + tlo;
+								const float S = mufu_rcp(1.f + mufu_ex2(a1 * tau));
+								V = fmaf(S, fmaf(F1, r0.x, F2 * r0.y), k0);
+							}
+						}
+#pragma unroll
+						for (int l = 0; l < NL; ++l) acc[l] = fmaf(G[l], V, acc[l]);
 					}
 #pragma unroll
-					for (int l = 0; l < NL; ++l) acc[l] = fmaf(G[l], V, acc[l]);
+					for (int l = 0; l < NL; ++l) {
+						const float s1 = sum[l] + acc[l];
+						const float bp = s1 - sum[l];
+						comp[l] += (sum[l] - (s1 - bp)) + (acc[l] - bp);
+						sum[l] = s1;
+					}
 				}
-#pragma unroll
-				for (int l = 0; l < NL; ++l) {
-					const float s1 = sum[l] + acc[l];
-					const float bp = s1 - sum[l];
-					comp[l] += (sum[l] - (s1 - bp)) + (acc[l] - bp);
-					sum[l] = s1;
-				}
-			}
+			};
+			if (MODE == MODE_HOISTED && saturated) time_loop(std::true_type{});
+			else time_loop(std::false_type{});
 		}
 	}
 
@@ -411,7 +441,8 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 		m->n_tiles = (int64_t)tiles.size(); m->tiles_B = B; m->tiles_T = T;
 	}
 	if (B * T >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "B * n_steps must be below 2^31");
-	const int64_t target_ctas = (int64_t)m->sm_count * 4 * 8;
+	// ~100 waves of CTAs: the tail of the last wave costs about 1/waves of the launch
+	const int64_t target_ctas = (int64_t)m->sm_count * 4 * 96;
 	int64_t want_segs = (target_ctas + m->n_tiles - 1) / m->n_tiles;
 	int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
 	seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
