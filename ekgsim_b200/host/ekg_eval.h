@@ -300,6 +300,8 @@ public:
 		}
 	}
 
+	const std::vector<double>& points() const { return points_; }
+
 	/// sum of squared misses
 	double operator()(const AP& ap) const {
 		double sum = 0;
@@ -308,11 +310,68 @@ public:
 	}
 };
 
+/// Per-point factors of the AP at the current iterate, kept so that a one-coefficient perturbation
+/// only recomputes the factor that coefficient enters.  Every factor is evaluated by exactly the
+/// expression WohlfartPlus::operator[] uses and the factors are multiplied in its order
+/// ((A*B)*C)+k0, so the values are bit-identical to a full evaluation.
+struct FitCache {
+	std::vector<double> A, E4, E5, Q;   // 1/(1+e^{-k1 t}),  e^{-k4 t},  e^{-k5 t},  (1+e^{-k7(t-k8)+c})^{-k6/k7}
+	void resize(size_t n) { A.resize(n); E4.resize(n); E5.resize(n); Q.resize(n); }
+};
+
+inline double fit_tail_c(const double* k) { return std::log(std::pow(2, (k[7] / k[6])) - 1); }
+inline double fit_A(const double* k, double t) { return 1.0 / (1.0 + std::exp(-k[1] * t)); }
+inline double fit_Q(const double* k, double c, double t) { return std::pow((1 + std::exp(-k[7] * (t - k[8]) + c)), -(k[6] / k[7])); }
+inline double fit_value(const double* k, double A, double E4, double E5, double Q) {
+	return A * (k[2] * ((1.0 - k[3]) * E4 + k[3])) * (E5 * (1 - Q)) + k[0];
+}
+
+/// f(x) with all factors computed (and remembered in `c`)
+inline double fit_eval_full(const LayerFitTarget& f, const AP& x, FitCache& c) {
+	const std::vector<double>& p = f.points();
+	const double* k = x.getK();
+	const double tc = fit_tail_c(k);
+	c.resize(p.size() / 2);
+	double sum = 0;
+	for (size_t i = 0, n = 0; i < p.size(); i += 2, ++n) {
+		const double t = p[i] - x.at;
+		c.A[n] = fit_A(k, t);
+		c.E4[n] = std::exp(-k[4] * t);
+		c.E5[n] = std::exp(-k[5] * t);
+		c.Q[n] = fit_Q(k, tc, t);
+		sum += sqr(fit_value(k, c.A[n], c.E4[n], c.E5[n], c.Q[n]) - p[i + 1]);
+	}
+	return sum;
+}
+
+/// f(x1) where x1 differs from the cached iterate only in coefficient `which`
+inline double fit_eval_perturbed(const LayerFitTarget& f, const AP& x1, size_t which, const FitCache& c) {
+	const std::vector<double>& p = f.points();
+	const double* k = x1.getK();
+	const double tc = (which == 6 || which == 7) ? fit_tail_c(k) : 0.0;
+	double sum = 0;
+	for (size_t i = 0, n = 0; i < p.size(); i += 2, ++n) {
+		const double t = p[i] - x1.at;
+		double A = c.A[n], E4 = c.E4[n], E5 = c.E5[n], Q = c.Q[n];
+		switch (which) {
+		case 1: A = fit_A(k, t); break;
+		case 4: E4 = std::exp(-k[4] * t); break;
+		case 5: E5 = std::exp(-k[5] * t); break;
+		case 6: case 7: Q = fit_Q(k, tc, t); break;
+		case 8: Q = fit_Q(k, std::log(std::pow(2, (k[7] / k[6])) - 1), t); break;
+		default: break;  // k0, k2, k3 only enter fit_value
+		}
+		sum += sqr(fit_value(k, A, E4, E5, Q) - p[i + 1]);
+	}
+	return sum;
+}
+
 /// sign-following steepest descent with per-coefficient step adaptation (nonlinearFit.h:92-168)
 inline int steepest_descent(const LayerFitTarget& f, AP& x0, const AP& d, double stepSize, double epsilon, int iterations) {
 	AP grad = x0, oldGrad = x0;
 	for (size_t i = 0; i < 9; ++i) oldGrad[i] = 0;
-	double y0 = f(x0);
+	FitCache cache, trial;
+	double y0 = fit_eval_full(f, x0, cache);
 	AP move = d;
 	for (; iterations > 0 && y0 > epsilon; --iterations) {
 		bool stepChange = false;
@@ -320,7 +379,7 @@ inline int steepest_descent(const LayerFitTarget& f, AP& x0, const AP& d, double
 			if (d[i] != 0) {
 				AP x1 = x0;
 				x1[i] += d[i] * .001;
-				grad[i] = (f(x1) - y0) / (d[i] * .001);
+				grad[i] = (fit_eval_perturbed(f, x1, i, cache) - y0) / (d[i] * .001);
 				if (grad[i] * oldGrad[i] < 0) { move[i] *= 0.5; stepChange = true; }
 				else if (std::fabs(grad[i]) > 0.75 * std::fabs(oldGrad[i])) move[i] *= 1.5;
 			} else grad[i] = 0;
@@ -328,8 +387,8 @@ inline int steepest_descent(const LayerFitTarget& f, AP& x0, const AP& d, double
 		oldGrad = grad;
 		AP x1 = x0;
 		for (size_t i = 0; i < 9; ++i) x1[i] -= stepSize * ((grad[i] > 0) ? move[i] : -move[i]);
-		const double y1 = f(x1);
-		if (y1 < y0) { y0 = y1; x0 = x1; }
+		const double y1 = fit_eval_full(f, x1, trial);
+		if (y1 < y0) { y0 = y1; x0 = x1; std::swap(cache, trial); }
 		else if (!stepChange) stepSize *= 0.5;
 	}
 	return iterations;
@@ -579,11 +638,13 @@ private:
 			borderAp(aps.front(), settings.baseAps.front(), solution, cursor, violation);
 			borderAp(aps[mid], settings.baseAps.back(), solution, cursor, violation);   // mid and epi both start from the LAST base ap
 			borderAp(aps.back(), settings.baseAps.back(), solution, cursor, violation);
-			fit.setBorderAps(aps.front(), aps.back());
+			// (the reference rebuilds the endo-mid connectors for every layer below mid; they only depend on
+			// the two border APs, so once is enough)
+			bool lowerReady = false;
 			for (size_t i = 1; i + 1 < n; ++i) {
 				if (i < mid) {
 					const double ratio = i / double(mid);
-					fit.setBorderAps(aps.front(), aps[mid]);
+					if (!lowerReady) { fit.setBorderAps(aps.front(), aps[mid]); lowerReady = true; }
 					fit.setupRatio(ratio);
 					aps[i] = aps[i - 1];
 					blend(aps[i], aps.front(), aps[mid], ratio);

@@ -127,3 +127,58 @@ def test_reference_glue_on_b200_simlib(testrun, golden):
     assert m.group(3) == "240.609"
     lines = open(os.path.join(testrun, "result.column")).read().split("\n")
     assert lines[2] == "#Time[ms]\t69.0145,128.133,-71.8312\t336.761,-112.667,183.886" and len(lines) == 403
+
+
+def test_excitation_sequence_dump_and_reload(built, tmp_path, model24, model24_delay):
+    """[output files] excitation sequence -> 3-decimal dump (simulator.cpp:71-106); [model] excitation
+    sequence -> loadExcitationSequence path (simulator.cpp:288-367) instead of the automaton."""
+    d = str(tmp_path)
+    ekgio.materialise_testrun(d, ini_edit=lambda s: s.replace("results filename = result.column",
+                                                              "results filename = result.column\nexcitation sequence = es_out.matrix"))
+    r = subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-out", "result"], cwd=d, capture_output=True, text=True)
+    assert "caught" not in r.stdout, r.stdout[-400:]
+    assert "calculating excitation sequence" in r.stderr
+    lines = open(os.path.join(d, "es_out.matrix")).read().split("\n")
+    assert lines[0].startswith("Excitation file") and lines[1] == "3D 93 x 124 x 124 tab"
+    dump = np.array(" ".join(lines[2:]).split(), dtype=np.float64).reshape(124, 124, 93)
+    assert np.abs(dump - model24_delay).max() <= 0.0005 + 1e-12 and dump[62, 62, 67] == 1.0
+    first = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in open(os.path.join(d, "result.column")).read().split("\n")[3:]]).T
+    # second run: read the (rounded) sequence back instead of computing it
+    ekgio.materialise_testrun(d, ini_edit=lambda s: s.replace("points = model_24_measuring_pos.txt",
+                                                              "points = model_24_measuring_pos.txt\nexcitation sequence = es_out.matrix"))
+    r = subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-out", "result"], cwd=d, capture_output=True, text=True)
+    assert "caught" not in r.stdout, r.stdout[-400:]
+    assert "loading excitation sequence" in r.stderr and "calculating excitation sequence" not in r.stderr
+    second = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in open(os.path.join(d, "result.column")).read().split("\n")[3:]]).T
+    # delays rounded to 1e-3 ms move the ECG a little, but only a little
+    assert 0 < np.abs(second - first).max() < 5e-2 * np.abs(first).max()
+
+
+def test_cli_layer_and_cell_ap_outputs(testrun, golden, model24, model24_delay):
+    """-out layer_aps / -out "cell_aps i j": the per-class AP table in first-seen raster order
+    (Simulation::setApIndices, simulator.cpp:561-621; sim.cpp:918-991)."""
+    from oracle import oracle
+    r = subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-out", "layer_aps", "-out", "cell_aps 0 5 50647 99999"],
+                       cwd=testrun, capture_output=True, text=True)
+    assert "caught" not in r.stdout, r.stdout[-400:]
+    i = list(golden["name"]).index("full1")
+    lay = open(os.path.join(testrun, "layer_aps.column")).read().split("\n")
+    assert lay[0] == "#Comment: " and lay[1].startswith("# ap_0 : k = [0, 2.5, 100, 0.9, 0.1, 0.00035813, 0.0890636, 0.0632915, 226.183]")
+    hdr = [ln for ln in lay if ln.startswith("#Time[ms]")][0].split("\t")
+    assert hdr[1:] == ["ap_%d" % n for n in range(24)]
+    rows = [ln for ln in lay if not ln.startswith("#")]
+    assert len(rows) == 700
+    v = np.array([float(x) for x in rows[123].split("\t")])
+    assert v[0] == 123.0
+    want = np.array([oracle.wohlfart_plus(golden["layer_k"][i][l], 123.0) for l in range(24)])
+    assert np.abs(v[1:] - want).max() < 1e-4 * np.abs(want).max()
+    cell = open(os.path.join(testrun, "cell_aps.column")).read().split("\n")
+    chdr = [ln for ln in cell if ln.startswith("#Time[ms]")][0].split("\t")
+    assert chdr[1:] == ["ap_0", "ap_5", "ap_50647"]          # 99999 is beyond the 50648 classes -> skipped
+    K, idx = oracle.ap_classes(model24["layers"], model24_delay, 24)
+    crow = np.array([float(x) for x in [ln for ln in cell if not ln.startswith("#")][200].split("\t")])
+    for col, cls in enumerate((0, 5, 50647)):
+        vox = np.argwhere(idx == cls)[0]
+        layer = int(model24["layers"][tuple(vox)] & 0x0FFF)
+        ref = oracle.lib().ekg_oracle_ap(golden["layer_k"][i][layer - 1].ctypes.data, float(model24_delay[tuple(vox)]), 200.0)
+        assert abs(crow[1 + col] - ref) < 1e-4 * max(1.0, abs(ref)), (cls, crow[1 + col], ref)
