@@ -324,6 +324,21 @@ def run_b200_arm(args):
                 "note": "same results within tolerance; executes 2 (or 0) MUFU ops per voxel-timestep instead of 7, so the "
                         "7-op roofline accounting does not apply to it"}
 
+    # -- BASELINE configs[0]: ONE simulation (B = 1), device time of the C-ABI call with resident inputs
+    single = {}
+    for nm, md in (("direct", ek.MODE_DIRECT), ("hoisted", ek.MODE_HOISTED)):
+        for _ in range(3):
+            model.simulate_device(d_k.data_ptr(), d_leads.data_ptr(), 1, L, d_ecg.data_ptr(), "3D4", 100.0, 1.0, float(T_FULL), mode=md, stream=stream)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(20):
+            model.simulate_device(d_k.data_ptr(), d_leads.data_ptr(), 1, L, d_ecg.data_ptr(), "3D4", 100.0, 1.0, float(T_FULL), mode=md, stream=stream)
+        s1.record()
+        torch.cuda.synchronize()
+        single[nm + "_ms"] = s0.elapsed_time(s1) / 20
+    single["reference_cpu_s"] = 205.28  # SURVEY.md section 6, measured with the compiled reference on one core
+
     # -- whole pipeline, parameter vectors -> criteria: host glue (C++, threads) + one GPU batch
     pipeline = None
     if world == 1 and not args.no_pipeline:
@@ -375,7 +390,9 @@ def run_b200_arm(args):
                       "-> frac %.3f" % (sm_mhz, peak_gops_max, achieved_gops / peak_gops_max),
         "algorithmic_ops_per_voxel_timestep": SFU_OPS_PER_VTS,
         "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch at
+        # B = 256 (profiles/r01_ecg_direct_v5_b256_ncu_full.txt): 14.7 MB read + 192.4 MB written (f64 partials)
+        "traffic": 207.1e6 if (B == 256 and mode == ek.MODE_DIRECT) else None,
         "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                 "note": "algorithmic bytes: 16 B/voxel per individual + f64 partials; the kernel is MUFU-bound, not HBM-bound"},
@@ -396,7 +413,7 @@ def run_b200_arm(args):
         "automaton": {"ms": automaton_ms, "sweeps": sweeps, "bit_exact_vs_reference": bool(act_ok),
                       "edges_per_s": 26 * N_VOX / (automaton_ms * 1e-3)},
         "parity_max_err_of_peak": parity,
-        "fast_path": fast, "pipeline": pipeline,
+        "fast_path": fast, "pipeline": pipeline, "single_sim": single,
     }
 
     if not args.no_cpu_baseline and world == 1:

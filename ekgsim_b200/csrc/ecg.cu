@@ -67,7 +67,7 @@ struct RowLayout {
 // in the first version of this kernel).  A tile therefore spans up to kMaxVecPerTile parameter
 // vectors; phase A computes the lead-field coefficients for each of them.
 template <int MODE, int NL>
-__global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
+__global__ void __launch_bounds__(kEcgThreads, MODE == MODE_DIRECT ? 5 : 4) ecg_kernel(const EcgArgs a) {
 	constexpr int ROW = RowLayout<MODE, NL>::kFloats;
 	__shared__ __align__(16) float s_vox[kSmemRows * ROW];
 	__shared__ float2 s_lead[kMaxVecPerTile * NL * 3];  // lead coordinate as fp32 hi + lo
@@ -388,8 +388,34 @@ static int launch_ecg(const EcgArgs& a, dim3 grid, int threads, cudaStream_t st)
 	return EKG_OK;
 }
 
+static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
+                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st);
+
+// Large batches are cut into sub-batches so that the f64 partial-sum scratch stays below ~1 GiB.
 int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
             double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st) {
+	if (B <= 0 || L <= 0) return fail(EKG_E_INVALID, "B and n_leads must be positive");
+	if (!(t_step > 0) || !(total_time > 0)) return fail(EKG_E_INVALID, "t_step and total_time must be positive");
+	const int64_t T = (int64_t)ceil(total_time / t_step);
+	if (T <= 0 || T > (1 << 24)) return fail(EKG_E_INVALID, "bad number of time steps");
+	// at ~100 waves the segment count is about (592 * 96) / (B * T / 256); partial bytes = segs * B * L * T * 8
+	const int64_t per_vector = std::max<int64_t>(L * T * 8, 1);
+	int64_t sub = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)1 << 30) / (per_vector * 160)));
+	sub = std::min<int64_t>(sub, 16384);
+	int64_t launches = 0;
+	for (int64_t b0 = 0; b0 < B; b0 += sub) {
+		const int64_t nb = std::min(sub, B - b0);
+		int rc = run_ecg_one(m, d_layer_k + b0 * m->n_layers * 9, d_leads + b0 * L * 3, nb, L, nbhd, t_start, t_step, total_time, flags,
+		                     d_ecg + b0 * L * T, st);
+		if (rc) return rc;
+		launches += m->last_launches;
+	}
+	m->last_launches = launches;
+	return EKG_OK;
+}
+
+static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
+                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st) {
 	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence: call ekg_model_activation or ekg_model_set_activation first");
 	if (B <= 0 || L <= 0) return fail(EKG_E_INVALID, "B and n_leads must be positive");
 	if (B > 65535) return fail(EKG_E_UNSUPPORTED, "at most 65535 parameter vectors per call");
@@ -442,7 +468,7 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 	}
 	if (B * T >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "B * n_steps must be below 2^31");
 	// ~100 waves of CTAs: the tail of the last wave costs about 1/waves of the launch
-	const int64_t target_ctas = (int64_t)m->sm_count * 4 * 96;
+	const int64_t target_ctas = (int64_t)m->sm_count * (mode == EKG_MODE_DIRECT ? 5 : 4) * 96;
 	int64_t want_segs = (target_ctas + m->n_tiles - 1) / m->n_tiles;
 	int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
 	seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));

@@ -4,7 +4,7 @@
 // hot-path headers (simlib/sim_lib.h, simulator.h, matrix.h, Wohlfart.h) and of simlib/support.h, pulls
 // the reference's non-hot-path helpers that its glue expects to arrive through them (Ini.h,
 // columnFile.h), and then provides the same names from ekgsim_b200/host/sim_lib.h.
-// Used by oracle/Makefile target `refglue` (test harness) and described in INTEGRATION.md section 2.
+// Used by the test harness that builds the reference glue on top of this facade.
 #pragma once
 #define SIM_LIB_H_INCLUDED
 #define SIMULATOR_H_INCLUDED

@@ -7,7 +7,7 @@ extern "C" {
 static thread_local std::string g_host_error;
 const char* ekg_host_last_error() { return g_host_error.c_str(); }
 
-/// AP formula (host f64), for cross-checking against the oracle
+/// AP formula (host f64), exposed for cross-checks in the tests
 double ekg_host_wohlfart_plus(const double* k, double t) {
 	SimLib::WohlfartPlus w(k);
 	return w[t];

@@ -255,3 +255,36 @@ def test_two_gpus_slabs_and_individuals(built, model24, model24_delay):
     assert (np.abs(parts - g["ecg"][:6]) / g["peak_full"][:6, :, None]).max() < ECG_TOL
     m0.close()
     m1.close()
+
+
+def test_ecg_large_batch_is_cut_into_sub_batches(built):
+    """B * L * T large enough that the library splits the batch (partial-sum scratch cap): vectors of
+    the later sub-batches must come out exactly like the same vectors evaluated alone."""
+    layers, transfer, leads = synth.small_heart(seed=33, shape=(10, 11, 12), n_layers=3)
+    nl = int((layers & 0xFFF).max())
+    B = 260
+    k = synth.layer_params(nl, seed=77, batch=B)
+    delay = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    m.set_activation(delay)
+    ecg = m.simulate(k, leads, "3D4", 0.0, 0.25, 800.0, mode=1)      # T = 3200 -> sub-batches of ~131 vectors
+    assert ecg.shape == (B, 2, 3200)
+    for b in (0, 130, 131, 259):
+        ref = oracle.run_factored(layers, delay, k[b], leads, "3D4", 0.0, 0.25, 800.0)
+        assert rel_err(ecg[b], ref) < ECG_TOL, b
+    m.close()
+
+
+def test_ecg_model24_batch_sample_vs_oracle(gpu_model24, model24, model24_delay):
+    """A spread of the 256-vector batch at full length against the (reference-pinned) oracle."""
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    pick = [5, 40, 77, 101, 150, 199, 230, 255]
+    gpu_model24.set_activation(model24_delay)
+    for mode in (1, 2):
+        ecg = gpu_model24.simulate(g["layer_k"], g["leads_zyx"], "3D4", 100.0, 1.0, 400.0, mode=mode)
+        worst = 0.0
+        for b in pick:
+            ref = oracle.run_factored(model24["layers"], model24_delay, g["layer_k"][b], g["leads_zyx"][b], "3D4", 100.0, 1.0, 400.0)
+            worst = max(worst, rel_err(ecg[b], ref))
+        print("batch sample mode %d: worst %.3g of peak" % (mode, worst))
+        assert worst < ECG_TOL
