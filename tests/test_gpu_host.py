@@ -182,3 +182,21 @@ def test_cli_layer_and_cell_ap_outputs(testrun, golden, model24, model24_delay):
         layer = int(model24["layers"][tuple(vox)] & 0x0FFF)
         ref = oracle.lib().ekg_oracle_ap(golden["layer_k"][i][layer - 1].ctypes.data, float(model24_delay[tuple(vox)]), 200.0)
         assert abs(crow[1 + col] - ref) < 1e-4 * max(1.0, abs(ref)), (cls, crow[1 + col], ref)
+
+
+def test_reference_optimizer_drives_the_b200_simlib(built, tmp_path):
+    """BASELINE config 5 in miniature: the reference's own AMS-DEMO optimizer (unmodified main.cpp, sequential
+    -DNO_MPI path, main.cpp:283-361) evaluating its population through the B200 simulator library.
+    Population 12, 2 generations; checks that the run completes and logs every evaluation."""
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "ekgSim_refglue_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ekgSim_refglue_b200 not built (needs /root/reference at build time)")
+    d = str(tmp_path)
+    ekgio.materialise_testrun(d, ini_edit=lambda s: s.replace("population size = 100", "population size = 12")
+                              .replace("number of generations = 100", "number of generations = 2"))
+    r = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "caught" not in r.stdout, r.stdout[-600:]
+    assert r.stdout.rstrip().endswith("All done")
+    ev = [ln for ln in open(os.path.join(d, "evaluations.txt")).read().split("\n") if ln and not ln.startswith("#")]
+    assert len(ev) >= 24, len(ev)          # initial population + the offspring of the generations
+    assert os.path.exists(os.path.join(d, "individuals.txt"))
