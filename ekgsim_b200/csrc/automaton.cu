@@ -13,14 +13,16 @@
 //
 // Two kernels, both persistent cooperative grids:
 //
-//  * automaton_brick_kernel (default) -- frontier based.  The grid is tiled by 8x8x8 bricks; a work
-//    queue holds the bricks whose surroundings changed in the previous round (initially the bricks
-//    of the start voxels).  A CTA takes a brick, stages it with a one-voxel halo in shared memory
-//    (1000 f64 times + 1000 u8 layers), relaxes it to a LOCAL fixed point with in-place sweeps in
-//    shared memory, writes the improved times back and queues the neighbouring bricks that touch a
-//    changed face/edge/corner voxel for the next round.  One grid.sync per round; the number of
-//    rounds is the number of brick hops of the slowest wavefront path, and only the bricks on the
-//    wavefront are touched in a round.
+//  * automaton_brick_kernel -- frontier based.  The grid is tiled by 4x4x4 bricks; a work queue holds
+//    the bricks whose surroundings changed in the previous round (initially the bricks of the start
+//    voxels).  ONE WARP takes a brick, stages it with a one-voxel halo in shared memory (216 f64
+//    times + 216 u8 layers, two interior voxels per lane), relaxes it to a LOCAL fixed point with
+//    in-place sweeps synchronised by __syncwarp only, writes the improved times back and queues a
+//    neighbouring brick if one of its cells would improve through a changed voxel.  There are no
+//    grid-wide rounds: warps pull brick ids from a lock-free ring (head/tail counters, a `pending`
+//    count of queued + in-work bricks for termination), so the wavefront advances at the pace of
+//    its own dependencies; write-back uses a 64-bit atomicMin because two warps may hold the same
+//    brick at once.
 //  * automaton_kernel (EKGSIM_B200_AUTOMATON=sweep) -- the plain label-correcting sweep over all
 //    occupied voxels, kept as the simple cross-check.
 //
@@ -29,6 +31,7 @@
 // Working set on model_24: 1.6 MB padded u8 layers + 13 MB padded f64 times -> L2 resident.
 
 #include <cooperative_groups.h>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -76,132 +79,157 @@ __global__ void __launch_bounds__(256) automaton_kernel(AutoArgs a) {
 	(void)inf;
 }
 
-__global__ void __launch_bounds__(256) automaton_brick_kernel(BrickArgs a) {
-	cg::grid_group grid = cg::this_grid();
-	__shared__ double s_t[kBrickCells];
-	__shared__ uint8_t s_l[kBrickCells];
-	__shared__ uint8_t s_todo[2][kBrickCells];  // cell must be re-evaluated in the sweep of that parity
-	__shared__ unsigned s_mask;
+// Work queue of the frontier automaton: a ring of brick ids.  A brick is in the ring at most once
+// (flag[b] = 1 from push to pop), so n_live slots can never overflow.  `pending` counts bricks that
+// are queued or being processed; it can only reach 0 when the whole field is at its fixed point.
+__device__ __forceinline__ void brick_push(const BrickArgs& a, int b) {
+	if (atomicExch(a.flag + b, 1) == 0) {
+		atomicAdd(a.counters + 2, 1);                                   // pending
+		const unsigned pos = atomicAdd((unsigned*)a.counters + 1, 1u);  // tail
+		atomicExch(a.queue + (pos & a.qmask), b);                       // publish (slot was -1)
+	}
+}
+
+template <int NBR>
+__global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(BrickArgs a) {
+	__shared__ double s_t_all[kBrickWarps][kBrickCells];
+	__shared__ uint8_t s_l_all[kBrickWarps][kBrickCells];
 	extern __shared__ double s_w[];  // edge-weight table [nl1][nl1][3] when it fits (a.w_in_smem)
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (a.w_in_smem) {
-		for (int i = tid; i < a.nl1 * a.nl1 * 3; i += 256) s_w[i] = __ldg(a.wtab + i);
+		for (int i = tid; i < a.nl1 * a.nl1 * 3; i += blockDim.x) s_w[i] = __ldg(a.wtab + i);
 		__syncthreads();
 	}
 	const double* __restrict__ wt = a.w_in_smem ? s_w : a.wtab;
-	constexpr int kOwn = kBrick * kBrick * kBrick / 256;  // interior voxels per thread (2)
-	constexpr int kInnerCap = 96;
+	double* s_t = s_t_all[warp];
+	uint8_t* s_l = s_l_all[warp];
+	constexpr int kOwn = kBrick * kBrick * kBrick / 32;  // interior voxels per lane (2)
+	constexpr int kInnerCap = 256;
+	constexpr unsigned kFull = 0xffffffffu;
 	int loc[kOwn], cz[kOwn], cy[kOwn], cx[kOwn];
 #pragma unroll
 	for (int o = 0; o < kOwn; ++o) {
-		const int v = tid + o * 256;
-		cz[o] = v >> 6; cy[o] = (v >> 3) & 7; cx[o] = v & 7;
+		const int v = lane + o * 32;
+		cz[o] = v / (kBrick * kBrick); cy[o] = (v / kBrick) % kBrick; cx[o] = v % kBrick;
 		loc[o] = ((cz[o] + 1) * kBrickHalo + (cy[o] + 1)) * kBrickHalo + (cx[o] + 1);
 	}
 	const double inf = __longlong_as_double(0x7ff0000000000000LL);
-	int round = 0;
-	int visits = 0;
-	for (; round < a.max_rounds; ++round) {
-		const int cur = round % 3, nxt = (round + 1) % 3, old = (round + 2) % 3;
-		const int par = round & 1;
-		const int n_active = __ldcg(a.counters + cur);
-		if (n_active == 0) break;
-		if (blockIdx.x == 0 && tid == 0) a.counters[old] = 0;  // consumed last round, appended to again next round
-		for (int q = blockIdx.x; q < n_active; q += gridDim.x) {
-			const int b = __ldcg(a.queue + (size_t)cur * a.n_live + q);
-			const uint32_t origin = __ldg(a.origin + b);
-			if (tid == 0) { a.flag[(size_t)par * a.n_live + b] = 0; s_mask = 0; ++visits; }
-			for (int i = tid; i < kBrickCells; i += 256) {
-				const int lz = i / (kBrickHalo * kBrickHalo), ly = (i / kBrickHalo) % kBrickHalo, lx = i % kBrickHalo;
-				const uint32_t p = origin + (uint32_t)(((lz - 1) * a.pY + (ly - 1)) * a.pX + (lx - 1));
-				s_l[i] = __ldg(a.layer + p);
-				s_t[i] = __ldcg(a.time + p);
-				s_todo[0][i] = 1;  // first sweep looks at every voxel, later ones only next to what changed
-				s_todo[1][i] = 0;
+	const int nl3 = a.nl1 * 3;
+	int visits = 0, sweeps = 0;
+	volatile int* vq = a.queue;
+	volatile int* vpending = a.counters + 2;
+
+	for (;;) {   // one warp per brick, no barrier wider than the warp anywhere in here
+		int b = -1;
+		if (lane == 0) {
+			const unsigned pos = atomicAdd((unsigned*)a.counters + 0, 1u);   // head: claim a ring position
+			for (unsigned spins = 0;; ++spins) {
+				b = vq[pos & a.qmask];
+				if (b >= 0) { vq[pos & a.qmask] = -1; break; }
+				if (*vpending == 0) { b = -2; break; }                       // nothing queued, nobody working: done
+				// a warp that found nothing for seconds retires (never spins forever, whatever happens);
+				// the host reports non-convergence if work was still pending when the last warp left
+				if (spins > (1u << 25)) { b = -2; break; }
+				__nanosleep(40);
 			}
-			__syncthreads();
-			double t_init[kOwn];
-			int lv[kOwn];
+		}
+		b = __shfl_sync(kFull, b, 0);
+		if (b < 0) break;
+		int first_i = 0;   // start bricks: reached voxels count as changed on the first visit
+		if (lane == 0) {
+			first_i = a.first_visit[b];
+			if (first_i) a.first_visit[b] = 0;
+			atomicExch(a.flag + b, 0);   // from here on, a neighbour that improves our halo queues us again
+			__threadfence();
+			++visits;
+		}
+		const bool first = __shfl_sync(kFull, first_i, 0) != 0;
+		const uint32_t origin = __ldg(a.origin + b);
+		for (int i = lane; i < kBrickCells; i += 32) {
+			const int lz = i / (kBrickHalo * kBrickHalo), ly = (i / kBrickHalo) % kBrickHalo, lx = i % kBrickHalo;
+			const uint32_t p = origin + (uint32_t)(((lz - 1) * a.pY + (ly - 1)) * a.pX + (lx - 1));
+			s_l[i] = __ldg(a.layer + p);
+			s_t[i] = __ldcg(a.time + p);
+		}
+		__syncwarp();
+		double t_init[kOwn];
+		int lv[kOwn];
 #pragma unroll
-			for (int o = 0; o < kOwn; ++o) { t_init[o] = s_t[loc[o]]; lv[o] = s_l[loc[o]]; }
-			int it = 0;
-			for (; it < kInnerCap; ++it) {
-				bool ch = false;
-				uint8_t* todo = s_todo[it & 1];
-				uint8_t* todo_next = s_todo[(it & 1) ^ 1];
-#pragma unroll
-				for (int o = 0; o < kOwn; ++o) {
-					if (lv[o] == 0 || !todo[loc[o]]) continue;
-					todo[loc[o]] = 0;
-					const double tv = s_t[loc[o]];
-					double best = tv;
-#pragma unroll 2
-					for (int k = 0; k < a.n_nbr; ++k) {
-						const int qq = loc[o] - a.loff[k];
-						const int lu = s_l[qq];
-						if (lu == 0) continue;
-						const double tu = s_t[qq];
-						if (tu >= best) continue;
-						const double cand = __dadd_rn(tu, wt[(lu * a.nl1 + lv[o]) * 3 + a.sq[k]]);
-						if (cand < best) best = cand;
-					}
-					if (best < tv) {
-						s_t[loc[o]] = best;
-						ch = true;
-						// a voxel's minimum can only move when a neighbour's time moved: wake the neighbours
-						for (int k = 0; k < a.n_nbr; ++k) todo_next[loc[o] - a.loff[k]] = 1;
-					}
-				}
-				if (!__syncthreads_or(ch)) break;
-			}
-			// write back what improved; queue a neighbouring brick only if one of ITS cells (our halo copy of
-			// it, never smaller than its current value) would actually improve through one of our changed
-			// voxels -- otherwise bricks that already hold better times would be revisited for nothing.
-			// In round 0 every reached voxel counts as changed (the start voxel itself never "improves").
-			unsigned bits = 0;
+		for (int o = 0; o < kOwn; ++o) { t_init[o] = s_t[loc[o]]; lv[o] = s_l[loc[o]]; }
+		// relax the brick to its local fixed point: in-place sweeps, values only decrease
+		for (int it = 0; it < kInnerCap; ++it) {
+			bool ch = false;
 #pragma unroll
 			for (int o = 0; o < kOwn; ++o) {
-				const double tf = s_t[loc[o]];
 				if (lv[o] == 0) continue;
-				const bool improved = tf < t_init[o];
-				if (improved) __stcg(a.time + origin + (uint32_t)((cz[o] * a.pY + cy[o]) * a.pX + cx[o]), tf);
-				const bool on_face = cz[o] == 0 || cz[o] == kBrick - 1 || cy[o] == 0 || cy[o] == kBrick - 1 || cx[o] == 0 || cx[o] == kBrick - 1;
-				if (!on_face || !(improved || (round == 0 && tf < inf))) continue;
-				for (int k = 0; k < a.n_nbr; ++k) {
+				// branch-free: empty cells have layer 0 whose weight row is +inf, unreached cells hold +inf;
+				// all NBR loads are independent so their latencies overlap
+				const double* __restrict__ wv = wt + lv[o] * 3;
+				const double tv = s_t[loc[o]];
+				double best = tv;
+#pragma unroll
+				for (int k = 0; k < NBR; ++k) {
 					const int qq = loc[o] - a.loff[k];
-					const int nz = cz[o] - a.dz[k], ny = cy[o] - a.dy[k], nx = cx[o] - a.dx[k];  // neighbour = index - dif
-					const int dz = nz < 0 ? -1 : nz >= kBrick ? 1 : 0;
-					const int dy = ny < 0 ? -1 : ny >= kBrick ? 1 : 0;
-					const int dx = nx < 0 ? -1 : nx >= kBrick ? 1 : 0;
-					if (!(dz | dy | dx)) continue;  // interior cell
-					const int lu = s_l[qq];
-					if (lu == 0) continue;
-					const double cand = __dadd_rn(tf, wt[(lv[o] * a.nl1 + lu) * 3 + a.sq[k]]);  // we excite it: T[ours][its]
-					if (cand < s_t[qq]) {
-						const int id = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
-						bits |= 1u << (id > 13 ? id - 1 : id);
-					}
+					const double cand = __dadd_rn(s_t[qq], wv[(int)s_l[qq] * nl3 + a.sq[k]]);
+					best = fmin(best, cand);
+				}
+				if (best < tv) { s_t[loc[o]] = best; ch = true; }
+			}
+			__syncwarp();
+			++sweeps;
+			if (!__any_sync(kFull, ch)) break;
+		}
+		// Write back what improved (atomicMin on the bit pattern: positive doubles order like integers, and
+		// two warps may hold the same brick at once).  Queue a neighbouring brick only if one of ITS cells
+		// (our halo copy of it, never smaller than its current value) would improve through a changed voxel.
+		unsigned bits = 0;
+#pragma unroll
+		for (int o = 0; o < kOwn; ++o) {
+			const double tf = s_t[loc[o]];
+			if (lv[o] == 0) continue;
+			const bool improved = tf < t_init[o];
+			if (improved)
+				atomicMin((unsigned long long*)(a.time + origin + (uint32_t)((cz[o] * a.pY + cy[o]) * a.pX + cx[o])),
+				          (unsigned long long)__double_as_longlong(tf));
+			const bool on_face = cz[o] == 0 || cz[o] == kBrick - 1 || cy[o] == 0 || cy[o] == kBrick - 1 || cx[o] == 0 || cx[o] == kBrick - 1;
+			if (!on_face || !(improved || (first && tf < inf))) continue;
+#pragma unroll
+			for (int k = 0; k < NBR; ++k) {
+				const int qq = loc[o] - a.loff[k];
+				const int nz = cz[o] - a.dz[k], ny = cy[o] - a.dy[k], nx = cx[o] - a.dx[k];  // neighbour = index - dif
+				const int dz = nz < 0 ? -1 : nz >= kBrick ? 1 : 0;
+				const int dy = ny < 0 ? -1 : ny >= kBrick ? 1 : 0;
+				const int dx = nx < 0 ? -1 : nx >= kBrick ? 1 : 0;
+				if (!(dz | dy | dx)) continue;  // interior cell
+				const int lu = s_l[qq];
+				if (lu == 0) continue;
+				const double cand = __dadd_rn(tf, wt[(lv[o] * a.nl1 + lu) * 3 + a.sq[k]]);  // we excite it: T[ours][its]
+				if (cand < s_t[qq]) {
+					const int id = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
+					bits |= 1u << (id > 13 ? id - 1 : id);
 				}
 			}
-			if (bits) atomicOr(&s_mask, bits);
-			__syncthreads();
-			const int np = par ^ 1;
-			if (tid < 26 && ((s_mask >> tid) & 1u)) {
-				const int nb = __ldg(a.nbr + (size_t)b * 26 + tid);
-				if (nb >= 0 && atomicExch(a.flag + (size_t)np * a.n_live + nb, 1) == 0)
-					a.queue[(size_t)nxt * a.n_live + atomicAdd(a.counters + nxt, 1)] = nb;
-			}
-			if (tid == 26 && it == kInnerCap) {  // not yet locally converged: come back next round
-				if (atomicExch(a.flag + (size_t)np * a.n_live + b, 1) == 0)
-					a.queue[(size_t)nxt * a.n_live + atomicAdd(a.counters + nxt, 1)] = b;
-			}
-			__syncthreads();  // s_mask / s_t are reused by the next brick
 		}
-		__threadfence();
-		grid.sync();
+		bits = __reduce_or_sync(kFull, bits);
+		__threadfence();   // our improved times are visible before anyone is told to look at them
+		// push the neighbours that need a visit: one tail reservation and one pending update per warp
+		// (head, tail and pending are single hot addresses; per-brick atomics on them would serialise)
+		int nb = -1;
+		if (lane < 26 && ((bits >> lane) & 1u)) {
+			nb = __ldg(a.nbr + (size_t)b * 26 + lane);
+			if (nb >= 0 && atomicExch(a.flag + nb, 1) != 0) nb = -1;   // already queued
+		}
+		const unsigned pushers = __ballot_sync(kFull, nb >= 0);
+		const int n_push = __popc(pushers);
+		unsigned base = 0;
+		if (lane == 0) {
+			if (n_push != 1) atomicAdd(a.counters + 2, n_push - 1);        // pending += pushes - (this brick done)
+			if (n_push) base = atomicAdd((unsigned*)a.counters + 1, (unsigned)n_push);
+		}
+		base = __shfl_sync(kFull, base, 0);
+		if (nb >= 0) atomicExch(a.queue + ((base + __popc(pushers & ((1u << lane) - 1u))) & a.qmask), nb);
 	}
-	if (tid == 0 && visits) atomicAdd(a.counters + 4, visits);
-	if (blockIdx.x == 0 && tid == 0) a.counters[3] = round;
+	if (lane == 0 && visits) { atomicAdd(a.counters + 4, visits); atomicAdd(a.counters + 5, sweeps); }
 }
 
 // Negative weights would make "tu >= best -> skip" wrong and Dijkstra itself ill-defined; the
@@ -222,13 +250,11 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out);
 int run_automaton(ekg_model* m, int64_t* sweeps_out) {
 	cudaStream_t st = m->stream;
 	const int64_t npad = m->pZ * m->pY * m->pX;
-	// Small models (time field resident in L2) relax fastest with plain sweeps; once the dense field
-	// outgrows L2 every sweep streams it from HBM and the brick frontier wins.  EKGSIM_B200_AUTOMATON
-	// = sweep | bricks overrides the choice.
+	// The brick frontier is the default (model_24: 1.2 ms vs 3.4 ms for sweeps; 4x heart: 40 ms vs 417 ms);
+	// EKGSIM_B200_AUTOMATON=sweep selects the plain sweeps as a cross-check.
 	const char* sel = getenv("EKGSIM_B200_AUTOMATON");
-	bool sweep = (size_t)npad * 9 <= (size_t)96 << 20;
+	bool sweep = false;
 	if (sel && std::string(sel) == "sweep") sweep = true;
-	if (sel && std::string(sel) == "bricks") sweep = false;
 	init_time_kernel<<<m->sm_count * 4, 256, 0, st>>>(m->d_time_pad, npad);
 	EKG_CUDA(cudaGetLastError());
 
@@ -288,23 +314,27 @@ int run_automaton(ekg_model* m, int64_t* sweeps_out) {
 static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
+	int64_t cap = 1;
+	while (cap < std::max<int64_t>(n, 2)) cap <<= 1;
+	// state = flag[n] | first_visit[n] | ring[cap] | counters[8]   (allocated as 5n + 8 ints; cap <= 2n)
 	int* flag = m->d_brick_state;
-	int* queue = flag + 2 * n;
-	int* counters = queue + 3 * n;
-	EKG_CUDA(cudaMemsetAsync(m->d_brick_state, 0, ((size_t)n * 5 + 8) * sizeof(int), st));
-	// round 0 processes the bricks of the start voxels
-	std::vector<int> q0(m->h_start_bricks.begin(), m->h_start_bricks.end());
-	const int n0 = (int)q0.size();
-	EKG_CUDA(cudaMemcpyAsync(queue, q0.data(), q0.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-	EKG_CUDA(cudaMemcpyAsync(counters, &n0, sizeof(int), cudaMemcpyHostToDevice, st));
-	EKG_CUDA(cudaStreamSynchronize(st));  // pageable sources
+	int* first = flag + n;
+	int* ring = first + n;
+	int* counters = ring + cap;
+	std::vector<int> h((size_t)(2 * n + cap + 8), 0);
+	std::fill(h.begin() + 2 * n, h.begin() + 2 * n + cap, -1);
+	int n0 = 0;
+	for (int32_t b : m->h_start_bricks) { h[(size_t)b] = 1; h[(size_t)(n + b)] = 1; h[(size_t)(2 * n + n0++)] = b; }
+	h[(size_t)(2 * n + cap + 1)] = n0;   // tail
+	h[(size_t)(2 * n + cap + 2)] = n0;   // pending
+	EKG_CUDA(cudaMemcpyAsync(m->d_brick_state, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+	EKG_CUDA(cudaStreamSynchronize(st));  // pageable source
 
 	BrickArgs a{};
 	a.layer = m->d_layer_pad; a.time = m->d_time_pad; a.wtab = m->d_wtab;
 	a.origin = m->d_brick_origin; a.nbr = m->d_brick_nbr;
-	a.flag = flag; a.queue = queue; a.counters = counters;
+	a.flag = flag; a.first_visit = first; a.queue = ring; a.counters = counters; a.qmask = (uint32_t)(cap - 1);
 	a.n_live = (int32_t)n; a.nl1 = m->n_layers + 1; a.pY = (int32_t)m->pY; a.pX = (int32_t)m->pX;
-	a.max_rounds = 1 << 20;
 	NbrTable nb;
 	make_nbr_table(m->Z > 1 ? EKG_NBHD_3D8 : EKG_NBHD_2D8, &nb);  // simulator.cpp:251-254
 	a.n_nbr = nb.n;
@@ -317,17 +347,21 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	a.w_in_smem = w_bytes <= 32 * 1024;
 	const size_t dyn = a.w_in_smem ? w_bytes : 0;
 	int per_sm = 0;
-	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, automaton_brick_kernel, 256, dyn));
+	const int threads = 32 * kBrickWarps;
+	void* kfun = a.n_nbr == 26 ? (void*)automaton_brick_kernel<26> : (void*)automaton_brick_kernel<8>;
+	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
-	const int grid = (int)std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>(n, 1));
+	// every CTA must be resident (waiting warps spin on the ring): never launch more than fit
+	const int grid = (int)std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>((n + kBrickWarps - 1) / kBrickWarps, 1));
 	void* kargs[] = {&a};
-	EKG_CUDA(cudaLaunchCooperativeKernel((void*)automaton_brick_kernel, dim3(grid), dim3(256), kargs, dyn, st));
-	int h[8] = {0};
-	EKG_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, st));
+	EKG_CUDA(cudaLaunchCooperativeKernel(kfun, dim3(grid), dim3(threads), kargs, dyn, st));
+	int hc[8] = {0};
+	EKG_CUDA(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, st));
 	EKG_CUDA(cudaStreamSynchronize(st));
-	if (rounds_out) *rounds_out = h[3];
-	m->last_brick_visits = h[4];
-	if (h[3] >= a.max_rounds) return fail(EKG_E_STATE, "activation automaton did not converge");
+	if (rounds_out) *rounds_out = hc[4];   // brick visits (there are no global rounds in the work-queue scheme)
+	m->last_brick_visits = hc[4];
+	if (getenv("EKGSIM_B200_DEBUG")) fprintf(stderr, "automaton bricks: visits %d inner sweeps %d pushes %d\n", hc[4], hc[5], hc[1]);
+	if (hc[2] != 0) return fail(EKG_E_STATE, "activation automaton did not converge");
 	return EKG_OK;
 }
 

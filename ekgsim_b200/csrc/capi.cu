@@ -171,7 +171,7 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 	ekg_model* m = new ekg_model();
 	m->device = device;
 	m->Z = Z; m->Y = Y; m->X = X;
-	// zero border of one voxel, extents rounded up to whole 8^3 bricks (brick-frontier automaton)
+	// zero border of one voxel, extents rounded up to a multiple of 8 (whole bricks for the frontier automaton)
 	m->pZ = (Z + 7) / 8 * 8 + 2; m->pY = (Y + 7) / 8 * 8 + 2; m->pX = (X + 7) / 8 * 8 + 2;
 	const int64_t n = Z * Y * X;
 	m->h_layer.resize((size_t)n);
@@ -234,15 +234,16 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_wtab, w.size() * 8));
 		if (upload(m, m->d_wtab, w.data(), w.size() * 8)) { free_model(m); return EKG_E_CUDA; }
 	}
-	// live bricks (8^3 tiles holding at least one occupied voxel), their origins and 26 neighbours
+	// live bricks (kBrick^3 tiles holding at least one occupied voxel), their origins and 26 neighbours
 	{
-		const int64_t bZ = (Z + 7) / 8, bY = (Y + 7) / 8, bX = (X + 7) / 8;
+		const int64_t kb = kBrick;
+		const int64_t bZ = (Z + kb - 1) / kb, bY = (Y + kb - 1) / kb, bX = (X + kb - 1) / kb;
 		std::vector<int32_t> index((size_t)(bZ * bY * bX), -1);
 		std::vector<uint32_t> origin;
 		for (int64_t z = 0; z < Z; ++z) for (int64_t y = 0; y < Y; ++y) for (int64_t x = 0; x < X; ++x) {
 			if (!m->h_layer[(size_t)((z * Y + y) * X + x)]) continue;
-			int32_t& bi = index[(size_t)(((z / 8) * bY + y / 8) * bX + x / 8)];
-			if (bi < 0) { bi = (int32_t)origin.size(); origin.push_back((uint32_t)pad_index(m, z / 8 * 8, y / 8 * 8, x / 8 * 8)); }
+			int32_t& bi = index[(size_t)(((z / kb) * bY + y / kb) * bX + x / kb)];
+			if (bi < 0) { bi = (int32_t)origin.size(); origin.push_back((uint32_t)pad_index(m, z / kb * kb, y / kb * kb, x / kb * kb)); }
 		}
 		const int64_t nb = (int64_t)origin.size();
 		std::vector<int32_t> nbr((size_t)std::max<int64_t>(nb, 1) * 26, -1);
@@ -259,7 +260,7 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		}
 		for (int64_t r : m->h_starts) {
 			const int64_t z = r / (Y * X), y = (r / X) % Y, x = r % X;
-			const int32_t bi = index[(size_t)(((z / 8) * bY + y / 8) * bX + x / 8)];
+			const int32_t bi = index[(size_t)(((z / kBrick) * bY + y / kBrick) * bX + x / kBrick)];
 			if (std::find(m->h_start_bricks.begin(), m->h_start_bricks.end(), bi) == m->h_start_bricks.end()) m->h_start_bricks.push_back(bi);
 		}
 		m->n_bricks = nb;

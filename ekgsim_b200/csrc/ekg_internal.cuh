@@ -83,10 +83,11 @@ struct AutoArgs {
 	int32_t max_sweeps;
 };
 
-// Brick-frontier automaton (automaton.cu): the padded grid is tiled by 8x8x8 bricks.
-constexpr int kBrick = 8;
-constexpr int kBrickHalo = kBrick + 2;                                // 10
-constexpr int kBrickCells = kBrickHalo * kBrickHalo * kBrickHalo;    // 1000 (brick + one-voxel halo)
+// Brick-frontier automaton (automaton.cu): the padded grid is tiled by 4x4x4 bricks, one warp per brick.
+constexpr int kBrick = 4;
+constexpr int kBrickHalo = kBrick + 2;                                // 6
+constexpr int kBrickCells = kBrickHalo * kBrickHalo * kBrickHalo;    // 216 (brick + one-voxel halo)
+constexpr int kBrickWarps = 8;                                        // bricks in flight per CTA
 
 struct BrickArgs {
 	const uint8_t* layer;    // padded dense grid
@@ -94,10 +95,12 @@ struct BrickArgs {
 	const double* wtab;      // [nl1][nl1][3]
 	const uint32_t* origin;  // [n_live] padded linear index of the brick's first voxel
 	const int32_t* nbr;      // [n_live][26] live index of the neighbouring brick in cube direction k, -1 = none
-	int* flag;               // [2][n_live] brick is queued for the round of that parity
-	int* queue;              // [3][n_live] work queues, rotating
-	int* counters;           // [0..2] queue lengths, [3] rounds, [4] brick visits
-	int32_t n_live, nl1, n_nbr, pY, pX, max_rounds, w_in_smem;
+	int* flag;               // [n_live] 1 while the brick sits in the ring
+	int* first_visit;        // [n_live] 1 for the bricks of the start voxels until their first visit
+	int* queue;              // ring of brick ids, -1 = empty slot, qmask + 1 slots
+	int* counters;           // [0] head, [1] tail, [2] pending (queued or in work), [4] visits, [5] inner sweeps
+	uint32_t qmask;
+	int32_t n_live, nl1, n_nbr, pY, pX, w_in_smem;
 	int32_t loff[kMaxNbr];   // neighbour offset inside the 10^3 shared-memory cell array
 	int32_t sq[kMaxNbr];     // |dif|^2 - 1
 	int8_t dz[kMaxNbr], dy[kMaxNbr], dx[kMaxNbr];

@@ -93,7 +93,7 @@ int64_t ekg_model_num_layers(const ekg_model* m);   /* = Simulation::getTargetNu
 
 /* Runs the activation-time automaton on the device; the map stays resident.  delay_out (host,
  * Z*Y*X doubles, 0.0 for empty / unreached voxels) may be NULL.  sweeps_out (may be NULL)
- * receives the number of relaxation rounds. */
+ * receives a work count: brick visits of the frontier kernel (sweeps of the cross-check kernel). */
 int  ekg_model_activation(ekg_model* m, double* delay_out, int64_t* sweeps_out);
 /* Device time (ms, CUDA events) of the last ekg_model_activation call on this handle. */
 double ekg_model_activation_ms(const ekg_model* m);
