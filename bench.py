@@ -410,8 +410,9 @@ def run_b200_arm(args):
         "launches_per_step": int(model.last_launch_count),
         "sims_per_s": value / (N_VOX * T_FULL), "e2e_sims_per_s": e2e_value / (N_VOX * T_FULL),
         "roofline": roofline, "clocks": clocks,
-        "automaton": {"ms": automaton_ms, "sweeps": sweeps, "bit_exact_vs_reference": bool(act_ok),
-                      "edges_per_s": 26 * N_VOX / (automaton_ms * 1e-3)},
+        "automaton": {"ms": automaton_ms, "kernel": "automaton_brick_kernel (4^3-brick frontier, work ring)", "brick_visits": sweeps,
+                      "bit_exact_vs_reference": bool(act_ok), "edges_per_s": 26 * N_VOX / (automaton_ms * 1e-3),
+                      "reference_cpu_s": 2.0},
         "parity_max_err_of_peak": parity,
         "fast_path": fast, "pipeline": pipeline, "single_sim": single,
     }
