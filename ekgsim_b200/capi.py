@@ -39,6 +39,7 @@ SYMBOLS = {
     "ekg_model_get_activation": (_int, [_p, _p]),
     "ekg_model_ap_classes": (_int, [_p, _p, C.POINTER(_i64)]),
     "ekg_simulate": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p]),
+    "ekg_simulate_criteria": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _i64, _p, _int, _p, _p]),
     "ekg_simulate_device": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _p]),
     "ekg_last_kernel_ms": (_d, [_p]),
     "ekg_last_launch_count": (_i64, [_p]),
@@ -171,6 +172,29 @@ class Model:
         _check(lib().ekg_simulate(self._h, _ptr(layer_k), _ptr(leads), B, L, NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd),
                                   float(t_start), float(t_step), float(total_time), int(mode), _ptr(out)))
         return out
+
+    def simulate_criteria(self, layer_k, leads_zyx, targets, comparison=2, target_offsets=None, nbhd="3D4", t_start=100.0,
+                          t_step=1.0, total_time=400.0, mode=MODE_DEFAULT, want_ecg=False):
+        """Simulation + the reference's curve comparison on the device; returns criteria [B, L] (and the ECGs)."""
+        layer_k = np.ascontiguousarray(layer_k, dtype=np.float64)
+        if layer_k.ndim == 2:
+            layer_k = layer_k[None]
+        B = layer_k.shape[0]
+        leads = np.ascontiguousarray(leads_zyx, dtype=np.float64)
+        if leads.ndim == 2:
+            leads = np.broadcast_to(leads[None], (B,) + leads.shape).copy()
+        L = leads.shape[1]
+        targets = np.ascontiguousarray(targets, dtype=np.float64)
+        assert targets.shape[0] == L
+        off = None if target_offsets is None else np.ascontiguousarray(target_offsets, dtype=np.float64)
+        T = n_steps(total_time, t_step)
+        crit = np.empty((B, L), dtype=np.float64)
+        ecg = np.empty((B, L, T), dtype=np.float64) if want_ecg else None
+        _check(lib().ekg_simulate_criteria(self._h, _ptr(layer_k), _ptr(leads), B, L, NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd),
+                                           float(t_start), float(t_step), float(total_time), int(mode), _ptr(targets), targets.shape[1],
+                                           _ptr(off) if off is not None else None, int(comparison), _ptr(crit),
+                                           _ptr(ecg) if ecg is not None else None))
+        return (crit, ecg) if want_ecg else crit
 
     def simulate_device(self, d_layer_k, d_leads, B, L, d_ecg, nbhd="3D4", t_start=100.0, t_step=1.0, total_time=400.0,
                         mode=MODE_DEFAULT, stream=0):

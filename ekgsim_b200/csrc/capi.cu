@@ -52,7 +52,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg};
+	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -371,9 +371,29 @@ int ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_l
 	return run_ecg(m, d_layer_k, d_leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, d_ecg_out, (cudaStream_t)stream);
 }
 
+static int simulate_host(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
+                         double t_start, double t_step, double total_time, int flags, double* ecg_out,
+                         const double* targets, int64_t n_target, const double* target_offsets, int comparison, double* criteria_out);
+
 int ekg_simulate(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
                  double t_start, double t_step, double total_time, int flags, double* ecg_out) {
-	if (!m || !layer_k || !leads_zyx || !ecg_out) return fail(EKG_E_INVALID, "NULL argument");
+	if (!ecg_out) return fail(EKG_E_INVALID, "NULL argument");
+	return simulate_host(m, layer_k, leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, ecg_out, nullptr, 0, nullptr, 0, nullptr);
+}
+
+int ekg_simulate_criteria(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
+                          double t_start, double t_step, double total_time, int flags,
+                          const double* targets, int64_t n_target, const double* target_offsets, int comparison,
+                          double* criteria_out, double* ecg_out) {
+	if (!targets || n_target <= 0 || !criteria_out) return fail(EKG_E_INVALID, "NULL argument");
+	return simulate_host(m, layer_k, leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, ecg_out, targets, n_target,
+	                     target_offsets, comparison, criteria_out);
+}
+
+static int simulate_host(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
+                         double t_start, double t_step, double total_time, int flags, double* ecg_out,
+                         const double* targets, int64_t n_target, const double* target_offsets, int comparison, double* criteria_out) {
+	if (!m || !layer_k || !leads_zyx) return fail(EKG_E_INVALID, "NULL argument");
 	if (B <= 0 || n_leads <= 0 || !(t_step > 0) || !(total_time > 0)) return fail(EKG_E_INVALID, "bad sizes");
 	EKG_CUDA(cudaSetDevice(m->device));
 	const int64_t T = (int64_t)ceil(total_time / t_step);
@@ -400,9 +420,23 @@ int ekg_simulate(ekg_model* m, const double* layer_k, const double* leads_zyx, i
 	EKG_CUDA(cudaMemcpyAsync(m->d_io_leads, m->h_pin_in + nk, (size_t)nlead * 8, cudaMemcpyHostToDevice, m->stream));
 	rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, flags, m->d_io_ecg, m->stream);
 	if (rc) return rc;
-	EKG_CUDA(cudaMemcpyAsync(m->h_pin_out, m->d_io_ecg, (size_t)necg * 8, cudaMemcpyDeviceToHost, m->stream));
+	std::vector<double> crit_host;
+	if (criteria_out) {
+		const int64_t ntg = n_leads * n_target;
+		if ((rc = ensure(&m->d_io_tgt, &m->io_tgt_cap, ntg + n_leads + B * n_leads))) return rc;
+		double* d_off = m->d_io_tgt + ntg;
+		double* d_crit = d_off + n_leads;
+		EKG_CUDA(cudaMemcpyAsync(m->d_io_tgt, targets, (size_t)ntg * 8, cudaMemcpyHostToDevice, m->stream));
+		if (target_offsets) EKG_CUDA(cudaMemcpyAsync(d_off, target_offsets, (size_t)n_leads * 8, cudaMemcpyHostToDevice, m->stream));
+		EKG_CUDA(cudaStreamSynchronize(m->stream));  // pageable sources
+		if ((rc = run_criteria(m, m->d_io_ecg, m->d_io_tgt, target_offsets ? d_off : nullptr, d_crit, B, n_leads, T, n_target, comparison, m->stream))) return rc;
+		crit_host.resize((size_t)(B * n_leads));
+		EKG_CUDA(cudaMemcpyAsync(crit_host.data(), d_crit, crit_host.size() * 8, cudaMemcpyDeviceToHost, m->stream));
+	}
+	if (ecg_out) EKG_CUDA(cudaMemcpyAsync(m->h_pin_out, m->d_io_ecg, (size_t)necg * 8, cudaMemcpyDeviceToHost, m->stream));
 	EKG_CUDA(cudaStreamSynchronize(m->stream));
-	memcpy(ecg_out, m->h_pin_out, (size_t)necg * 8);
+	if (ecg_out) memcpy(ecg_out, m->h_pin_out, (size_t)necg * 8);
+	if (criteria_out) memcpy(criteria_out, crit_host.data(), crit_host.size() * 8);
 	return EKG_OK;
 }
 

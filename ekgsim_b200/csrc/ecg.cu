@@ -268,6 +268,81 @@ __global__ void __launch_bounds__(256) ecg_reduce_kernel(const double* __restric
 	ecg[i] = s;
 }
 
+// ---- curve comparison on the device (calculateFitness, sim.cpp:600-702; vectorMath.h) -----------------
+// One CTA per (vector, lead); f64 block reductions over the n overlapping samples, offset 0.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0.0;
+	for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += scratch[w];
+	return s;
+}
+
+__device__ __forceinline__ double block_min(double v, double* scratch) {
+	for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_down_sync(0xffffffffu, v, o));
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = scratch[0];
+	for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s = fmin(s, scratch[w]);
+	return s;
+}
+
+__global__ void __launch_bounds__(256) ecg_criteria_kernel(const double* __restrict__ ecg, const double* __restrict__ targets,
+                                                           const double* __restrict__ offsets, double* __restrict__ crit,
+                                                           int L, int T, int n_target, int comparison) {
+	__shared__ double scratch[8];
+	const int l = blockIdx.x % L;
+	const double* a = ecg + (int64_t)blockIdx.x * T;
+	const double* b = targets + (int64_t)l * n_target;
+	const int n = min(T, n_target);
+	const double inv = 1.0 / (double)n;
+	double out;
+	if (comparison == 2) {   // 1 - Pearson (statisticalCorrelationCoeff with offset 0)
+		double sa = 0, sb = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) { sa += a[i]; sb += b[i]; }
+		const double ma = block_sum(sa, scratch) * inv, mb = block_sum(sb, scratch) * inv;
+		double va = 0, vb = 0, cv = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) { const double da = a[i] - ma, db = b[i] - mb; va += da * da; vb += db * db; cv += da * db; }
+		va = block_sum(va, scratch) * inv; vb = block_sum(vb, scratch) * inv; cv = block_sum(cv, scratch) * inv;
+		out = 1.0 - cv / (sqrt(va) * sqrt(vb));
+	} else if (comparison == 1) {   // RMS
+		double s = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) { const double d = a[i] - b[i]; s += d * d; }
+		out = sqrt(block_sum(s, scratch) * inv);
+	} else if (comparison == 4) {   // 1 - vector correlation
+		double ab = 0, aa = 0, bb = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) { ab += a[i] * b[i]; aa += a[i] * a[i]; bb += b[i] * b[i]; }
+		ab = block_sum(ab, scratch); aa = block_sum(aa, scratch); bb = block_sum(bb, scratch);
+		out = 1.0 - ab / (sqrt(aa) * sqrt(bb));
+	} else {   // deviation from linear: sqrt(var((a * aMult + ofs) / (b + ofs))), min/max of a over ALL T samples
+		double mn = 1e300, mx = -1e300;
+		for (int i = threadIdx.x; i < T; i += blockDim.x) { mn = fmin(mn, a[i]); mx = fmax(mx, a[i]); }
+		mn = block_min(mn, scratch); mx = -block_min(-mx, scratch);
+		const double mult = 1.0 / (mx - mn), ofs = offsets[l];
+		double s = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) s += (a[i] * mult + ofs) / (b[i] + ofs);
+		const double mean = block_sum(s, scratch) * inv;
+		double v = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) { const double d = (a[i] * mult + ofs) / (b[i] + ofs) - mean; v += d * d; }
+		v = block_sum(v, scratch) * inv;
+		out = v == 0 ? 1.0 / 1e-30 : sqrt(v);
+	}
+	if (threadIdx.x == 0) crit[blockIdx.x] = out;
+}
+
+int run_criteria(ekg_model* m, const double* d_ecg, const double* d_targets, const double* d_offsets, double* d_crit,
+                 int64_t B, int64_t L, int64_t T, int64_t n_target, int comparison, cudaStream_t st) {
+	if (comparison < 1 || comparison > 4) return fail(EKG_E_INVALID, "invalid comparison mode");
+	if (comparison == 3 && !d_offsets) return fail(EKG_E_INVALID, "comparison mode 3 needs target offsets");
+	ecg_criteria_kernel<<<(unsigned)(B * L), 256, 0, st>>>(d_ecg, d_targets, d_offsets, d_crit, (int)L, (int)T, (int)n_target, comparison);
+	EKG_CUDA(cudaGetLastError());
+	++m->last_launches;
+	return EKG_OK;
+}
+
 // ---- per-(vector, layer) coefficient tables, f64 -> f32 -------------------------------------------
 // P[0..11] = -k1 log2e, -k4 log2e, -k5 log2e, -k7 log2e, log2(2^(k7/k6)-1), -k6/k7, k2(1-k3), k2 k3,
 //            k0, hi(k8), lo(k8), t0

@@ -164,6 +164,7 @@ struct ekg_model {
 	double* d_io_k = nullptr;        int64_t io_k_cap = 0;     // staging for the host-buffer entry point
 	double* d_io_leads = nullptr;    int64_t io_leads_cap = 0;
 	double* d_io_ecg = nullptr;      int64_t io_ecg_cap = 0;
+	double* d_io_tgt = nullptr;      int64_t io_tgt_cap = 0;   // targets | offsets | criteria
 	double* h_pin_in = nullptr;      int64_t pin_in_cap = 0;   // pinned host staging
 	double* h_pin_out = nullptr;     int64_t pin_out_cap = 0;
 
@@ -178,6 +179,8 @@ int run_automaton(ekg_model* m, int64_t* sweeps_out);
 // ecg.cu
 int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
             double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st);
+int run_criteria(ekg_model* m, const double* d_ecg, const double* d_targets, const double* d_offsets, double* d_crit,
+                 int64_t B, int64_t L, int64_t T, int64_t n_target, int comparison, cudaStream_t st);
 int make_nbr_table(int nbhd, NbrTable* out);
 template <class T>
 int ensure(T** p, int64_t* cap, int64_t need);

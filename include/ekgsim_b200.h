@@ -120,6 +120,21 @@ int  ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_
                          double t_start, double t_step, double total_time,
                          int flags, double* d_ecg_out, void* stream);
 
+/* ekg_simulate + the reference's curve comparison on the device, so that only B x n_leads criteria
+ * have to leave the GPU: criteria_out[b][l] compares ECG[b][l][0..n) with
+ * targets[l][0..n), n = min(n_steps, n_target), offset 0, like calculateFitness does (sim.cpp:600-702):
+ *   comparison 1 = RMS of the difference                         (vectorMath.h:322-343)
+ *   comparison 2 = 1 - Pearson correlation                       (vectorMath.h:287-317)
+ *   comparison 3 = deviation from linear, needs target_offsets   (vectorMath.h:372-404)
+ *   comparison 4 = 1 - vector correlation                        (vectorMath.h:348-366)
+ * targets is [n_leads][n_target] (host), already normalised/resampled by the caller (loadTargets);
+ * target_offsets [n_leads] may be NULL unless comparison == 3; ecg_out (host) may be NULL. */
+int  ekg_simulate_criteria(ekg_model* m, const double* layer_k, const double* leads_zyx,
+                           int64_t B, int64_t n_leads, int nbhd,
+                           double t_start, double t_step, double total_time, int flags,
+                           const double* targets, int64_t n_target, const double* target_offsets,
+                           int comparison, double* criteria_out, double* ecg_out);
+
 /* Number of kernel launches the last ekg_simulate* call on this handle issued. */
 int64_t ekg_last_launch_count(const ekg_model* m);
 /* Device time (ms) of the ECG kernel launch(es) of the last call made with EKG_FLAG_TIME_KERNEL;

@@ -288,3 +288,35 @@ def test_ecg_model24_batch_sample_vs_oracle(gpu_model24, model24, model24_delay)
             worst = max(worst, rel_err(ecg[b], ref))
         print("batch sample mode %d: worst %.3g of peak" % (mode, worst))
         assert worst < ECG_TOL
+
+
+def test_criteria_on_device(gpu_model24, model24, model24_delay):
+    """ekg_simulate_criteria: the four curve comparisons of calculateFitness (vectorMath.h) computed on
+    the device agree with a numpy restatement applied to the ECGs of the same call, and comparison 2
+    reproduces the criteria the reference printed (1e-4)."""
+    g = np.load(os.path.join(GOLDEN, "golden_eval_full.npz"))
+    sel = [i for i, n in enumerate(g["name"]) if n != "v6full"]
+    tv = model24["target_v5"]
+    targets = np.stack([tv[:, c] / (tv[:, c].max() - tv[:, c].min()) for c in (1, 2)])      # loadTargets, sim.cpp:1016-1019
+    offsets = np.array([1.0 - tv[:, c].min() / (tv[:, c].max() - tv[:, c].min()) for c in (1, 2)])
+    gpu_model24.set_activation(model24_delay)
+    k, leads = g["layer_k"][sel], g["leads_zyx"][sel]
+    for cmp_mode in (1, 2, 3, 4):
+        crit, ecg = gpu_model24.simulate_criteria(k, leads, targets, comparison=cmp_mode, target_offsets=offsets, mode=1, want_ecg=True)
+        for b in range(len(sel)):
+            for l in range(2):
+                a, t = ecg[b, l], targets[l][:400]
+                if cmp_mode == 1:
+                    want = np.sqrt(np.mean((a - t) ** 2))
+                elif cmp_mode == 2:
+                    want = 1.0 - np.mean((a - a.mean()) * (t - t.mean())) / (a.std() * t.std())
+                elif cmp_mode == 4:
+                    want = 1.0 - a.dot(t) / (np.sqrt(a.dot(a)) * np.sqrt(t.dot(t)))
+                else:
+                    d = (a / (a.max() - a.min()) + offsets[l]) / (t + offsets[l])
+                    want = np.sqrt(d.var())
+                assert abs(crit[b, l] - want) < 1e-11 * max(1.0, abs(want)), (cmp_mode, b, l, crit[b, l], want)
+        if cmp_mode == 2:
+            assert np.abs(crit - g["criteria"][sel]).max() < 1e-4
+    only = gpu_model24.simulate_criteria(k, leads, targets, comparison=2, mode=2)     # no ECG download at all
+    assert np.abs(only - g["criteria"][sel]).max() < 1e-4
