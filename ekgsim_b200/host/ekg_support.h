@@ -22,6 +22,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <sys/stat.h>
 #include <sys/time.h>
 #include <vector>
 
@@ -215,6 +216,35 @@ inline void load_shape_matrix(const std::string& fname, std::vector<uint16_t>& l
 		}
 	}
 	if (i < n) throw std::runtime_error("reading file " + fname + " failed (while reading data)");
+}
+
+/// Optional binary side-car of a shape file (SURVEY 8(f) "input pipeline"): with EKGSIM_B200_CACHE=1 in the
+/// environment, `<file>.b200bin` (header + raw uint16 layers) is written after the first text parse and used
+/// afterwards as long as size and mtime of the text file are unchanged.  A 4x-resolution heart is ~200 MB of
+/// text (seconds to parse) but 183 MB of binary (a plain read).
+inline void load_shape_matrix_cached(const std::string& fname, std::vector<uint16_t>& layers, int64_t& Z, int64_t& Y, int64_t& X) {
+	const char* env = getenv("EKGSIM_B200_CACHE");
+	if (!env || env[0] == '0') { load_shape_matrix(fname, layers, Z, Y, X); return; }
+	struct stat st;
+	const bool have_src = stat(fname.c_str(), &st) == 0;
+	const std::string cache = fname + ".b200bin";
+	struct Header { char magic[8]; int64_t z, y, x, src_size, src_mtime; } h;
+	if (have_src) {
+		std::ifstream in(cache.c_str(), std::ios::binary);
+		if (in.read(reinterpret_cast<char*>(&h), sizeof h) && !memcmp(h.magic, "EKGSHP1", 8) && h.src_size == (int64_t)st.st_size &&
+		    h.src_mtime == (int64_t)st.st_mtime && h.z > 0 && h.y > 0 && h.x > 0) {
+			layers.resize((size_t)(h.z * h.y * h.x));
+			if (in.read(reinterpret_cast<char*>(layers.data()), (std::streamsize)(layers.size() * 2))) { Z = h.z; Y = h.y; X = h.x; return; }
+		}
+	}
+	load_shape_matrix(fname, layers, Z, Y, X);
+	if (have_src) {
+		memcpy(h.magic, "EKGSHP1", 8);
+		h.z = Z; h.y = Y; h.x = X; h.src_size = (int64_t)st.st_size; h.src_mtime = (int64_t)st.st_mtime;
+		std::ofstream out(cache.c_str(), std::ios::binary);
+		out.write(reinterpret_cast<const char*>(&h), sizeof h);
+		out.write(reinterpret_cast<const char*>(layers.data()), (std::streamsize)(layers.size() * 2));
+	}
 }
 
 /// 2-D matrix of doubles (conduction / transfer matrix), row major [Y][X]

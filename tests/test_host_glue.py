@@ -86,3 +86,34 @@ def test_char_matrix_and_2d_model(tmp_path, built):
         f.write("tiny\n2d 10 x 5\n" + "\n".join(rows) + "\n")
     ev = hostlib.Evaluator(d, with_device=False, n_layers=11)   # highest layer 'B' = 11
     ev.close()
+
+
+def test_binary_shape_cache(tmp_path, built, monkeypatch):
+    """EKGSIM_B200_CACHE=1: <shape>.b200bin is written on the first parse, used on the second, and
+    ignored when the text file changes."""
+    d = str(tmp_path)
+    ekgio.materialise_testrun(d)
+    monkeypatch.setenv("EKGSIM_B200_CACHE", "1")
+    hostlib.Evaluator(d, with_device=False).close()
+    cache = os.path.join(d, "model_24.matrix.b200bin")
+    assert os.path.getsize(cache) == 48 + 124 * 124 * 93 * 2
+    raw = np.fromfile(cache, dtype=np.uint16, offset=48).reshape(124, 124, 93)
+    assert (raw == ekgio.load_model24()["layers"]).all()
+    # corrupt the text but keep size and mtime -> the cache is trusted
+    st = os.stat(os.path.join(d, "model_24.matrix"))
+    txt = open(os.path.join(d, "model_24.matrix")).read()
+    at = txt.index(" 1 ", 100) + 1          # a layer-1 voxel somewhere in the body -> layer 2, same file size
+    with open(os.path.join(d, "model_24.matrix"), "r+") as f:
+        f.seek(at)
+        f.write("2")
+    os.utime(os.path.join(d, "model_24.matrix"), (st.st_atime, st.st_mtime))
+    ev = hostlib.Evaluator(d, with_device=False)
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    k, _, _ = ev.layer_coefficients(g["params"][0])
+    assert k.tobytes() == g["layer_k"][0].tobytes()
+    ev.close()
+    # a newer text file invalidates it
+    os.utime(os.path.join(d, "model_24.matrix"), (st.st_atime, st.st_mtime + 5))
+    hostlib.Evaluator(d, with_device=False).close()
+    raw2 = np.fromfile(cache, dtype=np.uint16, offset=48)
+    assert (raw2 != raw.reshape(-1)).sum() == 1
