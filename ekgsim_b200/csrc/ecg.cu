@@ -210,9 +210,15 @@ __global__ void __launch_bounds__(kEcgThreads, MODE == MODE_DIRECT ? 5 : 4) ecg_
 							const float S = mufu_rcp(1.f + mufu_ex2(a1 * tau));  // 1/(1+exp(-k1 t'))
 							const float k8s = k8hi - r0.x;                   // k8 - at  (simulator.cpp:156)
 							const float u = (tau - k8s) - k8lo;              // t' - k8'
-							const float e = mufu_ex2(fmaf(a7, u, c2));       // exp(-k7 (t'-k8') + ln(2^(k7/k6)-1))
-							const float Q = mufu_ex2(np * mufu_lg2(1.f + e)); // (1+e)^(-k6/k7)
-							const float Pp = fmaf(A, mufu_ex2(a4 * tau), Bc); // k2((1-k3) exp(-k4 t') + k3)
+							// (1+e)^(-k6/k7) with e = exp(-k7 (t'-k8') + ln(2^(k7/k6)-1)) = 2^z, evaluated as
+							// 2^(-(k6/k7) * log2(1+2^z)),  log2(1+2^z) = max(z,0) + log2(1 + 2^-|z|):
+							// the same two MUFU ops, but 2^z may exceed the fp32 range (small k6/k7 make
+							// (huge)^(-small) a perfectly ordinary number)
+							const float z = fmaf(a7, u, c2);
+							const float Q = mufu_ex2(np * (fmaxf(z, 0.f) + mufu_lg2(1.f + mufu_ex2(-fabsf(z)))));
+							// k2((1-k3) exp(-k4 t') + k3); the clamp only matters far before activation, where S is 0 and
+							// an overflowing exponential would turn 0 * inf into NaN (the f64 reference stays finite there)
+							const float Pp = fmaf(A, mufu_ex2(fminf(a4 * tau, 100.f)), Bc);
 							const float E5 = mufu_ex2(a5 * tau);
 							V = fmaf((S * Pp) * E5, 1.f - Q, k0);
 							G[0] = r0.y;

@@ -320,3 +320,30 @@ def test_criteria_on_device(gpu_model24, model24, model24_delay):
             assert np.abs(crit - g["criteria"][sel]).max() < 1e-4
     only = gpu_model24.simulate_criteria(k, leads, targets, comparison=2, mode=2)     # no ECG download at all
     assert np.abs(only - g["criteria"][sel]).max() < 1e-4
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_ecg_wide_parameter_ranges(built, seed):
+    """Coefficients far outside the testRun ranges (slow depolarisation sigmoid that never saturates,
+    large k4, non-zero k0, negative start time so that many samples lie before the activation time):
+    both kernels must still match the f64 oracle."""
+    rng = np.random.default_rng(100 + seed)
+    layers, transfer, leads = synth.small_heart(seed=40 + seed, shape=(13, 14, 15), n_layers=5)
+    nl = int((layers & 0xFFF).max())
+    B = 6
+    k = np.zeros((B, nl, 9))
+    for b in range(B):
+        for l in range(nl):
+            k[b, l] = [rng.uniform(-90, 10), rng.uniform(0.05, 3.5), rng.uniform(50, 150), rng.uniform(0.5, 0.99), rng.uniform(0.01, 0.5),
+                       rng.uniform(1e-4, 5e-3), rng.uniform(0.005, 0.3), rng.uniform(0.005, 0.3), rng.uniform(40, 500)]
+    delay = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    m.set_activation(delay)
+    for (t0, dt, tot) in [(-10.0, 1.0, 200.0), (0.0, 2.5, 600.0)]:
+        refs = [oracle.run_direct(layers, delay, k[b], leads, "3D4", t0, dt, tot) for b in range(B)]
+        for mode in (1, 2):
+            ecg = m.simulate(k, leads, "3D4", t0, dt, tot, mode=mode)
+            assert np.isfinite(ecg).all()
+            worst = max(rel_err(ecg[b], refs[b]) for b in range(B))
+            assert worst < ECG_TOL, (seed, mode, t0, worst)
+    m.close()
