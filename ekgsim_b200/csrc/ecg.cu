@@ -67,7 +67,7 @@ struct RowLayout {
 // in the first version of this kernel).  A tile therefore spans up to kMaxVecPerTile parameter
 // vectors; phase A computes the lead-field coefficients for each of them.
 template <int MODE, int NL>
-__global__ void __launch_bounds__(kEcgThreads, MODE == MODE_DIRECT ? 5 : 4) ecg_kernel(const EcgArgs a) {
+__global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	constexpr int ROW = RowLayout<MODE, NL>::kFloats;
 	__shared__ __align__(16) float s_vox[kSmemRows * ROW];
 	__shared__ float2 s_lead[kMaxVecPerTile * NL * 3];  // lead coordinate as fp32 hi + lo
@@ -549,7 +549,7 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	}
 	if (B * T >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "B * n_steps must be below 2^31");
 	// ~100 waves of CTAs: the tail of the last wave costs about 1/waves of the launch
-	const int64_t target_ctas = (int64_t)m->sm_count * (mode == EKG_MODE_DIRECT ? 5 : 4) * 96;
+	const int64_t target_ctas = (int64_t)m->sm_count * 4 * 96;
 	int64_t want_segs = (target_ctas + m->n_tiles - 1) / m->n_tiles;
 	int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
 	seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
