@@ -389,6 +389,9 @@ def run_b200_arm(args):
         "peak_basis": "148 SM x 16 MUFU lanes/clk x SM clock sampled under load (%s MHz); at clocks.max.sm the peak is %.0f Gop/s "
                       "-> frac %.3f" % (sm_mhz, peak_gops_max, achieved_gops / peak_gops_max),
         "algorithmic_ops_per_voxel_timestep": SFU_OPS_PER_VTS,
+        "executed_on_xu_pipe_per_voxel_timestep": 6 if mode == ek.MODE_DIRECT else 2,
+        "note": "DIRECT evaluates all 7 transcendental operations per voxel-timestep; the reciprocal of the depolarisation "
+                "sigmoid runs as a Newton iteration on the FMA pipe, the other 6 on the MUFU/XU pipe",
         "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch at
         # B = 256 (profiles/r01_ecg_direct_v5_b256_ncu_full.txt): 14.7 MB read + 192.4 MB written (f64 partials)

@@ -97,6 +97,21 @@ def test_batch_256_glue_plus_gpu(testrun):
     ev.close()
 
 
+def test_batch_256_criteria_match_oracle(testrun):
+    """All 256 vectors of the config-3 batch, parameter vector -> criteria through the product's own glue
+    and GPU path, against criteria derived with the reference-pinned oracle
+    (tests/golden/make_criteria256.py).  Tolerance 1e-4 (north_star)."""
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    want = np.load(os.path.join(GOLDEN, "golden_criteria256.npz"))
+    ev = hostlib.Evaluator(testrun, with_device=True)
+    crit, viol = ev.eval_batch(g["params"], threads=0)
+    ev.close()
+    err = np.abs(crit - want["criteria"])
+    print("256-vector criteria: worst |diff| %.3g" % err.max())
+    assert err.max() < 1e-4
+    assert np.abs(viol - want["violation"]).max() < 1e-9
+
+
 def test_cli_extern_protocol(testrun, golden):
     """AMS-DEMO ExternalEvaluation: <cmd> <homeDir>, input.txt -> output.txt (ExternalEvaluation.h:95-151)."""
     home = os.path.join(testrun, "process1")
