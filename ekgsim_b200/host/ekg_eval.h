@@ -739,7 +739,7 @@ private:
 	}
 
 	void writeOutputs(const Input& solution, const Individual& ind) {
-		saveAps("cell_aps.column", sim->getAps(), &outSettings.outputCellAps);
+		if (!outSettings.outputCellAps.empty()) saveAps("cell_aps.column", sim->getAps(), &outSettings.outputCellAps);
 		if (outSettings.layerAps) saveAps("layer_aps.column", ind.layerAps, nullptr);
 		if (outSettings.result) sim->saveMeasurement("input=" + angle_list(solution) + "; ");
 	}

@@ -224,8 +224,13 @@ public:
 	}
 
 	/// swaps: the caller's vector receives the previous contents (sim_lib.h:151, simulator.cpp:208-210)
-	void setApsDestructive(std::vector<ActionPotential>& destructible) { aps_.swap(destructible); }
-	const std::vector<ActionPotential>& getAps() const { return aps_; }
+	void setApsDestructive(std::vector<ActionPotential>& destructible) { aps_.swap(destructible); cellApsPending_ = false; }
+	/// layer APs before run(); after run() one AP per (layer, delay) class in first-seen raster order
+	/// (built on first use -- the class table costs a pass over the whole model)
+	const std::vector<ActionPotential>& getAps() const {
+		if (cellApsPending_) const_cast<EkgSim*>(this)->buildCellAps();
+		return aps_;
+	}
 
 	void loadTransferMatrix() {
 		ekg::LogTimer tm(std::cerr, "loading transfer matrix                     ");
@@ -310,6 +315,8 @@ public:
 			check(ekg_model_set_activation(model_, delay.data()));
 		}
 		haveActivation_ = true;
+		delayCache_.clear();
+		classFirstVoxel_.clear();
 		if (settings.outputExcitationSequence != "") {
 			std::vector<double> delay((size_t)(Z_ * Y_ * X_));
 			check(ekg_model_get_activation(model_, delay.data()));
@@ -347,7 +354,7 @@ public:
 		const size_t T = ecg.size() / std::max<size_t>(mps_.size(), 1);
 		measurement_.assign(mps_.size(), std::vector<double>());
 		for (size_t i = 0; i < mps_.size(); ++i) measurement_[i].assign(ecg.begin() + i * T, ecg.begin() + (i + 1) * T);
-		buildCellAps();
+		cellApsPending_ = true;
 	}
 
 	/// B parameter sets in one launch: layerK [B][layers][9], leadsZyx [B][leads][3] -> ecg [B][leads][T]
@@ -400,6 +407,8 @@ public:
 
 private:
 	std::vector<double> delayCache_;
+	std::vector<int64_t> classFirstVoxel_;
+	bool cellApsPending_ = false;
 
 	void saveMeasurements(const std::string& filename, const std::string& comment) {
 		std::vector<saveVecElement> v(mps_.size());
@@ -415,19 +424,22 @@ private:
 	/// after run() the reference's aps hold one AP per (layer, delay) class in first-seen raster
 	/// order (Simulation::setApIndices, simulator.cpp:561-621); `-out cell_aps n` indexes that table
 	void buildCellAps() {
-		std::vector<int64_t> idx(layers_.size());
-		int64_t K = 0;
-		check(ekg_model_ap_classes(model_, idx.data(), &K));
-		if (delayCache_.empty()) { delayCache_.resize(layers_.size()); check(ekg_model_get_activation(model_, delayCache_.data())); }
-		std::vector<ActionPotential> cells((size_t)K);
-		std::vector<char> seen((size_t)K, 0);
-		for (size_t i = 0; i < layers_.size(); ++i) {
-			const int64_t c = idx[i];
-			if (c < 0 || seen[(size_t)c]) continue;
-			seen[(size_t)c] = 1;
-			cells[(size_t)c].init(aps_[(layers_[i] & 0x0fff) - 1], delayCache_[i]);
+		if (classFirstVoxel_.empty()) {   // once per excitation sequence: first voxel of every class, raster order
+			std::vector<int64_t> idx(layers_.size());
+			int64_t K = 0;
+			check(ekg_model_ap_classes(model_, idx.data(), &K));
+			if (delayCache_.empty()) { delayCache_.resize(layers_.size()); check(ekg_model_get_activation(model_, delayCache_.data())); }
+			classFirstVoxel_.assign((size_t)K, -1);
+			for (size_t i = 0; i < layers_.size(); ++i)
+				if (idx[i] >= 0 && classFirstVoxel_[(size_t)idx[i]] < 0) classFirstVoxel_[(size_t)idx[i]] = (int64_t)i;
+		}
+		std::vector<ActionPotential> cells(classFirstVoxel_.size());
+		for (size_t c = 0; c < cells.size(); ++c) {
+			const size_t i = (size_t)classFirstVoxel_[c];
+			cells[c].init(aps_[(layers_[i] & 0x0fff) - 1], delayCache_[i]);
 		}
 		aps_.swap(cells);
+		cellApsPending_ = false;
 	}
 
 	EkgSim(const EkgSim&);
