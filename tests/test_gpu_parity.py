@@ -347,3 +347,29 @@ def test_ecg_wide_parameter_ranges(built, seed):
             worst = max(rel_err(ecg[b], refs[b]) for b in range(B))
             assert worst < ECG_TOL, (seed, mode, t0, worst)
     m.close()
+
+
+def test_full_size_properties(gpu_model24, model24, model24_delay):
+    """Size-independent properties at the BASELINE size (model_24, T = 400), no oracle needed:
+    (1) the ECG is linear in the AP amplitude k2 and blind to the offset k0 (sum of the lead-field
+    coefficients over the model is zero); (2) z-slabs add up to the whole model; (3) DIRECT and HOISTED
+    agree; (4) permuting the batch permutes the result."""
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    k, leads = g["layer_k"][:8].copy(), g["leads_zyx"][:8].copy()
+    gpu_model24.set_activation(model24_delay)
+    base = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=1)
+    peak = np.abs(base).max(axis=2, keepdims=True)
+    k2 = k.copy(); k2[:, :, 2] *= 2.0; k2[:, :, 0] = -37.5
+    scaled = gpu_model24.simulate(k2, leads, "3D4", 100.0, 1.0, 400.0, mode=1)
+    assert (np.abs(scaled - 2.0 * base) / peak).max() < 2e-5          # fp32 evaluation on both sides
+    hoisted = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=2)
+    assert (np.abs(hoisted - base) / peak).max() < ECG_TOL
+    perm = np.array([3, 0, 7, 1, 6, 2, 5, 4])
+    shuffled = gpu_model24.simulate(k[perm], leads[perm], "3D4", 100.0, 1.0, 400.0, mode=1)
+    assert (np.abs(shuffled - base[perm]) / peak[perm]).max() < 2e-6
+    parts = np.zeros_like(base)
+    for z0, z1 in [(0, 40), (40, 41), (41, 90), (90, 124)]:
+        gpu_model24.set_slab(z0, z1)
+        parts += gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=1)
+    gpu_model24.set_slab(0, 124)
+    assert (np.abs(parts - base) / peak).max() < 2e-6
