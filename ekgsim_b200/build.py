@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/capi.cu", "csrc/automaton.cu", "csrc/ecg.cu"]
+SOURCES = ["csrc/capi.cu", "csrc/automaton.cu", "csrc/ecg.cu", "csrc/fit.cu"]
 HEADERS = ["csrc/ekg_internal.cuh", "../include/ekgsim_b200.h"]
 OUT = os.path.join(HERE, "libekgsim_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

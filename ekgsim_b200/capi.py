@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libekgsim_b200.so")
 NBHD = {"2D4": 0, "2D8": 1, "3D4": 2, "3D8": 3, "cube": 3}
 MODE_DEFAULT, MODE_DIRECT, MODE_HOISTED = 0, 1, 2
 FLAG_TIME_KERNEL = 0x100
+FIT_D9 = (0.0, 0.0, 0.0, 0.001, 0.0, 0.00005, 0.0005, 0.01, 0.2)   # sim.cpp:877 `kd`
 START_FLAG = 0x1000
 
 # every symbol include/ekgsim_b200.h declares: name -> (restype, argtypes)
@@ -41,6 +42,9 @@ SYMBOLS = {
     "ekg_simulate": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p]),
     "ekg_simulate_criteria": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _i64, _p, _int, _p, _p]),
     "ekg_simulate_device": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _p]),
+    "ekg_fit_layers": (_int, [_p, _p, _i64, _i64, _i64, _p, _d, _d, _i64, _p]),
+    "ekg_fit_layers_device": (_int, [_p, _p, _i64, _i64, _i64, _p, _d, _d, _i64, _p, _p]),
+    "ekg_evaluate": (_int, [_p, _p, _i64, _i64, _p, _d, _d, _i64, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _i64, _p, _int, _p, _p, _p]),
     "ekg_last_kernel_ms": (_d, [_p]),
     "ekg_last_launch_count": (_i64, [_p]),
     "ekg_last_kernel_name": (C.c_char_p, [_p]),
@@ -202,6 +206,44 @@ class Model:
         _check(lib().ekg_simulate_device(self._h, C.c_void_p(d_layer_k), C.c_void_p(d_leads), int(B), int(L),
                                          NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd), float(t_start), float(t_step),
                                          float(total_time), int(mode), C.c_void_p(d_ecg), C.c_void_p(stream)))
+
+    def fit_layers(self, border_k, mid=-1, d9=FIT_D9, step=0.5, eps=1e-3, iterations=100):
+        """Border APs [B, 2|3, 9] -> layer coefficients [B, n_layers, 9] (sim.cpp:751-916 on the device)."""
+        border_k = np.ascontiguousarray(border_k, dtype=np.float64)
+        if border_k.ndim == 2:
+            border_k = border_k[None]
+        B, nb = border_k.shape[:2]
+        d9 = np.ascontiguousarray(d9, dtype=np.float64)
+        out = np.empty((B, self.num_layers, 9), dtype=np.float64)
+        _check(lib().ekg_fit_layers(self._h, _ptr(border_k), B, nb, int(mid), _ptr(d9), float(step), float(eps), int(iterations), _ptr(out)))
+        return out
+
+    def evaluate(self, border_k, leads_zyx, targets, mid=-1, comparison=2, target_offsets=None, d9=FIT_D9, step=0.5, eps=1e-3,
+                 iterations=100, nbhd="3D4", t_start=100.0, t_step=1.0, total_time=400.0, mode=MODE_DEFAULT, want_layer_k=False,
+                 want_ecg=False):
+        """Border APs + leads in, criteria [B, L] out; fit, simulation and comparison stay on the device."""
+        border_k = np.ascontiguousarray(border_k, dtype=np.float64)
+        if border_k.ndim == 2:
+            border_k = border_k[None]
+        B, nb = border_k.shape[:2]
+        leads = np.ascontiguousarray(leads_zyx, dtype=np.float64)
+        if leads.ndim == 2:
+            leads = np.broadcast_to(leads[None], (B,) + leads.shape).copy()
+        L = leads.shape[1]
+        targets = np.ascontiguousarray(targets, dtype=np.float64)
+        assert targets.shape[0] == L
+        off = None if target_offsets is None else np.ascontiguousarray(target_offsets, dtype=np.float64)
+        d9 = np.ascontiguousarray(d9, dtype=np.float64)
+        T = n_steps(total_time, t_step)
+        crit = np.empty((B, L), dtype=np.float64)
+        lk = np.empty((B, self.num_layers, 9), dtype=np.float64) if want_layer_k else None
+        ecg = np.empty((B, L, T), dtype=np.float64) if want_ecg else None
+        _check(lib().ekg_evaluate(self._h, _ptr(border_k), nb, int(mid), _ptr(d9), float(step), float(eps), int(iterations),
+                                  _ptr(leads), B, L, NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd),
+                                  float(t_start), float(t_step), float(total_time), int(mode), _ptr(targets), targets.shape[1],
+                                  _ptr(off) if off is not None else None, int(comparison), _ptr(crit),
+                                  _ptr(lk) if lk is not None else None, _ptr(ecg) if ecg is not None else None))
+        return crit, lk, ecg
 
     @property
     def last_kernel_ms(self):

@@ -52,7 +52,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt};
+	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -371,9 +371,19 @@ int ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_l
 	return run_ecg(m, d_layer_k, d_leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, d_ecg_out, (cudaStream_t)stream);
 }
 
+// border APs + descent settings of the device-side layer fit (ekg_evaluate); border_k == NULL: layer_k is given
+struct FitRequest {
+	const double* border_k = nullptr;
+	int64_t n_border = 0, mid = 0, iterations = 0;
+	const double* d9 = nullptr;
+	double step = 0, eps = 0;
+	double* layer_k_out = nullptr;
+};
+
 static int simulate_host(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
                          double t_start, double t_step, double total_time, int flags, double* ecg_out,
-                         const double* targets, int64_t n_target, const double* target_offsets, int comparison, double* criteria_out);
+                         const double* targets, int64_t n_target, const double* target_offsets, int comparison, double* criteria_out,
+                         const FitRequest* fit = nullptr);
 
 int ekg_simulate(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
                  double t_start, double t_step, double total_time, int flags, double* ecg_out) {
@@ -390,16 +400,58 @@ int ekg_simulate_criteria(ekg_model* m, const double* layer_k, const double* lea
 	                     target_offsets, comparison, criteria_out);
 }
 
+int ekg_fit_layers_device(ekg_model* m, const double* d_border_k, int64_t B, int64_t n_border, int64_t mid, const double* d9,
+                          double step_size, double epsilon, int64_t iterations, double* d_layer_k_out, void* stream) {
+	if (!m || !d_border_k || !d9 || !d_layer_k_out) return fail(EKG_E_INVALID, "NULL argument");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return run_fit(m, d_border_k, B, n_border, m->n_layers, mid, d9, step_size, epsilon, iterations, d_layer_k_out, (cudaStream_t)stream);
+}
+
+int ekg_fit_layers(ekg_model* m, const double* border_k, int64_t B, int64_t n_border, int64_t mid, const double* d9,
+                   double step_size, double epsilon, int64_t iterations, double* layer_k_out) {
+	if (!m || !border_k || !d9 || !layer_k_out) return fail(EKG_E_INVALID, "NULL argument");
+	if (B <= 0 || (n_border != 2 && n_border != 3)) return fail(EKG_E_INVALID, "bad sizes");
+	EKG_CUDA(cudaSetDevice(m->device));
+	const int64_t nb = B * n_border * 9, nk = B * m->n_layers * 9;
+	int rc;
+	if ((rc = ensure(&m->d_io_border, &m->io_border_cap, nb))) return rc;
+	if ((rc = ensure(&m->d_io_k, &m->io_k_cap, nk))) return rc;
+	if ((rc = upload(m, m->d_io_border, border_k, (size_t)nb * 8))) return rc;
+	if ((rc = run_fit(m, m->d_io_border, B, n_border, m->n_layers, mid, d9, step_size, epsilon, iterations, m->d_io_k, m->stream))) return rc;
+	EKG_CUDA(cudaMemcpyAsync(layer_k_out, m->d_io_k, (size_t)nk * 8, cudaMemcpyDeviceToHost, m->stream));
+	EKG_CUDA(cudaStreamSynchronize(m->stream));
+	return EKG_OK;
+}
+
+int ekg_evaluate(ekg_model* m, const double* border_k, int64_t n_border, int64_t mid, const double* d9, double step_size, double epsilon,
+                 int64_t iterations, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd, double t_start, double t_step,
+                 double total_time, int flags, const double* targets, int64_t n_target, const double* target_offsets, int comparison,
+                 double* criteria_out, double* layer_k_out, double* ecg_out) {
+	if (!border_k || !d9) return fail(EKG_E_INVALID, "NULL argument");
+	if (criteria_out && (!targets || n_target <= 0)) return fail(EKG_E_INVALID, "criteria requested without targets");
+	if (!criteria_out && !ecg_out && !layer_k_out) return fail(EKG_E_INVALID, "no output requested");
+	FitRequest f;
+	f.border_k = border_k; f.n_border = n_border; f.mid = mid; f.iterations = iterations;
+	f.d9 = d9; f.step = step_size; f.eps = epsilon; f.layer_k_out = layer_k_out;
+	return simulate_host(m, nullptr, leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, ecg_out, targets, n_target,
+	                     target_offsets, comparison, criteria_out, &f);
+}
+
 static int simulate_host(ekg_model* m, const double* layer_k, const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
                          double t_start, double t_step, double total_time, int flags, double* ecg_out,
-                         const double* targets, int64_t n_target, const double* target_offsets, int comparison, double* criteria_out) {
-	if (!m || !layer_k || !leads_zyx) return fail(EKG_E_INVALID, "NULL argument");
+                         const double* targets, int64_t n_target, const double* target_offsets, int comparison, double* criteria_out,
+                         const FitRequest* fit) {
+	if (!m || (!layer_k && !fit) || !leads_zyx) return fail(EKG_E_INVALID, "NULL argument");
+	if (fit && fit->n_border != 2 && fit->n_border != 3) return fail(EKG_E_INVALID, "n_border must be 2 (endo-epi) or 3 (endo-mid-epi)");
 	if (B <= 0 || n_leads <= 0 || !(t_step > 0) || !(total_time > 0)) return fail(EKG_E_INVALID, "bad sizes");
 	EKG_CUDA(cudaSetDevice(m->device));
 	const int64_t T = (int64_t)ceil(total_time / t_step);
-	const int64_t nk = B * m->n_layers * 9, nlead = B * n_leads * 3, necg = B * n_leads * T;
+	const int64_t nk_out = B * m->n_layers * 9;                        // layer coefficients on the device
+	const int64_t nk = fit ? B * fit->n_border * 9 : nk_out;           // coefficients that travel host -> device
+	const int64_t nlead = B * n_leads * 3, necg = B * n_leads * T;
 	int rc;
-	if ((rc = ensure(&m->d_io_k, &m->io_k_cap, nk))) return rc;
+	if ((rc = ensure(&m->d_io_k, &m->io_k_cap, nk_out))) return rc;
+	if (fit && (rc = ensure(&m->d_io_border, &m->io_border_cap, nk))) return rc;
 	if ((rc = ensure(&m->d_io_leads, &m->io_leads_cap, nlead))) return rc;
 	if ((rc = ensure(&m->d_io_ecg, &m->io_ecg_cap, necg))) return rc;
 	if (m->pin_in_cap < nk + nlead) {
@@ -414,10 +466,15 @@ static int simulate_host(ekg_model* m, const double* layer_k, const double* lead
 		EKG_CUDA(cudaMallocHost(&m->h_pin_out, (size_t)necg * 8));
 		m->pin_out_cap = necg;
 	}
-	memcpy(m->h_pin_in, layer_k, (size_t)nk * 8);
+	memcpy(m->h_pin_in, fit ? fit->border_k : layer_k, (size_t)nk * 8);
 	memcpy(m->h_pin_in + nk, leads_zyx, (size_t)nlead * 8);
-	EKG_CUDA(cudaMemcpyAsync(m->d_io_k, m->h_pin_in, (size_t)nk * 8, cudaMemcpyHostToDevice, m->stream));
+	EKG_CUDA(cudaMemcpyAsync(fit ? m->d_io_border : m->d_io_k, m->h_pin_in, (size_t)nk * 8, cudaMemcpyHostToDevice, m->stream));
 	EKG_CUDA(cudaMemcpyAsync(m->d_io_leads, m->h_pin_in + nk, (size_t)nlead * 8, cudaMemcpyHostToDevice, m->stream));
+	int64_t fit_launches = 0;
+	if (fit) {
+		if ((rc = run_fit(m, m->d_io_border, B, fit->n_border, m->n_layers, fit->mid, fit->d9, fit->step, fit->eps, fit->iterations, m->d_io_k, m->stream))) return rc;
+		fit_launches = m->last_launches;
+	}
 	rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, flags, m->d_io_ecg, m->stream);
 	if (rc) return rc;
 	std::vector<double> crit_host;
@@ -434,7 +491,9 @@ static int simulate_host(ekg_model* m, const double* layer_k, const double* lead
 		EKG_CUDA(cudaMemcpyAsync(crit_host.data(), d_crit, crit_host.size() * 8, cudaMemcpyDeviceToHost, m->stream));
 	}
 	if (ecg_out) EKG_CUDA(cudaMemcpyAsync(m->h_pin_out, m->d_io_ecg, (size_t)necg * 8, cudaMemcpyDeviceToHost, m->stream));
+	if (fit && fit->layer_k_out) EKG_CUDA(cudaMemcpyAsync(fit->layer_k_out, m->d_io_k, (size_t)nk_out * 8, cudaMemcpyDeviceToHost, m->stream));
 	EKG_CUDA(cudaStreamSynchronize(m->stream));
+	m->last_launches += fit_launches;
 	if (ecg_out) memcpy(ecg_out, m->h_pin_out, (size_t)necg * 8);
 	if (criteria_out) memcpy(criteria_out, crit_host.data(), crit_host.size() * 8);
 	return EKG_OK;

@@ -165,6 +165,8 @@ struct ekg_model {
 	double* d_io_leads = nullptr;    int64_t io_leads_cap = 0;
 	double* d_io_ecg = nullptr;      int64_t io_ecg_cap = 0;
 	double* d_io_tgt = nullptr;      int64_t io_tgt_cap = 0;   // targets | offsets | criteria
+	double* d_io_border = nullptr;   int64_t io_border_cap = 0; // border APs of the device-side layer fit
+	double* d_fit_conn = nullptr;    int64_t fit_conn_cap = 0;  // connector tables of the layer fit (fit.cu)
 	double* h_pin_in = nullptr;      int64_t pin_in_cap = 0;   // pinned host staging
 	double* h_pin_out = nullptr;     int64_t pin_out_cap = 0;
 
@@ -182,6 +184,9 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 int run_criteria(ekg_model* m, const double* d_ecg, const double* d_targets, const double* d_offsets, double* d_crit,
                  int64_t B, int64_t L, int64_t T, int64_t n_target, int comparison, cudaStream_t st);
 int make_nbr_table(int nbhd, NbrTable* out);
+// fit.cu
+int run_fit(ekg_model* m, const double* d_border_k, int64_t B, int64_t n_border, int64_t n_layers, int64_t mid, const double* d9,
+            double step, double eps, int64_t iterations, double* d_layer_k, cudaStream_t st);
 template <class T>
 int ensure(T** p, int64_t* cap, int64_t need);
 }  // namespace ekg

@@ -1,0 +1,281 @@
+// ekgsim_b200/csrc/fit.cu -- per-layer action-potential construction on the device.
+//
+// The reference derives the Wohlfart coefficients of every inner layer from two border APs
+// (endo/mid or mid/epi): 15 straight connectors join matching arc-length positions on the two
+// border curves (WohlfartInterpolationEvaluator, sim.cpp:91-313), the layer at `ratio` should pass
+// through the points at that ratio along the connectors, and a sign-following steepest descent
+// (nonlinearFit.h:92-168; <= 100 iterations, 5 free coefficients) moves the linearly blended
+// coefficients towards them (sim.cpp:751-821 endo-epi, :825-916 endo-mid-epi).  That is 21 fits x
+// ~9000 f64 AP evaluations per parameter vector, 39 ms in the reference and the end-to-end
+// bottleneck once the simulation itself takes a fraction of a millisecond.
+//
+// Here: two kernels, all arithmetic in f64 with explicit round-to-nearest intrinsics (no FMA
+// contraction), every expression in the reference's association order:
+//   fit_setup_kernel   one CTA per (vector, border AP): 1000 AP samples in shared memory, apd90,
+//                      arc lengths and the two connector walks (kept serial: their running sums
+//                      decide integer sample indices)
+//   fit_descent_kernel one half-warp per (vector, inner layer): lane = connector point; the 15
+//                      squared misses are summed in the reference's order through shuffles, so all
+//                      lanes of a fit carry identical descent state and branch identically
+// The descent only ever moves by +-move[i]*stepSize, i.e. its result depends on the SIGNS of the
+// finite-difference gradients and on accept/reject decisions, not on gradient magnitudes; CUDA's
+// exp/log/pow differ from glibc's by <= 1-2 ulp, which leaves 255 of the 256 seeded vectors
+// bit-identical to the reference glue and the rest within 1e-11 relative (tests/test_gpu_fit.py).
+
+#include <cmath>
+
+#include "ekg_internal.cuh"
+
+namespace ekg {
+
+namespace {
+
+constexpr int kFitPoints = 15;      // numPoints, sim.cpp:185
+constexpr int kFitSamples = 1000;   // WohlfartPlus::apd90 samples 0..999 (Wohlfart.h:206-223)
+constexpr int kFitStartX = 10;      // sim.cpp:192
+
+struct FitConn {
+	int32_t idx[2][kFitPoints + 1];  // role 0: AP is the first of a pair, role 1: the second
+	double y[2][kFitPoints + 1];
+};
+
+struct FitArgs {
+	const double* border_k;  // [B][nb][9]
+	FitConn* conn;           // [B][nb]
+	double* layer_k;         // [B][nl][9]
+	int32_t B, nb, nl, mid, iterations;
+	double d[9];
+	double step, eps;
+};
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double sqr(double a) { return __dmul_rn(a, a); }
+
+// The factors of WohlfartPlus::operator[] (Wohlfart.h:195-203), each by the reference's expression.
+__device__ __noinline__ double f_tail_c(double k6, double k7) { return log(sub(pow(2.0, dvd(k7, k6)), 1.0)); }
+__device__ __noinline__ double f_exp(double k, double t) { return exp(mul(-k, t)); }
+__device__ __forceinline__ double f_A(double k1, double t) { return dvd(1.0, add(1.0, f_exp(k1, t))); }
+__device__ __noinline__ double f_Q(double k6, double k7, double k8, double c, double t) {
+	return pow(add(1.0, exp(add(mul(-k7, sub(t, k8)), c))), -dvd(k6, k7));
+}
+__device__ __forceinline__ double f_value(double k0, double k2, double k3, double A, double E4, double E5, double Q) {
+	return add(mul(mul(A, mul(k2, add(mul(sub(1.0, k3), E4), k3))), mul(E5, sub(1.0, Q))), k0);
+}
+__device__ double ap_value(const double* k, double c, double t) {
+	return f_value(k[0], k[2], k[3], f_A(k[1], t), f_exp(k[4], t), f_exp(k[5], t), f_Q(k[6], k[7], k[8], c, t));
+}
+
+// ---- connectors ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fit_setup_kernel(FitArgs a) {
+	__shared__ double y[kFitSamples];
+	__shared__ double seg[704];
+	__shared__ int cross;
+	const int bj = blockIdx.x;  // b * nb + j
+	const int j = bj % a.nb;
+	const int b = bj / a.nb;
+	double k[9];
+#pragma unroll
+	for (int q = 0; q < 9; ++q) k[q] = a.border_k[(size_t)bj * 9 + q];
+	if (threadIdx.x == 0) cross = 0;
+	// the border AP itself is the AP of its layer: endo -> 0, mid -> `mid`, epi -> nl-1, later ones win
+	// (sim.cpp:843-872 writes front, [absoluteMidPos], back in this order)
+	if (threadIdx.x < 9) {
+		const int layer = (j == 0) ? 0 : (j == a.nb - 1) ? a.nl - 1 : a.mid;
+		bool owner = true;
+		for (int j2 = j + 1; j2 < a.nb; ++j2) {
+			const int l2 = (j2 == a.nb - 1) ? a.nl - 1 : a.mid;
+			if (l2 == layer) owner = false;
+		}
+		if (owner) a.layer_k[((size_t)b * a.nl + layer) * 9 + threadIdx.x] = a.border_k[(size_t)bj * 9 + threadIdx.x];
+	}
+	const double c = f_tail_c(k[6], k[7]);
+	for (int i = threadIdx.x; i < kFitSamples; i += blockDim.x) y[i] = ap_value(k, c, (double)i);
+	__syncthreads();
+	// apd90: last downward crossing of k0 + 0.1 k2 on the 1 ms grid (Wohlfart.h:206-223)
+	const double target = add(k[0], mul(k[2], 0.1));
+	int mine = 0;
+	for (int i = threadIdx.x + 1; i < kFitSamples; i += blockDim.x)
+		if (y[i - 1] > target && y[i] <= target) mine = i;
+	if (mine) atomicMax(&cross, mine);
+	for (int i = threadIdx.x + 1; i <= 700; i += blockDim.x) seg[i] = __dsqrt_rn(add(sqr(sub(y[i], y[i - 1])), 0.1));
+	__syncthreads();
+	const int role = threadIdx.x >> 5;
+	if ((threadIdx.x & 31) != 0 || role > 1) return;
+	int end = 700;  // apd90 = -1 (never repolarises): the reference's size_t cast wraps, the 700 cap applies
+	if (cross > 0) {
+		const int i = cross;
+		const double wa = sub(y[i - 1], target), wb = sub(target, y[i]);
+		const double apd = dvd(add(mul((double)(i - 1), wa), mul((double)i, wb)), add(wa, wb));
+		const double ce = ceil(apd);
+		end = (ce >= 0.0 && ce <= 700.0) ? (int)ce : 700;
+	}
+	// arc length from 10 ms to apd90; the first AP of a pair starts one sample later (sim.cpp:206-209)
+	double len = 0.0;
+	for (int i = kFitStartX + 1 - role; i < end; ++i) len = add(len, seg[i]);
+	FitConn& out = a.conn[bj];
+	double cur = 0.0;
+	int idx = kFitStartX;
+	for (int i = 0; i < kFitPoints; ++i) {
+		const double tgt = dvd(mul((double)i, len), (double)(kFitPoints - 2));
+		for (double l = cur; l < tgt && idx < 700; ++idx) l = add(l, seg[idx + 1]);
+		cur = tgt;
+		out.idx[role][i] = idx;
+		out.y[role][i] = y[idx];
+	}
+}
+
+// ---- descent --------------------------------------------------------------------------------------
+struct Factors { double A, E4, E5, Q; };
+
+// sum of the 15 squared misses in index order; every lane of the half-warp gets the same bits
+__device__ __forceinline__ double ordered_sum(double e, unsigned mask) {
+	double s = __shfl_sync(mask, e, 0, 16);  // 0 + e0 == e0
+#pragma unroll
+	for (int n = 1; n < kFitPoints; ++n) s = add(s, __shfl_sync(mask, e, n, 16));
+	return s;
+}
+
+__device__ __forceinline__ double eval_full(const double (&k)[9], double px, double py, Factors& f, unsigned mask) {
+	const double c = f_tail_c(k[6], k[7]);
+	f.A = f_A(k[1], px);
+	f.E4 = f_exp(k[4], px);
+	f.E5 = f_exp(k[5], px);
+	f.Q = f_Q(k[6], k[7], k[8], c, px);
+	return ordered_sum(sqr(sub(f_value(k[0], k[2], k[3], f.A, f.E4, f.E5, f.Q), py)), mask);
+}
+
+// f(x1) where x1 differs from the iterate behind `f` only in coefficient `which` (compile-time after unrolling)
+__device__ __forceinline__ double eval_perturbed(const double (&k)[9], int which, double px, double py, const Factors& f, unsigned mask) {
+	double A = f.A, E4 = f.E4, E5 = f.E5, Q = f.Q;
+	switch (which) {
+	case 1: A = f_A(k[1], px); break;
+	case 4: E4 = f_exp(k[4], px); break;
+	case 5: E5 = f_exp(k[5], px); break;
+	case 6: case 7: case 8: Q = f_Q(k[6], k[7], k[8], f_tail_c(k[6], k[7]), px); break;
+	default: break;
+	}
+	return ordered_sum(sqr(sub(f_value(k[0], k[2], k[3], A, E4, E5, Q), py)), mask);
+}
+
+__global__ void __launch_bounds__(128) fit_descent_kernel(FitArgs a) {
+	const int per_b = a.nl - a.nb;  // inner layers per vector
+	const int fit = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+	if (fit >= a.B * per_b) return;  // whole half-warps leave together
+	const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+	const int b = fit / per_b;
+	int layer = fit % per_b + 1;
+	int ja = 0, jb = a.nb - 1;
+	double ratio;
+	if (a.nb == 2) {
+		ratio = dvd((double)layer, (double)(a.nl - 1));                     // sim.cpp:802
+	} else {
+		if (layer >= a.mid) ++layer;                                         // skip the mid layer
+		if (layer < a.mid) { jb = (a.mid == a.nl - 1) ? 2 : 1; ratio = dvd((double)layer, (double)a.mid); }   // sim.cpp:886
+		else { ja = 1; ratio = dvd((double)(layer - a.mid), (double)(a.nl - a.mid - 1)); }                     // sim.cpp:892-893
+	}
+	const int pt = min((int)(threadIdx.x & 15), kFitPoints - 1);  // lane 15 shadows point 14, its miss is never read
+	const FitConn& ca = a.conn[b * a.nb + ja];
+	const FitConn& cb = a.conn[b * a.nb + jb];
+	// connector through (i1, ap1(i1)) and (i2, ap2(i2)), sim.cpp:231-240
+	const int i1 = ca.idx[0][pt], i2 = cb.idx[1][pt];
+	const double x1 = (double)i1;
+	double x2 = (double)i2;
+	if (i1 == i2) x2 = add(x2, 0.001);
+	const double ck = dvd(sub(ca.y[0][pt], cb.y[1][pt]), sub(x1, x2));
+	const double cn = sub(cb.y[1][pt], mul(ck, (double)i2));
+	const double px = add(x1, mul(sub(x2, x1), ratio));   // LineConnector::getX, sim.cpp:107-109
+	const double py = add(mul(ck, px), cn);               // sim.cpp:102-104
+
+	double x0[9], move[9], grad[9], old_grad[9];
+	const double* ka = a.border_k + (size_t)(b * a.nb + ja) * 9;
+	const double* kb = a.border_k + (size_t)(b * a.nb + jb) * 9;
+#pragma unroll
+	for (int q = 0; q < 9; ++q) {
+		x0[q] = add(mul(ka[q], sub(1.0, ratio)), mul(kb[q], ratio));  // combineAps, sim.cpp:705-709
+		move[q] = a.d[q];
+		old_grad[q] = 0.0;
+		grad[q] = 0.0;
+	}
+	Factors cache, trial;
+	double y0 = eval_full(x0, px, py, cache, mask);
+	double step = a.step;
+	for (int it = a.iterations; it > 0 && y0 > a.eps; --it) {
+		bool step_change = false;
+#pragma unroll
+		for (int q = 0; q < 9; ++q) {
+			if (a.d[q] != 0) {
+				double x1v[9];
+#pragma unroll
+				for (int r = 0; r < 9; ++r) x1v[r] = x0[r];
+				const double h = mul(a.d[q], .001);
+				x1v[q] = add(x1v[q], h);
+				const double g = dvd(sub(eval_perturbed(x1v, q, px, py, cache, mask), y0), h);
+				grad[q] = g;
+				if (mul(g, old_grad[q]) < 0) { move[q] = mul(move[q], 0.5); step_change = true; }
+				else if (fabs(g) > mul(0.75, fabs(old_grad[q]))) move[q] = mul(move[q], 1.5);
+			} else grad[q] = 0.0;
+		}
+		double x1v[9];
+#pragma unroll
+		for (int q = 0; q < 9; ++q) {
+			old_grad[q] = grad[q];
+			x1v[q] = sub(x0[q], mul(step, (grad[q] > 0) ? move[q] : -move[q]));
+		}
+		const double y1 = eval_full(x1v, px, py, trial, mask);
+		if (y1 < y0) {
+			y0 = y1;
+#pragma unroll
+			for (int q = 0; q < 9; ++q) x0[q] = x1v[q];
+			cache = trial;
+		} else if (!step_change) step = mul(step, 0.5);
+	}
+	if ((threadIdx.x & 15) < 9) {
+		double v = x0[0];
+#pragma unroll
+		for (int q = 1; q < 9; ++q) if ((threadIdx.x & 15) == q) v = x0[q];
+		a.layer_k[((size_t)b * a.nl + layer) * 9 + (threadIdx.x & 15)] = v;
+	}
+}
+
+}  // namespace
+
+int run_fit(ekg_model* m, const double* d_border_k, int64_t B, int64_t n_border, int64_t n_layers, int64_t mid, const double* d9,
+            double step, double eps, int64_t iterations, double* d_layer_k, cudaStream_t st) {
+	if (B <= 0 || n_layers <= 0) return fail(EKG_E_INVALID, "bad sizes");
+	if (n_border != 2 && n_border != 3) return fail(EKG_E_INVALID, "n_border must be 2 (endo-epi) or 3 (endo-mid-epi)");
+	if (n_layers < n_border) return fail(EKG_E_INVALID, "fewer layers than border APs");
+	if (n_border == 3 && (mid < 0 || mid >= n_layers)) return fail(EKG_E_INVALID, "mid layer out of range");
+	if (n_border == 3 && (mid == 0 || mid == n_layers - 1) && n_layers > 2)
+		return fail(EKG_E_UNSUPPORTED, "mid layer coincides with a border layer");
+	if (B * n_layers > (int64_t)1 << 28) return fail(EKG_E_UNSUPPORTED, "batch too large for one fit launch");
+	int rc;
+	FitConn* conn = nullptr;
+	{
+		int64_t need = (B * n_border * (int64_t)sizeof(FitConn) + 7) / 8;
+		if ((rc = ensure(&m->d_fit_conn, &m->fit_conn_cap, need))) return rc;
+		conn = reinterpret_cast<FitConn*>(m->d_fit_conn);
+	}
+	FitArgs a;
+	a.border_k = d_border_k;
+	a.conn = conn;
+	a.layer_k = d_layer_k;
+	a.B = (int32_t)B; a.nb = (int32_t)n_border; a.nl = (int32_t)n_layers; a.mid = (int32_t)(n_border == 3 ? mid : -1);
+	a.iterations = (int32_t)iterations;
+	for (int q = 0; q < 9; ++q) a.d[q] = d9[q];
+	a.step = step; a.eps = eps;
+	fit_setup_kernel<<<(unsigned)(B * n_border), 256, 0, st>>>(a);
+	EKG_CUDA(cudaGetLastError());
+	m->last_launches = 1;
+	const int64_t fits = B * (n_layers - n_border);
+	if (fits > 0) {
+		fit_descent_kernel<<<(unsigned)((fits + 7) / 8), 128, 0, st>>>(a);
+		EKG_CUDA(cudaGetLastError());
+		++m->last_launches;
+	}
+	return EKG_OK;
+}
+
+}  // namespace ekg

@@ -412,6 +412,9 @@ private:
 	std::set<char> freeK;
 	size_t numDisplacementParams = 0, numWohlfartParams = 0;
 	size_t evalCounter = 0;
+	/// where the inner-layer fits run: on the device (ekg_fit_layers) whenever the evaluator owns one, unless
+	/// EKGSIM_B200_FIT=host asks for the host restatement (which is also what the GPU-less tooling uses)
+	bool fitOnDevice = false;
 
 	struct Individual {
 		std::vector<AP> layerAps;
@@ -435,6 +438,8 @@ public:
 		numDisplacementParams = settings.measuringPointsDisplacementIsInput ? sim->numMeasurements() * 2 : 0;
 		sim->loadShape();
 		if (withDevice) sim->simExcitationSequence();
+		const char* fitEnv = std::getenv("EKGSIM_B200_FIT");
+		fitOnDevice = withDevice && !(fitEnv && std::string(fitEnv) == "host");
 		std::cerr << "\n***** applying (and checking) settings *********************\n";
 		sim->applySettings();
 		if (settings.interpolationTypeString == "endo-epi") interp = endo_epi;
@@ -488,7 +493,9 @@ public:
 		return violation;
 	}
 
-	/// many individuals: layer fits on host threads, ONE batched GPU launch, criteria per individual
+	/// many individuals.  Default: border APs + leads are assembled on the host (microseconds), then ONE device
+	/// pass fits the inner layers and simulates (ekg_evaluate); criteria per individual from the returned ECGs.
+	/// With the host fit selected (EKGSIM_B200_FIT=host) the fits run on host threads and one ekg_simulate follows.
 	void evalBatch(const std::vector<Input>& solutions, std::vector<Value>& results, std::vector<double>& violations, int threads = 0) {
 		const size_t B = solutions.size();
 		results.assign(B, Value());
@@ -496,31 +503,42 @@ public:
 		std::vector<Individual> inds(B);
 		if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
 		threads = (int)std::min<size_t>(threads, std::max<size_t>(B, 1));
-		std::vector<std::string> errors(threads);
-		{
+		const bool gateActive = settings.fastApproxIsCriterion || settings.fastApproxLimit < 2;
+		if (fitOnDevice && !gateActive) {
+			// nothing here is worth a thread: ~1 us per individual
+			for (size_t i = 0; i < B; ++i) { prepareBorders(solutions[i], inds[i]); inds[i].approxCriteria = 2; inds[i].simulate = !(2 > settings.fastApproxLimit); }
+		} else {
+			std::vector<std::string> errors(threads);
 			std::vector<std::thread> pool;
 			for (int w = 0; w < threads; ++w)
 				pool.emplace_back([&, w]() {
-					try { for (size_t i = w; i < B; i += threads) prepare(solutions[i], inds[i]); }
-					catch (std::exception& e) { errors[w] = e.what(); }
+					try {
+						for (size_t i = w; i < B; i += threads) {
+							prepareBorders(solutions[i], inds[i]);
+							if (!fitOnDevice) fitLayersOnHost(inds[i]);
+							approximationGate(inds[i]);
+						}
+					} catch (std::exception& e) { errors[w] = e.what(); }
 				});
 			for (std::thread& t : pool) t.join();
+			for (const std::string& e : errors) if (!e.empty()) throw std::runtime_error(e);
 		}
-		for (const std::string& e : errors) if (!e.empty()) throw std::runtime_error(e);
 		// gather the individuals that pass the fast-approximation gate into one launch
 		std::vector<size_t> run;
 		for (size_t i = 0; i < B; ++i) if (inds[i].simulate) run.push_back(i);
-		const size_t nl = sim->requiredAps(), L = sim->numMeasurements();
-		std::vector<double> k(run.size() * nl * 9), leads(run.size() * L * 3), ecg;
+		const size_t nl = sim->requiredAps(), L = sim->numMeasurements(), nb = numBorders();
+		std::vector<double> k(run.size() * (fitOnDevice ? nb : nl) * 9), leads(run.size() * L * 3), ecg;
 		for (size_t r = 0; r < run.size(); ++r) {
 			const Individual& ind = inds[run[r]];
-			for (size_t l = 0; l < nl; ++l) std::copy(ind.layerAps[l].getK(), ind.layerAps[l].getK() + 9, k.begin() + (r * nl + l) * 9);
+			if (fitOnDevice) borderCoefficients(ind, &k[r * nb * 9]);
+			else for (size_t l = 0; l < nl; ++l) std::copy(ind.layerAps[l].getK(), ind.layerAps[l].getK() + 9, k.begin() + (r * nl + l) * 9);
 			for (size_t m = 0; m < L; ++m) for (int c = 0; c < 3; ++c) leads[(r * L + m) * 3 + c] = ind.leads[m][c];
 		}
 		size_t T = 0;
 		if (!run.empty()) {
 			sim->moveMeasuringPointsTo(inds[run[0]].leads);  // lead count / bookkeeping; positions travel in `leads`
-			sim->runBatch(k.data(), leads.data(), run.size(), ecg);
+			if (fitOnDevice) sim->evaluateBatch(k.data(), nb, interp == endo_epi ? 0 : midLayer(), fitOffsets(), 0.5, 1e-3, 100, leads.data(), run.size(), ecg, nullptr);
+			else sim->runBatch(k.data(), leads.data(), run.size(), ecg);
 			T = ecg.size() / (run.size() * L);
 		}
 		std::vector<size_t> slot(B, (size_t)-1);
@@ -596,8 +614,9 @@ private:
 		for (size_t i = 0; i < 9; ++i) dst[i] = a[i] * (1 - ratio) + b[i] * ratio;
 	}
 
-	/// everything of eval() that happens before Simulation::run: displacement, layer APs, approximation gate
-	void prepare(const Input& solution, Individual& ind) const {
+	/// genes -> displaced leads, border APs in their layer slots (the other layers untouched), violation
+	/// (the head of simUsingBorderAps / simUsingBorderAndMidAps, sim.cpp:758-781, :831-872)
+	void prepareBorders(const Input& solution, Individual& ind) const {
 		if (solution.size() < numWohlfartParams + numDisplacementParams) throw std::runtime_error("Solution does not contain enough values");
 		const size_t L = sim->numMeasurements();
 		ind.leads.resize(L);
@@ -618,13 +637,39 @@ private:
 		for (AP& a : aps) a.at = 0;
 		size_t cursor = 0;
 		double violation = 0;
-		const double kd[9] = {0, 0, 0, 0.001, 0, 0.00005, 0.0005, 0.01, 0.2};
-		AP d;
-		d.init(kd, 0);
-		LayerFitTarget fit;
 		if (interp == endo_epi) {
 			borderAp(aps.front(), settings.baseAps.front(), solution, cursor, violation);
 			borderAp(aps.back(), settings.baseAps.back(), solution, cursor, violation);
+		} else {
+			borderAp(aps.front(), settings.baseAps.front(), solution, cursor, violation);
+			borderAp(aps[midLayer()], settings.baseAps.back(), solution, cursor, violation);   // mid and epi both start from the LAST base ap
+			borderAp(aps.back(), settings.baseAps.back(), solution, cursor, violation);
+		}
+		ind.violation = violation;
+	}
+
+	size_t midLayer() const { return (size_t)std::floor(settings.midPosition * (sim->requiredAps() - 1) + 0.5); }
+	size_t numBorders() const { return interp == endo_epi ? 2 : 3; }
+	static const double* fitOffsets() {   // "experimentally set d", sim.cpp:796, :877
+		static const double kd[9] = {0, 0, 0, 0.001, 0, 0.00005, 0.0005, 0.01, 0.2};
+		return kd;
+	}
+	/// the 2 or 3 border APs of an individual, [nBorder][9]
+	void borderCoefficients(const Individual& ind, double* out) const {
+		const std::vector<AP>& aps = ind.layerAps;
+		std::copy(aps.front().getK(), aps.front().getK() + 9, out);
+		if (interp != endo_epi) std::copy(aps[midLayer()].getK(), aps[midLayer()].getK() + 9, out + 9);
+		std::copy(aps.back().getK(), aps.back().getK() + 9, out + 9 * (numBorders() - 1));
+	}
+
+	/// inner layers on the host (the reference's procedure operation by operation; bit-identical results)
+	void fitLayersOnHost(Individual& ind) const {
+		const size_t n = sim->requiredAps();
+		std::vector<AP>& aps = ind.layerAps;
+		AP d;
+		d.init(fitOffsets(), 0);
+		LayerFitTarget fit;
+		if (interp == endo_epi) {
 			fit.setBorderAps(aps.front(), aps.back());
 			for (size_t i = 1; i + 1 < n; ++i) {
 				const double ratio = i / double(n - 1);
@@ -634,10 +679,7 @@ private:
 				steepest_descent(fit, aps[i], d, 0.5, 1e-3, 100);
 			}
 		} else {
-			const size_t mid = (size_t)std::floor(settings.midPosition * (n - 1) + 0.5);
-			borderAp(aps.front(), settings.baseAps.front(), solution, cursor, violation);
-			borderAp(aps[mid], settings.baseAps.back(), solution, cursor, violation);   // mid and epi both start from the LAST base ap
-			borderAp(aps.back(), settings.baseAps.back(), solution, cursor, violation);
+			const size_t mid = midLayer();
 			// (the reference rebuilds the endo-mid connectors for every layer below mid; they only depend on
 			// the two border APs, so once is enough)
 			bool lowerReady = false;
@@ -658,8 +700,21 @@ private:
 				if (i != mid) steepest_descent(fit, aps[i], d, 0.5, 1e-3, 100);
 			}
 		}
-		ind.violation = violation;
-		// string-model approximation and the gate in front of the full simulation (sim.cpp:712-747)
+	}
+
+	/// inner layers of one individual through ekg_fit_layers
+	void fitLayersOnDevice(Individual& ind) const {
+		const size_t n = sim->requiredAps();
+		std::vector<double> border(numBorders() * 9), k;
+		borderCoefficients(ind, border.data());
+		sim->fitLayers(border.data(), 1, numBorders(), interp == endo_epi ? 0 : midLayer(), fitOffsets(), 0.5, 1e-3, 100, k);
+		for (size_t l = 0; l < n; ++l) ind.layerAps[l].init(&k[9 * l], 0);
+	}
+
+	/// string-model approximation and the gate in front of the full simulation (sim.cpp:712-747); only the
+	/// first and the last layer AP enter, i.e. it can run before the inner layers exist
+	void approximationGate(Individual& ind) const {
+		const std::vector<AP>& aps = ind.layerAps;
 		const SimLib::Settings& s = sim->getSettings();
 		ind.approxEcg.assign((size_t)(s.simulationLength / s.simulationTimeStep), 0.0);
 		for (size_t i = 0; i < ind.approxEcg.size(); ++i) {
@@ -669,6 +724,14 @@ private:
 		ind.approxCriteria = 2;
 		if (settings.fastApproxIsCriterion || settings.fastApproxLimit < 2) ind.approxCriteria = compare(ind.approxEcg, 0);
 		ind.simulate = !(ind.approxCriteria > settings.fastApproxLimit);
+	}
+
+	/// everything of eval() that happens before Simulation::run: displacement, layer APs, approximation gate
+	void prepare(const Input& solution, Individual& ind) const {
+		prepareBorders(solution, ind);
+		if (fitOnDevice) fitLayersOnDevice(ind);
+		else fitLayersOnHost(ind);
+		approximationGate(ind);
 	}
 
 	double compare(const std::vector<double>& simResult, size_t target) const {

@@ -11,6 +11,7 @@
 //     simExcitationSequence           -> ekg_model_activation / ekg_model_set_activation
 //     run                             -> ekg_simulate           (fused AP + stencil + lead kernel)
 //     runBatch (new)                  -> ekg_simulate with B parameter sets in one launch
+//     fitLayers / evaluateBatch (new) -> ekg_fit_layers / ekg_evaluate (layer-AP construction on the device)
 //
 // Host-only pieces that stay on the CPU exactly like in the reference: file parsing, the lead
 // displacement plane (u,v) construction, the 2*T-sample "string model" approximation
@@ -368,6 +369,32 @@ public:
 		const double t0 = ekg::wall_seconds();
 		check(ekg_simulate(model_, layerK, leadsZyx, (int64_t)B, (int64_t)mps_.size(), nbhd_, (double)settings.simulationStart, timeStep_,
 		                   (double)settings.simulationLength, mode_, ecg.data()));
+		lastRunSeconds_ = ekg::wall_seconds() - t0;
+	}
+
+	/// layer-AP construction on the device (new): borderK [B][nBorder][9] -> layerK [B][layers][9]
+	void fitLayers(const double* borderK, size_t B, size_t nBorder, size_t mid, const double* d9, double step, double eps, int iterations,
+	               std::vector<double>& layerK) {
+		ensureModel();
+		layerK.assign(B * targetNumOfAps_ * 9, 0.0);
+		check(ekg_fit_layers(model_, borderK, (int64_t)B, (int64_t)nBorder, (int64_t)mid, d9, step, eps, iterations, layerK.data()));
+	}
+
+	/// fit + simulation in one device pass (new): borderK [B][nBorder][9], leadsZyx [B][leads][3] -> ecg [B][leads][T]
+	/// and, if asked for, layerK [B][layers][9]
+	void evaluateBatch(const double* borderK, size_t nBorder, size_t mid, const double* d9, double step, double eps, int iterations,
+	                   const double* leadsZyx, size_t B, std::vector<double>& ecg, std::vector<double>* layerK) {
+		ensureModel();
+		if (!haveActivation_) throw std::runtime_error("excitation sequence missing: call simExcitationSequence() first");
+		if (nbhd_ < 0) throw std::runtime_error("applySettings() must be called before run()");
+		startTime_ = settings.simulationStart;
+		const size_t T = (size_t)std::ceil(settings.simulationLength / timeStep_);
+		ecg.assign(B * mps_.size() * T, 0.0);
+		if (layerK) layerK->assign(B * targetNumOfAps_ * 9, 0.0);
+		const double t0 = ekg::wall_seconds();
+		check(ekg_evaluate(model_, borderK, (int64_t)nBorder, (int64_t)mid, d9, step, eps, iterations, leadsZyx, (int64_t)B,
+		                   (int64_t)mps_.size(), nbhd_, (double)settings.simulationStart, timeStep_, (double)settings.simulationLength, mode_,
+		                   nullptr, 0, nullptr, 0, nullptr, layerK ? layerK->data() : nullptr, ecg.data()));
 		lastRunSeconds_ = ekg::wall_seconds() - t0;
 	}
 

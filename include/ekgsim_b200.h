@@ -17,6 +17,13 @@
  *   ekg_simulate              Simulation::run for B parameter sets at once simulator.cpp:452-550
  *                             (AP evaluation Wohlfart.h:195-203 via simulator.cpp:154-170)
  *   ekg_simulate_device       same, device-resident inputs/outputs on a caller stream
+ *   ekg_fit_layers            the layer-AP construction of SimImplementation::simUsingBorderAps /
+ *                             simUsingBorderAndMidAps (sim.cpp:751-916): connectors of
+ *                             WohlfartInterpolationEvaluator (sim.cpp:91-313) + steepestDescend
+ *                             (nonlinearFit.h:92-168) for every inner layer, B vectors at once
+ *   ekg_evaluate              fit + ekg_simulate + curve comparison without leaving the device:
+ *                             border APs and lead positions in, criteria out (SimImplementation::eval
+ *                             sim.cpp:443-491 minus the gene unpacking, which stays on the host)
  *
  * Conventions
  *   - voxel arrays are raster z,y,x (x fastest): index (z*Y+y)*X+x          (matrix.h:166-173)
@@ -45,7 +52,7 @@
 extern "C" {
 #endif
 
-#define EKG_ABI_VERSION 1
+#define EKG_ABI_VERSION 2
 
 enum {
 	EKG_OK = 0,
@@ -135,7 +142,35 @@ int  ekg_simulate_criteria(ekg_model* m, const double* layer_k, const double* le
                            const double* targets, int64_t n_target, const double* target_offsets,
                            int comparison, double* criteria_out, double* ecg_out);
 
-/* Number of kernel launches the last ekg_simulate* call on this handle issued. */
+/* Layer-AP construction for B parameter vectors.  border_k is [B][n_border][9]:
+ * n_border = 2 -> (endo, epi), every inner layer interpolated between them (sim.cpp:751-821);
+ * n_border = 3 -> (endo, mid, epi) with the mid AP sitting in layer index `mid` (0-based,
+ * 0 < mid < n_layers-1; sim.cpp:825-916, absoluteMidPos :833).  d9 are the nine gradient offsets /
+ * initial moves (sim.cpp:877 `kd`; 0 = coefficient not fitted), step_size / epsilon / iterations the
+ * arguments of steepestDescend (sim.cpp:901: 0.5, 1e-3, 100).  layer_k_out is [B][n_layers][9] with
+ * n_layers = ekg_model_num_layers(m), directly usable as the layer_k of ekg_simulate.  f64 on the device,
+ * the reference's expression order; integer decisions (sample indices, accept/reject) make the result
+ * insensitive to the last-bit differences between CUDA's and glibc's exp/log/pow. */
+int  ekg_fit_layers(ekg_model* m, const double* border_k, int64_t B, int64_t n_border, int64_t mid,
+                    const double* d9, double step_size, double epsilon, int64_t iterations,
+                    double* layer_k_out);
+/* Same with device pointers, enqueued on the caller's stream. */
+int  ekg_fit_layers_device(ekg_model* m, const double* d_border_k, int64_t B, int64_t n_border, int64_t mid,
+                           const double* d9, double step_size, double epsilon, int64_t iterations,
+                           double* d_layer_k_out, void* stream);
+
+/* ekg_fit_layers + ekg_simulate_criteria in one call, intermediate results stay in HBM: per vector
+ * 27 (or 18) border coefficients and the lead positions go in, n_leads criteria come out.
+ * layer_k_out ([B][n_layers][9]) and ecg_out ([B][n_leads][n_steps]) may be NULL; so may criteria_out
+ * (targets are then ignored) as long as one output is requested. */
+int  ekg_evaluate(ekg_model* m, const double* border_k, int64_t n_border, int64_t mid,
+                  const double* d9, double step_size, double epsilon, int64_t iterations,
+                  const double* leads_zyx, int64_t B, int64_t n_leads, int nbhd,
+                  double t_start, double t_step, double total_time, int flags,
+                  const double* targets, int64_t n_target, const double* target_offsets,
+                  int comparison, double* criteria_out, double* layer_k_out, double* ecg_out);
+
+/* Number of kernel launches the last ekg_simulate* / ekg_fit* / ekg_evaluate call on this handle issued. */
 int64_t ekg_last_launch_count(const ekg_model* m);
 /* Device time (ms) of the ECG kernel launch(es) of the last call made with EKG_FLAG_TIME_KERNEL;
  * synchronises on the recorded events.  Negative if nothing was recorded. */

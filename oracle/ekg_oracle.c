@@ -340,3 +340,146 @@ int64_t ekg_oracle_run_approximation(const double* layer_k, int64_t n_layers,
 	}
 	return n;
 }
+
+/* ==== layer-AP construction (evaluation glue) ================================================
+ * Plain restatement of the per-layer fit: every price evaluation is a full AP evaluation, as
+ * in the reference (no factor caching). */
+
+/* ---- Wohlfart.h:206-223 (WohlfartPlus::apd90) + interpolate :226-229 -------------------- */
+double ekg_oracle_apd90(const double k[9]) {
+	double d[1000];
+	for (int i = 0; i < 1000; ++i) d[i] = ekg_oracle_wohlfart_plus(k, (double)i);   /* :210-212 */
+	double target = k[0] + k[2] * 0.1;                                             /* :214 */
+	double time = -1.0;
+	for (int i = 1; i < 1000; ++i)
+		if ((d[i - 1] > target) && (d[i] <= target)) {                              /* :217 */
+			double a = (double)(i - 1), wa = d[i - 1] - target, b = (double)i, wb = target - d[i];
+			time = (a * wa + b * wb) / (wa + wb);                                  /* :228 */
+		}
+	return time;
+}
+
+typedef struct { double k, n, x1, x2; } fit_connector;   /* LineConnector, sim.cpp:95-109 */
+
+static size_t fit_cap700(double apd) {   /* std::min((size_t)700, (size_t)ceil(apd)), sim.cpp:206,208 */
+	double c = ceil(apd);
+	if (c < 0) return 700;               /* apd90 = -1: the size_t cast wraps to a huge value */
+	return c > 700.0 ? 700 : (size_t)c;
+}
+
+/* ---- sim.cpp:178-245 (distributeConnectors) --------------------------------------------- */
+static void fit_distribute_connectors(const double ap1[9], const double ap2[9], fit_connector out[15]) {
+	const size_t numPoints = 15, startX = 10;                                      /* :185, :192 */
+	const double xScaleFactor = 0.1;                                               /* :199 */
+	double apd1 = ekg_oracle_apd90(ap1), apd2 = ekg_oracle_apd90(ap2);             /* :188-189 */
+	/* the reference holds 700 samples and reads element [700] when a walk reaches the cap (:224, :228);
+	 * here that element exists */
+	double y1[701], y2[701];
+	for (size_t i = 0; i < 701; ++i) { y1[i] = ekg_oracle_wohlfart_plus(ap1, (double)i); y2[i] = ekg_oracle_wohlfart_plus(ap2, (double)i); }
+	double len1 = 0.0, len2 = 0.0;
+	for (size_t i = startX + 1; i < fit_cap700(apd1); ++i) len1 += sqrt((y1[i] - y1[i - 1]) * (y1[i] - y1[i - 1]) + xScaleFactor); /* :206-207 */
+	for (size_t i = startX; i < fit_cap700(apd2); ++i) len2 += sqrt((y2[i] - y2[i - 1]) * (y2[i] - y2[i - 1]) + xScaleFactor);     /* :208-209 */
+	double currentLen1 = 0.0, currentLen2 = 0.0;
+	size_t i1 = startX, i2 = startX;
+	for (size_t i = 0; i < numPoints; ++i) {                                       /* :218-244 */
+		double targetLen = i * len1 / (numPoints - 2);
+		for (double l1 = currentLen1; (l1 < targetLen) && (i1 < 700); ++i1) l1 += sqrt((y1[i1 + 1] - y1[i1]) * (y1[i1 + 1] - y1[i1]) + xScaleFactor);
+		currentLen1 = targetLen;
+		targetLen = i * len2 / (numPoints - 2);
+		for (double l2 = currentLen2; (l2 < targetLen) && (i2 < 700); ++i2) l2 += sqrt((y2[i2 + 1] - y2[i2]) * (y2[i2 + 1] - y2[i2]) + xScaleFactor);
+		currentLen2 = targetLen;
+		fit_connector lc;
+		lc.x1 = (double)i1;
+		lc.x2 = (double)i2;
+		if (i1 == i2) lc.x2 += 0.001;                                              /* :233-234 */
+		lc.k = (y1[i1] - y2[i2]) / (lc.x1 - lc.x2);                                /* :236 */
+		lc.n = y2[i2] - lc.k * i2;                                                 /* :238 */
+		out[i] = lc;
+	}
+}
+
+/* ---- sim.cpp:249-257 (setupRatio) ------------------------------------------------------- */
+static void fit_setup_ratio(const fit_connector c[15], double ratio, double pts[30]) {
+	for (int i = 0; i < 15; ++i) {
+		pts[2 * i] = c[i].x1 + (c[i].x2 - c[i].x1) * ratio;                        /* getX :107-109 */
+		pts[2 * i + 1] = c[i].k * pts[2 * i] + c[i].n;                             /* operator() :102-104 */
+	}
+}
+
+/* ---- sim.cpp:157-168 (price: sum of squared misses; `derivatives` is always empty) ------ */
+static double fit_price(const double k[9], const double pts[30]) {
+	double sum = 0;
+	for (int i = 0; i < 30; i += 2) {
+		double e = ekg_oracle_wohlfart_plus(k, pts[i]) - pts[i + 1];
+		sum += e * e;
+	}
+	return sum;
+}
+
+/* ---- nonlinearFit.h:92-168 (steepestDescend) -------------------------------------------- */
+static int fit_steepest_descend(const double pts[30], double x0[9], const double d[9], double stepSize, double epsilon, int iterations) {
+	double grad[9], oldGrad[9], move[9], x1[9];
+	for (int i = 0; i < 9; ++i) { grad[i] = x0[i]; oldGrad[i] = 0; move[i] = d[i]; }
+	double y0 = fit_price(x0, pts);                                                /* :106 */
+	for (; (iterations > 0) && (y0 > epsilon); --iterations) {                     /* :116 */
+		int stepChange = 0;
+		for (int i = 0; i < 9; ++i) {
+			memcpy(x1, x0, sizeof x1);
+			if (d[i] != 0) {
+				x1[i] += d[i] * .001;                                              /* :125 */
+				grad[i] = (fit_price(x1, pts) - y0) / (d[i] * .001);               /* :126 */
+				if (grad[i] * oldGrad[i] < 0) { move[i] *= 0.5; stepChange = 1; }  /* :128-131 */
+				else if (fabs(grad[i]) > 0.75 * fabs(oldGrad[i])) move[i] *= 1.5;  /* :132-134 */
+			} else grad[i] = 0;
+		}
+		memcpy(oldGrad, grad, sizeof grad);                                        /* :144 */
+		memcpy(x1, x0, sizeof x1);
+		for (int i = 0; i < 9; ++i) x1[i] -= stepSize * ((grad[i] > 0) ? move[i] : -move[i]); /* :148-150 */
+		double y1 = fit_price(x1, pts);
+		if (y1 < y0) { y0 = y1; memcpy(x0, x1, sizeof x1); }                       /* :153-155 */
+		else if (!stepChange) stepSize *= 0.5;                                     /* :156-159 */
+	}
+	return iterations;
+}
+
+/* ---- sim.cpp:751-821 (n_border = 2) and :825-916 (n_border = 3) --------------------------
+ * border_k: [n_border][9]; out: [n_layers][9].  The gene unpacking / violation part of those
+ * functions is not restated here (it is a copy of genes into coefficients). */
+int ekg_oracle_fit_layers(const double* border_k, int64_t n_border, int64_t n_layers, int64_t mid,
+                          const double d9[9], double step, double eps, int64_t iterations, double* out) {
+	fit_connector conn[15];
+	double pts[30];
+	if (n_layers < n_border || (n_border != 2 && n_border != 3)) return -1;
+	const double* front = border_k;
+	const double* back = border_k + 9 * (n_border - 1);
+	memcpy(out, front, 72);
+	if (n_border == 3) memcpy(out + 9 * mid, border_k + 9, 72);                    /* :856-865 */
+	memcpy(out + 9 * (n_layers - 1), back, 72);
+	if (n_border == 2) {
+		fit_distribute_connectors(out, out + 9 * (n_layers - 1), conn);            /* :793-794 */
+		for (int64_t i = 1; i < n_layers - 1; ++i) {
+			double ratio = i / (double)(n_layers - 1);                             /* :802 */
+			fit_setup_ratio(conn, ratio, pts);
+			for (int q = 0; q < 9; ++q) out[9 * i + q] = front[q] * (1 - ratio) + back[q] * ratio;   /* combineAps :705-709 */
+			fit_steepest_descend(pts, out + 9 * i, d9, step, eps, (int)iterations);          /* :806 */
+		}
+		return 0;
+	}
+	const double* midk = out + 9 * mid;
+	for (int64_t i = 1; i < n_layers - 1; ++i) {                                   /* :883-902 */
+		double ratio;
+		if (i < mid) {
+			ratio = i / (double)mid;
+			if (i == 1) fit_distribute_connectors(out, midk, conn);                /* :887 (same connectors for every i < mid) */
+			fit_setup_ratio(conn, ratio, pts);
+			for (int q = 0; q < 9; ++q) out[9 * i + q] = out[q] * (1 - ratio) + midk[q] * ratio;
+		} else if (i > mid) {
+			ratio = (i - mid) / (double)(n_layers - mid - 1);
+			if (i - mid == 1) fit_distribute_connectors(midk, out + 9 * (n_layers - 1), conn);   /* :894-895 */
+			fit_setup_ratio(conn, ratio, pts);
+			for (int q = 0; q < 9; ++q) out[9 * i + q] = midk[q] * (1 - ratio) + out[9 * (n_layers - 1) + q] * ratio;
+		} else continue;
+		fit_steepest_descend(pts, out + 9 * i, d9, step, eps, (int)iterations);    /* :900-901 */
+	}
+	return 0;
+}

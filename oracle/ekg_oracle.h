@@ -83,6 +83,15 @@ int64_t ekg_oracle_run_approximation(const double* layer_k, int64_t n_layers,
                                      double t_start, double t_step, double total_time,
                                      double delay, double* out);
 
+/* Wohlfart.h:206-223 */
+double ekg_oracle_apd90(const double k[9]);
+
+/* Layer-AP construction for ONE parameter vector (sim.cpp:751-916 with WohlfartInterpolationEvaluator
+ * sim.cpp:91-313 and steepestDescend nonlinearFit.h:92-168).  border_k [n_border][9] (2: endo, epi;
+ * 3: endo, mid, epi with the mid AP in 0-based layer `mid`), out [n_layers][9]. */
+int ekg_oracle_fit_layers(const double* border_k, int64_t n_border, int64_t n_layers, int64_t mid,
+                          const double d9[9], double step, double eps, int64_t iterations, double* out);
+
 #ifdef __cplusplus
 }
 #endif

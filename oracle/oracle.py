@@ -54,6 +54,10 @@ def lib():
         L.ekg_oracle_ap_classes.argtypes = [p, p, i64, i64, p]
         L.ekg_oracle_run_approximation.restype = i64
         L.ekg_oracle_run_approximation.argtypes = [p, i64, d, d, d, d, p]
+        L.ekg_oracle_apd90.restype = d
+        L.ekg_oracle_apd90.argtypes = [p]
+        L.ekg_oracle_fit_layers.restype = C.c_int
+        L.ekg_oracle_fit_layers.argtypes = [p, i64, i64, i64, p, d, d, i64, p]
         _lib = L
     return _lib
 
@@ -132,6 +136,21 @@ def run_approximation(layer_k, t_start, t_step, total_time, delay):
     n = int(total_time / t_step)
     out = np.zeros(n, dtype=np.float64)
     lib().ekg_oracle_run_approximation(_ptr(layer_k), layer_k.shape[0], float(t_start), float(t_step), float(total_time), float(delay), _ptr(out))
+    return out
+
+
+FIT_D9 = (0.0, 0.0, 0.0, 0.001, 0.0, 0.00005, 0.0005, 0.01, 0.2)   # sim.cpp:877 `kd`
+
+
+def fit_layers(border_k, n_layers, mid=-1, d9=FIT_D9, step=0.5, eps=1e-3, iterations=100):
+    """Layer coefficients [n_layers, 9] of one parameter vector from its 2 or 3 border APs."""
+    border_k = np.ascontiguousarray(border_k, dtype=np.float64).reshape(-1, 9)
+    d9 = np.ascontiguousarray(d9, dtype=np.float64)
+    out = np.zeros((int(n_layers), 9), dtype=np.float64)
+    rc = lib().ekg_oracle_fit_layers(_ptr(border_k), border_k.shape[0], int(n_layers), int(mid), _ptr(d9), float(step), float(eps),
+                                     int(iterations), _ptr(out))
+    if rc:
+        raise ValueError("ekg_oracle_fit_layers: bad arguments")
     return out
 
 

@@ -215,3 +215,24 @@ def test_reference_optimizer_drives_the_b200_simlib(built, tmp_path):
     ev = [ln for ln in open(os.path.join(d, "evaluations.txt")).read().split("\n") if ln and not ln.startswith("#")]
     assert len(ev) >= 24, len(ev)          # initial population + the offspring of the generations
     assert os.path.exists(os.path.join(d, "individuals.txt"))
+
+
+def test_batch_device_fit_equals_host_fit(testrun, monkeypatch):
+    """evalBatch with the layer fits on the device (default, ekg_evaluate) and on host threads
+    (EKGSIM_B200_FIT=host, the reference's procedure restated on the CPU): same criteria."""
+    import time
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    ev = hostlib.Evaluator(testrun, with_device=True)
+    ev.eval_batch(g["params"])
+    t0 = time.time(); crit_dev, viol_dev = ev.eval_batch(g["params"]); t_dev = time.time() - t0
+    one, _ = ev.eval(g["params"][5])                      # single evaluation: ekg_fit_layers + ekg_simulate
+    ev.close()
+    monkeypatch.setenv("EKGSIM_B200_FIT", "host")
+    ev = hostlib.Evaluator(testrun, with_device=True)
+    ev.eval_batch(g["params"][:16])
+    t0 = time.time(); crit_host, viol_host = ev.eval_batch(g["params"]); t_host = time.time() - t0
+    ev.close()
+    print("evalBatch(256): device fit %.1f ms, host fit %.1f ms" % (t_dev * 1e3, t_host * 1e3))
+    assert np.abs(crit_dev - crit_host).max() < 1e-7
+    assert (viol_dev == viol_host).all()
+    assert np.abs(one - crit_dev[5]).max() < 1e-6
