@@ -52,7 +52,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn};
+	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_k1min};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -109,7 +109,8 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 	if ((rc = upload(m, m->d_ecg_pidx, pidx.data(), (size_t)n * 4))) return rc;
 	m->n_ecg = n;
 	m->slab_z0 = z0; m->slab_z1 = z1;
-	m->n_segs = 0; m->seg_len = 0;  // segment table depends on the list
+	m->n_segs = 0; m->seg_len = 0;  // segment tables depend on the list
+	m->n_msegs = 0; m->mseg_len = 0;
 	return EKG_OK;
 }
 
@@ -139,6 +140,7 @@ static int publish_activation(ekg_model* m, bool download) {
 	double lo = INFINITY, hi = -INFINITY;
 	for (int64_t i = 0; i < n; ++i) if (m->h_layer[i]) { lo = std::min(lo, m->h_delay[i]); hi = std::max(hi, m->h_delay[i]); }
 	m->t0 = (lo <= hi) ? 0.5 * (lo + hi) : 0.0;
+	m->at_max = (lo <= hi) ? hi : 0.0;
 	m->have_activation = true;
 	return gather_at(m);
 }
@@ -475,7 +477,14 @@ static int simulate_host(ekg_model* m, const double* layer_k, const double* lead
 		if ((rc = run_fit(m, m->d_io_border, B, fit->n_border, m->n_layers, fit->mid, fit->d9, fit->step, fit->eps, fit->iterations, m->d_io_k, m->stream))) return rc;
 		fit_launches = m->last_launches;
 	}
-	rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, flags, m->d_io_ecg, m->stream);
+	// smallest depolarisation rate of the batch, known here without asking the device: the caller's layer
+	// coefficients, or -- with the device fit -- the border APs (k1 of an inner layer is the blend of its two
+	// border values unless d9[1] asks the descent to move it)
+	double k1_min = INFINITY;
+	if (!fit) for (int64_t i = 0; i < B * m->n_layers; ++i) k1_min = std::min(k1_min, layer_k[i * 9 + 1]);
+	else if (fit->d9[1] == 0) for (int64_t i = 0; i < B * fit->n_border; ++i) k1_min = std::min(k1_min, fit->border_k[i * 9 + 1]);
+	if (!(k1_min > 0) || !std::isfinite(k1_min)) k1_min = 0.0;
+	rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, flags, m->d_io_ecg, m->stream, k1_min);
 	if (rc) return rc;
 	std::vector<double> crit_host;
 	if (criteria_out) {

@@ -276,13 +276,159 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	}
 }
 
+// ---- SEPARABLE path -------------------------------------------------------------------------------
+// Once the depolarisation sigmoid has saturated for every voxel (all of a run that starts after the QRS
+// complex, like the reference's testRun: activation ends at 39 ms, the simulation starts at 100 ms), the AP
+// is  V_c(t) = k0 + F1(t) h1_c + F2(t) h2_c  with F1, F2 functions of (vector, layer, t) only and
+// h1_c = exp((k4+k5)(at_c - t0)), h2_c = exp(k5 (at_c - t0)) functions of (vector, layer, voxel) only --
+// the HOISTED kernel's saturated loop evaluates exactly this per voxel and sample.  The sum over voxels
+// then leaves the time loop as well:
+//     ECG_l(t) = sum_layers [ k0 M0 + F1(t) M1 + F2(t) M2 ],   (M0, M1, M2) = sum_{c in layer} G_{l,c} (1, h1_c, h2_c)
+// i.e. O(voxels) work per simulation instead of O(voxels x samples).  ecg_moment_kernel computes the
+// moments (the phase A arithmetic of ecg_kernel + two ex2 per voxel and vector), ecg_combine_kernel
+// evaluates F1, F2 in f64 and sums the 3 x layers terms per sample.
+//
+// Threads of a CTA = VB parameter vectors x 256/VB voxel lanes (VB = 32 for batches: a warp works on ONE
+// voxel for 32 vectors, voxel loads are broadcasts and the occupancy-mask branches are warp-uniform; VB = 1
+// for a single simulation: all 256 threads stride over voxels).  Lead positions and layer constants live in
+// registers; fp32 sums over 16 voxels are folded into f64; the voxel lanes are reduced in a fixed order.
+template <int NL>
+__global__ void __launch_bounds__(256) ecg_moment_kernel(const MomentArgs a) {
+	__shared__ double s_red[256 * NL * 3];
+	const Segment sg = a.segs[blockIdx.x];
+	const int vb = 1 << a.vb_shift;
+	const int vs = threadIdx.x & (vb - 1), vl = threadIdx.x >> a.vb_shift, lanes = 256 >> a.vb_shift;
+	const int b = blockIdx.y * vb + vs;
+	const int bb = min(b, a.B - 1);   // surplus vector slots shadow the last vector, their sums are dropped
+
+	float lh[NL * 3], ll[NL * 3];
+#pragma unroll
+	for (int r = 0; r < NL * 3; ++r) {
+		const int l = a.lead0 + r / 3;
+		const double c = l < a.L ? a.leads[((int64_t)bb * a.L + l) * 3 + r % 3] : 0.0;
+		lh[r] = (float)c;
+		ll[r] = (float)(c - (double)lh[r]);
+	}
+	const float* Pv = a.params + ((int64_t)bb * a.n_layers + (sg.layer - 1)) * kParamStride;
+	const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
+	const float v45 = -(v4 + v5), nv5 = -v5;
+
+	float f0[NL], f1[NL], f2[NL];
+	double d0[NL], d1[NL], d2[NL];
+#pragma unroll
+	for (int l = 0; l < NL; ++l) { f0[l] = f1[l] = f2[l] = 0.f; d0[l] = d1[l] = d2[l] = 0.0; }
+	int pending = 0;
+	for (int j = sg.begin + vl; j < sg.end; j += lanes) {
+		const uint32_t pos = __ldg(a.pos + j);
+		const uint32_t mask = __ldg(a.mask + j);
+		const float da = __ldg(a.at32 + j) - t0;
+		const float pz = __uint_as_float(0x4B000000u | ((pos >> 22) + 1u)) - 8388608.f;
+		const float py = __uint_as_float(0x4B000000u | (((pos >> 11) & 0x7ffu) + 1u)) - 8388608.f;
+		const float px = __uint_as_float(0x4B000000u | ((pos & 0x7ffu) + 1u)) - 8388608.f;
+		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));   // same clamp as the HOISTED kernel and its table
+		const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
+#pragma unroll
+		for (int l = 0; l < NL; ++l) {
+			const float rz = (lh[3 * l] - pz) + ll[3 * l];
+			const float ry = (lh[3 * l + 1] - py) + ll[3 * l + 1];
+			const float rx = (lh[3 * l + 2] - px) + ll[3 * l + 2];
+			float g = 0.f, sz = 0.f, sy = 0.f, sx = 0.f;
+			for (int k = 0; k < a.nbr.n; ++k) {
+				if ((mask >> a.nbr.bit[k]) & 1u) {
+					const float dz = a.nbr.fz[k], dy = a.nbr.fy[k], dx = a.nbr.fx[k];
+					const float qz = rz + dz, qy = ry + dy, qx = rx + dx;
+					const float sq = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
+					const float dot = fmaf(dz, qz, fmaf(dy, qy, dx * qx));
+					g = fmaf(dot, inv_cube(sq), g);
+					sz += dz; sy += dy; sx += dx;
+				}
+			}
+			const float sqc = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+			g = fmaf(fmaf(sz, rz, fmaf(sy, ry, sx * rx)), inv_cube(sqc), g);
+			const float G = -g;
+			f0[l] += G;
+			f1[l] = fmaf(G, h1, f1[l]);
+			f2[l] = fmaf(G, h2, f2[l]);
+		}
+		if (++pending == 16) {
+			pending = 0;
+#pragma unroll
+			for (int l = 0; l < NL; ++l) {
+				d0[l] += (double)f0[l]; d1[l] += (double)f1[l]; d2[l] += (double)f2[l];
+				f0[l] = f1[l] = f2[l] = 0.f;
+			}
+		}
+	}
+#pragma unroll
+	for (int l = 0; l < NL; ++l) {
+		s_red[(threadIdx.x * NL + l) * 3 + 0] = d0[l] + (double)f0[l];
+		s_red[(threadIdx.x * NL + l) * 3 + 1] = d1[l] + (double)f1[l];
+		s_red[(threadIdx.x * NL + l) * 3 + 2] = d2[l] + (double)f2[l];
+	}
+	__syncthreads();
+	// thread (vector slot vs, lead l, moment q) adds the voxel lanes in lane order
+	for (int o = threadIdx.x; o < vb * NL * 3; o += 256) {
+		const int ovs = o / (NL * 3), r = o - ovs * (NL * 3);
+		const int ob = blockIdx.y * vb + ovs, lead = a.lead0 + r / 3;
+		if (ob >= a.B || lead >= a.L) continue;
+		double s = 0.0;
+		for (int lane = 0; lane < lanes; ++lane) s += s_red[((lane << a.vb_shift) + ovs) * (NL * 3) + r];
+		a.mom[(((int64_t)blockIdx.x * a.B + ob) * a.L + lead) * 3 + r % 3] = s;
+	}
+}
+
+// ECG[b][l][t] for the samples t >= t_off from the moments: one CTA per (vector, block of 128 samples).
+// Shared memory: the per-layer moments of this vector (segments added in order) and the t-invariant
+// ln(2^(k7/k6)-1) of every layer.  F1, F2 by the expressions of ecg_ftab_kernel, kept in f64.
+__global__ void __launch_bounds__(128) ecg_combine_kernel(const double* __restrict__ layer_k, const double* __restrict__ times,
+                                                           const double* __restrict__ mom, const int32_t* __restrict__ seg_first,
+                                                           double* __restrict__ ecg, int B, int L, int n_layers, int T, int t_off, double t0) {
+	extern __shared__ double s_dyn[];
+	double* s_mom = s_dyn;                       // [n_layers][L][3]
+	double* s_tail = s_dyn + n_layers * L * 3;   // [n_layers]
+	const int b = blockIdx.y;
+	for (int o = threadIdx.x; o < n_layers * L * 3; o += blockDim.x) {
+		const int layer = o / (L * 3), r = o - layer * (L * 3);
+		double s = 0.0;
+		for (int sgi = seg_first[layer]; sgi < seg_first[layer + 1]; ++sgi) s += mom[((int64_t)sgi * B + b) * L * 3 + r];
+		s_mom[o] = s;
+	}
+	for (int layer = threadIdx.x; layer < n_layers; layer += blockDim.x) {
+		const double* k = layer_k + ((int64_t)b * n_layers + layer) * 9;
+		s_tail[layer] = log(pow(2.0, k[7] / k[6]) - 1.0);
+	}
+	__syncthreads();
+	const int t = t_off + blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= T) return;
+	const double tt = times[t];
+	const double lim = 60.0 * 0.69314718055994530942;
+	for (int l0 = 0; l0 < L; l0 += 4) {
+		double acc[4] = {0.0, 0.0, 0.0, 0.0};
+		for (int layer = 0; layer < n_layers; ++layer) {
+			if (seg_first[layer] == seg_first[layer + 1]) continue;   // no voxels in this layer (inside the slab)
+			const double* k = layer_k + ((int64_t)b * n_layers + layer) * 9;
+			const double R = 1.0 - pow(1.0 + exp(-k[7] * (tt - k[8]) + s_tail[layer]), -(k[6] / k[7]));
+			const double F1 = k[2] * (1.0 - k[3]) * R * exp(fmin(-(k[4] + k[5]) * (tt - t0), lim));
+			const double F2 = k[2] * k[3] * R * exp(fmin(-k[5] * (tt - t0), lim));
+			const double* M = s_mom + layer * L * 3;
+#pragma unroll
+			for (int l = 0; l < 4; ++l)
+				if (l0 + l < L) acc[l] += k[0] * M[(l0 + l) * 3] + F1 * M[(l0 + l) * 3 + 1] + F2 * M[(l0 + l) * 3 + 2];
+		}
+#pragma unroll
+		for (int l = 0; l < 4; ++l) if (l0 + l < L) ecg[((int64_t)b * L + l0 + l) * T + t] = acc[l];
+	}
+}
+
 // ---- partial sums -> ECG, fixed order ------------------------------------------------------------
-__global__ void __launch_bounds__(256) ecg_reduce_kernel(const double* __restrict__ partial, double* __restrict__ ecg, int n_segs, int64_t n_out) {
+// (the time loop may cover only the first T_loop of T samples: row stride T on the output side)
+__global__ void __launch_bounds__(256) ecg_reduce_kernel(const double* __restrict__ partial, double* __restrict__ ecg, int n_segs, int64_t n_out,
+                                                         int T_loop, int T) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_out) return;
 	double s = 0.0;
 	for (int k = 0; k < n_segs; ++k) s += partial[(int64_t)k * n_out + i];
-	ecg[i] = s;
+	ecg[(i / T_loop) * T + i % T_loop] = s;
 }
 
 // ---- curve comparison on the device (calculateFitness, sim.cpp:600-702; vectorMath.h) -----------------
@@ -363,10 +509,13 @@ int run_criteria(ekg_model* m, const double* d_ecg, const double* d_targets, con
 // ---- per-(vector, layer) coefficient tables, f64 -> f32 -------------------------------------------
 // P[0..11] = -k1 log2e, -k4 log2e, -k5 log2e, -k7 log2e, log2(2^(k7/k6)-1), -k6/k7, k2(1-k3), k2 k3,
 //            k0, hi(k8), lo(k8), t0
-__global__ void ecg_params_kernel(const double* __restrict__ layer_k, float* __restrict__ P, int64_t n, float t0) {
+__global__ void ecg_params_kernel(const double* __restrict__ layer_k, float* __restrict__ P, int64_t n, float t0, int* __restrict__ k1min) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const double* k = layer_k + i * 9;
+	// smallest depolarisation rate of the batch (float bits order like ints for positive values; anything
+	// else -- k1 <= 0, NaN -- becomes 0 = "never saturates")
+	if (k1min) atomicMin(k1min, k[1] > 0 ? __float_as_int(__double2float_rd(k[1])) : 0);
 	const double log2e = 1.4426950408889634074;
 	float* p = P + i * kParamStride;
 	p[0] = (float)(-k[1] * log2e);
@@ -480,12 +629,45 @@ static int launch_ecg(const EcgArgs& a, dim3 grid, int threads, cudaStream_t st)
 	return EKG_OK;
 }
 
+template int ensure<int32_t>(int32_t**, int64_t*, int64_t);
+
+// segment table of the SEPARABLE path + the first segment of every layer
+static int build_moment_segments(ekg_model* m, int64_t seg_len, cudaStream_t st) {
+	if (m->mseg_len == seg_len && m->n_msegs > 0) return EKG_OK;
+	std::vector<Segment> segs;
+	std::vector<int32_t> first(m->n_layers + 1, 0);
+	for (int l = 1; l <= m->n_layers; ++l) {
+		first[l - 1] = (int32_t)segs.size();
+		const int64_t b0 = m->layer_off[l - 1], cnt = m->layer_off[l] - b0;
+		if (cnt <= 0) continue;
+		const int64_t pieces = (cnt + seg_len - 1) / seg_len;
+		for (int64_t p = 0; p < pieces; ++p) {
+			Segment sg;
+			sg.begin = (int32_t)(b0 + cnt * p / pieces);
+			sg.end = (int32_t)(b0 + cnt * (p + 1) / pieces);
+			sg.layer = l;
+			sg.pad = 0;
+			if (sg.end > sg.begin) segs.push_back(sg);
+		}
+	}
+	first[m->n_layers] = (int32_t)segs.size();
+	int rc;
+	if ((rc = ensure(&m->d_msegs, &m->msegs_cap, (int64_t)std::max<size_t>(segs.size(), 1)))) return rc;
+	if ((rc = ensure(&m->d_mseg_first, &m->mseg_first_cap, (int64_t)first.size()))) return rc;
+	EKG_CUDA(cudaMemcpyAsync(m->d_msegs, segs.data(), segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, st));
+	EKG_CUDA(cudaMemcpyAsync(m->d_mseg_first, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	EKG_CUDA(cudaStreamSynchronize(st));
+	m->n_msegs = (int64_t)segs.size();
+	m->mseg_len = seg_len;
+	return EKG_OK;
+}
+
 static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
-                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st);
+                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, double k1_min);
 
 // Large batches are cut into sub-batches so that the f64 partial-sum scratch stays below ~1 GiB.
 int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
-            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st) {
+            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, double k1_min) {
 	if (B <= 0 || L <= 0) return fail(EKG_E_INVALID, "B and n_leads must be positive");
 	if (!(t_step > 0) || !(total_time > 0)) return fail(EKG_E_INVALID, "t_step and total_time must be positive");
 	const int64_t T = (int64_t)ceil(total_time / t_step);
@@ -495,10 +677,15 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 	int64_t sub = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)1 << 30) / (per_vector * 160)));
 	sub = std::min<int64_t>(sub, 16384);
 	int64_t launches = 0;
+	const bool timed = (flags & EKG_FLAG_TIME_KERNEL) != 0;
+	m->ev_recorded = false;
+	if (timed) {
+		if (!m->ev_k0) { EKG_CUDA(cudaEventCreate(&m->ev_k0)); EKG_CUDA(cudaEventCreate(&m->ev_k1)); }
+	}
 	for (int64_t b0 = 0; b0 < B; b0 += sub) {
 		const int64_t nb = std::min(sub, B - b0);
 		int rc = run_ecg_one(m, d_layer_k + b0 * m->n_layers * 9, d_leads + b0 * L * 3, nb, L, nbhd, t_start, t_step, total_time, flags,
-		                     d_ecg + b0 * L * T, st);
+		                     d_ecg + b0 * L * T, st, k1_min);
 		if (rc) return rc;
 		launches += m->last_launches;
 	}
@@ -507,7 +694,7 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 }
 
 static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
-                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st) {
+                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, double k1_min) {
 	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence: call ekg_model_activation or ekg_model_set_activation first");
 	if (B <= 0 || L <= 0) return fail(EKG_E_INVALID, "B and n_leads must be positive");
 	if (B > 65535) return fail(EKG_E_UNSUPPORTED, "at most 65535 parameter vectors per call");
@@ -515,8 +702,8 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	const int64_t T = (int64_t)ceil(total_time / t_step);  // simulator.cpp:471
 	if (T <= 0 || T > (1 << 24)) return fail(EKG_E_INVALID, "bad number of time steps");
 	int mode = flags & 0xff;
-	if (mode == EKG_MODE_DEFAULT) mode = EKG_MODE_HOISTED;
-	if (mode != EKG_MODE_DIRECT && mode != EKG_MODE_HOISTED) return fail(EKG_E_INVALID, "unknown ECG mode");
+	if (mode == EKG_MODE_DEFAULT) mode = EKG_MODE_SEPARABLE;
+	if (mode != EKG_MODE_DIRECT && mode != EKG_MODE_HOISTED && mode != EKG_MODE_SEPARABLE) return fail(EKG_E_INVALID, "unknown ECG mode");
 
 	EcgArgs a{};
 	int rc = make_nbr_table(nbhd, &a.nbr);
@@ -528,94 +715,161 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	double* d_t64 = reinterpret_cast<double*>(m->d_times + 2 * T);
 	if (m->times_T != T || m->times_t_start != t_start || m->times_t_step != t_step) {
 		std::vector<float> h_t(2 * T);
-		std::vector<double> h_t64(T);
+		m->h_times.resize(T);
 		double st_ = t_start;
 		for (int64_t i = 0; i < T; ++i) {
-			h_t64[i] = st_;
+			m->h_times[i] = st_;
 			h_t[i] = (float)st_;
 			h_t[T + i] = (float)(st_ - (double)h_t[i]);
 			st_ += t_step;
 		}
 		EKG_CUDA(cudaMemcpyAsync(m->d_times, h_t.data(), 2 * T * sizeof(float), cudaMemcpyHostToDevice, st));
-		EKG_CUDA(cudaMemcpyAsync(d_t64, h_t64.data(), T * sizeof(double), cudaMemcpyHostToDevice, st));
+		EKG_CUDA(cudaMemcpyAsync(d_t64, m->h_times.data(), T * sizeof(double), cudaMemcpyHostToDevice, st));
 		EKG_CUDA(cudaStreamSynchronize(st));  // pageable sources go out of scope here
 		m->times_T = T; m->times_t_start = t_start; m->times_t_step = t_step;
 	}
 
-	// work decomposition: pair tiles (<= kEcgThreads pairs, <= kMaxVecPerTile vectors each) x segments
-	if (m->tiles_B != B || m->tiles_T != T) {
-		std::vector<PairTile> tiles;
-		const int64_t P = B * T;
-		for (int64_t p = 0; p < P;) {
-			int64_t e = std::min<int64_t>(p + kEcgThreads, P);
-			const int64_t b0 = p / T;
-			if ((e - 1) / T - b0 + 1 > kMaxVecPerTile) e = (b0 + kMaxVecPerTile) * T;
-			tiles.push_back(PairTile{(int32_t)p, (int32_t)e});
-			p = e;
-		}
-		if ((rc = ensure(&m->d_tiles, &m->tiles_cap, (int64_t)tiles.size()))) return rc;
-		EKG_CUDA(cudaMemcpyAsync(m->d_tiles, tiles.data(), tiles.size() * sizeof(PairTile), cudaMemcpyHostToDevice, st));
-		EKG_CUDA(cudaStreamSynchronize(st));
-		m->n_tiles = (int64_t)tiles.size(); m->tiles_B = B; m->tiles_T = T;
-	}
-	if (B * T >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "B * n_steps must be below 2^31");
-	// ~100 waves of CTAs: the tail of the last wave costs about 1/waves of the launch
-	const int64_t target_ctas = (int64_t)m->sm_count * 4 * 96;
-	int64_t want_segs = (target_ctas + m->n_tiles - 1) / m->n_tiles;
-	int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
-	seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
-	seg_len = (seg_len + kChunk - 1) / kChunk * kChunk;
-	if ((rc = build_segments(m, seg_len, st))) return rc;
-	if (m->n_tiles > 65535) return fail(EKG_E_UNSUPPORTED, "too many (vector, sample) pairs for one launch (B * n_steps <= 16.7 M)");
-
-	const int64_t n_out = B * L * T;
-	if ((rc = ensure(&m->d_partial, &m->partial_cap, m->n_segs * n_out))) return rc;
-	if ((rc = ensure(&m->d_params, &m->params_cap, B * m->n_layers * kParamStride))) return rc;
-
 	const int64_t n_bl = B * m->n_layers;
-	ecg_params_kernel<<<(int)((n_bl + 127) / 128), 128, 0, st>>>(d_layer_k, m->d_params, n_bl, (float)m->t0);
+	if ((rc = ensure(&m->d_params, &m->params_cap, n_bl * kParamStride))) return rc;
+	const bool want_k1 = mode == EKG_MODE_SEPARABLE && !(k1_min > 0);
+	if (want_k1) {
+		if (!m->d_k1min) EKG_CUDA(cudaMalloc(&m->d_k1min, sizeof(int)));
+		EKG_CUDA(cudaMemsetAsync(m->d_k1min, 0x7f, sizeof(int), st));  // 0x7f7f7f7f = 3.4e38f
+	}
+	ecg_params_kernel<<<(int)((n_bl + 127) / 128), 128, 0, st>>>(d_layer_k, m->d_params, n_bl, (float)m->t0, want_k1 ? m->d_k1min : nullptr);
 	EKG_CUDA(cudaGetLastError());
 	++m->last_launches;
-	if (mode == EKG_MODE_HOISTED) {
-		if ((rc = ensure(&m->d_ftab, &m->ftab_cap, n_bl * 2 * T))) return rc;
-		ecg_ftab_kernel<<<(int)((n_bl * T + 255) / 256), 256, 0, st>>>(d_layer_k, d_t64, m->d_ftab, n_bl, (int)T, (double)(float)m->t0);
+
+	// SEPARABLE: the time-loop kernel handles the first T_loop samples (those before every voxel's
+	// depolarisation sigmoid is exactly 1 in fp32: exp(-k1 (t - at)) < 2^-25, the HOISTED kernel's own
+	// saturation test), the moment path the rest.  T_loop = 0 for runs that start after the QRS complex.
+	int64_t T_loop = T;
+	int loop_mode = mode;
+	if (mode == EKG_MODE_SEPARABLE) {
+		loop_mode = EKG_MODE_HOISTED;
+		if (want_k1) {
+			int bits = 0;
+			EKG_CUDA(cudaMemcpyAsync(&bits, m->d_k1min, sizeof(int), cudaMemcpyDeviceToHost, st));
+			EKG_CUDA(cudaStreamSynchronize(st));
+			float f; memcpy(&f, &bits, 4);
+			k1_min = (double)f;
+		}
+		const size_t smem_need = (size_t)(m->n_layers * L * 3 + m->n_layers) * sizeof(double);
+		if (k1_min > 0 && smem_need <= 48 * 1024) {
+			// k1 log2e (t - at) > 25 (+ a margin of 1e-3 ms for the fp32 evaluation of the same test)
+			const double t_sat = m->at_max + 25.0 / (k1_min * 1.4426950408889634074) + 1e-3;
+			T_loop = 0;
+			while (T_loop < T && !(m->h_times[T_loop] > t_sat)) ++T_loop;
+		}
+	}
+
+	const bool timed = (flags & EKG_FLAG_TIME_KERNEL) != 0;
+	bool need_k0 = timed && !m->ev_recorded;   // first sub-batch of a timed call: event before the first main kernel
+
+	if (T_loop > 0) {
+		// work decomposition: pair tiles (<= kEcgThreads pairs, <= kMaxVecPerTile vectors each) x segments
+		if (m->tiles_B != B || m->tiles_T != T_loop) {
+			std::vector<PairTile> tiles;
+			const int64_t P = B * T_loop;
+			for (int64_t p = 0; p < P;) {
+				int64_t e = std::min<int64_t>(p + kEcgThreads, P);
+				const int64_t b0 = p / T_loop;
+				if ((e - 1) / T_loop - b0 + 1 > kMaxVecPerTile) e = (b0 + kMaxVecPerTile) * T_loop;
+				tiles.push_back(PairTile{(int32_t)p, (int32_t)e});
+				p = e;
+			}
+			if ((rc = ensure(&m->d_tiles, &m->tiles_cap, (int64_t)tiles.size()))) return rc;
+			EKG_CUDA(cudaMemcpyAsync(m->d_tiles, tiles.data(), tiles.size() * sizeof(PairTile), cudaMemcpyHostToDevice, st));
+			EKG_CUDA(cudaStreamSynchronize(st));
+			m->n_tiles = (int64_t)tiles.size(); m->tiles_B = B; m->tiles_T = T_loop;
+		}
+		if (B * T_loop >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "B * n_steps must be below 2^31");
+		// ~100 waves of CTAs: the tail of the last wave costs about 1/waves of the launch
+		const int64_t target_ctas = (int64_t)m->sm_count * 4 * 96;
+		int64_t want_segs = (target_ctas + m->n_tiles - 1) / m->n_tiles;
+		int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
+		seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
+		seg_len = (seg_len + kChunk - 1) / kChunk * kChunk;
+		if ((rc = build_segments(m, seg_len, st))) return rc;
+		if (m->n_tiles > 65535) return fail(EKG_E_UNSUPPORTED, "too many (vector, sample) pairs for one launch (B * n_steps <= 16.7 M)");
+
+		const int64_t n_out = B * L * T_loop;
+		if ((rc = ensure(&m->d_partial, &m->partial_cap, m->n_segs * n_out))) return rc;
+		if (loop_mode == EKG_MODE_HOISTED) {
+			if ((rc = ensure(&m->d_ftab, &m->ftab_cap, n_bl * 2 * T_loop))) return rc;
+			ecg_ftab_kernel<<<(int)((n_bl * T_loop + 255) / 256), 256, 0, st>>>(d_layer_k, d_t64, m->d_ftab, n_bl, (int)T_loop, (double)(float)m->t0);
+			EKG_CUDA(cudaGetLastError());
+			++m->last_launches;
+		}
+
+		a.pos = m->d_pos; a.mask = m->d_mask; a.at32 = m->d_at32; a.segs = m->d_segs; a.tiles = m->d_tiles;
+		a.params = m->d_params; a.ftab = m->d_ftab; a.leads = d_leads;
+		a.t_hi = m->d_times; a.t_lo = m->d_times + T;
+		a.partial = m->d_partial;
+		a.n_segs = (int32_t)m->n_segs; a.B = (int32_t)B; a.L = (int32_t)L; a.T = (int32_t)T_loop; a.n_layers = m->n_layers;
+
+		const dim3 grid((unsigned)m->n_segs, (unsigned)m->n_tiles, 1);
+		const int threads = kEcgThreads;
+		if (need_k0) { EKG_CUDA(cudaEventRecord(m->ev_k0, st)); need_k0 = false; }
+		for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
+			a.lead0 = lead0;
+			const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
+			if (loop_mode == EKG_MODE_DIRECT) {
+				if (nl <= 2) rc = launch_ecg<MODE_DIRECT, 2>(a, grid, threads, st);
+				else rc = launch_ecg<MODE_DIRECT, 4>(a, grid, threads, st);
+				m->last_kernel = "ecg_kernel<DIRECT>";
+			} else {
+				if (nl <= 2) rc = launch_ecg<MODE_HOISTED, 2>(a, grid, threads, st);
+				else rc = launch_ecg<MODE_HOISTED, 4>(a, grid, threads, st);
+				m->last_kernel = "ecg_kernel<HOISTED>";
+			}
+			if (rc) return rc;
+			++m->last_launches;
+		}
+		if (T_loop == T && timed) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
+		ecg_reduce_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(m->d_partial, d_ecg, (int)m->n_segs, n_out, (int)T_loop, (int)T);
 		EKG_CUDA(cudaGetLastError());
 		++m->last_launches;
 	}
 
-	a.pos = m->d_pos; a.mask = m->d_mask; a.at32 = m->d_at32; a.segs = m->d_segs; a.tiles = m->d_tiles;
-	a.params = m->d_params; a.ftab = m->d_ftab; a.leads = d_leads;
-	a.t_hi = m->d_times; a.t_lo = m->d_times + T;
-	a.partial = m->d_partial;
-	a.n_segs = (int32_t)m->n_segs; a.B = (int32_t)B; a.L = (int32_t)L; a.T = (int32_t)T; a.n_layers = m->n_layers;
-
-	const dim3 grid((unsigned)m->n_segs, (unsigned)m->n_tiles, 1);
-	const int threads = kEcgThreads;
-	const bool timed = (flags & EKG_FLAG_TIME_KERNEL) != 0;
-	m->ev_recorded = false;
-	if (timed) {
-		if (!m->ev_k0) { EKG_CUDA(cudaEventCreate(&m->ev_k0)); EKG_CUDA(cudaEventCreate(&m->ev_k1)); }
-		EKG_CUDA(cudaEventRecord(m->ev_k0, st));
-	}
-	for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
-		a.lead0 = lead0;
-		const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
-		if (mode == EKG_MODE_DIRECT) {
-			if (nl <= 2) rc = launch_ecg<MODE_DIRECT, 2>(a, grid, threads, st);
-			else rc = launch_ecg<MODE_DIRECT, 4>(a, grid, threads, st);
-			m->last_kernel = "ecg_kernel<DIRECT>";
-		} else {
-			if (nl <= 2) rc = launch_ecg<MODE_HOISTED, 2>(a, grid, threads, st);
-			else rc = launch_ecg<MODE_HOISTED, 4>(a, grid, threads, st);
-			m->last_kernel = "ecg_kernel<HOISTED>";
+	if (T_loop < T) {
+		// threads of a CTA = vb vectors x 256/vb voxel lanes; ~16 CTAs per SM in flight
+		int vb_shift = 0;
+		while (vb_shift < 5 && (1 << vb_shift) < B) ++vb_shift;
+		const int64_t groups = (B + (1 << vb_shift) - 1) >> vb_shift;
+		const int64_t lanes = 256 >> vb_shift;
+		const int64_t want_segs = std::max<int64_t>(1, ((int64_t)m->sm_count * 16 + groups - 1) / groups);
+		int64_t seg_len = (m->n_ecg + want_segs - 1) / want_segs;
+		seg_len = std::max<int64_t>(lanes * 16, std::min<int64_t>(seg_len, (int64_t)1 << 20));
+		seg_len = (seg_len + 255) / 256 * 256;
+		if ((rc = build_moment_segments(m, seg_len, st))) return rc;
+		if (groups > 65535) return fail(EKG_E_UNSUPPORTED, "too many parameter vectors for one launch");
+		if ((rc = ensure(&m->d_mom, &m->mom_cap, std::max<int64_t>(m->n_msegs, 1) * B * L * 3))) return rc;
+		MomentArgs ma{};
+		ma.pos = m->d_pos; ma.mask = m->d_mask; ma.at32 = m->d_at32; ma.segs = m->d_msegs; ma.params = m->d_params; ma.leads = d_leads;
+		ma.mom = m->d_mom; ma.B = (int32_t)B; ma.L = (int32_t)L; ma.n_layers = m->n_layers; ma.vb_shift = vb_shift; ma.nbr = a.nbr;
+		if (need_k0) { EKG_CUDA(cudaEventRecord(m->ev_k0, st)); need_k0 = false; }
+		if (m->n_msegs > 0) {
+			const dim3 grid((unsigned)m->n_msegs, (unsigned)groups, 1);
+			for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
+				ma.lead0 = lead0;
+				const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
+				if (nl <= 2) ecg_moment_kernel<2><<<grid, 256, 0, st>>>(ma);
+				else ecg_moment_kernel<4><<<grid, 256, 0, st>>>(ma);
+				EKG_CUDA(cudaGetLastError());
+				++m->last_launches;
+			}
 		}
-		if (rc) return rc;
+		if (timed) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
+		const int64_t n_late = T - T_loop;
+		const size_t smem = (size_t)(m->n_layers * L * 3 + m->n_layers) * sizeof(double);
+		const dim3 cgrid((unsigned)((n_late + 127) / 128), (unsigned)B, 1);
+		ecg_combine_kernel<<<cgrid, 128, smem, st>>>(d_layer_k, d_t64, m->d_mom, m->d_mseg_first, d_ecg, (int)B, (int)L, m->n_layers, (int)T,
+		                                            (int)T_loop, (double)(float)m->t0);
+		EKG_CUDA(cudaGetLastError());
 		++m->last_launches;
+		m->last_kernel = T_loop > 0 ? "ecg_kernel<HOISTED> + ecg_moment_kernel" : "ecg_moment_kernel";
 	}
-	if (timed) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
-	ecg_reduce_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(m->d_partial, d_ecg, (int)m->n_segs, n_out);
-	EKG_CUDA(cudaGetLastError());
-	++m->last_launches;
 	return EKG_OK;
 }
 

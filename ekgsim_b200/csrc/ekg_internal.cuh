@@ -68,6 +68,20 @@ struct EcgArgs {
 	NbrTable nbr;
 };
 
+// SEPARABLE path, moments of the lead field over the voxels of a segment (ecg_moment_kernel)
+struct MomentArgs {
+	const uint32_t* pos;
+	const uint32_t* mask;
+	const float* at32;
+	const Segment* segs;
+	const float* params;    // [B][n_layers][kParamStride]
+	const double* leads;    // [B][L][3]
+	double* mom;            // [n_segs][B][L][3]: sum G, sum G h1, sum G h2
+	int32_t B, L, n_layers, lead0;
+	int32_t vb_shift;       // log2 of the parameter vectors a CTA serves (threads = vectors x voxel lanes)
+	NbrTable nbr;
+};
+
 struct AutoArgs {
 	const uint8_t* layer;   // padded dense grid, 0 = empty
 	double* time;           // padded dense grid, +inf = not reached
@@ -126,6 +140,7 @@ struct ekg_model {
 	std::vector<double> h_delay;     // raster activation map (0 = empty / never reached)
 	bool have_activation = false;
 	double t0 = 0.0;                 // centre of the activation-time range (HOISTED kernel)
+	double at_max = 0.0;             // latest activation time of the model (SEPARABLE: first saturated sample)
 	float activation_ms = 0.f;       // device time of the last automaton run
 
 	// automaton state (device)
@@ -156,10 +171,16 @@ struct ekg_model {
 	// per-call scratch (grown on demand)
 	ekg::Segment* d_segs = nullptr;  int64_t segs_cap = 0;  int64_t n_segs = 0;  int64_t seg_len = 0;
 	ekg::PairTile* d_tiles = nullptr; int64_t tiles_cap = 0; int64_t n_tiles = 0; int64_t tiles_B = 0, tiles_T = 0;
+	// SEPARABLE path: its own segment table (sized for voxel x vector work, not for the time loop)
+	ekg::Segment* d_msegs = nullptr; int64_t msegs_cap = 0;  int64_t n_msegs = 0;  int64_t mseg_len = 0;
+	int32_t* d_mseg_first = nullptr; int64_t mseg_first_cap = 0;   // first segment of every layer, n_layers + 1 entries
+	double* d_mom = nullptr;         int64_t mom_cap = 0;          // [n_msegs][B][L][3] moments
+	int* d_k1min = nullptr;                                        // float bits of min k1 over (vector, layer), by ecg_params_kernel
 	float* d_params = nullptr;       int64_t params_cap = 0;
 	float* d_ftab = nullptr;         int64_t ftab_cap = 0;
 	float* d_times = nullptr;        int64_t times_cap = 0;
 	double times_t_start = 0, times_t_step = 0;  int64_t times_T = 0;  // what d_times currently holds
+	std::vector<double> h_times;     // host copy of the f64 sample times
 	double* d_partial = nullptr;     int64_t partial_cap = 0;
 	double* d_io_k = nullptr;        int64_t io_k_cap = 0;     // staging for the host-buffer entry point
 	double* d_io_leads = nullptr;    int64_t io_leads_cap = 0;
@@ -179,8 +200,10 @@ namespace ekg {
 // automaton.cu
 int run_automaton(ekg_model* m, int64_t* sweeps_out);
 // ecg.cu
+// k1_min: smallest depolarisation rate k1 over all (vector, layer) if the caller knows it on the host
+// (<= 0: unknown -- the SEPARABLE path then reads it back from the device, one stream synchronisation)
 int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
-            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st);
+            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, double k1_min = 0.0);
 int run_criteria(ekg_model* m, const double* d_ecg, const double* d_targets, const double* d_offsets, double* d_crit,
                  int64_t B, int64_t L, int64_t T, int64_t n_target, int comparison, cudaStream_t st);
 int make_nbr_table(int nbhd, NbrTable* out);

@@ -70,9 +70,11 @@ enum { EKG_NBHD_2D4 = 0, EKG_NBHD_2D8 = 1, EKG_NBHD_3D4 = 2, EKG_NBHD_3D8 = 3 };
 
 /* ECG kernel selection (flags argument of ekg_simulate*) */
 enum {
-	EKG_MODE_DEFAULT = 0,  /* library picks (currently EKG_MODE_HOISTED when valid, else DIRECT) */
+	EKG_MODE_DEFAULT = 0,  /* library picks (currently EKG_MODE_SEPARABLE) */
 	EKG_MODE_DIRECT = 1,   /* full 9-coefficient AP evaluated per voxel and time sample */
-	EKG_MODE_HOISTED = 2   /* voxel-invariant and time-invariant factors of the AP hoisted */
+	EKG_MODE_HOISTED = 2,  /* voxel-invariant and time-invariant factors of the AP hoisted */
+	EKG_MODE_SEPARABLE = 3 /* samples later than the last depolarisation: per-layer moments of the lead
+	                        * field replace the voxel x sample loop; earlier samples run as HOISTED */
 };
 
 /* OR-ed into flags: record CUDA events around the ECG kernel launch(es) on the launching stream

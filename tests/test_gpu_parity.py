@@ -80,7 +80,7 @@ def test_activation_errors(built):
     assert "transfer matrix too small" in str(e.value)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("nbhd", ["3D4", "3D8"])
 def test_ecg_small_vs_oracle(built, mode, nbhd):
     layers, transfer, leads = synth.small_heart(seed=7)
@@ -97,7 +97,7 @@ def test_ecg_small_vs_oracle(built, mode, nbhd):
     m.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_ecg_model24_golden_full(gpu_model24, model24_delay, mode):
     """Full-length model_24 simulations against ECGs dumped from the compiled reference."""
     g = np.load(os.path.join(GOLDEN, "golden_eval_full.npz"))
@@ -109,7 +109,7 @@ def test_ecg_model24_golden_full(gpu_model24, model24_delay, mode):
         assert e < ECG_TOL
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_ecg_model24_len16_batch(gpu_model24, model24_delay, mode):
     g = np.load(os.path.join(GOLDEN, "golden_len16.npz"))
     gpu_model24.set_activation(model24_delay)
@@ -161,7 +161,7 @@ def test_ecg_lead_counts(built, n_leads):
     delay = oracle.activation(layers, transfer)
     m = built.Model(layers, transfer)
     m.set_activation(delay)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         ecg = m.simulate(k, leads, "3D4", 0.0, 1.0, 80.0, mode=mode)
         assert ecg.shape == (2, n_leads, 80)
         for b in range(2):
@@ -178,7 +178,7 @@ def test_ecg_2d_model(built, nbhd):
     delay = oracle.activation(layers, transfer)
     m = built.Model(layers, transfer)
     m.set_activation(delay)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         ecg = m.simulate(k, leads, nbhd, 0.0, 1.0, 60.0, mode=mode)[0]
         ref = oracle.run_direct(layers, delay, k, leads, nbhd, 0.0, 1.0, 60.0)
         assert rel_err(ecg, ref) < ECG_TOL, (mode, nbhd, rel_err(ecg, ref))
@@ -199,7 +199,7 @@ def test_ecg_ragged_pair_tiles(built, B, t0, dt, total):
     m.set_activation(delay)
     lb = np.stack([leads + i for i in range(B)])  # every vector has its own lead positions
     full = [oracle.run_direct(layers, delay, k[b], lb[b], "3D4", 0.0, 1.0, 300.0) for b in range(min(B, 4))]
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         ecg = m.simulate(k, lb, "3D4", t0, dt, total, mode=mode)
         for b in range(min(B, 4)):
             ref = oracle.run_direct(layers, delay, k[b], lb[b], "3D4", t0, dt, total)
@@ -280,7 +280,7 @@ def test_ecg_model24_batch_sample_vs_oracle(gpu_model24, model24, model24_delay)
     g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
     pick = [5, 40, 77, 101, 150, 199, 230, 255]
     gpu_model24.set_activation(model24_delay)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         ecg = gpu_model24.simulate(g["layer_k"], g["leads_zyx"], "3D4", 100.0, 1.0, 400.0, mode=mode)
         worst = 0.0
         for b in pick:
@@ -341,7 +341,7 @@ def test_ecg_wide_parameter_ranges(built, seed):
     m.set_activation(delay)
     for (t0, dt, tot) in [(-10.0, 1.0, 200.0), (0.0, 2.5, 600.0)]:
         refs = [oracle.run_direct(layers, delay, k[b], leads, "3D4", t0, dt, tot) for b in range(B)]
-        for mode in (1, 2):
+        for mode in (1, 2, 3):
             ecg = m.simulate(k, leads, "3D4", t0, dt, tot, mode=mode)
             assert np.isfinite(ecg).all()
             worst = max(rel_err(ecg[b], refs[b]) for b in range(B))
@@ -364,6 +364,14 @@ def test_full_size_properties(gpu_model24, model24, model24_delay):
     assert (np.abs(scaled - 2.0 * base) / peak).max() < 2e-5          # fp32 evaluation on both sides
     hoisted = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=2)
     assert (np.abs(hoisted - base) / peak).max() < ECG_TOL
+    separable = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=3)
+    assert (np.abs(separable - base) / peak).max() < ECG_TOL
+    sep_parts = np.zeros_like(base)
+    for z0, z1 in [(0, 62), (62, 124)]:
+        gpu_model24.set_slab(z0, z1)
+        sep_parts += gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=3)
+    gpu_model24.set_slab(0, 124)
+    assert (np.abs(sep_parts - separable) / peak).max() < 2e-6
     perm = np.array([3, 0, 7, 1, 6, 2, 5, 4])
     shuffled = gpu_model24.simulate(k[perm], leads[perm], "3D4", 100.0, 1.0, 400.0, mode=1)
     assert (np.abs(shuffled - base[perm]) / peak[perm]).max() < 2e-6
@@ -373,3 +381,39 @@ def test_full_size_properties(gpu_model24, model24, model24_delay):
         parts += gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=1)
     gpu_model24.set_slab(0, 124)
     assert (np.abs(parts - base) / peak).max() < 2e-6
+
+
+def test_separable_split_and_single_vector(gpu_model24, model24, model24_delay):
+    """EKG_MODE_SEPARABLE: a run that starts inside the QRS complex is split into time-loop samples (before
+    the last voxel's depolarisation sigmoid saturates) and moment samples; the seam must not show.  Also B = 1
+    (all threads of a CTA stride over voxels) and odd batch sizes (partly filled vector groups)."""
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    gpu_model24.set_activation(model24_delay)
+    k, leads = g["layer_k"][:5], g["leads_zyx"][:5]
+    # activation ends at 39.02 ms, k1 = 2.5 -> saturation from 45.95 ms on: samples 0..21 loop, 22.. moments
+    ecg = gpu_model24.simulate(k, leads, "3D4", 25.0, 1.0, 60.0, mode=3)
+    assert gpu_model24.last_kernel_name == "ecg_kernel<HOISTED> + ecg_moment_kernel"
+    for b in (0, 4):
+        ref = oracle.run_factored(model24["layers"], model24_delay, k[b], leads[b], "3D4", 25.0, 1.0, 60.0)
+        assert rel_err(ecg[b], ref) < ECG_TOL, (b, rel_err(ecg[b], ref))
+    hoisted = gpu_model24.simulate(k, leads, "3D4", 25.0, 1.0, 60.0, mode=2)
+    peak = np.abs(hoisted).max(axis=2, keepdims=True)
+    assert (np.abs(ecg - hoisted) / peak).max() < 2e-6
+    # entirely before saturation: the whole run goes through the time loop
+    early = gpu_model24.simulate(k[:2], leads[:2], "3D4", 0.0, 1.0, 40.0, mode=3)
+    assert gpu_model24.last_kernel_name == "ecg_kernel<HOISTED>"
+    assert np.abs(early - gpu_model24.simulate(k[:2], leads[:2], "3D4", 0.0, 1.0, 40.0, mode=2)).max() == 0.0
+    # entirely after: moments only; one vector alone equals the same vector inside a batch of 5 or 37
+    late1 = gpu_model24.simulate(k[3], leads[3], "3D4", 100.0, 1.0, 400.0, mode=3)
+    assert gpu_model24.last_kernel_name == "ecg_moment_kernel"
+    late5 = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=3)
+    late37 = gpu_model24.simulate(g["layer_k"][:37], g["leads_zyx"][:37], "3D4", 100.0, 1.0, 400.0, mode=3)
+    pk = np.abs(late1).max(axis=2, keepdims=True)
+    assert (np.abs(late1[0] - late5[3]) / pk[0]).max() < 1e-6      # different voxel-lane grouping of the fp32 sums
+    assert (np.abs(late37[:5] - late5) / np.abs(late5).max(axis=2, keepdims=True)).max() < 1e-6
+    # a slow depolarisation (k1 = 0.2) pushes the seam far out: 39.02 + 25 / (0.2 log2 e) = 125.7 ms
+    slow = k.copy(); slow[:, :, 1] = 0.2
+    e3 = gpu_model24.simulate(slow, leads, "3D4", 100.0, 1.0, 100.0, mode=3)
+    assert gpu_model24.last_kernel_name == "ecg_kernel<HOISTED> + ecg_moment_kernel"
+    ref = oracle.run_factored(model24["layers"], model24_delay, slow[1], leads[1], "3D4", 100.0, 1.0, 100.0)
+    assert rel_err(e3[1], ref) < ECG_TOL

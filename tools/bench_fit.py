@@ -24,7 +24,7 @@ def main():
     m.activation()
     border = g["layer_k"][:, [0, 14, 23]].copy()
     out = {}
-    for B in (1, 16, 256, 1024):
+    for B in (1, 16, 256, 1024, 4096):
         b = np.tile(border, (max(1, B // 256), 1, 1))[:B]
         leads = np.tile(g["leads_zyx"], (max(1, B // 256), 1, 1))[:B]
         m.fit_layers(b, mid=14)
@@ -32,8 +32,8 @@ def main():
         for _ in range(5):
             t0 = time.perf_counter(); m.fit_layers(b, mid=14); t.append(time.perf_counter() - t0)
         out["fit_ms_B%d" % B] = round(1e3 * min(t), 3)
-        for mode, name in ((2, "hoisted"), (1, "direct")):
-            if B > 256 and mode == 1:
+        for mode, name in ((3, "separable"), (2, "hoisted"), (1, "direct")):
+            if B > 256 and mode != 3:
                 continue
             m.evaluate(b, leads, targets, mid=14, mode=mode)
             t = []
