@@ -31,6 +31,7 @@
 // Algorithmic traffic: 16 B per voxel (pos, mask, at) per CTA, re-read by the B CTAs of a
 // segment from L2; 0.04 B per voxel-timestep at T = 400 -> MUFU-bound, not HBM-bound.
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "ekg_internal.cuh"
@@ -367,6 +368,151 @@ __global__ void __launch_bounds__(256) ecg_moment_kernel(const MomentArgs a) {
 	}
 	__syncthreads();
 	// thread (vector slot vs, lead l, moment q) adds the voxel lanes in lane order
+	for (int o = threadIdx.x; o < vb * NL * 3; o += 256) {
+		const int ovs = o / (NL * 3), r = o - ovs * (NL * 3);
+		const int ob = blockIdx.y * vb + ovs, lead = a.lead0 + r / 3;
+		if (ob >= a.B || lead >= a.L) continue;
+		double s = 0.0;
+		for (int lane = 0; lane < lanes; ++lane) s += s_red[((lane << a.vb_shift) + ovs) * (NL * 3) + r];
+		a.mom[(((int64_t)blockIdx.x * a.B + ob) * a.L + lead) * 3 + r % 3] = s;
+	}
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, two lanes per issued instruction) --------
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(f2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); return x; }
+__device__ __forceinline__ float hi2(f2 a) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); return y; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+// 1/|q|^3 for two squared distances at once (two MUFU.RSQ + one packed Newton step + packed cube)
+__device__ __forceinline__ f2 inv_cube2(f2 sq) {
+	f2 y = mk2(mufu_rsq(lo2(sq)), mufu_rsq(hi2(sq)));
+	y = mul2(y, fma2(mul2(sq, mk2(-0.5f, -0.5f)), mul2(y, y), mk2(1.5f, 1.5f)));
+	return mul2(mul2(y, y), y);
+}
+
+// occupancy-mask bits of the 8 cube corners in the order (dz, dy, dx) = (-,-,-), (-,-,+), ... (+,+,+): their
+// positions in the 26-neighbour cube list (make_nbr_table; checked on the host before this kernel is chosen)
+__device__ constexpr int kCornerBit[8] = {0, 2, 6, 8, 17, 19, 23, 25};
+
+// The moment kernel specialised for the reference's default stencil "3D4" (= the 8 cube corners, sim_lib.h:133-141),
+// two leads per packed fp32x2 lane pair.  With d = (+-1, +-1, +-1) the neighbour offsets fold into six per-axis
+// terms p = r + 1, m = 1 - r: |r + d|^2 = (p|m)_z^2 + (p|m)_y^2 + (p|m)_x^2 and d . (r + d) = (p|m)_z + (p|m)_y + (p|m)_x,
+// 4 packed instructions + 2 MUFU + 7 packed for the inverse cube per corner and lead pair (the generic loop
+// issues ~35 scalar instructions per corner and lead).  NP = lead pairs per pass.
+template <int NP>
+__global__ void __launch_bounds__(256) ecg_moment_corners_kernel(const MomentArgs a) {
+	__shared__ double s_red[256 * NP * 6];
+	const Segment sg = a.segs[blockIdx.x];
+	const int vb = 1 << a.vb_shift;
+	const int vs = threadIdx.x & (vb - 1), vl = threadIdx.x >> a.vb_shift, lanes = 256 >> a.vb_shift;
+	const int b = blockIdx.y * vb + vs;
+	const int bb = min(b, a.B - 1);
+
+	f2 lh[NP][3], ll[NP][3];   // lead coordinates (z, y, x) of the two leads of a pair, fp32 hi and lo parts
+#pragma unroll
+	for (int p = 0; p < NP; ++p)
+#pragma unroll
+		for (int c = 0; c < 3; ++c) {
+			float h[2], l[2];
+#pragma unroll
+			for (int e = 0; e < 2; ++e) {
+				const int lead = a.lead0 + 2 * p + e;
+				const double v = lead < a.L ? a.leads[((int64_t)bb * a.L + lead) * 3 + c] : 1e6;   // a far-away dummy lead
+				h[e] = (float)v;
+				l[e] = (float)(v - (double)h[e]);
+			}
+			lh[p][c] = mk2(h[0], h[1]);
+			ll[p][c] = mk2(l[0], l[1]);
+		}
+	const float* Pv = a.params + ((int64_t)bb * a.n_layers + (sg.layer - 1)) * kParamStride;
+	const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
+	const float v45 = -(v4 + v5), nv5 = -v5;
+	const f2 one = mk2(1.f, 1.f);
+
+	f2 f0[NP], f1[NP], f2s[NP];
+	double d0[NP][2], d1[NP][2], d2[NP][2];
+#pragma unroll
+	for (int p = 0; p < NP; ++p) {
+		f0[p] = f1[p] = f2s[p] = mk2(0.f, 0.f);
+		d0[p][0] = d0[p][1] = d1[p][0] = d1[p][1] = d2[p][0] = d2[p][1] = 0.0;
+	}
+	int pending = 0;
+	for (int j = sg.begin + vl; j < sg.end; j += lanes) {
+		const uint32_t pos = __ldg(a.pos + j);
+		const uint32_t mask = __ldg(a.mask + j);
+		const float da = __ldg(a.at32 + j) - t0;
+		const float pz = __uint_as_float(0x4B000000u | ((pos >> 22) + 1u)) - 8388608.f;
+		const float py = __uint_as_float(0x4B000000u | (((pos >> 11) & 0x7ffu) + 1u)) - 8388608.f;
+		const float px = __uint_as_float(0x4B000000u | ((pos & 0x7ffu) + 1u)) - 8388608.f;
+		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));
+		const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
+		// S = sum of the offsets of the occupied corners, per axis: (# with +1) - (# with -1), as floats via the
+		// 2^23 trick (values -8..8, no I2F)
+		constexpr uint32_t kAll = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8) | (1u << 17) | (1u << 19) | (1u << 23) | (1u << 25);
+		constexpr uint32_t kZp = (1u << 17) | (1u << 19) | (1u << 23) | (1u << 25);
+		constexpr uint32_t kYp = (1u << 6) | (1u << 8) | (1u << 23) | (1u << 25);
+		constexpr uint32_t kXp = (1u << 2) | (1u << 8) | (1u << 19) | (1u << 25);
+		const int n_occ = __popc(mask & kAll);
+		const float szf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kZp) - n_occ)) - 8388616.f;
+		const float syf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kYp) - n_occ)) - 8388616.f;
+		const float sxf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kXp) - n_occ)) - 8388616.f;
+		const f2 PZ = mk2(pz, pz), PY = mk2(py, py), PX = mk2(px, px);
+#pragma unroll
+		for (int p = 0; p < NP; ++p) {
+			const f2 rz = add2(sub2(lh[p][0], PZ), ll[p][0]);
+			const f2 ry = add2(sub2(lh[p][1], PY), ll[p][1]);
+			const f2 rx = add2(sub2(lh[p][2], PX), ll[p][2]);
+			const f2 zt[2] = {sub2(one, rz), add2(rz, one)};   // [0]: d = -1 -> -(r - 1),  [1]: d = +1 -> r + 1
+			const f2 yt[2] = {sub2(one, ry), add2(ry, one)};
+			const f2 xt[2] = {sub2(one, rx), add2(rx, one)};
+			const f2 zq[2] = {mul2(zt[0], zt[0]), mul2(zt[1], zt[1])};
+			const f2 yq[2] = {mul2(yt[0], yt[0]), mul2(yt[1], yt[1])};
+			const f2 xq[2] = {mul2(xt[0], xt[0]), mul2(xt[1], xt[1])};
+			f2 g = mk2(0.f, 0.f);
+#pragma unroll
+			for (int zy = 0; zy < 4; ++zy) {
+				const f2 sq_zy = add2(zq[zy >> 1], yq[zy & 1]);
+				const f2 dt_zy = add2(zt[zy >> 1], yt[zy & 1]);
+#pragma unroll
+				for (int x = 0; x < 2; ++x) {
+					if (mask & (1u << kCornerBit[zy * 2 + x]))
+						g = fma2(add2(dt_zy, xt[x]), inv_cube2(add2(sq_zy, xq[x])), g);
+				}
+			}
+			const f2 sqc = fma2(rx, rx, fma2(ry, ry, mul2(rz, rz)));
+			const f2 sdot = fma2(mk2(szf, szf), rz, fma2(mk2(syf, syf), ry, mul2(mk2(sxf, sxf), rx)));
+			g = fma2(sdot, inv_cube2(sqc), g);
+			// G = -g
+			f0[p] = sub2(f0[p], g);
+			f1[p] = fma2(g, mk2(-h1, -h1), f1[p]);
+			f2s[p] = fma2(g, mk2(-h2, -h2), f2s[p]);
+		}
+		if (++pending == 16) {
+			pending = 0;
+#pragma unroll
+			for (int p = 0; p < NP; ++p) {
+				d0[p][0] += (double)lo2(f0[p]); d0[p][1] += (double)hi2(f0[p]);
+				d1[p][0] += (double)lo2(f1[p]); d1[p][1] += (double)hi2(f1[p]);
+				d2[p][0] += (double)lo2(f2s[p]); d2[p][1] += (double)hi2(f2s[p]);
+				f0[p] = f1[p] = f2s[p] = mk2(0.f, 0.f);
+			}
+		}
+	}
+#pragma unroll
+	for (int p = 0; p < NP; ++p)
+#pragma unroll
+		for (int e = 0; e < 2; ++e) {
+			double* o = s_red + (threadIdx.x * NP * 2 + p * 2 + e) * 3;
+			o[0] = d0[p][e] + (double)(e ? hi2(f0[p]) : lo2(f0[p]));
+			o[1] = d1[p][e] + (double)(e ? hi2(f1[p]) : lo2(f1[p]));
+			o[2] = d2[p][e] + (double)(e ? hi2(f2s[p]) : lo2(f2s[p]));
+		}
+	__syncthreads();
+	constexpr int NL = NP * 2;
 	for (int o = threadIdx.x; o < vb * NL * 3; o += 256) {
 		const int ovs = o / (NL * 3), r = o - ovs * (NL * 3);
 		const int ob = blockIdx.y * vb + ovs, lead = a.lead0 + r / 3;
@@ -849,12 +995,19 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		ma.pos = m->d_pos; ma.mask = m->d_mask; ma.at32 = m->d_at32; ma.segs = m->d_msegs; ma.params = m->d_params; ma.leads = d_leads;
 		ma.mom = m->d_mom; ma.B = (int32_t)B; ma.L = (int32_t)L; ma.n_layers = m->n_layers; ma.vb_shift = vb_shift; ma.nbr = a.nbr;
 		if (need_k0) { EKG_CUDA(cudaEventRecord(m->ev_k0, st)); need_k0 = false; }
+		// the 8-corner stencil ("3D4") has its own packed-fp32x2 kernel; make sure the table is what it hard-codes
+		static const int corner_bit[8] = {0, 2, 6, 8, 17, 19, 23, 25};
+		bool corners = a.nbr.n == 8 && getenv("EKGSIM_B200_GENERIC_MOMENTS") == nullptr;
+		for (int k = 0; corners && k < 8; ++k)
+			corners = a.nbr.bit[k] == corner_bit[k] && a.nbr.dz[k] == ((k & 4) ? 1 : -1) && a.nbr.dy[k] == ((k & 2) ? 1 : -1) && a.nbr.dx[k] == ((k & 1) ? 1 : -1);
 		if (m->n_msegs > 0) {
 			const dim3 grid((unsigned)m->n_msegs, (unsigned)groups, 1);
 			for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
 				ma.lead0 = lead0;
 				const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
-				if (nl <= 2) ecg_moment_kernel<2><<<grid, 256, 0, st>>>(ma);
+				if (corners && nl <= 2) ecg_moment_corners_kernel<1><<<grid, 256, 0, st>>>(ma);
+				else if (corners) ecg_moment_corners_kernel<2><<<grid, 256, 0, st>>>(ma);
+				else if (nl <= 2) ecg_moment_kernel<2><<<grid, 256, 0, st>>>(ma);
 				else ecg_moment_kernel<4><<<grid, 256, 0, st>>>(ma);
 				EKG_CUDA(cudaGetLastError());
 				++m->last_launches;
@@ -869,6 +1022,7 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		EKG_CUDA(cudaGetLastError());
 		++m->last_launches;
 		m->last_kernel = T_loop > 0 ? "ecg_kernel<HOISTED> + ecg_moment_kernel" : "ecg_moment_kernel";
+		(void)corners;
 	}
 	return EKG_OK;
 }

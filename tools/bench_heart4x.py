@@ -62,7 +62,7 @@ def main():
     k = np.ascontiguousarray(g["layer_k"][:1])
     lead_b = np.ascontiguousarray(leads[None])
     T = 400
-    mode = ek.MODE_DIRECT if a.mode == "direct" else ek.MODE_HOISTED
+    mode = {"direct": ek.MODE_DIRECT, "hoisted": ek.MODE_HOISTED, "separable": ek.MODE_SEPARABLE}[a.mode]
     d_k = torch.from_numpy(k).to(dev)
     d_l = torch.from_numpy(lead_b).to(dev)
     d_e = torch.empty((1, 2, T), dtype=torch.float64, device=dev)
