@@ -138,8 +138,8 @@ __device__ __forceinline__ double ordered_sum(double e, unsigned mask) {
 	return s;
 }
 
-__device__ __forceinline__ double eval_full(const double (&k)[9], double px, double py, Factors& f, unsigned mask) {
-	const double c = f_tail_c(k[6], k[7]);
+// f(x) with all factors computed (and remembered in `f`); c = f_tail_c(k6, k7)
+__device__ __forceinline__ double eval_full(const double (&k)[9], double c, double px, double py, Factors& f, unsigned mask) {
 	f.A = f_A(k[1], px);
 	f.E4 = f_exp(k[4], px);
 	f.E5 = f_exp(k[5], px);
@@ -147,20 +147,25 @@ __device__ __forceinline__ double eval_full(const double (&k)[9], double px, dou
 	return ordered_sum(sqr(sub(f_value(k[0], k[2], k[3], f.A, f.E4, f.E5, f.Q), py)), mask);
 }
 
-// f(x1) where x1 differs from the iterate behind `f` only in coefficient `which` (compile-time after unrolling)
-__device__ __forceinline__ double eval_perturbed(const double (&k)[9], int which, double px, double py, const Factors& f, unsigned mask) {
+// f(x1) where x1 differs from the iterate behind `f` only in coefficient `which` (compile-time after unrolling);
+// c = f_tail_c of x1's (k6, k7)
+__device__ __forceinline__ double eval_perturbed(const double (&k)[9], int which, double c, double px, double py, const Factors& f, unsigned mask) {
 	double A = f.A, E4 = f.E4, E5 = f.E5, Q = f.Q;
 	switch (which) {
 	case 1: A = f_A(k[1], px); break;
 	case 4: E4 = f_exp(k[4], px); break;
 	case 5: E5 = f_exp(k[5], px); break;
-	case 6: case 7: case 8: Q = f_Q(k[6], k[7], k[8], f_tail_c(k[6], k[7]), px); break;
+	case 6: case 7: case 8: Q = f_Q(k[6], k[7], k[8], c, px); break;
 	default: break;
 	}
 	return ordered_sum(sqr(sub(f_value(k[0], k[2], k[3], A, E4, E5, Q), py)), mask);
 }
 
-__global__ void __launch_bounds__(128) fit_descent_kernel(FitArgs a) {
+// DM: compile-time set of fitted coefficients (bit q <=> d[q] != 0), 0 = decide at run time.  The reference's
+// set {k3, k5, k6, k7, k8} has its own instantiation: state of the coefficients that never move stays out of
+// registers (96 registers -> 5 CTAs per SM, the whole 256-vector batch in one wave).
+template <unsigned DM>
+__global__ void __launch_bounds__(128, 5) fit_descent_kernel(FitArgs a) {
 	const int per_b = a.nl - a.nb;  // inner layers per vector
 	const int fit = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
 	if (fit >= a.B * per_b) return;  // whole half-warps leave together
@@ -189,44 +194,60 @@ __global__ void __launch_bounds__(128) fit_descent_kernel(FitArgs a) {
 	const double px = add(x1, mul(sub(x2, x1), ratio));   // LineConnector::getX, sim.cpp:107-109
 	const double py = add(mul(ck, px), cn);               // sim.cpp:102-104
 
-	double x0[9], move[9], grad[9], old_grad[9];
+	double x0[9], move[9], grad[9];   // grad: the previous iteration's gradient until overwritten in place
+	auto fitted = [&](int q) { return DM ? ((DM >> q) & 1u) != 0 : a.d[q] != 0; };
 	const double* ka = a.border_k + (size_t)(b * a.nb + ja) * 9;
 	const double* kb = a.border_k + (size_t)(b * a.nb + jb) * 9;
 #pragma unroll
 	for (int q = 0; q < 9; ++q) {
 		x0[q] = add(mul(ka[q], sub(1.0, ratio)), mul(kb[q], ratio));  // combineAps, sim.cpp:705-709
-		move[q] = a.d[q];
-		old_grad[q] = 0.0;
+		move[q] = fitted(q) ? a.d[q] : 0.0;
 		grad[q] = 0.0;
 	}
+	// ln(2^(k7/k6) - 1) depends on (k6, k7) only and is the same for all 15 points: computed once per distinct
+	// (k6, k7) -- the iterate's value c0 serves the k8 perturbation, the two values of the k6 and k7 perturbations
+	// are computed side by side in odd and even lanes and exchanged -- always by the same function, so every
+	// use sees the bits a fresh evaluation would give
 	Factors cache, trial;
-	double y0 = eval_full(x0, px, py, cache, mask);
+	double c0 = f_tail_c(x0[6], x0[7]);
+	double y0 = eval_full(x0, c0, px, py, cache, mask);
 	double step = a.step;
+	const double h6 = mul(a.d[6], .001), h7 = mul(a.d[7], .001);
+	const bool odd = threadIdx.x & 1;
 	for (int it = a.iterations; it > 0 && y0 > a.eps; --it) {
 		bool step_change = false;
+		double c6 = c0, c7 = c0;
+		if (fitted(6) || fitted(7)) {
+			const double t = f_tail_c(odd ? add(x0[6], h6) : x0[6], odd ? x0[7] : add(x0[7], h7));
+			c6 = __shfl_sync(mask, t, 1, 16);
+			c7 = __shfl_sync(mask, t, 0, 16);
+		}
 #pragma unroll
 		for (int q = 0; q < 9; ++q) {
-			if (a.d[q] != 0) {
+			if (fitted(q)) {
 				double x1v[9];
 #pragma unroll
 				for (int r = 0; r < 9; ++r) x1v[r] = x0[r];
 				const double h = mul(a.d[q], .001);
 				x1v[q] = add(x1v[q], h);
-				const double g = dvd(sub(eval_perturbed(x1v, q, px, py, cache, mask), y0), h);
-				grad[q] = g;
-				if (mul(g, old_grad[q]) < 0) { move[q] = mul(move[q], 0.5); step_change = true; }
-				else if (fabs(g) > mul(0.75, fabs(old_grad[q]))) move[q] = mul(move[q], 1.5);
-			} else grad[q] = 0.0;
+				const double c = q == 6 ? c6 : q == 7 ? c7 : c0;
+				const double g = dvd(sub(eval_perturbed(x1v, q, c, px, py, cache, mask), y0), h);
+				if (mul(g, grad[q]) < 0) { move[q] = mul(move[q], 0.5); step_change = true; }
+				else if (fabs(g) > mul(0.75, fabs(grad[q]))) move[q] = mul(move[q], 1.5);
+				grad[q] = g;   // oldGrad = grad, nonlinearFit.h:144 (only its own component is ever read)
+			}
 		}
 		double x1v[9];
 #pragma unroll
 		for (int q = 0; q < 9; ++q) {
-			old_grad[q] = grad[q];
-			x1v[q] = sub(x0[q], mul(step, (grad[q] > 0) ? move[q] : -move[q]));
+			// a coefficient that is not fitted has grad = 0 and move = d = 0: x - step * (-0) = x (nonlinearFit.h:148-150)
+			x1v[q] = fitted(q) ? sub(x0[q], mul(step, (grad[q] > 0) ? move[q] : -move[q])) : x0[q];
 		}
-		const double y1 = eval_full(x1v, px, py, trial, mask);
+		const double c1 = f_tail_c(x1v[6], x1v[7]);
+		const double y1 = eval_full(x1v, c1, px, py, trial, mask);
 		if (y1 < y0) {
 			y0 = y1;
+			c0 = c1;
 #pragma unroll
 			for (int q = 0; q < 9; ++q) x0[q] = x1v[q];
 			cache = trial;
@@ -271,7 +292,10 @@ int run_fit(ekg_model* m, const double* d_border_k, int64_t B, int64_t n_border,
 	m->last_launches = 1;
 	const int64_t fits = B * (n_layers - n_border);
 	if (fits > 0) {
-		fit_descent_kernel<<<(unsigned)((fits + 7) / 8), 128, 0, st>>>(a);
+		unsigned dm = 0;
+		for (int q = 0; q < 9; ++q) if (d9[q] != 0) dm |= 1u << q;
+		if (dm == 0x1E8u) fit_descent_kernel<0x1E8u><<<(unsigned)((fits + 7) / 8), 128, 0, st>>>(a);   // k3, k5, k6, k7, k8 (sim.cpp:877)
+		else fit_descent_kernel<0u><<<(unsigned)((fits + 7) / 8), 128, 0, st>>>(a);
 		EKG_CUDA(cudaGetLastError());
 		++m->last_launches;
 	}
