@@ -404,7 +404,7 @@ __device__ constexpr int kCornerBit[8] = {0, 2, 6, 8, 17, 19, 23, 25};
 // 4 packed instructions + 2 MUFU + 7 packed for the inverse cube per corner and lead pair (the generic loop
 // issues ~35 scalar instructions per corner and lead).  NP = lead pairs per pass.
 template <int NP>
-__global__ void __launch_bounds__(256) ecg_moment_corners_kernel(const MomentArgs a) {
+__global__ void __launch_bounds__(256, NP == 1 ? 4 : 2) ecg_moment_corners_kernel(const MomentArgs a) {
 	__shared__ double s_red[256 * NP * 6];
 	const Segment sg = a.segs[blockIdx.x];
 	const int vb = 1 << a.vb_shift;
@@ -412,21 +412,20 @@ __global__ void __launch_bounds__(256) ecg_moment_corners_kernel(const MomentArg
 	const int b = blockIdx.y * vb + vs;
 	const int bb = min(b, a.B - 1);
 
-	f2 lh[NP][3], ll[NP][3];   // lead coordinates (z, y, x) of the two leads of a pair, fp32 hi and lo parts
+	// lead coordinates (z, y, x) of the two leads of a pair, rounded to fp32: a lead displaced by < 2^-17 voxel for ALL
+	// voxels alike (the time-loop kernels carry a lo part as well; it changes the ECG by ~1e-7 of its peak)
+	f2 lh[NP][3];
 #pragma unroll
 	for (int p = 0; p < NP; ++p)
 #pragma unroll
 		for (int c = 0; c < 3; ++c) {
-			float h[2], l[2];
+			float h[2];
 #pragma unroll
 			for (int e = 0; e < 2; ++e) {
 				const int lead = a.lead0 + 2 * p + e;
-				const double v = lead < a.L ? a.leads[((int64_t)bb * a.L + lead) * 3 + c] : 1e6;   // a far-away dummy lead
-				h[e] = (float)v;
-				l[e] = (float)(v - (double)h[e]);
+				h[e] = (float)(lead < a.L ? a.leads[((int64_t)bb * a.L + lead) * 3 + c] : 1e6);   // a far-away dummy lead
 			}
 			lh[p][c] = mk2(h[0], h[1]);
-			ll[p][c] = mk2(l[0], l[1]);
 		}
 	const float* Pv = a.params + ((int64_t)bb * a.n_layers + (sg.layer - 1)) * kParamStride;
 	const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
@@ -450,22 +449,17 @@ __global__ void __launch_bounds__(256) ecg_moment_corners_kernel(const MomentArg
 		const float px = __uint_as_float(0x4B000000u | ((pos & 0x7ffu) + 1u)) - 8388608.f;
 		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));
 		const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
-		// S = sum of the offsets of the occupied corners, per axis: (# with +1) - (# with -1), as floats via the
-		// 2^23 trick (values -8..8, no I2F)
 		constexpr uint32_t kAll = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8) | (1u << 17) | (1u << 19) | (1u << 23) | (1u << 25);
 		constexpr uint32_t kZp = (1u << 17) | (1u << 19) | (1u << 23) | (1u << 25);
 		constexpr uint32_t kYp = (1u << 6) | (1u << 8) | (1u << 23) | (1u << 25);
 		constexpr uint32_t kXp = (1u << 2) | (1u << 8) | (1u << 19) | (1u << 25);
-		const int n_occ = __popc(mask & kAll);
-		const float szf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kZp) - n_occ)) - 8388616.f;
-		const float syf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kYp) - n_occ)) - 8388616.f;
-		const float sxf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kXp) - n_occ)) - 8388616.f;
+		const bool interior = (mask & kAll) == kAll;   // all 8 corners occupied: most of the model
 		const f2 PZ = mk2(pz, pz), PY = mk2(py, py), PX = mk2(px, px);
 #pragma unroll
 		for (int p = 0; p < NP; ++p) {
-			const f2 rz = add2(sub2(lh[p][0], PZ), ll[p][0]);
-			const f2 ry = add2(sub2(lh[p][1], PY), ll[p][1]);
-			const f2 rx = add2(sub2(lh[p][2], PX), ll[p][2]);
+			const f2 rz = sub2(lh[p][0], PZ);
+			const f2 ry = sub2(lh[p][1], PY);
+			const f2 rx = sub2(lh[p][2], PX);
 			const f2 zt[2] = {sub2(one, rz), add2(rz, one)};   // [0]: d = -1 -> -(r - 1),  [1]: d = +1 -> r + 1
 			const f2 yt[2] = {sub2(one, ry), add2(ry, one)};
 			const f2 xt[2] = {sub2(one, rx), add2(rx, one)};
@@ -473,19 +467,34 @@ __global__ void __launch_bounds__(256) ecg_moment_corners_kernel(const MomentArg
 			const f2 yq[2] = {mul2(yt[0], yt[0]), mul2(yt[1], yt[1])};
 			const f2 xq[2] = {mul2(xt[0], xt[0]), mul2(xt[1], xt[1])};
 			f2 g = mk2(0.f, 0.f);
+			auto corners = [&](auto all_tag) {
+				constexpr bool ALL = decltype(all_tag)::value;
 #pragma unroll
-			for (int zy = 0; zy < 4; ++zy) {
-				const f2 sq_zy = add2(zq[zy >> 1], yq[zy & 1]);
-				const f2 dt_zy = add2(zt[zy >> 1], yt[zy & 1]);
+				for (int zy = 0; zy < 4; ++zy) {
+					const f2 sq_zy = add2(zq[zy >> 1], yq[zy & 1]);
+					const f2 dt_zy = add2(zt[zy >> 1], yt[zy & 1]);
 #pragma unroll
-				for (int x = 0; x < 2; ++x) {
-					if (mask & (1u << kCornerBit[zy * 2 + x]))
-						g = fma2(add2(dt_zy, xt[x]), inv_cube2(add2(sq_zy, xq[x])), g);
+					for (int x = 0; x < 2; ++x) {
+						if (ALL || (mask & (1u << kCornerBit[zy * 2 + x])))
+							g = fma2(add2(dt_zy, xt[x]), inv_cube2(add2(sq_zy, xq[x])), g);
+					}
 				}
+			};
+			if (interior) {
+				// the offsets of all 8 corners add up to zero: no centre term (and no per-corner tests)
+				corners(std::true_type{});
+			} else {
+				corners(std::false_type{});
+				// S = sum of the offsets of the occupied corners, per axis: (# with +1) - (# with -1), as floats via the
+				// 2^23 trick (values -8..8, no I2F)
+				const int n_occ = __popc(mask & kAll);
+				const float szf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kZp) - n_occ)) - 8388616.f;
+				const float syf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kYp) - n_occ)) - 8388616.f;
+				const float sxf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kXp) - n_occ)) - 8388616.f;
+				const f2 sqc = fma2(rx, rx, fma2(ry, ry, mul2(rz, rz)));
+				const f2 sdot = fma2(mk2(szf, szf), rz, fma2(mk2(syf, syf), ry, mul2(mk2(sxf, sxf), rx)));
+				g = fma2(sdot, inv_cube2(sqc), g);
 			}
-			const f2 sqc = fma2(rx, rx, fma2(ry, ry, mul2(rz, rz)));
-			const f2 sdot = fma2(mk2(szf, szf), rz, fma2(mk2(syf, syf), ry, mul2(mk2(sxf, sxf), rx)));
-			g = fma2(sdot, inv_cube2(sqc), g);
 			// G = -g
 			f0[p] = sub2(f0[p], g);
 			f1[p] = fma2(g, mk2(-h1, -h1), f1[p]);

@@ -192,7 +192,7 @@ public:
 		if (const char* d = getenv("EKGSIM_B200_DEVICE")) device_ = atoi(d);
 		if (const char* m = getenv("EKGSIM_B200_MODE")) {
 			const std::string s(m);
-			mode_ = s == "direct" ? EKG_MODE_DIRECT : s == "hoisted" ? EKG_MODE_HOISTED : EKG_MODE_DEFAULT;
+			mode_ = s == "direct" ? EKG_MODE_DIRECT : s == "hoisted" ? EKG_MODE_HOISTED : s == "separable" ? EKG_MODE_SEPARABLE : EKG_MODE_DEFAULT;
 		}
 	}
 	~EkgSim() { if (model_) ekg_model_destroy(model_); }
