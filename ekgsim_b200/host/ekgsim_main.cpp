@@ -16,7 +16,10 @@
 //         line per vector.  This is what a population-based optimizer should call per generation.
 //     ekgSim -extern <homeDir>     AMS-DEMO ExternalEvaluation protocol (ExternalEvaluation.h:95-151):
 //         reads <homeDir>/input.txt (one gene per line, '#' comments), writes <homeDir>/output.txt
-//         (criteria, then "# violation v").
+//         (criteria, then "# violation v").  With -server <socket> or EKGSIM_B200_SERVER=<socket> the genes go to a
+//         resident server instead of a fresh process.
+//     ekgSim -serve <socket>       resident evaluation service (ekg_server.h): one Evaluator with the model on the GPU,
+//         concurrent requests are evaluated together in one batch.  ekgSim -shutdown <socket> ends it.
 // The optimizer itself (`ekgSim` without arguments, AMS-DEMO over MPI) is outside the hot path and is
 // not part of this build; use the reference's optimizer with `-extern` or `-batch` as its evaluator.
 
@@ -24,6 +27,7 @@
 #include <map>
 
 #include "ekg_eval.h"
+#include "ekg_server.h"
 
 namespace {
 
@@ -125,7 +129,14 @@ void run_batch(const std::string& file, const std::string& outfile, int threads)
 	std::cout << " batch of " << sols.size() << " simulations done in " << secs << " seconds (GPU part " << ev.simulator().lastRunSeconds() << " s)\n";
 }
 
-void run_extern(const std::string& home) {
+void write_extern_output(const std::string& dir, const std::vector<double>& result, double violation) {
+	std::ofstream out((dir + "output.txt").c_str());
+	out.precision(17);
+	for (double c : result) out << c << "\n";
+	out << "# violation " << violation << "\n";
+}
+
+void run_extern(const std::string& home, std::string server) {
 	const std::string dir = home.empty() ? std::string() : home + "/";
 	std::ifstream in((dir + "input.txt").c_str());
 	if (!in.is_open()) throw std::runtime_error("could not open " + dir + "input.txt");
@@ -136,13 +147,23 @@ void run_extern(const std::string& home) {
 		double d;
 		while (ls >> d) genes.push_back(d);
 	}
-	ekg::Evaluator ev("simulator.ini");
 	std::vector<double> result;
-	const double violation = ev.eval(genes, result);
-	std::ofstream out((dir + "output.txt").c_str());
-	out.precision(17);
-	for (double c : result) out << c << "\n";
-	out << "# violation " << violation << "\n";
+	double violation = 0;
+	if (server.empty()) if (const char* e = getenv("EKGSIM_B200_SERVER")) server = e;
+	if (!server.empty()) {
+		// a resident `ekgSim -serve` holds the model on the GPU: milliseconds instead of a process start-up per evaluation
+		if (ekg::remote_eval(server, genes, result, violation)) { write_extern_output(dir, result, violation); return; }
+		std::cerr << "no evaluation server at " << server << ", evaluating in this process\n";
+	}
+	ekg::Evaluator ev("simulator.ini");
+	violation = ev.eval(genes, result);
+	write_extern_output(dir, result, violation);
+}
+
+void run_serve(const std::string& path) {
+	std::cerr << "##### Starting the evaluation server ############################\n";
+	ekg::Evaluator ev("simulator.ini");
+	ekg::serve(ev, path);
 }
 
 }  // namespace
@@ -157,7 +178,9 @@ int main(int argc, char** argv) {
 			std::cout << "Argument list:\n   -? \tshow this help screen\n   -sim \tjust run single a simulation with parameters provided after -sim\n"
 			             "   -out \tspecify outputs of the program; possible values include result, layer_aps, cell_aps <num> [<num>]*\n"
 			             "   -batch \tevaluate every parameter vector of a text file in one GPU batch [-batchout file] [-threads n]\n"
-			             "   -extern \tAMS-DEMO ExternalEvaluation protocol: <homeDir>/input.txt -> <homeDir>/output.txt\n";
+			             "   -extern \tAMS-DEMO ExternalEvaluation protocol: <homeDir>/input.txt -> <homeDir>/output.txt [-server socket]\n"
+			             "   -serve \tresident evaluation server on a unix socket (clients: -extern with -server or EKGSIM_B200_SERVER)\n"
+			             "   -shutdown \task the server on the given socket to exit\n";
 		} else if (args.is_set("-sim")) {
 			const std::vector<double> params = parse_vector(args.get("-sim"));
 			std::cout << " parameters for single simulator run: " << ekg::angle_list(params) << "\n";
@@ -169,7 +192,13 @@ int main(int argc, char** argv) {
 			run_batch(args.get("-batch"), args.get("-batchout"), atoi(args.get("-threads").c_str()));
 		} else if (args.is_set("-extern")) {
 			std::cerr << "\n";
-			run_extern(args.get("-extern"));
+			run_extern(args.get("-extern"), args.get("-server"));
+		} else if (args.is_set("-serve")) {
+			std::cerr << "\n";
+			if (args.get("-serve").empty()) throw std::runtime_error("-serve needs a socket path");
+			run_serve(args.get("-serve"));
+		} else if (args.is_set("-shutdown")) {
+			ekg::remote_shutdown(args.get("-shutdown"));
 		} else {
 			std::cout << "the optimizer (AMS-DEMO) is not part of the B200 build; use -sim, -batch or -extern as its evaluator\n";
 		}

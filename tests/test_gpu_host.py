@@ -236,3 +236,57 @@ def test_batch_device_fit_equals_host_fit(testrun, monkeypatch):
     assert np.abs(crit_dev - crit_host).max() < 1e-7
     assert (viol_dev == viol_host).all()
     assert np.abs(one - crit_dev[5]).max() < 1e-6
+
+
+def test_evaluation_server_batches_concurrent_extern_clients(testrun, golden):
+    """`ekgSim -serve <socket>` keeps the model on the GPU; 12 concurrent `ekgSim -extern process<i>`
+    clients (what AMS-DEMO's MPI worker ranks start, ExternalEvaluation.h:95-151) are answered from it, several per batch."""
+    import time
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    want = np.load(os.path.join(GOLDEN, "golden_criteria256.npz"))
+    sock = os.path.join(testrun, "ekg.sock")
+    srv = subprocess.Popen([hostlib.CLI, "-serve", sock], cwd=testrun, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock) or srv.poll() is not None:
+                break
+            time.sleep(0.1)
+        assert os.path.exists(sock), srv.stderr.read()
+        n = 12
+        for i in range(n):
+            os.makedirs(os.path.join(testrun, "process%d" % i), exist_ok=True)
+            with open(os.path.join(testrun, "process%d" % i, "input.txt"), "w") as f:
+                f.write("# file generated by ExternalEvaluation class\n" + "\n".join("%.17g" % v for v in g["params"][i]) + "\n")
+        env = dict(os.environ, EKGSIM_B200_SERVER=sock)
+        t0 = time.time()
+        procs = [subprocess.Popen([hostlib.CLI, "-extern", "process%d" % i], cwd=testrun, env=env, stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL, text=True) for i in range(n)]
+        outs = [p.communicate(timeout=120)[0] for p in procs]
+        dt = time.time() - t0
+        for i in range(n):
+            assert "All done" in outs[i] and "error" not in outs[i], outs[i]
+            lines = open(os.path.join(testrun, "process%d" % i, "output.txt")).read().split("\n")
+            crit = np.array([float(lines[0]), float(lines[1])])
+            assert np.abs(crit - want["criteria"][i]).max() < 1e-4, (i, crit)
+            assert abs(float(lines[2].split()[-1]) - want["violation"][i]) < 1e-9
+        # one more, alone, timed: connection + evaluation + files
+        t1 = time.time()
+        subprocess.run([hostlib.CLI, "-extern", "process0"], cwd=testrun, env=env, capture_output=True, text=True, timeout=60)
+        one = time.time() - t1
+        print("evaluation server: %d concurrent -extern clients in %.3f s, one client alone %.1f ms" % (n, dt, one * 1e3))
+        # a chromosome of the wrong length is refused without disturbing the server
+        with open(os.path.join(testrun, "process1", "input.txt"), "w") as f:
+            f.write("1\n2\n3\n")
+        r = subprocess.run([hostlib.CLI, "-extern", "process1"], cwd=testrun, env=env, capture_output=True, text=True, timeout=60)
+        assert "runtime error caught: chromosome size does not agree" in r.stdout
+        r = subprocess.run([hostlib.CLI, "-extern", "process2"], cwd=testrun, env=env, capture_output=True, text=True, timeout=60)
+        assert "All done" in r.stdout and "error" not in r.stdout
+    finally:
+        subprocess.run([hostlib.CLI, "-shutdown", sock], cwd=testrun, capture_output=True, timeout=30)
+        try:
+            err = srv.communicate(timeout=30)[1]
+        except subprocess.TimeoutExpired:
+            srv.kill()
+            err = srv.communicate()[1]
+    assert "evaluations in" in err, err[-500:]
+    assert not os.path.exists(sock)

@@ -117,3 +117,48 @@ def test_binary_shape_cache(tmp_path, built, monkeypatch):
     hostlib.Evaluator(d, with_device=False).close()
     raw2 = np.fromfile(cache, dtype=np.uint16, offset=48)
     assert (raw2 != raw.reshape(-1)).sum() == 1
+
+
+def test_extern_client_speaks_the_server_protocol(tmp_path, built):
+    """`ekgSim -extern <homeDir> -server <socket>` against a stand-in server written in Python: request =
+    'EKG1' | u32 n | f64 genes[n], reply = i32 0 | u32 n | f64 violation | f64 criteria[n]  (ekg_server.h).
+    No GPU and no simulator.ini needed on the client side."""
+    import socket
+    import struct
+    import threading
+    d = str(tmp_path)
+    os.makedirs(os.path.join(d, "process3"))
+    genes = [0.00035813, 0.0890636, 226.183, -13.5]
+    with open(os.path.join(d, "process3", "input.txt"), "w") as f:
+        f.write("# file generated by ExternalEvaluation class\n" + "\n".join("%.17g" % g for g in genes) + "\n")
+    path = os.path.join(d, "s.sock")
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(path)
+    srv.listen(4)
+    seen = {}
+
+    def serve_two():
+        for k in range(2):
+            c, _ = srv.accept()
+            magic, n = struct.unpack("<II", c.recv(8, socket.MSG_WAITALL))
+            seen[k] = (magic, struct.unpack("<%dd" % n, c.recv(8 * n, socket.MSG_WAITALL)))
+            if k == 0:
+                c.sendall(struct.pack("<iId2d", 0, 2, 240.609, 1.48975, 1.22272))
+            else:
+                msg = b"chromosome size does not agree"
+                c.sendall(struct.pack("<iI", -1, len(msg)) + msg)
+            c.close()
+
+    th = threading.Thread(target=serve_two, daemon=True)
+    th.start()
+    r = subprocess.run([hostlib.CLI, "-extern", "process3", "-server", path], cwd=d, capture_output=True, text=True, timeout=30)
+    assert "All done" in r.stdout, r.stdout
+    out = open(os.path.join(d, "process3", "output.txt")).read().split("\n")
+    assert [float(x) for x in out[:2]] == [1.48975, 1.22272] and out[2] == "# violation 240.60900000000001"
+    assert seen[0] == (0x31474B45, tuple(genes))
+    # an error reply surfaces like every other error of the CLI (main.cpp:405-413)
+    r = subprocess.run([hostlib.CLI, "-extern", "process3"], cwd=d, capture_output=True, text=True, timeout=30,
+                       env=dict(os.environ, EKGSIM_B200_SERVER=path))
+    th.join(timeout=10)
+    assert "runtime error caught: chromosome size does not agree" in r.stdout
+    srv.close()
