@@ -16,7 +16,7 @@
 //         line per vector.  This is what a population-based optimizer should call per generation.
 //     ekgSim -extern <homeDir>     AMS-DEMO ExternalEvaluation protocol (ExternalEvaluation.h:95-151):
 //         reads <homeDir>/input.txt (one gene per line, '#' comments), writes <homeDir>/output.txt
-//         (criteria, then "# violation v").  With -server <socket> or EKGSIM_B200_SERVER=<socket> the genes go to a
+//         ("# violation v", then the criteria).  With -server <socket> or EKGSIM_B200_SERVER=<socket> the genes go to a
 //         resident server instead of a fresh process.
 //     ekgSim -serve <socket>       resident evaluation service (ekg_server.h): one Evaluator with the model on the GPU,
 //         concurrent requests are evaluated together in one batch.  ekgSim -shutdown <socket> ends it.
@@ -130,10 +130,12 @@ void run_batch(const std::string& file, const std::string& outfile, int threads)
 }
 
 void write_extern_output(const std::string& dir, const std::vector<double>& result, double violation) {
+	// ExternalEvaluation::readOut (ExternalEvaluation.h:118-151) only looks for a '#' where it expects the next value
+	// and stops after the last value: comment lines -- the violation among them -- must come BEFORE the criteria
 	std::ofstream out((dir + "output.txt").c_str());
 	out.precision(17);
+	out << "# written by ekgSim -extern (B200)\n# violation " << violation << "\n";
 	for (double c : result) out << c << "\n";
-	out << "# violation " << violation << "\n";
 }
 
 void run_extern(const std::string& home, std::string server) {

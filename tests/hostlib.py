@@ -86,3 +86,31 @@ class Evaluator:
         if rc:
             raise RuntimeError(lib().ekg_host_last_error().decode())
         return crit, viol
+
+
+def read_extern_output(path, n_criteria, n_properties=0):
+    """ExternalEvaluation::readOut restated (ExternalEvaluation.h:118-151): at every position where a value is
+    expected a '#' starts a comment line ("violation <v>" sets the violation); reading stops after the last value."""
+    data = open(path).read()
+    pos, values, violation = 0, [], 0.0
+    while len(values) < n_criteria + n_properties:
+        if pos < len(data) and data[pos] == "#":          # file.peek() == '#'
+            end = data.find("\n", pos)
+            end = len(data) if end < 0 else end
+            words = data[pos + 1:end].split()
+            if words and words[0] == "violation":
+                violation = float(words[1])
+            pos = end + 1                                   # getline consumes the newline
+        else:
+            while pos < len(data) and data[pos].isspace():  # operator>> skips leading whitespace ...
+                pos += 1
+            end = pos
+            while end < len(data) and not data[end].isspace():
+                end += 1
+            try:
+                values.append(float(data[pos:end]))
+            except ValueError:                              # ... and a failed read leaves infinity behind
+                values.append(float("inf"))
+                violation = float("inf")
+            pos = end                                       # the newline after a value is NOT consumed
+    return values[:n_criteria], violation

@@ -121,10 +121,16 @@ def test_cli_extern_protocol(testrun, golden):
         f.write("# file generated by ExternalEvaluation class\n" + "\n".join("%.17g" % v for v in golden["params"][i]) + "\n")
     r = subprocess.run([hostlib.CLI, "-extern", "process1"], cwd=testrun, capture_output=True, text=True)
     assert r.returncode == 0 and "caught" not in r.stdout, r.stdout
-    txt = open(os.path.join(home, "output.txt")).read().split("\n")
-    crit = [float(x) for x in txt[:2]]
+    crit, viol = hostlib.read_extern_output(os.path.join(home, "output.txt"), 2)     # the reference's own reader, restated
     assert np.abs(np.array(crit) - golden["criteria"][i]).max() < 1e-4
-    assert txt[2].startswith("# violation 0")
+    assert viol == golden["violation"][i]
+    # an out-of-bounds vector: the violation must reach the optimizer through that reader
+    j = list(golden["name"]).index("full1")
+    with open(os.path.join(home, "input.txt"), "w") as f:
+        f.write("# file generated by ExternalEvaluation class\n" + "\n".join("%.17g" % v for v in golden["params"][j]) + "\n")
+    subprocess.run([hostlib.CLI, "-extern", "process1"], cwd=testrun, capture_output=True, text=True)
+    crit, viol = hostlib.read_extern_output(os.path.join(home, "output.txt"), 2)
+    assert viol > 0 and abs(viol - golden["violation"][j]) < 1e-9 and np.abs(np.array(crit) - golden["criteria"][j]).max() < 1e-4
 
 
 def test_reference_glue_on_b200_simlib(testrun, golden):
@@ -265,10 +271,9 @@ def test_evaluation_server_batches_concurrent_extern_clients(testrun, golden):
         dt = time.time() - t0
         for i in range(n):
             assert "All done" in outs[i] and "error" not in outs[i], outs[i]
-            lines = open(os.path.join(testrun, "process%d" % i, "output.txt")).read().split("\n")
-            crit = np.array([float(lines[0]), float(lines[1])])
-            assert np.abs(crit - want["criteria"][i]).max() < 1e-4, (i, crit)
-            assert abs(float(lines[2].split()[-1]) - want["violation"][i]) < 1e-9
+            crit, viol = hostlib.read_extern_output(os.path.join(testrun, "process%d" % i, "output.txt"), 2)
+            assert np.abs(np.array(crit) - want["criteria"][i]).max() < 1e-4, (i, crit)
+            assert abs(viol - want["violation"][i]) < 1e-9
         # one more, alone, timed: connection + evaluation + files
         t1 = time.time()
         subprocess.run([hostlib.CLI, "-extern", "process0"], cwd=testrun, env=env, capture_output=True, text=True, timeout=60)
@@ -290,3 +295,77 @@ def test_evaluation_server_batches_concurrent_extern_clients(testrun, golden):
             err = srv.communicate()[1]
     assert "evaluations in" in err, err[-500:]
     assert not os.path.exists(sock)
+
+
+AMS_DEMO_SETTINGS = """[evaluation]
+command line = {cli} -extern
+input file name = input.txt
+output file name = output.txt
+chromosome vector length = 16
+criteria vector length = 2
+properties vector length = 0
+
+[optimization]
+random seed = 11
+population size = {pop}
+max number of generations = {gens}
+DE schema = rand/1/bin
+p crossover = 0.3
+scaling factors = 0.5
+queue length = 1
+
+[initial population]
+gene min = 0.0003, 0.01, 0.01, 200, 0.0003, 0.01, 0.01, 200, 0.0003, 0.01, 0.01, 200, -50, -50, -50, -50
+gene max = 0.001, 0.1, 0.1, 400, 0.001, 0.1, 0.1, 400, 0.001, 0.1, 0.1, 400, 50, 50, 50, 50
+"""
+
+
+def test_reference_ams_demo_drives_extern_and_server(built, tmp_path):
+    """BASELINE config 5 as a drop-in: the reference's UNMODIFIED stand-alone optimizer (AMS-DEMO/main.cpp, sequential
+    build, oracle/_ref/DEMO_ref) evaluates through its ExternalEvaluation protocol -- `ekgSim -extern <homeDir>` per
+    individual, answered by the resident `ekgSim -serve`.  Every row of its evaluations.txt must carry the criteria and
+    the violation this build computes for the genes the optimizer wrote to input.txt (6 significant digits,
+    ExternalEvaluation.h:111-112)."""
+    import time
+    demo = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "DEMO_ref")
+    if not os.path.exists(demo):
+        pytest.skip("oracle/_ref/DEMO_ref not built (needs /root/reference at build time)")
+    d = str(tmp_path)
+    ekgio.materialise_testrun(d, targets="target_ecg_v2_v6.column")
+    pop, gens = 12, 2
+    with open(os.path.join(d, "settings.ini"), "w") as f:
+        f.write(AMS_DEMO_SETTINGS.format(cli=hostlib.CLI, pop=pop, gens=gens))
+    sock = os.path.join(d, "ekg.sock")
+    srv = subprocess.Popen([hostlib.CLI, "-serve", sock], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock) or srv.poll() is not None:
+                break
+            time.sleep(0.1)
+        assert os.path.exists(sock)
+        t0 = time.time()
+        r = subprocess.run([demo], cwd=d, capture_output=True, text=True, timeout=600, env=dict(os.environ, EKGSIM_B200_SERVER=sock))
+        dt = time.time() - t0
+    finally:
+        subprocess.run([hostlib.CLI, "-shutdown", sock], cwd=d, capture_output=True, timeout=30)
+        try:
+            err = srv.communicate(timeout=30)[1]
+        except subprocess.TimeoutExpired:
+            srv.kill()
+            err = srv.communicate()[1]
+    assert "last front saved as front.txt" in r.stdout, r.stdout[-500:]
+    rows = [ln.split("\t") for ln in open(os.path.join(d, "evaluations.txt")) if ln.strip() and not ln.startswith("#")]
+    assert len(rows) >= pop * gens
+    vec = lambda s: np.array([float(x) for x in s.strip().strip("<>").split(",") if x])
+    genes = np.array([vec(rw[1]) for rw in rows])
+    seen = np.array([[float("%g" % v) for v in gn] for gn in genes])        # what writeIn put into input.txt
+    viol = np.array([float(rw[2]) for rw in rows])
+    crit = np.array([vec(rw[4]) for rw in rows])
+    ev = hostlib.Evaluator(d, with_device=True)
+    want_c, want_v = ev.eval_batch(seen)
+    ev.close()
+    # (one vector per server batch there, one batch of all here: the fp32 partial sums group differently)
+    assert np.abs(crit - want_c).max() < 1e-6 and np.abs(viol - want_v).max() < 1e-9
+    assert (viol > 0).any() and (viol == 0).any()      # the gene box is wider than the k8 limits of the ini: both cases occur
+    print("AMS-DEMO (reference optimizer) + ekgSim -extern + server: %d evaluations in %.2f s (%.1f ms each); server: %s"
+          % (len(rows), dt, 1e3 * dt / len(rows), err.strip().split("\n")[-1]))

@@ -153,8 +153,8 @@ def test_extern_client_speaks_the_server_protocol(tmp_path, built):
     th.start()
     r = subprocess.run([hostlib.CLI, "-extern", "process3", "-server", path], cwd=d, capture_output=True, text=True, timeout=30)
     assert "All done" in r.stdout, r.stdout
-    out = open(os.path.join(d, "process3", "output.txt")).read().split("\n")
-    assert [float(x) for x in out[:2]] == [1.48975, 1.22272] and out[2] == "# violation 240.60900000000001"
+    crit, viol = hostlib.read_extern_output(os.path.join(d, "process3", "output.txt"), 2)   # ExternalEvaluation::readOut restated
+    assert crit == [1.48975, 1.22272] and viol == 240.609
     assert seen[0] == (0x31474B45, tuple(genes))
     # an error reply surfaces like every other error of the CLI (main.cpp:405-413)
     r = subprocess.run([hostlib.CLI, "-extern", "process3"], cwd=d, capture_output=True, text=True, timeout=30,
