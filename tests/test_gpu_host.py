@@ -369,3 +369,40 @@ def test_reference_ams_demo_drives_extern_and_server(built, tmp_path):
     assert (viol > 0).any() and (viol == 0).any()      # the gene box is wider than the k8 limits of the ini: both cases occur
     print("AMS-DEMO (reference optimizer) + ekgSim -extern + server: %d evaluations in %.2f s (%.1f ms each); server: %s"
           % (len(rows), dt, 1e3 * dt / len(rows), err.strip().split("\n")[-1]))
+
+
+def test_reference_main_with_embedded_optimizer_on_the_b200_evaluator(built, tmp_path, golden):
+    """The reference's UNMODIFIED main.cpp -- CLI and embedded AMS-DEMO optimizer -- linked against
+    ekgsim_b200/host/compat/sim_b200.cpp (struct OptimizationFunction of sim.h, the in-process
+    VirtualOptimizationFunction interface, over ekg::Evaluator) instead of sim.cpp + simlib:
+    (1) `test -sim` prints the reference's criteria, (2) `ekgSim` without arguments runs the optimizer and every
+    row of its evaluations.txt carries the criteria this build computes for that chromosome."""
+    import re
+    import time
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "ekgSim_refmain_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ekgSim_refmain_b200 not built (needs /root/reference at build time)")
+    d = str(tmp_path)
+    ekgio.materialise_testrun(d, ini_edit=lambda s: s.replace("population size = 100", "population size = 20")
+                              .replace("number of generations = 100", "number of generations = 3"))
+    i = list(golden["name"]).index("full1")
+    r = subprocess.run([exe, "test", "-sim", ",".join("%.17g" % v for v in golden["params"][i]), "-out", "result"], cwd=d,
+                       capture_output=True, text=True, timeout=300)
+    m = re.search(r" criteria = <([0-9.e+-]+),([0-9.e+-]+)>, violation = ([0-9.e+-]+)\n", r.stdout)
+    assert m, r.stdout[-600:]
+    assert abs(float(m.group(1)) - golden["criteria"][i][0]) < 1e-4 and abs(float(m.group(2)) - golden["criteria"][i][1]) < 1e-4
+    assert abs(float(m.group(3)) - golden["violation"][i]) < 1e-3
+    t0 = time.time()
+    r = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=600)
+    dt = time.time() - t0
+    assert r.returncode == 0 and "caught" not in r.stdout and r.stdout.rstrip().endswith("All done"), r.stdout[-600:]
+    rows = [ln.split("\t") for ln in open(os.path.join(d, "evaluations.txt")) if ln.strip() and not ln.startswith("#")]
+    assert len(rows) >= 60
+    vec = lambda s: np.array([float(x) for x in s.strip().strip("<>").split(",") if x])
+    genes = np.array([vec(rw[1]) for rw in rows])
+    ev = hostlib.Evaluator(d, with_device=True)
+    want_c, want_v = ev.eval_batch(genes)
+    ev.close()
+    assert np.abs(np.array([vec(rw[4]) for rw in rows]) - want_c).max() < 1e-6
+    assert np.abs(np.array([float(rw[2]) for rw in rows]) - want_v).max() < 1e-9
+    print("reference main.cpp + embedded AMS-DEMO on the B200 evaluator: %d evaluations, %.2f s for the whole process" % (len(rows), dt))
