@@ -218,6 +218,12 @@ class Model:
         _check(lib().ekg_fit_layers(self._h, _ptr(border_k), B, nb, int(mid), _ptr(d9), float(step), float(eps), int(iterations), _ptr(out)))
         return out
 
+    def fit_layers_device(self, d_border_k, B, n_border, d_layer_k, mid=-1, d9=FIT_D9, step=0.5, eps=1e-3, iterations=100, stream=0):
+        """Raw device pointers (ints) on this model's device; asynchronous on `stream`."""
+        d9 = np.ascontiguousarray(d9, dtype=np.float64)
+        _check(lib().ekg_fit_layers_device(self._h, C.c_void_p(d_border_k), int(B), int(n_border), int(mid), _ptr(d9), float(step),
+                                           float(eps), int(iterations), C.c_void_p(d_layer_k), C.c_void_p(stream)))
+
     def evaluate(self, border_k, leads_zyx, targets, mid=-1, comparison=2, target_offsets=None, d9=FIT_D9, step=0.5, eps=1e-3,
                  iterations=100, nbhd="3D4", t_start=100.0, t_step=1.0, total_time=400.0, mode=MODE_DEFAULT, want_layer_k=False,
                  want_ecg=False):

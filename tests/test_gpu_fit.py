@@ -114,3 +114,38 @@ def test_evaluate_256_border_aps_to_criteria(gpu_model24, model24):
     # the ECGs it returns are the ones ekg_simulate gives for the same coefficients
     ref = gpu_model24.simulate(lk, g["leads_zyx"], "3D4", 100.0, 1.0, 400.0, mode=2)
     assert np.abs(ref - ecg).max() == 0.0
+
+
+def test_device_pointer_entry_points_on_a_side_stream(gpu_model24):
+    """ekg_fit_layers_device -> ekg_simulate_device chained on a caller's (non-default) stream with device-resident
+    buffers (torch only provides the memory and the stream): same coefficients and ECGs as the host-buffer calls.
+    In SEPARABLE mode the library does not know k1 on the host here and reads its minimum back from the device."""
+    import torch
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    B = 40
+    border = np.ascontiguousarray(g["layer_k"][:B, [0, 14, 23]])
+    leads = np.ascontiguousarray(g["leads_zyx"][:B])
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        d_border = torch.from_numpy(border).to(dev, non_blocking=False)
+        d_leads = torch.from_numpy(leads).to(dev)
+        d_k = torch.empty((B, 24, 9), dtype=torch.float64, device=dev)
+        d_ecg = torch.empty((3, B, 2, 400), dtype=torch.float64, device=dev)
+        gpu_model24.fit_layers_device(d_border.data_ptr(), B, 3, d_k.data_ptr(), mid=14, stream=side.cuda_stream)
+        for i, mode in enumerate((1, 2, 3)):
+            gpu_model24.simulate_device(d_k.data_ptr(), d_leads.data_ptr(), B, 2, d_ecg[i].data_ptr(), "3D4", 100.0, 1.0, 400.0,
+                                        mode=mode, stream=side.cuda_stream)
+        side.synchronize()
+        k = d_k.cpu().numpy()
+        ecg = d_ecg.cpu().numpy()
+    assert k.tobytes() == gpu_model24.fit_layers(border, mid=14).tobytes()
+    for i, mode in enumerate((1, 2, 3)):
+        host = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=mode)
+        assert np.abs(host - ecg[i]).max() == 0.0, mode
+    # a run that starts inside the QRS complex: the device-side k1 minimum must put the seam where the host-side one does
+    d_e2 = torch.empty((B, 2, 60), dtype=torch.float64, device=dev)
+    gpu_model24.simulate_device(d_k.data_ptr(), d_leads.data_ptr(), B, 2, d_e2.data_ptr(), "3D4", 25.0, 1.0, 60.0, mode=3, stream=0)
+    torch.cuda.synchronize()
+    assert gpu_model24.last_kernel_name == "ecg_kernel<HOISTED> + ecg_moment_kernel"
+    assert np.abs(gpu_model24.simulate(k, leads, "3D4", 25.0, 1.0, 60.0, mode=3) - d_e2.cpu().numpy()).max() == 0.0
