@@ -402,7 +402,7 @@ def run_b200_arm(args):
             ekgio.materialise_testrun(wd)
             ev = hostlib.Evaluator(wd, with_device=True)
             pipeline = {"api": "Evaluator::evalBatch (parameter vectors -> border APs on the host -> ekg_evaluate: layer fit, "
-                               "simulation in the default mode -> ECGs -> criteria on the host)", "host_threads": host_cores()}
+                               "simulation in the default mode, curve comparison -> B x 2 criteria back to the host)", "host_threads": host_cores()}
             for pb in sorted({B, 1024}):
                 genes = np.tile(g["params"], ((pb + 255) // 256, 1))[:pb]
                 ev.eval_batch(genes)

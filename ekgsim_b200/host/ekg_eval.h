@@ -535,6 +535,23 @@ public:
 			for (size_t m = 0; m < L; ++m) for (int c = 0; c < 3; ++c) leads[(r * L + m) * 3 + c] = ind.leads[m][c];
 		}
 		size_t T = 0;
+		if (!run.empty() && fitOnDevice && criteriaOnDevice()) {
+			// plain settings (one criterion per lead, no peak-position criterion): the comparison runs on the device too,
+			// B x leads doubles come back instead of the ECGs
+			sim->moveMeasuringPointsTo(inds[run[0]].leads);
+			std::vector<double> tg(L * targets[0].size()), crit;
+			for (size_t m = 0; m < L; ++m) std::copy(targets[m].begin(), targets[m].end(), tg.begin() + m * targets[0].size());
+			sim->evaluateBatchCriteria(k.data(), nb, interp == endo_epi ? 0 : midLayer(), fitOffsets(), 0.5, 1e-3, 100, leads.data(), run.size(),
+			                           tg.data(), targets[0].size(), targetOffsets.data(), (int)settings.comparisonMode, crit);
+			std::vector<size_t> slotOf(B, (size_t)-1);
+			for (size_t r = 0; r < run.size(); ++r) slotOf[run[r]] = r;
+			for (size_t i = 0; i < B; ++i) {
+				if (slotOf[i] == (size_t)-1) { violations[i] = inds[i].violation + fitness(inds[i], {}, false, results[i]); continue; }
+				violations[i] = inds[i].violation + fitnessFromCriteria(inds[i], &crit[slotOf[i] * L], results[i]);
+			}
+			evalCounter += B;
+			return;
+		}
 		if (!run.empty()) {
 			sim->moveMeasuringPointsTo(inds[run[0]].leads);  // lead count / bookkeeping; positions travel in `leads`
 			if (fitOnDevice) sim->evaluateBatch(k.data(), nb, interp == endo_epi ? 0 : midLayer(), fitOffsets(), 0.5, 1e-3, 100, leads.data(), run.size(), ecg, nullptr);
@@ -734,6 +751,45 @@ private:
 		approximationGate(ind);
 	}
 
+	/// the device-side comparison (ekg_criteria_kernel) covers the settings where every criterion is one lead compared with
+	/// its target: no peak-position criterion, as many equally long targets as leads
+	bool criteriaOnDevice() const {
+		const size_t L = sim->numMeasurements();
+		if (getenv("EKGSIM_B200_HOST_CRITERIA")) return false;
+		if (settings.criteriaMode != EvalSettings::every_lead || settings.peakPositionIsCriterion) return false;
+		if (targets.size() < L || L == 0) return false;
+		for (size_t m = 1; m < L; ++m) if (targets[m].size() != targets[0].size()) return false;
+		return (int)settings.comparisonMode >= 1 && (int)settings.comparisonMode <= 4 && !targets[0].empty();
+	}
+
+	/// calculateFitness for an individual whose per-lead comparison values were computed on the device
+	double fitnessFromCriteria(const Individual& ind, const double* crit, Value& result) const {
+		if (result.empty()) result.resize(deducedNumOfCriteria);
+		if (result.size() != deducedNumOfCriteria) throw std::runtime_error("error in result.size() - doesn't match deducedNumOfCriteria");
+		result[0] = 0;
+		const size_t nCrit = std::min(sim->numMeasurements(), targets.size());
+		if (settings.fastApproxIsCriterion) result[nCrit] = ind.approxCriteria;
+		for (size_t i = 0; i < nCrit; ++i) {
+			result[i] = crit[i];
+			if (result[i] < 0 || !std::isfinite(result[i]) || !std::isnormal(result[i])) {
+				std::cerr << " warning, ConvolutionResult returned wierd value: " << crit[i] << ", causing fitness to be " << result[i]
+				          << "; making correction - setting fitness to a large number\n";
+				result[i] = 2e10;
+			}
+		}
+		if (settings.endoEpiMinCriterionDelay >= 0) result[result.size() - 1] = endoEpiCriterion(ind);
+		return 0.0;
+	}
+
+	double endoEpiCriterion(const Individual& ind) const {
+		double sd = 0.0;
+		for (double t = 1.0; t < 700.0; t += 1.0) {
+			const double dd = ind.layerAps.front()(t + settings.endoEpiMinCriterionDelay) - ind.layerAps.back()(t);
+			sd += dd * dd;
+		}
+		return sd;
+	}
+
 	double compare(const std::vector<double>& simResult, size_t target) const {
 		switch (settings.comparisonMode) {
 		case EvalSettings::cmp_correlation: return 1.0 - pearson(simResult, targets[target], 0).value;
@@ -768,14 +824,7 @@ private:
 				result[at] = 2e10;
 			}
 		}
-		if (settings.endoEpiMinCriterionDelay >= 0) {
-			double sd = 0.0;
-			for (double t = 1.0; t < 700.0; t += 1.0) {
-				const double dd = ind.layerAps.front()(t + settings.endoEpiMinCriterionDelay) - ind.layerAps.back()(t);
-				sd += dd * dd;
-			}
-			result[result.size() - 1] = sd;
-		}
+		if (settings.endoEpiMinCriterionDelay >= 0) result[result.size() - 1] = endoEpiCriterion(ind);
 		return 0.0;
 	}
 

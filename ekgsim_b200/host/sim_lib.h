@@ -398,6 +398,23 @@ public:
 		lastRunSeconds_ = ekg::wall_seconds() - t0;
 	}
 
+	/// fit + simulation + curve comparison in one device pass (new): only B x leads criteria come back.
+	/// targets [leads][nTarget] (normalised / resampled by the caller), comparison = the ini's ECG comparison mode
+	void evaluateBatchCriteria(const double* borderK, size_t nBorder, size_t mid, const double* d9, double step, double eps, int iterations,
+	                           const double* leadsZyx, size_t B, const double* targets, size_t nTarget, const double* targetOffsets,
+	                           int comparison, std::vector<double>& criteria) {
+		ensureModel();
+		if (!haveActivation_) throw std::runtime_error("excitation sequence missing: call simExcitationSequence() first");
+		if (nbhd_ < 0) throw std::runtime_error("applySettings() must be called before run()");
+		startTime_ = settings.simulationStart;
+		criteria.assign(B * mps_.size(), 0.0);
+		const double t0 = ekg::wall_seconds();
+		check(ekg_evaluate(model_, borderK, (int64_t)nBorder, (int64_t)mid, d9, step, eps, iterations, leadsZyx, (int64_t)B,
+		                   (int64_t)mps_.size(), nbhd_, (double)settings.simulationStart, timeStep_, (double)settings.simulationLength, mode_,
+		                   targets, (int64_t)nTarget, targetOffsets, comparison, criteria.data(), nullptr, nullptr));
+		lastRunSeconds_ = ekg::wall_seconds() - t0;
+	}
+
 	/// "string model": endo delayed minus epi, layer APs only (Simulation::runApproximation)
 	void runApproximation(double delay, std::vector<double>& result) {
 		result.assign((size_t)(settings.simulationLength / timeStep_), 0.0);

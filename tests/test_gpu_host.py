@@ -238,7 +238,16 @@ def test_batch_device_fit_equals_host_fit(testrun, monkeypatch):
     ev.eval_batch(g["params"][:16])
     t0 = time.time(); crit_host, viol_host = ev.eval_batch(g["params"]); t_host = time.time() - t0
     ev.close()
-    print("evalBatch(256): device fit %.1f ms, host fit %.1f ms" % (t_dev * 1e3, t_host * 1e3))
+    # device fit, but the curve comparison on the host from downloaded ECGs
+    monkeypatch.delenv("EKGSIM_B200_FIT")
+    monkeypatch.setenv("EKGSIM_B200_HOST_CRITERIA", "1")
+    ev = hostlib.Evaluator(testrun, with_device=True)
+    ev.eval_batch(g["params"])
+    t0 = time.time(); crit_hc, _ = ev.eval_batch(g["params"]); t_hc = time.time() - t0
+    ev.close()
+    assert np.abs(crit_dev - crit_hc).max() < 1e-12
+    print("evalBatch(256): device fit + device criteria %.2f ms, device fit + host criteria %.2f ms, host fit %.1f ms"
+          % (t_dev * 1e3, t_hc * 1e3, t_host * 1e3))
     assert np.abs(crit_dev - crit_host).max() < 1e-7
     assert (viol_dev == viol_host).all()
     assert np.abs(one - crit_dev[5]).max() < 1e-6
