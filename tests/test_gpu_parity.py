@@ -55,6 +55,35 @@ def test_activation_small_bit_exact(built, seed):
     m.close()
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_activation_random_conduction_and_many_starts(built, seed):
+    """Asymmetric random conduction matrices (T[exciting][excited] != T[excited][exciting], three orders of
+    magnitude apart), several start voxels, odd grid extents that do not fill whole 4^3 bricks, both automaton
+    kernels: the least fixed point of the relaxation must come out with the reference's bits whatever the visiting order."""
+    rng = np.random.default_rng(seed)
+    shape = (int(rng.integers(9, 30)), int(rng.integers(9, 34)), int(rng.integers(9, 31)))
+    nl = int(rng.integers(2, 9))
+    layers, transfer, _ = synth.small_heart(seed=seed, shape=shape, n_layers=nl)
+    n = transfer.shape[0]
+    transfer[1:, 1:] = 10.0 ** rng.uniform(-2, 1, size=(n - 1, n - 1))
+    occ = np.argwhere((layers & 0x0FFF) > 0)
+    for idx in rng.choice(len(occ), size=int(rng.integers(1, 6)), replace=False):
+        layers[tuple(occ[idx])] |= 0x1000
+    ref = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    delay, _ = m.activation()
+    assert delay.tobytes() == ref.tobytes()
+    m.close()
+    os.environ["EKGSIM_B200_AUTOMATON"] = "sweep"
+    try:
+        m = built.Model(layers, transfer)
+        delay, _ = m.activation()
+        assert delay.tobytes() == ref.tobytes()
+        m.close()
+    finally:
+        del os.environ["EKGSIM_B200_AUTOMATON"]
+
+
 def test_activation_2d_and_unreachable(built):
     layers, transfer, _ = synth.small_heart(seed=4, shape=(1, 40, 36), n_layers=5, hole=False)
     layers[0, :, 18] = 0  # cut the ring in two places -> still connected around; then isolate an island
