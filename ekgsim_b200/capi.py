@@ -38,6 +38,12 @@ SYMBOLS = {
     "ekg_model_activation_brick_visits": (_i64, [_p]),
     "ekg_model_set_activation": (_int, [_p, _p]),
     "ekg_model_get_activation": (_int, [_p, _p]),
+    "ekg_model_activation_begin": (_int, [_p]),
+    "ekg_model_activation_relax": (_int, [_p, C.POINTER(_i64)]),
+    "ekg_model_plane_elems": (_i64, [_p]),
+    "ekg_model_activation_export": (_int, [_p, _i64, _i64, _p, _p]),
+    "ekg_model_activation_merge": (_int, [_p, _i64, _i64, _p, C.POINTER(_i64), _p]),
+    "ekg_model_activation_end": (_int, [_p, _p]),
     "ekg_model_ap_classes": (_int, [_p, _p, C.POINTER(_i64)]),
     "ekg_simulate": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p]),
     "ekg_simulate_criteria": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _i64, _p, _int, _p, _p]),
@@ -143,6 +149,32 @@ class Model:
     @property
     def activation_brick_visits(self):
         return int(lib().ekg_model_activation_brick_visits(self._h))
+
+    # -- z-slab sharded automaton (driver: ekgsim_b200/dist.py::sharded_activation) --
+    @property
+    def plane_elems(self):
+        return int(lib().ekg_model_plane_elems(self._h))
+
+    def activation_begin(self):
+        _check(lib().ekg_model_activation_begin(self._h))
+
+    def activation_relax(self):
+        v = C.c_int64(0)
+        _check(lib().ekg_model_activation_relax(self._h, C.byref(v)))
+        return int(v.value)
+
+    def activation_export(self, z_begin, z_end, d_planes, stream=0):
+        _check(lib().ekg_model_activation_export(self._h, int(z_begin), int(z_end), C.c_void_p(d_planes), C.c_void_p(stream)))
+
+    def activation_merge(self, z_begin, z_end, d_planes, stream=0):
+        n = C.c_int64(0)
+        _check(lib().ekg_model_activation_merge(self._h, int(z_begin), int(z_end), C.c_void_p(d_planes), C.byref(n), C.c_void_p(stream)))
+        return int(n.value)
+
+    def activation_end(self):
+        out = np.empty(self.shape, dtype=np.float64)
+        _check(lib().ekg_model_activation_end(self._h, _ptr(out)))
+        return out
 
     def set_activation(self, delay):
         delay = np.ascontiguousarray(delay, dtype=np.float64)

@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 		int nb = -1;
 		if (lane < 26 && ((bits >> lane) & 1u)) {
 			nb = __ldg(a.nbr + (size_t)b * 26 + lane);
+			if (nb >= 0 && a.own && !a.own[nb]) nb = -1;               // sharded run: another rank relaxes that brick
 			if (nb >= 0 && atomicExch(a.flag + nb, 1) != 0) nb = -1;   // already queued
 		}
 		const unsigned pushers = __ballot_sync(kFull, nb >= 0);
@@ -311,16 +312,19 @@ int run_automaton(ekg_model* m, int64_t* sweeps_out) {
 	return EKG_OK;
 }
 
+static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* visits_out);
+
+static int64_t ring_capacity(int64_t n) {
+	int64_t cap = 1;
+	while (cap < std::max<int64_t>(n, 2)) cap <<= 1;
+	return cap;
+}
+
 static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
-	int64_t cap = 1;
-	while (cap < std::max<int64_t>(n, 2)) cap <<= 1;
+	const int64_t cap = ring_capacity(n);
 	// state = flag[n] | first_visit[n] | ring[cap] | counters[8]   (allocated as 5n + 8 ints; cap <= 2n)
-	int* flag = m->d_brick_state;
-	int* first = flag + n;
-	int* ring = first + n;
-	int* counters = ring + cap;
 	std::vector<int> h((size_t)(2 * n + cap + 8), 0);
 	std::fill(h.begin() + 2 * n, h.begin() + 2 * n + cap, -1);
 	int n0 = 0;
@@ -329,10 +333,22 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	h[(size_t)(2 * n + cap + 2)] = n0;   // pending
 	EKG_CUDA(cudaMemcpyAsync(m->d_brick_state, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
 	EKG_CUDA(cudaStreamSynchronize(st));  // pageable source
+	return launch_bricks(m, nullptr, rounds_out);
+}
+
+// the frontier kernel over whatever the ring holds; d_own restricts the pushes (sharded run)
+static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out) {
+	cudaStream_t st = m->stream;
+	const int64_t n = m->n_bricks;
+	const int64_t cap = ring_capacity(n);
+	int* flag = m->d_brick_state;
+	int* first = flag + n;
+	int* ring = first + n;
+	int* counters = ring + cap;
 
 	BrickArgs a{};
 	a.layer = m->d_layer_pad; a.time = m->d_time_pad; a.wtab = m->d_wtab;
-	a.origin = m->d_brick_origin; a.nbr = m->d_brick_nbr;
+	a.origin = m->d_brick_origin; a.nbr = m->d_brick_nbr; a.own = d_own;
 	a.flag = flag; a.first_visit = first; a.queue = ring; a.counters = counters; a.qmask = (uint32_t)(cap - 1);
 	a.n_live = (int32_t)n; a.nl1 = m->n_layers + 1; a.pY = (int32_t)m->pY; a.pX = (int32_t)m->pX;
 	NbrTable nb;
@@ -362,6 +378,153 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	m->last_brick_visits = hc[4];
 	if (getenv("EKGSIM_B200_DEBUG")) fprintf(stderr, "automaton bricks: visits %d inner sweeps %d pushes %d\n", hc[4], hc[5], hc[1]);
 	if (hc[2] != 0) return fail(EKG_E_STATE, "activation automaton did not converge");
+	return EKG_OK;
+}
+
+// ---- z-slab sharded automaton ("automaton on a sharded model") -----------------------------------
+// Every rank keeps the whole padded grid but relaxes only the bricks that intersect its z-slab.  Between
+// relaxations the ranks exchange the planes next to their slab faces (the 26-neighbourhood reaches one plane
+// across); merging is an elementwise minimum, which can only move values towards the least fixed point of
+// d(v) = min_u fl(d(u) + w(u,v)) -- the same bits the single-GPU run and the reference's Dijkstra produce --
+// and the loop ends when a whole exchange improved nothing anywhere.  Values a rank holds outside its slab are
+// upper bounds only (its bricks may straddle the slab face); they are overwritten by the final gather.
+
+// bricks of the slab that can see cell (z, y, x) (voxel coordinates) get marked for the next relaxation
+__global__ void shard_merge_kernel(double* __restrict__ time, const double* __restrict__ src, int64_t n_cells, int64_t first_cell,
+                                   int pY, int pX, int Z, int Y, int X, const int32_t* __restrict__ bindex, int bZ, int bY, int bX,
+                                   const uint8_t* __restrict__ own, int* __restrict__ mark, unsigned long long* __restrict__ improved) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_cells) return;
+	const int64_t p = first_cell + i;
+	const double v = src[i];
+	if (!(v < time[p])) return;
+	time[p] = v;
+	atomicAdd(improved, 1ull);
+	const int z = (int)(p / ((int64_t)pY * pX)) - 1, y = (int)((p / pX) % pY) - 1, x = (int)(p % pX) - 1;
+	for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+		const int cz = z + dz, cy = y + dy, cx = x + dx;
+		if (cz < 0 || cz >= Z || cy < 0 || cy >= Y || cx < 0 || cx >= X) continue;
+		const int32_t b = bindex[((int64_t)(cz / kBrick) * bY + cy / kBrick) * bX + cx / kBrick];
+		if (b >= 0 && own[b]) mark[b] = 1;
+	}
+}
+
+// marked bricks -> ring (as "first visits": their reached voxels count as changed, whoever changed them)
+__global__ void shard_enqueue_kernel(int* __restrict__ mark, int n_live, int* __restrict__ flag, int* __restrict__ first,
+                                     int* __restrict__ ring, int* __restrict__ counters, uint32_t qmask) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_live || !mark[b]) return;
+	mark[b] = 0;
+	flag[b] = 1;
+	first[b] = 1;
+	const unsigned pos = atomicAdd((unsigned*)counters + 1, 1u);
+	ring[pos & qmask] = b;
+	atomicAdd(counters + 2, 1);
+}
+
+static int shard_check(ekg_model* m) {
+	if (m->h_starts.empty()) return fail(EKG_E_NO_START, "Could not find starting point for excitation sequence");
+	if (m->n_layers >= m->t_cols || m->n_layers >= m->t_rows) return fail(EKG_E_TRANSFER, "transfer (conduction) matrix does not define every layer");
+	return EKG_OK;
+}
+
+int shard_begin(ekg_model* m) {
+	int rc = shard_check(m);
+	if (rc) return rc;
+	cudaStream_t st = m->stream;
+	const int64_t n = m->n_bricks;
+	const size_t nn = (size_t)std::max<int64_t>(n, 1);
+	if (!m->d_brick_index) {
+		EKG_CUDA(cudaMalloc(&m->d_brick_index, std::max<size_t>(m->h_brick_index.size(), 1) * sizeof(int32_t)));
+		EKG_CUDA(cudaMalloc(&m->d_brick_own, nn));
+		EKG_CUDA(cudaMalloc(&m->d_brick_mark, nn * sizeof(int)));
+		EKG_CUDA(cudaMalloc(&m->d_improved, sizeof(unsigned long long)));
+		EKG_CUDA(cudaMemcpyAsync(m->d_brick_index, m->h_brick_index.data(), m->h_brick_index.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	}
+	// bricks that intersect the slab [slab_z0, slab_z1); brick bz covers the voxel planes [4 bz, 4 bz + 4)
+	std::vector<uint8_t> own(nn, 0);
+	std::vector<int> mark(nn, 0);
+	for (int64_t bz = 0; bz < m->bZ; ++bz) {
+		const bool in = bz * kBrick < m->slab_z1 && (bz + 1) * kBrick > m->slab_z0;
+		if (!in) continue;
+		for (int64_t i = bz * m->bY * m->bX; i < (bz + 1) * m->bY * m->bX; ++i) if (m->h_brick_index[(size_t)i] >= 0) own[(size_t)m->h_brick_index[(size_t)i]] = 1;
+	}
+	for (int32_t b : m->h_start_bricks) if (own[(size_t)b]) mark[(size_t)b] = 1;
+	EKG_CUDA(cudaMemcpyAsync(m->d_brick_own, own.data(), nn, cudaMemcpyHostToDevice, st));
+	EKG_CUDA(cudaMemcpyAsync(m->d_brick_mark, mark.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
+	const int64_t npad = m->pZ * m->pY * m->pX;
+	init_time_kernel<<<m->sm_count * 4, 256, 0, st>>>(m->d_time_pad, npad);
+	EKG_CUDA(cudaGetLastError());
+	// every rank sets every start voxel (simulator.cpp:263); only the owner's bricks relax from it
+	std::vector<uint32_t> h_starts(m->h_starts.size());
+	for (size_t i = 0; i < h_starts.size(); ++i) {
+		const int64_t r = m->h_starts[i];
+		const int64_t z = r / (m->Y * m->X), y = (r / m->X) % m->Y, x = r % m->X;
+		h_starts[i] = (uint32_t)(((z + 1) * m->pY + (y + 1)) * m->pX + (x + 1));
+	}
+	uint32_t* d_starts = nullptr;
+	EKG_CUDA(cudaMalloc(&d_starts, h_starts.size() * sizeof(uint32_t)));
+	EKG_CUDA(cudaMemcpyAsync(d_starts, h_starts.data(), h_starts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	set_start_kernel<<<(int)((h_starts.size() + 127) / 128), 128, 0, st>>>(m->d_time_pad, d_starts, (int)h_starts.size());
+	EKG_CUDA(cudaGetLastError());
+	EKG_CUDA(cudaStreamSynchronize(st));  // pageable sources
+	EKG_CUDA(cudaFree(d_starts));
+	m->have_activation = false;
+	m->shard_active = true;
+	return EKG_OK;
+}
+
+int shard_relax(ekg_model* m, int64_t* visits_out) {
+	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
+	cudaStream_t st = m->stream;
+	const int64_t n = m->n_bricks;
+	if (n == 0) { if (visits_out) *visits_out = 0; return EKG_OK; }
+	const int64_t cap = ring_capacity(n);
+	int* flag = m->d_brick_state;
+	int* ring = flag + 2 * n;
+	int* counters = ring + cap;
+	EKG_CUDA(cudaMemsetAsync(flag, 0, (size_t)(2 * n) * sizeof(int), st));
+	EKG_CUDA(cudaMemsetAsync(ring, 0xff, (size_t)cap * sizeof(int), st));   // -1 = empty slot
+	EKG_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(int), st));
+	shard_enqueue_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_brick_mark, (int)n, flag, flag + n, ring, counters, (uint32_t)(cap - 1));
+	EKG_CUDA(cudaGetLastError());
+	return launch_bricks(m, m->d_brick_own, visits_out);
+}
+
+static int plane_range(ekg_model* m, int64_t z_begin, int64_t z_end, int64_t* first_cell, int64_t* n_cells) {
+	if (z_begin < -1 || z_end > m->pZ - 1 || z_begin > z_end) return fail(EKG_E_INVALID, "bad plane range");
+	*first_cell = (z_begin + 1) * m->pY * m->pX;
+	*n_cells = (z_end - z_begin) * m->pY * m->pX;
+	return EKG_OK;
+}
+
+int shard_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, cudaStream_t st) {
+	int64_t first, n;
+	int rc = plane_range(m, z_begin, z_end, &first, &n);
+	if (rc) return rc;
+	if (n) {
+		EKG_CUDA(cudaMemcpyAsync(d_planes, m->d_time_pad + first, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+		EKG_CUDA(cudaStreamSynchronize(st));   // the caller hands the buffer to a collective on a stream of its own
+	}
+	return EKG_OK;
+}
+
+int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, cudaStream_t st) {
+	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
+	int64_t first, n;
+	int rc = plane_range(m, z_begin, z_end, &first, &n);
+	if (rc) return rc;
+	unsigned long long h = 0;
+	if (n) {
+		EKG_CUDA(cudaMemsetAsync(m->d_improved, 0, sizeof(unsigned long long), st));
+		shard_merge_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_time_pad, d_planes, n, first, (int)m->pY, (int)m->pX, (int)m->Z, (int)m->Y,
+		                                                         (int)m->X, m->d_brick_index, (int)m->bZ, (int)m->bY, (int)m->bX, m->d_brick_own,
+		                                                         m->d_brick_mark, m->d_improved);
+		EKG_CUDA(cudaGetLastError());
+		EKG_CUDA(cudaMemcpyAsync(&h, m->d_improved, sizeof h, cudaMemcpyDeviceToHost, st));
+		EKG_CUDA(cudaStreamSynchronize(st));
+	}
+	if (improved_out) *improved_out = (int64_t)h;
 	return EKG_OK;
 }
 

@@ -52,7 +52,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_k1min};
+	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -266,6 +266,8 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 			if (std::find(m->h_start_bricks.begin(), m->h_start_bricks.end(), bi) == m->h_start_bricks.end()) m->h_start_bricks.push_back(bi);
 		}
 		m->n_bricks = nb;
+		m->h_brick_index = index; m->h_brick_origin = origin;
+		m->bZ = bZ; m->bY = bY; m->bX = bX;
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_origin, (size_t)std::max<int64_t>(nb, 1) * 4));
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_nbr, nbr.size() * 4));
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, ((size_t)nb * 5 + 8) * sizeof(int)));
@@ -315,6 +317,44 @@ int ekg_model_activation(ekg_model* m, double* delay_out, int64_t* sweeps_out) {
 	cudaEventDestroy(e1);
 	if (rc) return rc;
 	rc = publish_activation(m, true);
+	if (rc) return rc;
+	if (delay_out) memcpy(delay_out, m->h_delay.data(), m->h_delay.size() * 8);
+	return EKG_OK;
+}
+
+// ---- z-slab sharded automaton ---------------------------------------------------------------------------------
+int ekg_model_activation_begin(ekg_model* m) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_begin(m);
+}
+
+int ekg_model_activation_relax(ekg_model* m, int64_t* brick_visits_out) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_relax(m, brick_visits_out);
+}
+
+int64_t ekg_model_plane_elems(const ekg_model* m) { return m ? m->pY * m->pX : 0; }
+
+int ekg_model_activation_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, void* stream) {
+	if (!m || !d_planes) return fail(EKG_E_INVALID, "NULL argument");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_export(m, z_begin, z_end, d_planes, (cudaStream_t)stream);
+}
+
+int ekg_model_activation_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, void* stream) {
+	if (!m || !d_planes) return fail(EKG_E_INVALID, "NULL argument");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_merge(m, z_begin, z_end, d_planes, improved_out, (cudaStream_t)stream);
+}
+
+int ekg_model_activation_end(ekg_model* m, double* delay_out) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
+	EKG_CUDA(cudaSetDevice(m->device));
+	m->shard_active = false;
+	int rc = publish_activation(m, true);
 	if (rc) return rc;
 	if (delay_out) memcpy(delay_out, m->h_delay.data(), m->h_delay.size() * 8);
 	return EKG_OK;

@@ -111,6 +111,7 @@ struct BrickArgs {
 	const int32_t* nbr;      // [n_live][26] live index of the neighbouring brick in cube direction k, -1 = none
 	int* flag;               // [n_live] 1 while the brick sits in the ring
 	int* first_visit;        // [n_live] 1 for the bricks of the start voxels until their first visit
+	const uint8_t* own;      // [n_live] sharded run: 1 for the bricks this rank relaxes (NULL = all)
 	int* queue;              // ring of brick ids, -1 = empty slot, qmask + 1 slots
 	int* counters;           // [0] head, [1] tail, [2] pending (queued or in work), [4] visits, [5] inner sweeps
 	uint32_t qmask;
@@ -156,6 +157,15 @@ struct ekg_model {
 	int32_t* d_brick_nbr = nullptr;
 	int* d_brick_state = nullptr;        // flag[2][n] | queue[3][n] | counters[8]
 	std::vector<int32_t> h_start_bricks;
+	// z-slab sharded automaton (ekg_model_activation_begin / _relax / _export / _merge / _end)
+	std::vector<int32_t> h_brick_index;  // dense brick grid [bZ][bY][bX] -> live brick id, -1 = no occupied voxel
+	std::vector<uint32_t> h_brick_origin;
+	int64_t bZ = 0, bY = 0, bX = 0;
+	int32_t* d_brick_index = nullptr;
+	uint8_t* d_brick_own = nullptr;
+	int* d_brick_mark = nullptr;         // bricks to queue at the next relax
+	unsigned long long* d_improved = nullptr;
+	bool shard_active = false;
 	int64_t last_brick_visits = 0;
 
 	// ECG voxel list (layer-sorted, restricted to the slab)
@@ -199,6 +209,10 @@ struct ekg_model {
 namespace ekg {
 // automaton.cu
 int run_automaton(ekg_model* m, int64_t* sweeps_out);
+int shard_begin(ekg_model* m);
+int shard_relax(ekg_model* m, int64_t* visits_out);
+int shard_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, cudaStream_t st);
+int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, cudaStream_t st);
 // ecg.cu
 // k1_min: smallest depolarisation rate k1 over all (vector, layer) if the caller knows it on the host
 // (<= 0: unknown -- the SEPARABLE path then reads it back from the device, one stream synchronisation)

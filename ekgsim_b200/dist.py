@@ -97,3 +97,104 @@ def max_over_ranks(x: float, device=None) -> float:
     t = torch.tensor([x], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class ModelPlanes:
+    """Adapter between a device-resident `Model` (capi.py) and torch tensors: the sharded automaton's plane
+    exchange needs tensors for the collectives, the model only speaks raw device pointers."""
+
+    def __init__(self, model, device):
+        import torch
+        self.model, self.device, self.torch = model, device, torch
+        self.plane_elems = model.plane_elems
+
+    def begin(self):
+        self.model.activation_begin()
+
+    def relax(self):
+        return self.model.activation_relax()
+
+    def export(self, z_begin, z_end):
+        t = self.torch.empty((max(z_end - z_begin, 0), self.plane_elems), dtype=self.torch.float64, device=self.device)
+        if t.numel():
+            self.model.activation_export(z_begin, z_end, t.data_ptr(), self.torch.cuda.current_stream(self.device).cuda_stream)
+        return t
+
+    def merge(self, z_begin, planes):
+        if planes.numel() == 0:
+            return 0
+        self.torch.cuda.current_stream(self.device).synchronize()   # the collective that filled `planes` is done
+        return self.model.activation_merge(z_begin, z_begin + planes.shape[0], planes.data_ptr(),
+                                           self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def end(self):
+        return self.model.activation_end()
+
+
+def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000):
+    """The activation automaton of a model sharded into z-slabs.
+
+    `planes` offers begin / relax / export(z0, z1) -> tensor[z1-z0, plane_elems] / merge(z0, tensor) -> improved cells /
+    end (ModelPlanes for the CUDA model); `slabs[r] = (z_begin, z_end)` is rank r's slab, already set on the model.
+    Per round every rank relaxes its slab to the fixed point of its current halo, sends its first and last own plane
+    to the rank below / above (one point-to-point message each way over NCCL / NVLink), merges what it receives
+    (elementwise minimum) and the ranks agree through one all-reduce whether anything improved anywhere.  Min-merging
+    never overshoots the least fixed point, so the result has the bits of the single-GPU run.  At the end every rank
+    broadcasts its slab so that all ranks hold the whole map, like after `ekg_model_activation`.
+    Returns (delay[Z, Y, X] as numpy, rounds, brick visits of this rank)."""
+    import torch
+    import torch.distributed as dist
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    assert len(slabs) == world
+    live = [r for r in range(world) if slabs[r][1] > slabs[r][0]]     # ranks with an empty slab only take part in the collectives
+    below = max([r for r in live if r < rank], default=None) if rank in live else None
+    above = min([r for r in live if r > rank], default=None) if rank in live else None
+    z0, z1 = slabs[rank]
+    planes.begin()
+    visits, rounds = 0, 0
+    while True:
+        rounds += 1
+        if rank in live:
+            visits += planes.relax()
+        improved = 0
+        if world > 1:
+            ops, recv_below, recv_above = [], None, None
+            if below is not None:
+                send_dn = planes.export(z0, z0 + 1)                     # my first plane is the halo of the rank below
+                recv_below = torch.empty_like(send_dn)
+                ops += [dist.P2POp(dist.isend, send_dn, below), dist.P2POp(dist.irecv, recv_below, below)]
+            if above is not None:
+                send_up = planes.export(z1 - 1, z1)
+                recv_above = torch.empty_like(send_up)
+                ops += [dist.P2POp(dist.isend, send_up, above), dist.P2POp(dist.irecv, recv_above, above)]
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            if recv_below is not None:
+                improved += planes.merge(slabs[below][1] - 1, recv_below)   # = its last own plane
+            if recv_above is not None:
+                improved += planes.merge(slabs[above][0], recv_above)
+            flag = torch.tensor([improved], dtype=torch.int64, device=send_device(planes))
+            dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+            improved = int(flag.item())
+        if improved == 0:
+            break
+        if rounds >= max_rounds:
+            raise RuntimeError("sharded activation automaton did not converge in %d rounds" % max_rounds)
+    # every rank ends up with the whole map: rank s broadcasts its slab, the others min-merge it (what they hold
+    # outside their own slab are upper bounds)
+    if world > 1:
+        for s in live:
+            a, b = slabs[s]
+            buf = planes.export(a, b) if s == rank else torch.empty((b - a, planes.plane_elems), dtype=torch.float64, device=send_device(planes))
+            dist.broadcast(buf, src=s)
+            if s != rank:
+                planes.merge(a, buf)
+    return planes.end(), rounds, visits
+
+
+def send_device(planes):
+    return getattr(planes, "device", "cpu")

@@ -10,7 +10,7 @@
 //
 //     g++ ... -I<reference> -I<reference>/copyOfLibs -I<repo> -include ekgsim_b200/host/compat/refglue_shim.h \
 //         <reference>/main.cpp ekgsim_b200/host/compat/sim_b200.cpp <reference>/copyOfLibs/{Ini,Random,Arguments}.cpp \
-//         -lekgsim_b200                      (recipe: oracle/Makefile, target _ref/ekgSim_refmain_b200)
+//         -lekgsim_b200                      (the test harness builds it as ekgSim_refmain_b200)
 //
 // It is compiled against the reference's own headers where they lie; nothing of them is copied here.
 #include "sim.h"   // the reference's sim.h (include path), declares OutputSettings / OptimizationFunction

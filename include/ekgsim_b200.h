@@ -109,6 +109,27 @@ double ekg_model_activation_ms(const ekg_model* m);
 /* Brick visits of the last frontier automaton run (work actually done, in units of 8^3 bricks). */
 int64_t ekg_model_activation_brick_visits(const ekg_model* m);
 int  ekg_model_set_activation(ekg_model* m, const double* delay);
+
+/* The automaton on a model sharded into z-slabs over several GPUs ("automaton on a sharded model").
+ * Every rank holds the whole model and has restricted itself to its slab with ekg_model_set_slab; it relaxes only the
+ * bricks that intersect the slab.  One round = relax, then exchange the planes at the slab faces with the neighbouring
+ * ranks (NCCL / P2P, the caller's job) and merge what arrives by an elementwise minimum; the loop ends when no rank's
+ * merge improved anything.  The result has the bits of ekg_model_activation.  ekgsim_b200/dist.py::sharded_activation
+ * is the driver; planes are (z, all y, all x) slices of the zero-bordered grid, ekg_model_plane_elems() doubles each,
+ * z from -1 (border) to Z.
+ *   begin   times = +inf, start voxels = 1 (simulator.cpp:263); the start bricks inside the slab are queued
+ *   relax   frontier relaxation from the queued bricks until the slab is at its fixed point for its current halo
+ *   export  copies planes [z_begin, z_end) into a device buffer (complete on return)
+ *   merge   time = min(time, planes); bricks of the slab that can see an improved cell are queued for the next
+ *           relax; improved_out = number of improved cells
+ *   end     publishes the map like ekg_model_activation does (host copy, ECG voxel list); delay_out may be NULL */
+int     ekg_model_activation_begin(ekg_model* m);
+int     ekg_model_activation_relax(ekg_model* m, int64_t* brick_visits_out);
+int64_t ekg_model_plane_elems(const ekg_model* m);
+int     ekg_model_activation_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, void* stream);
+int     ekg_model_activation_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes,
+                                   int64_t* improved_out, void* stream);
+int     ekg_model_activation_end(ekg_model* m, double* delay_out);
 int  ekg_model_get_activation(const ekg_model* m, double* delay_out);
 
 /* (layer, delay) class table in first-seen raster order: ap_index_out[Z*Y*X] (-1 = empty);

@@ -54,3 +54,20 @@ def layer_params(n_layers, seed=0, batch=None):
                          k5[0] * (1 - f) + k5[1] * f, k6[0] * (1 - f) + k6[1] * f,
                          k7[0] * (1 - f) + k7[1] * f, k8[0] * (1 - f) + k8[1] * f]
     return out if batch else out[0]
+
+
+def serpentine(n_turns=10, height=12):
+    """A one-voxel-thick path that runs up and down in z while advancing in x (square wave): the excitation has to
+    cross any z = const cut once per turn, so a z-slab sharded automaton needs about n_turns exchange rounds.
+    Two layers alternate along the path.  Returns (layers, transfer)."""
+    Z, Y, X = height + 4, 3, 4 * n_turns + 2
+    layers = np.zeros((Z, Y, X), dtype=np.uint16)
+    lo, hi = 2, height + 1
+    for i in range(n_turns):
+        z_run = lo if i % 2 == 0 else hi
+        layers[z_run, 1, 4 * i:4 * i + 4] = 1 + i % 2
+        layers[lo:hi + 1, 1, 4 * i + 3] = 1 + i % 2          # the connector to the other level
+    layers[lo, 1, 0] |= START_FLAG
+    transfer = np.full((4, 4), -1.0)
+    transfer[1:3, 1:3] = [[0.166667, 1.0], [2.0, 0.25]]
+    return layers, transfer

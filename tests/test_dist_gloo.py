@@ -84,3 +84,92 @@ def test_world2_gloo_sharding_and_collectives(built):
     assert gathered_err == 0.0       # gather is a pure permutation
     assert slab_err < 1e-12          # two slabs add up to the whole model
     assert tmax == 2.0
+
+
+class NumpySlabPlanes:
+    """CPU stand-in for ekgsim_b200.dist.ModelPlanes: the same begin / relax / export / merge / end contract on a
+    zero-bordered numpy grid, relaxing only the voxels of its z-slab (vectorised label-correcting sweeps with the
+    reference's edge weights fl(T[exciting][excited] * sqrt(|dif|^2)) and fl(+))."""
+
+    def __init__(self, layers, transfer, z0, z1):
+        self.z0, self.z1 = z0, z1
+        self.lay = np.pad((layers & 0x0FFF).astype(np.int64), 1)
+        self.start = np.pad((layers & 0x1000) != 0, 1)
+        self.T = transfer
+        self.shape = layers.shape
+        self.plane_elems = self.lay.shape[1] * self.lay.shape[2]
+        self.device = "cpu"
+
+    def begin(self):
+        self.t = np.full(self.lay.shape, np.inf)
+        self.t[self.start] = 1.0
+
+    def relax(self):
+        Z, Y, X = self.shape
+        own = (slice(self.z0 + 1, self.z1 + 1), slice(1, Y + 1), slice(1, X + 1))
+        lv = self.lay[own]
+        sweeps = 0
+        while True:
+            best = self.t[own].copy()
+            for dz in (-1, 0, 1):
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        if not (dz or dy or dx):
+                            continue
+                        src = (slice(self.z0 + 1 + dz, self.z1 + 1 + dz), slice(1 + dy, Y + 1 + dy), slice(1 + dx, X + 1 + dx))
+                        lu = self.lay[src]
+                        w = self.T[lu, lv] * np.sqrt(float(dz * dz + dy * dy + dx * dx))
+                        cand = np.where((lu > 0) & (lv > 0), self.t[src] + w, np.inf)
+                        best = np.minimum(best, cand)
+            sweeps += 1
+            if not (best < self.t[own]).any():
+                return sweeps
+            self.t[own] = best
+
+    def export(self, z_begin, z_end):
+        return torch.from_numpy(self.t[z_begin + 1:z_end + 1].reshape(z_end - z_begin, -1).copy())
+
+    def merge(self, z_begin, planes):
+        cur = self.t[z_begin + 1:z_begin + 1 + planes.shape[0]]
+        new = planes.numpy().reshape(cur.shape)
+        improved = int((new < cur).sum())
+        np.minimum(cur, new, out=cur)
+        return improved
+
+    def end(self):
+        out = self.t[1:-1, 1:-1, 1:-1].copy()
+        out[~np.isfinite(out) | (self.lay[1:-1, 1:-1, 1:-1] == 0)] = 0.0
+        return out
+
+
+def _automaton_worker(rank, world, port, q, cuts):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    r, w, _ = ekdist.init("gloo")
+    layers, transfer, _ = synth.small_heart(seed=6, shape=(14, 13, 12), n_layers=4)
+    slabs = [(cuts[i], cuts[i + 1]) for i in range(w)]
+    planes = NumpySlabPlanes(layers, transfer, *slabs[r])
+    delay, rounds, _ = ekdist.sharded_activation(planes, slabs, r, w)
+    ref = oracle.activation(layers, transfer)
+    q.put((r, delay.tobytes() == ref.tobytes(), rounds))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cuts", [[0, 7, 14], [0, 5, 5, 14], [0, 1, 13, 14]])
+def test_sharded_automaton_driver_gloo(built, cuts):
+    """ekgsim_b200.dist.sharded_activation (plane exchange, global termination, final gather) over gloo with a numpy
+    stand-in for the per-rank relaxation: every rank must end with the oracle's bits -- also with an empty slab in the
+    middle and with one-plane slabs."""
+    world = len(cuts) - 1
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_automaton_worker, args=(r, world, port, q, cuts)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    got = sorted(q.get() for _ in range(world))
+    assert all(ok for _, ok, _ in got), got
+    assert got[0][2] >= 2 and len({rounds for _, _, rounds in got}) == 1      # every rank leaves the loop in the same round

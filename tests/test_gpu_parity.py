@@ -446,3 +446,87 @@ def test_separable_split_and_single_vector(gpu_model24, model24, model24_delay):
     assert gpu_model24.last_kernel_name == "ecg_kernel<HOISTED> + ecg_moment_kernel"
     ref = oracle.run_factored(model24["layers"], model24_delay, slow[1], leads[1], "3D4", 100.0, 1.0, 100.0)
     assert rel_err(e3[1], ref) < ECG_TOL
+
+
+def run_sharded(ranks, slabs):
+    """The exchange loop of ekgsim_b200.dist.sharded_activation with the planes handed over directly."""
+    world = len(ranks)
+    for p in ranks:
+        p.begin()
+    rounds, visits = 0, 0
+    while True:
+        rounds += 1
+        visits += sum(p.relax() for p in ranks)
+        improved = 0
+        for r in range(world - 1):
+            up = ranks[r].export(slabs[r][1] - 1, slabs[r][1])            # last plane of r -> halo of r + 1
+            dn = ranks[r + 1].export(slabs[r + 1][0], slabs[r + 1][0] + 1)  # first plane of r + 1 -> halo of r
+            improved += ranks[r + 1].merge(slabs[r][1] - 1, up)
+            improved += ranks[r].merge(slabs[r + 1][0], dn)
+        if improved == 0:
+            break
+        assert rounds < 500
+    for s in range(world):
+        buf = ranks[s].export(*slabs[s])
+        for r in range(world):
+            if r != s:
+                ranks[r].merge(slabs[s][0], buf)
+    return rounds, visits, [p.end() for p in ranks]
+
+
+def test_sharded_automaton_many_crossings(built):
+    """A serpentine path crosses the slab faces once per turn: the wave has to be handed back and forth ~10 times, through
+    faces that cut bricks in the middle as well as faces on brick boundaries."""
+    import torch
+    from ekgsim_b200 import dist as ekdist
+    layers, transfer = synth.serpentine(n_turns=10, height=12)
+    ref = oracle.activation(layers, transfer)
+    assert (ref[(layers & 0x0FFF) > 0] > 0).all()
+    for slabs in ([(0, 8), (8, 16)], [(0, 6), (6, 7), (7, 16)], [(0, 4), (4, 12), (12, 16)]):
+        ranks = []
+        for z0, z1 in slabs:
+            m = built.Model(layers, transfer, device=0)
+            m.set_slab(z0, z1)
+            ranks.append(ekdist.ModelPlanes(m, torch.device("cuda", 0)))
+        rounds, visits, delays = run_sharded(ranks, slabs)
+        for d in delays:
+            assert d.tobytes() == ref.tobytes(), slabs
+        assert rounds >= 10, (slabs, rounds)
+        print("serpentine, slabs %s: %d rounds, %d brick visits" % (slabs, rounds, visits))
+        for p in ranks:
+            p.model.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_automaton_entry_points(built, model24, model24_delay, world):
+    """ekg_model_activation_begin / _relax / _export / _merge / _end: `world` handles on ONE device play the ranks of a
+    z-slab sharded run (planes handed over directly instead of through NCCL; the collective driver itself is covered
+    by the gloo test and tools/bench_heart4x.py --sharded-automaton).  Every handle must end with the reference's bits."""
+    import torch
+    from ekgsim_b200 import dist as ekdist
+    occ = ((model24["layers"] & 0x0FFF) > 0).sum(axis=(1, 2))
+    slabs = ekdist.slab_ranges(occ, world)
+    # the start voxel (z = 62) lies in one slab only; the other ranks have nothing to do until a halo arrives
+    slabs = [(0, 41), (41, 124)] if world == 2 else [(0, 30), (30, 61), (61, 124)]
+    dev = torch.device("cuda", 0)
+    ranks = []
+    for z0, z1 in slabs:
+        m = built.Model(model24["layers"], model24["transfer"], device=0)
+        m.set_slab(z0, z1)
+        ranks.append(ekdist.ModelPlanes(m, dev))
+    rounds, visits, delays = run_sharded(ranks, slabs)
+    assert rounds >= 2
+    for delay in delays:
+        assert delay.tobytes() == model24_delay.tobytes()
+    print("sharded automaton, %d slabs on model_24: %d rounds, %d brick visits in total" % (world, rounds, visits))
+    # the handles are usable afterwards like after ekg_model_activation: slab ECGs add up
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    parts = sum(p.model.simulate(g["layer_k"][:2], g["leads_zyx"][:2], "3D4", 100.0, 1.0, 50.0, mode=3) for p in ranks)
+    whole = ranks[0].model
+    whole.set_slab(0, 124)
+    ref = whole.simulate(g["layer_k"][:2], g["leads_zyx"][:2], "3D4", 100.0, 1.0, 50.0, mode=3)
+    assert rel_err(parts, ref) < 2e-6
+    with pytest.raises(built.EkgError):
+        whole.activation_relax()                                           # not between begin and end
+    for p in ranks:
+        p.model.close()

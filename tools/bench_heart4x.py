@@ -44,6 +44,8 @@ def main():
     ap.add_argument("--factor", type=int, default=4)
     ap.add_argument("--mode", default="direct")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--sharded-automaton", action="store_true",
+                    help="also run the automaton sharded over the z-slabs (plane exchange over NCCL) and compare with the replicated run")
     a = ap.parse_args()
     rank, world, local = ekdist.init()
     dev = torch.device("cuda", local)
@@ -58,6 +60,22 @@ def main():
     occ_z = ((layers & 0x0FFF) > 0).sum(axis=(1, 2))
     z0, z1 = ekdist.slab_ranges(occ_z, world)[rank]
     model.set_slab(z0, z1)
+    sharded = None
+    if a.sharded_automaton:
+        slabs = ekdist.slab_ranges(occ_z, world)
+        planes = ekdist.ModelPlanes(model, dev)
+        for _ in range(2):
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            t0 = time.perf_counter()
+            d2, rounds, visits = ekdist.sharded_activation(planes, slabs, rank, world)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        same = bool(d2.tobytes() == delay.tobytes())
+        sharded = {"ms_total_incl_final_gather_and_publish": ekdist.max_over_ranks(dt * 1e3, dev), "rounds": rounds, "brick_visits_rank0": visits,
+                   "bit_identical_to_replicated_run": same}
+        assert same, "sharded automaton differs from the replicated run"
     g = np.load(os.path.join(ROOT, "tests", "golden", "golden_glue256.npz"))
     k = np.ascontiguousarray(g["layer_k"][:1])
     lead_b = np.ascontiguousarray(leads[None])
@@ -87,7 +105,7 @@ def main():
     ecg = d_e.cpu().numpy()[0]
     out = {"workload": "configs[3]: %dx heart, %d occupied voxels, z-slab sharded over %d GPU(s)" % (a.factor, n_occ, world),
            "n_gpus": world, "ms_per_sim": ms, "voxel_timesteps_per_s": n_occ * T / (ms * 1e-3), "mode": a.mode,
-           "automaton_ms": auto_ms, "automaton_sweeps": sweeps, "model_create_s": t_create,
+           "automaton_ms": auto_ms, "automaton_sweeps": sweeps, "sharded_automaton": sharded, "model_create_s": t_create,
            "slab_voxels_rank0": model.num_voxels, "ecg_peak": np.abs(ecg).max(axis=1).tolist()}
     if a.check and rank == 0:
         from oracle import oracle
