@@ -12,6 +12,8 @@ The path shards in two ways:
   lead-field coefficient of a voxel only needs the *occupancy* of its neighbours, which every rank
   knows from the full layer map, so no halo of potentials is exchanged; the partial ECGs
   [B][L][T] (f64, 6.4 kB per simulation on model_24) are summed with one all-reduce.
+* the activation automaton on such a sharded model (`sharded_activation`): the one place with a real halo exchange --
+  per round one plane each way between neighbouring slabs plus an all-reduce of the "anything improved?" counts.
 """
 from __future__ import annotations
 
@@ -131,7 +133,7 @@ class ModelPlanes:
         return self.model.activation_end()
 
 
-def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000):
+def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, timings=None):
     """The activation automaton of a model sharded into z-slabs.
 
     `planes` offers begin / relax / export(z0, z1) -> tensor[z1-z0, plane_elems] / merge(z0, tensor) -> improved cells /
@@ -141,7 +143,9 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000):
     (elementwise minimum) and the ranks agree through one all-reduce whether anything improved anywhere.  Min-merging
     never overshoots the least fixed point, so the result has the bits of the single-GPU run.  At the end every rank
     broadcasts its slab so that all ranks hold the whole map, like after `ekg_model_activation`.
-    Returns (delay[Z, Y, X] as numpy, rounds, brick visits of this rank)."""
+    Returns (delay[Z, Y, X] as numpy, rounds, brick visits of this rank); `timings` (a dict) receives the wall seconds
+    of the three phases: rounds, gather, publish."""
+    import time
     import torch
     import torch.distributed as dist
     if rank is None:
@@ -153,6 +157,7 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000):
     below = max([r for r in live if r < rank], default=None) if rank in live else None
     above = min([r for r in live if r > rank], default=None) if rank in live else None
     z0, z1 = slabs[rank]
+    t_begin = time.perf_counter()
     planes.begin()
     visits, rounds = 0, 0
     while True:
@@ -184,6 +189,7 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000):
             break
         if rounds >= max_rounds:
             raise RuntimeError("sharded activation automaton did not converge in %d rounds" % max_rounds)
+    t_rounds = time.perf_counter()
     # every rank ends up with the whole map: rank s broadcasts its slab, the others min-merge it (what they hold
     # outside their own slab are upper bounds)
     if world > 1:
@@ -193,7 +199,11 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000):
             dist.broadcast(buf, src=s)
             if s != rank:
                 planes.merge(a, buf)
-    return planes.end(), rounds, visits
+    t_gather = time.perf_counter()
+    delay = planes.end()
+    if timings is not None:
+        timings.update(rounds_s=t_rounds - t_begin, gather_s=t_gather - t_rounds, publish_s=time.perf_counter() - t_gather)
+    return delay, rounds, visits
 
 
 def send_device(planes):

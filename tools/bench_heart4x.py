@@ -69,11 +69,14 @@ def main():
             if world > 1:
                 torch.distributed.barrier()
             t0 = time.perf_counter()
-            d2, rounds, visits = ekdist.sharded_activation(planes, slabs, rank, world)
+            tm = {}
+            d2, rounds, visits = ekdist.sharded_activation(planes, slabs, rank, world, timings=tm)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         same = bool(d2.tobytes() == delay.tobytes())
-        sharded = {"ms_total_incl_final_gather_and_publish": ekdist.max_over_ranks(dt * 1e3, dev), "rounds": rounds, "brick_visits_rank0": visits,
+        sharded = {"ms_total_incl_final_gather_and_publish": ekdist.max_over_ranks(dt * 1e3, dev),
+                   "ms_rounds": ekdist.max_over_ranks(tm["rounds_s"] * 1e3, dev), "ms_gather": ekdist.max_over_ranks(tm["gather_s"] * 1e3, dev),
+                   "ms_publish_host_copy": ekdist.max_over_ranks(tm["publish_s"] * 1e3, dev), "rounds": rounds, "brick_visits_rank0": visits,
                    "bit_identical_to_replicated_run": same}
         assert same, "sharded automaton differs from the replicated run"
     g = np.load(os.path.join(ROOT, "tests", "golden", "golden_glue256.npz"))
