@@ -141,6 +141,7 @@ static int publish_activation(ekg_model* m, bool download) {
 	for (int64_t i = 0; i < n; ++i) if (m->h_layer[i]) { lo = std::min(lo, m->h_delay[i]); hi = std::max(hi, m->h_delay[i]); }
 	m->t0 = (lo <= hi) ? 0.5 * (lo + hi) : 0.0;
 	m->at_max = (lo <= hi) ? hi : 0.0;
+	m->at_min = (lo <= hi) ? lo : 0.0;
 	m->have_activation = true;
 	return gather_at(m);
 }
@@ -520,11 +521,21 @@ static int simulate_host(ekg_model* m, const double* layer_k, const double* lead
 	// smallest depolarisation rate of the batch, known here without asking the device: the caller's layer
 	// coefficients, or -- with the device fit -- the border APs (k1 of an inner layer is the blend of its two
 	// border values unless d9[1] asks the descent to move it)
-	double k1_min = INFINITY;
-	if (!fit) for (int64_t i = 0; i < B * m->n_layers; ++i) k1_min = std::min(k1_min, layer_k[i * 9 + 1]);
-	else if (fit->d9[1] == 0) for (int64_t i = 0; i < B * fit->n_border; ++i) k1_min = std::min(k1_min, fit->border_k[i * 9 + 1]);
-	if (!(k1_min > 0) || !std::isfinite(k1_min)) k1_min = 0.0;
-	rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, flags, m->d_io_ecg, m->stream, k1_min);
+	KHints hints;
+	{
+		const double* src = fit ? fit->border_k : layer_k;
+		const int64_t n = B * (fit ? fit->n_border : m->n_layers);
+		double k1_min = INFINITY, decay = 0.0;
+		for (int64_t i = 0; i < n; ++i) {
+			k1_min = std::min(k1_min, src[i * 9 + 1]);
+			decay = std::max(decay, std::max(std::fabs(src[i * 9 + 4] + src[i * 9 + 5]), std::fabs(src[i * 9 + 5])));
+		}
+		// with the device fit: k1 and k4 of an inner layer are blends of the border values (unless d9 asks the descent to
+		// move them), k5 moves by a few percent -- a factor 2 on the decay rate covers it, the limit is 10x away anyway
+		const bool known = !fit || (fit->d9[1] == 0 && fit->d9[4] == 0);
+		if (known && k1_min > 0 && std::isfinite(k1_min) && std::isfinite(decay)) { hints.k1_min = k1_min; hints.decay_max = fit ? 2.0 * decay : decay; }
+	}
+	rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, flags, m->d_io_ecg, m->stream, hints);
 	if (rc) return rc;
 	std::vector<double> crit_host;
 	if (criteria_out) {

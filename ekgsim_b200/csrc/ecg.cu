@@ -670,7 +670,11 @@ __global__ void ecg_params_kernel(const double* __restrict__ layer_k, float* __r
 	const double* k = layer_k + i * 9;
 	// smallest depolarisation rate of the batch (float bits order like ints for positive values; anything
 	// else -- k1 <= 0, NaN -- becomes 0 = "never saturates")
-	if (k1min) atomicMin(k1min, k[1] > 0 ? __float_as_int(__double2float_rd(k[1])) : 0);
+	if (k1min) {
+		atomicMin(k1min, k[1] > 0 ? __float_as_int(__double2float_rd(k[1])) : 0);
+		const double decay = fmax(fabs(k[4] + k[5]), fabs(k[5]));
+		atomicMax(k1min + 1, decay == decay ? __float_as_int(__double2float_ru(fmin(decay, 3e38))) : 0x7f7fffff);   // NaN -> "too large"
+	}
 	const double log2e = 1.4426950408889634074;
 	float* p = P + i * kParamStride;
 	p[0] = (float)(-k[1] * log2e);
@@ -818,11 +822,11 @@ static int build_moment_segments(ekg_model* m, int64_t seg_len, cudaStream_t st)
 }
 
 static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
-                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, double k1_min);
+                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, KHints hints);
 
 // Large batches are cut into sub-batches so that the f64 partial-sum scratch stays below ~1 GiB.
 int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
-            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, double k1_min) {
+            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, KHints hints) {
 	if (B <= 0 || L <= 0) return fail(EKG_E_INVALID, "B and n_leads must be positive");
 	if (!(t_step > 0) || !(total_time > 0)) return fail(EKG_E_INVALID, "t_step and total_time must be positive");
 	const int64_t T = (int64_t)ceil(total_time / t_step);
@@ -840,7 +844,7 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 	for (int64_t b0 = 0; b0 < B; b0 += sub) {
 		const int64_t nb = std::min(sub, B - b0);
 		int rc = run_ecg_one(m, d_layer_k + b0 * m->n_layers * 9, d_leads + b0 * L * 3, nb, L, nbhd, t_start, t_step, total_time, flags,
-		                     d_ecg + b0 * L * T, st, k1_min);
+		                     d_ecg + b0 * L * T, st, hints);
 		if (rc) return rc;
 		launches += m->last_launches;
 	}
@@ -849,7 +853,7 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 }
 
 static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
-                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, double k1_min) {
+                       double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, KHints hints) {
 	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence: call ekg_model_activation or ekg_model_set_activation first");
 	if (B <= 0 || L <= 0) return fail(EKG_E_INVALID, "B and n_leads must be positive");
 	if (B > 65535) return fail(EKG_E_UNSUPPORTED, "at most 65535 parameter vectors per call");
@@ -886,14 +890,30 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 
 	const int64_t n_bl = B * m->n_layers;
 	if ((rc = ensure(&m->d_params, &m->params_cap, n_bl * kParamStride))) return rc;
-	const bool want_k1 = mode == EKG_MODE_SEPARABLE && !(k1_min > 0);
+	const bool want_k1 = mode == EKG_MODE_SEPARABLE && !(hints.k1_min > 0);
 	if (want_k1) {
-		if (!m->d_k1min) EKG_CUDA(cudaMalloc(&m->d_k1min, sizeof(int)));
+		if (!m->d_k1min) EKG_CUDA(cudaMalloc(&m->d_k1min, 2 * sizeof(int)));
 		EKG_CUDA(cudaMemsetAsync(m->d_k1min, 0x7f, sizeof(int), st));  // 0x7f7f7f7f = 3.4e38f
+		EKG_CUDA(cudaMemsetAsync(m->d_k1min + 1, 0, sizeof(int), st));
 	}
 	ecg_params_kernel<<<(int)((n_bl + 127) / 128), 128, 0, st>>>(d_layer_k, m->d_params, n_bl, (float)m->t0, want_k1 ? m->d_k1min : nullptr);
 	EKG_CUDA(cudaGetLastError());
 	++m->last_launches;
+	if (want_k1) {
+		int bits[2] = {0, 0};
+		EKG_CUDA(cudaMemcpyAsync(bits, m->d_k1min, sizeof bits, cudaMemcpyDeviceToHost, st));
+		EKG_CUDA(cudaStreamSynchronize(st));
+		float f[2]; memcpy(f, bits, 8);
+		hints.k1_min = (double)f[0];
+		hints.decay_max = (double)f[1];
+	}
+	// The HOISTED and SEPARABLE kernels factor exp(-k (t - at)) = exp(-k (t - t0)) exp(k (at - t0)) and clamp both exponents
+	// at 2^60; a batch whose decay rates or whose distance from t0 would reach the clamp runs through DIRECT instead (known
+	// rates only: an explicit HOISTED request with raw device pointers stays asynchronous and unchecked)
+	if (mode != EKG_MODE_DIRECT && hints.k1_min > 0) {
+		const double span = std::max(std::max(m->at_max - m->t0, m->t0 - m->at_min), std::max(m->t0 - t_start, 0.0));
+		if (!(hints.decay_max * span * 1.4426950408889634074 <= 55.0)) mode = EKG_MODE_DIRECT;
+	}
 
 	// SEPARABLE: the time-loop kernel handles the first T_loop samples (those before every voxel's
 	// depolarisation sigmoid is exactly 1 in fp32: exp(-k1 (t - at)) < 2^-25, the HOISTED kernel's own
@@ -902,13 +922,7 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	int loop_mode = mode;
 	if (mode == EKG_MODE_SEPARABLE) {
 		loop_mode = EKG_MODE_HOISTED;
-		if (want_k1) {
-			int bits = 0;
-			EKG_CUDA(cudaMemcpyAsync(&bits, m->d_k1min, sizeof(int), cudaMemcpyDeviceToHost, st));
-			EKG_CUDA(cudaStreamSynchronize(st));
-			float f; memcpy(&f, &bits, 4);
-			k1_min = (double)f;
-		}
+		const double k1_min = hints.k1_min;
 		const size_t smem_need = (size_t)(m->n_layers * L * 3 + m->n_layers) * sizeof(double);
 		if (k1_min > 0 && smem_need <= 48 * 1024) {
 			// k1 log2e (t - at) > 25 (+ a margin of 1e-3 ms for the fp32 evaluation of the same test)

@@ -142,6 +142,7 @@ struct ekg_model {
 	bool have_activation = false;
 	double t0 = 0.0;                 // centre of the activation-time range (HOISTED kernel)
 	double at_max = 0.0;             // latest activation time of the model (SEPARABLE: first saturated sample)
+	double at_min = 0.0;
 	float activation_ms = 0.f;       // device time of the last automaton run
 
 	// automaton state (device)
@@ -185,7 +186,7 @@ struct ekg_model {
 	ekg::Segment* d_msegs = nullptr; int64_t msegs_cap = 0;  int64_t n_msegs = 0;  int64_t mseg_len = 0;
 	int32_t* d_mseg_first = nullptr; int64_t mseg_first_cap = 0;   // first segment of every layer, n_layers + 1 entries
 	double* d_mom = nullptr;         int64_t mom_cap = 0;          // [n_msegs][B][L][3] moments
-	int* d_k1min = nullptr;                                        // float bits of min k1 over (vector, layer), by ecg_params_kernel
+	int* d_k1min = nullptr;                                        // [2] float bits of min k1 / max decay rate over (vector, layer), by ecg_params_kernel
 	float* d_params = nullptr;       int64_t params_cap = 0;
 	float* d_ftab = nullptr;         int64_t ftab_cap = 0;
 	float* d_times = nullptr;        int64_t times_cap = 0;
@@ -214,10 +215,14 @@ int shard_relax(ekg_model* m, int64_t* visits_out);
 int shard_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, cudaStream_t st);
 int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, cudaStream_t st);
 // ecg.cu
-// k1_min: smallest depolarisation rate k1 over all (vector, layer) if the caller knows it on the host
-// (<= 0: unknown -- the SEPARABLE path then reads it back from the device, one stream synchronisation)
+// What the caller knows on the host about the coefficients of the batch (all zero: nothing -- the SEPARABLE path
+// then reads both back from the device, one stream synchronisation):
+//   k1_min     smallest depolarisation rate k1 over all (vector, layer): where the sigmoid saturates
+//   decay_max  largest of |k4 + k5|, |k5|: whether the hoisted exponentials exp(+-k (at - t0)), exp(-k (t - t0)) stay
+//              inside the 2^60 clamp of the HOISTED / SEPARABLE kernels (otherwise the run goes through DIRECT)
+struct KHints { double k1_min = 0.0, decay_max = 0.0; };
 int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
-            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, double k1_min = 0.0);
+            double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, KHints hints = KHints());
 int run_criteria(ekg_model* m, const double* d_ecg, const double* d_targets, const double* d_offsets, double* d_crit,
                  int64_t B, int64_t L, int64_t T, int64_t n_target, int comparison, cudaStream_t st);
 int make_nbr_table(int nbhd, NbrTable* out);

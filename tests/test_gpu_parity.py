@@ -530,3 +530,24 @@ def test_sharded_automaton_entry_points(built, model24, model24_delay, world):
         whole.activation_relax()                                           # not between begin and end
     for p in ranks:
         p.model.close()
+
+
+def test_fast_decay_falls_back_to_direct(gpu_model24, model24, model24_delay):
+    """The HOISTED / SEPARABLE factorisation exp(-k (t - at)) = exp(-k (t - t0)) exp(k (at - t0)) is clamped at 2^60 per
+    factor; a plateau decay k4 = 4 /ms over the 39 ms activation range would need 2^112.  The library notices (it knows
+    the coefficients of a host-buffer call) and runs DIRECT instead of returning clamped numbers."""
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    gpu_model24.set_activation(model24_delay)
+    k = g["layer_k"][:3].copy()
+    k[:, :, 4] = 4.0
+    leads = g["leads_zyx"][:3]
+    ref = oracle.run_factored(model24["layers"], model24_delay, k[1], leads[1], "3D4", 100.0, 1.0, 80.0)
+    for mode in (2, 3, 0):
+        ecg = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 80.0, mode=mode)
+        assert gpu_model24.last_kernel_name == "ecg_kernel<DIRECT>", mode
+        assert rel_err(ecg[1], ref) < ECG_TOL, (mode, rel_err(ecg[1], ref))
+    # the ordinary range keeps the fast paths
+    gpu_model24.simulate(g["layer_k"][:3], leads, "3D4", 100.0, 1.0, 80.0, mode=2)
+    assert gpu_model24.last_kernel_name == "ecg_kernel<HOISTED>"
+    gpu_model24.simulate(g["layer_k"][:3], leads, "3D4", 100.0, 1.0, 80.0, mode=0)
+    assert gpu_model24.last_kernel_name == "ecg_moment_kernel"
