@@ -371,7 +371,10 @@ def run_b200_arm(args):
         separable = {"kernel": sep_kernel, "ms_per_step": sms, "sims_per_s": world * B / (sms * 1e-3),
                      "equivalent_voxel_timesteps_per_s": vts_step_global / (sms * 1e-3),
                      "moment_kernel_ms": mk, "launches_per_step": sep_launches,
-                     "moment_kernel_mufu_gops": 20 * B * N_VOX / (mk * 1e-3) / 1e9,
+                     "moment_kernel_mufu_gops": 18 * B * N_VOX / (mk * 1e-3) / 1e9,
+                     # per (voxel, vector) at 2 leads: ~100 packed fp32x2 operations = 200 fp32 lane-operations (an FFMA2
+                     # occupies the FMA pipe for two cycles) and 16-18 rsqrt + 2 ex2; the fp32 pipe binds
+                     "moment_kernel_fp32_lane_gops": 200 * B * N_VOX / (mk * 1e-3) / 1e9,
                      "e2e_ms_per_step": 1e3 * sep_e2e, "e2e_sims_per_s": world * B / sep_e2e,
                      "e2e_api": "ekg_simulate (C ABI, host buffers, EKG_MODE_DEFAULT)",
                      "note": "valid because every sample of the run is later than the last activation time + 25/(k1 log2 e) "
@@ -464,6 +467,11 @@ def run_b200_arm(args):
                 "note": "algorithmic bytes: 16 B/voxel per individual + f64 partials; the kernel is MUFU-bound, not HBM-bound"},
     }
 
+    if separable:
+        fp32_peak = sm_count * 128 * sm_mhz * 1e6 / 1e9
+        separable["moment_kernel_roofline"] = {"bound": "fp32", "achieved": separable["moment_kernel_fp32_lane_gops"], "peak": fp32_peak,
+                                               "unit": "G lane-op/s (FMA pipe)", "frac": separable["moment_kernel_fp32_lane_gops"] / fp32_peak,
+                                               "mufu_frac": separable["moment_kernel_mufu_gops"] / peak_gops}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
