@@ -135,11 +135,12 @@ class Model:
     def set_slab(self, z0, z1):
         _check(lib().ekg_model_set_slab(self._h, int(z0), int(z1)))
 
-    def activation(self):
-        """Runs the automaton on the GPU; returns (delay[Z,Y,X] f64, sweeps)."""
-        out = np.empty(self.shape, dtype=np.float64)
+    def activation(self, download=True):
+        """Runs the automaton on the GPU; returns (delay[Z,Y,X] f64, sweeps).  download=False leaves the map on the
+        device (delay is None; `get_activation` fetches it later if it is wanted after all)."""
+        out = np.empty(self.shape, dtype=np.float64) if download else None
         sweeps = C.c_int64(0)
-        _check(lib().ekg_model_activation(self._h, _ptr(out), C.byref(sweeps)))
+        _check(lib().ekg_model_activation(self._h, _ptr(out) if download else None, C.byref(sweeps)))
         return out, int(sweeps.value)
 
     @property
@@ -171,9 +172,9 @@ class Model:
         _check(lib().ekg_model_activation_merge(self._h, int(z_begin), int(z_end), C.c_void_p(d_planes), C.byref(n), C.c_void_p(stream)))
         return int(n.value)
 
-    def activation_end(self):
-        out = np.empty(self.shape, dtype=np.float64)
-        _check(lib().ekg_model_activation_end(self._h, _ptr(out)))
+    def activation_end(self, download=True):
+        out = np.empty(self.shape, dtype=np.float64) if download else None
+        _check(lib().ekg_model_activation_end(self._h, _ptr(out) if download else None))
         return out
 
     def set_activation(self, delay):

@@ -52,7 +52,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved};
+	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -122,26 +122,137 @@ static int gather_at(ekg_model* m) {
 	return EKG_OK;
 }
 
-// after d_time_pad holds a map: refresh the host raster copy, t0 and the ECG-list gather
-static int publish_activation(ekg_model* m, bool download) {
+// order-preserving map of a double onto an unsigned 64-bit key (and back), for atomicMin / atomicMax
+__host__ __device__ inline unsigned long long range_key(double v) {
+	long long b;
+	memcpy(&b, &v, 8);
+	return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
+}
+static double range_unkey(unsigned long long k) {
+	long long b = (long long)k;
+	b = (b < 0) ? (b ^ (long long)0x8000000000000000ULL) : ~b;
+	double v;
+	memcpy(&v, &b, 8);
+	return v;
+}
+
+// smallest / largest activation time over the occupied voxels of the WHOLE model (never reached counts as 0, like the
+// excitationDelay the reference leaves untouched, simulator.cpp:219): range[0] = min key, range[1] = max key
+__global__ void activation_range_kernel(const double* __restrict__ time_pad, const uint32_t* __restrict__ pidx, int64_t n,
+                                        unsigned long long* __restrict__ range) {
+	unsigned long long lo = ~0ULL, hi = 0ULL;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		double v = time_pad[pidx[i]];
+		if (isinf(v)) v = 0.0;
+		const unsigned long long k = range_key(v);
+		lo = min(lo, k);
+		hi = max(hi, k);
+	}
+	for (int o = 16; o; o >>= 1) {
+		lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+		hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+	}
+	if ((threadIdx.x & 31) == 0 && lo <= hi) {
+		atomicMin(range, lo);
+		atomicMax(range + 1, hi);
+	}
+}
+
+// raster elements [i0, i0 + cnt) of the activation map out of the padded grid: 0 for empty and never-reached voxels
+__global__ void unpad_activation_kernel(const double* __restrict__ time_pad, const uint8_t* __restrict__ layer_pad,
+                                        double* __restrict__ out, int64_t i0, int64_t cnt, int64_t Y, int64_t X, int64_t pY, int64_t pX) {
+	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= cnt) return;
+	const int64_t i = i0 + j;
+	const int64_t x = i % X, zy = i / X, y = zy % Y, z = zy / Y;
+	const int64_t p = ((z + 1) * pY + (y + 1)) * pX + (x + 1);
+	double v = 0.0;
+	if (layer_pad[p]) {
+		v = time_pad[p];
+		if (isinf(v)) v = 0.0;
+	}
+	out[j] = v;
+}
+
+// The raster host copy of the device-resident map (Z*Y*X doubles), made only when a caller asks for it: unpadded on the
+// device, brought over in chunks through two pinned buffers so that the copy of one chunk overlaps the memcpy of the
+// previous one into the caller's (pageable) array.
+static int download_activation(ekg_model* m, double* dst) {
 	const int64_t n = m->Z * m->Y * m->X;
-	if (download) {
-		std::vector<double> padded((size_t)(m->pZ * m->pY * m->pX));
-		EKG_CUDA(cudaMemcpyAsync(padded.data(), m->d_time_pad, padded.size() * 8, cudaMemcpyDeviceToHost, m->stream));
-		EKG_CUDA(cudaStreamSynchronize(m->stream));
-		m->h_delay.assign((size_t)n, 0.0);
-		for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < m->Y; ++y) for (int64_t x = 0; x < m->X; ++x) {
-			const int64_t i = (z * m->Y + y) * m->X + x;
-			if (!m->h_layer[i]) continue;
-			const double v = padded[pad_index(m, z, y, x)];
-			m->h_delay[i] = std::isinf(v) ? 0.0 : v;
+	const int64_t chunk = std::min<int64_t>(n, (int64_t)4 << 20);  // 32 MB of doubles
+	double* d_buf[2] = {nullptr, nullptr};
+	double* h_buf[2] = {nullptr, nullptr};
+	cudaEvent_t done[2] = {nullptr, nullptr};
+	auto cleanup = [&]() {
+		for (int i = 0; i < 2; ++i) {
+			if (d_buf[i]) cudaFree(d_buf[i]);
+			if (h_buf[i]) cudaFreeHost(h_buf[i]);
+			if (done[i]) cudaEventDestroy(done[i]);
+		}
+	};
+#define EKG_DL_CUDA(call)                                                                          \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                                  \
+		if (e__ != cudaSuccess) { cleanup(); return cuda_fail(e__, #call, __FILE__, __LINE__); }   \
+	} while (0)
+	const int n_buf = n > chunk ? 2 : 1;
+	for (int i = 0; i < n_buf; ++i) {
+		EKG_DL_CUDA(cudaMalloc(&d_buf[i], (size_t)chunk * 8));
+		EKG_DL_CUDA(cudaMallocHost(&h_buf[i], (size_t)chunk * 8));
+		EKG_DL_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+	}
+	const int64_t n_chunks = (n + chunk - 1) / chunk;
+	for (int64_t c = 0; c <= n_chunks; ++c) {
+		if (c < n_chunks) {
+			const int b = (int)(c % n_buf);
+			const int64_t i0 = c * chunk, cnt = std::min(chunk, n - i0);
+			unpad_activation_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, m->stream>>>(m->d_time_pad, m->d_layer_pad, d_buf[b], i0, cnt, m->Y, m->X, m->pY, m->pX);
+			EKG_DL_CUDA(cudaGetLastError());
+			EKG_DL_CUDA(cudaMemcpyAsync(h_buf[b], d_buf[b], (size_t)cnt * 8, cudaMemcpyDeviceToHost, m->stream));
+			EKG_DL_CUDA(cudaEventRecord(done[b], m->stream));
+		}
+		if (c > 0) {  // chunk c - 1 has arrived (its buffers are reused by chunk c + 1, enqueued after this memcpy)
+			const int b = (int)((c - 1) % n_buf);
+			const int64_t i0 = (c - 1) * chunk, cnt = std::min(chunk, n - i0);
+			EKG_DL_CUDA(cudaEventSynchronize(done[b]));
+			memcpy(dst + i0, h_buf[b], (size_t)cnt * 8);
 		}
 	}
-	double lo = INFINITY, hi = -INFINITY;
-	for (int64_t i = 0; i < n; ++i) if (m->h_layer[i]) { lo = std::min(lo, m->h_delay[i]); hi = std::max(hi, m->h_delay[i]); }
-	m->t0 = (lo <= hi) ? 0.5 * (lo + hi) : 0.0;
-	m->at_max = (lo <= hi) ? hi : 0.0;
-	m->at_min = (lo <= hi) ? lo : 0.0;
+#undef EKG_DL_CUDA
+	cleanup();
+	return EKG_OK;
+}
+
+// h_delay on demand (ekg_model_get_activation, ekg_model_ap_classes)
+static int ensure_host_delay(ekg_model* m) {
+	if (m->h_delay_valid) return EKG_OK;
+	EKG_CUDA(cudaSetDevice(m->device));
+	m->h_delay.resize((size_t)(m->Z * m->Y * m->X));
+	int rc = download_activation(m, m->h_delay.data());
+	if (rc) return rc;
+	m->h_delay_valid = true;
+	return EKG_OK;
+}
+
+// after d_time_pad holds a map: the range of activation times (t0 of the hoisted forms, the saturation time of the
+// SEPARABLE path) by a device reduction, then the ECG-list gather.  The map itself stays on the device.
+static int publish_activation(ekg_model* m) {
+	double lo = 0.0, hi = 0.0;
+	if (m->n_occ > 0) {
+		unsigned long long h_range[2] = {~0ULL, 0ULL};
+		if (!m->d_range) EKG_CUDA(cudaMalloc(&m->d_range, 2 * sizeof(unsigned long long)));
+		EKG_CUDA(cudaMemcpyAsync(m->d_range, h_range, sizeof h_range, cudaMemcpyHostToDevice, m->stream));
+		const int blocks = (int)std::min<int64_t>((m->n_occ + 255) / 256, (int64_t)m->sm_count * 8);
+		activation_range_kernel<<<blocks, 256, 0, m->stream>>>(m->d_time_pad, m->d_auto_pidx, m->n_occ, m->d_range);
+		EKG_CUDA(cudaGetLastError());
+		EKG_CUDA(cudaMemcpyAsync(h_range, m->d_range, sizeof h_range, cudaMemcpyDeviceToHost, m->stream));
+		EKG_CUDA(cudaStreamSynchronize(m->stream));
+		lo = range_unkey(h_range[0]);
+		hi = range_unkey(h_range[1]);
+	}
+	m->t0 = 0.5 * (lo + hi);
+	m->at_max = hi;
+	m->at_min = lo;
 	m->have_activation = true;
 	return gather_at(m);
 }
@@ -317,9 +428,11 @@ int ekg_model_activation(ekg_model* m, double* delay_out, int64_t* sweeps_out) {
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
 	if (rc) return rc;
-	rc = publish_activation(m, true);
+	m->h_delay_valid = false;
+	std::vector<double>().swap(m->h_delay);
+	rc = publish_activation(m);
 	if (rc) return rc;
-	if (delay_out) memcpy(delay_out, m->h_delay.data(), m->h_delay.size() * 8);
+	if (delay_out) return download_activation(m, delay_out);
 	return EKG_OK;
 }
 
@@ -355,9 +468,11 @@ int ekg_model_activation_end(ekg_model* m, double* delay_out) {
 	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
 	EKG_CUDA(cudaSetDevice(m->device));
 	m->shard_active = false;
-	int rc = publish_activation(m, true);
+	m->h_delay_valid = false;
+	std::vector<double>().swap(m->h_delay);
+	int rc = publish_activation(m);
 	if (rc) return rc;
-	if (delay_out) memcpy(delay_out, m->h_delay.data(), m->h_delay.size() * 8);
+	if (delay_out) return download_activation(m, delay_out);
 	return EKG_OK;
 }
 
@@ -365,20 +480,23 @@ int ekg_model_set_activation(ekg_model* m, const double* delay) {
 	if (!m || !delay) return fail(EKG_E_INVALID, "NULL argument");
 	EKG_CUDA(cudaSetDevice(m->device));
 	const int64_t n = m->Z * m->Y * m->X;
-	m->h_delay.assign(delay, delay + n);
+	m->h_delay.assign(delay, delay + n);  // the caller's values as given (also those of empty voxels)
+	m->h_delay_valid = true;
 	std::vector<double> padded((size_t)(m->pZ * m->pY * m->pX), 0.0);
 	for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < m->Y; ++y)
 		memcpy(&padded[(size_t)pad_index(m, z, y, 0)], &delay[(z * m->Y + y) * m->X], (size_t)m->X * 8);
 	int rc = upload(m, m->d_time_pad, padded.data(), padded.size() * 8);
 	if (rc) return rc;
-	return publish_activation(m, false);
+	return publish_activation(m);
 }
 
 int ekg_model_get_activation(const ekg_model* m, double* delay_out) {
 	if (!m || !delay_out) return fail(EKG_E_INVALID, "NULL argument");
 	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence yet");
-	memcpy(delay_out, m->h_delay.data(), m->h_delay.size() * 8);
-	return EKG_OK;
+	if (m->h_delay_valid) { memcpy(delay_out, m->h_delay.data(), m->h_delay.size() * 8); return EKG_OK; }
+	ekg_model* mm = const_cast<ekg_model*>(m);  // the handle's scratch, not its state
+	EKG_CUDA(cudaSetDevice(mm->device));
+	return download_activation(mm, delay_out);
 }
 
 int64_t ekg_model_activation_brick_visits(const ekg_model* m) { return m ? m->last_brick_visits : 0; }
@@ -387,6 +505,7 @@ double ekg_model_activation_ms(const ekg_model* m) { return m ? (double)m->activ
 int ekg_model_ap_classes(const ekg_model* m, int64_t* ap_index_out, int64_t* n_classes_out) {
 	if (!m || !ap_index_out || !n_classes_out) return fail(EKG_E_INVALID, "NULL argument");
 	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence yet");
+	if (int rc = ensure_host_delay(const_cast<ekg_model*>(m))) return rc;  // lazily cached host copy
 	// one (layer, exact delay) -> index map, indices handed out in first-seen raster order
 	// (simulator.cpp:566-590 keeps one std::map<double,size_t> per layer with a shared counter)
 	struct Key { uint64_t bits; uint32_t layer; bool operator==(const Key& o) const { return bits == o.bits && layer == o.layer; } };

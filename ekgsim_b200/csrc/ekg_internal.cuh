@@ -138,7 +138,9 @@ struct ekg_model {
 	std::vector<int64_t> h_starts;   // raster indices of start voxels
 	std::vector<double> h_transfer;
 	int64_t t_rows = 0, t_cols = 0;
-	std::vector<double> h_delay;     // raster activation map (0 = empty / never reached)
+	std::vector<double> h_delay;     // raster activation map (0 = empty / never reached): a lazily made host copy,
+	bool h_delay_valid = false;      // the map itself lives in d_time_pad
+	unsigned long long* d_range = nullptr;  // [2] min / max key of the activation times (publish_activation)
 	bool have_activation = false;
 	double t0 = 0.0;                 // centre of the activation-time range (HOISTED kernel)
 	double at_max = 0.0;             // latest activation time of the model (SEPARABLE: first saturated sample)

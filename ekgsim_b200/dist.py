@@ -129,11 +129,11 @@ class ModelPlanes:
         return self.model.activation_merge(z_begin, z_begin + planes.shape[0], planes.data_ptr(),
                                            self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def end(self):
-        return self.model.activation_end()
+    def end(self, download=True):
+        return self.model.activation_end(download=download)
 
 
-def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, timings=None):
+def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, timings=None, download=True):
     """The activation automaton of a model sharded into z-slabs.
 
     `planes` offers begin / relax / export(z0, z1) -> tensor[z1-z0, plane_elems] / merge(z0, tensor) -> improved cells /
@@ -144,7 +144,8 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, t
     never overshoots the least fixed point, so the result has the bits of the single-GPU run.  At the end every rank
     broadcasts its slab so that all ranks hold the whole map, like after `ekg_model_activation`.
     Returns (delay[Z, Y, X] as numpy, rounds, brick visits of this rank); `timings` (a dict) receives the wall seconds
-    of the three phases: rounds, gather, publish."""
+    of the three phases: rounds, gather, publish.  download=False leaves the map on the device (delay is None): the
+    ECG entry points only need it there."""
     import time
     import torch
     import torch.distributed as dist
@@ -200,7 +201,7 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, t
             if s != rank:
                 planes.merge(a, buf)
     t_gather = time.perf_counter()
-    delay = planes.end()
+    delay = planes.end() if download else planes.end(download=False)
     if timings is not None:
         timings.update(rounds_s=t_rounds - t_begin, gather_s=t_gather - t_rounds, publish_s=time.perf_counter() - t_gather)
     return delay, rounds, visits

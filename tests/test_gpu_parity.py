@@ -96,6 +96,49 @@ def test_activation_2d_and_unreachable(built):
     m.close()
 
 
+def test_activation_map_stays_on_device(built):
+    """The raster host copy of the activation map is optional (ekg_model_activation with delay_out = NULL, what the
+    facade passes) and made lazily: the ECG entry points work without it, ekg_model_get_activation /
+    ekg_model_ap_classes fetch it on demand -- here through more than one 32 MB download chunk."""
+    small, transfer, leads = synth.small_heart(seed=5, shape=(23, 27, 25))
+    layers = np.zeros((172, 160, 161), dtype=np.uint16)          # 4.43 M voxels = 35 MB of doubles: two chunks
+    layers[140:163, 100:127, 120:145] = small
+    leads = leads + np.array([140.0, 100.0, 120.0])
+    m = built.Model(layers, transfer)
+    none, visits = m.activation(download=False)
+    assert none is None and visits > 0
+    ref = oracle.activation(layers, transfer)
+    layer_k = synth.layer_params(int((layers & 0xFFF).max()), seed=2)
+    want = oracle.run_direct(layers, ref, layer_k, leads, "3D4", 0.0, 1.0, 64.0)
+    for mode in (1, 2, 3):
+        assert rel_err(m.simulate(layer_k, leads, "3D4", 0.0, 1.0, 64.0, mode=mode)[0], want) < ECG_TOL
+    got = m.get_activation()
+    assert got.tobytes() == ref.tobytes()
+    K, idx = m.ap_classes()
+    Ko, idxo = oracle.ap_classes(layers, ref, int((layers & 0xFFF).max()))
+    assert K == Ko and (idx == idxo).all()
+    delay, _ = m.activation()                                    # and the eager form still returns the same map
+    assert delay.tobytes() == ref.tobytes()
+    m.close()
+
+
+def test_set_activation_range_and_copy(built):
+    """ekg_model_set_activation (loadExcitationSequence, simulator.cpp:288-367): the range of the loaded times -- also
+    negative ones -- is found on the device (centre of the hoisted exponentials, saturation time of the SEPARABLE
+    path), and ekg_model_get_activation returns the caller's array as given."""
+    layers, transfer, leads = synth.small_heart(seed=6)
+    m = built.Model(layers, transfer)
+    base = oracle.activation(layers, transfer)
+    shifted = np.where((layers & 0xFFF) > 0, base - 7.5, -3.0)    # negative times; junk in the empty voxels
+    m.set_activation(shifted)
+    assert m.get_activation().tobytes() == shifted.tobytes()
+    layer_k = synth.layer_params(int((layers & 0xFFF).max()), seed=9)
+    want = oracle.run_direct(layers, shifted, layer_k, leads, "3D4", -5.0, 1.0, 80.0)
+    for mode in (1, 2, 3):
+        assert rel_err(m.simulate(layer_k, leads, "3D4", -5.0, 1.0, 80.0, mode=mode)[0], want) < ECG_TOL
+    m.close()
+
+
 def test_activation_errors(built):
     layers, transfer, _ = synth.small_heart(seed=0)
     nostart = layers & 0x0FFF
