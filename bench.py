@@ -336,6 +336,16 @@ def run_b200_arm(args):
         for _ in range(3):
             step_sep()
         barrier()
+        # A/B of the moment kernel: interior voxels through the direct 8-corner sum (EKG_FLAG_CORNER_SUM) instead of the series
+        corner_sum_ms = []
+        for i in range(3 + args.steps):
+            flush.fill_(1)
+            model.simulate_device(d_k.data_ptr(), d_leads.data_ptr(), B, L, d_ecg.data_ptr(), "3D4", 100.0, 1.0, float(T_FULL),
+                                  mode=ek.MODE_SEPARABLE | ek.FLAG_TIME_KERNEL | ek.FLAG_CORNER_SUM, stream=stream)
+            if i >= 3:
+                corner_sum_ms.append(model.last_kernel_ms)
+        ecg_corner_sum = d_ecg.cpu().numpy()
+        barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sep_kernel_ms = []
         f0.record()
@@ -365,16 +375,32 @@ def run_b200_arm(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sep_e2e = float(t.item())
-        # moment kernel: 18 rsqrt + 2 ex2 on the MUFU pipe per (voxel, vector) at 2 leads and the 3D4 stencil (9 lead-field
-        # evaluations per lead); ~420 FP32 instructions per (voxel, vector)
+        # moment kernel, per (voxel, vector) at 2 leads and the 3D4 stencil:
+        #   boundary voxel (a corner missing): 9 lead-field evaluations -> ~100 packed fp32x2 operations = 200 fp32 lane-operations
+        #                                      (an FFMA2 occupies the FMA pipe for two cycles), 16-18 rsqrt + 2 ex2
+        #   interior voxel (all 8 corners):    the series of the corner sum -> 34 packed + 8 scalar = 76 lane-operations, 2 rsqrt + 2 ex2
+        occ = (m24["layers"] & 0x0FFF) > 0
+        inner = occ.copy()
+        pad = np.pad(occ, 1)
+        Zs, Ys, Xs = occ.shape
+        for dz in (0, 2):
+            for dy in (0, 2):
+                for dx in (0, 2):
+                    inner &= pad[dz:dz + Zs, dy:dy + Ys, dx:dx + Xs]
+        f_int = float(inner.sum()) / float(occ.sum())
+        lane_ops = f_int * 76 + (1 - f_int) * 200
+        mufu_ops = f_int * 4 + (1 - f_int) * 20
         mk = sum(sep_kernel_ms) / len(sep_kernel_ms)
+        mk_sum = sum(corner_sum_ms) / len(corner_sum_ms)
+        ecg_series = d_ecg.cpu().numpy()
         separable = {"kernel": sep_kernel, "ms_per_step": sms, "sims_per_s": world * B / (sms * 1e-3),
                      "equivalent_voxel_timesteps_per_s": vts_step_global / (sms * 1e-3),
                      "moment_kernel_ms": mk, "launches_per_step": sep_launches,
-                     "moment_kernel_mufu_gops": 18 * B * N_VOX / (mk * 1e-3) / 1e9,
-                     # per (voxel, vector) at 2 leads: ~100 packed fp32x2 operations = 200 fp32 lane-operations (an FFMA2
-                     # occupies the FMA pipe for two cycles) and 16-18 rsqrt + 2 ex2; the fp32 pipe binds
-                     "moment_kernel_fp32_lane_gops": 200 * B * N_VOX / (mk * 1e-3) / 1e9,
+                     "interior_voxel_fraction": f_int,
+                     "moment_kernel_mufu_gops": mufu_ops * B * N_VOX / (mk * 1e-3) / 1e9,
+                     "moment_kernel_fp32_lane_gops": lane_ops * B * N_VOX / (mk * 1e-3) / 1e9,
+                     "moment_kernel_ms_with_direct_corner_sum": mk_sum,
+                     "series_vs_corner_sum_max_diff_of_peak": float((np.abs(ecg_series - ecg_corner_sum) / np.abs(ecg_series).max(axis=-1, keepdims=True)).max()),
                      "e2e_ms_per_step": 1e3 * sep_e2e, "e2e_sims_per_s": world * B / sep_e2e,
                      "e2e_api": "ekg_simulate (C ABI, host buffers, EKG_MODE_DEFAULT)",
                      "note": "valid because every sample of the run is later than the last activation time + 25/(k1 log2 e) "

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libekgsim_b200.so")
 NBHD = {"2D4": 0, "2D8": 1, "3D4": 2, "3D8": 3, "cube": 3}
 MODE_DEFAULT, MODE_DIRECT, MODE_HOISTED, MODE_SEPARABLE = 0, 1, 2, 3
 FLAG_TIME_KERNEL = 0x100
+FLAG_CORNER_SUM = 0x200   # SEPARABLE: interior voxels by the direct corner sum instead of the series (cross-check)
 FIT_D9 = (0.0, 0.0, 0.0, 0.001, 0.0, 0.00005, 0.0005, 0.01, 0.2)   # sim.cpp:877 `kd`
 START_FLAG = 0x1000
 

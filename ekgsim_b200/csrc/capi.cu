@@ -26,14 +26,20 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 constexpr uint16_t kStartFlag = 0x1000;  // ShapeElement::layerStartingPoint (matrix.h:90)
 
-__global__ void gather_at_kernel(const double* __restrict__ time_pad, const uint32_t* __restrict__ pidx, double* __restrict__ at,
-                                 float* __restrict__ at32, int64_t n) {
+__global__ void gather_at_kernel(const double* __restrict__ time_pad, const uint32_t* __restrict__ pidx, const uint32_t* __restrict__ pos,
+                                 const uint32_t* __restrict__ mask, double* __restrict__ at, float* __restrict__ at32, float4* __restrict__ vox,
+                                 int64_t n) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	double v = time_pad[pidx[i]];
 	if (isinf(v)) v = 0.0;  // never reached -> excitationDelay stays 0 (simulator.cpp:219)
 	at[i] = v;
 	at32[i] = (float)v;
+	// the moment kernel's record: bordered coordinates (simulator.cpp:458-463 adds a border of one voxel), x negated unless
+	// all 8 cube corners are occupied
+	const uint32_t p = pos[i];
+	const float x = (float)((p & 0x7ffu) + 1u);
+	vox[i] = make_float4((float)((p >> 22) + 1u), (float)(((p >> 11) & 0x7ffu) + 1u), (mask[i] & kCornerMask) == kCornerMask ? x : -x, (float)v);
 }
 
 // Host -> device upload that is COMPLETE on return.  A plain cudaMemcpy from pageable memory may return
@@ -52,7 +58,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
+	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -95,14 +101,15 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 		pidx[j] = (uint32_t)p;
 	}
 
-	for (void* p : {(void*)m->d_pos, (void*)m->d_mask, (void*)m->d_ecg_pidx, (void*)m->d_at, (void*)m->d_at32}) if (p) cudaFree(p);
-	m->d_pos = m->d_mask = m->d_ecg_pidx = nullptr; m->d_at = nullptr; m->d_at32 = nullptr;
+	for (void* p : {(void*)m->d_pos, (void*)m->d_mask, (void*)m->d_ecg_pidx, (void*)m->d_at, (void*)m->d_at32, (void*)m->d_vox}) if (p) cudaFree(p);
+	m->d_pos = m->d_mask = m->d_ecg_pidx = nullptr; m->d_at = nullptr; m->d_at32 = nullptr; m->d_vox = nullptr;
 	const size_t nn = (size_t)std::max<int64_t>(n, 1);
 	EKG_CUDA(cudaMalloc(&m->d_pos, nn * 4));
 	EKG_CUDA(cudaMalloc(&m->d_mask, nn * 4));
 	EKG_CUDA(cudaMalloc(&m->d_ecg_pidx, nn * 4));
 	EKG_CUDA(cudaMalloc(&m->d_at, nn * 8));
 	EKG_CUDA(cudaMalloc(&m->d_at32, nn * 4));
+	EKG_CUDA(cudaMalloc(&m->d_vox, nn * sizeof(float4)));
 	int rc;
 	if ((rc = upload(m, m->d_pos, pos.data(), (size_t)n * 4))) return rc;
 	if ((rc = upload(m, m->d_mask, mask.data(), (size_t)n * 4))) return rc;
@@ -116,7 +123,7 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 
 static int gather_at(ekg_model* m) {
 	if (m->n_ecg == 0) return EKG_OK;
-	gather_at_kernel<<<(int)((m->n_ecg + 255) / 256), 256, 0, m->stream>>>(m->d_time_pad, m->d_ecg_pidx, m->d_at, m->d_at32, m->n_ecg);
+	gather_at_kernel<<<(int)((m->n_ecg + 255) / 256), 256, 0, m->stream>>>(m->d_time_pad, m->d_ecg_pidx, m->d_pos, m->d_mask, m->d_at, m->d_at32, m->d_vox, m->n_ecg);
 	EKG_CUDA(cudaGetLastError());
 	EKG_CUDA(cudaStreamSynchronize(m->stream));
 	return EKG_OK;

@@ -394,6 +394,33 @@ __device__ __forceinline__ f2 inv_cube2(f2 sq) {
 	return mul2(mul2(y, y), y);
 }
 
+// The stencil sum of an INTERIOR voxel (all 8 cube corners occupied) as a series.  With q = lead - voxel and
+// f = 1/|q|:   g = sum_{d in {+-1}^3} d.(q+d)/|q+d|^3 = -d/ds [ sum_d f(q + s d) ]_{s=1},
+//              sum_d f(q + s d) = 8 cosh(s d/dx) cosh(s d/dy) cosh(s d/dz) f.
+// f is harmonic, so the s^2 term vanishes and the rest are cubic harmonics:  with u = 1/|q|^2, xi_i = q_i^2 u,
+// e2 = xi_z xi_y + xi_y xi_x + xi_x xi_z, e3 = xi_z xi_y xi_x
+//     g = |q|^-5 [ (112 - 560 e2) + u (3024 e2 - 33264 e3 - 288) + u^2 (-51480 e2^2 + 14256 e2 + 41184 e3 - 792) + O(u^3) ]
+// The 8 corner terms are O(|q|^-2) each and cancel down to this O(|q|^-5) remainder -- summed directly in fp32 they
+// leave 1e-4..1e-2 relative noise on g (it averages out over the model, which is why the direct sum passes its
+// tolerance); the series has no cancellation (1e-6 relative in fp32), a truncation error below 5e-8 relative for
+// |q| >= 32 voxels (3e-8 measured at 35, falling like |q|^-6) and costs 28 packed operations + 2 MUFU per lead
+// pair instead of ~110 + 16.  Leads closer than kSeriesMinR2 take the direct sum.
+constexpr float kSeriesMinR2 = 1024.f;
+__device__ __forceinline__ f2 c2(float c) { return mk2(c, c); }
+__device__ __forceinline__ f2 corner_series2(f2 qz, f2 qy, f2 qx, f2 r2) {
+	f2 y = mk2(mufu_rsq(lo2(r2)), mufu_rsq(hi2(r2)));
+	y = mul2(y, fma2(mul2(r2, c2(-0.5f)), mul2(y, y), c2(1.5f)));
+	const f2 u = mul2(y, y);
+	const f2 xz = mul2(qz, u), xy = mul2(qy, u), xx = mul2(qx, u);
+	const f2 zy = mul2(xz, xy);
+	const f2 e2 = fma2(add2(xz, xy), xx, zy);
+	const f2 e3 = mul2(zy, xx);
+	const f2 a4 = fma2(c2(-560.f), e2, c2(112.f));
+	const f2 a6 = fma2(c2(3024.f), e2, fma2(c2(-33264.f), e3, c2(-288.f)));
+	const f2 a8 = fma2(fma2(c2(-51480.f), e2, c2(14256.f)), e2, fma2(c2(41184.f), e3, c2(-792.f)));
+	return mul2(mul2(mul2(u, u), y), fma2(fma2(a8, u, a6), u, a4));
+}
+
 // occupancy-mask bits of the 8 cube corners in the order (dz, dy, dx) = (-,-,-), (-,-,+), ... (+,+,+): their
 // positions in the 26-neighbour cube list (make_nbr_table; checked on the host before this kernel is chosen)
 __device__ constexpr int kCornerBit[8] = {0, 2, 6, 8, 17, 19, 23, 25};
@@ -403,8 +430,10 @@ __device__ constexpr int kCornerBit[8] = {0, 2, 6, 8, 17, 19, 23, 25};
 // terms p = r + 1, m = 1 - r: |r + d|^2 = (p|m)_z^2 + (p|m)_y^2 + (p|m)_x^2 and d . (r + d) = (p|m)_z + (p|m)_y + (p|m)_x,
 // 4 packed instructions + 2 MUFU + 7 packed for the inverse cube per corner and lead pair (the generic loop
 // issues ~35 scalar instructions per corner and lead).  NP = lead pairs per pass.
-template <int NP>
-__global__ void __launch_bounds__(256, NP == 1 ? 4 : 2) ecg_moment_corners_kernel(const MomentArgs a) {
+// OCC = CTAs per SM the register budget is cut for (NP = 1: 3 -> 80 registers, nothing spilled; 4 -> 64 registers, the
+// loop invariants of the boundary path spill).
+template <int NP, int OCC>
+__global__ void __launch_bounds__(256, OCC) ecg_moment_corners_kernel(const MomentArgs a) {
 	__shared__ double s_red[256 * NP * 6];
 	const Segment sg = a.segs[blockIdx.x];
 	const int vb = 1 << a.vb_shift;
@@ -441,25 +470,37 @@ __global__ void __launch_bounds__(256, NP == 1 ? 4 : 2) ecg_moment_corners_kerne
 	}
 	int pending = 0;
 	for (int j = sg.begin + vl; j < sg.end; j += lanes) {
-		const uint32_t pos = __ldg(a.pos + j);
-		const uint32_t mask = __ldg(a.mask + j);
-		const float da = __ldg(a.at32 + j) - t0;
-		const float pz = __uint_as_float(0x4B000000u | ((pos >> 22) + 1u)) - 8388608.f;
-		const float py = __uint_as_float(0x4B000000u | (((pos >> 11) & 0x7ffu) + 1u)) - 8388608.f;
-		const float px = __uint_as_float(0x4B000000u | ((pos & 0x7ffu) + 1u)) - 8388608.f;
+		// one 16-byte record per voxel: bordered coordinates as floats, the sign of x = "all 8 corners occupied"
+		// (most of the model), the activation time; the occupancy mask is only read for boundary voxels
+		const float4 vx = __ldg(a.vox + j);
+		const float da = vx.w - t0;
+		const float pz = vx.x, py = vx.y, px = fabsf(vx.z);
 		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));
 		const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
-		constexpr uint32_t kAll = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8) | (1u << 17) | (1u << 19) | (1u << 23) | (1u << 25);
+		constexpr uint32_t kAll = kCornerMask;
 		constexpr uint32_t kZp = (1u << 17) | (1u << 19) | (1u << 23) | (1u << 25);
 		constexpr uint32_t kYp = (1u << 6) | (1u << 8) | (1u << 23) | (1u << 25);
 		constexpr uint32_t kXp = (1u << 2) | (1u << 8) | (1u << 19) | (1u << 25);
-		const bool interior = (mask & kAll) == kAll;   // all 8 corners occupied: most of the model
+		const bool interior = vx.z > 0.f;
+		const uint32_t mask = interior ? kAll : __ldg(a.mask + j);
 		const f2 PZ = mk2(pz, pz), PY = mk2(py, py), PX = mk2(px, px);
 #pragma unroll
 		for (int p = 0; p < NP; ++p) {
 			const f2 rz = sub2(lh[p][0], PZ);
 			const f2 ry = sub2(lh[p][1], PY);
 			const f2 rx = sub2(lh[p][2], PX);
+			if (interior && a.series) {
+				// all 8 corners occupied (most of the model): the series of the corner sum, unless a lead is close
+				const f2 qz = mul2(rz, rz), qy = mul2(ry, ry), qx = mul2(rx, rx);
+				const f2 r2 = add2(add2(qz, qy), qx);
+				if (fminf(lo2(r2), hi2(r2)) >= kSeriesMinR2) {
+					const f2 g = corner_series2(qz, qy, qx, r2);
+					f0[p] = sub2(f0[p], g);
+					f1[p] = fma2(g, mk2(-h1, -h1), f1[p]);
+					f2s[p] = fma2(g, mk2(-h2, -h2), f2s[p]);
+					continue;
+				}
+			}
 			const f2 zt[2] = {sub2(one, rz), add2(rz, one)};   // [0]: d = -1 -> -(r - 1),  [1]: d = +1 -> r + 1
 			const f2 yt[2] = {sub2(one, ry), add2(ry, one)};
 			const f2 xt[2] = {sub2(one, rx), add2(rx, one)};
@@ -1016,6 +1057,10 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		if ((rc = ensure(&m->d_mom, &m->mom_cap, std::max<int64_t>(m->n_msegs, 1) * B * L * 3))) return rc;
 		MomentArgs ma{};
 		ma.pos = m->d_pos; ma.mask = m->d_mask; ma.at32 = m->d_at32; ma.segs = m->d_msegs; ma.params = m->d_params; ma.leads = d_leads;
+		ma.vox = m->d_vox;
+		// EKG_FLAG_CORNER_SUM: interior voxels through the direct corner sum as well (the cross-check of the series)
+		static const bool occ4 = getenv("EKGSIM_B200_MOMENT_OCC") && atoi(getenv("EKGSIM_B200_MOMENT_OCC")) == 4;
+		ma.series = (flags & EKG_FLAG_CORNER_SUM) ? 0 : 1;
 		ma.mom = m->d_mom; ma.B = (int32_t)B; ma.L = (int32_t)L; ma.n_layers = m->n_layers; ma.vb_shift = vb_shift; ma.nbr = a.nbr;
 		if (need_k0) { EKG_CUDA(cudaEventRecord(m->ev_k0, st)); need_k0 = false; }
 		// the 8-corner stencil ("3D4") has its own packed-fp32x2 kernel; make sure the table is what it hard-codes
@@ -1028,8 +1073,9 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 			for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
 				ma.lead0 = lead0;
 				const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
-				if (corners && nl <= 2) ecg_moment_corners_kernel<1><<<grid, 256, 0, st>>>(ma);
-				else if (corners) ecg_moment_corners_kernel<2><<<grid, 256, 0, st>>>(ma);
+				if (corners && nl <= 2 && occ4) ecg_moment_corners_kernel<1, 4><<<grid, 256, 0, st>>>(ma);
+				else if (corners && nl <= 2) ecg_moment_corners_kernel<1, 3><<<grid, 256, 0, st>>>(ma);
+				else if (corners) ecg_moment_corners_kernel<2, 2><<<grid, 256, 0, st>>>(ma);
 				else if (nl <= 2) ecg_moment_kernel<2><<<grid, 256, 0, st>>>(ma);
 				else ecg_moment_kernel<4><<<grid, 256, 0, st>>>(ma);
 				EKG_CUDA(cudaGetLastError());

@@ -73,14 +73,19 @@ struct MomentArgs {
 	const uint32_t* pos;
 	const uint32_t* mask;
 	const float* at32;
+	const float4* vox;      // corners kernel: {z + 1, y + 1, +-(x + 1), activation time}; +: all 8 cube corners occupied
 	const Segment* segs;
 	const float* params;    // [B][n_layers][kParamStride]
 	const double* leads;    // [B][L][3]
 	double* mom;            // [n_segs][B][L][3]: sum G, sum G h1, sum G h2
 	int32_t B, L, n_layers, lead0;
 	int32_t vb_shift;       // log2 of the parameter vectors a CTA serves (threads = vectors x voxel lanes)
+	int32_t series;         // corners kernel: interior voxels by the series of the corner sum (ecg.cu, corner_series2)
 	NbrTable nbr;
 };
+
+// occupancy-mask bits of the 8 cube corners (the reference's "3D4" stencil) in the 26-neighbour cube list
+constexpr uint32_t kCornerMask = (1u << 0) | (1u << 2) | (1u << 6) | (1u << 8) | (1u << 17) | (1u << 19) | (1u << 23) | (1u << 25);
 
 struct AutoArgs {
 	const uint8_t* layer;   // padded dense grid, 0 = empty
@@ -179,6 +184,7 @@ struct ekg_model {
 	uint32_t* d_ecg_pidx = nullptr;  // padded index, for gathering activation times
 	double* d_at = nullptr;
 	float* d_at32 = nullptr;
+	float4* d_vox = nullptr;         // per-voxel record of the moment kernel (MomentArgs::vox), refreshed with d_at
 	std::vector<int64_t> layer_off;  // n_layers + 1 offsets into the ECG list
 
 	// per-call scratch (grown on demand)

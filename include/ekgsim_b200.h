@@ -80,6 +80,10 @@ enum {
 /* OR-ed into flags: record CUDA events around the ECG kernel launch(es) on the launching stream
  * so that ekg_last_kernel_ms() can report the dominant kernel's device time (bench.py roofline). */
 #define EKG_FLAG_TIME_KERNEL 0x100
+/* OR-ed into flags: the SEPARABLE path evaluates the stencil sum of interior voxels (all 8 corners of the "3D4" stencil
+ * occupied) by its harmonic series (csrc/ecg.cu, corner_series2); this flag makes it add the 8 corner terms like it does
+ * for boundary voxels -- slower and, in fp32, noisier; kept as the independent cross-check of the series. */
+#define EKG_FLAG_CORNER_SUM 0x200
 
 typedef struct ekg_model ekg_model;
 

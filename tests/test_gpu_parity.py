@@ -491,6 +491,48 @@ def test_separable_split_and_single_vector(gpu_model24, model24, model24_delay):
     assert rel_err(e3[1], ref) < ECG_TOL
 
 
+def test_separable_series_vs_corner_sum(gpu_model24, model24, model24_delay):
+    """The moment kernel evaluates the stencil sum of interior voxels (all 8 corners occupied, 86 % of model_24) by its
+    harmonic series; EKG_FLAG_CORNER_SUM adds the 8 corner terms instead.  Both must agree with the reference's ECG, the
+    series at least as closely as the sum (it has no cancellation), for a batch and for one vector alone."""
+    f = np.load(os.path.join(GOLDEN, "golden_eval_full.npz"))      # four full-length runs of the compiled reference
+    gpu_model24.set_activation(model24_delay)
+    k, leads, ref = f["layer_k"], f["leads_zyx"], f["ecg"]
+    ser = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=3)
+    assert gpu_model24.last_kernel_name == "ecg_moment_kernel"
+    csum = gpu_model24.simulate(k, leads, "3D4", 100.0, 1.0, 400.0, mode=3 | built.FLAG_CORNER_SUM)
+    e_ser, e_sum = rel_err(ser, ref), rel_err(csum, ref)
+    print("series %.3g, corner sum %.3g of peak" % (e_ser, e_sum))
+    assert e_ser < ECG_TOL and e_sum < ECG_TOL
+    assert e_ser < 2e-6
+    assert rel_err(ser, csum) < 3e-6
+    one = gpu_model24.simulate(k[1], leads[1], "3D4", 100.0, 1.0, 400.0, mode=3)      # VB = 1: lanes stride over voxels
+    assert rel_err(one[0], ref[1]) < 2e-6
+
+
+@pytest.mark.parametrize("scale", [0.6, 1.0, 3.0, 12.0])
+@pytest.mark.parametrize("n_leads", [2, 3])
+def test_separable_series_lead_distance(built, scale, n_leads):
+    """Leads next to the heart (closer than 32 voxels: the series is not used), at a few heart diameters (series for some
+    voxels, direct sum for others, mixed inside one packed lead pair) and far away (series everywhere; the remainder of
+    the cancelling corner terms is all that is left of an interior voxel) against the f64 oracle."""
+    layers, transfer, leads = synth.small_heart(seed=7, shape=(26, 30, 28), n_layers=5, hole=False)
+    centre = np.array(layers.shape, dtype=np.float64) / 2
+    leads = np.vstack([leads, [[40.0, 45.0, -30.0]]])[:n_leads]
+    leads = centre + (leads - centre) * scale
+    m = built.Model(layers, transfer)
+    delay, _ = m.activation()
+    layer_k = synth.layer_params(int((layers & 0xFFF).max()), seed=1, batch=3)
+    leads_b = np.stack([leads, leads + 1.25, leads - 0.5])
+    t_start = float(delay.max()) + 30.0
+    got = m.simulate(layer_k, leads_b, "3D4", t_start, 1.0, 50.0, mode=3)
+    assert m.last_kernel_name == "ecg_moment_kernel"
+    for b in range(3):
+        want = oracle.run_direct(layers, delay, layer_k[b], leads_b[b], "3D4", t_start, 1.0, 50.0)
+        assert rel_err(got[b], want) < ECG_TOL, (b, rel_err(got[b], want))
+    m.close()
+
+
 def run_sharded(ranks, slabs):
     """The exchange loop of ekgsim_b200.dist.sharded_activation with the planes handed over directly."""
     world = len(ranks)
