@@ -469,10 +469,15 @@ __global__ void __launch_bounds__(256, OCC) ecg_moment_corners_kernel(const Mome
 		d0[p][0] = d0[p][1] = d1[p][0] = d1[p][1] = d2[p][0] = d2[p][1] = 0.0;
 	}
 	int pending = 0;
-	for (int j = sg.begin + vl; j < sg.end; j += lanes) {
-		// one 16-byte record per voxel: bordered coordinates as floats, the sign of x = "all 8 corners occupied"
-		// (most of the model), the activation time; the occupancy mask is only read for boundary voxels
-		const float4 vx = __ldg(a.vox + j);
+	// one 16-byte record per voxel: bordered coordinates as floats, the sign of x = "all 8 corners occupied"
+	// (most of the model), the activation time; the occupancy mask is only read for boundary voxels.  The record of
+	// the next iteration is requested before this one is worked on: an iteration is one dependent chain, and with
+	// 24 warps per SM the load latency would otherwise be the larger part of it.
+	int j = sg.begin + vl;
+	float4 nxt = j < sg.end ? __ldg(a.vox + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+	for (; j < sg.end; j += lanes) {
+		const float4 vx = nxt;
+		if (j + lanes < sg.end) nxt = __ldg(a.vox + j + lanes);
 		const float da = vx.w - t0;
 		const float pz = vx.x, py = vx.y, px = fabsf(vx.z);
 		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));
@@ -1043,14 +1048,17 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	}
 
 	if (T_loop < T) {
-		// threads of a CTA = vb vectors x 256/vb voxel lanes; ~16 CTAs per SM in flight
+		// threads of a CTA = vb vectors x 256/vb voxel lanes
 		int vb_shift = 0;
 		while (vb_shift < 5 && (1 << vb_shift) < B) ++vb_shift;
 		const int64_t groups = (B + (1 << vb_shift) - 1) >> vb_shift;
 		const int64_t lanes = 256 >> vb_shift;
-		const int64_t want_segs = std::max<int64_t>(1, ((int64_t)m->sm_count * 16 + groups - 1) / groups);
+		// segments differ in cost by up to 3x (boundary voxels take the 9-term sum, the first and last layer are all
+		// boundary): ~48 CTAs per SM keep the tail of the launch short; at least 4 voxels per thread
+		static const int64_t ctas_per_sm = getenv("EKGSIM_B200_MOMENT_CTAS") ? std::max(1, atoi(getenv("EKGSIM_B200_MOMENT_CTAS"))) : 48;
+		const int64_t want_segs = std::max<int64_t>(1, ((int64_t)m->sm_count * ctas_per_sm + groups - 1) / groups);
 		int64_t seg_len = (m->n_ecg + want_segs - 1) / want_segs;
-		seg_len = std::max<int64_t>(lanes * 16, std::min<int64_t>(seg_len, (int64_t)1 << 20));
+		seg_len = std::max<int64_t>(lanes * 4, std::min<int64_t>(seg_len, (int64_t)1 << 20));
 		seg_len = (seg_len + 255) / 256 * 256;
 		if ((rc = build_moment_segments(m, seg_len, st))) return rc;
 		if (groups > 65535) return fail(EKG_E_UNSUPPORTED, "too many parameter vectors for one launch");

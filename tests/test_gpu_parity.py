@@ -491,7 +491,7 @@ def test_separable_split_and_single_vector(gpu_model24, model24, model24_delay):
     assert rel_err(e3[1], ref) < ECG_TOL
 
 
-def test_separable_series_vs_corner_sum(gpu_model24, model24, model24_delay):
+def test_separable_series_vs_corner_sum(built, gpu_model24, model24, model24_delay):
     """The moment kernel evaluates the stencil sum of interior voxels (all 8 corners occupied, 86 % of model_24) by its
     harmonic series; EKG_FLAG_CORNER_SUM adds the 8 corner terms instead.  Both must agree with the reference's ECG, the
     series at least as closely as the sum (it has no cancellation), for a batch and for one vector alone."""
