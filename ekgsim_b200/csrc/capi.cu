@@ -35,11 +35,17 @@ __global__ void gather_at_kernel(const double* __restrict__ time_pad, const uint
 	if (isinf(v)) v = 0.0;  // never reached -> excitationDelay stays 0 (simulator.cpp:219)
 	at[i] = v;
 	at32[i] = (float)v;
-	// the moment kernel's record: bordered coordinates (simulator.cpp:458-463 adds a border of one voxel), x negated unless
-	// all 8 cube corners are occupied
-	const uint32_t p = pos[i];
+	// the moment kernels' record: bordered coordinates (simulator.cpp:458-463 adds a border of one voxel); for a boundary
+	// voxel the occupancy of the corners (dz, dy, dx) = (-,-,-), (-,-,+), ... (+,+,+) in the low 8 mantissa bits of y, which
+	// are zero for an integer <= 2048 (interior voxels sit in segments of their own and keep a clean y)
+	const uint32_t p = pos[i], mk = mask[i];
+	const int corner_bit[8] = {0, 2, 6, 8, 17, 19, 23, 25};   // their positions in the 26-neighbour cube list (make_nbr_table)
+	uint32_t c8 = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) c8 |= ((mk >> corner_bit[k]) & 1u) << k;
 	const float x = (float)((p & 0x7ffu) + 1u);
-	vox[i] = make_float4((float)((p >> 22) + 1u), (float)(((p >> 11) & 0x7ffu) + 1u), (mask[i] & kCornerMask) == kCornerMask ? x : -x, (float)v);
+	const float y = __uint_as_float(__float_as_uint((float)(((p >> 11) & 0x7ffu) + 1u)) | (c8 == 0xffu ? 0u : c8));
+	vox[i] = make_float4((float)((p >> 22) + 1u), y, x, (float)v);
 }
 
 // Host -> device upload that is COMPLETE on return.  A plain cudaMemcpy from pageable memory may return
@@ -58,7 +64,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
+	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_near, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -68,17 +74,11 @@ static void free_model(ekg_model* m) {
 	delete m;
 }
 
-// (re)build the layer-sorted ECG voxel list for z in [z0, z1)
+// (re)build the ECG voxel list for z in [z0, z1): sorted by layer; inside a layer first the interior voxels (all 8 cube
+// corners occupied -- the moment kernels treat them by a series, ecg.cu), then the boundary voxels, raster order in both parts
 static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 	const int64_t Y = m->Y, X = m->X;
 	const int nl = m->n_layers;
-	std::vector<int64_t> cnt(nl + 2, 0);
-	for (int64_t z = z0; z < z1; ++z) for (int64_t i = z * Y * X; i < (z + 1) * Y * X; ++i) if (m->h_layer[i]) ++cnt[m->h_layer[i]];
-	m->layer_off.assign(nl + 1, 0);
-	for (int l = 1; l <= nl; ++l) m->layer_off[l] = m->layer_off[l - 1] + cnt[l];
-	const int64_t n = m->layer_off[nl];
-	std::vector<uint32_t> pos(n), mask(n), pidx(n);
-	std::vector<int64_t> cur(m->layer_off.begin(), m->layer_off.end());
 
 	// padded layer map for bounds-free neighbour tests
 	std::vector<uint8_t> lp((size_t)(m->pZ * m->pY * m->pX), 0);
@@ -88,18 +88,46 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 	make_nbr_table(EKG_NBHD_3D8, &cube);
 	int64_t off[kMaxNbr];
 	for (int k = 0; k < cube.n; ++k) off[k] = (cube.dz[k] * m->pY + cube.dy[k]) * m->pX + cube.dx[k];
+	auto cube_mask = [&](int64_t p) {
+		uint32_t mk = 0;
+		for (int k = 0; k < cube.n; ++k) if (lp[p - off[k]]) mk |= 1u << k;  // neighbour = index - dif (simulator.cpp:514)
+		return mk;
+	};
 
+	// pass 1 (raster order): occupancy mask of every voxel of the slab, voxels per (layer, interior | boundary)
+	std::vector<uint32_t> r_pos, r_mask, r_pidx;
+	std::vector<uint8_t> r_layer;
+	std::vector<int64_t> cnt_in(nl + 2, 0), cnt_bd(nl + 2, 0);
 	for (int64_t z = z0; z < z1; ++z) for (int64_t y = 0; y < Y; ++y) for (int64_t x = 0; x < X; ++x) {
 		const uint8_t l = m->h_layer[(z * Y + y) * X + x];
 		if (!l) continue;
 		const int64_t p = pad_index(m, z, y, x);
-		uint32_t mk = 0;
-		for (int k = 0; k < cube.n; ++k) if (lp[p - off[k]]) mk |= 1u << k;  // neighbour = index - dif (simulator.cpp:514)
-		const int64_t j = cur[l - 1]++;
-		pos[j] = (uint32_t)x | ((uint32_t)y << 11) | ((uint32_t)z << 22);
-		mask[j] = mk;
-		pidx[j] = (uint32_t)p;
+		const uint32_t mk = cube_mask(p);
+		r_pos.push_back((uint32_t)x | ((uint32_t)y << 11) | ((uint32_t)z << 22));
+		r_mask.push_back(mk);
+		r_pidx.push_back((uint32_t)p);
+		r_layer.push_back(l);
+		if ((mk & kCornerMask) == kCornerMask) ++cnt_in[l]; else ++cnt_bd[l];
 	}
+	m->layer_off.assign(nl + 1, 0);
+	m->interior_cnt.assign(nl + 1, 0);
+	for (int l = 1; l <= nl; ++l) {
+		m->layer_off[l] = m->layer_off[l - 1] + cnt_in[l] + cnt_bd[l];
+		m->interior_cnt[l - 1] = cnt_in[l];
+	}
+	const int64_t n = m->layer_off[nl];
+	std::vector<uint32_t> pos(n), mask(n), pidx(n);
+	std::vector<int64_t> cur_in(nl + 1), cur_bd(nl + 1);
+	for (int l = 0; l < nl; ++l) { cur_in[l] = m->layer_off[l]; cur_bd[l] = m->layer_off[l] + m->interior_cnt[l]; }
+	// pass 2: stable scatter into the (layer, kind) ranges
+	for (int64_t i = 0; i < n; ++i) {
+		const int l = r_layer[i];
+		const int64_t j = ((r_mask[i] & kCornerMask) == kCornerMask) ? cur_in[l - 1]++ : cur_bd[l - 1]++;
+		pos[j] = r_pos[i];
+		mask[j] = r_mask[i];
+		pidx[j] = r_pidx[i];
+	}
+	std::vector<uint32_t>().swap(r_pos); std::vector<uint32_t>().swap(r_mask); std::vector<uint32_t>().swap(r_pidx); std::vector<uint8_t>().swap(r_layer);
 
 	for (void* p : {(void*)m->d_pos, (void*)m->d_mask, (void*)m->d_ecg_pidx, (void*)m->d_at, (void*)m->d_at32, (void*)m->d_vox}) if (p) cudaFree(p);
 	m->d_pos = m->d_mask = m->d_ecg_pidx = nullptr; m->d_at = nullptr; m->d_at32 = nullptr; m->d_vox = nullptr;

@@ -404,7 +404,7 @@ __device__ __forceinline__ f2 inv_cube2(f2 sq) {
 // leave 1e-4..1e-2 relative noise on g (it averages out over the model, which is why the direct sum passes its
 // tolerance); the series has no cancellation (1e-6 relative in fp32), a truncation error below 5e-8 relative for
 // |q| >= 32 voxels (3e-8 measured at 35, falling like |q|^-6) and costs 28 packed operations + 2 MUFU per lead
-// pair instead of ~110 + 16.  Leads closer than kSeriesMinR2 take the direct sum.
+// pair instead of ~110 + 16.  Segments with a lead closer than sqrt(kSeriesMinR2) take the direct sum.
 constexpr float kSeriesMinR2 = 1024.f;
 __device__ __forceinline__ f2 c2(float c) { return mk2(c, c); }
 __device__ __forceinline__ f2 corner_series2(f2 qz, f2 qy, f2 qx, f2 r2) {
@@ -421,29 +421,49 @@ __device__ __forceinline__ f2 corner_series2(f2 qz, f2 qy, f2 qx, f2 r2) {
 	return mul2(mul2(mul2(u, u), y), fma2(fma2(a8, u, a6), u, a4));
 }
 
-// occupancy-mask bits of the 8 cube corners in the order (dz, dy, dx) = (-,-,-), (-,-,+), ... (+,+,+): their
-// positions in the 26-neighbour cube list (make_nbr_table; checked on the host before this kernel is chosen)
-__device__ constexpr int kCornerBit[8] = {0, 2, 6, 8, 17, 19, 23, 25};
+// ---- the moment kernels of the reference's default stencil "3D4" (= the 8 cube corners, sim_lib.h:133-141) ----------
+// Two leads ride in the two lanes of packed fp32x2 instructions (NP = lead pairs per pass).  Every layer's part of the
+// voxel list starts with its interior voxels (capi.cu, build_ecg_list) and the moment segments do not mix the two kinds:
+//   ecg_moment_interior_kernel  interior segments by the series above: one short dependent chain per (voxel, vector),
+//                               48 registers.  A CTA that meets a lead closer than sqrt(kSeriesMinR2) raises its
+//                               near_flag and stores nothing;
+//   ecg_moment_corners_kernel   boundary segments -- and the flagged (or, with EKG_FLAG_CORNER_SUM, all) interior segments --
+//                               by the direct sum over the occupied corners + the centre term.
+// Both: threads of a CTA = VB parameter vectors x 256/VB voxel lanes; one 16-byte record per voxel (capi.cu,
+// gather_at_kernel), the record of the next iteration requested before this one is worked on (an iteration is one
+// dependent chain; the load latency would otherwise be the larger part of it); fp32 sums over 16 voxels in registers,
+// their f64 totals in the thread's own column of s_red ([row][thread], row = lead * 3 + moment), voxel lanes reduced in
+// a fixed order -> deterministic.
+template <int NP>
+struct MomentAcc {
+	f2 f0[NP], f1[NP], f2s[NP];
+	__device__ __forceinline__ void init(double* s_red) {
+#pragma unroll
+		for (int p = 0; p < NP; ++p) f0[p] = f1[p] = f2s[p] = mk2(0.f, 0.f);
+#pragma unroll
+		for (int r = 0; r < NP * 6; ++r) s_red[r * 256 + threadIdx.x] = 0.0;
+	}
+	// G = -g
+	__device__ __forceinline__ void add(int p, f2 g, float h1, float h2) {
+		f0[p] = sub2(f0[p], g);
+		f1[p] = fma2(g, mk2(-h1, -h1), f1[p]);
+		f2s[p] = fma2(g, mk2(-h2, -h2), f2s[p]);
+	}
+	__device__ __forceinline__ void fold(double* s_red) {
+#pragma unroll
+		for (int p = 0; p < NP; ++p) {
+			double* o = s_red + (p * 6) * 256 + threadIdx.x;
+			o[0 * 256] += (double)lo2(f0[p]); o[1 * 256] += (double)lo2(f1[p]); o[2 * 256] += (double)lo2(f2s[p]);
+			o[3 * 256] += (double)hi2(f0[p]); o[4 * 256] += (double)hi2(f1[p]); o[5 * 256] += (double)hi2(f2s[p]);
+			f0[p] = f1[p] = f2s[p] = mk2(0.f, 0.f);
+		}
+	}
+};
 
-// The moment kernel specialised for the reference's default stencil "3D4" (= the 8 cube corners, sim_lib.h:133-141),
-// two leads per packed fp32x2 lane pair.  With d = (+-1, +-1, +-1) the neighbour offsets fold into six per-axis
-// terms p = r + 1, m = 1 - r: |r + d|^2 = (p|m)_z^2 + (p|m)_y^2 + (p|m)_x^2 and d . (r + d) = (p|m)_z + (p|m)_y + (p|m)_x,
-// 4 packed instructions + 2 MUFU + 7 packed for the inverse cube per corner and lead pair (the generic loop
-// issues ~35 scalar instructions per corner and lead).  NP = lead pairs per pass.
-// OCC = CTAs per SM the register budget is cut for (NP = 1: 3 -> 80 registers, nothing spilled; 4 -> 64 registers, the
-// loop invariants of the boundary path spill).
-template <int NP, int OCC>
-__global__ void __launch_bounds__(256, OCC) ecg_moment_corners_kernel(const MomentArgs a) {
-	__shared__ double s_red[256 * NP * 6];
-	const Segment sg = a.segs[blockIdx.x];
-	const int vb = 1 << a.vb_shift;
-	const int vs = threadIdx.x & (vb - 1), vl = threadIdx.x >> a.vb_shift, lanes = 256 >> a.vb_shift;
-	const int b = blockIdx.y * vb + vs;
-	const int bb = min(b, a.B - 1);
-
-	// lead coordinates (z, y, x) of the two leads of a pair, rounded to fp32: a lead displaced by < 2^-17 voxel for ALL
-	// voxels alike (the time-loop kernels carry a lo part as well; it changes the ECG by ~1e-7 of its peak)
-	f2 lh[NP][3];
+// lead coordinates (z, y, x) of the two leads of a pair, rounded to fp32: a lead displaced by < 2^-17 voxel for ALL
+// voxels alike (the time-loop kernels carry a lo part as well; it changes the ECG by ~1e-7 of its peak)
+template <int NP>
+__device__ __forceinline__ void load_lead_pairs(const MomentArgs& a, int bb, f2 (&lh)[NP][3]) {
 #pragma unroll
 	for (int p = 0; p < NP; ++p)
 #pragma unroll
@@ -456,56 +476,113 @@ __global__ void __launch_bounds__(256, OCC) ecg_moment_corners_kernel(const Mome
 			}
 			lh[p][c] = mk2(h[0], h[1]);
 		}
+}
+
+// after the loop: thread (vector slot, lead, moment) adds the voxel lanes in lane order
+template <int NP>
+__device__ __forceinline__ void store_moments(const MomentArgs& a, const double* s_red) {
+	constexpr int NL = NP * 2;
+	const int vb = 1 << a.vb_shift, lanes = 256 >> a.vb_shift;
+	for (int o = threadIdx.x; o < vb * NL * 3; o += 256) {
+		const int ovs = o / (NL * 3), r = o - ovs * (NL * 3);
+		const int ob = blockIdx.y * vb + ovs, lead = a.lead0 + r / 3;
+		if (ob >= a.B || lead >= a.L) continue;
+		double s = 0.0;
+		for (int lane = 0; lane < lanes; ++lane) s += s_red[r * 256 + (lane << a.vb_shift) + ovs];
+		a.mom[(((int64_t)blockIdx.x * a.B + ob) * a.L + lead) * 3 + r % 3] = s;
+	}
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256, NP == 1 ? 4 : 3) ecg_moment_interior_kernel(const MomentArgs a) {
+	__shared__ double s_red[256 * NP * 6];
+	const Segment sg = a.segs[blockIdx.x];
+	if (sg.kind != kSegInterior) return;
+	const int vb = 1 << a.vb_shift;
+	const int vs = threadIdx.x & (vb - 1), vl = threadIdx.x >> a.vb_shift, lanes = 256 >> a.vb_shift;
+	const int bb = min(blockIdx.y * vb + vs, a.B - 1);   // surplus vector slots shadow the last vector, their sums are dropped
+	f2 lh[NP][3];
+	load_lead_pairs<NP>(a, bb, lh);
+	const float* Pv = a.params + ((int64_t)bb * a.n_layers + (sg.layer - 1)) * kParamStride;
+	const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
+	const float v45 = -(v4 + v5), nv5 = -v5;
+	MomentAcc<NP> acc;
+	acc.init(s_red);
+	float r2_min = 3.0e38f;
+	int pending = 0;
+	const float4* pv = a.vox + (sg.begin + vl);
+	const float4* const pv_end = a.vox + sg.end;
+	float4 nxt = pv < pv_end ? __ldg(pv) : make_float4(0.f, 0.f, 0.f, 0.f);
+	for (; pv < pv_end; pv += lanes) {
+		const float4 vx = nxt;
+		if (pv + lanes < pv_end) nxt = __ldg(pv + lanes);
+		const float da = vx.w - t0;
+		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));   // same clamp as the HOISTED kernel and its table
+		const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
+		const f2 PZ = mk2(vx.x, vx.x), PY = mk2(vx.y, vx.y), PX = mk2(vx.z, vx.z);
+#pragma unroll
+		for (int p = 0; p < NP; ++p) {
+			const f2 rz = sub2(lh[p][0], PZ), ry = sub2(lh[p][1], PY), rx = sub2(lh[p][2], PX);
+			const f2 qz = mul2(rz, rz), qy = mul2(ry, ry), qx = mul2(rx, rx);
+			const f2 r2 = add2(add2(qz, qy), qx);
+			r2_min = fminf(r2_min, fminf(lo2(r2), hi2(r2)));
+			acc.add(p, corner_series2(qz, qy, qx, r2), h1, h2);
+		}
+		if (++pending == 16) {
+			pending = 0;
+			acc.fold(s_red);
+		}
+	}
+	acc.fold(s_red);
+	// a lead inside the series' validity radius (NaN counts as near): leave this (segment, vector group) to the direct sum
+	const int near = __syncthreads_or(!(r2_min >= kSeriesMinR2));
+	if (threadIdx.x == 0) a.near_flag[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = near;
+	if (near) return;
+	store_moments<NP>(a, s_red);
+}
+
+// The direct sum.  With d = (+-1, +-1, +-1) the neighbour offsets fold into six per-axis terms p = r + 1, m = 1 - r:
+// |r + d|^2 = (p|m)_z^2 + (p|m)_y^2 + (p|m)_x^2 and d . (r + d) = (p|m)_z + (p|m)_y + (p|m)_x, 4 packed instructions + 2 MUFU +
+// 7 packed for the inverse cube per corner and lead pair (the generic loop issues ~35 scalar instructions per corner and lead).
+template <int NP>
+__global__ void __launch_bounds__(256, NP == 1 ? 3 : 2) ecg_moment_corners_kernel(const MomentArgs a) {
+	__shared__ double s_red[256 * NP * 6];
+	const Segment sg = a.segs[blockIdx.x];
+	const bool interior = sg.kind == kSegInterior;   // all 8 corners of every voxel occupied: no centre term, no per-corner tests
+	if (interior && !a.force_sum && !a.near_flag[(int64_t)blockIdx.y * gridDim.x + blockIdx.x]) return;
+	const int vb = 1 << a.vb_shift;
+	const int vs = threadIdx.x & (vb - 1), vl = threadIdx.x >> a.vb_shift, lanes = 256 >> a.vb_shift;
+	const int bb = min(blockIdx.y * vb + vs, a.B - 1);
+	f2 lh[NP][3];
+	load_lead_pairs<NP>(a, bb, lh);
 	const float* Pv = a.params + ((int64_t)bb * a.n_layers + (sg.layer - 1)) * kParamStride;
 	const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
 	const float v45 = -(v4 + v5), nv5 = -v5;
 	const f2 one = mk2(1.f, 1.f);
-
-	f2 f0[NP], f1[NP], f2s[NP];
-	double d0[NP][2], d1[NP][2], d2[NP][2];
-#pragma unroll
-	for (int p = 0; p < NP; ++p) {
-		f0[p] = f1[p] = f2s[p] = mk2(0.f, 0.f);
-		d0[p][0] = d0[p][1] = d1[p][0] = d1[p][1] = d2[p][0] = d2[p][1] = 0.0;
-	}
+	MomentAcc<NP> acc;
+	acc.init(s_red);
 	int pending = 0;
-	// one 16-byte record per voxel: bordered coordinates as floats, the sign of x = "all 8 corners occupied"
-	// (most of the model), the activation time; the occupancy mask is only read for boundary voxels.  The record of
-	// the next iteration is requested before this one is worked on: an iteration is one dependent chain, and with
-	// 24 warps per SM the load latency would otherwise be the larger part of it.
-	int j = sg.begin + vl;
-	float4 nxt = j < sg.end ? __ldg(a.vox + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-	for (; j < sg.end; j += lanes) {
+	const float4* pv = a.vox + (sg.begin + vl);
+	const float4* const pv_end = a.vox + sg.end;
+	float4 nxt = pv < pv_end ? __ldg(pv) : make_float4(0.f, 0.f, 0.f, 0.f);
+	for (; pv < pv_end; pv += lanes) {
 		const float4 vx = nxt;
-		if (j + lanes < sg.end) nxt = __ldg(a.vox + j + lanes);
+		if (pv + lanes < pv_end) nxt = __ldg(pv + lanes);
 		const float da = vx.w - t0;
-		const float pz = vx.x, py = vx.y, px = fabsf(vx.z);
+		// boundary voxels carry the occupancy of their corners, order (dz, dy, dx) = (-,-,-), (-,-,+), ... (+,+,+), in the low
+		// 8 mantissa bits of y (zero for an integer <= 2048)
+		const uint32_t yb = __float_as_uint(vx.y);
+		const uint32_t mask = interior ? 0xffu : (yb & 0xffu);
+		const float pz = vx.x, py = __uint_as_float(yb & ~0xffu), px = vx.z;
 		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));
 		const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
-		constexpr uint32_t kAll = kCornerMask;
-		constexpr uint32_t kZp = (1u << 17) | (1u << 19) | (1u << 23) | (1u << 25);
-		constexpr uint32_t kYp = (1u << 6) | (1u << 8) | (1u << 23) | (1u << 25);
-		constexpr uint32_t kXp = (1u << 2) | (1u << 8) | (1u << 19) | (1u << 25);
-		const bool interior = vx.z > 0.f;
-		const uint32_t mask = interior ? kAll : __ldg(a.mask + j);
+		constexpr uint32_t kZp = 0xf0u, kYp = 0xccu, kXp = 0xaau;   // corners with dz (dy, dx) = +1
 		const f2 PZ = mk2(pz, pz), PY = mk2(py, py), PX = mk2(px, px);
 #pragma unroll
 		for (int p = 0; p < NP; ++p) {
 			const f2 rz = sub2(lh[p][0], PZ);
 			const f2 ry = sub2(lh[p][1], PY);
 			const f2 rx = sub2(lh[p][2], PX);
-			if (interior && a.series) {
-				// all 8 corners occupied (most of the model): the series of the corner sum, unless a lead is close
-				const f2 qz = mul2(rz, rz), qy = mul2(ry, ry), qx = mul2(rx, rx);
-				const f2 r2 = add2(add2(qz, qy), qx);
-				if (fminf(lo2(r2), hi2(r2)) >= kSeriesMinR2) {
-					const f2 g = corner_series2(qz, qy, qx, r2);
-					f0[p] = sub2(f0[p], g);
-					f1[p] = fma2(g, mk2(-h1, -h1), f1[p]);
-					f2s[p] = fma2(g, mk2(-h2, -h2), f2s[p]);
-					continue;
-				}
-			}
 			const f2 zt[2] = {sub2(one, rz), add2(rz, one)};   // [0]: d = -1 -> -(r - 1),  [1]: d = +1 -> r + 1
 			const f2 yt[2] = {sub2(one, ry), add2(ry, one)};
 			const f2 xt[2] = {sub2(one, rx), add2(rx, one)};
@@ -521,19 +598,19 @@ __global__ void __launch_bounds__(256, OCC) ecg_moment_corners_kernel(const Mome
 					const f2 dt_zy = add2(zt[zy >> 1], yt[zy & 1]);
 #pragma unroll
 					for (int x = 0; x < 2; ++x) {
-						if (ALL || (mask & (1u << kCornerBit[zy * 2 + x])))
+						if (ALL || (mask & (1u << (zy * 2 + x))))
 							g = fma2(add2(dt_zy, xt[x]), inv_cube2(add2(sq_zy, xq[x])), g);
 					}
 				}
 			};
 			if (interior) {
-				// the offsets of all 8 corners add up to zero: no centre term (and no per-corner tests)
+				// the offsets of all 8 corners add up to zero: no centre term
 				corners(std::true_type{});
 			} else {
 				corners(std::false_type{});
 				// S = sum of the offsets of the occupied corners, per axis: (# with +1) - (# with -1), as floats via the
 				// 2^23 trick (values -8..8, no I2F)
-				const int n_occ = __popc(mask & kAll);
+				const int n_occ = __popc(mask);
 				const float szf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kZp) - n_occ)) - 8388616.f;
 				const float syf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kYp) - n_occ)) - 8388616.f;
 				const float sxf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kXp) - n_occ)) - 8388616.f;
@@ -541,41 +618,16 @@ __global__ void __launch_bounds__(256, OCC) ecg_moment_corners_kernel(const Mome
 				const f2 sdot = fma2(mk2(szf, szf), rz, fma2(mk2(syf, syf), ry, mul2(mk2(sxf, sxf), rx)));
 				g = fma2(sdot, inv_cube2(sqc), g);
 			}
-			// G = -g
-			f0[p] = sub2(f0[p], g);
-			f1[p] = fma2(g, mk2(-h1, -h1), f1[p]);
-			f2s[p] = fma2(g, mk2(-h2, -h2), f2s[p]);
+			acc.add(p, g, h1, h2);
 		}
 		if (++pending == 16) {
 			pending = 0;
-#pragma unroll
-			for (int p = 0; p < NP; ++p) {
-				d0[p][0] += (double)lo2(f0[p]); d0[p][1] += (double)hi2(f0[p]);
-				d1[p][0] += (double)lo2(f1[p]); d1[p][1] += (double)hi2(f1[p]);
-				d2[p][0] += (double)lo2(f2s[p]); d2[p][1] += (double)hi2(f2s[p]);
-				f0[p] = f1[p] = f2s[p] = mk2(0.f, 0.f);
-			}
+			acc.fold(s_red);
 		}
 	}
-#pragma unroll
-	for (int p = 0; p < NP; ++p)
-#pragma unroll
-		for (int e = 0; e < 2; ++e) {
-			double* o = s_red + (threadIdx.x * NP * 2 + p * 2 + e) * 3;
-			o[0] = d0[p][e] + (double)(e ? hi2(f0[p]) : lo2(f0[p]));
-			o[1] = d1[p][e] + (double)(e ? hi2(f1[p]) : lo2(f1[p]));
-			o[2] = d2[p][e] + (double)(e ? hi2(f2s[p]) : lo2(f2s[p]));
-		}
+	acc.fold(s_red);
 	__syncthreads();
-	constexpr int NL = NP * 2;
-	for (int o = threadIdx.x; o < vb * NL * 3; o += 256) {
-		const int ovs = o / (NL * 3), r = o - ovs * (NL * 3);
-		const int ob = blockIdx.y * vb + ovs, lead = a.lead0 + r / 3;
-		if (ob >= a.B || lead >= a.L) continue;
-		double s = 0.0;
-		for (int lane = 0; lane < lanes; ++lane) s += s_red[((lane << a.vb_shift) + ovs) * (NL * 3) + r];
-		a.mom[(((int64_t)blockIdx.x * a.B + ob) * a.L + lead) * 3 + r % 3] = s;
-	}
+	store_moments<NP>(a, s_red);
 }
 
 // ECG[b][l][t] for the samples t >= t_off from the moments: one CTA per (vector, block of 128 samples).
@@ -813,7 +865,7 @@ static int build_segments(ekg_model* m, int64_t seg_len, cudaStream_t st) {
 			s.begin = (int32_t)(b0 + cnt * p / pieces);
 			s.end = (int32_t)(b0 + cnt * (p + 1) / pieces);
 			s.layer = l;
-			s.pad = 0;
+			s.kind = 0;
 			if (s.end > s.begin) segs.push_back(s);
 		}
 	}
@@ -841,19 +893,25 @@ static int build_moment_segments(ekg_model* m, int64_t seg_len, cudaStream_t st)
 	if (m->mseg_len == seg_len && m->n_msegs > 0) return EKG_OK;
 	std::vector<Segment> segs;
 	std::vector<int32_t> first(m->n_layers + 1, 0);
-	for (int l = 1; l <= m->n_layers; ++l) {
-		first[l - 1] = (int32_t)segs.size();
-		const int64_t b0 = m->layer_off[l - 1], cnt = m->layer_off[l] - b0;
-		if (cnt <= 0) continue;
-		const int64_t pieces = (cnt + seg_len - 1) / seg_len;
+	// pieces of one kind: interior voxels (all 8 cube corners occupied; they lead every layer's range of the list) and
+	// boundary voxels never share a segment.  A boundary voxel costs ~3x an interior one: half-length pieces.
+	auto cut = [&](int64_t b0, int64_t cnt, int64_t len, int l, int32_t kind) {
+		if (cnt <= 0) return;
+		const int64_t pieces = (cnt + len - 1) / len;
 		for (int64_t p = 0; p < pieces; ++p) {
 			Segment sg;
 			sg.begin = (int32_t)(b0 + cnt * p / pieces);
 			sg.end = (int32_t)(b0 + cnt * (p + 1) / pieces);
 			sg.layer = l;
-			sg.pad = 0;
+			sg.kind = kind;
 			if (sg.end > sg.begin) segs.push_back(sg);
 		}
+	};
+	for (int l = 1; l <= m->n_layers; ++l) {
+		first[l - 1] = (int32_t)segs.size();
+		const int64_t b0 = m->layer_off[l - 1], cnt = m->layer_off[l] - b0, n_in = m->interior_cnt[l - 1];
+		cut(b0, n_in, seg_len, l, kSegInterior);
+		cut(b0 + n_in, cnt - n_in, std::max<int64_t>(seg_len / 2, 1), l, 0);
 	}
 	first[m->n_layers] = (int32_t)segs.size();
 	int rc;
@@ -1063,15 +1121,15 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		if ((rc = build_moment_segments(m, seg_len, st))) return rc;
 		if (groups > 65535) return fail(EKG_E_UNSUPPORTED, "too many parameter vectors for one launch");
 		if ((rc = ensure(&m->d_mom, &m->mom_cap, std::max<int64_t>(m->n_msegs, 1) * B * L * 3))) return rc;
+		if ((rc = ensure(&m->d_near, &m->near_cap, std::max<int64_t>(m->n_msegs, 1) * groups))) return rc;
 		MomentArgs ma{};
 		ma.pos = m->d_pos; ma.mask = m->d_mask; ma.at32 = m->d_at32; ma.segs = m->d_msegs; ma.params = m->d_params; ma.leads = d_leads;
-		ma.vox = m->d_vox;
+		ma.vox = m->d_vox; ma.near_flag = m->d_near;
 		// EKG_FLAG_CORNER_SUM: interior voxels through the direct corner sum as well (the cross-check of the series)
-		static const bool occ4 = getenv("EKGSIM_B200_MOMENT_OCC") && atoi(getenv("EKGSIM_B200_MOMENT_OCC")) == 4;
-		ma.series = (flags & EKG_FLAG_CORNER_SUM) ? 0 : 1;
+		ma.force_sum = (flags & EKG_FLAG_CORNER_SUM) ? 1 : 0;
 		ma.mom = m->d_mom; ma.B = (int32_t)B; ma.L = (int32_t)L; ma.n_layers = m->n_layers; ma.vb_shift = vb_shift; ma.nbr = a.nbr;
 		if (need_k0) { EKG_CUDA(cudaEventRecord(m->ev_k0, st)); need_k0 = false; }
-		// the 8-corner stencil ("3D4") has its own packed-fp32x2 kernel; make sure the table is what it hard-codes
+		// the 8-corner stencil ("3D4") has its own packed-fp32x2 kernels; make sure the table is what they hard-code
 		static const int corner_bit[8] = {0, 2, 6, 8, 17, 19, 23, 25};
 		bool corners = a.nbr.n == 8 && getenv("EKGSIM_B200_GENERIC_MOMENTS") == nullptr;
 		for (int k = 0; corners && k < 8; ++k)
@@ -1081,9 +1139,18 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 			for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
 				ma.lead0 = lead0;
 				const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
-				if (corners && nl <= 2 && occ4) ecg_moment_corners_kernel<1, 4><<<grid, 256, 0, st>>>(ma);
-				else if (corners && nl <= 2) ecg_moment_corners_kernel<1, 3><<<grid, 256, 0, st>>>(ma);
-				else if (corners) ecg_moment_corners_kernel<2, 2><<<grid, 256, 0, st>>>(ma);
+				if (corners) {
+					// interior segments by the series (raising near_flag where a lead is too close), then the boundary
+					// segments and whatever was flagged by the direct sum
+					if (!ma.force_sum) {
+						if (nl <= 2) ecg_moment_interior_kernel<1><<<grid, 256, 0, st>>>(ma);
+						else ecg_moment_interior_kernel<2><<<grid, 256, 0, st>>>(ma);
+						EKG_CUDA(cudaGetLastError());
+						++m->last_launches;
+					}
+					if (nl <= 2) ecg_moment_corners_kernel<1><<<grid, 256, 0, st>>>(ma);
+					else ecg_moment_corners_kernel<2><<<grid, 256, 0, st>>>(ma);
+				}
 				else if (nl <= 2) ecg_moment_kernel<2><<<grid, 256, 0, st>>>(ma);
 				else ecg_moment_kernel<4><<<grid, 256, 0, st>>>(ma);
 				EKG_CUDA(cudaGetLastError());

@@ -43,8 +43,9 @@ struct NbrTable {
 struct Segment {
 	int32_t begin, end;  // [begin, end) into the ECG voxel list
 	int32_t layer;       // 1-based layer number
-	int32_t pad;
+	int32_t kind;        // moment segments: kSegInterior = every voxel has all 8 cube corners occupied; else 0
 };
+constexpr int32_t kSegInterior = 1;
 
 // A run of consecutive (vector b, sample t) pairs, p = b*T + t.
 struct PairTile {
@@ -73,14 +74,15 @@ struct MomentArgs {
 	const uint32_t* pos;
 	const uint32_t* mask;
 	const float* at32;
-	const float4* vox;      // corners kernel: {z + 1, y + 1, +-(x + 1), activation time}; +: all 8 cube corners occupied
+	const float4* vox;      // corners kernels: {z + 1, y + 1 | corner bits, x + 1, activation time} (capi.cu, gather_at_kernel)
+	int32_t* near_flag;     // [groups][n_segs] set by the interior kernel: a lead is too close for the series, redo by direct sum
 	const Segment* segs;
 	const float* params;    // [B][n_layers][kParamStride]
 	const double* leads;    // [B][L][3]
 	double* mom;            // [n_segs][B][L][3]: sum G, sum G h1, sum G h2
 	int32_t B, L, n_layers, lead0;
 	int32_t vb_shift;       // log2 of the parameter vectors a CTA serves (threads = vectors x voxel lanes)
-	int32_t series;         // corners kernel: interior voxels by the series of the corner sum (ecg.cu, corner_series2)
+	int32_t force_sum;      // corners kernel: take every interior segment too (EKG_FLAG_CORNER_SUM), not only the flagged ones
 	NbrTable nbr;
 };
 
@@ -186,6 +188,8 @@ struct ekg_model {
 	float* d_at32 = nullptr;
 	float4* d_vox = nullptr;         // per-voxel record of the moment kernel (MomentArgs::vox), refreshed with d_at
 	std::vector<int64_t> layer_off;  // n_layers + 1 offsets into the ECG list
+	std::vector<int64_t> interior_cnt;  // per layer: its range of the list starts with this many interior voxels (all 8 cube
+	                                    // corners occupied), the boundary voxels follow; raster order inside both parts
 
 	// per-call scratch (grown on demand)
 	ekg::Segment* d_segs = nullptr;  int64_t segs_cap = 0;  int64_t n_segs = 0;  int64_t seg_len = 0;
@@ -194,6 +198,7 @@ struct ekg_model {
 	ekg::Segment* d_msegs = nullptr; int64_t msegs_cap = 0;  int64_t n_msegs = 0;  int64_t mseg_len = 0;
 	int32_t* d_mseg_first = nullptr; int64_t mseg_first_cap = 0;   // first segment of every layer, n_layers + 1 entries
 	double* d_mom = nullptr;         int64_t mom_cap = 0;          // [n_msegs][B][L][3] moments
+	int32_t* d_near = nullptr;       int64_t near_cap = 0;         // MomentArgs::near_flag
 	int* d_k1min = nullptr;                                        // [2] float bits of min k1 / max decay rate over (vector, layer), by ecg_params_kernel
 	float* d_params = nullptr;       int64_t params_cap = 0;
 	float* d_ftab = nullptr;         int64_t ftab_cap = 0;

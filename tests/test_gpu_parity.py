@@ -524,12 +524,21 @@ def test_separable_series_lead_distance(built, scale, n_leads):
     delay, _ = m.activation()
     layer_k = synth.layer_params(int((layers & 0xFFF).max()), seed=1, batch=3)
     leads_b = np.stack([leads, leads + 1.25, leads - 0.5])
-    t_start = float(delay.max()) + 30.0
-    got = m.simulate(layer_k, leads_b, "3D4", t_start, 1.0, 50.0, mode=3)
-    assert m.last_kernel_name == "ecg_moment_kernel"
+    # the whole trace: the QRS samples run through the time loop, everything after the last depolarisation through the
+    # moments.  The tolerance is relative to the peak lead amplitude of the trace (north_star); on the plateau alone the
+    # ECG all but vanishes (a uniform V gives exactly 0), so a window without the QRS complex would measure nothing.
+    got = m.simulate(layer_k, leads_b, "3D4", 0.0, 2.0, 400.0, mode=3)
+    assert m.last_kernel_name == "ecg_kernel<HOISTED> + ecg_moment_kernel"
+    csum = m.simulate(layer_k, leads_b, "3D4", 0.0, 2.0, 400.0, mode=3 | built.FLAG_CORNER_SUM)
+    first_moment_sample = int((float(delay.max()) + 25.0 / (2.5 * 1.4426950408889634)) / 2.0) + 2
     for b in range(3):
-        want = oracle.run_direct(layers, delay, layer_k[b], leads_b[b], "3D4", t_start, 1.0, 50.0)
-        assert rel_err(got[b], want) < ECG_TOL, (b, rel_err(got[b], want))
+        want = oracle.run_direct(layers, delay, layer_k[b], leads_b[b], "3D4", 0.0, 2.0, 400.0)
+        e_ser, e_sum = rel_err(got[b], want), rel_err(csum[b], want)
+        peak = np.abs(want).max(axis=-1, keepdims=True)
+        late = float((np.abs(got[b] - want)[:, first_moment_sample:] / peak).max())
+        print("scale %g vector %d: series %.3g, corner sum %.3g of peak; moment samples %.3g" % (scale, b, e_ser, e_sum, late))
+        assert e_ser < ECG_TOL and e_sum < ECG_TOL, (b, e_ser, e_sum)
+        assert late < 2e-6, (b, late)
     m.close()
 
 

@@ -1,6 +1,6 @@
 """tools/prof_moment.py -- device time of the SEPARABLE path's moment kernel on model_24 (B = 256 and B = 1) under the
 tuning knobs the library reads from the environment (one subprocess per setting, the knobs are read once):
-EKGSIM_B200_MOMENT_CTAS (CTAs per SM the segment table is sized for), EKGSIM_B200_MOMENT_OCC (register budget 3|4 CTAs/SM).
+EKGSIM_B200_MOMENT_CTAS (CTAs per SM the segment table is sized for).
 Usage: python tools/prof_moment.py [--sweep]   -> one JSON line per setting."""
 import json
 import os
@@ -24,7 +24,7 @@ def one():
     dev = torch.device("cuda", 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    out = {"ctas_per_sm": os.environ.get("EKGSIM_B200_MOMENT_CTAS", "default"), "occ": os.environ.get("EKGSIM_B200_MOMENT_OCC", "default")}
+    out = {"ctas_per_sm": os.environ.get("EKGSIM_B200_MOMENT_CTAS", "default")}
     for B in (256, 1):
         d_k = torch.from_numpy(np.ascontiguousarray(g["layer_k"][:B])).to(dev)
         d_l = torch.from_numpy(np.ascontiguousarray(g["leads_zyx"][:B])).to(dev)
@@ -43,9 +43,8 @@ def one():
 
 if __name__ == "__main__":
     if "--sweep" in sys.argv:
-        for ctas in ("16", "32", "48", "96", "192"):
-            for occ in ("3", "4"):
-                env = dict(os.environ, EKGSIM_B200_MOMENT_CTAS=ctas, EKGSIM_B200_MOMENT_OCC=occ)
-                subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False)
+        for ctas in ("24", "48", "96"):
+            env = dict(os.environ, EKGSIM_B200_MOMENT_CTAS=ctas)
+            subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False)
     else:
         one()
