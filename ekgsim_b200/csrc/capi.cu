@@ -8,6 +8,8 @@
 #include <cstring>
 #include <unordered_map>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "ekg_internal.cuh"
 
 namespace ekg {
@@ -74,60 +76,56 @@ static void free_model(ekg_model* m) {
 	delete m;
 }
 
-// (re)build the ECG voxel list for z in [z0, z1): sorted by layer; inside a layer first the interior voxels (all 8 cube
-// corners occupied -- the moment kernels treat them by a series, ecg.cu), then the boundary voxels, raster order in both parts
+// ---- the ECG voxel list, built on the device ------------------------------------------------------------------------
+// The list holds the occupied voxels with z in [z0, z1), sorted by layer; inside a layer first the interior voxels (all 8
+// cube corners occupied -- the moment kernels treat them by a series, ecg.cu), then the boundary voxels, raster order in
+// both parts.  Everything it needs is resident already: the padded layer map and the raster list of occupied voxels
+// (d_auto_pidx; padded indices grow with the raster index, so a z-slab is a contiguous run of it).
+struct CubeOffsets { int32_t off[kMaxNbr]; int32_t n; };
+
+// key = 2 (layer - 1) + (boundary ? 1 : 0); mask bit k: voxel `index - dif_k` occupied (simulator.cpp:514)
+__global__ void ecg_list_keys_kernel(const uint8_t* __restrict__ layer_pad, const uint32_t* __restrict__ pidx, int64_t n, const CubeOffsets co,
+                                     uint16_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ masks) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int64_t p = pidx[i];
+	uint32_t mk = 0;
+#pragma unroll
+	for (int k = 0; k < 26; ++k) if (layer_pad[p - co.off[k]]) mk |= 1u << k;
+	keys[i] = (uint16_t)(2u * (layer_pad[p] - 1u) + ((mk & kCornerMask) == kCornerMask ? 0u : 1u));
+	vals[i] = (uint32_t)i;
+	masks[i] = mk;
+}
+
+__global__ void ecg_list_gather_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ pidx, const uint32_t* __restrict__ masks,
+                                       int64_t n, int64_t pY, int64_t pX, uint32_t* __restrict__ pos, uint32_t* __restrict__ mask,
+                                       uint32_t* __restrict__ ecg_pidx) {
+	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const uint32_t src = order[j];
+	const uint32_t p = pidx[src];
+	const uint32_t x = p % (uint32_t)pX - 1u, zy = p / (uint32_t)pX, y = zy % (uint32_t)pY - 1u, z = zy / (uint32_t)pY - 1u;
+	pos[j] = x | (y << 11) | (z << 22);
+	mask[j] = masks[src];
+	ecg_pidx[j] = p;
+}
+
+// bounds[k] = first position of the sorted key array whose key is >= k, k = 0 .. n_keys
+__global__ void ecg_list_bounds_kernel(const uint16_t* __restrict__ keys, int64_t n, int32_t n_keys, int64_t* __restrict__ bounds) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k > n_keys) return;
+	int64_t lo = 0, hi = n;
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) >> 1;
+		if ((int)keys[mid] < k) lo = mid + 1; else hi = mid;
+	}
+	bounds[k] = lo;
+}
+
 static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
-	const int64_t Y = m->Y, X = m->X;
 	const int nl = m->n_layers;
-
-	// padded layer map for bounds-free neighbour tests
-	std::vector<uint8_t> lp((size_t)(m->pZ * m->pY * m->pX), 0);
-	for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < Y; ++y)
-		memcpy(&lp[pad_index(m, z, y, 0)], &m->h_layer[(z * Y + y) * X], (size_t)X);
-	NbrTable cube;
-	make_nbr_table(EKG_NBHD_3D8, &cube);
-	int64_t off[kMaxNbr];
-	for (int k = 0; k < cube.n; ++k) off[k] = (cube.dz[k] * m->pY + cube.dy[k]) * m->pX + cube.dx[k];
-	auto cube_mask = [&](int64_t p) {
-		uint32_t mk = 0;
-		for (int k = 0; k < cube.n; ++k) if (lp[p - off[k]]) mk |= 1u << k;  // neighbour = index - dif (simulator.cpp:514)
-		return mk;
-	};
-
-	// pass 1 (raster order): occupancy mask of every voxel of the slab, voxels per (layer, interior | boundary)
-	std::vector<uint32_t> r_pos, r_mask, r_pidx;
-	std::vector<uint8_t> r_layer;
-	std::vector<int64_t> cnt_in(nl + 2, 0), cnt_bd(nl + 2, 0);
-	for (int64_t z = z0; z < z1; ++z) for (int64_t y = 0; y < Y; ++y) for (int64_t x = 0; x < X; ++x) {
-		const uint8_t l = m->h_layer[(z * Y + y) * X + x];
-		if (!l) continue;
-		const int64_t p = pad_index(m, z, y, x);
-		const uint32_t mk = cube_mask(p);
-		r_pos.push_back((uint32_t)x | ((uint32_t)y << 11) | ((uint32_t)z << 22));
-		r_mask.push_back(mk);
-		r_pidx.push_back((uint32_t)p);
-		r_layer.push_back(l);
-		if ((mk & kCornerMask) == kCornerMask) ++cnt_in[l]; else ++cnt_bd[l];
-	}
-	m->layer_off.assign(nl + 1, 0);
-	m->interior_cnt.assign(nl + 1, 0);
-	for (int l = 1; l <= nl; ++l) {
-		m->layer_off[l] = m->layer_off[l - 1] + cnt_in[l] + cnt_bd[l];
-		m->interior_cnt[l - 1] = cnt_in[l];
-	}
-	const int64_t n = m->layer_off[nl];
-	std::vector<uint32_t> pos(n), mask(n), pidx(n);
-	std::vector<int64_t> cur_in(nl + 1), cur_bd(nl + 1);
-	for (int l = 0; l < nl; ++l) { cur_in[l] = m->layer_off[l]; cur_bd[l] = m->layer_off[l] + m->interior_cnt[l]; }
-	// pass 2: stable scatter into the (layer, kind) ranges
-	for (int64_t i = 0; i < n; ++i) {
-		const int l = r_layer[i];
-		const int64_t j = ((r_mask[i] & kCornerMask) == kCornerMask) ? cur_in[l - 1]++ : cur_bd[l - 1]++;
-		pos[j] = r_pos[i];
-		mask[j] = r_mask[i];
-		pidx[j] = r_pidx[i];
-	}
-	std::vector<uint32_t>().swap(r_pos); std::vector<uint32_t>().swap(r_mask); std::vector<uint32_t>().swap(r_pidx); std::vector<uint8_t>().swap(r_layer);
+	const int64_t i0 = m->h_occ_before_z[(size_t)z0], n = m->h_occ_before_z[(size_t)z1] - i0;
+	if (n >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "more than 2^31 occupied voxels in one slab");
 
 	for (void* p : {(void*)m->d_pos, (void*)m->d_mask, (void*)m->d_ecg_pidx, (void*)m->d_at, (void*)m->d_at32, (void*)m->d_vox}) if (p) cudaFree(p);
 	m->d_pos = m->d_mask = m->d_ecg_pidx = nullptr; m->d_at = nullptr; m->d_at32 = nullptr; m->d_vox = nullptr;
@@ -138,10 +136,59 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 	EKG_CUDA(cudaMalloc(&m->d_at, nn * 8));
 	EKG_CUDA(cudaMalloc(&m->d_at32, nn * 4));
 	EKG_CUDA(cudaMalloc(&m->d_vox, nn * sizeof(float4)));
-	int rc;
-	if ((rc = upload(m, m->d_pos, pos.data(), (size_t)n * 4))) return rc;
-	if ((rc = upload(m, m->d_mask, mask.data(), (size_t)n * 4))) return rc;
-	if ((rc = upload(m, m->d_ecg_pidx, pidx.data(), (size_t)n * 4))) return rc;
+
+	m->layer_off.assign(nl + 1, 0);
+	m->interior_cnt.assign(nl + 1, 0);
+	if (n > 0) {
+		NbrTable cube;
+		make_nbr_table(EKG_NBHD_3D8, &cube);
+		CubeOffsets co{};
+		co.n = cube.n;
+		for (int k = 0; k < cube.n; ++k) co.off[k] = (int32_t)((cube.dz[k] * m->pY + cube.dy[k]) * m->pX + cube.dx[k]);
+
+		// scratch: keys in / out, order in / out, masks in raster order, bounds, radix-sort workspace
+		uint16_t *d_keys = nullptr, *d_keys_sorted = nullptr;
+		uint32_t *d_vals = nullptr, *d_order = nullptr, *d_rmask = nullptr;
+		int64_t* d_bounds = nullptr;
+		void* d_tmp = nullptr;
+		auto cleanup = [&]() { for (void* p : {(void*)d_keys, (void*)d_keys_sorted, (void*)d_vals, (void*)d_order, (void*)d_rmask, (void*)d_bounds, d_tmp}) if (p) cudaFree(p); };
+#define EKG_LIST_CUDA(call)                                                                        \
+		do {                                                                                       \
+			cudaError_t e__ = (call);                                                              \
+			if (e__ != cudaSuccess) { cleanup(); return cuda_fail(e__, #call, __FILE__, __LINE__); } \
+		} while (0)
+		const int n_keys = 2 * nl;
+		EKG_LIST_CUDA(cudaMalloc(&d_keys, nn * 2));
+		EKG_LIST_CUDA(cudaMalloc(&d_keys_sorted, nn * 2));
+		EKG_LIST_CUDA(cudaMalloc(&d_vals, nn * 4));
+		EKG_LIST_CUDA(cudaMalloc(&d_order, nn * 4));
+		EKG_LIST_CUDA(cudaMalloc(&d_rmask, nn * 4));
+		EKG_LIST_CUDA(cudaMalloc(&d_bounds, (size_t)(n_keys + 1) * 8));
+		int end_bit = 1;
+		while ((1 << end_bit) < n_keys) ++end_bit;
+		size_t tmp_bytes = 0;
+		EKG_LIST_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_sorted, d_vals, d_order, (int)n, 0, end_bit, m->stream));
+		EKG_LIST_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 1)));
+		const unsigned blocks = (unsigned)((n + 255) / 256);
+		ecg_list_keys_kernel<<<blocks, 256, 0, m->stream>>>(m->d_layer_pad, m->d_auto_pidx + i0, n, co, d_keys, d_vals, d_rmask);
+		EKG_LIST_CUDA(cudaGetLastError());
+		// LSD radix sort: stable, so the raster order survives inside every (layer, kind) range
+		EKG_LIST_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_sorted, d_vals, d_order, (int)n, 0, end_bit, m->stream));
+		ecg_list_gather_kernel<<<blocks, 256, 0, m->stream>>>(d_order, m->d_auto_pidx + i0, d_rmask, n, m->pY, m->pX, m->d_pos, m->d_mask, m->d_ecg_pidx);
+		EKG_LIST_CUDA(cudaGetLastError());
+		ecg_list_bounds_kernel<<<(n_keys + 1 + 127) / 128, 128, 0, m->stream>>>(d_keys_sorted, n, n_keys, d_bounds);
+		EKG_LIST_CUDA(cudaGetLastError());
+		std::vector<int64_t> bounds((size_t)n_keys + 1);
+		EKG_LIST_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds, bounds.size() * 8, cudaMemcpyDeviceToHost, m->stream));
+		EKG_LIST_CUDA(cudaStreamSynchronize(m->stream));
+#undef EKG_LIST_CUDA
+		cleanup();
+		for (int l = 0; l < nl; ++l) {
+			m->layer_off[l] = bounds[2 * l];
+			m->interior_cnt[l] = bounds[2 * l + 1] - bounds[2 * l];
+		}
+		m->layer_off[nl] = bounds[n_keys];
+	}
 	m->n_ecg = n;
 	m->slab_z0 = z0; m->slab_z1 = z1;
 	m->n_segs = 0; m->seg_len = 0;  // segment tables depend on the list
@@ -324,13 +371,17 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 	m->pZ = (Z + 7) / 8 * 8 + 2; m->pY = (Y + 7) / 8 * 8 + 2; m->pX = (X + 7) / 8 * 8 + 2;
 	const int64_t n = Z * Y * X;
 	m->h_layer.resize((size_t)n);
+	m->h_occ_before_z.assign((size_t)Z + 1, 0);
 	int max_layer = 0;
-	for (int64_t i = 0; i < n; ++i) {
-		uint16_t l = layers[i];
-		if (l & kStartFlag) { m->h_starts.push_back(i); l = (uint16_t)(l - kStartFlag); }  // simulator.cpp:261-264
-		if (l > 255) { delete m; return fail(EKG_E_UNSUPPORTED, "more than 255 layers"); }
-		m->h_layer[(size_t)i] = (uint8_t)l;
-		if (l) { ++m->n_occ; max_layer = std::max<int>(max_layer, l); }
+	for (int64_t z = 0, i = 0; z < Z; ++z) {
+		for (const int64_t plane_end = (z + 1) * Y * X; i < plane_end; ++i) {
+			uint16_t l = layers[i];
+			if (l & kStartFlag) { m->h_starts.push_back(i); l = (uint16_t)(l - kStartFlag); }  // simulator.cpp:261-264
+			if (l > 255) { delete m; return fail(EKG_E_UNSUPPORTED, "more than 255 layers"); }
+			m->h_layer[(size_t)i] = (uint8_t)l;
+			if (l) { ++m->n_occ; max_layer = std::max<int>(max_layer, l); }
+		}
+		m->h_occ_before_z[(size_t)z + 1] = m->n_occ;
 	}
 	m->n_layers = max_layer;  // targetNumOfAps = highest layer number (simulator.cpp:186-198)
 	if (t_rows < max_layer || t_cols < max_layer) { delete m; return fail(EKG_E_TRANSFER, "loaded transfer matrix too small"); }  // simulator.cpp:203-205

@@ -143,6 +143,7 @@ struct ekg_model {
 	// host copies
 	std::vector<uint8_t> h_layer;    // raster, start flags stripped
 	std::vector<int64_t> h_starts;   // raster indices of start voxels
+	std::vector<int64_t> h_occ_before_z;  // [Z + 1] occupied voxels in the planes below z (a z-slab is a run of d_auto_pidx)
 	std::vector<double> h_transfer;
 	int64_t t_rows = 0, t_cols = 0;
 	std::vector<double> h_delay;     // raster activation map (0 = empty / never reached): a lazily made host copy,
