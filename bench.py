@@ -346,15 +346,20 @@ def run_b200_arm(args):
                 corner_sum_ms.append(model.last_kernel_ms)
         ecg_corner_sum = d_ecg.cpu().numpy()
         barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sep_kernel_ms = []
-        f0.record()
+        # a step is ~0.7 ms, the 256 MiB L2 flush before it ~0.07 ms: every step gets its own event pair, the flush stays
+        # between the timed intervals
+        sep_kernel_ms, sep_events = [], []
         for _ in range(args.steps):
-            step_sep(timed=True)
+            flush.fill_(1)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            model.simulate_device(d_k.data_ptr(), d_leads.data_ptr(), B, L, d_ecg.data_ptr(), "3D4", 100.0, 1.0, float(T_FULL),
+                                  mode=ek.MODE_SEPARABLE | ek.FLAG_TIME_KERNEL, stream=stream)
+            f1.record()
+            sep_events.append((f0, f1))
             sep_kernel_ms.append(model.last_kernel_ms)
-        f1.record()
         barrier()
-        sms = f0.elapsed_time(f1) / args.steps
+        sms = sum(a.elapsed_time(b) for a, b in sep_events) / args.steps
         t = torch.tensor([sms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -378,7 +383,9 @@ def run_b200_arm(args):
         # moment kernel, per (voxel, vector) at 2 leads and the 3D4 stencil:
         #   boundary voxel (a corner missing): 9 lead-field evaluations -> ~100 packed fp32x2 operations = 200 fp32 lane-operations
         #                                      (an FFMA2 occupies the FMA pipe for two cycles), 16-18 rsqrt + 2 ex2
-        #   interior voxel (all 8 corners):    the series of the corner sum -> 34 packed + 8 scalar = 76 lane-operations, 2 rsqrt + 2 ex2
+        #   interior voxel (all 8 corners):    the series of the corner sum -> 30 packed + 8 scalar = 68 lane-operations, 2 rsqrt + 2 ex2
+        #   (the two kinds sit in segments of their own: ecg_moment_interior_kernel + ecg_moment_corners_kernel; moment_kernel_ms
+        #   is the device time of both launches)
         occ = (m24["layers"] & 0x0FFF) > 0
         inner = occ.copy()
         pad = np.pad(occ, 1)
@@ -388,7 +395,7 @@ def run_b200_arm(args):
                 for dx in (0, 2):
                     inner &= pad[dz:dz + Zs, dy:dy + Ys, dx:dx + Xs]
         f_int = float(inner.sum()) / float(occ.sum())
-        lane_ops = f_int * 76 + (1 - f_int) * 200
+        lane_ops = f_int * 68 + (1 - f_int) * 200
         mufu_ops = f_int * 4 + (1 - f_int) * 20
         mk = sum(sep_kernel_ms) / len(sep_kernel_ms)
         mk_sum = sum(corner_sum_ms) / len(corner_sum_ms)

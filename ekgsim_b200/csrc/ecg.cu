@@ -402,14 +402,15 @@ __device__ __forceinline__ f2 inv_cube2(f2 sq) {
 //     g = |q|^-5 [ (112 - 560 e2) + u (3024 e2 - 33264 e3 - 288) + u^2 (-51480 e2^2 + 14256 e2 + 41184 e3 - 792) + O(u^3) ]
 // The 8 corner terms are O(|q|^-2) each and cancel down to this O(|q|^-5) remainder -- summed directly in fp32 they
 // leave 1e-4..1e-2 relative noise on g (it averages out over the model, which is why the direct sum passes its
-// tolerance); the series has no cancellation (1e-6 relative in fp32), a truncation error below 5e-8 relative for
-// |q| >= 32 voxels (3e-8 measured at 35, falling like |q|^-6) and costs 28 packed operations + 2 MUFU per lead
+// tolerance); the series has no cancellation (3e-6 relative in fp32), a truncation error below 5e-8 relative for
+// |q| >= 32 voxels (3e-8 measured at 35, falling like |q|^-6) and costs 24 packed operations + 2 MUFU per lead
 // pair instead of ~110 + 16.  Segments with a lead closer than sqrt(kSeriesMinR2) take the direct sum.
 constexpr float kSeriesMinR2 = 1024.f;
 __device__ __forceinline__ f2 c2(float c) { return mk2(c, c); }
 __device__ __forceinline__ f2 corner_series2(f2 qz, f2 qy, f2 qx, f2 r2) {
-	f2 y = mk2(mufu_rsq(lo2(r2)), mufu_rsq(hi2(r2)));
-	y = mul2(y, fma2(mul2(r2, c2(-0.5f)), mul2(y, y), c2(1.5f)));
+	// MUFU.RSQ as it comes (2 ulp): with nothing to cancel, 1e-6 relative on g is far inside the budget (the direct sum
+	// needs its Newton step because its terms cancel by 4..6 orders of magnitude)
+	const f2 y = mk2(mufu_rsq(lo2(r2)), mufu_rsq(hi2(r2)));
 	const f2 u = mul2(y, y);
 	const f2 xz = mul2(qz, u), xy = mul2(qy, u), xx = mul2(qx, u);
 	const f2 zy = mul2(xz, xy);
