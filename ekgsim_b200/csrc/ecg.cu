@@ -286,8 +286,9 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 // then leaves the time loop as well:
 //     ECG_l(t) = sum_layers [ k0 M0 + F1(t) M1 + F2(t) M2 ],   (M0, M1, M2) = sum_{c in layer} G_{l,c} (1, h1_c, h2_c)
 // i.e. O(voxels) work per simulation instead of O(voxels x samples).  ecg_moment_kernel computes the
-// moments (the phase A arithmetic of ecg_kernel + two ex2 per voxel and vector), ecg_combine_kernel
-// evaluates F1, F2 in f64 and sums the 3 x layers terms per sample.
+// moments for any stencil (the phase A arithmetic of ecg_kernel + two ex2 per voxel and vector) -- the reference's
+// default stencil has the two specialised kernels further down --, ecg_combine_kernel evaluates F1, F2 in f64 and
+// sums the 3 x layers terms per sample.
 //
 // Threads of a CTA = VB parameter vectors x 256/VB voxel lanes (VB = 32 for batches: a warp works on ONE
 // voxel for 32 vectors, voxel loads are broadcasts and the occupancy-mask branches are warp-uniform; VB = 1
