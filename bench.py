@@ -63,7 +63,7 @@ def workload_config(args, n_gpus):
     return {
         "workload": "configs[2]: batched evaluation of %d parameter vectors per GPU on testRun model_24 "
                     "(555868 voxels x 400 samples x 2 leads, 3D4 stencil)" % args.batch,
-        "model": "model_24", "voxels": N_VOX, "time_samples": T_FULL, "leads": 2,
+        "heart": "model_24", "voxels": N_VOX, "time_samples": T_FULL, "leads": 2,
         "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus,
         "parallelism": "individuals sharded over %d GPU(s), model replicated, no collective" % n_gpus,
     }
@@ -508,7 +508,8 @@ def run_b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 AP evaluation, f64 accumulation", "data": "reference testRun model_24 (compact fixture) + 256 seeded vectors "
+        "dtype": "f32", "dtype_note": "f32 AP evaluation and lead-field coefficients, compensated (f64-grade) accumulation, f64 partial sums and outputs",
+        "data": "reference testRun model_24 (compact fixture) + 256 seeded vectors "
         "(layer coefficients from the reference glue); random-free, no checkpoint needed",
         "config": dict(workload_config(args, world), l2="flushed between iterations (256 MiB fill)", ecg_mode=args.mode),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
