@@ -403,7 +403,7 @@ __device__ __forceinline__ f2 inv_cube2(f2 sq) {
 //     g = |q|^-5 [ (112 - 560 e2) + u (3024 e2 - 33264 e3 - 288) + u^2 (-51480 e2^2 + 14256 e2 + 41184 e3 - 792) + O(u^3) ]
 // The 8 corner terms are O(|q|^-2) each and cancel down to this O(|q|^-5) remainder -- summed directly in fp32 they
 // leave 1e-4..1e-2 relative noise on g (it averages out over the model, which is why the direct sum passes its
-// tolerance); the series has no cancellation (3e-6 relative in fp32), a truncation error below 5e-8 relative for
+// tolerance); the series has no cancellation (3e-6 relative in fp32), a truncation error below 7e-8 relative for
 // |q| >= 32 voxels (3e-8 measured at 35, falling like |q|^-6) and costs 24 packed operations + 2 MUFU per lead
 // pair instead of ~110 + 16.  Segments with a lead closer than sqrt(kSeriesMinR2) take the direct sum.
 constexpr float kSeriesMinR2 = 1024.f;
