@@ -277,6 +277,50 @@ inline void load_delay_matrix(const std::string& fname, int64_t Z, int64_t Y, in
 	}
 }
 
+/// "Shape file" dump (simulator.cpp:71-106 with excit = false): one character per voxel -- 'X' for a start voxel, '0'..'9',
+/// then 'A'.. for layers from 10 on --, one text line per y, an empty line after every z block
+inline void export_shape_matrix(const std::string& fname, int64_t Z, int64_t Y, int64_t X, const std::vector<uint16_t>& layers) {
+	if (file_extension(fname) != ".matrix") throw std::runtime_error("can only export to .matrix for the time being");
+	std::ofstream out(fname.c_str());
+	out << "Shape file (next line specifies matrix type (2D) size (X x Y x Z) and elemet separator type (tab) after that comes data"
+	       " (x are rows, y are lines, z are blocks - separated with empty line)\n";
+	if (Z > 1) out << "3D " << X << " x " << Y << " x " << Z;
+	else out << "2D " << X << " x " << Y;
+	out << "\n";
+	for (int64_t z = 0; z < Z; ++z) {
+		for (int64_t y = 0; y < Y; ++y) {
+			for (int64_t x = 0; x < X; ++x) {
+				const uint16_t l = layers[(size_t)((z * Y + y) * X + x)];
+				out << ((l & 0x1000) ? 'X' : (l > 9 ? (char)(l - 10 + 'A') : (char)('0' + (unsigned char)l)));
+			}
+			out << "\n";
+		}
+		out << "\n";
+	}
+}
+
+/// The reference's built-in test shape (InputLoader::generateTestShape, simulator.h:600-644; used by EkgSim::loadShape when
+/// `[model] shape` is empty): a 2-D ring of 160 x 120 voxels around (y, x) = (80, 30), layer = floor(floor(d - 50) / 2) for
+/// 50 < d < 76 (so 0 = empty up to d = 52, then layers 1..12), start voxel = first occupied voxel at x = 30 from y = 80 upwards;
+/// like the reference it also writes the shape to autoGeneratedShape.matrix in the current directory.
+inline void generate_test_shape(std::vector<uint16_t>& layers, int64_t& Z, int64_t& Y, int64_t& X, const char* export_as = "autoGeneratedShape.matrix") {
+	Z = 1; Y = 160; X = 120;
+	const int dLow = 50, dHigh = 76;
+	layers.assign((size_t)(Y * X), 0);
+	const int64_t mid1 = Y / 2, mid2 = X / 4;
+	for (int64_t i = 0; i < Y; ++i)
+		for (int64_t j = 0; j < X; ++j) {
+			const double d = std::sqrt((double)((i - mid1) * (i - mid1)) + (double)((j - mid2) * (j - mid2)));
+			if (d > dLow && d < dHigh) layers[(size_t)(i * X + j)] = (uint16_t)((size_t)(d - dLow) / 2);
+		}
+	int64_t sy = Y / 2;
+	const int64_t sx = X / 4;
+	for (; sy < Y; ++sy) if (layers[(size_t)(sy * X + sx)] > 0) break;
+	if (sy == Y) throw std::runtime_error("Could not create starting point for excitation sequence");
+	layers[(size_t)(sy * X + sx)] = (uint16_t)(layers[(size_t)(sy * X + sx)] + 0x1000);   // ShapeElement::layerStartingPoint
+	if (export_as && *export_as) export_shape_matrix(export_as, Z, Y, X, layers);
+}
+
 /// "Excitation file" dump, 3 decimals, tab separated (simulator.cpp:71-106 with excit = true)
 inline void export_delay_matrix(const std::string& fname, int64_t Z, int64_t Y, int64_t X, const std::vector<double>& delay) {
 	if (file_extension(fname) != ".matrix") throw std::runtime_error("can only export to .matrix for the time being");

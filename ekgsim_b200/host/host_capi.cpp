@@ -18,6 +18,31 @@ double ekg_host_apd90(const double* k) {
 	return w.apd90();
 }
 
+/// the built-in test shape (InputLoader::generateTestShape): layers_out[160 * 120] u16, dims_out = {Z, Y, X}; export_as may be ""
+int ekg_host_generate_test_shape(uint16_t* layers_out, int64_t* dims_out, const char* export_as) {
+	try {
+		std::vector<uint16_t> layers;
+		int64_t Z, Y, X;
+		ekg::generate_test_shape(layers, Z, Y, X, export_as);
+		std::copy(layers.begin(), layers.end(), layers_out);
+		dims_out[0] = Z; dims_out[1] = Y; dims_out[2] = X;
+		return 0;
+	} catch (std::exception& e) { g_host_error = e.what(); return -1; }
+}
+
+/// .matrix shape file -> layers (u16, start flag 0x1000), the parser the facade's loadShape uses; returns the voxel count or -1
+int64_t ekg_host_load_shape(const char* fname, uint16_t* layers_out, int64_t capacity, int64_t* dims_out) {
+	try {
+		std::vector<uint16_t> layers;
+		int64_t Z, Y, X;
+		ekg::load_shape_matrix(fname, layers, Z, Y, X);
+		if ((int64_t)layers.size() > capacity) throw std::runtime_error("buffer too small");
+		std::copy(layers.begin(), layers.end(), layers_out);
+		dims_out[0] = Z; dims_out[1] = Y; dims_out[2] = X;
+		return (int64_t)layers.size();
+	} catch (std::exception& e) { g_host_error = e.what(); return -1; }
+}
+
 /// Evaluator over the simulator.ini of the CURRENT directory (like the CLI).  Needs a GPU.
 void* ekg_host_evaluator_create(const char* ini, int with_device) {
 	try { return new ekg::Evaluator(ini, with_device != 0); }

@@ -294,8 +294,9 @@ public:
 
 	void loadShape() {
 		ekg::LogTimer tm(std::cerr, "loading shape                               ");
-		if (settings.inputShapeFilename == "") throw std::runtime_error("no shape file given (the built-in test shape generator is not part of the B200 build)");
-		ekg::load_shape_matrix_cached(settings.inputShapeFilename, layers_, Z_, Y_, X_);
+		// no file name: the built-in test shape, like InputLoader::loadShape (simulator.h:646-651)
+		if (settings.inputShapeFilename == "") ekg::generate_test_shape(layers_, Z_, Y_, X_);
+		else ekg::load_shape_matrix_cached(settings.inputShapeFilename, layers_, Z_, Y_, X_);
 		size_t maxLayer = 0;
 		for (uint16_t l : layers_) maxLayer = std::max<size_t>(maxLayer, l & 0x0fff);
 		targetNumOfAps_ = maxLayer;

@@ -26,8 +26,30 @@ def lib():
         L.ekg_host_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ekg_host_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ekg_host_layer_coefficients.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ekg_host_generate_test_shape.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        L.ekg_host_load_shape.restype = C.c_int64
+        L.ekg_host_load_shape.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
         _lib = L
     return _lib
+
+
+def generate_test_shape(export_as=""):
+    """The facade's built-in test shape (InputLoader::generateTestShape): layers u16 [1, 160, 120] with the start flag."""
+    layers = np.zeros(160 * 120, dtype=np.uint16)
+    dims = np.zeros(3, dtype=np.int64)
+    if lib().ekg_host_generate_test_shape(layers.ctypes.data, dims.ctypes.data, export_as.encode()) != 0:
+        raise RuntimeError(lib().ekg_host_last_error().decode())
+    return layers.reshape(tuple(int(d) for d in dims))
+
+
+def load_shape(fname, capacity=1 << 22):
+    """A .matrix shape file through the facade's parser: layers u16 [Z, Y, X] with the start flag."""
+    layers = np.zeros(capacity, dtype=np.uint16)
+    dims = np.zeros(3, dtype=np.int64)
+    n = lib().ekg_host_load_shape(fname.encode(), layers.ctypes.data, capacity, dims.ctypes.data)
+    if n < 0:
+        raise RuntimeError(lib().ekg_host_last_error().decode())
+    return layers[:n].reshape(tuple(int(d) for d in dims)).copy()
 
 
 class Evaluator:

@@ -257,6 +257,31 @@ def test_ecg_2d_model(built, nbhd):
     m.close()
 
 
+def test_builtin_test_shape_on_the_device(built):
+    """The reference's built-in 2-D test ring (InputLoader::generateTestShape, what loadShape falls back to without a shape
+    file; the facade's copy is pinned byte for byte in tests/test_host_glue.py) through the CUDA path: activation times
+    bit-exact, ECG in both 2-D stencils within tolerance."""
+    import hostlib
+    layers = hostlib.generate_test_shape()
+    n = int((layers & 0x0FFF).max()) + 2
+    transfer = np.full((n, n), -1.0)
+    for i in range(1, n):
+        for j in range(1, n):
+            transfer[i, j] = 0.166667 if i == j else float(abs(i - j))
+    m = built.Model(layers, transfer)
+    delay, _ = m.activation()
+    ref_delay = oracle.activation(layers, transfer)
+    assert delay.tobytes() == ref_delay.tobytes()
+    leads = np.array([[60.0, -40.0, 30.0], [-35.0, 200.0, 160.0]])
+    k = synth.layer_params(n - 2, seed=12)
+    for nbhd in ("2D4", "2D8"):
+        ref = oracle.run_direct(layers, ref_delay, k, leads, nbhd, 0.0, 1.0, 80.0)
+        for mode in (1, 2, 3):
+            ecg = m.simulate(k, leads, nbhd, 0.0, 1.0, 80.0, mode=mode)[0]
+            assert rel_err(ecg, ref) < ECG_TOL, (mode, nbhd, rel_err(ecg, ref))
+    m.close()
+
+
 @pytest.mark.parametrize("B,t0,dt,total", [(10, 0.0, 1.0, 7.0), (37, 5.0, 0.25, 3.0), (3, 0.0, 2.0, 1500.0), (1, 20.0, 1.0, 1.0)])
 def test_ecg_ragged_pair_tiles(built, B, t0, dt, total):
     """Few samples per vector (one 256-pair tile spans many vectors and is cut at 4), more samples

@@ -162,3 +162,20 @@ def test_extern_client_speaks_the_server_protocol(tmp_path, built):
     th.join(timeout=10)
     assert "runtime error caught: chromosome size does not agree" in r.stdout
     srv.close()
+
+
+def test_builtin_test_shape_matches_reference(tmp_path):
+    """`[model] shape =` (empty) makes the reference generate a 2-D test ring and export it as autoGeneratedShape.matrix
+    (InputLoader::generateTestShape / loadShape, simulator.h:600-651).  The facade does the same: the exported file equals
+    the reference's byte for byte (golden written by `ref_dump testshape`, tests/golden/run_reference.sh), and reading it
+    back through the one-character-per-voxel branch of the .matrix parser (matrix.h:206-218) returns the same layers."""
+    out = str(tmp_path / "autoGeneratedShape.matrix")
+    layers = hostlib.generate_test_shape(out)
+    assert layers.shape == (1, 160, 120)
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "autoGeneratedShape_ref.matrix")
+    assert open(out, "rb").read() == open(golden, "rb").read()
+    starts = np.argwhere(layers & 0x1000)
+    assert starts.tolist() == [[0, 132, 30]] and int(layers[0, 132, 30]) == 0x1001      # first ring voxel above the centre line
+    assert int((layers & 0x0FFF).max()) == 12 and int(((layers & 0x0FFF) > 0).sum()) == 6346   # the ring is clipped by the grid
+    back = hostlib.load_shape(out)
+    assert back.shape == layers.shape and (back == layers).all()      # 'X' reads back as start flag + layer 1, which is what it was
