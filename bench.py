@@ -493,8 +493,8 @@ def run_b200_arm(args):
                 "sigmoid runs as a Newton iteration on the FMA pipe, the other 6 on the MUFU/XU pipe",
         "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch at
-        # B = 256 (profiles/r01_ecg_direct_v5_b256_ncu_full.txt): 14.7 MB read + 192.4 MB written (f64 partials)
-        "traffic": 207.1e6 if (B == 256 and mode == ek.MODE_DIRECT) else None,
+        # B = 256 (profiles/r01_ecg_direct_v11_b256_ncu_full.txt): 14.1 MB read + 190.7 MB written (f64 partials)
+        "traffic": 204.8e6 if (B == 256 and mode == ek.MODE_DIRECT) else None,
         "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                 "note": "algorithmic bytes: 16 B/voxel per individual + f64 partials; the kernel is MUFU-bound, not HBM-bound"},
