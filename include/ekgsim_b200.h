@@ -105,8 +105,10 @@ int64_t ekg_model_num_voxels(const ekg_model* m);   /* occupied voxels (inside t
 int64_t ekg_model_num_layers(const ekg_model* m);   /* = Simulation::getTargetNumOfAps(), simulator.h:570 */
 
 /* Runs the activation-time automaton on the device; the map stays resident.  delay_out (host,
- * Z*Y*X doubles, 0.0 for empty / unreached voxels) may be NULL.  sweeps_out (may be NULL)
- * receives a work count: brick visits of the frontier kernel (sweeps of the cross-check kernel). */
+ * Z*Y*X doubles, 0.0 for empty / unreached voxels) may be NULL: the map is then not copied to the
+ * host at all (the ECG entry points only need it in HBM; ekg_model_get_activation and
+ * ekg_model_ap_classes fetch the raster copy on demand).  sweeps_out (may be NULL) receives a work
+ * count: brick visits of the frontier kernel (sweeps of the cross-check kernel). */
 int  ekg_model_activation(ekg_model* m, double* delay_out, int64_t* sweeps_out);
 /* Device time (ms, CUDA events) of the last ekg_model_activation call on this handle. */
 double ekg_model_activation_ms(const ekg_model* m);
@@ -126,7 +128,8 @@ int  ekg_model_set_activation(ekg_model* m, const double* delay);
  *   export  copies planes [z_begin, z_end) into a device buffer (complete on return)
  *   merge   time = min(time, planes); bricks of the slab that can see an improved cell are queued for the next
  *           relax; improved_out = number of improved cells
- *   end     publishes the map like ekg_model_activation does (host copy, ECG voxel list); delay_out may be NULL */
+ *   end     publishes the map like ekg_model_activation does (range of the times, ECG voxel list; host copy only if
+ *           delay_out is not NULL) */
 int     ekg_model_activation_begin(ekg_model* m);
 int     ekg_model_activation_relax(ekg_model* m, int64_t* brick_visits_out);
 int64_t ekg_model_plane_elems(const ekg_model* m);
