@@ -56,6 +56,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--ref-length", type=int, default=24, help="time samples per reference sample run")
+    ap.add_argument("--ref-full", action="store_true",
+                    help="cpu_baseline: additionally time ONE process of the reference at the full 400 samples (~210 s)")
+    ap.add_argument("--no-heart", action="store_true", help="skip the config-4 block (synthetic finer heart, z-slabs + all-reduce)")
+    ap.add_argument("--heart-factor", type=int, default=4)
+    ap.add_argument("--heart-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -116,6 +121,37 @@ class ClockSampler:
         # samples under load = upper half (idle samples before/after the region pull the median down)
         med = sm[len(sm) // 2] if sm else None
         return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+
+# ---- ncu evidence: numbers quoted in the JSON line come from the committed summaries, not from constants ----
+PROFILE_DIRECT = "profiles/r02_ecg_direct_b256_ncu_full.txt"
+PROFILE_FIT = "profiles/r02_fit_b256_ncu_full.txt"
+
+
+def profile_metrics(rel_path, kernel_substr):
+    """Metrics of the first kernel whose name contains `kernel_substr` in a summary written by tools/ncu_summary.py
+    (`kernel: <name> ...` followed by `  <metric>  <unit>  <value>` lines).  Byte counts are returned in bytes."""
+    path = os.path.join(ROOT, rel_path)
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    out, on = {}, False
+    for ln in open(path):
+        if ln.startswith("kernel:"):
+            if on:
+                break
+            on = kernel_substr in ln
+            continue
+        if on:
+            f = ln.split()
+            if len(f) >= 2:
+                try:
+                    v = float(f[-1].replace(",", ""))
+                except ValueError:
+                    continue
+                out[f[0]] = v * scale.get(f[1], 1.0) if len(f) >= 3 else v
+    return out or None
 
 
 # ---- the reference arm / cpu baseline --------------------------------------------------------------
@@ -191,6 +227,178 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+
+# ---- BASELINE configs[3]: synthetic finer heart, one simulation, z-slab sharded ---------------------------
+def heart_block(args, rank, world, local):
+    """ONE simulation of ekgio.scaled_heart(f) (f = 4: 496 x 496 x 372 grid, 35.6 M occupied voxels), the voxels split
+    into z-slabs over the ranks (ekg_model_set_slab), the partial ECGs [L][T] summed with ONE all-reduce per simulation
+    (no per-timestep halo is needed because V is a closed form of static voxel data).  Strong scaling:
+    the same simulation is first timed on this rank's whole model (the N = 1 value, same run, same box).  Parity in the
+    run: sha256 of the activation map and the first 16 ECG samples against the oracle's goldens
+    (tests/golden/golden_heart<f>x.json).  The automaton runs replicated and -- for N > 1 -- sharded over the slabs."""
+    import hashlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ekgio
+    import ekgsim_b200 as ek
+    from ekgsim_b200 import dist as ekdist
+
+    f = args.heart_factor
+    dev = torch.device("cuda", local)
+    layers, transfer, _ = ekgio.scaled_heart(f)
+    gpath = os.path.join(ROOT, "tests", "golden", "golden_heart%dx.json" % f)
+    gold = json.load(open(gpath)) if os.path.exists(gpath) else None
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_glue256.npz"))
+    k = np.ascontiguousarray(g["layer_k"][:1])
+    leads = np.ascontiguousarray((g["leads_zyx"][0] * f)[None])
+    occ = (layers & 0x0FFF) > 0
+    n_occ = int(occ.sum())
+    occ_z = occ.sum(axis=(1, 2))
+    del occ
+    t0 = time.perf_counter()
+    model = ek.Model(layers, transfer, device=local)
+    create_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _, visits = model.activation(download=False)
+    auto_call_ms = 1e3 * (time.perf_counter() - t0)
+    auto_ms = model.activation_ms
+    out = {"workload": "configs[3]: %dx heart, %d occupied voxels, one simulation, z-slabs over %d GPU(s) + one all-reduce of the "
+                       "[2][400] partial ECGs per simulation" % (f, n_occ, world),
+           "factor": f, "voxels": n_occ, "n_gpus": world, "model_create_s": create_s,
+           "automaton": {"ms": auto_ms, "call_ms": auto_call_ms, "brick_visits": visits, "replicated": True}}
+    if rank == 0 and gold is not None:
+        delay = model.get_activation()
+        out["automaton_bit_exact"] = bool(hashlib.sha256(delay.tobytes()).hexdigest() == gold["sha256_f64_raster"])
+        del delay
+    T = T_FULL
+    d_k = torch.from_numpy(k).to(dev)
+    d_l = torch.from_numpy(leads).to(dev)
+    d_e = torch.empty((1, 2, T), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    modes = (("direct", ek.MODE_DIRECT), ("default", ek.MODE_DEFAULT))
+
+    def timed(step, steps):
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return ekdist.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+
+    # N = 1 value: the whole model on this rank, no collective
+    one = {}
+    for nm, md in modes:
+        one[nm] = timed(lambda: model.simulate_device(d_k.data_ptr(), d_l.data_ptr(), 1, 2, d_e.data_ptr(), "3D4", 100.0, 1.0, float(T),
+                                                      mode=md, stream=stream), args.heart_steps)
+    slabs = ekdist.slab_ranges(occ_z, world)
+    z0, z1 = slabs[rank]
+    model.set_slab(z0, z1)
+    for nm, md in modes:
+        def step():
+            model.simulate_device(d_k.data_ptr(), d_l.data_ptr(), 1, 2, d_e.data_ptr(), "3D4", 100.0, 1.0, float(T), mode=md, stream=stream)
+            ekdist.allreduce_sum_(d_e)
+        ms = timed(step, args.heart_steps)
+        ecg = d_e.cpu().numpy()[0]
+        r = {"ms_per_sim": ms, "ms_per_sim_1gpu_same_run": one[nm], "efficiency": one[nm] / (world * ms),
+             "voxel_timesteps_per_s": n_occ * T / (ms * 1e-3), "kernel": model.last_kernel_name,
+             "launches_per_sim": int(model.last_launch_count), "collectives_per_sim": 1 if world > 1 else 0}
+        if gold is not None:
+            peak = np.array(gold["peak_full"])[:, None]
+            err = float((np.abs(ecg[:, :16] - np.array(gold["ecg16"])) / peak).max())
+            for t, want in gold["ecg_at_t"].items():
+                err = max(err, float((np.abs(ecg[:, int(t)] - np.array(want)) / peak[:, 0]).max()))
+            r["ecg_err_of_peak"] = err
+        if nm == "direct":
+            r["roofline_frac_7op"] = SFU_OPS_PER_VTS * n_occ * T / (ms * 1e-3) / (world * 148 * SFU_LANES_PER_SM * 1.965e9)
+        out[nm] = r
+    out["ms_per_sim"] = out["direct"]["ms_per_sim"]
+    out["efficiency"] = out["direct"]["efficiency"]
+    if gold is not None:
+        out["ecg_err_of_peak"] = max(out["direct"]["ecg_err_of_peak"], out["default"]["ecg_err_of_peak"])
+    if world > 1:
+        # the automaton on the sharded model (SURVEY 8(e) row 3): plane exchange per round, bits as in the replicated run
+        planes = ekdist.ModelPlanes(model, dev)
+        best, info = None, None
+        for _ in range(2):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            tm = {}
+            _, rounds, v = ekdist.sharded_activation(planes, slabs, rank, world, timings=tm, download=False)
+            torch.cuda.synchronize()
+            dt = ekdist.max_over_ranks(1e3 * (time.perf_counter() - t0), dev)
+            if best is None or dt < best:
+                best, info = dt, {"ms": dt, "ms_rounds": ekdist.max_over_ranks(tm["rounds_s"] * 1e3, dev),
+                                  "ms_gather": ekdist.max_over_ranks(tm["gather_s"] * 1e3, dev), "rounds": rounds, "brick_visits_rank0": v}
+        if rank == 0 and gold is not None:
+            d2 = model.get_activation()
+            info["bit_exact"] = bool(hashlib.sha256(d2.tobytes()).hexdigest() == gold["sha256_f64_raster"])
+        info["speedup_vs_replicated"] = auto_ms / info["ms"]
+        out["automaton_sharded"] = info
+    model.close()
+    return out
+
+
+
+# ---- BASELINE configs[4]: an optimizer generation through the evaluation boundary ------------------------
+def generation_block(n_gpus):
+    """Population 100 against target_ecg_v2_v6.column on the N GPUs of the box, through the
+    reference-facing boundaries: (a) `ekgSim -batch pop.txt -devices N`: the generation as ONE batch split over the GPUs;
+    (b) the reference's UNMODIFIED stand-alone optimizer (oracle/_ref/DEMO_ref, AMS-DEMO/main.cpp, sequential build: one
+    ExternalEvaluation at a time) driving `ekgSim -extern` against a resident `ekgSim -serve -devices N`.  The reference
+    itself needs 100 x 205 s of CPU per generation."""
+    import ekgio
+    out = {"population": 100, "n_gpus": n_gpus, "reference_cpu_core_seconds_per_generation": 100 * 205.28}
+    cli = os.path.join(ROOT, "ekgsim_b200", "bin", "ekgSim")
+    d = tempfile.mkdtemp(prefix="ekg_gen_")
+    try:
+        ekgio.materialise_testrun(d, targets="target_ecg_v2_v6.column")
+        vec = open(os.path.join(ROOT, "tests", "golden", "vectors256.txt")).read().strip().split("\n")[:100]
+        open(os.path.join(d, "pop.txt"), "w").write("\n".join(vec) + "\n")
+        env = dict(os.environ)
+        env.pop("EKGSIM_B200_DEVICE", None)
+        t0 = time.time()
+        r = subprocess.run([cli, "-batch", "pop.txt", "-batchout", "crit.txt", "-devices", str(n_gpus)], cwd=d, capture_output=True, text=True, env=env)
+        dt = time.time() - t0
+        m = re.search(r"batch of (\d+) simulations done in ([0-9.e+-]+) seconds on (\d+) GPU", r.stdout)
+        out["batched_cli"] = {"process_wall_s": dt, "s_per_generation": float(m.group(2)) if m else None, "devices": int(m.group(3)) if m else None}
+        demo = os.path.join(ROOT, "oracle", "_ref", "DEMO_ref")
+        if os.path.exists(demo):
+            open(os.path.join(d, "settings.ini"), "w").write("[evaluation]\ncommand line = %s -extern\ninput file name = input.txt\n"
+                "output file name = output.txt\nchromosome vector length = 16\ncriteria vector length = 2\nproperties vector length = 0\n\n"
+                "[optimization]\nrandom seed = 11\npopulation size = 100\nmax number of generations = 2\nDE schema = rand/1/bin\n"
+                "p crossover = 0.3\nscaling factors = 0.5\nqueue length = 1\n\n[initial population]\n"
+                "gene min = 0.0003, 0.01, 0.01, 200, 0.0003, 0.01, 0.01, 200, 0.0003, 0.01, 0.01, 200, -50, -50, -50, -50\n"
+                "gene max = 0.001, 0.1, 0.1, 400, 0.001, 0.1, 0.1, 400, 0.001, 0.1, 0.1, 400, 50, 50, 50, 50\n" % cli)
+            sock = os.path.join(d, "ekg.sock")
+            srv = subprocess.Popen([cli, "-serve", sock, "-devices", str(n_gpus)], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env)
+            for _ in range(900):
+                if os.path.exists(sock) or srv.poll() is not None:
+                    break
+                time.sleep(0.1)
+            t0 = time.time()
+            r = subprocess.run([demo], cwd=d, capture_output=True, text=True, env=dict(env, EKGSIM_B200_SERVER=sock), timeout=300)
+            dt = time.time() - t0
+            subprocess.run([cli, "-shutdown", sock], cwd=d, capture_output=True)
+            err = srv.communicate(timeout=60)[1]
+            n_eval = len([ln for ln in open(os.path.join(d, "evaluations.txt")) if ln.strip() and not ln.startswith("#")])
+            out["reference_ams_demo_via_extern_server"] = {"evaluations": n_eval, "wall_s": dt, "s_per_generation_of_100": dt * 100 / max(n_eval, 1),
+                                                           "ms_per_evaluation": 1e3 * dt / max(n_eval, 1), "ok": "front.txt" in r.stdout,
+                                                           "note": "the sequential optimizer build evaluates one individual at a time (no MPI runtime in "
+                                                                   "this image): a process start + socket round trip per evaluation, one GPU busy at a time",
+                                                           "server": err.strip().split("\n")[-1] if err.strip() else ""}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return out
 
 
 # ---- our arm ---------------------------------------------------------------------------------------
@@ -270,6 +478,8 @@ def run_b200_arm(args):
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
+    direct_kernel_name = model.last_kernel_name
+    direct_launches = int(model.last_launch_count)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -428,34 +638,98 @@ def run_b200_arm(args):
         single[nm + "_ms"] = s0.elapsed_time(s1) / 20
     single["reference_cpu_s"] = 205.28  # SURVEY.md section 6, measured with the compiled reference on one core
 
-    # -- whole pipeline, parameter vectors -> criteria: host glue (C++, threads) + one GPU batch
+    # -- whole pipeline, parameter vectors -> criteria: Evaluator::evalBatch = border APs on the host +
+    #    ekg_evaluate (layer fit, simulation in the default mode, curve comparison on the device), B x 2 criteria back.
+    #    Every rank evaluates its own 256 vectors on its own GPU (weak, like `value`); then rank 0 alone evaluates ONE
+    #    batch of 256 through the product's C++ multi-device evaluator on all N GPUs of the box (config 3 as worded:
+    #    "256 vectors sharded across 1/2/4/8 B200" -- strong scaling, 32 vectors per GPU at N = 8).
     pipeline = None
-    if world == 1 and not args.no_pipeline:
+    if not args.no_pipeline:
         try:
             import tempfile
             import hostlib
             wd = tempfile.mkdtemp(prefix="ekg_pipe_")
             ekgio.materialise_testrun(wd)
+            os.environ["EKGSIM_B200_DEVICE"] = str(local)
             ev = hostlib.Evaluator(wd, with_device=True)
             pipeline = {"api": "Evaluator::evalBatch (parameter vectors -> border APs on the host -> ekg_evaluate: layer fit, "
                                "simulation in the default mode, curve comparison -> B x 2 criteria back to the host)", "host_threads": host_cores()}
-            for pb in sorted({B, 1024}):
+            for pb in sorted({B, 1024} if world == 1 else {B}):
                 genes = np.tile(g["params"], ((pb + 255) // 256, 1))[:pb]
                 ev.eval_batch(genes)
                 best = 1e9
                 for _ in range(3):
+                    barrier()
                     t0 = time.perf_counter()
                     crit, viol = ev.eval_batch(genes)
-                    best = min(best, time.perf_counter() - t0)
-                pipeline["batch_%d" % pb] = {"seconds": best, "sims_per_s": pb / best}
+                    dt = time.perf_counter() - t0
+                    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                    if world > 1:
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    best = min(best, float(t.item()))
+                pipeline["batch_%d" % pb] = {"seconds": best, "sims_per_s": world * pb / best, "per_gpu": pb}
             pipeline["sims_per_s"] = pipeline["batch_%d" % B]["sims_per_s"]
             t0 = time.perf_counter()
             for i in range(20):
                 ev.eval(g["params"][i])
             pipeline["single_eval_ms"] = 1e3 * (time.perf_counter() - t0) / 20
             ev.close()
+            # the layer fit alone (the dominant kernel of this pipeline), device time at B = 256 and B = 1
+            nb = g["layer_k"].shape[1]
+            border = np.ascontiguousarray(g["layer_k"][:, [0, 14, nb - 1]])
+            d_b = torch.from_numpy(border).to(dev)
+            d_lk = torch.empty((border.shape[0], nb, 9), dtype=torch.float64, device=dev)
+            fit_ms = {}
+            for fb in (1, 256):
+                for _ in range(2):
+                    model.fit_layers_device(d_b.data_ptr(), fb, 3, d_lk.data_ptr(), mid=14, stream=stream)
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(5):
+                    model.fit_layers_device(d_b.data_ptr(), fb, 3, d_lk.data_ptr(), mid=14, stream=stream)
+                f1.record()
+                torch.cuda.synchronize()
+                fit_ms["B%d" % fb] = f0.elapsed_time(f1) / 5
+            pipeline["fit_ms"] = fit_ms
+            pipeline["fit_bit_identical_to_reference_glue"] = bool(d_lk.cpu().numpy().tobytes() == np.ascontiguousarray(g["layer_k"]).tobytes())
+            barrier()
+            if rank == 0:
+                # strong scaling of ONE 256-vector batch over the N GPUs of the box, inside one process (C++ host threads)
+                evN = hostlib.Evaluator(wd, devices=str(world))
+                genes = g["params"][:256]
+                evN.eval_batch(genes)
+                best = 1e9
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    critN, violN = evN.eval_batch(genes)
+                    best = min(best, time.perf_counter() - t0)
+                want = np.load(os.path.join(ROOT, "tests", "golden", "golden_criteria256.npz"))
+                pipeline["strong_256"] = {"api": "Evaluator::evalBatch on %d device(s) from one process (`ekgSim -batch -devices %d`)" % (evN.n_devices, world),
+                                          "devices": evN.n_devices, "vectors_per_gpu": 256 // max(world, 1), "seconds": best, "sims_per_s": 256 / best,
+                                          "criteria_max_abs_diff_vs_reference_pinned_oracle": float(np.abs(critN - want["criteria"]).max())}
+                evN.close()
+            barrier()
         except Exception as e:
             pipeline = {"error": str(e)}
+
+    # -- BASELINE configs[3]: the synthetic finer heart, z-slab sharded (all ranks)
+    heart = None
+    if not args.no_heart:
+        try:
+            heart = heart_block(args, rank, world, local)
+        except Exception as e:
+            heart = {"error": repr(e)}
+        barrier()
+
+    # -- BASELINE configs[4]: one AMS-DEMO generation (population 100) through the evaluation boundary, all N GPUs (rank 0)
+    generation = None
+    if rank == 0 and not args.no_pipeline:
+        try:
+            generation = generation_block(world)
+        except Exception as e:
+            generation = {"error": repr(e)}
+    barrier()
 
     # -- parity spot check inside the bench (first vectors against the reference-pinned goldens)
     gf = np.load(os.path.join(ROOT, "tests", "golden", "golden_eval_full.npz"))
@@ -482,8 +756,13 @@ def run_b200_arm(args):
     peak_gops_max = sm_count * SFU_LANES_PER_SM * (clocks["sm_max_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     alg_bytes = B * N_VOX * BYTES_PER_VOXEL + 2 * model_partial_bytes(B, L)
+    traffic = None
+    if B == 256 and mode == ek.MODE_DIRECT:
+        pm = profile_metrics(PROFILE_DIRECT, "ecg_kernel")
+        if pm and "dram__bytes_read.sum" in pm:
+            traffic = pm["dram__bytes_read.sum"] + pm.get("dram__bytes_write.sum", 0.0)
     roofline = {
-        "bound": "sfu", "kernel": model.last_kernel_name,
+        "bound": "sfu", "kernel": direct_kernel_name,
         "achieved": achieved_gops, "peak": peak_gops, "unit": "Gop/s (MUFU)", "frac": achieved_gops / peak_gops,
         "peak_basis": "148 SM x 16 MUFU lanes/clk x SM clock sampled under load (%s MHz); at clocks.max.sm the peak is %.0f Gop/s "
                       "-> frac %.3f" % (sm_mhz, peak_gops_max, achieved_gops / peak_gops_max),
@@ -492,14 +771,32 @@ def run_b200_arm(args):
         "note": "DIRECT evaluates all 7 transcendental operations per voxel-timestep; the reciprocal of the depolarisation "
                 "sigmoid runs as a Newton iteration on the FMA pipe, the other 6 on the MUFU/XU pipe",
         "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch at
-        # B = 256 (profiles/r01_ecg_direct_v11_b256_ncu_full.txt): 14.1 MB read + 190.7 MB written (f64 partials)
-        "traffic": 204.8e6 if (B == 256 and mode == ek.MODE_DIRECT) else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch at B = 256, parsed from
+        # the committed summary (null when the batch / mode differs from the captured one or the file is absent)
+        "traffic": traffic, "traffic_source": PROFILE_DIRECT if traffic is not None else None,
         "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                 "note": "algorithmic bytes: 16 B/voxel per individual + f64 partials; the kernel is MUFU-bound, not HBM-bound"},
     }
 
+    # config 1 (ONE simulation, the north_star's Target): the same 7-op accounting on the B = 1 device time
+    single["roofline"] = {"bound": "sfu", "kernel": "ecg_kernel<DIRECT> (+ params + reduce launches)",
+                          "achieved": SFU_OPS_PER_VTS * N_VOX * T_FULL / (single["direct_ms"] * 1e-3) / 1e9, "peak": peak_gops_max,
+                          "unit": "Gop/s (MUFU)", "frac": SFU_OPS_PER_VTS * N_VOX * T_FULL / (single["direct_ms"] * 1e-3) / 1e9 / peak_gops_max,
+                          "peak_basis": "148 SM x 16 lanes x clocks.max.sm (a 0.4 ms call is too short for the clock sampler)"}
+    if pipeline and "fit_ms" in pipeline:
+        # dominant kernel of the genes -> criteria pipeline: fit_descent_kernel, f64 on the FP64 pipe (16 lanes per SM
+        # sub-partition: one warp instruction per 2 cycles).  Instruction counts from the committed ncu summary.
+        pf = profile_metrics(PROFILE_FIT, "fit_descent_kernel")
+        fit_roof = {"bound": "fp64", "kernel": "fit_descent_kernel", "ms_B256": pipeline["fit_ms"]["B256"], "ms_B1": pipeline["fit_ms"]["B1"],
+                    "share_of_pipeline_batch_256": pipeline["fit_ms"]["B256"] * 1e-3 / pipeline["batch_%d" % B]["seconds"] if B == 256 else None,
+                    "source": PROFILE_FIT if pf else None}
+        if pf and "smsp__inst_executed_pipe_fp64.sum" in pf:
+            n64 = pf["smsp__inst_executed_pipe_fp64.sum"]
+            fit_roof.update(achieved=n64 / (pipeline["fit_ms"]["B256"] * 1e-3) / 1e9, peak=sm_count * 4 * 0.5 * sm_mhz * 1e6 / 1e9,
+                            unit="G warp-instructions/s (FP64 pipe)")
+            fit_roof["frac"] = fit_roof["achieved"] / fit_roof["peak"]
+        pipeline["roofline"] = fit_roof
     if separable:
         fp32_peak = sm_count * 128 * sm_mhz * 1e6 / 1e9
         separable["moment_kernel_roofline"] = {"bound": "fp32", "achieved": separable["moment_kernel_fp32_lane_gops"], "peak": fp32_peak,
@@ -514,8 +811,8 @@ def run_b200_arm(args):
         "config": dict(workload_config(args, world), l2="flushed between iterations (256 MiB fill)", ecg_mode=args.mode),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps, "api": "ekg_simulate (C ABI, host buffers)"},
-        "gpu_launches": int(model.last_launch_count) * args.steps,
-        "launches_per_step": int(model.last_launch_count),
+        "gpu_launches": direct_launches * args.steps,
+        "launches_per_step": direct_launches,
         "sims_per_s": value / (N_VOX * T_FULL), "e2e_sims_per_s": e2e_value / (N_VOX * T_FULL),
         "roofline": roofline, "clocks": clocks,
         "automaton": {"ms": automaton_ms, "kernel": "automaton_brick_kernel (4^3-brick frontier, work ring)", "brick_visits": sweeps,
@@ -523,6 +820,7 @@ def run_b200_arm(args):
                       "reference_cpu_s": 2.0},
         "parity_max_err_of_peak": parity,
         "fast_path": fast, "separable_path": separable, "pipeline": pipeline, "single_sim": single,
+        "heart4x": heart, "generation": generation,
     }
 
     if not args.no_cpu_baseline and world == 1:
@@ -533,6 +831,9 @@ def run_b200_arm(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                                     "sample": "%d concurrent processes of the unmodified reference CLI, one vector each, "
                                               "length %d of 400 samples (%.1f s wall)" % (cores, args.ref_length, wall)}
+            if args.ref_full:   # one process, all 400 samples: the reference's ~5 s of fixed cost per run fully amortised
+                vf, sf, wf = reference_sample(T_FULL, 1, vec_lines)
+                line["cpu_baseline"]["full_length_one_process"] = {"seconds": sf[0], "voxel_timesteps_per_s_per_core": vf, "sims_per_s_per_core": 1.0 / sf[0]}
         except Exception as e:  # the reference binary is a prebuilt artefact; say so instead of failing the bench
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
     sys.stdout.flush()

@@ -66,7 +66,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_ftab, m->d_times, m->d_partial, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_near, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
+	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_tail, m->d_ftab, m->d_times, m->d_partial, m->d_partial2, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_near, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -376,7 +376,13 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 	for (int64_t z = 0, i = 0; z < Z; ++z) {
 		for (const int64_t plane_end = (z + 1) * Y * X; i < plane_end; ++i) {
 			uint16_t l = layers[i];
-			if (l & kStartFlag) { m->h_starts.push_back(i); l = (uint16_t)(l - kStartFlag); }  // simulator.cpp:261-264
+			if (l & kStartFlag) {   // simulator.cpp:261-264
+				l = (uint16_t)(l - kStartFlag);
+				// the text format cannot express "start voxel of layer 0" (matrix.h:124-129 maps -v to 0x1000 + v, v >= 1); through
+				// the raw ABI it would be a start voxel outside the model (no brick, no layer to conduct from)
+				if (l == 0) { delete m; return fail(EKG_E_INVALID, "start voxel without a layer (value 0x1000)"); }
+				m->h_starts.push_back(i);
+			}
 			if (l > 255) { delete m; return fail(EKG_E_UNSUPPORTED, "more than 255 layers"); }
 			m->h_layer[(size_t)i] = (uint8_t)l;
 			if (l) { ++m->n_occ; max_layer = std::max<int>(max_layer, l); }
@@ -461,6 +467,7 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		for (int64_t r : m->h_starts) {
 			const int64_t z = r / (Y * X), y = (r / X) % Y, x = r % X;
 			const int32_t bi = index[(size_t)(((z / kBrick) * bY + y / kBrick) * bX + x / kBrick)];
+			if (bi < 0) { free_model(m); return fail(EKG_E_INVALID, "start voxel outside every occupied brick"); }   // cannot happen: a start voxel is occupied
 			if (std::find(m->h_start_bricks.begin(), m->h_start_bricks.end(), bi) == m->h_start_bricks.end()) m->h_start_bricks.push_back(bi);
 		}
 		m->n_bricks = nb;
@@ -468,7 +475,8 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		m->bZ = bZ; m->bY = bY; m->bX = bX;
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_origin, (size_t)std::max<int64_t>(nb, 1) * 4));
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_nbr, nbr.size() * 4));
-		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, ((size_t)nb * 5 + 8) * sizeof(int)));
+		// flag[n] | first_visit[n] | ring[capacity <= max(2n, 2)] | counters[8]   (automaton.cu, run_automaton_bricks)
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, ((size_t)nb * 5 + 16) * sizeof(int)));
 		if (upload(m, m->d_brick_origin, origin.data(), origin.size() * 4) || upload(m, m->d_brick_nbr, nbr.data(), nbr.size() * 4)) { free_model(m); return EKG_E_CUDA; }
 	}
 	int rc = build_ecg_list(m, 0, Z);

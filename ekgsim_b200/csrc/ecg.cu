@@ -78,29 +78,53 @@ struct RowLayout {
 // busy; a 400-sample trace is 12.5 warps, which left one sub-partition with 33 % more MUFU work
 // in the first version of this kernel).  A tile therefore spans up to kMaxVecPerTile parameter
 // vectors; phase A computes the lead-field coefficients for each of them.
+//
+// Voxel slices (small batches): when B*T is not a multiple of the tile size the last tile would be
+// part empty (B = 1, T = 400: tiles of 256 + 144 pairs, 22 % of the lanes idle).  The pair index is
+// therefore generalised to (slice s, vector b, sample t), p = (s*B + b)*T + t with S = 256/gcd(B*T, 256)
+// slices, so that S*B*T is a whole number of tiles (T = 400, B = 1: S = 16, 25 full tiles).  A "virtual
+// vector" vv = s*B + b evaluates vector b on the s-th of S equal sub-ranges of the CTA's segment; the
+// threads of one tile belong to at most kMaxVecPerTile virtual vectors, each with its own sub-range
+// staged in shared memory (rows of one chunk position sit side by side, so the two halves of a warp
+// that straddles a slice boundary read two adjacent 16-byte rows: still one wavefront).  Every thread
+// walks the same number (+-1) of voxels; the partial sums carry the slice in their segment index.
 template <int MODE, int NL>
 __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	constexpr int ROW = RowLayout<MODE, NL>::kFloats;
 	__shared__ __align__(16) float s_vox[kSmemRows * ROW];
 	__shared__ float2 s_lead[kMaxVecPerTile * NL * 3];  // lead coordinate as fp32 hi + lo
 	__shared__ int s_atmax[2];                          // HOISTED: latest activation time of the chunk (float bits)
+	__shared__ int s_sub[kMaxVecPerTile][2];            // voxel sub-range [begin, end) of every virtual vector of the tile
 
 	const Segment sg = a.segs[blockIdx.x];
 	const PairTile tile = a.tiles[blockIdx.y];
-	const int b0 = tile.begin / a.T;
-	const int nb = (tile.end - 1) / a.T - b0 + 1;   // parameter vectors touched by this tile (<= kMaxVecPerTile)
+	const int vv0 = tile.begin / a.T;
+	const int nb = (tile.end - 1) / a.T - vv0 + 1;   // virtual vectors touched by this tile (<= kMaxVecPerTile)
 	const int p = tile.begin + threadIdx.x;
 	const bool live = p < tile.end;
-	const int b = live ? p / a.T : b0;
-	const int t = live ? p - b * a.T : 0;
-	const int bl = b - b0;
+	const int vv = live ? p / a.T : vv0;
+	const int t = live ? p - vv * a.T : 0;
+	const int bl = vv - vv0;
+	const int sl = vv / a.B;                          // voxel slice of this thread
+	const int b = vv - sl * a.B;                      // parameter vector of this thread
 	const int chunk = min(kChunk, kSmemRows / nb);
+	const int seg_n = sg.end - sg.begin;
+	// sub-range of slice s: [begin + n s / S, begin + n (s + 1) / S)  (the whole segment for S = 1)
+	const int my_sub_b = sg.begin + (int)((int64_t)seg_n * sl / a.S);
+	const int my_sub_n = sg.begin + (int)((int64_t)seg_n * (sl + 1) / a.S) - my_sub_b;
+	int n_iter = 0;                                   // chunks of the longest sub-range of the tile
+	for (int v = 0; v < nb; ++v) {
+		const int s = (vv0 + v) / a.B;
+		const int sb = sg.begin + (int)((int64_t)seg_n * s / a.S), se = sg.begin + (int)((int64_t)seg_n * (s + 1) / a.S);
+		if (threadIdx.x == 0) { s_sub[v][0] = sb; s_sub[v][1] = se; }
+		n_iter = max(n_iter, (se - sb + chunk - 1) / chunk);
+	}
 
 	if (threadIdx.x < 2) s_atmax[threadIdx.x] = 0;
 	if (threadIdx.x < nb * NL * 3) {
 		const int v = threadIdx.x / (NL * 3), r = threadIdx.x % (NL * 3);
 		const int l = a.lead0 + r / 3;
-		const double c = l < a.L ? a.leads[((int64_t)(b0 + v) * a.L + l) * 3 + r % 3] : 0.0;
+		const double c = l < a.L ? a.leads[((int64_t)((vv0 + v) % a.B) * a.L + l) * 3 + r % 3] : 0.0;
 		const float hi = (float)c;
 		s_lead[threadIdx.x] = make_float2(hi, (float)(c - (double)hi));
 	}
@@ -128,13 +152,15 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	for (int l = 0; l < NL; ++l) { sum[l] = 0.f; comp[l] = 0.f; }
 
 	int parity = 0;
-	for (int base = sg.begin; base < sg.end; base += chunk, parity ^= 1) {
-		const int n = min(chunk, sg.end - base);
-		__syncthreads();  // phase B of the previous chunk is done with s_vox; s_lead is visible
+	for (int it = 0; it < n_iter; ++it, parity ^= 1) {
+		const int n = max(0, min(chunk, my_sub_n - it * chunk));   // voxels of this thread's sub-range in this chunk
+		__syncthreads();  // phase B of the previous chunk is done with s_vox; s_lead and s_sub are visible
 
-		// ---- phase A: per-(voxel, vector) time-invariant data -> shared memory ----
-		for (int idx = threadIdx.x; idx < n * nb; idx += kEcgThreads) {
+		// ---- phase A: per-(voxel, virtual vector) time-invariant data -> shared memory ----
+		for (int idx = threadIdx.x; idx < chunk * nb; idx += kEcgThreads) {
 			const int j = idx / nb, v = idx - j * nb;
+			const int base = s_sub[v][0] + it * chunk;
+			if (base + j >= s_sub[v][1]) continue;
 			const uint32_t pos = __ldg(a.pos + base + j);
 			const uint32_t mask = __ldg(a.mask + base + j);
 			const float at = __ldg(a.at32 + base + j);
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 			} else {
 				// time-invariant AP factors exp((k4+k5)(at-t0)), exp(k5 (at-t0)); clamped so that
 				// the products with the (also clamped) table entries can never be inf*0
-				const float* Pv = a.params + ((int64_t)(b0 + v) * a.n_layers + (sg.layer - 1)) * kParamStride;
+				const float* Pv = a.params + ((int64_t)((vv0 + v) % a.B) * a.n_layers + (sg.layer - 1)) * kParamStride;
 				const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
 				const float da = at - t0;
 				// row = (h1, h2, G_0..G_{NL-1}, at): the saturated loop only needs the leading part
@@ -272,7 +298,7 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 #pragma unroll
 		for (int l = 0; l < NL; ++l) {
 			const int lead = a.lead0 + l;
-			if (lead < a.L) a.partial[(((int64_t)blockIdx.x * a.B + b) * a.L + lead) * a.T + t] = (double)sum[l] + (double)comp[l];
+			if (lead < a.L) a.partial[((((int64_t)blockIdx.x * a.S + sl) * a.B + b) * a.L + lead) * a.T + t] = (double)sum[l] + (double)comp[l];
 		}
 	}
 }
@@ -495,6 +521,47 @@ __device__ __forceinline__ void store_moments(const MomentArgs& a, const double*
 	}
 }
 
+// The voxels of a segment, thread by thread: lane vl of `lanes` takes the voxels begin + vl, begin + vl + lanes, ...  in
+// blocks of 16 with a fixed trip count (no per-voxel bookkeeping: the loads of an unrolled group are issued together, the
+// fp32 sums are folded into their f64 totals after every block), then the remainder.
+template <int UNROLL, class Body, class Fold>
+__device__ __forceinline__ void walk_voxels(const float4* __restrict__ vox, int begin, int end, int vl, int lanes, Body&& body, Fold&& fold) {
+	const int n = end - begin;
+	int n_mine = vl < n ? (n - vl + lanes - 1) / lanes : 0;
+	const float4* pv = vox + begin + vl;
+	for (; n_mine >= 16; n_mine -= 16) {
+#pragma unroll UNROLL
+		for (int u = 0; u < 16; ++u, pv += lanes) body(__ldg(pv));
+		fold();
+	}
+	for (; n_mine > 0; --n_mine, pv += lanes) body(__ldg(pv));
+	fold();
+}
+
+// series walk over an interior segment; returns the smallest squared lead distance seen by this thread
+template <int NP>
+__device__ __forceinline__ float moment_series_walk(const MomentArgs& a, const Segment& sg, const f2 (&lh)[NP][3], float v45, float nv5, float t0,
+                                                    int vl, int lanes, MomentAcc<NP>& acc, double* s_red) {
+	float r2_min = 3.0e38f;
+	walk_voxels<4>(a.vox, sg.begin, sg.end, vl, lanes,
+		[&](const float4 vx) {
+			const float da = vx.w - t0;
+			const float h1 = mufu_ex2(fminf(v45 * da, 60.f));   // same clamp as the HOISTED kernel and its table
+			const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
+			const f2 PZ = mk2(vx.x, vx.x), PY = mk2(vx.y, vx.y), PX = mk2(vx.z, vx.z);
+#pragma unroll
+			for (int p = 0; p < NP; ++p) {
+				const f2 rz = sub2(lh[p][0], PZ), ry = sub2(lh[p][1], PY), rx = sub2(lh[p][2], PX);
+				const f2 qz = mul2(rz, rz), qy = mul2(ry, ry), qx = mul2(rx, rx);
+				const f2 r2 = add2(add2(qz, qy), qx);
+				r2_min = fminf(r2_min, fminf(lo2(r2), hi2(r2)));
+				acc.add(p, corner_series2(qz, qy, qx, r2), h1, h2);
+			}
+		},
+		[&]() { acc.fold(s_red); });
+	return r2_min;
+}
+
 template <int NP>
 __global__ void __launch_bounds__(256, NP == 1 ? 4 : 3) ecg_moment_interior_kernel(const MomentArgs a) {
 	__shared__ double s_red[256 * NP * 6];
@@ -507,35 +574,9 @@ __global__ void __launch_bounds__(256, NP == 1 ? 4 : 3) ecg_moment_interior_kern
 	load_lead_pairs<NP>(a, bb, lh);
 	const float* Pv = a.params + ((int64_t)bb * a.n_layers + (sg.layer - 1)) * kParamStride;
 	const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
-	const float v45 = -(v4 + v5), nv5 = -v5;
 	MomentAcc<NP> acc;
 	acc.init(s_red);
-	float r2_min = 3.0e38f;
-	int pending = 0;
-	const float4* pv = a.vox + (sg.begin + vl);
-	const float4* const pv_end = a.vox + sg.end;
-	float4 nxt = pv < pv_end ? __ldg(pv) : make_float4(0.f, 0.f, 0.f, 0.f);
-	for (; pv < pv_end; pv += lanes) {
-		const float4 vx = nxt;
-		if (pv + lanes < pv_end) nxt = __ldg(pv + lanes);
-		const float da = vx.w - t0;
-		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));   // same clamp as the HOISTED kernel and its table
-		const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
-		const f2 PZ = mk2(vx.x, vx.x), PY = mk2(vx.y, vx.y), PX = mk2(vx.z, vx.z);
-#pragma unroll
-		for (int p = 0; p < NP; ++p) {
-			const f2 rz = sub2(lh[p][0], PZ), ry = sub2(lh[p][1], PY), rx = sub2(lh[p][2], PX);
-			const f2 qz = mul2(rz, rz), qy = mul2(ry, ry), qx = mul2(rx, rx);
-			const f2 r2 = add2(add2(qz, qy), qx);
-			r2_min = fminf(r2_min, fminf(lo2(r2), hi2(r2)));
-			acc.add(p, corner_series2(qz, qy, qx, r2), h1, h2);
-		}
-		if (++pending == 16) {
-			pending = 0;
-			acc.fold(s_red);
-		}
-	}
-	acc.fold(s_red);
+	const float r2_min = moment_series_walk<NP>(a, sg, lh, -(v4 + v5), -v5, t0, vl, lanes, acc, s_red);
 	// a lead inside the series' validity radius (NaN counts as near): leave this (segment, vector group) to the direct sum
 	const int near = __syncthreads_or(!(r2_min >= kSeriesMinR2));
 	if (threadIdx.x == 0) a.near_flag[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = near;
@@ -546,6 +587,68 @@ __global__ void __launch_bounds__(256, NP == 1 ? 4 : 3) ecg_moment_interior_kern
 // The direct sum.  With d = (+-1, +-1, +-1) the neighbour offsets fold into six per-axis terms p = r + 1, m = 1 - r:
 // |r + d|^2 = (p|m)_z^2 + (p|m)_y^2 + (p|m)_x^2 and d . (r + d) = (p|m)_z + (p|m)_y + (p|m)_x, 4 packed instructions + 2 MUFU +
 // 7 packed for the inverse cube per corner and lead pair (the generic loop issues ~35 scalar instructions per corner and lead).
+template <int NP>
+__device__ __forceinline__ void moment_corner_walk(const MomentArgs& a, const Segment& sg, const bool interior, const f2 (&lh)[NP][3], float v45, float nv5,
+                                                   float t0, int vl, int lanes, MomentAcc<NP>& acc, double* s_red) {
+	const f2 one = mk2(1.f, 1.f);
+	walk_voxels<2>(a.vox, sg.begin, sg.end, vl, lanes,
+		[&](const float4 vx) {
+			const float da = vx.w - t0;
+			// boundary voxels carry the occupancy of their corners, order (dz, dy, dx) = (-,-,-), (-,-,+), ... (+,+,+), in the low
+			// 8 mantissa bits of y (zero for an integer <= 2048)
+			const uint32_t yb = __float_as_uint(vx.y);
+			const uint32_t mask = interior ? 0xffu : (yb & 0xffu);
+			const float pz = vx.x, py = __uint_as_float(yb & ~0xffu), px = vx.z;
+			const float h1 = mufu_ex2(fminf(v45 * da, 60.f));
+			const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
+			constexpr uint32_t kZp = 0xf0u, kYp = 0xccu, kXp = 0xaau;   // corners with dz (dy, dx) = +1
+			const f2 PZ = mk2(pz, pz), PY = mk2(py, py), PX = mk2(px, px);
+#pragma unroll
+			for (int p = 0; p < NP; ++p) {
+				const f2 rz = sub2(lh[p][0], PZ);
+				const f2 ry = sub2(lh[p][1], PY);
+				const f2 rx = sub2(lh[p][2], PX);
+				const f2 zt[2] = {sub2(one, rz), add2(rz, one)};   // [0]: d = -1 -> -(r - 1),  [1]: d = +1 -> r + 1
+				const f2 yt[2] = {sub2(one, ry), add2(ry, one)};
+				const f2 xt[2] = {sub2(one, rx), add2(rx, one)};
+				const f2 zq[2] = {mul2(zt[0], zt[0]), mul2(zt[1], zt[1])};
+				const f2 yq[2] = {mul2(yt[0], yt[0]), mul2(yt[1], yt[1])};
+				const f2 xq[2] = {mul2(xt[0], xt[0]), mul2(xt[1], xt[1])};
+				f2 g = mk2(0.f, 0.f);
+				auto corners = [&](auto all_tag) {
+					constexpr bool ALL = decltype(all_tag)::value;
+#pragma unroll
+					for (int zy = 0; zy < 4; ++zy) {
+						const f2 sq_zy = add2(zq[zy >> 1], yq[zy & 1]);
+						const f2 dt_zy = add2(zt[zy >> 1], yt[zy & 1]);
+#pragma unroll
+						for (int x = 0; x < 2; ++x) {
+							if (ALL || (mask & (1u << (zy * 2 + x))))
+								g = fma2(add2(dt_zy, xt[x]), inv_cube2(add2(sq_zy, xq[x])), g);
+						}
+					}
+				};
+				if (interior) {
+					// the offsets of all 8 corners add up to zero: no centre term
+					corners(std::true_type{});
+				} else {
+					corners(std::false_type{});
+					// S = sum of the offsets of the occupied corners, per axis: (# with +1) - (# with -1), as floats via the
+					// 2^23 trick (values -8..8, no I2F)
+					const int n_occ = __popc(mask);
+					const float szf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kZp) - n_occ)) - 8388616.f;
+					const float syf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kYp) - n_occ)) - 8388616.f;
+					const float sxf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kXp) - n_occ)) - 8388616.f;
+					const f2 sqc = fma2(rx, rx, fma2(ry, ry, mul2(rz, rz)));
+					const f2 sdot = fma2(mk2(szf, szf), rz, fma2(mk2(syf, syf), ry, mul2(mk2(sxf, sxf), rx)));
+					g = fma2(sdot, inv_cube2(sqc), g);
+				}
+				acc.add(p, g, h1, h2);
+			}
+		},
+		[&]() { acc.fold(s_red); });
+}
+
 template <int NP>
 __global__ void __launch_bounds__(256, NP == 1 ? 3 : 2) ecg_moment_corners_kernel(const MomentArgs a) {
 	__shared__ double s_red[256 * NP * 6];
@@ -559,88 +662,52 @@ __global__ void __launch_bounds__(256, NP == 1 ? 3 : 2) ecg_moment_corners_kerne
 	load_lead_pairs<NP>(a, bb, lh);
 	const float* Pv = a.params + ((int64_t)bb * a.n_layers + (sg.layer - 1)) * kParamStride;
 	const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
-	const float v45 = -(v4 + v5), nv5 = -v5;
-	const f2 one = mk2(1.f, 1.f);
 	MomentAcc<NP> acc;
 	acc.init(s_red);
-	int pending = 0;
-	const float4* pv = a.vox + (sg.begin + vl);
-	const float4* const pv_end = a.vox + sg.end;
-	float4 nxt = pv < pv_end ? __ldg(pv) : make_float4(0.f, 0.f, 0.f, 0.f);
-	for (; pv < pv_end; pv += lanes) {
-		const float4 vx = nxt;
-		if (pv + lanes < pv_end) nxt = __ldg(pv + lanes);
-		const float da = vx.w - t0;
-		// boundary voxels carry the occupancy of their corners, order (dz, dy, dx) = (-,-,-), (-,-,+), ... (+,+,+), in the low
-		// 8 mantissa bits of y (zero for an integer <= 2048)
-		const uint32_t yb = __float_as_uint(vx.y);
-		const uint32_t mask = interior ? 0xffu : (yb & 0xffu);
-		const float pz = vx.x, py = __uint_as_float(yb & ~0xffu), px = vx.z;
-		const float h1 = mufu_ex2(fminf(v45 * da, 60.f));
-		const float h2 = mufu_ex2(fminf(nv5 * da, 60.f));
-		constexpr uint32_t kZp = 0xf0u, kYp = 0xccu, kXp = 0xaau;   // corners with dz (dy, dx) = +1
-		const f2 PZ = mk2(pz, pz), PY = mk2(py, py), PX = mk2(px, px);
-#pragma unroll
-		for (int p = 0; p < NP; ++p) {
-			const f2 rz = sub2(lh[p][0], PZ);
-			const f2 ry = sub2(lh[p][1], PY);
-			const f2 rx = sub2(lh[p][2], PX);
-			const f2 zt[2] = {sub2(one, rz), add2(rz, one)};   // [0]: d = -1 -> -(r - 1),  [1]: d = +1 -> r + 1
-			const f2 yt[2] = {sub2(one, ry), add2(ry, one)};
-			const f2 xt[2] = {sub2(one, rx), add2(rx, one)};
-			const f2 zq[2] = {mul2(zt[0], zt[0]), mul2(zt[1], zt[1])};
-			const f2 yq[2] = {mul2(yt[0], yt[0]), mul2(yt[1], yt[1])};
-			const f2 xq[2] = {mul2(xt[0], xt[0]), mul2(xt[1], xt[1])};
-			f2 g = mk2(0.f, 0.f);
-			auto corners = [&](auto all_tag) {
-				constexpr bool ALL = decltype(all_tag)::value;
-#pragma unroll
-				for (int zy = 0; zy < 4; ++zy) {
-					const f2 sq_zy = add2(zq[zy >> 1], yq[zy & 1]);
-					const f2 dt_zy = add2(zt[zy >> 1], yt[zy & 1]);
-#pragma unroll
-					for (int x = 0; x < 2; ++x) {
-						if (ALL || (mask & (1u << (zy * 2 + x))))
-							g = fma2(add2(dt_zy, xt[x]), inv_cube2(add2(sq_zy, xq[x])), g);
-					}
-				}
-			};
-			if (interior) {
-				// the offsets of all 8 corners add up to zero: no centre term
-				corners(std::true_type{});
-			} else {
-				corners(std::false_type{});
-				// S = sum of the offsets of the occupied corners, per axis: (# with +1) - (# with -1), as floats via the
-				// 2^23 trick (values -8..8, no I2F)
-				const int n_occ = __popc(mask);
-				const float szf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kZp) - n_occ)) - 8388616.f;
-				const float syf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kYp) - n_occ)) - 8388616.f;
-				const float sxf = __uint_as_float(0x4B000000u + (uint32_t)(8 + 2 * __popc(mask & kXp) - n_occ)) - 8388616.f;
-				const f2 sqc = fma2(rx, rx, fma2(ry, ry, mul2(rz, rz)));
-				const f2 sdot = fma2(mk2(szf, szf), rz, fma2(mk2(syf, syf), ry, mul2(mk2(sxf, sxf), rx)));
-				g = fma2(sdot, inv_cube2(sqc), g);
-			}
-			acc.add(p, g, h1, h2);
-		}
-		if (++pending == 16) {
-			pending = 0;
-			acc.fold(s_red);
-		}
-	}
-	acc.fold(s_red);
+	moment_corner_walk<NP>(a, sg, interior, lh, -(v4 + v5), -v5, t0, vl, lanes, acc, s_red);
 	__syncthreads();
 	store_moments<NP>(a, s_red);
 }
 
-// ECG[b][l][t] for the samples t >= t_off from the moments: one CTA per (vector, block of 128 samples).
-// Shared memory: the per-layer moments of this vector (segments added in order) and the t-invariant
-// ln(2^(k7/k6)-1) of every layer.  F1, F2 by the expressions of ecg_ftab_kernel, kept in f64.
-__global__ void __launch_bounds__(128) ecg_combine_kernel(const double* __restrict__ layer_k, const double* __restrict__ times,
-                                                           const double* __restrict__ mom, const int32_t* __restrict__ seg_first,
-                                                           double* __restrict__ ecg, int B, int L, int n_layers, int T, int t_off, double t0) {
+// Both kinds of segment in ONE launch, for small batches (a single simulation is bound by launch latencies, not by
+// arithmetic): interior segments by the series, falling back to the direct sum inside the same CTA when a lead is near.
+template <int NP>
+__global__ void __launch_bounds__(256, NP == 1 ? 3 : 2) ecg_moment_fused_kernel(const MomentArgs a) {
+	__shared__ double s_red[256 * NP * 6];
+	const Segment sg = a.segs[blockIdx.x];
+	const bool interior = sg.kind == kSegInterior;
+	const int vb = 1 << a.vb_shift;
+	const int vs = threadIdx.x & (vb - 1), vl = threadIdx.x >> a.vb_shift, lanes = 256 >> a.vb_shift;
+	const int bb = min(blockIdx.y * vb + vs, a.B - 1);
+	f2 lh[NP][3];
+	load_lead_pairs<NP>(a, bb, lh);
+	const float* Pv = a.params + ((int64_t)bb * a.n_layers + (sg.layer - 1)) * kParamStride;
+	const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
+	MomentAcc<NP> acc;
+	acc.init(s_red);
+	if (interior && !a.force_sum) {
+		const float r2_min = moment_series_walk<NP>(a, sg, lh, -(v4 + v5), -v5, t0, vl, lanes, acc, s_red);
+		if (!__syncthreads_or(!(r2_min >= kSeriesMinR2))) { store_moments<NP>(a, s_red); return; }
+		acc.init(s_red);   // every thread resets its own column only
+	}
+	moment_corner_walk<NP>(a, sg, interior, lh, -(v4 + v5), -v5, t0, vl, lanes, acc, s_red);
+	__syncthreads();
+	store_moments<NP>(a, s_red);
+}
+
+// ECG[b][l][t] for the samples t >= t_off from the moments: one CTA per (vector, block of 32 samples), threads =
+// 32 samples x 8 layer lanes (lane g takes the layers g, g + 8, ...; a single simulation still yields 13 CTAs x 256
+// threads of f64 pow/exp work instead of 4 x 128).  Shared memory: the per-layer moments of this vector (segments
+// added in order) and the lanes' partial sums, added in lane order -> deterministic.  F1, F2 by the expressions of
+// ecg_ftab_kernel, kept in f64; ln(2^(k7/k6)-1) per (vector, layer) comes from ecg_params_kernel.
+constexpr int kCombSamples = 32, kCombLanes = 8;
+__global__ void __launch_bounds__(kCombSamples * kCombLanes) ecg_combine_kernel(const double* __restrict__ layer_k, const double* __restrict__ tail,
+                                                                               const double* __restrict__ times, const double* __restrict__ mom,
+                                                                               const int32_t* __restrict__ seg_first, double* __restrict__ ecg,
+                                                                               int B, int L, int n_layers, int T, int t_off, double t0) {
 	extern __shared__ double s_dyn[];
 	double* s_mom = s_dyn;                       // [n_layers][L][3]
-	double* s_tail = s_dyn + n_layers * L * 3;   // [n_layers]
+	double* s_acc = s_dyn + n_layers * L * 3;    // [kCombLanes][4][kCombSamples + 1]
 	const int b = blockIdx.y;
 	for (int o = threadIdx.x; o < n_layers * L * 3; o += blockDim.x) {
 		const int layer = o / (L * 3), r = o - layer * (L * 3);
@@ -648,42 +715,73 @@ __global__ void __launch_bounds__(128) ecg_combine_kernel(const double* __restri
 		for (int sgi = seg_first[layer]; sgi < seg_first[layer + 1]; ++sgi) s += mom[((int64_t)sgi * B + b) * L * 3 + r];
 		s_mom[o] = s;
 	}
-	for (int layer = threadIdx.x; layer < n_layers; layer += blockDim.x) {
-		const double* k = layer_k + ((int64_t)b * n_layers + layer) * 9;
-		s_tail[layer] = log(pow(2.0, k[7] / k[6]) - 1.0);
-	}
 	__syncthreads();
-	const int t = t_off + blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= T) return;
-	const double tt = times[t];
+	const int ts = threadIdx.x & (kCombSamples - 1), g = threadIdx.x / kCombSamples;
+	const int t = t_off + blockIdx.x * kCombSamples + ts;
+	const bool valid = t < T;
+	const double tt = valid ? times[t] : 0.0;
 	const double lim = 60.0 * 0.69314718055994530942;
 	for (int l0 = 0; l0 < L; l0 += 4) {
 		double acc[4] = {0.0, 0.0, 0.0, 0.0};
-		for (int layer = 0; layer < n_layers; ++layer) {
-			if (seg_first[layer] == seg_first[layer + 1]) continue;   // no voxels in this layer (inside the slab)
-			const double* k = layer_k + ((int64_t)b * n_layers + layer) * 9;
-			const double R = 1.0 - pow(1.0 + exp(-k[7] * (tt - k[8]) + s_tail[layer]), -(k[6] / k[7]));
-			const double F1 = k[2] * (1.0 - k[3]) * R * exp(fmin(-(k[4] + k[5]) * (tt - t0), lim));
-			const double F2 = k[2] * k[3] * R * exp(fmin(-k[5] * (tt - t0), lim));
-			const double* M = s_mom + layer * L * 3;
+		if (valid) {
+			for (int layer = g; layer < n_layers; layer += kCombLanes) {
+				if (seg_first[layer] == seg_first[layer + 1]) continue;   // no voxels in this layer (inside the slab)
+				const double* k = layer_k + ((int64_t)b * n_layers + layer) * 9;
+				const double R = 1.0 - pow(1.0 + exp(-k[7] * (tt - k[8]) + tail[(int64_t)b * n_layers + layer]), -(k[6] / k[7]));
+				const double F1 = k[2] * (1.0 - k[3]) * R * exp(fmin(-(k[4] + k[5]) * (tt - t0), lim));
+				const double F2 = k[2] * k[3] * R * exp(fmin(-k[5] * (tt - t0), lim));
+				const double* M = s_mom + layer * L * 3;
 #pragma unroll
-			for (int l = 0; l < 4; ++l)
-				if (l0 + l < L) acc[l] += k[0] * M[(l0 + l) * 3] + F1 * M[(l0 + l) * 3 + 1] + F2 * M[(l0 + l) * 3 + 2];
+				for (int l = 0; l < 4; ++l)
+					if (l0 + l < L) acc[l] += k[0] * M[(l0 + l) * 3] + F1 * M[(l0 + l) * 3 + 1] + F2 * M[(l0 + l) * 3 + 2];
+			}
 		}
+		if (l0) __syncthreads();   // the previous pass is done with s_acc
 #pragma unroll
-		for (int l = 0; l < 4; ++l) if (l0 + l < L) ecg[((int64_t)b * L + l0 + l) * T + t] = acc[l];
+		for (int l = 0; l < 4; ++l) s_acc[(g * 4 + l) * (kCombSamples + 1) + ts] = acc[l];
+		__syncthreads();
+		if (threadIdx.x < 4 * kCombSamples) {
+			const int l = threadIdx.x / kCombSamples;   // one (lead, sample) per thread of the first four warps
+			const int tw = t_off + blockIdx.x * kCombSamples + ts;
+			if (l0 + l < L && tw < T) {
+				double r = s_acc[l * (kCombSamples + 1) + ts];
+#pragma unroll
+				for (int q = 1; q < kCombLanes; ++q) r += s_acc[(q * 4 + l) * (kCombSamples + 1) + ts];
+				ecg[((int64_t)b * L + l0 + l) * T + tw] = r;
+			}
+		}
 	}
 }
 
 // ---- partial sums -> ECG, fixed order ------------------------------------------------------------
-// (the time loop may cover only the first T_loop of T samples: row stride T on the output side)
-__global__ void __launch_bounds__(256) ecg_reduce_kernel(const double* __restrict__ partial, double* __restrict__ ecg, int n_segs, int64_t n_out,
-                                                         int T_loop, int T) {
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_out) return;
+// partial is [n_rows][n_out] (n_rows = segments x slices).  A CTA owns 32 outputs and one block of kRedRows rows
+// (grid.y); its 8 warps each add every 8th row of the block (coalesced 256-byte reads, 8 independent chains instead of
+// one chain of n_rows dependent loads -- a single simulation has only 800 outputs but ~10^4 rows), the 8 sub-sums are
+// added in warp order.  More than one row block: the block sums go to a scratch array and a second launch adds those.
+// Every order is fixed -> bitwise run-to-run determinism.
+// (the time loop may cover only the first T_loop of T samples: row stride T on the output side of the final pass)
+constexpr int kRedGroups = 8;
+constexpr int kRedRows = 512;
+__global__ void __launch_bounds__(32 * kRedGroups) ecg_reduce_kernel(const double* __restrict__ partial, double* __restrict__ out, int n_rows,
+                                                                   int64_t n_out, int T_loop, int T, int final_pass) {
+	__shared__ double s_part[kRedGroups][33];
+	const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+	const int64_t i = (int64_t)blockIdx.x * 32 + o;
+	const int r0 = blockIdx.y * kRedRows, r1 = min(n_rows, r0 + kRedRows);
 	double s = 0.0;
-	for (int k = 0; k < n_segs; ++k) s += partial[(int64_t)k * n_out + i];
-	ecg[(i / T_loop) * T + i % T_loop] = s;
+	if (i < n_out) {
+#pragma unroll 4
+		for (int k = r0 + g; k < r1; k += kRedGroups) s += __ldg(partial + (int64_t)k * n_out + i);
+	}
+	s_part[g][o] = s;
+	__syncthreads();
+	if (g == 0 && i < n_out) {
+		double r = s_part[0][o];
+#pragma unroll
+		for (int q = 1; q < kRedGroups; ++q) r += s_part[q][o];
+		if (final_pass) out[(i / T_loop) * T + i % T_loop] = r;
+		else out[(int64_t)blockIdx.y * n_out + i] = r;
+	}
 }
 
 // ---- curve comparison on the device (calculateFitness, sim.cpp:600-702; vectorMath.h) -----------------
@@ -764,7 +862,8 @@ int run_criteria(ekg_model* m, const double* d_ecg, const double* d_targets, con
 // ---- per-(vector, layer) coefficient tables, f64 -> f32 -------------------------------------------
 // P[0..11] = -k1 log2e, -k4 log2e, -k5 log2e, -k7 log2e, log2(2^(k7/k6)-1), -k6/k7, k2(1-k3), k2 k3,
 //            k0, hi(k8), lo(k8), t0
-__global__ void ecg_params_kernel(const double* __restrict__ layer_k, float* __restrict__ P, int64_t n, float t0, int* __restrict__ k1min) {
+__global__ void ecg_params_kernel(const double* __restrict__ layer_k, float* __restrict__ P, double* __restrict__ tail, int64_t n, float t0,
+                                  int* __restrict__ k1min) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const double* k = layer_k + i * 9;
@@ -781,7 +880,9 @@ __global__ void ecg_params_kernel(const double* __restrict__ layer_k, float* __r
 	p[1] = (float)(-k[4] * log2e);
 	p[2] = (float)(-k[5] * log2e);
 	p[3] = (float)(-k[7] * log2e);
-	p[4] = (float)(log(pow(2.0, k[7] / k[6]) - 1.0) * log2e);
+	const double tc = log(pow(2.0, k[7] / k[6]) - 1.0);   // ln(2^(k7/k6) - 1), Wohlfart.h:200
+	tail[i] = tc;
+	p[4] = (float)(tc * log2e);
 	p[5] = (float)(-(k[6] / k[7]));
 	p[6] = (float)(k[2] * (1.0 - k[3]));
 	p[7] = (float)(k[2] * k[3]);
@@ -996,13 +1097,14 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 
 	const int64_t n_bl = B * m->n_layers;
 	if ((rc = ensure(&m->d_params, &m->params_cap, n_bl * kParamStride))) return rc;
+	if ((rc = ensure(&m->d_tail, &m->tail_cap, n_bl))) return rc;
 	const bool want_k1 = mode == EKG_MODE_SEPARABLE && !(hints.k1_min > 0);
 	if (want_k1) {
 		if (!m->d_k1min) EKG_CUDA(cudaMalloc(&m->d_k1min, 2 * sizeof(int)));
 		EKG_CUDA(cudaMemsetAsync(m->d_k1min, 0x7f, sizeof(int), st));  // 0x7f7f7f7f = 3.4e38f
 		EKG_CUDA(cudaMemsetAsync(m->d_k1min + 1, 0, sizeof(int), st));
 	}
-	ecg_params_kernel<<<(int)((n_bl + 127) / 128), 128, 0, st>>>(d_layer_k, m->d_params, n_bl, (float)m->t0, want_k1 ? m->d_k1min : nullptr);
+	ecg_params_kernel<<<(int)((n_bl + 127) / 128), 128, 0, st>>>(d_layer_k, m->d_params, m->d_tail, n_bl, (float)m->t0, want_k1 ? m->d_k1min : nullptr);
 	EKG_CUDA(cudaGetLastError());
 	++m->last_launches;
 	if (want_k1) {
@@ -1029,7 +1131,7 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	if (mode == EKG_MODE_SEPARABLE) {
 		loop_mode = EKG_MODE_HOISTED;
 		const double k1_min = hints.k1_min;
-		const size_t smem_need = (size_t)(m->n_layers * L * 3 + m->n_layers) * sizeof(double);
+		const size_t smem_need = (size_t)(m->n_layers * L * 3 + kCombLanes * 4 * (kCombSamples + 1)) * sizeof(double);
 		if (k1_min > 0 && smem_need <= 48 * 1024) {
 			// k1 log2e (t - at) > 25 (+ a margin of 1e-3 ms for the fp32 evaluation of the same test)
 			const double t_sat = m->at_max + 25.0 / (k1_min * 1.4426950408889634074) + 1e-3;
@@ -1042,10 +1144,24 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	bool need_k0 = timed && !m->ev_recorded;   // first sub-batch of a timed call: event before the first main kernel
 
 	if (T_loop > 0) {
-		// work decomposition: pair tiles (<= kEcgThreads pairs, <= kMaxVecPerTile vectors each) x segments
-		if (m->tiles_B != B || m->tiles_T != T_loop) {
+		// voxel slices: S * B * T_loop a whole number of tiles when the batch alone would leave a noticeable part of its
+		// last tile empty (see ecg_kernel); S = 1 for anything with more than a few dozen tiles
+		int64_t S = 1;
+		{
+			const int64_t P1 = B * T_loop, tiles1 = (P1 + kEcgThreads - 1) / kEcgThreads;
+			static const int64_t max_s = getenv("EKGSIM_B200_ECG_SLICES") ? std::max(1, atoi(getenv("EKGSIM_B200_ECG_SLICES"))) : 16;
+			if (P1 % kEcgThreads != 0 && tiles1 <= 32) {
+				int64_t g = P1, h = kEcgThreads;
+				while (h) { const int64_t r = g % h; g = h; h = r; }
+				S = std::min<int64_t>(kEcgThreads / g, max_s);
+			}
+		}
+		const int64_t VB = S * B;   // virtual vectors
+		// work decomposition: pair tiles (<= kEcgThreads pairs, <= kMaxVecPerTile virtual vectors each) x segments
+		if (m->tiles_B != VB || m->tiles_T != T_loop) {
 			std::vector<PairTile> tiles;
-			const int64_t P = B * T_loop;
+			const int64_t P = VB * T_loop;
+			if (P >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "B * n_steps must be below 2^31");
 			for (int64_t p = 0; p < P;) {
 				int64_t e = std::min<int64_t>(p + kEcgThreads, P);
 				const int64_t b0 = p / T_loop;
@@ -1056,20 +1172,26 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 			if ((rc = ensure(&m->d_tiles, &m->tiles_cap, (int64_t)tiles.size()))) return rc;
 			EKG_CUDA(cudaMemcpyAsync(m->d_tiles, tiles.data(), tiles.size() * sizeof(PairTile), cudaMemcpyHostToDevice, st));
 			EKG_CUDA(cudaStreamSynchronize(st));
-			m->n_tiles = (int64_t)tiles.size(); m->tiles_B = B; m->tiles_T = T_loop;
+			m->n_tiles = (int64_t)tiles.size(); m->tiles_B = VB; m->tiles_T = T_loop;
 		}
-		if (B * T_loop >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "B * n_steps must be below 2^31");
-		// ~100 waves of CTAs: the tail of the last wave costs about 1/waves of the launch
+		// ~100 waves of CTAs: the tail of the last wave costs about 1/waves of the launch.  A thread walks seg_len / S
+		// voxels: at least kMinSub of them (a CTA pays ~1 us of fixed cost: parameter loads, phase A, two barriers)
+		static const int64_t kMinSub = getenv("EKGSIM_B200_ECG_SUB") ? std::max(32, atoi(getenv("EKGSIM_B200_ECG_SUB"))) : 128;
 		const int64_t target_ctas = (int64_t)m->sm_count * 4 * 96;
 		int64_t want_segs = (target_ctas + m->n_tiles - 1) / m->n_tiles;
 		int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
-		seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
-		seg_len = (seg_len + kChunk - 1) / kChunk * kChunk;
+		if (S == 1) {
+			seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
+			seg_len = (seg_len + kChunk - 1) / kChunk * kChunk;
+		} else {
+			seg_len = std::max<int64_t>(kMinSub * S, std::min<int64_t>(seg_len, 16384));
+			seg_len = (seg_len + S - 1) / S * S;
+		}
 		if ((rc = build_segments(m, seg_len, st))) return rc;
 		if (m->n_tiles > 65535) return fail(EKG_E_UNSUPPORTED, "too many (vector, sample) pairs for one launch (B * n_steps <= 16.7 M)");
 
 		const int64_t n_out = B * L * T_loop;
-		if ((rc = ensure(&m->d_partial, &m->partial_cap, m->n_segs * n_out))) return rc;
+		if ((rc = ensure(&m->d_partial, &m->partial_cap, m->n_segs * S * n_out))) return rc;
 		if (loop_mode == EKG_MODE_HOISTED) {
 			if ((rc = ensure(&m->d_ftab, &m->ftab_cap, n_bl * 2 * T_loop))) return rc;
 			ecg_ftab_kernel<<<(int)((n_bl * T_loop + 255) / 256), 256, 0, st>>>(d_layer_k, d_t64, m->d_ftab, n_bl, (int)T_loop, (double)(float)m->t0);
@@ -1082,6 +1204,7 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		a.t_hi = m->d_times; a.t_lo = m->d_times + T;
 		a.partial = m->d_partial;
 		a.n_segs = (int32_t)m->n_segs; a.B = (int32_t)B; a.L = (int32_t)L; a.T = (int32_t)T_loop; a.n_layers = m->n_layers;
+		a.S = (int32_t)S;
 
 		const dim3 grid((unsigned)m->n_segs, (unsigned)m->n_tiles, 1);
 		const int threads = kEcgThreads;
@@ -1102,9 +1225,22 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 			++m->last_launches;
 		}
 		if (T_loop == T && timed) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
-		ecg_reduce_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(m->d_partial, d_ecg, (int)m->n_segs, n_out, (int)T_loop, (int)T);
-		EKG_CUDA(cudaGetLastError());
-		++m->last_launches;
+		{
+			const int64_t n_rows = m->n_segs * S, n_blocks = (n_rows + kRedRows - 1) / kRedRows;
+			const unsigned gx = (unsigned)((n_out + 31) / 32);
+			if (n_blocks > 1) {
+				if (n_blocks > kRedRows) return fail(EKG_E_UNSUPPORTED, "too many partial sums for the two-pass reduction");
+				if ((rc = ensure(&m->d_partial2, &m->partial2_cap, n_blocks * n_out))) return rc;
+				ecg_reduce_kernel<<<dim3(gx, (unsigned)n_blocks), 32 * kRedGroups, 0, st>>>(m->d_partial, m->d_partial2, (int)n_rows, n_out, (int)T_loop, (int)T, 0);
+				EKG_CUDA(cudaGetLastError());
+				++m->last_launches;
+				ecg_reduce_kernel<<<dim3(gx, 1), 32 * kRedGroups, 0, st>>>(m->d_partial2, d_ecg, (int)n_blocks, n_out, (int)T_loop, (int)T, 1);
+			} else {
+				ecg_reduce_kernel<<<dim3(gx, 1), 32 * kRedGroups, 0, st>>>(m->d_partial, d_ecg, (int)n_rows, n_out, (int)T_loop, (int)T, 1);
+			}
+			EKG_CUDA(cudaGetLastError());
+			++m->last_launches;
+		}
 	}
 
 	if (T_loop < T) {
@@ -1136,12 +1272,18 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		bool corners = a.nbr.n == 8 && getenv("EKGSIM_B200_GENERIC_MOMENTS") == nullptr;
 		for (int k = 0; corners && k < 8; ++k)
 			corners = a.nbr.bit[k] == corner_bit[k] && a.nbr.dz[k] == ((k & 4) ? 1 : -1) && a.nbr.dy[k] == ((k & 2) ? 1 : -1) && a.nbr.dx[k] == ((k & 1) ? 1 : -1);
+		// small batches: one launch for both kinds of segment (EKGSIM_B200_MOMENT_FUSED=0/1 overrides)
+		static const int fused_env = getenv("EKGSIM_B200_MOMENT_FUSED") ? atoi(getenv("EKGSIM_B200_MOMENT_FUSED")) : -1;
+		const bool fused = fused_env >= 0 ? fused_env != 0 : groups <= 2;
 		if (m->n_msegs > 0) {
 			const dim3 grid((unsigned)m->n_msegs, (unsigned)groups, 1);
 			for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
 				ma.lead0 = lead0;
 				const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
-				if (corners) {
+				if (corners && fused) {
+					if (nl <= 2) ecg_moment_fused_kernel<1><<<grid, 256, 0, st>>>(ma);
+					else ecg_moment_fused_kernel<2><<<grid, 256, 0, st>>>(ma);
+				} else if (corners) {
 					// interior segments by the series (raising near_flag where a lead is too close), then the boundary
 					// segments and whatever was flagged by the direct sum
 					if (!ma.force_sum) {
@@ -1161,10 +1303,10 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		}
 		if (timed) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
 		const int64_t n_late = T - T_loop;
-		const size_t smem = (size_t)(m->n_layers * L * 3 + m->n_layers) * sizeof(double);
-		const dim3 cgrid((unsigned)((n_late + 127) / 128), (unsigned)B, 1);
-		ecg_combine_kernel<<<cgrid, 128, smem, st>>>(d_layer_k, d_t64, m->d_mom, m->d_mseg_first, d_ecg, (int)B, (int)L, m->n_layers, (int)T,
-		                                            (int)T_loop, (double)(float)m->t0);
+		const size_t smem = (size_t)(m->n_layers * L * 3 + kCombLanes * 4 * (kCombSamples + 1)) * sizeof(double);
+		const dim3 cgrid((unsigned)((n_late + kCombSamples - 1) / kCombSamples), (unsigned)B, 1);
+		ecg_combine_kernel<<<cgrid, kCombSamples * kCombLanes, smem, st>>>(d_layer_k, m->d_tail, d_t64, m->d_mom, m->d_mseg_first, d_ecg, (int)B, (int)L,
+		                                                                  m->n_layers, (int)T, (int)T_loop, (double)(float)m->t0);
 		EKG_CUDA(cudaGetLastError());
 		++m->last_launches;
 		m->last_kernel = T_loop > 0 ? "ecg_kernel<HOISTED> + ecg_moment_kernel" : "ecg_moment_kernel";

@@ -47,7 +47,7 @@ struct Segment {
 };
 constexpr int32_t kSegInterior = 1;
 
-// A run of consecutive (vector b, sample t) pairs, p = b*T + t.
+// A run of consecutive (slice s, vector b, sample t) pairs, p = (s*B + b)*T + t.
 struct PairTile {
 	int32_t begin, end;
 };
@@ -63,8 +63,9 @@ struct EcgArgs {
 	const double* leads;    // [B][L][3] (z,y,x)
 	const float* t_hi;      // [T] time samples, hi/lo split of the f64 value
 	const float* t_lo;
-	double* partial;        // [n_segs][B][L][T]
+	double* partial;        // [n_segs][S][B][L][T]
 	int32_t n_segs, B, L, T, n_layers;
+	int32_t S;              // voxel slices per segment (ecg.cu: pair index = (slice, vector, sample)); 1 = none
 	int32_t lead0;          // first lead handled by this launch (L > kMaxLeadsPerPass -> several passes)
 	NbrTable nbr;
 };
@@ -194,7 +195,7 @@ struct ekg_model {
 
 	// per-call scratch (grown on demand)
 	ekg::Segment* d_segs = nullptr;  int64_t segs_cap = 0;  int64_t n_segs = 0;  int64_t seg_len = 0;
-	ekg::PairTile* d_tiles = nullptr; int64_t tiles_cap = 0; int64_t n_tiles = 0; int64_t tiles_B = 0, tiles_T = 0;
+	ekg::PairTile* d_tiles = nullptr; int64_t tiles_cap = 0; int64_t n_tiles = 0; int64_t tiles_B = 0, tiles_T = 0;  // tiles_B = S * B
 	// SEPARABLE path: its own segment table (sized for voxel x vector work, not for the time loop)
 	ekg::Segment* d_msegs = nullptr; int64_t msegs_cap = 0;  int64_t n_msegs = 0;  int64_t mseg_len = 0;
 	int32_t* d_mseg_first = nullptr; int64_t mseg_first_cap = 0;   // first segment of every layer, n_layers + 1 entries
@@ -202,11 +203,13 @@ struct ekg_model {
 	int32_t* d_near = nullptr;       int64_t near_cap = 0;         // MomentArgs::near_flag
 	int* d_k1min = nullptr;                                        // [2] float bits of min k1 / max decay rate over (vector, layer), by ecg_params_kernel
 	float* d_params = nullptr;       int64_t params_cap = 0;
+	double* d_tail = nullptr;        int64_t tail_cap = 0;         // ln(2^(k7/k6) - 1) per (vector, layer), f64 (ecg_params_kernel)
 	float* d_ftab = nullptr;         int64_t ftab_cap = 0;
 	float* d_times = nullptr;        int64_t times_cap = 0;
 	double times_t_start = 0, times_t_step = 0;  int64_t times_T = 0;  // what d_times currently holds
 	std::vector<double> h_times;     // host copy of the f64 sample times
 	double* d_partial = nullptr;     int64_t partial_cap = 0;
+	double* d_partial2 = nullptr;    int64_t partial2_cap = 0;   // row-block sums of the two-pass reduction
 	double* d_io_k = nullptr;        int64_t io_k_cap = 0;     // staging for the host-buffer entry point
 	double* d_io_leads = nullptr;    int64_t io_leads_cap = 0;
 	double* d_io_ecg = nullptr;      int64_t io_ecg_cap = 0;

@@ -394,6 +394,25 @@ inline int steepest_descent(const LayerFitTarget& f, AP& x0, const AP& d, double
 	return iterations;
 }
 
+/// "all" | "<count>" | "<id>,<id>,..." -> device ids (new; `-devices` of the CLI, EKGSIM_B200_DEVICES).  An id may repeat:
+/// two replicas on one GPU (that is how a single-GPU box exercises the multi-device code).
+inline std::vector<int> parse_device_list(const std::string& spec) {
+	std::vector<int> ids;
+	const int have = ekg_device_count();
+	if (spec.empty()) return ids;
+	if (spec == "all") { for (int i = 0; i < have; ++i) ids.push_back(i); return ids; }
+	if (spec.find(',') == std::string::npos) {
+		const int n = atoi(spec.c_str());
+		if (n <= 0) throw std::runtime_error("bad device list: " + spec);
+		for (int i = 0; i < n; ++i) ids.push_back(i);
+	} else {
+		std::istringstream in(spec);
+		for (std::string tok; std::getline(in, tok, ',');) if (!tok.empty()) ids.push_back(atoi(tok.c_str()));
+	}
+	for (int id : ids) if (id < 0 || id >= have) throw std::runtime_error("no such CUDA device in device list: " + spec);
+	return ids;
+}
+
 // ---- the evaluator ---------------------------------------------------------------------------------------------
 class Evaluator {
 public:
@@ -406,6 +425,9 @@ public:
 
 private:
 	std::unique_ptr<EkgSim> sim;
+	/// further GPUs (new): evalBatch splits its batch over `sim` and these, one host thread per device -- individuals
+	/// over GPUs without a collective, the in-process form of the reference's MPI task farm (ParallelFramework.h:388-429)
+	std::vector<std::unique_ptr<EkgSim>> replicas;
 	std::vector<std::vector<double>> targets;
 	std::vector<double> targetOffsets;
 	enum Interp { unknown = 0, endo_epi = 1, endo_mid_epi = 2 } interp = unknown;
@@ -428,10 +450,14 @@ private:
 public:
 	/// withDevice = false builds everything that lives on the host (settings, leads, targets, layer-AP
 	/// construction) but never touches the GPU: eval()/evalBatch() then throw, layerCoefficients() works.
-	explicit Evaluator(const char* ini = "simulator.ini", bool withDevice = true) {
+	/// `devices`: GPUs to evaluate batches on (empty: EKGSIM_B200_DEVICES if set -- "all", a count or a list --, else the one
+	/// device of EKGSIM_B200_DEVICE / 0).  eval() always runs on the first.
+	explicit Evaluator(const char* ini = "simulator.ini", bool withDevice = true, std::vector<int> devices = std::vector<int>()) {
 		std::cerr << "***** setting up Ekg Simulator *****************************\n";
 		settings.load(ini);
 		sim.reset(new EkgSim);
+		if (withDevice && devices.empty()) if (const char* e = std::getenv("EKGSIM_B200_DEVICES")) devices = parse_device_list(e);
+		if (!devices.empty()) sim->setDevice(devices[0]);
 		sim->loadSettings(ini);
 		sim->loadTransferMatrix();
 		sim->loadMeasuringPoints();
@@ -464,9 +490,22 @@ public:
 			std::cerr << "   endo-epi min delay is also a criterion (" << settings.endoEpiMinCriterionDelay << ")\n";
 		}
 		std::cerr << " total number of criteria = " << deducedNumOfCriteria << "\n\n";
+		if (withDevice && devices.size() > 1) {
+			std::vector<std::string> errors(devices.size());
+			std::vector<std::thread> pool;
+			replicas.resize(devices.size() - 1);
+			for (size_t d = 1; d < devices.size(); ++d)
+				pool.emplace_back([&, d]() {
+					try { replicas[d - 1] = sim->replicate(devices[d]); } catch (std::exception& e) { errors[d] = e.what(); }
+				});
+			for (std::thread& t : pool) t.join();
+			for (const std::string& e : errors) if (!e.empty()) throw std::runtime_error(e);
+			std::cerr << " evaluating batches on " << devices.size() << " GPUs\n\n";
+		}
 	}
 
 	EkgSim& simulator() { return *sim; }
+	size_t numDevices() const { return 1 + replicas.size(); }
 	size_t numGenes() const { return numWohlfartParams + numDisplacementParams; }
 
 	/// one individual: returns the violation, fills `result` with the criteria (SimImplementation::eval)
@@ -538,11 +577,15 @@ public:
 		if (!run.empty() && fitOnDevice && criteriaOnDevice()) {
 			// plain settings (one criterion per lead, no peak-position criterion): the comparison runs on the device too,
 			// B x leads doubles come back instead of the ECGs
-			sim->moveMeasuringPointsTo(inds[run[0]].leads);
-			std::vector<double> tg(L * targets[0].size()), crit;
+			std::vector<double> tg(L * targets[0].size()), crit(run.size() * L);
 			for (size_t m = 0; m < L; ++m) std::copy(targets[m].begin(), targets[m].end(), tg.begin() + m * targets[0].size());
-			sim->evaluateBatchCriteria(k.data(), nb, interp == endo_epi ? 0 : midLayer(), fitOffsets(), 0.5, 1e-3, 100, leads.data(), run.size(),
-			                           tg.data(), targets[0].size(), targetOffsets.data(), (int)settings.comparisonMode, crit);
+			onDevices(run.size(), [&](EkgSim& s, size_t b0, size_t b1) {
+				s.moveMeasuringPointsTo(inds[run[b0]].leads);
+				std::vector<double> part;
+				s.evaluateBatchCriteria(&k[b0 * nb * 9], nb, interp == endo_epi ? 0 : midLayer(), fitOffsets(), 0.5, 1e-3, 100, &leads[b0 * L * 3],
+				                        b1 - b0, tg.data(), targets[0].size(), targetOffsets.data(), (int)settings.comparisonMode, part);
+				std::copy(part.begin(), part.end(), crit.begin() + b0 * L);
+			});
 			std::vector<size_t> slotOf(B, (size_t)-1);
 			for (size_t r = 0; r < run.size(); ++r) slotOf[run[r]] = r;
 			for (size_t i = 0; i < B; ++i) {
@@ -553,10 +596,17 @@ public:
 			return;
 		}
 		if (!run.empty()) {
-			sim->moveMeasuringPointsTo(inds[run[0]].leads);  // lead count / bookkeeping; positions travel in `leads`
-			if (fitOnDevice) sim->evaluateBatch(k.data(), nb, interp == endo_epi ? 0 : midLayer(), fitOffsets(), 0.5, 1e-3, 100, leads.data(), run.size(), ecg, nullptr);
-			else sim->runBatch(k.data(), leads.data(), run.size(), ecg);
-			T = ecg.size() / (run.size() * L);
+			const size_t kPer = (fitOnDevice ? nb : nl) * 9;
+			const EkgSim& s0 = *sim;
+			T = (size_t)std::ceil(s0.settingsView().simulationLength / s0.settingsView().simulationTimeStep);
+			ecg.assign(run.size() * L * T, 0.0);
+			onDevices(run.size(), [&](EkgSim& s, size_t b0, size_t b1) {
+				s.moveMeasuringPointsTo(inds[run[b0]].leads);  // lead count / bookkeeping; positions travel in `leads`
+				std::vector<double> part;
+				if (fitOnDevice) s.evaluateBatch(&k[b0 * kPer], nb, interp == endo_epi ? 0 : midLayer(), fitOffsets(), 0.5, 1e-3, 100, &leads[b0 * L * 3], b1 - b0, part, nullptr);
+				else s.runBatch(&k[b0 * kPer], &leads[b0 * L * 3], b1 - b0, part);
+				std::copy(part.begin(), part.end(), ecg.begin() + b0 * L * T);
+			});
 		}
 		std::vector<size_t> slot(B, (size_t)-1);
 		for (size_t r = 0; r < run.size(); ++r) slot[run[r]] = r;
@@ -609,6 +659,24 @@ public:
 	}
 
 private:
+	/// fn(simulator, begin, end) for a contiguous, balanced share of [0, n) on every device, one host thread per
+	/// further device (the handles are independent; the C ABI keeps its error string per thread)
+	template <class Fn>
+	void onDevices(size_t n, Fn fn) {
+		const size_t D = std::min(numDevices(), std::max<size_t>(n, 1));
+		if (D <= 1) { fn(*sim, 0, n); return; }
+		auto share = [&](size_t d) { return n * d / D; };
+		std::vector<std::string> errors(D);
+		std::vector<std::thread> pool;
+		for (size_t d = 1; d < D; ++d)
+			pool.emplace_back([&, d]() {
+				try { fn(*replicas[d - 1], share(d), share(d + 1)); } catch (std::exception& e) { errors[d] = e.what(); }
+			});
+		try { fn(*sim, share(0), share(1)); } catch (std::exception& e) { errors[0] = e.what(); }
+		for (std::thread& t : pool) t.join();
+		for (const std::string& e : errors) if (!e.empty()) throw std::runtime_error(e);
+	}
+
 	double kViolation(const AP& ap, size_t i) const {
 		if (ap[i] < settings.kMin[i]) return settings.kMin[i] - ap[i];
 		if (ap[i] > settings.kMax[i]) return ap[i] - settings.kMax[i];

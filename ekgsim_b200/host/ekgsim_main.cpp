@@ -20,6 +20,9 @@
 //         resident server instead of a fresh process.
 //     ekgSim -serve <socket>       resident evaluation service (ekg_server.h): one Evaluator with the model on the GPU,
 //         concurrent requests are evaluated together in one batch.  ekgSim -shutdown <socket> ends it.
+//     -devices all|<count>|<id,id,...>   with -batch / -serve: one model replica per GPU, every batch split over them by
+//         one host thread per device (individuals over GPUs, no collective; default EKGSIM_B200_DEVICES, else one GPU:
+//         EKGSIM_B200_DEVICE or 0).  With MPI workers of the reference's optimizer set EKGSIM_B200_DEVICE=<rank % gpus>.
 // The optimizer itself (`ekgSim` without arguments, AMS-DEMO over MPI) is outside the hot path and is
 // not part of this build; use the reference's optimizer with `-extern` or `-batch` as its evaluator.
 
@@ -100,7 +103,7 @@ void run_single(const std::vector<double>& params, const ekg::OutputSettings& ou
 	std::cout << " criteria = " << ekg::angle_list(result) << ", violation = " << violation << "\n";
 }
 
-void run_batch(const std::string& file, const std::string& outfile, int threads) {
+void run_batch(const std::string& file, const std::string& outfile, int threads, const std::string& devices) {
 	std::cerr << "##### Running a batch of simulations ############################\n";
 	std::ifstream in(file.c_str());
 	if (!in.is_open()) throw std::runtime_error("could not open " + file);
@@ -110,7 +113,7 @@ void run_batch(const std::string& file, const std::string& outfile, int threads)
 		std::vector<double> v = parse_vector(line);
 		if (!v.empty()) sols.push_back(v);
 	}
-	ekg::Evaluator ev("simulator.ini");
+	ekg::Evaluator ev("simulator.ini", true, ekg::parse_device_list(devices));
 	std::vector<std::vector<double>> results;
 	std::vector<double> violations;
 	const double t0 = ekg::wall_seconds();
@@ -126,7 +129,8 @@ void run_batch(const std::string& file, const std::string& outfile, int threads)
 			of << violations[i] << "\n";
 		}
 	}
-	std::cout << " batch of " << sols.size() << " simulations done in " << secs << " seconds (GPU part " << ev.simulator().lastRunSeconds() << " s)\n";
+	std::cout << " batch of " << sols.size() << " simulations done in " << secs << " seconds on " << ev.numDevices() << " GPU(s) (GPU part "
+	          << ev.simulator().lastRunSeconds() << " s)\n";
 }
 
 void write_extern_output(const std::string& dir, const std::vector<double>& result, double violation) {
@@ -162,9 +166,9 @@ void run_extern(const std::string& home, std::string server) {
 	write_extern_output(dir, result, violation);
 }
 
-void run_serve(const std::string& path) {
+void run_serve(const std::string& path, const std::string& devices) {
 	std::cerr << "##### Starting the evaluation server ############################\n";
-	ekg::Evaluator ev("simulator.ini");
+	ekg::Evaluator ev("simulator.ini", true, ekg::parse_device_list(devices));
 	ekg::serve(ev, path);
 }
 
@@ -180,6 +184,7 @@ int main(int argc, char** argv) {
 			std::cout << "Argument list:\n   -? \tshow this help screen\n   -sim \tjust run single a simulation with parameters provided after -sim\n"
 			             "   -out \tspecify outputs of the program; possible values include result, layer_aps, cell_aps <num> [<num>]*\n"
 			             "   -batch \tevaluate every parameter vector of a text file in one GPU batch [-batchout file] [-threads n]\n"
+			             "   -devices \twith -batch / -serve: GPUs to split the batches over: all, a count, or a list 0,1,2 (default: EKGSIM_B200_DEVICES, else one)\n"
 			             "   -extern \tAMS-DEMO ExternalEvaluation protocol: <homeDir>/input.txt -> <homeDir>/output.txt [-server socket]\n"
 			             "   -serve \tresident evaluation server on a unix socket (clients: -extern with -server or EKGSIM_B200_SERVER)\n"
 			             "   -shutdown \task the server on the given socket to exit\n";
@@ -191,14 +196,14 @@ int main(int argc, char** argv) {
 			run_single(params, out);
 		} else if (args.is_set("-batch")) {
 			std::cerr << "\n";
-			run_batch(args.get("-batch"), args.get("-batchout"), atoi(args.get("-threads").c_str()));
+			run_batch(args.get("-batch"), args.get("-batchout"), atoi(args.get("-threads").c_str()), args.get("-devices"));
 		} else if (args.is_set("-extern")) {
 			std::cerr << "\n";
 			run_extern(args.get("-extern"), args.get("-server"));
 		} else if (args.is_set("-serve")) {
 			std::cerr << "\n";
 			if (args.get("-serve").empty()) throw std::runtime_error("-serve needs a socket path");
-			run_serve(args.get("-serve"));
+			run_serve(args.get("-serve"), args.get("-devices"));
 		} else if (args.is_set("-shutdown")) {
 			ekg::remote_shutdown(args.get("-shutdown"));
 		} else {

@@ -18,6 +18,26 @@ double ekg_host_apd90(const double* k) {
 	return w.apd90();
 }
 
+/// EkgSim::runApproximation (Simulation::runApproximation, simulator.cpp:552-559) for layer APs layer_k [n_layers][9]:
+/// out must hold (size_t)(length / step) values; returns that count.  Host only, no device needed.
+int64_t ekg_host_run_approximation(const double* layer_k, int n_layers, int start, int length, double step, double delay, double* out) {
+	try {
+		SimLib::EkgSim sim;
+		sim.getSettings().simulationStart = start;
+		sim.getSettings().simulationLength = length;
+		sim.getSettings().simulationTimeStep = step;
+		sim.getSettings().neighbourhoodType = "3D4";
+		sim.applySettings();
+		std::vector<SimLib::ActionPotential> aps((size_t)n_layers);
+		for (int l = 0; l < n_layers; ++l) aps[(size_t)l].init(layer_k + 9 * l, 0);
+		sim.setApsDestructive(aps);
+		std::vector<double> r;
+		sim.runApproximation(delay, r);
+		std::copy(r.begin(), r.end(), out);
+		return (int64_t)r.size();
+	} catch (std::exception& e) { g_host_error = e.what(); return -1; }
+}
+
 /// the built-in test shape (InputLoader::generateTestShape): layers_out[160 * 120] u16, dims_out = {Z, Y, X}; export_as may be ""
 int ekg_host_generate_test_shape(uint16_t* layers_out, int64_t* dims_out, const char* export_as) {
 	try {
@@ -48,6 +68,12 @@ void* ekg_host_evaluator_create(const char* ini, int with_device) {
 	try { return new ekg::Evaluator(ini, with_device != 0); }
 	catch (std::exception& e) { g_host_error = e.what(); return nullptr; }
 }
+/// the same on several GPUs: devices = "all" | "<count>" | "0,1,..." (ekg::parse_device_list); evalBatch splits its batch
+void* ekg_host_evaluator_create_on(const char* ini, const char* devices) {
+	try { return new ekg::Evaluator(ini, true, ekg::parse_device_list(devices ? devices : "")); }
+	catch (std::exception& e) { g_host_error = e.what(); return nullptr; }
+}
+int ekg_host_num_devices(void* ev) { return (int)static_cast<ekg::Evaluator*>(ev)->numDevices(); }
 void ekg_host_evaluator_destroy(void* ev) { delete static_cast<ekg::Evaluator*>(ev); }
 int ekg_host_num_criteria(void* ev) { return (int)static_cast<ekg::Evaluator*>(ev)->deducedNumOfCriteria; }
 

@@ -198,6 +198,35 @@ public:
 	~EkgSim() { if (model_) ekg_model_destroy(model_); }
 
 	void setDevice(int device) { device_ = device; }
+	int device() const { return device_; }
+
+	/// A second simulator with the same inputs and settings on another GPU (new; multi-GPU evaluation in one process,
+	/// the in-process counterpart of the reference's "every MPI rank builds its own OptimizationFunction",
+	/// main.cpp:301-302): the parsed host state is copied, the device model is created and the activation map
+	/// computed on `device` (bit-identical on every device).  Quiet: the console contract belongs to the primary.
+	std::unique_ptr<EkgSim> replicate(int device) const {
+		std::unique_ptr<EkgSim> r(new EkgSim);
+		r->settings = settings;
+		r->layers_ = layers_; r->Z_ = Z_; r->Y_ = Y_; r->X_ = X_;
+		r->transfer_ = transfer_; r->tRows_ = tRows_; r->tCols_ = tCols_;
+		r->device_ = device;
+		r->targetNumOfAps_ = targetNumOfAps_;
+		r->nbhd_ = nbhd_; r->timeStep_ = timeStep_; r->mode_ = mode_;
+		r->originalMeasuringPositions = originalMeasuringPositions; r->measuringPositions = measuringPositions;
+		r->vectorU = vectorU; r->vectorV = vectorV; r->mps_ = mps_;
+		r->measurement_.assign(mps_.size(), std::vector<double>());
+		if (haveActivation_) {
+			r->ensureModel();
+			if (settings.inputExcitationSequenceFilename == "") check(ekg_model_activation(r->model_, nullptr, nullptr));
+			else {
+				std::vector<double> delay((size_t)(Z_ * Y_ * X_));
+				check(ekg_model_get_activation(model_, delay.data()));
+				check(ekg_model_set_activation(r->model_, delay.data()));
+			}
+			r->haveActivation_ = true;
+		}
+		return r;
+	}
 	void setMode(int mode) { mode_ = mode; }
 	double lastRunSeconds() const { return lastRunSeconds_; }
 	ekg_model* handle() { ensureModel(); return model_; }
@@ -211,6 +240,7 @@ public:
 	}
 
 	Settings& getSettings() { return settings; }
+	const Settings& settingsView() const { return settings; }
 
 	/// applies the selected timestep and neighbourhood (sim_lib.h:131-148; note that "3D4" selects the
 	/// 8 cube corners and "2D4" the 4 in-plane diagonals, simulator.h:338-364)
@@ -346,8 +376,9 @@ public:
 		if (aps_.size() != targetNumOfAps_) throw std::runtime_error("run: need exactly one action potential per layer");
 		std::vector<double> k(aps_.size() * 9);
 		for (size_t l = 0; l < aps_.size(); ++l) {
+			// as stored: setApIndices builds every cell AP with init(aps[layer], delay), which keeps the layer AP's k8 as it
+			// is (already shifted by the layer AP's own `at`, if a caller set one) and replaces `at` (simulator.cpp:161-165, :600)
 			std::copy(aps_[l].getK(), aps_[l].getK() + 9, k.begin() + 9 * l);
-			k[9 * l + 8] += aps_[l].at;  // layer APs carry at = 0; undo a shift if a caller set one
 		}
 		std::vector<double> leads(mps_.size() * 3);
 		for (size_t i = 0; i < mps_.size(); ++i) for (int c = 0; c < 3; ++c) leads[3 * i + c] = mps_[i][c];

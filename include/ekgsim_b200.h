@@ -112,7 +112,7 @@ int64_t ekg_model_num_layers(const ekg_model* m);   /* = Simulation::getTargetNu
 int  ekg_model_activation(ekg_model* m, double* delay_out, int64_t* sweeps_out);
 /* Device time (ms, CUDA events) of the last ekg_model_activation call on this handle. */
 double ekg_model_activation_ms(const ekg_model* m);
-/* Brick visits of the last frontier automaton run (work actually done, in units of 8^3 bricks). */
+/* Brick visits of the last frontier automaton run (work actually done, in units of 4x4x4 bricks). */
 int64_t ekg_model_activation_brick_visits(const ekg_model* m);
 int  ekg_model_set_activation(ekg_model* m, const double* delay);
 

@@ -21,6 +21,9 @@ def lib():
         L.ekg_host_apd90.argtypes = [C.c_void_p]
         L.ekg_host_evaluator_create.restype = C.c_void_p
         L.ekg_host_evaluator_create.argtypes = [C.c_char_p, C.c_int]
+        L.ekg_host_evaluator_create_on.restype = C.c_void_p
+        L.ekg_host_evaluator_create_on.argtypes = [C.c_char_p, C.c_char_p]
+        L.ekg_host_num_devices.argtypes = [C.c_void_p]
         L.ekg_host_evaluator_destroy.argtypes = [C.c_void_p]
         L.ekg_host_num_criteria.argtypes = [C.c_void_p]
         L.ekg_host_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -29,8 +32,20 @@ def lib():
         L.ekg_host_generate_test_shape.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
         L.ekg_host_load_shape.restype = C.c_int64
         L.ekg_host_load_shape.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.ekg_host_run_approximation.restype = C.c_int64
+        L.ekg_host_run_approximation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
         _lib = L
     return _lib
+
+
+def run_approximation(layer_k, start, length, step, delay):
+    """EkgSim::runApproximation of the facade (host only): endo AP delayed minus epi AP."""
+    k = np.ascontiguousarray(layer_k, dtype=np.float64).reshape(-1, 9)
+    out = np.zeros(int(length / step) + 8)
+    n = lib().ekg_host_run_approximation(k.ctypes.data, k.shape[0], int(start), int(length), float(step), float(delay), out.ctypes.data)
+    if n < 0:
+        raise RuntimeError(lib().ekg_host_last_error().decode())
+    return out[:n].copy()
 
 
 def generate_test_shape(export_as=""):
@@ -55,17 +70,22 @@ def load_shape(fname, capacity=1 << 22):
 class Evaluator:
     """Runs in `workdir` (must hold simulator.ini + inputs, like the reference CLI)."""
 
-    def __init__(self, workdir, with_device=True, n_layers=24, n_leads=2):
+    def __init__(self, workdir, with_device=True, n_layers=24, n_leads=2, devices=None):
+        """devices: None (one GPU) | "all" | "<count>" | "0,1,..." -- batches are split over them (Evaluator::evalBatch)"""
         self.workdir, self.n_layers, self.n_leads = workdir, n_layers, n_leads
         cwd = os.getcwd()
         os.chdir(workdir)
         try:
-            self.h = lib().ekg_host_evaluator_create(b"simulator.ini", 1 if with_device else 0)
+            if devices is not None:
+                self.h = lib().ekg_host_evaluator_create_on(b"simulator.ini", str(devices).encode())
+            else:
+                self.h = lib().ekg_host_evaluator_create(b"simulator.ini", 1 if with_device else 0)
         finally:
             os.chdir(cwd)
         if not self.h:
             raise RuntimeError(lib().ekg_host_last_error().decode())
         self.n_crit = lib().ekg_host_num_criteria(self.h)
+        self.n_devices = lib().ekg_host_num_devices(self.h) if with_device else 0
 
     def close(self):
         if self.h:

@@ -415,3 +415,40 @@ def test_reference_main_with_embedded_optimizer_on_the_b200_evaluator(built, tmp
     assert np.abs(np.array([vec(rw[4]) for rw in rows]) - want_c).max() < 1e-6
     assert np.abs(np.array([float(rw[2]) for rw in rows]) - want_v).max() < 1e-9
     print("reference main.cpp + embedded AMS-DEMO on the B200 evaluator: %d evaluations, %.2f s for the whole process" % (len(rows), dt))
+
+
+def test_evaluator_splits_batches_over_devices(testrun):
+    """Multi-GPU in the product's own C++ host (the in-process form of the reference's MPI task farm, main.cpp:283-361,
+    ParallelFramework.h:388-429): one model replica per listed device, evalBatch splits the batch, one host thread per
+    device.  "0,0" puts two replicas on GPU 0, so the splitting logic is exercised on a single-GPU box; "all" uses every
+    GPU of the box.  Individuals are independent: the criteria must not depend on how the batch was cut."""
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    want = np.load(os.path.join(GOLDEN, "golden_criteria256.npz"))
+    genes = g["params"][:67]   # an odd count: uneven shares
+    ev1 = hostlib.Evaluator(testrun, with_device=True)
+    c1, v1 = ev1.eval_batch(genes)
+    ev1.close()
+    for spec, n_dev in (("0,0", 2), ("0,0,0", 3), ("all", None)):
+        ev = hostlib.Evaluator(testrun, devices=spec)
+        if n_dev is not None:
+            assert ev.n_devices == n_dev
+        c, v = ev.eval_batch(genes)
+        one, _ = ev.eval(genes[5])          # eval() runs on the first device
+        ev.close()
+        assert np.abs(c - want["criteria"][:67]).max() < 1e-4
+        assert np.abs(c - c1).max() < 1e-6 and (v == v1).all()
+        assert np.abs(one - c[5]).max() < 1e-6
+    # fewer individuals than devices, and the CLI spelling
+    ev = hostlib.Evaluator(testrun, devices="0,0,0")
+    c, v = ev.eval_batch(genes[:2])
+    ev.close()
+    assert np.abs(c - c1[:2]).max() < 1e-6
+    with open(os.path.join(testrun, "vec5.txt"), "w") as f:
+        for p in genes[:5]:
+            f.write(",".join("%.17g" % x for x in p) + "\n")
+    r = subprocess.run([hostlib.CLI, "-batch", "vec5.txt", "-batchout", "crit5.txt", "-devices", "0,0"], cwd=testrun, capture_output=True, text=True)
+    assert r.returncode == 0 and "on 2 GPU(s)" in r.stdout, r.stdout + r.stderr
+    got = np.loadtxt(os.path.join(testrun, "crit5.txt"))
+    assert np.abs(got[:, :2] - c1[:5]).max() < 1e-6
+    r = subprocess.run([hostlib.CLI, "-batch", "vec5.txt", "-devices", "7,99"], cwd=testrun, capture_output=True, text=True)
+    assert "runtime error caught: no such CUDA device in device list" in r.stdout

@@ -179,3 +179,21 @@ def test_builtin_test_shape_matches_reference(tmp_path):
     assert int((layers & 0x0FFF).max()) == 12 and int(((layers & 0x0FFF) > 0).sum()) == 6346   # the ring is clipped by the grid
     back = hostlib.load_shape(out)
     assert back.shape == layers.shape and (back == layers).all()      # 'X' reads back as start flag + layer 1, which is what it was
+
+
+def test_run_approximation_matches_oracle(built):
+    """EkgSim::runApproximation (the "string model", simulator.cpp:552-559) of the facade against the oracle's restatement:
+    same expression per sample, host f64 on both sides -> identical bits.  Sizes: the testRun axis, a fractional step
+    (result.size() = (size_t)(length / step)), a non-zero start."""
+    from oracle import oracle
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    for vec, (start, length, step, delay) in zip((0, 7, 100), ((100, 400, 1.0, 10.0), (0, 50, 0.5, 0.0), (37, 100, 1.0 / 3.0, 2.5))):
+        k = g["layer_k"][vec]
+        got = hostlib.run_approximation(k, start, length, step, delay)
+        want = oracle.run_approximation(k, float(start), step, float(length), delay)
+        assert got.shape == want.shape == (int(length / step),)
+        assert got.tobytes() == want.tobytes()
+        # and against the formula itself for one sample (endo delayed minus epi, layer APs carry at = 0)
+        i = len(got) // 2
+        t = start + i * step
+        assert got[i] == hostlib.lib().ekg_host_wohlfart_plus(k[0].ctypes.data, t + delay) - hostlib.lib().ekg_host_wohlfart_plus(k[-1].ctypes.data, t)
