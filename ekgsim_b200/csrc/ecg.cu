@@ -35,6 +35,7 @@
 #include <type_traits>
 
 #include "ekg_internal.cuh"
+#include "fit_math.cuh"   // f64 exp / log / pow: glibc's table-driven algorithms, 2-3x fewer operations than CUDA's (the f64 table kernels below)
 
 namespace ekg {
 
@@ -727,9 +728,9 @@ __global__ void __launch_bounds__(kCombSamples * kCombLanes) ecg_combine_kernel(
 			for (int layer = g; layer < n_layers; layer += kCombLanes) {
 				if (seg_first[layer] == seg_first[layer + 1]) continue;   // no voxels in this layer (inside the slab)
 				const double* k = layer_k + ((int64_t)b * n_layers + layer) * 9;
-				const double R = 1.0 - pow(1.0 + exp(-k[7] * (tt - k[8]) + tail[(int64_t)b * n_layers + layer]), -(k[6] / k[7]));
-				const double F1 = k[2] * (1.0 - k[3]) * R * exp(fmin(-(k[4] + k[5]) * (tt - t0), lim));
-				const double F2 = k[2] * k[3] * R * exp(fmin(-k[5] * (tt - t0), lim));
+				const double R = 1.0 - ekg_fm::pow_(1.0 + ekg_fm::exp_(-k[7] * (tt - k[8]) + tail[(int64_t)b * n_layers + layer]), -(k[6] / k[7]));
+				const double F1 = k[2] * (1.0 - k[3]) * R * ekg_fm::exp_(fmin(-(k[4] + k[5]) * (tt - t0), lim));
+				const double F2 = k[2] * k[3] * R * ekg_fm::exp_(fmin(-k[5] * (tt - t0), lim));
 				const double* M = s_mom + layer * L * 3;
 #pragma unroll
 				for (int l = 0; l < 4; ++l)
@@ -880,7 +881,7 @@ __global__ void ecg_params_kernel(const double* __restrict__ layer_k, float* __r
 	p[1] = (float)(-k[4] * log2e);
 	p[2] = (float)(-k[5] * log2e);
 	p[3] = (float)(-k[7] * log2e);
-	const double tc = log(pow(2.0, k[7] / k[6]) - 1.0);   // ln(2^(k7/k6) - 1), Wohlfart.h:200
+	const double tc = ekg_fm::log_(ekg_fm::pow_(2.0, k[7] / k[6]) - 1.0);   // ln(2^(k7/k6) - 1), Wohlfart.h:200
 	tail[i] = tc;
 	p[4] = (float)(tc * log2e);
 	p[5] = (float)(-(k[6] / k[7]));
@@ -904,10 +905,10 @@ __global__ void ecg_ftab_kernel(const double* __restrict__ layer_k, const double
 	const int t = (int)(i % T);
 	const double* k = layer_k + bl * 9;
 	const double tt = times[t];
-	const double R = 1.0 - pow(1.0 + exp(-k[7] * (tt - k[8]) + log(pow(2.0, k[7] / k[6]) - 1.0)), -(k[6] / k[7]));
+	const double R = 1.0 - ekg_fm::pow_(1.0 + ekg_fm::exp_(-k[7] * (tt - k[8]) + ekg_fm::log_(ekg_fm::pow_(2.0, k[7] / k[6]) - 1.0)), -(k[6] / k[7]));
 	const double lim = 60.0 * 0.69314718055994530942;  // same clamp as phase A (2^60)
-	const double f1 = k[2] * (1.0 - k[3]) * R * exp(fmin(-(k[4] + k[5]) * (tt - t0), lim));
-	const double f2 = k[2] * k[3] * R * exp(fmin(-k[5] * (tt - t0), lim));
+	const double f1 = k[2] * (1.0 - k[3]) * R * ekg_fm::exp_(fmin(-(k[4] + k[5]) * (tt - t0), lim));
+	const double f2 = k[2] * k[3] * R * ekg_fm::exp_(fmin(-k[5] * (tt - t0), lim));
 	F[(bl * 2) * T + t] = (float)f1;
 	F[(bl * 2 + 1) * T + t] = (float)f2;
 }

@@ -17,14 +17,16 @@
 //   fit_descent_kernel one half-warp per (vector, inner layer): lane = connector point; the 15
 //                      squared misses are summed in the reference's order through shuffles, so all
 //                      lanes of a fit carry identical descent state and branch identically
-// The descent only ever moves by +-move[i]*stepSize, i.e. its result depends on the SIGNS of the
-// finite-difference gradients and on accept/reject decisions, not on gradient magnitudes; CUDA's
-// exp/log/pow differ from glibc's by <= 1-2 ulp, which leaves 255 of the 256 seeded vectors
-// bit-identical to the reference glue and the rest within 1e-11 relative (tests/test_gpu_fit.py).
+// exp / log / pow are NOT CUDA's: fit_math.cuh restates glibc's own algorithms (the reference's libm) operation
+// by operation, so every accept/reject and sign decision of the descent is taken on the bits the reference's
+// host glue sees -- and the three functions cost 15-40 f64 operations each instead of CUDA's 40-200
+// (tests/test_libm_port.py: bit-identical to the host libm on 10^7 arguments; tests/test_gpu_fit.py: all 256
+// seeded vectors bit-identical to the reference glue's 24x9 coefficients).
 
 #include <cmath>
 
 #include "ekg_internal.cuh"
+#include "fit_math.cuh"
 
 namespace ekg {
 
@@ -55,11 +57,11 @@ __device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, 
 __device__ __forceinline__ double sqr(double a) { return __dmul_rn(a, a); }
 
 // The factors of WohlfartPlus::operator[] (Wohlfart.h:195-203), each by the reference's expression.
-__device__ __noinline__ double f_tail_c(double k6, double k7) { return log(sub(pow(2.0, dvd(k7, k6)), 1.0)); }
-__device__ __noinline__ double f_exp(double k, double t) { return exp(mul(-k, t)); }
+__device__ __forceinline__ double f_tail_c(double k6, double k7) { return ekg_fm::log_(sub(ekg_fm::pow_(2.0, dvd(k7, k6)), 1.0)); }
+__device__ __forceinline__ double f_exp(double k, double t) { return ekg_fm::exp_(mul(-k, t)); }
 __device__ __forceinline__ double f_A(double k1, double t) { return dvd(1.0, add(1.0, f_exp(k1, t))); }
-__device__ __noinline__ double f_Q(double k6, double k7, double k8, double c, double t) {
-	return pow(add(1.0, exp(add(mul(-k7, sub(t, k8)), c))), -dvd(k6, k7));
+__device__ __forceinline__ double f_Q(double k6, double k7, double k8, double c, double t) {
+	return ekg_fm::pow_(add(1.0, ekg_fm::exp_(add(mul(-k7, sub(t, k8)), c))), -dvd(k6, k7));
 }
 __device__ __forceinline__ double f_value(double k0, double k2, double k3, double A, double E4, double E5, double Q) {
 	return add(mul(mul(A, mul(k2, add(mul(sub(1.0, k3), E4), k3))), mul(E5, sub(1.0, Q))), k0);
@@ -130,46 +132,45 @@ __global__ void __launch_bounds__(256) fit_setup_kernel(FitArgs a) {
 // ---- descent --------------------------------------------------------------------------------------
 struct Factors { double A, E4, E5, Q; };
 
-// sum of the 15 squared misses in index order; every lane of the half-warp gets the same bits
-__device__ __forceinline__ double ordered_sum(double e, unsigned mask) {
-	double s = __shfl_sync(mask, e, 0, 16);  // 0 + e0 == e0
+constexpr int kFitsPerCta = 8;   // 128 threads, one half-warp per fit
+
+// sum of the 15 squared misses in index order; every lane of the half-warp gets the same bits.  The values go through
+// the fit's 16-slot row of shared memory: one store, eight 16-byte broadcast loads and the 14 dependent additions the
+// reference's loop performs (the same through shuffles costs 30 SHFL + 14 DADD).
+__device__ __forceinline__ double ordered_sum(double e, double* row, int lane16, unsigned mask) {
+	row[lane16] = e;
+	__syncwarp(mask);
+	const double2* r2 = reinterpret_cast<const double2*>(row);
+	double2 v = r2[0];
+	double s = add(v.x, v.y);   // 0 + e0 == e0
 #pragma unroll
-	for (int n = 1; n < kFitPoints; ++n) s = add(s, __shfl_sync(mask, e, n, 16));
+	for (int n = 1; n < 7; ++n) { v = r2[n]; s = add(add(s, v.x), v.y); }
+	s = add(s, row[14]);
+	__syncwarp(mask);           // everybody has read before the next evaluation overwrites the row
 	return s;
-}
-
-// f(x) with all factors computed (and remembered in `f`); c = f_tail_c(k6, k7)
-__device__ __forceinline__ double eval_full(const double (&k)[9], double c, double px, double py, Factors& f, unsigned mask) {
-	f.A = f_A(k[1], px);
-	f.E4 = f_exp(k[4], px);
-	f.E5 = f_exp(k[5], px);
-	f.Q = f_Q(k[6], k[7], k[8], c, px);
-	return ordered_sum(sqr(sub(f_value(k[0], k[2], k[3], f.A, f.E4, f.E5, f.Q), py)), mask);
-}
-
-// f(x1) where x1 differs from the iterate behind `f` only in coefficient `which` (compile-time after unrolling);
-// c = f_tail_c of x1's (k6, k7)
-__device__ __forceinline__ double eval_perturbed(const double (&k)[9], int which, double c, double px, double py, const Factors& f, unsigned mask) {
-	double A = f.A, E4 = f.E4, E5 = f.E5, Q = f.Q;
-	switch (which) {
-	case 1: A = f_A(k[1], px); break;
-	case 4: E4 = f_exp(k[4], px); break;
-	case 5: E5 = f_exp(k[5], px); break;
-	case 6: case 7: case 8: Q = f_Q(k[6], k[7], k[8], c, px); break;
-	default: break;
-	}
-	return ordered_sum(sqr(sub(f_value(k[0], k[2], k[3], A, E4, E5, Q), py)), mask);
 }
 
 // DM: compile-time set of fitted coefficients (bit q <=> d[q] != 0), 0 = decide at run time.  The reference's
 // set {k3, k5, k6, k7, k8} has its own instantiation: state of the coefficients that never move stays out of
-// registers (96 registers -> 5 CTAs per SM, the whole 256-vector batch in one wave).
+// registers, and the AP factors they alone enter (the depolarisation sigmoid for k1, exp(-k4 t) for k4) are computed
+// once instead of once per trial point -- the same inputs give the same bits.
+//
+// Per iteration (nonlinearFit.h:104-164): one one-sided difference per fitted coefficient (only the factor that
+// coefficient enters is recomputed, like the host glue does), the sign-following update, one full evaluation of the
+// trial point.  ln(2^(k7/k6) - 1) depends on (k6, k7) only and is the same for all 15 points: the values for the trial
+// point and for its k6- and k7-perturbed neighbours (needed by the NEXT iteration if the trial point is accepted) are
+// computed side by side in three lanes of ONE call -- always by the same function, so every use sees the bits a fresh
+// evaluation would give.  After a rejected trial point the iterate, and with it every difference quotient, is
+// unchanged: the next iteration reuses them (grad[] holds exactly those values).
 template <unsigned DM>
-__global__ void __launch_bounds__(128, 5) fit_descent_kernel(FitArgs a) {
+__global__ void __launch_bounds__(16 * kFitsPerCta, 5) fit_descent_kernel(FitArgs a) {
+	__shared__ __align__(16) double s_sum[kFitsPerCta][16];
 	const int per_b = a.nl - a.nb;  // inner layers per vector
-	const int fit = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+	const int fit = blockIdx.x * kFitsPerCta + (threadIdx.x >> 4);
 	if (fit >= a.B * per_b) return;  // whole half-warps leave together
 	const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+	const int lane16 = threadIdx.x & 15;
+	double* row = s_sum[threadIdx.x >> 4];
 	const int b = fit / per_b;
 	int layer = fit % per_b + 1;
 	int ja = 0, jb = a.nb - 1;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(128, 5) fit_descent_kernel(FitArgs a) {
 		if (layer < a.mid) { jb = (a.mid == a.nl - 1) ? 2 : 1; ratio = dvd((double)layer, (double)a.mid); }   // sim.cpp:886
 		else { ja = 1; ratio = dvd((double)(layer - a.mid), (double)(a.nl - a.mid - 1)); }                     // sim.cpp:892-893
 	}
-	const int pt = min((int)(threadIdx.x & 15), kFitPoints - 1);  // lane 15 shadows point 14, its miss is never read
+	const int pt = min(lane16, kFitPoints - 1);  // lane 15 shadows point 14, its miss is never read
 	const FitConn& ca = a.conn[b * a.nb + ja];
 	const FitConn& cb = a.conn[b * a.nb + jb];
 	// connector through (i1, ap1(i1)) and (i2, ap2(i2)), sim.cpp:231-240
@@ -204,60 +205,83 @@ __global__ void __launch_bounds__(128, 5) fit_descent_kernel(FitArgs a) {
 		move[q] = fitted(q) ? a.d[q] : 0.0;
 		grad[q] = 0.0;
 	}
-	// ln(2^(k7/k6) - 1) depends on (k6, k7) only and is the same for all 15 points: computed once per distinct
-	// (k6, k7) -- the iterate's value c0 serves the k8 perturbation, the two values of the k6 and k7 perturbations
-	// are computed side by side in odd and even lanes and exchanged -- always by the same function, so every
-	// use sees the bits a fresh evaluation would give
-	Factors cache, trial;
-	double c0 = f_tail_c(x0[6], x0[7]);
-	double y0 = eval_full(x0, c0, px, py, cache, mask);
-	double step = a.step;
 	const double h6 = mul(a.d[6], .001), h7 = mul(a.d[7], .001);
-	const bool odd = threadIdx.x & 1;
+	const bool tails = fitted(6) || fitted(7);
+	// lanes 0, 1, 2 of the half-warp: ln(2^(k7/k6) - 1) at (k6, k7), (k6 + h6, k7), (k6, k7 + h7)
+	auto tail3 = [&](double k6, double k7, double& c, double& c6, double& c7) {
+		const double t = f_tail_c(lane16 == 1 ? add(k6, h6) : k6, lane16 == 2 ? add(k7, h7) : k7);
+		c = __shfl_sync(mask, t, 0, 16);
+		c6 = tails ? __shfl_sync(mask, t, 1, 16) : c;
+		c7 = tails ? __shfl_sync(mask, t, 2, 16) : c;
+	};
+	auto miss = [&](const double (&k)[9], const Factors& f) {
+		return ordered_sum(sqr(sub(f_value(k[0], k[2], k[3], f.A, f.E4, f.E5, f.Q), py)), row, lane16, mask);
+	};
+	Factors cache;
+	double c0, c6, c7;
+	tail3(x0[6], x0[7], c0, c6, c7);
+	cache.A = f_A(x0[1], px);
+	cache.E4 = f_exp(x0[4], px);
+	cache.E5 = f_exp(x0[5], px);
+	cache.Q = f_Q(x0[6], x0[7], x0[8], c0, px);
+	double y0 = miss(x0, cache);
+	double step = a.step;
+	bool reuse = false;   // the last trial point was rejected: iterate and difference quotients are unchanged
 	for (int it = a.iterations; it > 0 && y0 > a.eps; --it) {
 		bool step_change = false;
-		double c6 = c0, c7 = c0;
-		if (fitted(6) || fitted(7)) {
-			const double t = f_tail_c(odd ? add(x0[6], h6) : x0[6], odd ? x0[7] : add(x0[7], h7));
-			c6 = __shfl_sync(mask, t, 1, 16);
-			c7 = __shfl_sync(mask, t, 0, 16);
-		}
 #pragma unroll
 		for (int q = 0; q < 9; ++q) {
 			if (fitted(q)) {
-				double x1v[9];
+				double g = grad[q];
+				if (!reuse) {
+					double kq[9];
 #pragma unroll
-				for (int r = 0; r < 9; ++r) x1v[r] = x0[r];
-				const double h = mul(a.d[q], .001);
-				x1v[q] = add(x1v[q], h);
-				const double c = q == 6 ? c6 : q == 7 ? c7 : c0;
-				const double g = dvd(sub(eval_perturbed(x1v, q, c, px, py, cache, mask), y0), h);
+					for (int r = 0; r < 9; ++r) kq[r] = x0[r];
+					const double h = mul(a.d[q], .001);
+					kq[q] = add(kq[q], h);
+					Factors f = cache;
+					if (q == 1) f.A = f_A(kq[1], px);
+					if (q == 4) f.E4 = f_exp(kq[4], px);
+					if (q == 5) f.E5 = f_exp(kq[5], px);
+					if (q == 6 || q == 7 || q == 8) f.Q = f_Q(kq[6], kq[7], kq[8], q == 6 ? c6 : q == 7 ? c7 : c0, px);
+					g = dvd(sub(miss(kq, f), y0), h);
+				}
 				if (mul(g, grad[q]) < 0) { move[q] = mul(move[q], 0.5); step_change = true; }
 				else if (fabs(g) > mul(0.75, fabs(grad[q]))) move[q] = mul(move[q], 1.5);
 				grad[q] = g;   // oldGrad = grad, nonlinearFit.h:144 (only its own component is ever read)
 			}
 		}
-		double x1v[9];
+		double kt[9];
 #pragma unroll
 		for (int q = 0; q < 9; ++q) {
 			// a coefficient that is not fitted has grad = 0 and move = d = 0: x - step * (-0) = x (nonlinearFit.h:148-150)
-			x1v[q] = fitted(q) ? sub(x0[q], mul(step, (grad[q] > 0) ? move[q] : -move[q])) : x0[q];
+			kt[q] = fitted(q) ? sub(x0[q], mul(step, (grad[q] > 0) ? move[q] : -move[q])) : x0[q];
 		}
-		const double c1 = f_tail_c(x1v[6], x1v[7]);
-		const double y1 = eval_full(x1v, c1, px, py, trial, mask);
+		double c1, c61, c71;
+		tail3(kt[6], kt[7], c1, c61, c71);
+		Factors trial = cache;
+		if (fitted(1)) trial.A = f_A(kt[1], px);
+		if (fitted(4)) trial.E4 = f_exp(kt[4], px);
+		if (fitted(5)) trial.E5 = f_exp(kt[5], px);
+		if (fitted(6) || fitted(7) || fitted(8)) trial.Q = f_Q(kt[6], kt[7], kt[8], c1, px);
+		const double y1 = miss(kt, trial);
 		if (y1 < y0) {
 			y0 = y1;
-			c0 = c1;
+			c0 = c1; c6 = c61; c7 = c71;
 #pragma unroll
-			for (int q = 0; q < 9; ++q) x0[q] = x1v[q];
+			for (int q = 0; q < 9; ++q) x0[q] = kt[q];
 			cache = trial;
-		} else if (!step_change) step = mul(step, 0.5);
+			reuse = false;
+		} else {
+			if (!step_change) step = mul(step, 0.5);
+			reuse = true;
+		}
 	}
-	if ((threadIdx.x & 15) < 9) {
+	if (lane16 < 9) {
 		double v = x0[0];
 #pragma unroll
-		for (int q = 1; q < 9; ++q) if ((threadIdx.x & 15) == q) v = x0[q];
-		a.layer_k[((size_t)b * a.nl + layer) * 9 + (threadIdx.x & 15)] = v;
+		for (int q = 1; q < 9; ++q) if (lane16 == q) v = x0[q];
+		a.layer_k[((size_t)b * a.nl + layer) * 9 + lane16] = v;
 	}
 }
 
@@ -294,8 +318,8 @@ int run_fit(ekg_model* m, const double* d_border_k, int64_t B, int64_t n_border,
 	if (fits > 0) {
 		unsigned dm = 0;
 		for (int q = 0; q < 9; ++q) if (d9[q] != 0) dm |= 1u << q;
-		if (dm == 0x1E8u) fit_descent_kernel<0x1E8u><<<(unsigned)((fits + 7) / 8), 128, 0, st>>>(a);   // k3, k5, k6, k7, k8 (sim.cpp:877)
-		else fit_descent_kernel<0u><<<(unsigned)((fits + 7) / 8), 128, 0, st>>>(a);
+		if (dm == 0x1E8u) fit_descent_kernel<0x1E8u><<<(unsigned)((fits + kFitsPerCta - 1) / kFitsPerCta), 16 * kFitsPerCta, 0, st>>>(a);   // k3, k5, k6, k7, k8 (sim.cpp:877)
+		else fit_descent_kernel<0u><<<(unsigned)((fits + kFitsPerCta - 1) / kFitsPerCta), 16 * kFitsPerCta, 0, st>>>(a);
 		EKG_CUDA(cudaGetLastError());
 		++m->last_launches;
 	}

@@ -182,6 +182,21 @@ def test_ecg_model24_golden_full(gpu_model24, model24_delay, mode):
 
 
 @pytest.mark.parametrize("mode", [1, 2, 3])
+def test_ecg_model24_golden_single(gpu_model24, model24_delay, mode):
+    """BASELINE config 1 as the facade issues it: ONE simulation per call (B = 1: the time-loop kernels then split the
+    segment's voxels into 16 slices so that 16 x 400 (slice, sample) pairs fill 25 whole tiles), each of the four
+    full-length reference ECGs on its own."""
+    g = np.load(os.path.join(GOLDEN, "golden_eval_full.npz"))
+    gpu_model24.set_activation(model24_delay)
+    for i in range(g["ecg"].shape[0]):
+        ecg = gpu_model24.simulate(g["layer_k"][i], g["leads_zyx"][i], "3D4", 100.0, 1.0, 400.0, mode=mode)
+        assert ecg.shape == (1, 2, 400) and np.isfinite(ecg).all()
+        e = rel_err(ecg[0], g["ecg"][i])
+        print("golden %s alone, mode %d: max err %.3g of peak" % (g["name"][i], mode, e))
+        assert e < ECG_TOL
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_ecg_model24_len16_batch(gpu_model24, model24_delay, mode):
     g = np.load(os.path.join(GOLDEN, "golden_len16.npz"))
     gpu_model24.set_activation(model24_delay)
