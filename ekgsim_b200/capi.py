@@ -41,6 +41,7 @@ SYMBOLS = {
     "ekg_model_get_activation": (_int, [_p, _p]),
     "ekg_model_activation_begin": (_int, [_p]),
     "ekg_model_activation_relax": (_int, [_p, C.POINTER(_i64)]),
+    "ekg_model_activation_relax_bounded": (_int, [_p, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "ekg_model_plane_elems": (_i64, [_p]),
     "ekg_model_activation_export": (_int, [_p, _i64, _i64, _p, _p]),
     "ekg_model_activation_merge": (_int, [_p, _i64, _i64, _p, C.POINTER(_i64), _p]),
@@ -164,6 +165,12 @@ class Model:
         v = C.c_int64(0)
         _check(lib().ekg_model_activation_relax(self._h, C.byref(v)))
         return int(v.value)
+
+    def activation_relax_bounded(self, max_visits):
+        """-> (brick visits, bricks still queued); max_visits = 0: until the slab's fixed point"""
+        v, left = C.c_int64(0), C.c_int64(0)
+        _check(lib().ekg_model_activation_relax_bounded(self._h, int(max_visits), C.byref(v), C.byref(left)))
+        return int(v.value), int(left.value)
 
     def activation_export(self, z_begin, z_end, d_planes, stream=0):
         _check(lib().ekg_model_activation_export(self._h, int(z_begin), int(z_end), C.c_void_p(d_planes), C.c_void_p(stream)))

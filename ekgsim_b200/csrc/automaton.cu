@@ -118,15 +118,20 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 	int visits = 0, sweeps = 0;
 	volatile int* vq = a.queue;
 	volatile int* vpending = a.counters + 2;
+	volatile int* vstop = a.counters + 6;
 
 	for (;;) {   // one warp per brick, no barrier wider than the warp anywhere in here
 		int b = -1;
 		if (lane == 0) {
-			const unsigned pos = atomicAdd((unsigned*)a.counters + 0, 1u);   // head: claim a ring position
-			for (unsigned spins = 0;; ++spins) {
+			// bounded run: once `budget` ring positions have been claimed nobody claims another one; the bricks still
+			// flagged as queued are carried into the next relaxation by the host (flag[] is authoritative, the ring is rebuilt)
+			if (a.budget && (*(volatile unsigned*)a.counters >= a.budget || vstop[0])) { vstop[0] = 1; b = -2; }
+			const unsigned pos = b == -2 ? 0u : atomicAdd((unsigned*)a.counters + 0, 1u);   // head: claim a ring position
+			for (unsigned spins = 0; b != -2; ++spins) {
 				b = vq[pos & a.qmask];
 				if (b >= 0) { vq[pos & a.qmask] = -1; break; }
 				if (*vpending == 0) { b = -2; break; }                       // nothing queued, nobody working: done
+				if (a.budget && vstop[0]) { b = -2; break; }                 // bounded run over: the producers have left
 				// a warp that found nothing for seconds retires (never spins forever, whatever happens);
 				// the host reports non-convergence if work was still pending when the last warp left
 				if (spins > (1u << 25)) { b = -2; break; }
@@ -312,7 +317,7 @@ int run_automaton(ekg_model* m, int64_t* sweeps_out) {
 	return EKG_OK;
 }
 
-static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* visits_out);
+static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* visits_out, int64_t budget = 0, int64_t* leftover_out = nullptr);
 
 static int64_t ring_capacity(int64_t n) {
 	int64_t cap = 1;
@@ -337,7 +342,7 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 }
 
 // the frontier kernel over whatever the ring holds; d_own restricts the pushes (sharded run)
-static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out) {
+static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out, int64_t budget, int64_t* leftover_out) {
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
 	const int64_t cap = ring_capacity(n);
@@ -351,6 +356,7 @@ static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out
 	a.origin = m->d_brick_origin; a.nbr = m->d_brick_nbr; a.own = d_own;
 	a.flag = flag; a.first_visit = first; a.queue = ring; a.counters = counters; a.qmask = (uint32_t)(cap - 1);
 	a.n_live = (int32_t)n; a.nl1 = m->n_layers + 1; a.pY = (int32_t)m->pY; a.pX = (int32_t)m->pX;
+	a.budget = (uint32_t)std::min<int64_t>(std::max<int64_t>(budget, 0), 0x7fffffff);
 	NbrTable nb;
 	make_nbr_table(m->Z > 1 ? EKG_NBHD_3D8 : EKG_NBHD_2D8, &nb);  // simulator.cpp:251-254
 	a.n_nbr = nb.n;
@@ -377,7 +383,8 @@ static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out
 	if (rounds_out) *rounds_out = hc[4];   // brick visits (there are no global rounds in the work-queue scheme)
 	m->last_brick_visits = hc[4];
 	if (getenv("EKGSIM_B200_DEBUG")) fprintf(stderr, "automaton bricks: visits %d inner sweeps %d pushes %d\n", hc[4], hc[5], hc[1]);
-	if (hc[2] != 0) return fail(EKG_E_STATE, "activation automaton did not converge");
+	if (leftover_out) *leftover_out = hc[2];   // bricks still flagged as queued (bounded run)
+	else if (hc[2] != 0) return fail(EKG_E_STATE, "activation automaton did not converge");
 	return EKG_OK;
 }
 
@@ -422,6 +429,15 @@ __global__ void shard_enqueue_kernel(int* __restrict__ mark, int n_live, int* __
 	atomicAdd(counters + 2, 1);
 }
 
+__global__ void shard_own_kernel(const uint32_t* __restrict__ origin, int n_live, int64_t plane, int64_t z0, int64_t z1, uint8_t* __restrict__ own,
+                                 int* __restrict__ mark) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_live) return;
+	const int64_t z = (int64_t)origin[b] / plane - 1;   // first voxel plane of the brick
+	own[b] = (z < z1 && z + kBrick > z0) ? 1 : 0;
+	mark[b] = 0;
+}
+
 static int shard_check(ekg_model* m) {
 	if (m->h_starts.empty()) return fail(EKG_E_NO_START, "Could not find starting point for excitation sequence");
 	if (m->n_layers >= m->t_cols || m->n_layers >= m->t_rows) return fail(EKG_E_TRANSFER, "transfer (conduction) matrix does not define every layer");
@@ -434,24 +450,23 @@ int shard_begin(ekg_model* m) {
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
 	const size_t nn = (size_t)std::max<int64_t>(n, 1);
-	if (!m->d_brick_index) {
-		EKG_CUDA(cudaMalloc(&m->d_brick_index, std::max<size_t>(m->h_brick_index.size(), 1) * sizeof(int32_t)));
+	if (!m->d_brick_own) {
 		EKG_CUDA(cudaMalloc(&m->d_brick_own, nn));
 		EKG_CUDA(cudaMalloc(&m->d_brick_mark, nn * sizeof(int)));
 		EKG_CUDA(cudaMalloc(&m->d_improved, sizeof(unsigned long long)));
-		EKG_CUDA(cudaMemcpyAsync(m->d_brick_index, m->h_brick_index.data(), m->h_brick_index.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
 	}
-	// bricks that intersect the slab [slab_z0, slab_z1); brick bz covers the voxel planes [4 bz, 4 bz + 4)
-	std::vector<uint8_t> own(nn, 0);
-	std::vector<int> mark(nn, 0);
-	for (int64_t bz = 0; bz < m->bZ; ++bz) {
-		const bool in = bz * kBrick < m->slab_z1 && (bz + 1) * kBrick > m->slab_z0;
-		if (!in) continue;
-		for (int64_t i = bz * m->bY * m->bX; i < (bz + 1) * m->bY * m->bX; ++i) if (m->h_brick_index[(size_t)i] >= 0) own[(size_t)m->h_brick_index[(size_t)i]] = 1;
+	// bricks that intersect the slab [slab_z0, slab_z1) (brick bz covers the voxel planes [4 bz, 4 bz + 4)); of those, the
+	// bricks of the start voxels are queued
+	if (n > 0) {
+		shard_own_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_brick_origin, (int)n, m->pY * m->pX, m->slab_z0, m->slab_z1, m->d_brick_own, m->d_brick_mark);
+		EKG_CUDA(cudaGetLastError());
+		static const int one = 1;
+		for (size_t i = 0; i < m->h_start_bricks.size(); ++i) {
+			const int64_t bz = m->h_start_brick_bz[i];
+			if (bz * kBrick < m->slab_z1 && (bz + 1) * kBrick > m->slab_z0)
+				EKG_CUDA(cudaMemcpyAsync(m->d_brick_mark + m->h_start_bricks[i], &one, sizeof(int), cudaMemcpyHostToDevice, st));
+		}
 	}
-	for (int32_t b : m->h_start_bricks) if (own[(size_t)b]) mark[(size_t)b] = 1;
-	EKG_CUDA(cudaMemcpyAsync(m->d_brick_own, own.data(), nn, cudaMemcpyHostToDevice, st));
-	EKG_CUDA(cudaMemcpyAsync(m->d_brick_mark, mark.data(), nn * sizeof(int), cudaMemcpyHostToDevice, st));
 	const int64_t npad = m->pZ * m->pY * m->pX;
 	init_time_kernel<<<m->sm_count * 4, 256, 0, st>>>(m->d_time_pad, npad);
 	EKG_CUDA(cudaGetLastError());
@@ -469,26 +484,44 @@ int shard_begin(ekg_model* m) {
 	EKG_CUDA(cudaGetLastError());
 	EKG_CUDA(cudaStreamSynchronize(st));  // pageable sources
 	EKG_CUDA(cudaFree(d_starts));
+	if (n > 0) EKG_CUDA(cudaMemsetAsync(m->d_brick_state, 0, (size_t)(2 * n) * sizeof(int), st));   // flags: nothing carried over
+	EKG_CUDA(cudaStreamSynchronize(st));
 	m->have_activation = false;
 	m->shard_active = true;
 	return EKG_OK;
 }
 
-int shard_relax(ekg_model* m, int64_t* visits_out) {
+// bricks a bounded relaxation left flagged as queued -> marked for the next one
+__global__ void shard_carry_kernel(const int* __restrict__ flag, int* __restrict__ mark, int n_live) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b < n_live && flag[b]) mark[b] = 1;
+}
+
+// max_visits > 0 bounds the relaxation (the wave is handed to the neighbouring slabs before this slab has reached its
+// fixed point, so that the ranks work side by side instead of one after the other); *leftover_out = bricks still queued
+int shard_relax(ekg_model* m, int64_t max_visits, int64_t* visits_out, int64_t* leftover_out) {
 	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
+	if (leftover_out) *leftover_out = 0;
 	if (n == 0) { if (visits_out) *visits_out = 0; return EKG_OK; }
 	const int64_t cap = ring_capacity(n);
 	int* flag = m->d_brick_state;
 	int* ring = flag + 2 * n;
 	int* counters = ring + cap;
+	shard_carry_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(flag, m->d_brick_mark, (int)n);
+	EKG_CUDA(cudaGetLastError());
 	EKG_CUDA(cudaMemsetAsync(flag, 0, (size_t)(2 * n) * sizeof(int), st));
 	EKG_CUDA(cudaMemsetAsync(ring, 0xff, (size_t)cap * sizeof(int), st));   // -1 = empty slot
 	EKG_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(int), st));
 	shard_enqueue_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_brick_mark, (int)n, flag, flag + n, ring, counters, (uint32_t)(cap - 1));
 	EKG_CUDA(cudaGetLastError());
-	return launch_bricks(m, m->d_brick_own, visits_out);
+	int64_t left = 0;
+	int rc = launch_bricks(m, m->d_brick_own, visits_out, max_visits, &left);
+	if (rc) return rc;
+	if (max_visits <= 0 && left != 0) return fail(EKG_E_STATE, "activation automaton did not converge");
+	if (leftover_out) *leftover_out = left;
+	return EKG_OK;
 }
 
 static int plane_range(ekg_model* m, int64_t z_begin, int64_t z_end, int64_t* first_cell, int64_t* n_cells) {

@@ -9,6 +9,9 @@
 #include <unordered_map>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "ekg_internal.cuh"
 
@@ -339,6 +342,127 @@ static int publish_activation(ekg_model* m) {
 	return gather_at(m);
 }
 
+
+// ---- model creation on the device ---------------------------------------------------------------------------------------
+// ekg_model_create receives the layer map as the .matrix reader left it (u16 raster, 0x1000 = start flag).  One upload,
+// then everything the automaton and the ECG list need is derived by kernels: the zero-bordered u8 layer map, the
+// occupied voxels per z-plane, the start voxels, the raster list of occupied voxels (stream compaction), the live 4^3
+// bricks with their origins and 26 neighbours.  (Round 1 made three host passes over the dense grid: 0.46 s at 4x.)
+struct CreateStats {
+	int32_t max_layer;      // highest layer number
+	int32_t bad_layer;      // a layer number > 255
+	int32_t bad_start;      // a start voxel without a layer
+	int32_t n_starts;       // start voxels seen (the first kMaxStarts are recorded)
+};
+constexpr int kMaxStarts = 4096;
+
+__global__ void __launch_bounds__(256) create_pad_kernel(const uint16_t* __restrict__ raw, int64_t n, int64_t Y, int64_t X, int64_t pY, int64_t pX,
+                                                         uint8_t* __restrict__ layer_pad, unsigned long long* __restrict__ occ_z,
+                                                         CreateStats* __restrict__ stats, long long* __restrict__ starts) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int l = 0;
+	int64_t z = -1;
+	if (i < n) {
+		l = raw[i];
+		const int64_t x = i % X, zy = i / X, y = zy % Y;
+		z = zy / Y;
+		if (l & kStartFlag) {   // simulator.cpp:261-264
+			l -= kStartFlag;
+			if (l == 0) atomicExch(&stats->bad_start, 1);
+			const int slot = atomicAdd(&stats->n_starts, 1);
+			if (slot < kMaxStarts) starts[slot] = i;
+		}
+		if (l > 255) { atomicExch(&stats->bad_layer, 1); l = 0; }
+		if (l) layer_pad[((z + 1) * pY + (y + 1)) * pX + (x + 1)] = (uint8_t)l;
+	}
+	// occupied voxels per plane: a warp usually sits inside one plane
+	const unsigned occ = __ballot_sync(0xffffffffu, l != 0);
+	const int64_t z0 = __shfl_sync(0xffffffffu, z, 0);
+	if (__all_sync(0xffffffffu, z == z0)) {
+		if ((threadIdx.x & 31) == 0 && occ && z0 >= 0) atomicAdd(occ_z + z0, (unsigned long long)__popc(occ));
+	} else if (l) atomicAdd(occ_z + z, 1ull);
+	const int mx = __reduce_max_sync(0xffffffffu, l);
+	if ((threadIdx.x & 31) == 0 && mx) atomicMax(&stats->max_layer, mx);
+}
+
+// padded indices [p0, p0 + cnt) of occupied voxels, ascending (= raster order), appended at out + *n_out
+struct OccupiedAt {
+	const uint8_t* layer_pad;
+	__device__ bool operator()(uint32_t p) const { return layer_pad[p] != 0; }
+};
+
+// live[c] = 1 if brick cell c (dense brick grid [bZ][bY][bX]) holds an occupied voxel
+__global__ void brick_live_kernel(const uint8_t* __restrict__ layer_pad, int64_t n_cells, int bY, int bX, int64_t pY, int64_t pX, int32_t* __restrict__ live) {
+	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_cells) return;
+	const int64_t bx = c % bX, t = c / bX, by = t % bY, bz = t / bY;
+	const uint8_t* base = layer_pad + ((bz * kBrick + 1) * pY + (by * kBrick + 1)) * pX + (bx * kBrick + 1);   // the padded extents cover whole bricks
+	int any = 0;
+	for (int z = 0; z < kBrick; ++z) for (int y = 0; y < kBrick; ++y) {
+		const uint8_t* r = base + (z * pY + y) * pX;
+		any |= r[0] | r[1] | r[2] | r[3];
+	}
+	live[c] = any ? 1 : 0;
+}
+
+// index[c] = live brick id (exclusive scan of live) or -1; origin of every live brick
+__global__ void brick_index_kernel(const int32_t* __restrict__ live, const int32_t* __restrict__ scan, int64_t n_cells, int bY, int bX, int64_t pY, int64_t pX,
+                                   int32_t* __restrict__ index, uint32_t* __restrict__ origin) {
+	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_cells) return;
+	if (!live[c]) { index[c] = -1; return; }
+	const int64_t bx = c % bX, t = c / bX, by = t % bY, bz = t / bY;
+	index[c] = scan[c];
+	origin[scan[c]] = (uint32_t)(((bz * kBrick + 1) * pY + (by * kBrick + 1)) * pX + (bx * kBrick + 1));
+}
+
+__global__ void brick_nbr_kernel(const int32_t* __restrict__ index, int64_t n_cells, int bZ, int bY, int bX, int32_t* __restrict__ nbr) {
+	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_cells) return;
+	const int32_t bi = index[c];
+	if (bi < 0) return;
+	const int bx = (int)(c % bX), by = (int)((c / bX) % bY), bz = (int)(c / ((int64_t)bX * bY));
+	int k = 0;
+	for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+		if (!dz && !dy && !dx) continue;
+		const int cz = bz + dz, cy = by + dy, cx = bx + dx;
+		int32_t v = -1;
+		if (cz >= 0 && cz < bZ && cy >= 0 && cy < bY && cx >= 0 && cx < bX) v = index[((int64_t)cz * bY + cy) * bX + cx];
+		nbr[(size_t)bi * 26 + k++] = v;
+	}
+}
+
+// raster activation map -> padded grid (ekg_model_set_activation)
+__global__ void pad_activation_kernel(const double* __restrict__ raster, int64_t n, int64_t Y, int64_t X, int64_t pY, int64_t pX, double* __restrict__ time_pad) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int64_t x = i % X, zy = i / X, y = zy % Y, z = zy / Y;
+	time_pad[((z + 1) * pY + (y + 1)) * pX + (x + 1)] = raster[i];
+}
+
+// raster u8 layer map (start flags stripped) out of the padded one: the lazily made host copy behind ekg_model_ap_classes
+__global__ void unpad_layer_kernel(const uint8_t* __restrict__ layer_pad, int64_t n, int64_t Y, int64_t X, int64_t pY, int64_t pX, uint8_t* __restrict__ out) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int64_t x = i % X, zy = i / X, y = zy % Y, z = zy / Y;
+	out[i] = layer_pad[((z + 1) * pY + (y + 1)) * pX + (x + 1)];
+}
+
+static int ensure_host_layer(ekg_model* m) {
+	const int64_t n = m->Z * m->Y * m->X;
+	if ((int64_t)m->h_layer.size() == n) return EKG_OK;
+	EKG_CUDA(cudaSetDevice(m->device));
+	uint8_t* d = nullptr;
+	EKG_CUDA(cudaMalloc(&d, (size_t)n));
+	unpad_layer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->d_layer_pad, n, m->Y, m->X, m->pY, m->pX, d);
+	m->h_layer.resize((size_t)n);
+	cudaError_t e = cudaMemcpyAsync(m->h_layer.data(), d, (size_t)n, cudaMemcpyDeviceToHost, m->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+	cudaFree(d);
+	if (e != cudaSuccess) { m->h_layer.clear(); return cuda_fail(e, "download of the layer map", __FILE__, __LINE__); }
+	return EKG_OK;
+}
+
 }  // namespace ekg
 
 using namespace ekg;
@@ -370,60 +494,92 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 	// zero border of one voxel, extents rounded up to a multiple of 8 (whole bricks for the frontier automaton)
 	m->pZ = (Z + 7) / 8 * 8 + 2; m->pY = (Y + 7) / 8 * 8 + 2; m->pX = (X + 7) / 8 * 8 + 2;
 	const int64_t n = Z * Y * X;
-	m->h_layer.resize((size_t)n);
-	m->h_occ_before_z.assign((size_t)Z + 1, 0);
-	int max_layer = 0;
-	for (int64_t z = 0, i = 0; z < Z; ++z) {
-		for (const int64_t plane_end = (z + 1) * Y * X; i < plane_end; ++i) {
-			uint16_t l = layers[i];
-			if (l & kStartFlag) {   // simulator.cpp:261-264
-				l = (uint16_t)(l - kStartFlag);
-				// the text format cannot express "start voxel of layer 0" (matrix.h:124-129 maps -v to 0x1000 + v, v >= 1); through
-				// the raw ABI it would be a start voxel outside the model (no brick, no layer to conduct from)
-				if (l == 0) { delete m; return fail(EKG_E_INVALID, "start voxel without a layer (value 0x1000)"); }
-				m->h_starts.push_back(i);
-			}
-			if (l > 255) { delete m; return fail(EKG_E_UNSUPPORTED, "more than 255 layers"); }
-			m->h_layer[(size_t)i] = (uint8_t)l;
-			if (l) { ++m->n_occ; max_layer = std::max<int>(max_layer, l); }
-		}
-		m->h_occ_before_z[(size_t)z + 1] = m->n_occ;
-	}
-	m->n_layers = max_layer;  // targetNumOfAps = highest layer number (simulator.cpp:186-198)
-	if (t_rows < max_layer || t_cols < max_layer) { delete m; return fail(EKG_E_TRANSFER, "loaded transfer matrix too small"); }  // simulator.cpp:203-205
 	m->h_transfer.assign(transfer, transfer + t_rows * t_cols);
 	m->t_rows = t_rows; m->t_cols = t_cols;
 
 #define EKG_CREATE_CUDA(call)                                                                   \
 	do {                                                                                        \
 		cudaError_t e__ = (call);                                                               \
-		if (e__ != cudaSuccess) { int rc__ = cuda_fail(e__, #call, __FILE__, __LINE__); free_model(m); return rc__; } \
+		if (e__ != cudaSuccess) { int rc__ = cuda_fail(e__, #call, __FILE__, __LINE__); cleanup(); free_model(m); return rc__; } \
 	} while (0)
+
+	// scratch of this function
+	uint16_t* d_raw = nullptr;
+	unsigned long long* d_occ_z = nullptr;
+	CreateStats* d_stats = nullptr;
+	long long* d_starts = nullptr;
+	int32_t *d_live = nullptr, *d_scan = nullptr;
+	uint32_t* d_nsel = nullptr;
+	void* d_tmp = nullptr;
+	auto cleanup = [&]() { for (void* p : {(void*)d_raw, (void*)d_occ_z, (void*)d_stats, (void*)d_starts, (void*)d_live, (void*)d_scan, (void*)d_nsel, d_tmp}) if (p) cudaFree(p); };
 
 	EKG_CREATE_CUDA(cudaSetDevice(device));
 	EKG_CREATE_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
 	EKG_CREATE_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
+	cudaStream_t st = m->stream;
 
-	// padded dense layer map + raster list of occupied voxels (automaton)
+	// (1) upload, padded u8 layer map, per-plane counts, start voxels
 	const int64_t npad = m->pZ * m->pY * m->pX;
+	EKG_CREATE_CUDA(cudaMalloc(&d_raw, (size_t)n * 2));
+	EKG_CREATE_CUDA(cudaMalloc(&d_occ_z, (size_t)Z * 8));
+	EKG_CREATE_CUDA(cudaMalloc(&d_stats, sizeof(CreateStats)));
+	EKG_CREATE_CUDA(cudaMalloc(&d_starts, kMaxStarts * 8));
+	EKG_CREATE_CUDA(cudaMalloc(&m->d_layer_pad, (size_t)npad));
+	EKG_CREATE_CUDA(cudaMalloc(&m->d_time_pad, (size_t)npad * 8));
+	EKG_CREATE_CUDA(cudaMalloc(&m->d_flags, (size_t)(m->max_sweeps + 1) * sizeof(int)));
+	EKG_CREATE_CUDA(cudaMemcpyAsync(d_raw, layers, (size_t)n * 2, cudaMemcpyHostToDevice, st));
+	EKG_CREATE_CUDA(cudaMemsetAsync(m->d_layer_pad, 0, (size_t)npad, st));
+	EKG_CREATE_CUDA(cudaMemsetAsync(m->d_time_pad, 0, (size_t)npad * 8, st));
+	EKG_CREATE_CUDA(cudaMemsetAsync(d_occ_z, 0, (size_t)Z * 8, st));
+	EKG_CREATE_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(CreateStats), st));
+	create_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_raw, n, Y, X, m->pY, m->pX, m->d_layer_pad, d_occ_z, d_stats, d_starts);
+	EKG_CREATE_CUDA(cudaGetLastError());
+	CreateStats stats;
+	std::vector<unsigned long long> occ_z((size_t)Z);
+	EKG_CREATE_CUDA(cudaMemcpyAsync(&stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, st));
+	EKG_CREATE_CUDA(cudaMemcpyAsync(occ_z.data(), d_occ_z, (size_t)Z * 8, cudaMemcpyDeviceToHost, st));
+	EKG_CREATE_CUDA(cudaStreamSynchronize(st));   // also: the caller's (pageable) layer array has been consumed
+	if (stats.bad_layer) { cleanup(); free_model(m); return fail(EKG_E_UNSUPPORTED, "more than 255 layers"); }
+	// the text format cannot express "start voxel of layer 0" (matrix.h:124-129 maps -v to 0x1000 + v, v >= 1); through the
+	// raw ABI it would be a start voxel outside the model (no brick, no layer to conduct from)
+	if (stats.bad_start) { cleanup(); free_model(m); return fail(EKG_E_INVALID, "start voxel without a layer (value 0x1000)"); }
+	const int max_layer = stats.max_layer;
+	m->n_layers = max_layer;  // targetNumOfAps = highest layer number (simulator.cpp:186-198)
+	if (t_rows < max_layer || t_cols < max_layer) { cleanup(); free_model(m); return fail(EKG_E_TRANSFER, "loaded transfer matrix too small"); }  // simulator.cpp:203-205
+	m->h_occ_before_z.assign((size_t)Z + 1, 0);
+	for (int64_t z = 0; z < Z; ++z) m->h_occ_before_z[(size_t)z + 1] = m->h_occ_before_z[(size_t)z] + (int64_t)occ_z[(size_t)z];
+	m->n_occ = m->h_occ_before_z[(size_t)Z];
+	if (stats.n_starts <= kMaxStarts) {
+		std::vector<long long> hs((size_t)stats.n_starts);
+		if (!hs.empty()) EKG_CREATE_CUDA(cudaMemcpy(hs.data(), d_starts, hs.size() * 8, cudaMemcpyDeviceToHost));
+		std::sort(hs.begin(), hs.end());
+		m->h_starts.assign(hs.begin(), hs.end());
+	} else {   // a model made of start voxels: read them off the caller's array
+		for (int64_t i = 0; i < n; ++i) if (layers[i] & kStartFlag) m->h_starts.push_back(i);
+	}
+
+	// (2) raster list of the occupied voxels (padded indices): stream compaction, in chunks CUB's 32-bit item counts can take
+	EKG_CREATE_CUDA(cudaMalloc(&m->d_auto_pidx, (size_t)std::max<int64_t>(m->n_occ, 1) * 4));
+	EKG_CREATE_CUDA(cudaMalloc(&d_nsel, 4));
 	{
-		std::vector<uint8_t> lp((size_t)npad, 0);
-		std::vector<uint32_t> pidx((size_t)std::max<int64_t>(m->n_occ, 1));
-		int64_t j = 0;
-		for (int64_t z = 0; z < Z; ++z) for (int64_t y = 0; y < Y; ++y) for (int64_t x = 0; x < X; ++x) {
-			const uint8_t l = m->h_layer[(size_t)((z * Y + y) * X + x)];
-			if (!l) continue;
-			const int64_t p = pad_index(m, z, y, x);
-			lp[(size_t)p] = l;
-			pidx[(size_t)j++] = (uint32_t)p;
+		const int64_t chunk = (int64_t)1 << 30;
+		size_t tmp_bytes = 0;
+		OccupiedAt pred{m->d_layer_pad};
+		EKG_CREATE_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, cub::CountingInputIterator<uint32_t>(0u), m->d_auto_pidx, d_nsel,
+		                                      (int)std::min<int64_t>(npad, chunk), pred, st));
+		EKG_CREATE_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 1)));
+		int64_t done = 0;
+		for (int64_t p0 = 0; p0 < npad; p0 += chunk) {
+			const int cnt = (int)std::min<int64_t>(chunk, npad - p0);
+			EKG_CREATE_CUDA(cub::DeviceSelect::If(d_tmp, tmp_bytes, cub::CountingInputIterator<uint32_t>((uint32_t)p0), m->d_auto_pidx + done, d_nsel, cnt, pred, st));
+			if (p0 + chunk < npad) {
+				uint32_t got = 0;
+				EKG_CREATE_CUDA(cudaMemcpyAsync(&got, d_nsel, 4, cudaMemcpyDeviceToHost, st));
+				EKG_CREATE_CUDA(cudaStreamSynchronize(st));
+				done += got;
+			}
 		}
-		EKG_CREATE_CUDA(cudaMalloc(&m->d_layer_pad, (size_t)npad));
-		EKG_CREATE_CUDA(cudaMalloc(&m->d_time_pad, (size_t)npad * 8));
-		EKG_CREATE_CUDA(cudaMalloc(&m->d_auto_pidx, pidx.size() * 4));
-		EKG_CREATE_CUDA(cudaMalloc(&m->d_flags, (size_t)(m->max_sweeps + 1) * sizeof(int)));
-		if (upload(m, m->d_layer_pad, lp.data(), (size_t)npad) || upload(m, m->d_auto_pidx, pidx.data(), pidx.size() * 4)) { free_model(m); return EKG_E_CUDA; }
-		EKG_CREATE_CUDA(cudaMemsetAsync(m->d_time_pad, 0, (size_t)npad * 8, m->stream));
-		EKG_CREATE_CUDA(cudaStreamSynchronize(m->stream));
+		cudaFree(d_tmp); d_tmp = nullptr;
 	}
 	// edge weights: lag = T[layer][neighbour layer] * sqrt(sqrLength(dif)) (simulator.cpp:239-240), host IEEE arithmetic
 	{
@@ -431,54 +587,59 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		std::vector<double> w((size_t)nl1 * nl1 * 3, INFINITY);
 		for (int lu = 1; lu < nl1; ++lu) for (int lv = 1; lv < nl1; ++lv) {
 			if (lu >= t_rows || lv >= t_cols) continue;
-			for (int s = 1; s <= 3; ++s) {
+			for (int sq = 1; sq <= 3; ++sq) {
 				double lag = transfer[(int64_t)lu * t_cols + lv];
-				lag *= std::sqrt((double)s);
-				w[((size_t)lu * nl1 + lv) * 3 + (s - 1)] = lag;
+				lag *= std::sqrt((double)sq);
+				w[((size_t)lu * nl1 + lv) * 3 + (sq - 1)] = lag;
 			}
 		}
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_wtab, w.size() * 8));
-		if (upload(m, m->d_wtab, w.data(), w.size() * 8)) { free_model(m); return EKG_E_CUDA; }
+		if (upload(m, m->d_wtab, w.data(), w.size() * 8)) { cleanup(); free_model(m); return EKG_E_CUDA; }
 	}
-	// live bricks (kBrick^3 tiles holding at least one occupied voxel), their origins and 26 neighbours
+	// (3) live bricks (kBrick^3 tiles holding at least one occupied voxel) in brick-raster order, their origins and 26 neighbours
 	{
 		const int64_t kb = kBrick;
-		const int64_t bZ = (Z + kb - 1) / kb, bY = (Y + kb - 1) / kb, bX = (X + kb - 1) / kb;
-		std::vector<int32_t> index((size_t)(bZ * bY * bX), -1);
-		std::vector<uint32_t> origin;
-		for (int64_t z = 0; z < Z; ++z) for (int64_t y = 0; y < Y; ++y) for (int64_t x = 0; x < X; ++x) {
-			if (!m->h_layer[(size_t)((z * Y + y) * X + x)]) continue;
-			int32_t& bi = index[(size_t)(((z / kb) * bY + y / kb) * bX + x / kb)];
-			if (bi < 0) { bi = (int32_t)origin.size(); origin.push_back((uint32_t)pad_index(m, z / kb * kb, y / kb * kb, x / kb * kb)); }
-		}
-		const int64_t nb = (int64_t)origin.size();
-		std::vector<int32_t> nbr((size_t)std::max<int64_t>(nb, 1) * 26, -1);
-		for (int64_t bz = 0; bz < bZ; ++bz) for (int64_t by = 0; by < bY; ++by) for (int64_t bx = 0; bx < bX; ++bx) {
-			const int32_t bi = index[(size_t)((bz * bY + by) * bX + bx)];
-			if (bi < 0) continue;
-			int k = 0;
-			for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
-				if (!dz && !dy && !dx) continue;
-				const int64_t cz = bz + dz, cy = by + dy, cx = bx + dx;
-				if (cz >= 0 && cz < bZ && cy >= 0 && cy < bY && cx >= 0 && cx < bX) nbr[(size_t)bi * 26 + k] = index[(size_t)((cz * bY + cy) * bX + cx)];
-				++k;
-			}
-		}
-		for (int64_t r : m->h_starts) {
-			const int64_t z = r / (Y * X), y = (r / X) % Y, x = r % X;
-			const int32_t bi = index[(size_t)(((z / kBrick) * bY + y / kBrick) * bX + x / kBrick)];
-			if (bi < 0) { free_model(m); return fail(EKG_E_INVALID, "start voxel outside every occupied brick"); }   // cannot happen: a start voxel is occupied
-			if (std::find(m->h_start_bricks.begin(), m->h_start_bricks.end(), bi) == m->h_start_bricks.end()) m->h_start_bricks.push_back(bi);
-		}
-		m->n_bricks = nb;
-		m->h_brick_index = index; m->h_brick_origin = origin;
+		const int64_t bZ = (Z + kb - 1) / kb, bY = (Y + kb - 1) / kb, bX = (X + kb - 1) / kb, n_cells = bZ * bY * bX;
 		m->bZ = bZ; m->bY = bY; m->bX = bX;
+		EKG_CREATE_CUDA(cudaMalloc(&d_live, (size_t)n_cells * 4));
+		EKG_CREATE_CUDA(cudaMalloc(&d_scan, (size_t)n_cells * 4));
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_index, (size_t)n_cells * 4));
+		const unsigned cb = (unsigned)((n_cells + 255) / 256);
+		brick_live_kernel<<<cb, 256, 0, st>>>(m->d_layer_pad, n_cells, (int)bY, (int)bX, m->pY, m->pX, d_live);
+		EKG_CREATE_CUDA(cudaGetLastError());
+		size_t tmp_bytes = 0;
+		EKG_CREATE_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_live, d_scan, (int)n_cells, st));
+		EKG_CREATE_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 1)));
+		EKG_CREATE_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_live, d_scan, (int)n_cells, st));
+		int32_t last[2] = {0, 0};
+		EKG_CREATE_CUDA(cudaMemcpyAsync(&last[0], d_live + (n_cells - 1), 4, cudaMemcpyDeviceToHost, st));
+		EKG_CREATE_CUDA(cudaMemcpyAsync(&last[1], d_scan + (n_cells - 1), 4, cudaMemcpyDeviceToHost, st));
+		EKG_CREATE_CUDA(cudaStreamSynchronize(st));
+		const int64_t nb = (int64_t)last[0] + last[1];
+		m->n_bricks = nb;
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_origin, (size_t)std::max<int64_t>(nb, 1) * 4));
-		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_nbr, nbr.size() * 4));
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_nbr, (size_t)std::max<int64_t>(nb, 1) * 26 * 4));
 		// flag[n] | first_visit[n] | ring[capacity <= max(2n, 2)] | counters[8]   (automaton.cu, run_automaton_bricks)
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, ((size_t)nb * 5 + 16) * sizeof(int)));
-		if (upload(m, m->d_brick_origin, origin.data(), origin.size() * 4) || upload(m, m->d_brick_nbr, nbr.data(), nbr.size() * 4)) { free_model(m); return EKG_E_CUDA; }
+		brick_index_kernel<<<cb, 256, 0, st>>>(d_live, d_scan, n_cells, (int)bY, (int)bX, m->pY, m->pX, m->d_brick_index, m->d_brick_origin);
+		EKG_CREATE_CUDA(cudaGetLastError());
+		brick_nbr_kernel<<<cb, 256, 0, st>>>(m->d_brick_index, n_cells, (int)bZ, (int)bY, (int)bX, m->d_brick_nbr);
+		EKG_CREATE_CUDA(cudaGetLastError());
+		for (int64_t r : m->h_starts) {
+			const int64_t z = r / (Y * X), y = (r / X) % Y, x = r % X;
+			int32_t bi = -1;
+			EKG_CREATE_CUDA(cudaMemcpyAsync(&bi, m->d_brick_index + (((z / kBrick) * bY + y / kBrick) * bX + x / kBrick), 4, cudaMemcpyDeviceToHost, st));
+			EKG_CREATE_CUDA(cudaStreamSynchronize(st));
+			if (bi < 0) { cleanup(); free_model(m); return fail(EKG_E_INVALID, "start voxel outside every occupied brick"); }   // cannot happen: a start voxel is occupied
+			if (std::find(m->h_start_bricks.begin(), m->h_start_bricks.end(), bi) == m->h_start_bricks.end()) {
+				m->h_start_bricks.push_back(bi);
+				m->h_start_brick_bz.push_back(z / kBrick);
+			}
+		}
+		EKG_CREATE_CUDA(cudaStreamSynchronize(st));
 	}
+	cleanup();
+#undef EKG_CREATE_CUDA
 	int rc = build_ecg_list(m, 0, Z);
 	if (rc) { free_model(m); return rc; }
 	*out = m;
@@ -540,7 +701,14 @@ int ekg_model_activation_begin(ekg_model* m) {
 int ekg_model_activation_relax(ekg_model* m, int64_t* brick_visits_out) {
 	if (!m) return fail(EKG_E_INVALID, "model is NULL");
 	EKG_CUDA(cudaSetDevice(m->device));
-	return shard_relax(m, brick_visits_out);
+	return shard_relax(m, 0, brick_visits_out, nullptr);
+}
+
+int ekg_model_activation_relax_bounded(ekg_model* m, int64_t max_brick_visits, int64_t* brick_visits_out, int64_t* bricks_left_out) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	if (max_brick_visits < 0) return fail(EKG_E_INVALID, "negative visit bound");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_relax(m, max_brick_visits, brick_visits_out, bricks_left_out);
 }
 
 int64_t ekg_model_plane_elems(const ekg_model* m) { return m ? m->pY * m->pX : 0; }
@@ -576,11 +744,17 @@ int ekg_model_set_activation(ekg_model* m, const double* delay) {
 	const int64_t n = m->Z * m->Y * m->X;
 	m->h_delay.assign(delay, delay + n);  // the caller's values as given (also those of empty voxels)
 	m->h_delay_valid = true;
-	std::vector<double> padded((size_t)(m->pZ * m->pY * m->pX), 0.0);
-	for (int64_t z = 0; z < m->Z; ++z) for (int64_t y = 0; y < m->Y; ++y)
-		memcpy(&padded[(size_t)pad_index(m, z, y, 0)], &delay[(z * m->Y + y) * m->X], (size_t)m->X * 8);
-	int rc = upload(m, m->d_time_pad, padded.data(), padded.size() * 8);
-	if (rc) return rc;
+	double* d_raster = nullptr;
+	EKG_CUDA(cudaMalloc(&d_raster, (size_t)n * 8));
+	cudaError_t e = cudaMemcpyAsync(d_raster, delay, (size_t)n * 8, cudaMemcpyHostToDevice, m->stream);
+	if (e == cudaSuccess) e = cudaMemsetAsync(m->d_time_pad, 0, (size_t)(m->pZ * m->pY * m->pX) * 8, m->stream);
+	if (e == cudaSuccess) {
+		pad_activation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(d_raster, n, m->Y, m->X, m->pY, m->pX, m->d_time_pad);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+	cudaFree(d_raster);
+	if (e != cudaSuccess) return cuda_fail(e, "upload of the activation map", __FILE__, __LINE__);
 	return publish_activation(m);
 }
 
@@ -599,7 +773,8 @@ double ekg_model_activation_ms(const ekg_model* m) { return m ? (double)m->activ
 int ekg_model_ap_classes(const ekg_model* m, int64_t* ap_index_out, int64_t* n_classes_out) {
 	if (!m || !ap_index_out || !n_classes_out) return fail(EKG_E_INVALID, "NULL argument");
 	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence yet");
-	if (int rc = ensure_host_delay(const_cast<ekg_model*>(m))) return rc;  // lazily cached host copy
+	if (int rc = ensure_host_delay(const_cast<ekg_model*>(m))) return rc;  // lazily cached host copies
+	if (int rc = ensure_host_layer(const_cast<ekg_model*>(m))) return rc;
 	// one (layer, exact delay) -> index map, indices handed out in first-seen raster order
 	// (simulator.cpp:566-590 keeps one std::map<double,size_t> per layer with a shared counter)
 	struct Key { uint64_t bits; uint32_t layer; bool operator==(const Key& o) const { return bits == o.bits && layer == o.layer; } };

@@ -121,7 +121,8 @@ struct BrickArgs {
 	int* first_visit;        // [n_live] 1 for the bricks of the start voxels until their first visit
 	const uint8_t* own;      // [n_live] sharded run: 1 for the bricks this rank relaxes (NULL = all)
 	int* queue;              // ring of brick ids, -1 = empty slot, qmask + 1 slots
-	int* counters;           // [0] head, [1] tail, [2] pending (queued or in work), [4] visits, [5] inner sweeps
+	int* counters;           // [0] head, [1] tail, [2] pending (queued or in work), [4] visits, [5] inner sweeps, [6] stop
+	uint32_t budget;         // bounded relaxation (sharded run): no further ring position is claimed once `budget` have been; 0 = no bound
 	uint32_t qmask;
 	int32_t n_live, nl1, n_nbr, pY, pX, w_in_smem;
 	int32_t loff[kMaxNbr];   // neighbour offset inside the 10^3 shared-memory cell array
@@ -142,7 +143,7 @@ struct ekg_model {
 	int sm_count = 148;
 
 	// host copies
-	std::vector<uint8_t> h_layer;    // raster, start flags stripped
+	std::vector<uint8_t> h_layer;    // raster, start flags stripped: a lazily made host copy (ekg_model_ap_classes)
 	std::vector<int64_t> h_starts;   // raster indices of start voxels
 	std::vector<int64_t> h_occ_before_z;  // [Z + 1] occupied voxels in the planes below z (a z-slab is a run of d_auto_pidx)
 	std::vector<double> h_transfer;
@@ -169,11 +170,10 @@ struct ekg_model {
 	int32_t* d_brick_nbr = nullptr;
 	int* d_brick_state = nullptr;        // flag[2][n] | queue[3][n] | counters[8]
 	std::vector<int32_t> h_start_bricks;
+	std::vector<int64_t> h_start_brick_bz;   // brick z index of every start brick
 	// z-slab sharded automaton (ekg_model_activation_begin / _relax / _export / _merge / _end)
-	std::vector<int32_t> h_brick_index;  // dense brick grid [bZ][bY][bX] -> live brick id, -1 = no occupied voxel
-	std::vector<uint32_t> h_brick_origin;
 	int64_t bZ = 0, bY = 0, bX = 0;
-	int32_t* d_brick_index = nullptr;
+	int32_t* d_brick_index = nullptr;    // dense brick grid [bZ][bY][bX] -> live brick id, -1 = no occupied voxel
 	uint8_t* d_brick_own = nullptr;
 	int* d_brick_mark = nullptr;         // bricks to queue at the next relax
 	unsigned long long* d_improved = nullptr;
@@ -228,7 +228,7 @@ namespace ekg {
 // automaton.cu
 int run_automaton(ekg_model* m, int64_t* sweeps_out);
 int shard_begin(ekg_model* m);
-int shard_relax(ekg_model* m, int64_t* visits_out);
+int shard_relax(ekg_model* m, int64_t max_visits, int64_t* visits_out, int64_t* leftover_out);
 int shard_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, cudaStream_t st);
 int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, cudaStream_t st);
 // ecg.cu

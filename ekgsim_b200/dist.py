@@ -113,8 +113,9 @@ class ModelPlanes:
     def begin(self):
         self.model.activation_begin()
 
-    def relax(self):
-        return self.model.activation_relax()
+    def relax(self, max_visits=0):
+        """-> (brick visits, bricks still queued)"""
+        return self.model.activation_relax_bounded(max_visits)
 
     def export(self, z_begin, z_end):
         t = self.torch.empty((max(z_end - z_begin, 0), self.plane_elems), dtype=self.torch.float64, device=self.device)
@@ -133,16 +134,20 @@ class ModelPlanes:
         return self.model.activation_end(download=download)
 
 
-def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, timings=None, download=True):
+def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, timings=None, download=True, visits_per_round=None):
     """The activation automaton of a model sharded into z-slabs.
 
-    `planes` offers begin / relax / export(z0, z1) -> tensor[z1-z0, plane_elems] / merge(z0, tensor) -> improved cells /
-    end (ModelPlanes for the CUDA model); `slabs[r] = (z_begin, z_end)` is rank r's slab, already set on the model.
-    Per round every rank relaxes its slab to the fixed point of its current halo, sends its first and last own plane
-    to the rank below / above (one point-to-point message each way over NCCL / NVLink), merges what it receives
-    (elementwise minimum) and the ranks agree through one all-reduce whether anything improved anywhere.  Min-merging
-    never overshoots the least fixed point, so the result has the bits of the single-GPU run.  At the end every rank
-    broadcasts its slab so that all ranks hold the whole map, like after `ekg_model_activation`.
+    `planes` offers begin / relax(max_visits) -> (visits, bricks left) / export(z0, z1) -> tensor[z1-z0, plane_elems] /
+    merge(z0, tensor) -> improved cells / end (ModelPlanes for the CUDA model); `slabs[r] = (z_begin, z_end)` is rank r's
+    slab, already set on the model.  Per round every rank relaxes its slab for at most `visits_per_round` brick visits
+    (None: a bound derived from the slab size; 0: to the fixed point of its current halo), sends its first and last
+    own plane to the rank below / above (one point-to-point message each way over NCCL / NVLink), merges what it
+    receives (elementwise minimum) and the ranks agree through one all-reduce whether anything improved or is still
+    queued anywhere.  Bounding the relaxation hands the wave to the neighbouring slabs early: an excitation wave
+    crosses the slabs one after the other, and with unbounded rounds the ranks would work one after the other, too.
+    Min-merging never overshoots the least fixed point, so the result has the bits of the single-GPU run whatever the
+    bound.  At the end every rank broadcasts its slab so that all ranks hold the whole map, like after
+    `ekg_model_activation`.
     Returns (delay[Z, Y, X] as numpy, rounds, brick visits of this rank); `timings` (a dict) receives the wall seconds
     of the three phases: rounds, gather, publish.  download=False leaves the map on the device (delay is None): the
     ECG entry points only need it there."""
@@ -158,14 +163,20 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, t
     below = max([r for r in live if r < rank], default=None) if rank in live else None
     above = min([r for r in live if r > rank], default=None) if rank in live else None
     z0, z1 = slabs[rank]
+    if visits_per_round is None:
+        # about one visit per 4^3 brick of a grid-sized slab: a fraction of what the slab needs in total (a brick is
+        # visited ~5 times), a millisecond or so of work -- several times the cost of the exchange that follows
+        visits_per_round = 0 if world == 1 else max(16384, (z1 - z0) * planes.plane_elems // 64)
     t_begin = time.perf_counter()
     planes.begin()
     visits, rounds = 0, 0
     while True:
         rounds += 1
+        left = 0
         if rank in live:
-            visits += planes.relax()
-        improved = 0
+            v, left = planes.relax(visits_per_round)
+            visits += v
+        improved = left
         if world > 1:
             ops, recv_below, recv_above = [], None, None
             if below is not None:

@@ -125,6 +125,11 @@ int  ekg_model_set_activation(ekg_model* m, const double* delay);
  * z from -1 (border) to Z.
  *   begin   times = +inf, start voxels = 1 (simulator.cpp:263); the start bricks inside the slab are queued
  *   relax   frontier relaxation from the queued bricks until the slab is at its fixed point for its current halo
+ *   relax_bounded   the same, but at most ~max_brick_visits brick visits (0 = no bound); bricks_left_out = bricks still
+ *           queued, they are carried into the next relax.  With a bound the wave reaches the neighbouring slabs
+ *           before this slab is finished, so the ranks work side by side; the loop then ends when no merge improved
+ *           anything AND no rank has bricks left.  Min-merging stale values is harmless: times only ever decrease
+ *           towards the least fixed point, the bits are those of the unbounded run.
  *   export  copies planes [z_begin, z_end) into a device buffer (complete on return)
  *   merge   time = min(time, planes); bricks of the slab that can see an improved cell are queued for the next
  *           relax; improved_out = number of improved cells
@@ -132,6 +137,7 @@ int  ekg_model_set_activation(ekg_model* m, const double* delay);
  *           delay_out is not NULL) */
 int     ekg_model_activation_begin(ekg_model* m);
 int     ekg_model_activation_relax(ekg_model* m, int64_t* brick_visits_out);
+int     ekg_model_activation_relax_bounded(ekg_model* m, int64_t max_brick_visits, int64_t* brick_visits_out, int64_t* bricks_left_out);
 int64_t ekg_model_plane_elems(const ekg_model* m);
 int     ekg_model_activation_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, void* stream);
 int     ekg_model_activation_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes,

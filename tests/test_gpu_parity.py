@@ -582,7 +582,7 @@ def test_separable_series_lead_distance(built, scale, n_leads):
     m.close()
 
 
-def run_sharded(ranks, slabs):
+def run_sharded(ranks, slabs, budget=0):
     """The exchange loop of ekgsim_b200.dist.sharded_activation with the planes handed over directly."""
     world = len(ranks)
     for p in ranks:
@@ -590,8 +590,11 @@ def run_sharded(ranks, slabs):
     rounds, visits = 0, 0
     while True:
         rounds += 1
-        visits += sum(p.relax() for p in ranks)
         improved = 0
+        for p in ranks:
+            v, left = p.relax(budget)
+            visits += v
+            improved += left
         for r in range(world - 1):
             up = ranks[r].export(slabs[r][1] - 1, slabs[r][1])            # last plane of r -> halo of r + 1
             dn = ranks[r + 1].export(slabs[r + 1][0], slabs[r + 1][0] + 1)  # first plane of r + 1 -> halo of r
@@ -599,7 +602,7 @@ def run_sharded(ranks, slabs):
             improved += ranks[r].merge(slabs[r + 1][0], dn)
         if improved == 0:
             break
-        assert rounds < 500
+        assert rounds < 5000
     for s in range(world):
         buf = ranks[s].export(*slabs[s])
         for r in range(world):
@@ -627,6 +630,11 @@ def test_sharded_automaton_many_crossings(built):
             assert d.tobytes() == ref.tobytes(), slabs
         assert rounds >= 10, (slabs, rounds)
         print("serpentine, slabs %s: %d rounds, %d brick visits" % (slabs, rounds, visits))
+        # bounded relaxation: at most ~3 brick visits per rank and round, the leftovers are carried over
+        rounds_b, visits_b, delays_b = run_sharded(ranks, slabs, budget=3)
+        for d in delays_b:
+            assert d.tobytes() == ref.tobytes(), slabs
+        assert rounds_b > rounds
         for p in ranks:
             p.model.close()
 
@@ -653,6 +661,12 @@ def test_sharded_automaton_entry_points(built, model24, model24_delay, world):
     for delay in delays:
         assert delay.tobytes() == model24_delay.tobytes()
     print("sharded automaton, %d slabs on model_24: %d rounds, %d brick visits in total" % (world, rounds, visits))
+    # bounded rounds (what the NCCL driver uses so that the ranks work side by side): same bits, more rounds
+    rounds_b, visits_b, delays_b = run_sharded(ranks, slabs, budget=4000)
+    assert rounds_b > rounds
+    for delay in delays_b:
+        assert delay.tobytes() == model24_delay.tobytes()
+    print("  bounded to 4000 visits per round: %d rounds, %d brick visits" % (rounds_b, visits_b))
     # the handles are usable afterwards like after ekg_model_activation: slab ECGs add up
     g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
     parts = sum(p.model.simulate(g["layer_k"][:2], g["leads_zyx"][:2], "3D4", 100.0, 1.0, 50.0, mode=3) for p in ranks)
@@ -662,6 +676,8 @@ def test_sharded_automaton_entry_points(built, model24, model24_delay, world):
     assert rel_err(parts, ref) < 2e-6
     with pytest.raises(built.EkgError):
         whole.activation_relax()                                           # not between begin and end
+    with pytest.raises(built.EkgError):
+        whole.activation_relax_bounded(100)
     for p in ranks:
         p.model.close()
 
