@@ -698,24 +698,32 @@ __global__ void __launch_bounds__(256, NP == 1 ? 3 : 2) ecg_moment_fused_kernel(
 
 // ECG[b][l][t] for the samples t >= t_off from the moments: one CTA per (vector, block of 32 samples), threads =
 // 32 samples x 8 layer lanes (lane g takes the layers g, g + 8, ...; a single simulation still yields 13 CTAs x 256
-// threads of f64 pow/exp work instead of 4 x 128).  Shared memory: the per-layer moments of this vector (segments
-// added in order) and the lanes' partial sums, added in lane order -> deterministic.  F1, F2 by the expressions of
+// threads of f64 pow/exp work instead of 4 x 128).  Shared memory: the per-layer moments of this vector
+// (ecg_layer_moments_kernel: segments added in order) and the lanes' partial sums, added in lane order -> deterministic.  F1, F2 by the expressions of
 // ecg_ftab_kernel, kept in f64; ln(2^(k7/k6)-1) per (vector, layer) comes from ecg_params_kernel.
 constexpr int kCombSamples = 32, kCombLanes = 8;
+
+// per-(vector, layer) moments: the segments of a layer added in segment order, once (not once per combine CTA)
+__global__ void __launch_bounds__(128) ecg_layer_moments_kernel(const double* __restrict__ mom, const int32_t* __restrict__ seg_first,
+                                                                double* __restrict__ lmom, int B, int L, int n_layers) {
+	const int b = blockIdx.x;
+	for (int o = threadIdx.x; o < n_layers * L * 3; o += blockDim.x) {
+		const int layer = o / (L * 3), r = o - layer * (L * 3);
+		double s = 0.0;
+		for (int sgi = seg_first[layer]; sgi < seg_first[layer + 1]; ++sgi) s += mom[((int64_t)sgi * B + b) * L * 3 + r];
+		lmom[(int64_t)b * n_layers * L * 3 + o] = s;
+	}
+}
+
 __global__ void __launch_bounds__(kCombSamples * kCombLanes) ecg_combine_kernel(const double* __restrict__ layer_k, const double* __restrict__ tail,
-                                                                               const double* __restrict__ times, const double* __restrict__ mom,
+                                                                               const double* __restrict__ times, const double* __restrict__ lmom,
                                                                                const int32_t* __restrict__ seg_first, double* __restrict__ ecg,
                                                                                int B, int L, int n_layers, int T, int t_off, double t0) {
 	extern __shared__ double s_dyn[];
 	double* s_mom = s_dyn;                       // [n_layers][L][3]
 	double* s_acc = s_dyn + n_layers * L * 3;    // [kCombLanes][4][kCombSamples + 1]
 	const int b = blockIdx.y;
-	for (int o = threadIdx.x; o < n_layers * L * 3; o += blockDim.x) {
-		const int layer = o / (L * 3), r = o - layer * (L * 3);
-		double s = 0.0;
-		for (int sgi = seg_first[layer]; sgi < seg_first[layer + 1]; ++sgi) s += mom[((int64_t)sgi * B + b) * L * 3 + r];
-		s_mom[o] = s;
-	}
+	for (int o = threadIdx.x; o < n_layers * L * 3; o += blockDim.x) s_mom[o] = lmom[(int64_t)b * n_layers * L * 3 + o];
 	__syncthreads();
 	const int ts = threadIdx.x & (kCombSamples - 1), g = threadIdx.x / kCombSamples;
 	const int t = t_off + blockIdx.x * kCombSamples + ts;
@@ -1306,7 +1314,11 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		const int64_t n_late = T - T_loop;
 		const size_t smem = (size_t)(m->n_layers * L * 3 + kCombLanes * 4 * (kCombSamples + 1)) * sizeof(double);
 		const dim3 cgrid((unsigned)((n_late + kCombSamples - 1) / kCombSamples), (unsigned)B, 1);
-		ecg_combine_kernel<<<cgrid, kCombSamples * kCombLanes, smem, st>>>(d_layer_k, m->d_tail, d_t64, m->d_mom, m->d_mseg_first, d_ecg, (int)B, (int)L,
+		if ((rc = ensure(&m->d_lmom, &m->lmom_cap, B * m->n_layers * L * 3))) return rc;
+		ecg_layer_moments_kernel<<<(unsigned)B, 128, 0, st>>>(m->d_mom, m->d_mseg_first, m->d_lmom, (int)B, (int)L, m->n_layers);
+		EKG_CUDA(cudaGetLastError());
+		++m->last_launches;
+		ecg_combine_kernel<<<cgrid, kCombSamples * kCombLanes, smem, st>>>(d_layer_k, m->d_tail, d_t64, m->d_lmom, m->d_mseg_first, d_ecg, (int)B, (int)L,
 		                                                                  m->n_layers, (int)T, (int)T_loop, (double)(float)m->t0);
 		EKG_CUDA(cudaGetLastError());
 		++m->last_launches;

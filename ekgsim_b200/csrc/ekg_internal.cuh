@@ -200,6 +200,7 @@ struct ekg_model {
 	ekg::Segment* d_msegs = nullptr; int64_t msegs_cap = 0;  int64_t n_msegs = 0;  int64_t mseg_len = 0;
 	int32_t* d_mseg_first = nullptr; int64_t mseg_first_cap = 0;   // first segment of every layer, n_layers + 1 entries
 	double* d_mom = nullptr;         int64_t mom_cap = 0;          // [n_msegs][B][L][3] moments
+	double* d_lmom = nullptr;        int64_t lmom_cap = 0;         // [B][n_layers][L][3] the same per layer
 	int32_t* d_near = nullptr;       int64_t near_cap = 0;         // MomentArgs::near_flag
 	int* d_k1min = nullptr;                                        // [2] float bits of min k1 / max decay rate over (vector, layer), by ecg_params_kernel
 	float* d_params = nullptr;       int64_t params_cap = 0;

@@ -130,47 +130,56 @@ __global__ void __launch_bounds__(256) fit_setup_kernel(FitArgs a) {
 }
 
 // ---- descent --------------------------------------------------------------------------------------
-struct Factors { double A, E4, E5, Q; };
+constexpr int kFitsPerCta = 8;    // 128 threads, one half-warp per fit
+constexpr int kRowStride = 18;    // doubles per row of squared misses: 16-byte aligned, rows 4 banks apart
 
-constexpr int kFitsPerCta = 8;   // 128 threads, one half-warp per fit
+// State of one fit that is the same for all its 15 points, in shared memory (every lane of the half-warp reads the same
+// word: a broadcast), plus the rows the ordered sums go through.
+template <int NROWS>
+struct FitShared {
+	double x0[9];                       // iterate
+	double kt[9];                       // trial point; coefficients that are not fitted stay equal to x0
+	double move[9], grad[9];            // per-coefficient step factor and the previous difference quotient
+	double rows[NROWS][kRowStride];     // squared misses of one evaluation per row, [row][point]
+};
 
-// sum of the 15 squared misses in index order; every lane of the half-warp gets the same bits.  The values go through
-// the fit's 16-slot row of shared memory: one store, eight 16-byte broadcast loads and the 14 dependent additions the
-// reference's loop performs (the same through shuffles costs 30 SHFL + 14 DADD).
-__device__ __forceinline__ double ordered_sum(double e, double* row, int lane16, unsigned mask) {
-	row[lane16] = e;
-	__syncwarp(mask);
+// sum of the 15 squared misses of a row in index order ((e0 + e1) + e2) + ... exactly like the reference's loop
+__device__ __forceinline__ double row_sum(const double* row) {
 	const double2* r2 = reinterpret_cast<const double2*>(row);
 	double2 v = r2[0];
 	double s = add(v.x, v.y);   // 0 + e0 == e0
 #pragma unroll
 	for (int n = 1; n < 7; ++n) { v = r2[n]; s = add(add(s, v.x), v.y); }
-	s = add(s, row[14]);
-	__syncwarp(mask);           // everybody has read before the next evaluation overwrites the row
-	return s;
+	return add(s, row[14]);
 }
 
 // DM: compile-time set of fitted coefficients (bit q <=> d[q] != 0), 0 = decide at run time.  The reference's
-// set {k3, k5, k6, k7, k8} has its own instantiation: state of the coefficients that never move stays out of
-// registers, and the AP factors they alone enter (the depolarisation sigmoid for k1, exp(-k4 t) for k4) are computed
-// once instead of once per trial point -- the same inputs give the same bits.
+// set {k3, k5, k6, k7, k8} has its own instantiation.
 //
-// Per iteration (nonlinearFit.h:104-164): one one-sided difference per fitted coefficient (only the factor that
-// coefficient enters is recomputed, like the host glue does), the sign-following update, one full evaluation of the
-// trial point.  ln(2^(k7/k6) - 1) depends on (k6, k7) only and is the same for all 15 points: the values for the trial
-// point and for its k6- and k7-perturbed neighbours (needed by the NEXT iteration if the trial point is accepted) are
-// computed side by side in three lanes of ONE call -- always by the same function, so every use sees the bits a fresh
-// evaluation would give.  After a rejected trial point the iterate, and with it every difference quotient, is
-// unchanged: the next iteration reuses them (grad[] holds exactly those values).
+// One half-warp per (vector, inner layer): lane = connector point for everything that is evaluated per point (the AP
+// factors), lane = fitted coefficient for everything that is evaluated per coefficient (the ordered sums of the squared
+// misses, the difference quotients, the step-factor updates, the trial point) -- the five perturbed evaluations of an
+// iteration cost one pass of 14 dependent additions and one division instead of five.  The three perturbations that go
+// through the repolarisation term (k6, k7, k8: exp + pow each) are evaluated together by exp_n / pow_n: three
+// independent dependency chains in one straight line of code.  Per iteration (nonlinearFit.h:104-164):
+//   1. one-sided differences: only the AP factor a coefficient enters is recomputed (like the host glue does),
+//   2. sign-following update of the step factors and the trial point,
+//   3. ln(2^(k7/k6) - 1) for the trial point and its k6- / k7-perturbed neighbours (needed by the NEXT iteration if the
+//      trial point is accepted) side by side in three lanes of ONE call,
+//   4. full evaluation of the trial point, accept / reject.
+// After a rejected trial point the iterate, and with it every difference quotient, is unchanged: the next iteration
+// reuses them (grad[] holds exactly those values).  Every value is produced by the same function from the same inputs
+// as in the reference's serial loop -- only WHO computes it changed -- so the bits are the reference's.
 template <unsigned DM>
 __global__ void __launch_bounds__(16 * kFitsPerCta, 5) fit_descent_kernel(FitArgs a) {
-	__shared__ __align__(16) double s_sum[kFitsPerCta][16];
+	constexpr int NROWS = DM ? (int)__builtin_popcount(DM) : 9;
+	__shared__ __align__(16) FitShared<NROWS> s_fit[kFitsPerCta];
 	const int per_b = a.nl - a.nb;  // inner layers per vector
 	const int fit = blockIdx.x * kFitsPerCta + (threadIdx.x >> 4);
 	if (fit >= a.B * per_b) return;  // whole half-warps leave together
 	const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
 	const int lane16 = threadIdx.x & 15;
-	double* row = s_sum[threadIdx.x >> 4];
+	FitShared<NROWS>& S = s_fit[threadIdx.x >> 4];
 	const int b = fit / per_b;
 	int layer = fit % per_b + 1;
 	int ja = 0, jb = a.nb - 1;
@@ -195,16 +204,23 @@ __global__ void __launch_bounds__(16 * kFitsPerCta, 5) fit_descent_kernel(FitArg
 	const double px = add(x1, mul(sub(x2, x1), ratio));   // LineConnector::getX, sim.cpp:107-109
 	const double py = add(mul(ck, px), cn);               // sim.cpp:102-104
 
-	double x0[9], move[9], grad[9];   // grad: the previous iteration's gradient until overwritten in place
 	auto fitted = [&](int q) { return DM ? ((DM >> q) & 1u) != 0 : a.d[q] != 0; };
-	const double* ka = a.border_k + (size_t)(b * a.nb + ja) * 9;
-	const double* kb = a.border_k + (size_t)(b * a.nb + jb) * 9;
+	// the coefficient this lane looks after: the lane16-th fitted one; its row; the number of fitted coefficients
+	int myq = -1, n_fitted = 0;
 #pragma unroll
-	for (int q = 0; q < 9; ++q) {
-		x0[q] = add(mul(ka[q], sub(1.0, ratio)), mul(kb[q], ratio));  // combineAps, sim.cpp:705-709
-		move[q] = fitted(q) ? a.d[q] : 0.0;
-		grad[q] = 0.0;
+	for (int q = 0; q < 9; ++q) if (fitted(q)) { if (n_fitted == lane16) myq = q; ++n_fitted; }
+	const int my_row = min(lane16, max(n_fitted - 1, 0));
+	const double my_h = myq >= 0 ? mul(a.d[myq], .001) : 1.0;
+	if (lane16 < 9) {
+		const double* ka = a.border_k + (size_t)(b * a.nb + ja) * 9;
+		const double* kb = a.border_k + (size_t)(b * a.nb + jb) * 9;
+		const double v = add(mul(ka[lane16], sub(1.0, ratio)), mul(kb[lane16], ratio));  // combineAps, sim.cpp:705-709
+		S.x0[lane16] = v;
+		S.kt[lane16] = v;
+		S.move[lane16] = fitted(lane16) ? a.d[lane16] : 0.0;
+		S.grad[lane16] = 0.0;
 	}
+	__syncwarp(mask);
 	const double h6 = mul(a.d[6], .001), h7 = mul(a.d[7], .001);
 	const bool tails = fitted(6) || fitted(7);
 	// lanes 0, 1, 2 of the half-warp: ln(2^(k7/k6) - 1) at (k6, k7), (k6 + h6, k7), (k6, k7 + h7)
@@ -214,75 +230,94 @@ __global__ void __launch_bounds__(16 * kFitsPerCta, 5) fit_descent_kernel(FitArg
 		c6 = tails ? __shfl_sync(mask, t, 1, 16) : c;
 		c7 = tails ? __shfl_sync(mask, t, 2, 16) : c;
 	};
-	auto miss = [&](const double (&k)[9], const Factors& f) {
-		return ordered_sum(sqr(sub(f_value(k[0], k[2], k[3], f.A, f.E4, f.E5, f.Q), py)), row, lane16, mask);
-	};
-	Factors cache;
+	// per-point factors of the AP at the iterate (Wohlfart.h:195-203)
 	double c0, c6, c7;
-	tail3(x0[6], x0[7], c0, c6, c7);
-	cache.A = f_A(x0[1], px);
-	cache.E4 = f_exp(x0[4], px);
-	cache.E5 = f_exp(x0[5], px);
-	cache.Q = f_Q(x0[6], x0[7], x0[8], c0, px);
-	double y0 = miss(x0, cache);
+	tail3(S.x0[6], S.x0[7], c0, c6, c7);
+	double A = f_A(S.x0[1], px);
+	double E4 = f_exp(S.x0[4], px);
+	double E5 = f_exp(S.x0[5], px);
+	double Q = f_Q(S.x0[6], S.x0[7], S.x0[8], c0, px);
+	S.rows[0][lane16] = sqr(sub(f_value(S.x0[0], S.x0[2], S.x0[3], A, E4, E5, Q), py));
+	__syncwarp(mask);
+	double y0 = row_sum(S.rows[0]);
+	__syncwarp(mask);
 	double step = a.step;
 	bool reuse = false;   // the last trial point was rejected: iterate and difference quotients are unchanged
 	for (int it = a.iterations; it > 0 && y0 > a.eps; --it) {
-		bool step_change = false;
+		double g = 0.0;   // this lane's coefficient: (f(x0 + h e_q) - f(x0)) / h
+		if (!reuse) {
+			const double k0 = S.x0[0], k2 = S.x0[2], k3 = S.x0[3], k6 = S.x0[6], k7 = S.x0[7], k8 = S.x0[8];
+			double Qp[3] = {Q, Q, Q};
+			if (fitted(6) || fitted(7) || fitted(8)) {
+				const double k6v[3] = {add(k6, h6), k6, k6}, k7v[3] = {k7, add(k7, h7), k7};
+				const double k8v[3] = {k8, k8, add(k8, mul(a.d[8], .001))}, cv[3] = {c6, c7, c0};
+				double arg[3], e[3], base[3], ex[3];
 #pragma unroll
-		for (int q = 0; q < 9; ++q) {
-			if (fitted(q)) {
-				double g = grad[q];
-				if (!reuse) {
-					double kq[9];
+				for (int i = 0; i < 3; ++i) arg[i] = add(mul(-k7v[i], sub(px, k8v[i])), cv[i]);
+				ekg_fm::exp_n<3>(arg, e);
 #pragma unroll
-					for (int r = 0; r < 9; ++r) kq[r] = x0[r];
-					const double h = mul(a.d[q], .001);
-					kq[q] = add(kq[q], h);
-					Factors f = cache;
-					if (q == 1) f.A = f_A(kq[1], px);
-					if (q == 4) f.E4 = f_exp(kq[4], px);
-					if (q == 5) f.E5 = f_exp(kq[5], px);
-					if (q == 6 || q == 7 || q == 8) f.Q = f_Q(kq[6], kq[7], kq[8], q == 6 ? c6 : q == 7 ? c7 : c0, px);
-					g = dvd(sub(miss(kq, f), y0), h);
-				}
-				if (mul(g, grad[q]) < 0) { move[q] = mul(move[q], 0.5); step_change = true; }
-				else if (fabs(g) > mul(0.75, fabs(grad[q]))) move[q] = mul(move[q], 1.5);
-				grad[q] = g;   // oldGrad = grad, nonlinearFit.h:144 (only its own component is ever read)
+				for (int i = 0; i < 3; ++i) { base[i] = add(1.0, e[i]); ex[i] = -dvd(k6v[i], k7v[i]); }
+				ekg_fm::pow_n<3>(base, ex, Qp);
 			}
-		}
-		double kt[9];
+			const double Ap = fitted(1) ? f_A(add(S.x0[1], mul(a.d[1], .001)), px) : A;
+			const double E4p = fitted(4) ? f_exp(add(S.x0[4], mul(a.d[4], .001)), px) : E4;
+			const double E5p = fitted(5) ? f_exp(add(S.x0[5], mul(a.d[5], .001)), px) : E5;
+			int row = 0;
 #pragma unroll
-		for (int q = 0; q < 9; ++q) {
-			// a coefficient that is not fitted has grad = 0 and move = d = 0: x - step * (-0) = x (nonlinearFit.h:148-150)
-			kt[q] = fitted(q) ? sub(x0[q], mul(step, (grad[q] > 0) ? move[q] : -move[q])) : x0[q];
+			for (int q = 0; q < 9; ++q) {
+				if (fitted(q)) {
+					const double h = mul(a.d[q], .001);
+					const double v = f_value(q == 0 ? add(k0, h) : k0, q == 2 ? add(k2, h) : k2, q == 3 ? add(k3, h) : k3, q == 1 ? Ap : A,
+					                         q == 4 ? E4p : E4, q == 5 ? E5p : E5, q == 6 ? Qp[0] : q == 7 ? Qp[1] : q == 8 ? Qp[2] : Q);
+					S.rows[row][lane16] = sqr(sub(v, py));
+					++row;
+				}
+			}
+			__syncwarp(mask);
+			g = dvd(sub(row_sum(S.rows[my_row]), y0), my_h);
+			__syncwarp(mask);   // the rows are free again
+		} else if (myq >= 0) g = S.grad[myq];
+		bool sc = false;
+		if (myq >= 0) {
+			double mv = S.move[myq];
+			const double gr = S.grad[myq];
+			if (mul(g, gr) < 0) { mv = mul(mv, 0.5); sc = true; }
+			else if (fabs(g) > mul(0.75, fabs(gr))) mv = mul(mv, 1.5);
+			S.move[myq] = mv;
+			S.grad[myq] = g;   // oldGrad = grad, nonlinearFit.h:144 (only its own component is ever read)
+			S.kt[myq] = sub(S.x0[myq], mul(step, (g > 0) ? mv : -mv));   // nonlinearFit.h:148-150
 		}
+		const bool step_change = __any_sync(mask, sc);
+		__syncwarp(mask);
 		double c1, c61, c71;
-		tail3(kt[6], kt[7], c1, c61, c71);
-		Factors trial = cache;
-		if (fitted(1)) trial.A = f_A(kt[1], px);
-		if (fitted(4)) trial.E4 = f_exp(kt[4], px);
-		if (fitted(5)) trial.E5 = f_exp(kt[5], px);
-		if (fitted(6) || fitted(7) || fitted(8)) trial.Q = f_Q(kt[6], kt[7], kt[8], c1, px);
-		const double y1 = miss(kt, trial);
+		tail3(S.kt[6], S.kt[7], c1, c61, c71);
+		const double At = fitted(1) ? f_A(S.kt[1], px) : A;
+		const double E4t = fitted(4) ? f_exp(S.kt[4], px) : E4;
+		double E5t = E5, Qt = Q;
+		if (fitted(5) || fitted(6) || fitted(7) || fitted(8)) {
+			// exp(-k5 t) and the exponential inside the repolarisation term together, then the power
+			const double arg[2] = {mul(-S.kt[5], px), add(mul(-S.kt[7], sub(px, S.kt[8])), c1)};
+			double e[2];
+			ekg_fm::exp_n<2>(arg, e);
+			E5t = e[0];
+			Qt = ekg_fm::pow_(add(1.0, e[1]), -dvd(S.kt[6], S.kt[7]));
+		}
+		S.rows[0][lane16] = sqr(sub(f_value(S.kt[0], S.kt[2], S.kt[3], At, E4t, E5t, Qt), py));
+		__syncwarp(mask);
+		const double y1 = row_sum(S.rows[0]);
 		if (y1 < y0) {
 			y0 = y1;
 			c0 = c1; c6 = c61; c7 = c71;
-#pragma unroll
-			for (int q = 0; q < 9; ++q) x0[q] = kt[q];
-			cache = trial;
+			A = At; E4 = E4t; E5 = E5t; Q = Qt;
+			if (myq >= 0) S.x0[myq] = S.kt[myq];
 			reuse = false;
 		} else {
 			if (!step_change) step = mul(step, 0.5);
 			reuse = true;
 		}
+		__syncwarp(mask);
 	}
-	if (lane16 < 9) {
-		double v = x0[0];
-#pragma unroll
-		for (int q = 1; q < 9; ++q) if (lane16 == q) v = x0[q];
-		a.layer_k[((size_t)b * a.nl + layer) * 9 + lane16] = v;
-	}
+	if (lane16 < 9) a.layer_k[((size_t)b * a.nl + layer) * 9 + lane16] = S.x0[lane16];
 }
 
 }  // namespace

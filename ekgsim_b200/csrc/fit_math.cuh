@@ -85,13 +85,27 @@ EKG_FM_INLINE double exp_core(double x, double xtail, bool with_tail) {
 	return fma_(scale, tmp, scale);
 }
 
-EKG_FM_INLINE double exp_(double x) {
+EKG_FM_INLINE bool exp_special(double x) {                // |x| < 2^-54 or |x| >= 512 (or not finite)
 	const uint32_t abstop = (uint32_t)(bits_(x) >> 52) & 0x7ffu;
-	if (abstop - 0x3c9u >= 0x3fu) {                        // |x| < 2^-54 or |x| >= 512 (or not finite)
-		if (abstop < 0x3c9u) return add_(1.0, x);
-		return exp(x);
-	}
+	return abstop - 0x3c9u >= 0x3fu;
+}
+EKG_FM_INLINE double exp_slow(double x) {
+	const uint32_t abstop = (uint32_t)(bits_(x) >> 52) & 0x7ffu;
+	if (abstop < 0x3c9u) return add_(1.0, x);
+	return exp(x);
+}
+EKG_FM_INLINE double exp_(double x) {
+	if (exp_special(x)) return exp_slow(x);
 	return exp_core(x, 0.0, false);
+}
+// N independent evaluations in one straight line of code: the main paths first (no branch between them, so that the
+// instruction scheduler interleaves the N dependency chains), the rare special operands patched afterwards
+template <int N>
+EKG_FM_INLINE void exp_n(const double (&x)[N], double (&out)[N]) {
+#pragma unroll
+	for (int i = 0; i < N; ++i) out[i] = exp_core(x[i], 0.0, false);
+#pragma unroll
+	for (int i = 0; i < N; ++i) if (exp_special(x[i])) out[i] = exp_slow(x[i]);
 }
 
 // ---- log (e_log.c: __log) -----------------------------------------------------------------------------------------------
@@ -145,11 +159,12 @@ EKG_FM_INLINE double log_(double x) {
 }
 
 // ---- pow (e_pow.c: __pow = log_inline in double-double, then exp_inline) ---------------------------------------------
-EKG_FM_INLINE double pow_(double x, double y) {
+// main path; `special` = the operands (or y log x) are outside it and the general function has to be used instead
+EKG_FM_INLINE double pow_core(double x, double y, bool& special) {
 	const uint64_t ix = bits_(x), iy = bits_(y);
 	const uint32_t topx = (uint32_t)(ix >> 52), topy = (uint32_t)(iy >> 52);
-	// x subnormal / zero / negative / inf / nan, or |y| outside [2^-65, 2^63): the general function
-	if (topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ffu) - 0x3beu >= 0x43eu - 0x3beu) return pow(x, y);
+	// x subnormal / zero / negative / inf / nan, or |y| outside [2^-65, 2^63)
+	special = topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ffu) - 0x3beu >= 0x43eu - 0x3beu;
 	// log_inline
 	const double* A = ekg_libm_powlog_c + 2;   // A[0..6]
 	const uint64_t tmp = ix - 0x3fe6955500000000ull;
@@ -186,11 +201,25 @@ EKG_FM_INLINE double pow_(double x, double y) {
 	const double elo = fma_(y, llo, fma_(lhi, y, -ehi));
 	// exp_inline (sign_bias = 0: x > 0)
 	const uint32_t abstop = (uint32_t)(bits_(ehi) >> 52) & 0x7ffu;
-	if (abstop - 0x3c9u >= 0x3fu) {
-		if (abstop < 0x3c9u) return add_(1.0, ehi);        // |y log x| < 2^-54
-		return pow(x, y);                                     // overflow / underflow range: the general function
-	}
-	return exp_core(ehi, elo, true);
+	const bool tiny = abstop < 0x3c9u;                         // |y log x| < 2^-54: 1 + y log x (e_pow.c, exp_inline)
+	special = special || (abstop - 0x3c9u >= 0x3fu && !tiny);  // overflow / underflow range: the general function
+	const double e = exp_core(ehi, elo, true);
+	return tiny ? add_(1.0, ehi) : e;
+}
+EKG_FM_INLINE double pow_slow(double x, double y) { return pow(x, y); }
+EKG_FM_INLINE double pow_(double x, double y) {
+	bool special;
+	const double r = pow_core(x, y, special);
+	if (special) return pow_slow(x, y);
+	return r;
+}
+template <int N>
+EKG_FM_INLINE void pow_n(const double (&x)[N], const double (&y)[N], double (&out)[N]) {
+	bool sp[N];
+#pragma unroll
+	for (int i = 0; i < N; ++i) out[i] = pow_core(x[i], y[i], sp[i]);
+#pragma unroll
+	for (int i = 0; i < N; ++i) if (sp[i]) out[i] = pow_slow(x[i], y[i]);
 }
 
 }  // namespace ekg_fm

@@ -46,5 +46,20 @@ int main(int argc, char** argv) {
 	fails += run("pow wide", n, [](double& x, double& y) { x = logu(1e-200, 1e200); y = uni(-3, 3); }, p1, p2);
 	fails += run("pow specials", 8, [](double& x, double& y) { static int c = 0; const double vx[8] = {1.0, 0.0, -2.0, 2.0, 1e-310, INFINITY, 3.0, 1.0000000000000002};
 	                                                      const double vy[8] = {5.0, 2.0, 3.0, 1e-70, 0.5, -1.0, 700.0, 1e15}; x = vx[c & 7]; y = vy[c & 7]; ++c; }, p1, p2);
+	// the N-wide entry points (what the fit kernel calls) against the scalar ones
+	{
+		long bad = 0;
+		for (long i = 0; i < n / 4; ++i) {
+			double x[3], y[3], o[3], e[3];
+			for (int j = 0; j < 3; ++j) { x[j] = 1.0 + std::exp(uni(-90, 90)); y[j] = -uni(0.01, 0.1) / uni(0.01, 0.1); e[j] = uni(-800, 100); }
+			if (i % 97 == 0) { x[1] = -1.0; e[2] = 1e-30; }
+			ekg_fm::pow_n<3>(x, y, o);
+			for (int j = 0; j < 3; ++j) bad += !same(o[j], std::pow(x[j], y[j]));
+			ekg_fm::exp_n<3>(e, o);
+			for (int j = 0; j < 3; ++j) bad += !same(o[j], std::exp(e[j]));
+		}
+		printf("%-28s %ld %ld\n", "pow_n<3> / exp_n<3>", n / 4 * 6, bad);
+		fails += bad != 0;
+	}
 	return fails;
 }

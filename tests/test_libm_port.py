@@ -26,7 +26,7 @@ def test_fit_math_matches_host_libm_bit_for_bit(tmp_path):
     print(r.stdout)
     assert r.returncode == 0, r.stdout
     lines = [ln.split() for ln in r.stdout.strip().split("\n")]
-    assert len(lines) == 12 and all(ln[-1] == "0" for ln in lines)
+    assert len(lines) == 13 and all(ln[-1] == "0" for ln in lines)
 
 
 def test_libm_tables_are_what_the_generator_extracts():
