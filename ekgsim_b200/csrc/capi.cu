@@ -919,28 +919,46 @@ static int simulate_host(ekg_model* m, const double* layer_k, const double* lead
 			decay = std::max(decay, std::max(std::fabs(src[i * 9 + 4] + src[i * 9 + 5]), std::fabs(src[i * 9 + 5])));
 		}
 		// with the device fit: k1 and k4 of an inner layer are blends of the border values (unless d9 asks the descent to
-		// move them), k5 moves by a few percent -- a factor 2 on the decay rate covers it, the limit is 10x away anyway
+		// move them), k5 is fitted and moves by a few percent -- a factor 2 on the decay rate is the working assumption, and
+		// the true rates of the fitted layers come back with the results and are checked below (hints.verify)
 		const bool known = !fit || (fit->d9[1] == 0 && fit->d9[4] == 0);
 		if (known && k1_min > 0 && std::isfinite(k1_min) && std::isfinite(decay)) { hints.k1_min = k1_min; hints.decay_max = fit ? 2.0 * decay : decay; }
+		hints.verify = fit != nullptr && hints.k1_min > 0;
 	}
-	rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, flags, m->d_io_ecg, m->stream, hints);
-	if (rc) return rc;
+	int mode_flags = flags;
 	std::vector<double> crit_host;
-	if (criteria_out) {
-		const int64_t ntg = n_leads * n_target;
-		if ((rc = ensure(&m->d_io_tgt, &m->io_tgt_cap, ntg + n_leads + B * n_leads))) return rc;
-		double* d_off = m->d_io_tgt + ntg;
-		double* d_crit = d_off + n_leads;
-		EKG_CUDA(cudaMemcpyAsync(m->d_io_tgt, targets, (size_t)ntg * 8, cudaMemcpyHostToDevice, m->stream));
-		if (target_offsets) EKG_CUDA(cudaMemcpyAsync(d_off, target_offsets, (size_t)n_leads * 8, cudaMemcpyHostToDevice, m->stream));
-		EKG_CUDA(cudaStreamSynchronize(m->stream));  // pageable sources
-		if ((rc = run_criteria(m, m->d_io_ecg, m->d_io_tgt, target_offsets ? d_off : nullptr, d_crit, B, n_leads, T, n_target, comparison, m->stream))) return rc;
-		crit_host.resize((size_t)(B * n_leads));
-		EKG_CUDA(cudaMemcpyAsync(crit_host.data(), d_crit, crit_host.size() * 8, cudaMemcpyDeviceToHost, m->stream));
+	for (int pass = 0; pass < 2; ++pass) {
+		rc = run_ecg(m, m->d_io_k, m->d_io_leads, B, n_leads, nbhd, t_start, t_step, total_time, mode_flags, m->d_io_ecg, m->stream, hints);
+		if (rc) return rc;
+		int rate_bits[2] = {0, 0};
+		if (hints.verify) EKG_CUDA(cudaMemcpyAsync(rate_bits, m->d_k1min, sizeof rate_bits, cudaMemcpyDeviceToHost, m->stream));
+		if (criteria_out) {
+			const int64_t ntg = n_leads * n_target;
+			if ((rc = ensure(&m->d_io_tgt, &m->io_tgt_cap, ntg + n_leads + B * n_leads))) return rc;
+			double* d_off = m->d_io_tgt + ntg;
+			double* d_crit = d_off + n_leads;
+			EKG_CUDA(cudaMemcpyAsync(m->d_io_tgt, targets, (size_t)ntg * 8, cudaMemcpyHostToDevice, m->stream));
+			if (target_offsets) EKG_CUDA(cudaMemcpyAsync(d_off, target_offsets, (size_t)n_leads * 8, cudaMemcpyHostToDevice, m->stream));
+			// (pageable sources: cudaMemcpyAsync returns once they have been staged)
+			if ((rc = run_criteria(m, m->d_io_ecg, m->d_io_tgt, target_offsets ? d_off : nullptr, d_crit, B, n_leads, T, n_target, comparison, m->stream))) return rc;
+			crit_host.resize((size_t)(B * n_leads));
+			EKG_CUDA(cudaMemcpyAsync(crit_host.data(), d_crit, crit_host.size() * 8, cudaMemcpyDeviceToHost, m->stream));
+		}
+		if (ecg_out) EKG_CUDA(cudaMemcpyAsync(m->h_pin_out, m->d_io_ecg, (size_t)necg * 8, cudaMemcpyDeviceToHost, m->stream));
+		if (fit && fit->layer_k_out) EKG_CUDA(cudaMemcpyAsync(fit->layer_k_out, m->d_io_k, (size_t)nk_out * 8, cudaMemcpyDeviceToHost, m->stream));
+		EKG_CUDA(cudaStreamSynchronize(m->stream));
+		if (!hints.verify) break;
+		// the fitted layers' true rates: were the estimates the mode decision was taken on good enough?
+		float rate[2];
+		memcpy(rate, rate_bits, 8);
+		const bool k1_ok = (double)rate[0] >= hints.k1_min * (1.0 - 1e-6);
+		const bool decay_ok = (flags & 0xff) == EKG_MODE_DIRECT || decay_within_clamp(m, (double)rate[1], t_start) ||
+		                      !decay_within_clamp(m, hints.decay_max, t_start);   // (already sent through DIRECT)
+		if (k1_ok && decay_ok) break;
+		hints.k1_min = (double)rate[0];
+		hints.decay_max = (double)rate[1];
+		hints.verify = false;   // second pass with the measured rates
 	}
-	if (ecg_out) EKG_CUDA(cudaMemcpyAsync(m->h_pin_out, m->d_io_ecg, (size_t)necg * 8, cudaMemcpyDeviceToHost, m->stream));
-	if (fit && fit->layer_k_out) EKG_CUDA(cudaMemcpyAsync(fit->layer_k_out, m->d_io_k, (size_t)nk_out * 8, cudaMemcpyDeviceToHost, m->stream));
-	EKG_CUDA(cudaStreamSynchronize(m->stream));
 	m->last_launches += fit_launches;
 	if (ecg_out) memcpy(ecg_out, m->h_pin_out, (size_t)necg * 8);
 	if (criteria_out) memcpy(criteria_out, crit_host.data(), crit_host.size() * 8);

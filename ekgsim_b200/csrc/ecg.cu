@@ -703,15 +703,19 @@ __global__ void __launch_bounds__(256, NP == 1 ? 3 : 2) ecg_moment_fused_kernel(
 // ecg_ftab_kernel, kept in f64; ln(2^(k7/k6)-1) per (vector, layer) comes from ecg_params_kernel.
 constexpr int kCombSamples = 32, kCombLanes = 8;
 
-// per-(vector, layer) moments: the segments of a layer added in segment order, once (not once per combine CTA)
-__global__ void __launch_bounds__(128) ecg_layer_moments_kernel(const double* __restrict__ mom, const int32_t* __restrict__ seg_first,
+// per-(vector, layer) moments, once (not once per combine CTA): a warp per (layer, lead, moment); lane i adds the segments
+// i, i + 32, ... of the layer in that order, then the 32 lane sums are combined by a fixed butterfly -- the loads are
+// independent (a serial sum over ~30 segments is ~30 dependent L2 round trips) and the order is fixed -> deterministic
+__global__ void __launch_bounds__(256) ecg_layer_moments_kernel(const double* __restrict__ mom, const int32_t* __restrict__ seg_first,
                                                                 double* __restrict__ lmom, int B, int L, int n_layers) {
-	const int b = blockIdx.x;
-	for (int o = threadIdx.x; o < n_layers * L * 3; o += blockDim.x) {
+	const int b = blockIdx.x, lane = threadIdx.x & 31;
+	for (int o = threadIdx.x >> 5; o < n_layers * L * 3; o += blockDim.x >> 5) {
 		const int layer = o / (L * 3), r = o - layer * (L * 3);
 		double s = 0.0;
-		for (int sgi = seg_first[layer]; sgi < seg_first[layer + 1]; ++sgi) s += mom[((int64_t)sgi * B + b) * L * 3 + r];
-		lmom[(int64_t)b * n_layers * L * 3 + o] = s;
+		for (int sgi = seg_first[layer] + lane; sgi < seg_first[layer + 1]; sgi += 32) s += mom[((int64_t)sgi * B + b) * L * 3 + r];
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+		if (lane == 0) lmom[(int64_t)b * n_layers * L * 3 + o] = s;
 	}
 }
 
@@ -1068,6 +1072,13 @@ int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_
 	return EKG_OK;
 }
 
+// exp(-k (t - at)) = exp(-k (t - t0)) exp(k (at - t0)), both factors clamped at 2^60: fine as long as the largest decay rate
+// times the largest distance from t0 (of an activation time, or of the first sample) stays below 55 octaves
+bool decay_within_clamp(const ekg_model* m, double decay_max, double t_start) {
+	const double span = std::max(std::max(m->at_max - m->t0, m->t0 - m->at_min), std::max(m->t0 - t_start, 0.0));
+	return decay_max * span * 1.4426950408889634074 <= 55.0;
+}
+
 static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
                        double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, KHints hints) {
 	if (!m->have_activation) return fail(EKG_E_STATE, "no excitation sequence: call ekg_model_activation or ekg_model_set_activation first");
@@ -1107,7 +1118,8 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	const int64_t n_bl = B * m->n_layers;
 	if ((rc = ensure(&m->d_params, &m->params_cap, n_bl * kParamStride))) return rc;
 	if ((rc = ensure(&m->d_tail, &m->tail_cap, n_bl))) return rc;
-	const bool want_k1 = mode == EKG_MODE_SEPARABLE && !(hints.k1_min > 0);
+	const bool read_k1 = mode == EKG_MODE_SEPARABLE && !(hints.k1_min > 0);
+	const bool want_k1 = read_k1 || hints.verify;
 	if (want_k1) {
 		if (!m->d_k1min) EKG_CUDA(cudaMalloc(&m->d_k1min, 2 * sizeof(int)));
 		EKG_CUDA(cudaMemsetAsync(m->d_k1min, 0x7f, sizeof(int), st));  // 0x7f7f7f7f = 3.4e38f
@@ -1116,7 +1128,7 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	ecg_params_kernel<<<(int)((n_bl + 127) / 128), 128, 0, st>>>(d_layer_k, m->d_params, m->d_tail, n_bl, (float)m->t0, want_k1 ? m->d_k1min : nullptr);
 	EKG_CUDA(cudaGetLastError());
 	++m->last_launches;
-	if (want_k1) {
+	if (read_k1) {
 		int bits[2] = {0, 0};
 		EKG_CUDA(cudaMemcpyAsync(bits, m->d_k1min, sizeof bits, cudaMemcpyDeviceToHost, st));
 		EKG_CUDA(cudaStreamSynchronize(st));
@@ -1127,10 +1139,7 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 	// The HOISTED and SEPARABLE kernels factor exp(-k (t - at)) = exp(-k (t - t0)) exp(k (at - t0)) and clamp both exponents
 	// at 2^60; a batch whose decay rates or whose distance from t0 would reach the clamp runs through DIRECT instead (known
 	// rates only: an explicit HOISTED request with raw device pointers stays asynchronous and unchecked)
-	if (mode != EKG_MODE_DIRECT && hints.k1_min > 0) {
-		const double span = std::max(std::max(m->at_max - m->t0, m->t0 - m->at_min), std::max(m->t0 - t_start, 0.0));
-		if (!(hints.decay_max * span * 1.4426950408889634074 <= 55.0)) mode = EKG_MODE_DIRECT;
-	}
+	if (mode != EKG_MODE_DIRECT && hints.k1_min > 0 && !decay_within_clamp(m, hints.decay_max, t_start)) mode = EKG_MODE_DIRECT;
 
 	// SEPARABLE: the time-loop kernel handles the first T_loop samples (those before every voxel's
 	// depolarisation sigmoid is exactly 1 in fp32: exp(-k1 (t - at)) < 2^-25, the HOISTED kernel's own
@@ -1315,7 +1324,7 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		const size_t smem = (size_t)(m->n_layers * L * 3 + kCombLanes * 4 * (kCombSamples + 1)) * sizeof(double);
 		const dim3 cgrid((unsigned)((n_late + kCombSamples - 1) / kCombSamples), (unsigned)B, 1);
 		if ((rc = ensure(&m->d_lmom, &m->lmom_cap, B * m->n_layers * L * 3))) return rc;
-		ecg_layer_moments_kernel<<<(unsigned)B, 128, 0, st>>>(m->d_mom, m->d_mseg_first, m->d_lmom, (int)B, (int)L, m->n_layers);
+		ecg_layer_moments_kernel<<<(unsigned)B, 256, 0, st>>>(m->d_mom, m->d_mseg_first, m->d_lmom, (int)B, (int)L, m->n_layers);
 		EKG_CUDA(cudaGetLastError());
 		++m->last_launches;
 		ecg_combine_kernel<<<cgrid, kCombSamples * kCombLanes, smem, st>>>(d_layer_k, m->d_tail, d_t64, m->d_lmom, m->d_mseg_first, d_ecg, (int)B, (int)L,

@@ -238,7 +238,10 @@ int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_pl
 //   k1_min     smallest depolarisation rate k1 over all (vector, layer): where the sigmoid saturates
 //   decay_max  largest of |k4 + k5|, |k5|: whether the hoisted exponentials exp(+-k (at - t0)), exp(-k (t - t0)) stay
 //              inside the 2^60 clamp of the HOISTED / SEPARABLE kernels (otherwise the run goes through DIRECT)
-struct KHints { double k1_min = 0.0, decay_max = 0.0; };
+//   verify     the hints are an estimate (device-side layer fit: k5 is a fitted coefficient): ecg_params_kernel also reduces the
+//              true values into ekg_model::d_k1min, which the caller reads back with its results and checks (decay_within_clamp)
+struct KHints { double k1_min = 0.0, decay_max = 0.0; bool verify = false; };
+bool decay_within_clamp(const ekg_model* m, double decay_max, double t_start);
 int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
             double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, KHints hints = KHints());
 int run_criteria(ekg_model* m, const double* d_ecg, const double* d_targets, const double* d_offsets, double* d_crit,

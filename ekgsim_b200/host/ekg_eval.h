@@ -471,6 +471,9 @@ public:
 		if (settings.interpolationTypeString == "endo-epi") interp = endo_epi;
 		else if (settings.interpolationTypeString == "endo-mid-epi") interp = endo_mid_epi;
 		else throw std::runtime_error("unknown interpolation type [" + settings.interpolationTypeString + "]");
+		// a mid AP position that rounds onto the first or the last layer: the later border AP overwrites the earlier one and
+		// the fit proceeds (sim.cpp:833-902); the device fit does not implement that corner, the host restatement does
+		if (fitOnDevice && interp == endo_mid_epi && sim->requiredAps() > 2 && (midLayer() == 0 || midLayer() == sim->requiredAps() - 1)) fitOnDevice = false;
 		for (int k : settings.freeKs) freeK.insert((char)k);
 		numWohlfartParams = freeK.size() * (interp == endo_epi ? 2 : 3);
 		std::cerr << " ok\n";

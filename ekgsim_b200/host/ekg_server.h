@@ -23,6 +23,7 @@
 #include <cstring>
 #include <poll.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <sys/un.h>
 #include <unistd.h>
 
@@ -67,11 +68,13 @@ inline bool remote_eval(const std::string& path, const std::vector<double>& gene
 	ok = ok && io_all(fd, &status, 4, false) && io_all(fd, &n, 4, false);
 	if (!ok) { ::close(fd); throw std::runtime_error("evaluation server at " + path + " closed the connection"); }
 	if (status != 0) {
+		if (n > (1u << 20)) n = 1u << 20;
 		std::string msg(n, ' ');
 		io_all(fd, &msg[0], n, false);
 		::close(fd);
 		throw std::runtime_error(msg);
 	}
+	if (n > (1u << 20)) { ::close(fd); throw std::runtime_error("evaluation server at " + path + " sent an implausible reply"); }
 	criteria.assign(n, 0.0);
 	ok = io_all(fd, &violation, 8, false) && io_all(fd, criteria.data(), (size_t)n * 8, false);
 	::close(fd);
@@ -123,6 +126,12 @@ inline void serve(Evaluator& ev, const std::string& path, int max_batch = 4096) 
 				if (::poll(&one, 1, 0) <= 0) break;
 				const int fd = ::accept(lfd, nullptr, nullptr);
 				if (fd < 0) break;
+				// a client that stalls in the middle of a request or does not read its reply must not hold up the others:
+				// blocking reads and writes on this connection give up after 2 s and the connection is dropped
+				timeval tv;
+				tv.tv_sec = 2; tv.tv_usec = 0;
+				::setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+				::setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof tv);
 				idle.push_back(fd);
 			}
 		}

@@ -295,6 +295,17 @@ def test_evaluation_server_batches_concurrent_extern_clients(testrun, golden):
         assert "runtime error caught: chromosome size does not agree" in r.stdout
         r = subprocess.run([hostlib.CLI, "-extern", "process2"], cwd=testrun, env=env, capture_output=True, text=True, timeout=60)
         assert "All done" in r.stdout and "error" not in r.stdout
+        # a client that stalls in the middle of its request (a crashed or paused worker) is dropped after the server's
+        # 2 s socket timeout instead of blocking everybody else; several devices behind one server ("0,0": two replicas)
+        import socket
+        import struct
+        stalled = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        stalled.connect(sock)
+        stalled.sendall(struct.pack("<I", 0x31474B45))          # half a header, then silence
+        t1 = time.time()
+        r = subprocess.run([hostlib.CLI, "-extern", "process3"], cwd=testrun, env=env, capture_output=True, text=True, timeout=60)
+        assert "All done" in r.stdout and "error" not in r.stdout and time.time() - t1 < 15
+        stalled.close()
     finally:
         subprocess.run([hostlib.CLI, "-shutdown", sock], cwd=testrun, capture_output=True, timeout=30)
         try:

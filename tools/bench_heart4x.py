@@ -28,16 +28,6 @@ import ekgsim_b200 as ek  # noqa: E402
 from ekgsim_b200 import dist as ekdist  # noqa: E402
 
 
-def heart4x(f=4):
-    m = ekgio.load_model24()
-    base = m["layers"]
-    start = np.argwhere(base & ek.START_FLAG)[0]
-    plain = (base & 0x0FFF).astype(np.uint16)
-    big = np.repeat(np.repeat(np.repeat(plain, f, axis=0), f, axis=1), f, axis=2)
-    big[tuple(start * f)] |= ek.START_FLAG   # first replica of the original start voxel in raster order
-    return big, m["transfer"], m["leads_zyx"] * f
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=3)
@@ -46,11 +36,12 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--sharded-automaton", action="store_true",
                     help="also run the automaton sharded over the z-slabs (plane exchange over NCCL) and compare with the replicated run")
+    ap.add_argument("--visits-per-round", type=int, default=-1, help="bound of the sharded automaton's relaxation per round (-1: the driver's default, 0: none)")
     a = ap.parse_args()
     rank, world, local = ekdist.init()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(local)
-    layers, transfer, leads = heart4x(a.factor)
+    layers, transfer, leads = ekgio.scaled_heart(a.factor)
     n_occ = int(((layers & 0x0FFF) > 0).sum())
     t0 = time.time()
     model = ek.Model(layers, transfer, device=local)
@@ -75,7 +66,8 @@ def main():
                 torch.distributed.barrier()
             t0 = time.perf_counter()
             tm = {}
-            _, rounds, visits = ekdist.sharded_activation(planes, slabs, rank, world, timings=tm, download=False)
+            _, rounds, visits = ekdist.sharded_activation(planes, slabs, rank, world, timings=tm, download=False,
+                                                          visits_per_round=None if a.visits_per_round < 0 else a.visits_per_round)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         d2 = model.get_activation()
@@ -83,6 +75,7 @@ def main():
         sharded = {"ms_total_incl_final_gather": ekdist.max_over_ranks(dt * 1e3, dev),
                    "ms_rounds": ekdist.max_over_ranks(tm["rounds_s"] * 1e3, dev), "ms_gather": ekdist.max_over_ranks(tm["gather_s"] * 1e3, dev),
                    "ms_publish_on_device": ekdist.max_over_ranks(tm["publish_s"] * 1e3, dev), "rounds": rounds, "brick_visits_rank0": visits,
+                   "visits_per_round": a.visits_per_round,
                    "bit_identical_to_replicated_run": same}
         assert same, "sharded automaton differs from the replicated run"
     g = np.load(os.path.join(ROOT, "tests", "golden", "golden_glue256.npz"))
