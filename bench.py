@@ -457,6 +457,16 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # While rank 0 alone drives ALL GPUs of the box (the C++ multi-device evaluator, the generation block) the other ranks
+    # must not wait inside an NCCL barrier: that is a kernel spinning on their GPU, and kernels of two processes on one
+    # GPU are time-sliced, not run side by side.  They wait on the CPU (gloo) instead.
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def idle_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -693,7 +703,7 @@ def run_b200_arm(args):
                 fit_ms["B%d" % fb] = f0.elapsed_time(f1) / 5
             pipeline["fit_ms"] = fit_ms
             pipeline["fit_bit_identical_to_reference_glue"] = bool(d_lk.cpu().numpy().tobytes() == np.ascontiguousarray(g["layer_k"]).tobytes())
-            barrier()
+            idle_barrier()
             if rank == 0:
                 # strong scaling of ONE 256-vector batch over the N GPUs of the box, inside one process (C++ host threads)
                 evN = hostlib.Evaluator(wd, devices=str(world))
@@ -709,7 +719,7 @@ def run_b200_arm(args):
                                           "devices": evN.n_devices, "vectors_per_gpu": 256 // max(world, 1), "seconds": best, "sims_per_s": 256 / best,
                                           "criteria_max_abs_diff_vs_reference_pinned_oracle": float(np.abs(critN - want["criteria"]).max())}
                 evN.close()
-            barrier()
+            idle_barrier()
         except Exception as e:
             pipeline = {"error": str(e)}
 
@@ -724,12 +734,13 @@ def run_b200_arm(args):
 
     # -- BASELINE configs[4]: one AMS-DEMO generation (population 100) through the evaluation boundary, all N GPUs (rank 0)
     generation = None
+    idle_barrier()
     if rank == 0 and not args.no_pipeline:
         try:
             generation = generation_block(world)
         except Exception as e:
             generation = {"error": repr(e)}
-    barrier()
+    idle_barrier()
 
     # -- parity spot check inside the bench (first vectors against the reference-pinned goldens)
     gf = np.load(os.path.join(ROOT, "tests", "golden", "golden_eval_full.npz"))

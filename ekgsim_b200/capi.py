@@ -45,6 +45,7 @@ SYMBOLS = {
     "ekg_model_plane_elems": (_i64, [_p]),
     "ekg_model_activation_export": (_int, [_p, _i64, _i64, _p, _p]),
     "ekg_model_activation_merge": (_int, [_p, _i64, _i64, _p, C.POINTER(_i64), _p]),
+    "ekg_model_activation_merge_async": (_int, [_p, _i64, _i64, _p, _p, _p]),
     "ekg_model_activation_end": (_int, [_p, _p]),
     "ekg_model_ap_classes": (_int, [_p, _p, C.POINTER(_i64)]),
     "ekg_simulate": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p]),
@@ -179,6 +180,10 @@ class Model:
         n = C.c_int64(0)
         _check(lib().ekg_model_activation_merge(self._h, int(z_begin), int(z_end), C.c_void_p(d_planes), C.byref(n), C.c_void_p(stream)))
         return int(n.value)
+
+    def activation_merge_async(self, z_begin, z_end, d_planes, d_counter, stream=0):
+        """like activation_merge, but the number of improved cells is added to the u64 device counter at `d_counter`"""
+        _check(lib().ekg_model_activation_merge_async(self._h, int(z_begin), int(z_end), C.c_void_p(d_planes), C.c_void_p(d_counter), C.c_void_p(stream)))
 
     def activation_end(self, download=True):
         out = np.empty(self.shape, dtype=np.float64) if download else None

@@ -504,6 +504,7 @@ int shard_relax(ekg_model* m, int64_t max_visits, int64_t* visits_out, int64_t* 
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
 	if (leftover_out) *leftover_out = 0;
+	if (m->merge_pending) { EKG_CUDA(cudaStreamSynchronize(m->merge_stream)); m->merge_pending = false; }   // asynchronous merges have landed
 	if (n == 0) { if (visits_out) *visits_out = 0; return EKG_OK; }
 	const int64_t cap = ring_capacity(n);
 	int* flag = m->d_brick_state;
@@ -535,27 +536,32 @@ int shard_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes,
 	int64_t first, n;
 	int rc = plane_range(m, z_begin, z_end, &first, &n);
 	if (rc) return rc;
-	if (n) {
-		EKG_CUDA(cudaMemcpyAsync(d_planes, m->d_time_pad + first, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-		EKG_CUDA(cudaStreamSynchronize(st));   // the caller hands the buffer to a collective on a stream of its own
-	}
+	// asynchronous on the caller's stream (the relaxation that produced the values has completed: shard_relax synchronises
+	// the model's stream); a collective the caller enqueues after this on the same stream is ordered behind the copy
+	if (n) EKG_CUDA(cudaMemcpyAsync(d_planes, m->d_time_pad + first, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
 	return EKG_OK;
 }
 
-int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, cudaStream_t st) {
+// d_count != NULL: the number of improved cells is ADDED to that device counter and nothing is read back (asynchronous: the
+// driver all-reduces the counter anyway); else it is returned through improved_out (one stream synchronisation)
+int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, unsigned long long* d_count,
+                cudaStream_t st) {
 	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
 	int64_t first, n;
 	int rc = plane_range(m, z_begin, z_end, &first, &n);
 	if (rc) return rc;
 	unsigned long long h = 0;
 	if (n) {
-		EKG_CUDA(cudaMemsetAsync(m->d_improved, 0, sizeof(unsigned long long), st));
+		unsigned long long* counter = d_count ? d_count : m->d_improved;
+		if (!d_count) EKG_CUDA(cudaMemsetAsync(m->d_improved, 0, sizeof(unsigned long long), st));
 		shard_merge_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_time_pad, d_planes, n, first, (int)m->pY, (int)m->pX, (int)m->Z, (int)m->Y,
 		                                                         (int)m->X, m->d_brick_index, (int)m->bZ, (int)m->bY, (int)m->bX, m->d_brick_own,
-		                                                         m->d_brick_mark, m->d_improved);
+		                                                         m->d_brick_mark, counter);
 		EKG_CUDA(cudaGetLastError());
-		EKG_CUDA(cudaMemcpyAsync(&h, m->d_improved, sizeof h, cudaMemcpyDeviceToHost, st));
-		EKG_CUDA(cudaStreamSynchronize(st));
+		if (!d_count) {
+			EKG_CUDA(cudaMemcpyAsync(&h, m->d_improved, sizeof h, cudaMemcpyDeviceToHost, st));
+			EKG_CUDA(cudaStreamSynchronize(st));
+		}
 	}
 	if (improved_out) *improved_out = (int64_t)h;
 	return EKG_OK;

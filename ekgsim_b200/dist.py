@@ -109,6 +109,7 @@ class ModelPlanes:
         import torch
         self.model, self.device, self.torch = model, device, torch
         self.plane_elems = model.plane_elems
+        self.async_merge = True   # merges add into the driver's device counter
 
     def begin(self):
         self.model.activation_begin()
@@ -123,12 +124,17 @@ class ModelPlanes:
             self.model.activation_export(z_begin, z_end, t.data_ptr(), self.torch.cuda.current_stream(self.device).cuda_stream)
         return t
 
-    def merge(self, z_begin, planes):
+    def merge(self, z_begin, planes, counter=None):
+        """counter: an int64 device tensor the number of improved cells is added to (no read-back, no synchronisation);
+        None: the count is returned"""
         if planes.numel() == 0:
             return 0
-        self.torch.cuda.current_stream(self.device).synchronize()   # the collective that filled `planes` is done
-        return self.model.activation_merge(z_begin, z_begin + planes.shape[0], planes.data_ptr(),
-                                           self.torch.cuda.current_stream(self.device).cuda_stream)
+        stream = self.torch.cuda.current_stream(self.device)   # the collective that filled `planes` was ordered on it (req.wait())
+        if counter is not None:
+            self.model.activation_merge_async(z_begin, z_begin + planes.shape[0], planes.data_ptr(), counter.data_ptr(), stream.cuda_stream)
+            return 0
+        stream.synchronize()
+        return self.model.activation_merge(z_begin, z_begin + planes.shape[0], planes.data_ptr(), stream.cuda_stream)
 
     def end(self, download=True):
         return self.model.activation_end(download=download)
@@ -164,9 +170,12 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, t
     above = min([r for r in live if r > rank], default=None) if rank in live else None
     z0, z1 = slabs[rank]
     if visits_per_round is None:
-        # about one visit per 4^3 brick of a grid-sized slab: a fraction of what the slab needs in total (a brick is
-        # visited ~5 times), a millisecond or so of work -- several times the cost of the exchange that follows
-        visits_per_round = 0 if world == 1 else max(16384, (z1 - z0) * planes.plane_elems // 64)
+        # Two slabs: the wave starts next to the cut, both ranks are busy from the first round on -- unbounded rounds are
+        # best (measured on the 4x heart, 2 GPUs: 22 ms in 2-3 rounds; 25 ms / 5 rounds bounded to 400 k visits, 35 ms /
+        # 18 rounds bounded to 100 k: a round costs ~0.5 ms of launches, exchange and agreement).  More slabs: a bound
+        # of about a fifth of the slab's brick cells (live bricks are ~40 % of the cells and are visited ~5 times each, so
+        # ~10 rounds per slab) hands the wave on after one round instead of after the slab is finished.
+        visits_per_round = 0 if world <= 2 else max(16384, (z1 - z0) * planes.plane_elems // (64 * 5))
     t_begin = time.perf_counter()
     planes.begin()
     visits, rounds = 0, 0
@@ -190,11 +199,16 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, t
             if ops:
                 for req in dist.batch_isend_irecv(ops):
                     req.wait()
+            # improved cells of both merges + bricks still queued, summed over the ranks; on the GPU the merges add into the
+            # device counter (no read-back): the only host synchronisation of the exchange is the .item() below
+            flag = torch.full((1,), improved, dtype=torch.int64, device=send_device(planes))
+            dev_counter = flag if getattr(planes, "async_merge", False) else None
             if recv_below is not None:
-                improved += planes.merge(slabs[below][1] - 1, recv_below)   # = its last own plane
+                improved += planes.merge(slabs[below][1] - 1, recv_below, dev_counter) if dev_counter is not None else planes.merge(slabs[below][1] - 1, recv_below)   # = its last own plane
             if recv_above is not None:
-                improved += planes.merge(slabs[above][0], recv_above)
-            flag = torch.tensor([improved], dtype=torch.int64, device=send_device(planes))
+                improved += planes.merge(slabs[above][0], recv_above, dev_counter) if dev_counter is not None else planes.merge(slabs[above][0], recv_above)
+            if dev_counter is None:
+                flag.fill_(improved)
             dist.all_reduce(flag, op=dist.ReduceOp.SUM)
             improved = int(flag.item())
         if improved == 0:

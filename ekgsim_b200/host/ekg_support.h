@@ -218,17 +218,22 @@ inline void load_shape_matrix(const std::string& fname, std::vector<uint16_t>& l
 	if (i < n) throw std::runtime_error("reading file " + fname + " failed (while reading data)");
 }
 
-/// Optional binary side-car of a shape file (SURVEY 8(f) "input pipeline"): with EKGSIM_B200_CACHE=1 in the
-/// environment, `<file>.b200bin` (header + raw uint16 layers) is written after the first text parse and used
-/// afterwards as long as size and mtime of the text file are unchanged.  A 4x-resolution heart is ~200 MB of
-/// text (seconds to parse) but 183 MB of binary (a plain read).
+/// Binary side-cars of the two big text inputs (SURVEY 8(f) "input pipeline"): `<file>.b200bin` next to a shape file
+/// (u16 layers) or an excitation-sequence dump (f64 delays at FULL precision -- the text form keeps 3 decimals,
+/// simulator.cpp:92).  A side-car is USED whenever it exists and is fresh (size and mtime of the text file as recorded in
+/// its header); it is WRITTEN for shape files only with EKGSIM_B200_CACHE=1 (nothing appears in the user's directory
+/// unasked) and always together with an excitation-sequence dump (that file is an output of this program anyway).
+/// EKGSIM_B200_CACHE=0 switches both off.
+inline bool sidecar_enabled() { const char* e = getenv("EKGSIM_B200_CACHE"); return !(e && e[0] == '0'); }
+inline bool sidecar_write_enabled() { const char* e = getenv("EKGSIM_B200_CACHE"); return e && e[0] != '0'; }
+struct SidecarHeader { char magic[8]; int64_t z, y, x, src_size, src_mtime; };
+
 inline void load_shape_matrix_cached(const std::string& fname, std::vector<uint16_t>& layers, int64_t& Z, int64_t& Y, int64_t& X) {
-	const char* env = getenv("EKGSIM_B200_CACHE");
-	if (!env || env[0] == '0') { load_shape_matrix(fname, layers, Z, Y, X); return; }
+	if (!sidecar_enabled()) { load_shape_matrix(fname, layers, Z, Y, X); return; }
 	struct stat st;
 	const bool have_src = stat(fname.c_str(), &st) == 0;
 	const std::string cache = fname + ".b200bin";
-	struct Header { char magic[8]; int64_t z, y, x, src_size, src_mtime; } h;
+	SidecarHeader h;
 	if (have_src) {
 		std::ifstream in(cache.c_str(), std::ios::binary);
 		if (in.read(reinterpret_cast<char*>(&h), sizeof h) && !memcmp(h.magic, "EKGSHP1", 8) && h.src_size == (int64_t)st.st_size &&
@@ -238,7 +243,7 @@ inline void load_shape_matrix_cached(const std::string& fname, std::vector<uint1
 		}
 	}
 	load_shape_matrix(fname, layers, Z, Y, X);
-	if (have_src) {
+	if (have_src && sidecar_write_enabled()) {
 		memcpy(h.magic, "EKGSHP1", 8);
 		h.z = Z; h.y = Y; h.x = X; h.src_size = (int64_t)st.st_size; h.src_mtime = (int64_t)st.st_mtime;
 		std::ofstream out(cache.c_str(), std::ios::binary);
@@ -265,6 +270,16 @@ inline void load_double_matrix(const std::string& fname, std::vector<double>& m,
 /// excitation sequence stored as a .matrix of doubles of the model's size (simulator.cpp:288-367)
 inline void load_delay_matrix(const std::string& fname, int64_t Z, int64_t Y, int64_t X, std::vector<double>& delay) {
 	if (file_extension(fname) != ".matrix") throw std::runtime_error("can only import from .matrix for the time being");
+	struct stat st;
+	if (sidecar_enabled() && stat(fname.c_str(), &st) == 0) {   // full-precision side-car written with the dump
+		SidecarHeader h;
+		std::ifstream bin((fname + ".b200bin").c_str(), std::ios::binary);
+		if (bin.read(reinterpret_cast<char*>(&h), sizeof h) && !memcmp(h.magic, "EKGACT1", 8) && h.src_size == (int64_t)st.st_size &&
+		    h.src_mtime == (int64_t)st.st_mtime && h.z == Z && h.y == Y && h.x == X) {
+			delay.resize((size_t)(Z * Y * X));
+			if (bin.read(reinterpret_cast<char*>(delay.data()), (std::streamsize)(delay.size() * 8))) return;
+		}
+	}
 	std::ifstream in(fname.c_str());
 	if (!in.is_open()) throw std::runtime_error("could not open file " + fname + " to load excitation sequence");
 	const MatrixHeader h = read_matrix_header(in, fname, 3);
@@ -340,6 +355,16 @@ inline void export_delay_matrix(const std::string& fname, int64_t Z, int64_t Y, 
 			out << "\n";
 		}
 		out << "\n";
+	}
+	out.close();
+	struct stat st;
+	if (sidecar_enabled() && stat(fname.c_str(), &st) == 0) {   // the same map at full precision (see sidecar_enabled)
+		SidecarHeader h;
+		memcpy(h.magic, "EKGACT1", 8);
+		h.z = Z; h.y = Y; h.x = X; h.src_size = (int64_t)st.st_size; h.src_mtime = (int64_t)st.st_mtime;
+		std::ofstream bin((fname + ".b200bin").c_str(), std::ios::binary);
+		bin.write(reinterpret_cast<const char*>(&h), sizeof h);
+		bin.write(reinterpret_cast<const char*>(delay.data()), (std::streamsize)(delay.size() * 8));
 	}
 }
 

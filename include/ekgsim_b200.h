@@ -130,9 +130,13 @@ int  ekg_model_set_activation(ekg_model* m, const double* delay);
  *           before this slab is finished, so the ranks work side by side; the loop then ends when no merge improved
  *           anything AND no rank has bricks left.  Min-merging stale values is harmless: times only ever decrease
  *           towards the least fixed point, the bits are those of the unbounded run.
- *   export  copies planes [z_begin, z_end) into a device buffer (complete on return)
+ *   export  copies planes [z_begin, z_end) into a device buffer, asynchronously on `stream` (work enqueued on the same
+ *           stream afterwards -- the collective -- is ordered behind the copy)
  *   merge   time = min(time, planes); bricks of the slab that can see an improved cell are queued for the next
- *           relax; improved_out = number of improved cells
+ *           relax; improved_out = number of improved cells (one stream synchronisation)
+ *   merge_async   the same without reading anything back: the number of improved cells is ADDED to the caller's
+ *           device counter *d_improved_accum (which the driver all-reduces over the ranks anyway); the next relax /
+ *           end waits for the stream
  *   end     publishes the map like ekg_model_activation does (range of the times, ECG voxel list; host copy only if
  *           delay_out is not NULL) */
 int     ekg_model_activation_begin(ekg_model* m);
@@ -142,6 +146,8 @@ int64_t ekg_model_plane_elems(const ekg_model* m);
 int     ekg_model_activation_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, void* stream);
 int     ekg_model_activation_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes,
                                    int64_t* improved_out, void* stream);
+int     ekg_model_activation_merge_async(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes,
+                                         uint64_t* d_improved_accum, void* stream);
 int     ekg_model_activation_end(ekg_model* m, double* delay_out);
 int  ekg_model_get_activation(const ekg_model* m, double* delay_out);
 

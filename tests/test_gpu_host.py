@@ -171,8 +171,26 @@ def test_excitation_sequence_dump_and_reload(built, tmp_path, model24, model24_d
     assert "caught" not in r.stdout, r.stdout[-400:]
     assert "loading excitation sequence" in r.stderr and "calculating excitation sequence" not in r.stderr
     second = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in open(os.path.join(d, "result.column")).read().split("\n")[3:]]).T
-    # delays rounded to 1e-3 ms move the ECG a little, but only a little
-    assert 0 < np.abs(second - first).max() < 5e-2 * np.abs(first).max()
+    # the dump came with its full-precision side-car (es_out.matrix.b200bin: raw f64, the input-pipeline cache of SURVEY
+    # 8(f)), which is fresh -> the reloaded map is the computed one, bit for bit, and so is the ECG
+    side = os.path.join(d, "es_out.matrix.b200bin")
+    assert os.path.getsize(side) == 48 + 124 * 124 * 93 * 8
+    assert np.fromfile(side, dtype=np.float64, offset=48).tobytes() == model24_delay.tobytes()
+    assert np.abs(second - first).max() == 0.0
+    # without the side-car (EKGSIM_B200_CACHE=0, or a dump written by the reference): the 3-decimal text, like the
+    # reference's loadExcitationSequence -- delays rounded to 1e-3 ms move the ECG a little, but only a little
+    r = subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-out", "result"], cwd=d, capture_output=True, text=True,
+                       env=dict(os.environ, EKGSIM_B200_CACHE="0"))
+    assert "caught" not in r.stdout and "loading excitation sequence" in r.stderr
+    third = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in open(os.path.join(d, "result.column")).read().split("\n")[3:]]).T
+    assert 0 < np.abs(third - first).max() < 5e-2 * np.abs(first).max()
+    # a text file that changed after the side-car was written is trusted over it
+    os.utime(os.path.join(d, "es_out.matrix"), None)
+    st = os.stat(os.path.join(d, "es_out.matrix"))
+    os.utime(os.path.join(d, "es_out.matrix"), (st.st_atime, st.st_mtime + 7))
+    subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-out", "result"], cwd=d, capture_output=True, text=True)
+    fourth = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in open(os.path.join(d, "result.column")).read().split("\n")[3:]]).T
+    assert np.abs(fourth - third).max() == 0.0
 
 
 def test_cli_layer_and_cell_ap_outputs(testrun, golden, model24, model24_delay):

@@ -89,8 +89,8 @@ def test_char_matrix_and_2d_model(tmp_path, built):
 
 
 def test_binary_shape_cache(tmp_path, built, monkeypatch):
-    """EKGSIM_B200_CACHE=1: <shape>.b200bin is written on the first parse, used on the second, and
-    ignored when the text file changes."""
+    """EKGSIM_B200_CACHE=1: <shape>.b200bin is written on the first parse; a fresh side-car is used by default (also
+    without the variable), ignored when the text file changes or with EKGSIM_B200_CACHE=0."""
     d = str(tmp_path)
     ekgio.materialise_testrun(d)
     monkeypatch.setenv("EKGSIM_B200_CACHE", "1")
@@ -112,6 +112,12 @@ def test_binary_shape_cache(tmp_path, built, monkeypatch):
     k, _, _ = ev.layer_coefficients(g["params"][0])
     assert k.tobytes() == g["layer_k"][0].tobytes()
     ev.close()
+    # reading a fresh side-car needs no opt-in; nothing is written without it
+    monkeypatch.delenv("EKGSIM_B200_CACHE")
+    before = os.stat(cache).st_mtime_ns
+    hostlib.Evaluator(d, with_device=False).close()
+    assert os.stat(cache).st_mtime_ns == before
+    monkeypatch.setenv("EKGSIM_B200_CACHE", "1")
     # a newer text file invalidates it
     os.utime(os.path.join(d, "model_24.matrix"), (st.st_atime, st.st_mtime + 5))
     hostlib.Evaluator(d, with_device=False).close()
