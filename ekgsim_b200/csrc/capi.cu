@@ -69,7 +69,7 @@ static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_vox, m->d_segs, m->d_plan, m->d_tiles, m->d_params, m->d_tail, m->d_ftab, m->d_times, m->d_partial, m->d_partial2, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_lmom, m->d_near, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
+	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_tail, m->d_ftab, m->d_times, m->d_partial, m->d_partial2, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_lmom, m->d_near, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -194,7 +194,7 @@ static int build_ecg_list(ekg_model* m, int64_t z0, int64_t z1) {
 	}
 	m->n_ecg = n;
 	m->slab_z0 = z0; m->slab_z1 = z1;
-	m->n_segs = 0; m->seg_len = 0; m->plan_segs = -1;  // segment tables depend on the list
+	m->n_segs = 0; m->seg_len = 0;  // segment tables depend on the list
 	m->n_msegs = 0; m->mseg_len = 0;
 	return EKG_OK;
 }

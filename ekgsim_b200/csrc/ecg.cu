@@ -73,37 +73,22 @@ struct RowLayout {
 };
 
 // ---- the fused kernel ---------------------------------------------------------------------------
-// Pairs and tiles.  The (parameter vector b, time sample t) pairs of the whole batch are flattened, p = b*T + t, and cut
-// into tiles of kEcgThreads = 256 consecutive pairs (8 warps = 2 per SM sub-partition, every lane busy; a 400-sample
-// trace is 12.5 warps, which left one sub-partition with 33 % more MUFU work in the first version of this kernel).  A
-// tile therefore spans up to kMaxVecPerTile parameter vectors; phase A computes the lead-field coefficients for each.
+// Work decomposition: grid.x = segment (a run of voxels of ONE layer), grid.y = pair tile.  The
+// (parameter vector b, time sample t) pairs of the whole batch are flattened, p = b*T + t, and cut
+// into tiles of kEcgThreads = 256 consecutive pairs (8 warps = 2 per SM sub-partition, every lane
+// busy; a 400-sample trace is 12.5 warps, which left one sub-partition with 33 % more MUFU work
+// in the first version of this kernel).  A tile therefore spans up to kMaxVecPerTile parameter
+// vectors; phase A computes the lead-field coefficients for each of them.
 //
-// Voxel slices (small batches): when B*T is not a multiple of the tile size the last tile would be part empty (B = 1,
-// T = 400: tiles of 256 + 144 pairs, 22 % of the lanes idle).  The pair index is therefore generalised to (slice s,
-// vector b, sample t), p = (s*B + b)*T + t with S = 256/gcd(B*T, 256) slices, so that S*B*T is a whole number of tiles
-// (T = 400, B = 1: S = 16, 25 full tiles).  A "virtual vector" vv = s*B + b evaluates vector b on the s-th of S equal
-// sub-ranges of every segment; the threads of one tile belong to at most kMaxVecPerTile virtual vectors, each with its
-// own sub-range staged in shared memory (rows of one chunk position sit side by side, so the two halves of a warp that
-// straddles a slice boundary read two adjacent 16-byte rows: still one wavefront).
-//
-// Work decomposition: ONE WAVE of resident CTAs, each with an equal share of the work.  A unit of work is (tile,
-// segment, chunk of <= 256 voxels) -- phase A + phase B below -- and costs the same everywhere (one AP per thread and
-// voxel); the units are numbered tile-major and CTA k takes the units [U k / G, U (k + 1) / G), G = SMs x 4.  The per-lead
-// sums of a thread stay in registers for as long as the CTA stays on one tile (across chunks, segments and layers: the
-// layer's AP coefficients are reloaded when the segment changes) and are written once per (CTA, tile) "piece":
-// n_tiles + G pieces of 256 x NL doubles per launch (4 MB for the 256-vector batch; the first versions of this kernel
-// launched ~100 waves of (segment, tile) CTAs and wrote 200 MB of partial sums per launch) and no tail: every CTA
-// finishes at the same time.  ecg_piece_reduce_kernel adds the pieces of a pair in a fixed order -> bitwise
-// run-to-run determinism.
-__device__ __forceinline__ int upper_bound_i32(const int32_t* __restrict__ a, int n, int64_t v) {   // first index with a[i] > v
-	int lo = 0, hi = n;
-	while (lo < hi) {
-		const int mid = (lo + hi) >> 1;
-		if ((int64_t)__ldg(a + mid) <= v) lo = mid + 1; else hi = mid;
-	}
-	return lo;
-}
-
+// Voxel slices (small batches): when B*T is not a multiple of the tile size the last tile would be
+// part empty (B = 1, T = 400: tiles of 256 + 144 pairs, 22 % of the lanes idle).  The pair index is
+// therefore generalised to (slice s, vector b, sample t), p = (s*B + b)*T + t with S = 256/gcd(B*T, 256)
+// slices, so that S*B*T is a whole number of tiles (T = 400, B = 1: S = 16, 25 full tiles).  A "virtual
+// vector" vv = s*B + b evaluates vector b on the s-th of S equal sub-ranges of the CTA's segment; the
+// threads of one tile belong to at most kMaxVecPerTile virtual vectors, each with its own sub-range
+// staged in shared memory (rows of one chunk position sit side by side, so the two halves of a warp
+// that straddles a slice boundary read two adjacent 16-byte rows: still one wavefront).  Every thread
+// walks the same number (+-1) of voxels; the partial sums carry the slice in their segment index.
 template <int MODE, int NL>
 __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	constexpr int ROW = RowLayout<MODE, NL>::kFloats;
@@ -112,249 +97,211 @@ __global__ void __launch_bounds__(kEcgThreads, 4) ecg_kernel(const EcgArgs a) {
 	__shared__ int s_atmax[2];                          // HOISTED: latest activation time of the chunk (float bits)
 	__shared__ int s_sub[kMaxVecPerTile][2];            // voxel sub-range [begin, end) of every virtual vector of the tile
 
-	int64_t u = a.n_units * (int64_t)blockIdx.x / gridDim.x;
-	const int64_t u_end = a.n_units * (int64_t)(blockIdx.x + 1) / gridDim.x;
-	if (u >= u_end) return;
-	int tile_i = upper_bound_i32(a.tile_units, a.n_tiles + 1, u) - 1;
-	int piece = __ldg(a.piece_base + blockIdx.x);
+	const Segment sg = a.segs[blockIdx.x];
+	const PairTile tile = a.tiles[blockIdx.y];
+	const int vv0 = tile.begin / a.T;
+	const int nb = (tile.end - 1) / a.T - vv0 + 1;   // virtual vectors touched by this tile (<= kMaxVecPerTile)
+	const int p = tile.begin + threadIdx.x;
+	const bool live = p < tile.end;
+	const int vv = live ? p / a.T : vv0;
+	const int t = live ? p - vv * a.T : 0;
+	const int bl = vv - vv0;
+	const int sl = vv / a.B;                          // voxel slice of this thread
+	const int b = vv - sl * a.B;                      // parameter vector of this thread
+	const int chunk = min(kChunk, kSmemRows / nb);
+	const int seg_n = sg.end - sg.begin;
+	// sub-range of slice s: [begin + n s / S, begin + n (s + 1) / S)  (the whole segment for S = 1)
+	const int my_sub_b = sg.begin + (int)((int64_t)seg_n * sl / a.S);
+	const int my_sub_n = sg.begin + (int)((int64_t)seg_n * (sl + 1) / a.S) - my_sub_b;
+	int n_iter = 0;                                   // chunks of the longest sub-range of the tile
+	for (int v = 0; v < nb; ++v) {
+		const int s = (vv0 + v) / a.B;
+		const int sb = sg.begin + (int)((int64_t)seg_n * s / a.S), se = sg.begin + (int)((int64_t)seg_n * (s + 1) / a.S);
+		if (threadIdx.x == 0) { s_sub[v][0] = sb; s_sub[v][1] = se; }
+		n_iter = max(n_iter, (se - sb + chunk - 1) / chunk);
+	}
+
 	if (threadIdx.x < 2) s_atmax[threadIdx.x] = 0;
-	int parity = 0;
+	if (threadIdx.x < nb * NL * 3) {
+		const int v = threadIdx.x / (NL * 3), r = threadIdx.x % (NL * 3);
+		const int l = a.lead0 + r / 3;
+		const double c = l < a.L ? a.leads[((int64_t)((vv0 + v) % a.B) * a.L + l) * 3 + r % 3] : 0.0;
+		const float hi = (float)c;
+		s_lead[threadIdx.x] = make_float2(hi, (float)(c - (double)hi));
+	}
 
-	for (; u < u_end; ++tile_i, ++piece) {
-		// ---- this CTA's part of tile tile_i ----
-		const PairTile tile = a.tiles[tile_i];
-		const int vv0 = tile.begin / a.T;
-		const int nb = (tile.end - 1) / a.T - vv0 + 1;   // virtual vectors touched by this tile (<= kMaxVecPerTile)
-		const int p = tile.begin + threadIdx.x;
-		const bool live = p < tile.end;
-		const int vv = live ? p / a.T : vv0;
-		const int t = live ? p - vv * a.T : 0;
-		const int bl = vv - vv0;
-		const int sl = vv / a.B;                          // voxel slice of this thread
-		const int b = vv - sl * a.B;                      // parameter vector of this thread
-		const int chunk = min(kChunk, kSmemRows / nb);
-		const int32_t* seg_units = a.seg_units + (nb - 1) * (a.n_segs + 1);   // chunks of the segments before segment i, for this tile's chunk size
-		const int64_t tile_u0 = __ldg(a.tile_units + tile_i);
-		const int64_t tile_u_end = min(u_end, (int64_t)__ldg(a.tile_units + tile_i + 1));
-		int seg_i = upper_bound_i32(seg_units, a.n_segs + 1, u - tile_u0) - 1;
-		int it = (int)(u - tile_u0 - __ldg(seg_units + seg_i));
-		// (written after the barrier that follows the previous unit's phase A, read after the barrier in front of the next one)
-		if (threadIdx.x < nb * NL * 3) {
-			const int v = threadIdx.x / (NL * 3), r = threadIdx.x % (NL * 3);
-			const int l = a.lead0 + r / 3;
-			const double c = l < a.L ? a.leads[((int64_t)((vv0 + v) % a.B) * a.L + l) * 3 + r % 3] : 0.0;
-			const float hi = (float)c;
-			s_lead[threadIdx.x] = make_float2(hi, (float)(c - (double)hi));
-		}
-		const float thi = live ? __ldg(a.t_hi + t) : 0.f;
-		const float tlo = live ? __ldg(a.t_lo + t) : 0.f;
+	// per-thread constants of (vector b, layer, sample t)
+	const float* P = a.params + ((int64_t)b * a.n_layers + (sg.layer - 1)) * kParamStride;
+	const float a1 = __ldg(P + 0), k0 = __ldg(P + 8);
+	float a4 = 0.f, a5 = 0.f, a7 = 0.f, c2 = 0.f, np = 0.f, A = 0.f, Bc = 0.f, k8hi = 0.f, k8lo = 0.f, F1 = 0.f, F2 = 0.f;
+	if (MODE == MODE_DIRECT) {
+		a4 = __ldg(P + 1); a5 = __ldg(P + 2);
+		a7 = __ldg(P + 3); c2 = __ldg(P + 4); np = __ldg(P + 5); A = __ldg(P + 6); Bc = __ldg(P + 7);
+		k8hi = __ldg(P + 9); k8lo = __ldg(P + 10);
+	} else if (live) {
+		const float* F = a.ftab + (((int64_t)b * a.n_layers + (sg.layer - 1)) * 2) * a.T + t;
+		F1 = __ldg(F);
+		F2 = __ldg(F + a.T);
+	}
+	const float thi = live ? __ldg(a.t_hi + t) : 0.f;
+	const float tlo = live ? __ldg(a.t_lo + t) : 0.f;
 
-		// per-lead running sums: fp32 for 32 voxels at a time, folded into an fp32 (sum, compensation)
-		// pair with an error-free TwoSum -- f64-grade accumulation without conversions on the XU pipe
-		float sum[NL], comp[NL];
+	// per-lead running sums: fp32 for 32 voxels at a time, folded into an fp32 (sum, compensation)
+	// pair with an error-free TwoSum -- f64-grade accumulation without conversions on the XU pipe
+	float sum[NL], comp[NL];
 #pragma unroll
-		for (int l = 0; l < NL; ++l) { sum[l] = 0.f; comp[l] = 0.f; }
+	for (int l = 0; l < NL; ++l) { sum[l] = 0.f; comp[l] = 0.f; }
 
-		for (; u < tile_u_end; ++seg_i, it = 0) {
-			// ---- segment seg_i: a run of voxels of ONE layer ----
-			const Segment sg = a.segs[seg_i];
-			const int seg_n = sg.end - sg.begin;
-			const int n_iter = __ldg(seg_units + seg_i + 1) - __ldg(seg_units + seg_i);
-			// sub-range of slice s: [begin + n s / S, begin + n (s + 1) / S)  (the whole segment for S = 1)
-			const int my_sub_b = sg.begin + (int)((int64_t)seg_n * sl / a.S);
-			const int my_sub_n = sg.begin + (int)((int64_t)seg_n * (sl + 1) / a.S) - my_sub_b;
-			if (threadIdx.x < nb) {
-				const int s = (vv0 + threadIdx.x) / a.B;
-				s_sub[threadIdx.x][0] = sg.begin + (int)((int64_t)seg_n * s / a.S);
-				s_sub[threadIdx.x][1] = sg.begin + (int)((int64_t)seg_n * (s + 1) / a.S);
+	int parity = 0;
+	for (int it = 0; it < n_iter; ++it, parity ^= 1) {
+		const int n = max(0, min(chunk, my_sub_n - it * chunk));   // voxels of this thread's sub-range in this chunk
+		__syncthreads();  // phase B of the previous chunk is done with s_vox; s_lead and s_sub are visible
+
+		// ---- phase A: per-(voxel, virtual vector) time-invariant data -> shared memory ----
+		for (int idx = threadIdx.x; idx < chunk * nb; idx += kEcgThreads) {
+			const int j = idx / nb, v = idx - j * nb;
+			const int base = s_sub[v][0] + it * chunk;
+			if (base + j >= s_sub[v][1]) continue;
+			const uint32_t pos = __ldg(a.pos + base + j);
+			const uint32_t mask = __ldg(a.mask + base + j);
+			const float at = __ldg(a.at32 + base + j);
+			// voxel position = its index in the zero-bordered matrix (simulator.cpp:487, :531);
+			// integer -> float through the 2^23 mantissa trick (keeps I2F off the MUFU/XU pipe)
+			const float pz = __uint_as_float(0x4B000000u | ((pos >> 22) + 1u)) - 8388608.f;
+			const float py = __uint_as_float(0x4B000000u | (((pos >> 11) & 0x7ffu) + 1u)) - 8388608.f;
+			const float px = __uint_as_float(0x4B000000u | ((pos & 0x7ffu) + 1u)) - 8388608.f;
+			const float2* lead = s_lead + v * NL * 3;
+			float G[NL];
+#pragma unroll
+			for (int l = 0; l < NL; ++l) {
+				const float rz = (lead[3 * l].x - pz) + lead[3 * l].y;      // mp - p_c, exact difference + low part
+				const float ry = (lead[3 * l + 1].x - py) + lead[3 * l + 1].y;
+				const float rx = (lead[3 * l + 2].x - px) + lead[3 * l + 2].y;
+				float g = 0.f;
+				float sz = 0.f, sy = 0.f, sx = 0.f;
+				for (int k = 0; k < a.nbr.n; ++k) {
+					if ((mask >> a.nbr.bit[k]) & 1u) {
+						const float dz = a.nbr.fz[k], dy = a.nbr.fy[k], dx = a.nbr.fx[k];
+						const float qz = rz + dz, qy = ry + dy, qx = rx + dx;  // mp - p_{c-dif}
+						const float sq = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
+						const float dot = fmaf(dz, qz, fmaf(dy, qy, dx * qx));
+						g = fmaf(dot, inv_cube(sq), g);
+						sz += dz; sy += dy; sx += dx;
+					}
+				}
+				const float sqc = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+				g = fmaf(fmaf(sz, rz, fmaf(sy, ry, sx * rx)), inv_cube(sqc), g);
+				G[l] = (a.lead0 + l < a.L) ? -g : 0.f;
 			}
-			// per-thread constants of (vector b, layer, sample t)
-			const float* P = a.params + ((int64_t)b * a.n_layers + (sg.layer - 1)) * kParamStride;
-			const float a1 = __ldg(P + 0), k0 = __ldg(P + 8);
-			float a4 = 0.f, a5 = 0.f, a7 = 0.f, c2 = 0.f, np = 0.f, A = 0.f, Bc = 0.f, k8hi = 0.f, k8lo = 0.f, F1 = 0.f, F2 = 0.f;
+			float* row = s_vox + idx * ROW;
 			if (MODE == MODE_DIRECT) {
-				a4 = __ldg(P + 1); a5 = __ldg(P + 2);
-				a7 = __ldg(P + 3); c2 = __ldg(P + 4); np = __ldg(P + 5); A = __ldg(P + 6); Bc = __ldg(P + 7);
-				k8hi = __ldg(P + 9); k8lo = __ldg(P + 10);
-			} else if (live) {
-				const float* F = a.ftab + (((int64_t)b * a.n_layers + (sg.layer - 1)) * 2) * a.T + t;
-				F1 = __ldg(F);
-				F2 = __ldg(F + a.T);
+				row[0] = at;
+#pragma unroll
+				for (int l = 0; l < NL; ++l) row[1 + l] = G[l];
+			} else {
+				// time-invariant AP factors exp((k4+k5)(at-t0)), exp(k5 (at-t0)); clamped so that
+				// the products with the (also clamped) table entries can never be inf*0
+				const float* Pv = a.params + ((int64_t)((vv0 + v) % a.B) * a.n_layers + (sg.layer - 1)) * kParamStride;
+				const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
+				const float da = at - t0;
+				// row = (h1, h2, G_0..G_{NL-1}, at): the saturated loop only needs the leading part
+				row[0] = mufu_ex2(fminf(-(v4 + v5) * da, 60.f));
+				row[1] = mufu_ex2(fminf(-v5 * da, 60.f));
+#pragma unroll
+				for (int l = 0; l < NL; ++l) row[2 + l] = G[l];
+				row[2 + NL] = at;
+				// activation times are >= 0, so their float bit patterns order like ints
+				const int amax = __reduce_max_sync(__activemask(), __float_as_int(at));
+				if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicMax(&s_atmax[parity], amax);
 			}
-			const int it_end = (int)min((int64_t)n_iter, it + (tile_u_end - u));
-			for (; it < it_end; ++it, ++u, parity ^= 1) {
-				const int n = max(0, min(chunk, my_sub_n - it * chunk));   // voxels of this thread's sub-range in this chunk
-				__syncthreads();  // phase B of the previous chunk is done with s_vox; s_lead and s_sub are visible
+		}
+		__syncthreads();
+		// HOISTED: once every sample of this warp is later than the chunk's last activation by enough
+		// that exp(-k1 (t-at)) < 2^-25, the depolarisation sigmoid is exactly 1 in fp32 and the two
+		// MUFU ops per voxel can be skipped (always the case for T/U-wave runs that start at 100 ms)
+		bool saturated = false;
+		if (MODE == MODE_HOISTED) {
+			const float tau_min = (thi - __int_as_float(s_atmax[parity])) + tlo;
+			saturated = __all_sync(0xffffffffu, !live || a1 * tau_min < -25.f);
+			if (threadIdx.x == 0) s_atmax[parity ^ 1] = 0;  // for the next chunk (written after the barrier above)
+		}
 
-				// ---- phase A: per-(voxel, virtual vector) time-invariant data -> shared memory ----
-				for (int idx = threadIdx.x; idx < chunk * nb; idx += kEcgThreads) {
-					const int j = idx / nb, v = idx - j * nb;
-					const int base = s_sub[v][0] + it * chunk;
-					if (base + j >= s_sub[v][1]) continue;
-					const uint32_t pos = __ldg(a.pos + base + j);
-					const uint32_t mask = __ldg(a.mask + base + j);
-					const float at = __ldg(a.at32 + base + j);
-					// voxel position = its index in the zero-bordered matrix (simulator.cpp:487, :531);
-					// integer -> float through the 2^23 mantissa trick (keeps I2F off the MUFU/XU pipe)
-					const float pz = __uint_as_float(0x4B000000u | ((pos >> 22) + 1u)) - 8388608.f;
-					const float py = __uint_as_float(0x4B000000u | (((pos >> 11) & 0x7ffu) + 1u)) - 8388608.f;
-					const float px = __uint_as_float(0x4B000000u | ((pos & 0x7ffu) + 1u)) - 8388608.f;
-					const float2* lead = s_lead + v * NL * 3;
-					float G[NL];
+		// ---- phase B: time loop, one (vector, sample) pair per thread, voxel rows from shared memory ----
+		if (live) {
+			const float* my_rows = s_vox + bl * ROW;
+			const int stride = nb * ROW;
+			// SAT = true is the HOISTED loop without the depolarisation sigmoid (see above)
+			auto time_loop = [&](auto sat_tag) {
+				constexpr bool SAT = decltype(sat_tag)::value;
+				for (int j0 = 0; j0 < n; j0 += 32) {
+					const int j1 = min(j0 + 32, n);
+					float acc[NL];
+#pragma unroll
+					for (int l = 0; l < NL; ++l) acc[l] = 0.f;
+					const float4* rp = reinterpret_cast<const float4*>(my_rows + j0 * stride);
+#pragma unroll 4
+					for (int j = j0; j < j1; ++j, rp += stride / 4) {
+						const float4 r0 = rp[0];
+						float V;
+						float G[NL];
+						if (MODE == MODE_DIRECT) {
+							const float tau = (thi - r0.x) + tlo;               // t - at   (simulator.cpp:169)
+							const float S = fma_rcp(1.f + mufu_ex2(fminf(a1 * tau, 126.f)));  // 1/(1+exp(-k1 t'))
+							const float k8s = k8hi - r0.x;                   // k8 - at  (simulator.cpp:156)
+							const float u = (tau - k8s) - k8lo;              // t' - k8'
+							// (1+e)^(-k6/k7) with e = exp(-k7 (t'-k8') + ln(2^(k7/k6)-1)) = 2^z, evaluated as
+							// 2^(-(k6/k7) * log2(1+2^z)),  log2(1+2^z) = max(z,0) + log2(1 + 2^-|z|):
+							// the same two MUFU ops, but 2^z may exceed the fp32 range (small k6/k7 make
+							// (huge)^(-small) a perfectly ordinary number)
+							const float z = fmaf(a7, u, c2);
+							const float Q = mufu_ex2(np * (fmaxf(z, 0.f) + mufu_lg2(1.f + mufu_ex2(-fabsf(z)))));
+							// k2((1-k3) exp(-k4 t') + k3); the clamp only matters far before activation, where S is 0 and
+							// an overflowing exponential would turn 0 * inf into NaN (the f64 reference stays finite there)
+							const float Pp = fmaf(A, mufu_ex2(fminf(a4 * tau, 100.f)), Bc);
+							const float E5 = mufu_ex2(a5 * tau);
+							V = fmaf((S * Pp) * E5, 1.f - Q, k0);
+							G[0] = r0.y;
+							if (NL >= 2) G[1] = r0.z;
+							if (NL >= 3) G[2] = r0.w;
+							if (NL >= 4) G[3] = rp[1].x;
+						} else {
+							G[0] = r0.z;
+							if (NL >= 2) G[1] = r0.w;
+							if (NL >= 3) G[2] = rp[1].x;
+							if (NL >= 4) G[3] = rp[1].y;
+							if (SAT) {
+								V = fmaf(F1, r0.x, fmaf(F2, r0.y, k0));
+							} else {
+								const float at = NL <= 2 ? rp[1].x : rp[1].z;
+								const float tau = (thi - at) + tlo;
+								const float S = mufu_rcp(1.f + mufu_ex2(a1 * tau));
+								V = fmaf(S, fmaf(F1, r0.x, F2 * r0.y), k0);
+							}
+						}
+#pragma unroll
+						for (int l = 0; l < NL; ++l) acc[l] = fmaf(G[l], V, acc[l]);
+					}
 #pragma unroll
 					for (int l = 0; l < NL; ++l) {
-						const float rz = (lead[3 * l].x - pz) + lead[3 * l].y;      // mp - p_c, exact difference + low part
-						const float ry = (lead[3 * l + 1].x - py) + lead[3 * l + 1].y;
-						const float rx = (lead[3 * l + 2].x - px) + lead[3 * l + 2].y;
-						float g = 0.f;
-						float sz = 0.f, sy = 0.f, sx = 0.f;
-						for (int k = 0; k < a.nbr.n; ++k) {
-							if ((mask >> a.nbr.bit[k]) & 1u) {
-								const float dz = a.nbr.fz[k], dy = a.nbr.fy[k], dx = a.nbr.fx[k];
-								const float qz = rz + dz, qy = ry + dy, qx = rx + dx;  // mp - p_{c-dif}
-								const float sq = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
-								const float dot = fmaf(dz, qz, fmaf(dy, qy, dx * qx));
-								g = fmaf(dot, inv_cube(sq), g);
-								sz += dz; sy += dy; sx += dx;
-							}
-						}
-						const float sqc = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
-						g = fmaf(fmaf(sz, rz, fmaf(sy, ry, sx * rx)), inv_cube(sqc), g);
-						G[l] = (a.lead0 + l < a.L) ? -g : 0.f;
-					}
-					float* row = s_vox + idx * ROW;
-					if (MODE == MODE_DIRECT) {
-						row[0] = at;
-#pragma unroll
-						for (int l = 0; l < NL; ++l) row[1 + l] = G[l];
-					} else {
-						// time-invariant AP factors exp((k4+k5)(at-t0)), exp(k5 (at-t0)); clamped so that
-						// the products with the (also clamped) table entries can never be inf*0
-						const float* Pv = a.params + ((int64_t)((vv0 + v) % a.B) * a.n_layers + (sg.layer - 1)) * kParamStride;
-						const float v4 = __ldg(Pv + 1), v5 = __ldg(Pv + 2), t0 = __ldg(Pv + 11);
-						const float da = at - t0;
-						// row = (h1, h2, G_0..G_{NL-1}, at): the saturated loop only needs the leading part
-						row[0] = mufu_ex2(fminf(-(v4 + v5) * da, 60.f));
-						row[1] = mufu_ex2(fminf(-v5 * da, 60.f));
-#pragma unroll
-						for (int l = 0; l < NL; ++l) row[2 + l] = G[l];
-						row[2 + NL] = at;
-						// activation times are >= 0, so their float bit patterns order like ints
-						const int amax = __reduce_max_sync(__activemask(), __float_as_int(at));
-						if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicMax(&s_atmax[parity], amax);
+						const float s1 = sum[l] + acc[l];
+						const float bp = s1 - sum[l];
+						comp[l] += (sum[l] - (s1 - bp)) + (acc[l] - bp);
+						sum[l] = s1;
 					}
 				}
-				__syncthreads();
-				// HOISTED: once every sample of this warp is later than the chunk's last activation by enough
-				// that exp(-k1 (t-at)) < 2^-25, the depolarisation sigmoid is exactly 1 in fp32 and the two
-				// MUFU ops per voxel can be skipped (always the case for T/U-wave runs that start at 100 ms)
-				bool saturated = false;
-				if (MODE == MODE_HOISTED) {
-					const float tau_min = (thi - __int_as_float(s_atmax[parity])) + tlo;
-					saturated = __all_sync(0xffffffffu, !live || a1 * tau_min < -25.f);
-					if (threadIdx.x == 0) s_atmax[parity ^ 1] = 0;  // for the next chunk (written after the barrier above)
-				}
-
-				// ---- phase B: time loop, one (vector, sample) pair per thread, voxel rows from shared memory ----
-				if (live) {
-					const float* my_rows = s_vox + bl * ROW;
-					const int stride = nb * ROW;
-					// SAT = true is the HOISTED loop without the depolarisation sigmoid (see above)
-					auto time_loop = [&](auto sat_tag) {
-						constexpr bool SAT = decltype(sat_tag)::value;
-						for (int j0 = 0; j0 < n; j0 += 32) {
-							const int j1 = min(j0 + 32, n);
-							float acc[NL];
-#pragma unroll
-							for (int l = 0; l < NL; ++l) acc[l] = 0.f;
-							const float4* rp = reinterpret_cast<const float4*>(my_rows + j0 * stride);
-#pragma unroll 4
-							for (int j = j0; j < j1; ++j, rp += stride / 4) {
-								const float4 r0 = rp[0];
-								float V;
-								float G[NL];
-								if (MODE == MODE_DIRECT) {
-									const float tau = (thi - r0.x) + tlo;               // t - at   (simulator.cpp:169)
-									const float S = fma_rcp(1.f + mufu_ex2(fminf(a1 * tau, 126.f)));  // 1/(1+exp(-k1 t'))
-									const float k8s = k8hi - r0.x;                   // k8 - at  (simulator.cpp:156)
-									const float u = (tau - k8s) - k8lo;              // t' - k8'
-									// (1+e)^(-k6/k7) with e = exp(-k7 (t'-k8') + ln(2^(k7/k6)-1)) = 2^z, evaluated as
-									// 2^(-(k6/k7) * log2(1+2^z)),  log2(1+2^z) = max(z,0) + log2(1 + 2^-|z|):
-									// the same two MUFU ops, but 2^z may exceed the fp32 range (small k6/k7 make
-									// (huge)^(-small) a perfectly ordinary number)
-									const float z = fmaf(a7, u, c2);
-									const float Q = mufu_ex2(np * (fmaxf(z, 0.f) + mufu_lg2(1.f + mufu_ex2(-fabsf(z)))));
-									// k2((1-k3) exp(-k4 t') + k3); the clamp only matters far before activation, where S is 0 and
-									// an overflowing exponential would turn 0 * inf into NaN (the f64 reference stays finite there)
-									const float Pp = fmaf(A, mufu_ex2(fminf(a4 * tau, 100.f)), Bc);
-									const float E5 = mufu_ex2(a5 * tau);
-									V = fmaf((S * Pp) * E5, 1.f - Q, k0);
-									G[0] = r0.y;
-									if (NL >= 2) G[1] = r0.z;
-									if (NL >= 3) G[2] = r0.w;
-									if (NL >= 4) G[3] = rp[1].x;
-								} else {
-									G[0] = r0.z;
-									if (NL >= 2) G[1] = r0.w;
-									if (NL >= 3) G[2] = rp[1].x;
-									if (NL >= 4) G[3] = rp[1].y;
-									if (SAT) {
-										V = fmaf(F1, r0.x, fmaf(F2, r0.y, k0));
-									} else {
-										const float at = NL <= 2 ? rp[1].x : rp[1].z;
-										const float tau = (thi - at) + tlo;
-										const float S = mufu_rcp(1.f + mufu_ex2(a1 * tau));
-										V = fmaf(S, fmaf(F1, r0.x, F2 * r0.y), k0);
-									}
-								}
-#pragma unroll
-								for (int l = 0; l < NL; ++l) acc[l] = fmaf(G[l], V, acc[l]);
-							}
-#pragma unroll
-							for (int l = 0; l < NL; ++l) {
-								const float s1 = sum[l] + acc[l];
-								const float bp = s1 - sum[l];
-								comp[l] += (sum[l] - (s1 - bp)) + (acc[l] - bp);
-								sum[l] = s1;
-							}
-						}
-					};
-					if (MODE == MODE_HOISTED && saturated) time_loop(std::true_type{});
-					else time_loop(std::false_type{});
-				}
-			}
+			};
+			if (MODE == MODE_HOISTED && saturated) time_loop(std::true_type{});
+			else time_loop(std::false_type{});
 		}
+	}
 
-		// ---- one piece per (CTA, tile): [piece][lead][thread] ----
+	if (live) {
 #pragma unroll
-		for (int l = 0; l < NL; ++l)
-			a.partial[((int64_t)piece * NL + l) * kEcgThreads + threadIdx.x] = live ? (double)sum[l] + (double)comp[l] : 0.0;
-	}
-}
-
-// pieces -> ECG.  Output (b, lead, t) = sum over the slices s and over the pieces of the tile that holds the pair
-// p = (s B + b) T + t, slices and pieces in ascending order.  `tiles` are consecutive runs of pairs; piece_first[i] is the
-// first piece of tile i (the pieces of a tile are consecutive: the CTAs' unit ranges are consecutive in tile-major order).
-// (the time loop may cover only the first T_loop of T samples: row stride T on the output side)
-__global__ void __launch_bounds__(256) ecg_piece_reduce_kernel(const double* __restrict__ partial, const PairTile* __restrict__ tiles,
-                                                               const int32_t* __restrict__ piece_first, int n_tiles, int NL, int lead0, int B, int L,
-                                                               int S, int T_loop, int T, double* __restrict__ ecg) {
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (b, l, t) with l in [0, min(NL, L - lead0))
-	const int nl = min(NL, L - lead0);
-	if (i >= (int64_t)B * nl * T_loop) return;
-	const int t = (int)(i % T_loop), l = (int)((i / T_loop) % nl), b = (int)(i / ((int64_t)T_loop * nl));
-	double acc = 0.0;
-	for (int s = 0; s < S; ++s) {
-		const int p = (s * B + b) * T_loop + t;
-		int lo = 0, hi = n_tiles;   // last tile with begin <= p
-		while (hi - lo > 1) {
-			const int mid = (lo + hi) >> 1;
-			if (__ldg(&tiles[mid].begin) <= p) lo = mid; else hi = mid;
+		for (int l = 0; l < NL; ++l) {
+			const int lead = a.lead0 + l;
+			if (lead < a.L) a.partial[((((int64_t)blockIdx.x * a.S + sl) * a.B + b) * a.L + lead) * a.T + t] = (double)sum[l] + (double)comp[l];
 		}
-		const int slot = p - __ldg(&tiles[lo].begin);
-		for (int pc = __ldg(piece_first + lo); pc < __ldg(piece_first + lo + 1); ++pc) acc += __ldg(partial + ((int64_t)pc * NL + l) * kEcgThreads + slot);
 	}
-	ecg[((int64_t)b * L + lead0 + l) * T + t] = acc;
 }
 
 // ---- SEPARABLE path -------------------------------------------------------------------------------
@@ -819,6 +766,37 @@ __global__ void __launch_bounds__(kCombSamples * kCombLanes) ecg_combine_kernel(
 	}
 }
 
+// ---- partial sums -> ECG, fixed order ------------------------------------------------------------
+// partial is [n_rows][n_out] (n_rows = segments x slices).  A CTA owns 32 outputs and one block of kRedRows rows
+// (grid.y); its 8 warps each add every 8th row of the block (coalesced 256-byte reads, 8 independent chains instead of
+// one chain of n_rows dependent loads -- a single simulation has only 800 outputs but ~10^4 rows), the 8 sub-sums are
+// added in warp order.  More than one row block: the block sums go to a scratch array and a second launch adds those.
+// Every order is fixed -> bitwise run-to-run determinism.
+// (the time loop may cover only the first T_loop of T samples: row stride T on the output side of the final pass)
+constexpr int kRedGroups = 8;
+constexpr int kRedRows = 512;
+__global__ void __launch_bounds__(32 * kRedGroups) ecg_reduce_kernel(const double* __restrict__ partial, double* __restrict__ out, int n_rows,
+                                                                   int64_t n_out, int T_loop, int T, int final_pass) {
+	__shared__ double s_part[kRedGroups][33];
+	const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+	const int64_t i = (int64_t)blockIdx.x * 32 + o;
+	const int r0 = blockIdx.y * kRedRows, r1 = min(n_rows, r0 + kRedRows);
+	double s = 0.0;
+	if (i < n_out) {
+#pragma unroll 4
+		for (int k = r0 + g; k < r1; k += kRedGroups) s += __ldg(partial + (int64_t)k * n_out + i);
+	}
+	s_part[g][o] = s;
+	__syncthreads();
+	if (g == 0 && i < n_out) {
+		double r = s_part[0][o];
+#pragma unroll
+		for (int q = 1; q < kRedGroups; ++q) r += s_part[q][o];
+		if (final_pass) out[(i / T_loop) * T + i % T_loop] = r;
+		else out[(int64_t)blockIdx.y * n_out + i] = r;
+	}
+}
+
 // ---- curve comparison on the device (calculateFitness, sim.cpp:600-702; vectorMath.h) -----------------
 // One CTA per (vector, lead); f64 block reductions over the n overlapping samples, offset 0.
 __device__ __forceinline__ double block_sum(double v, double* scratch) {
@@ -1014,8 +992,6 @@ static int build_segments(ekg_model* m, int64_t seg_len, cudaStream_t st) {
 	EKG_CUDA(cudaStreamSynchronize(st));
 	m->n_segs = (int64_t)segs.size();
 	m->seg_len = seg_len;
-	m->h_segs = segs;
-	++m->segs_version;
 	return EKG_OK;
 }
 
@@ -1068,15 +1044,16 @@ static int build_moment_segments(ekg_model* m, int64_t seg_len, cudaStream_t st)
 static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
                        double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, KHints hints);
 
-// Very large batches are cut into sub-batches (pair indices are 32-bit).
+// Large batches are cut into sub-batches so that the f64 partial-sum scratch stays below ~1 GiB.
 int run_ecg(ekg_model* m, const double* d_layer_k, const double* d_leads, int64_t B, int64_t L, int nbhd,
             double t_start, double t_step, double total_time, int flags, double* d_ecg, cudaStream_t st, KHints hints) {
 	if (B <= 0 || L <= 0) return fail(EKG_E_INVALID, "B and n_leads must be positive");
 	if (!(t_step > 0) || !(total_time > 0)) return fail(EKG_E_INVALID, "t_step and total_time must be positive");
 	const int64_t T = (int64_t)ceil(total_time / t_step);
 	if (T <= 0 || T > (1 << 24)) return fail(EKG_E_INVALID, "bad number of time steps");
-	// sub-batches only keep the flattened (slice, vector, sample) pair index inside 31 bits
-	int64_t sub = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)1 << 26) / std::max<int64_t>(T, 1)));
+	// at ~100 waves the segment count is about (592 * 96) / (B * T / 256); partial bytes = segs * B * L * T * 8
+	const int64_t per_vector = std::max<int64_t>(L * T * 8, 1);
+	int64_t sub = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)1 << 30) / (per_vector * 160)));
 	sub = std::min<int64_t>(sub, 16384);
 	int64_t launches = 0;
 	const bool timed = (flags & EKG_FLAG_TIME_KERNEL) != 0;
@@ -1214,75 +1191,25 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 			EKG_CUDA(cudaMemcpyAsync(m->d_tiles, tiles.data(), tiles.size() * sizeof(PairTile), cudaMemcpyHostToDevice, st));
 			EKG_CUDA(cudaStreamSynchronize(st));
 			m->n_tiles = (int64_t)tiles.size(); m->tiles_B = VB; m->tiles_T = T_loop;
-			m->h_tiles.swap(tiles);
 		}
-		if (m->n_ecg == 0) {
-			EKG_CUDA(cudaMemsetAsync(d_ecg, 0, (size_t)(B * L * T) * sizeof(double), st));   // a slab without voxels
-			return EKG_OK;
+		// ~100 waves of CTAs: the tail of the last wave costs about 1/waves of the launch.  A thread walks seg_len / S
+		// voxels: at least kMinSub of them (a CTA pays ~1 us of fixed cost: parameter loads, phase A, two barriers)
+		static const int64_t kMinSub = getenv("EKGSIM_B200_ECG_SUB") ? std::max(32, atoi(getenv("EKGSIM_B200_ECG_SUB"))) : 128;
+		const int64_t target_ctas = (int64_t)m->sm_count * 4 * 96;
+		int64_t want_segs = (target_ctas + m->n_tiles - 1) / m->n_tiles;
+		int64_t seg_len = (m->n_ecg + want_segs - 1) / std::max<int64_t>(want_segs, 1);
+		if (S == 1) {
+			seg_len = std::max<int64_t>(kChunk, std::min<int64_t>(seg_len, 16384));
+			seg_len = (seg_len + kChunk - 1) / kChunk * kChunk;
+		} else {
+			seg_len = std::max<int64_t>(kMinSub * S, std::min<int64_t>(seg_len, 16384));
+			seg_len = (seg_len + S - 1) / S * S;
 		}
-		// segments: runs of one layer (long ones cut so that 32-bit voxel counts stay comfortable); their length no longer
-		// matters for parallelism, the launch is one wave of CTAs with equal shares of the (tile, segment, chunk) units
-		if ((rc = build_segments(m, (int64_t)1 << 22, st))) return rc;
-		static int occ[2][2] = {{0, 0}, {0, 0}};   // resident CTAs per SM of the four instantiations
-		for (int md = 0; md < 2; ++md) for (int w = 0; w < 2; ++w) if (!occ[md][w]) {
-			const void* f = md == 0 ? (w == 0 ? (const void*)ecg_kernel<MODE_DIRECT, 2> : (const void*)ecg_kernel<MODE_DIRECT, 4>)
-			                        : (w == 0 ? (const void*)ecg_kernel<MODE_HOISTED, 2> : (const void*)ecg_kernel<MODE_HOISTED, 4>);
-			EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[md][w], f, kEcgThreads, 0));
-			if (occ[md][w] < 1) return fail(EKG_E_CUDA, "ECG kernel does not fit on the device");
-		}
-		const int nl_pass = (int)std::min<int64_t>(kMaxLeadsPerPass, L);
-		const int width = nl_pass <= 2 ? 2 : 4;
-		const int64_t G_max = (int64_t)m->sm_count * occ[loop_mode == EKG_MODE_DIRECT ? 0 : 1][width == 2 ? 0 : 1];
-		// unit tables: chunks per segment for the four chunk sizes (a tile of nb virtual vectors stages 512 / nb rows per
-		// chunk), units before every tile, first piece of every CTA and of every tile
-		if (m->plan_VB != VB || m->plan_T != T_loop || m->plan_S != S || m->plan_G != G_max || m->plan_segs != m->segs_version) {
-			const std::vector<PairTile>& tiles = m->h_tiles;
-			const int64_t ns = m->n_segs, nt = m->n_tiles;
-			std::vector<int32_t> seg_units((size_t)(kMaxVecPerTile * (ns + 1)), 0);
-			for (int c = 0; c < kMaxVecPerTile; ++c) {
-				const int64_t chunk = std::min<int64_t>(kChunk, kSmemRows / (c + 1));
-				for (int64_t i = 0; i < ns; ++i) {
-					const int64_t len = m->h_segs[(size_t)i].end - m->h_segs[(size_t)i].begin, sub = (len + S - 1) / S;
-					seg_units[(size_t)(c * (ns + 1) + i + 1)] = seg_units[(size_t)(c * (ns + 1) + i)] + (int32_t)((sub + chunk - 1) / chunk);
-				}
-			}
-			std::vector<int32_t> tile_units((size_t)nt + 1, 0);
-			int64_t U = 0;
-			for (int64_t i = 0; i < nt; ++i) {
-				const int64_t vv0 = tiles[(size_t)i].begin / T_loop, nb = (tiles[(size_t)i].end - 1) / T_loop - vv0 + 1;
-				U += seg_units[(size_t)((nb - 1) * (ns + 1) + ns)];
-				if (U >= ((int64_t)1 << 31)) return fail(EKG_E_UNSUPPORTED, "too much work for one launch: split the batch");
-				tile_units[(size_t)i + 1] = (int32_t)U;
-			}
-			const int64_t G = std::max<int64_t>(1, std::min<int64_t>(G_max, U));
-			std::vector<int32_t> piece_base((size_t)G, 0), piece_first((size_t)nt + 1, -1);
-			int32_t next_piece = 0;
-			int64_t tcur = 0;
-			for (int64_t k = 0; k < G; ++k) {
-				const int64_t u0 = U * k / G, u1 = U * (k + 1) / G;
-				piece_base[(size_t)k] = next_piece;
-				if (u0 >= u1) continue;
-				while (tile_units[(size_t)tcur + 1] <= u0) ++tcur;          // tile of unit u0 (same rule as the kernel's search)
-				int64_t tl = tcur;
-				while (tile_units[(size_t)tl + 1] < u1) ++tl;               // tile of unit u1 - 1
-				for (int64_t t2 = tcur; t2 <= tl; ++t2, ++next_piece) if (piece_first[(size_t)t2] < 0) piece_first[(size_t)t2] = next_piece;
-				tcur = tl;
-			}
-			piece_first[(size_t)nt] = next_piece;
-			for (int64_t i = nt - 1; i >= 0; --i) if (piece_first[(size_t)i] < 0) piece_first[(size_t)i] = piece_first[(size_t)i + 1];   // tiles without units
-			const int64_t words = (int64_t)seg_units.size() + 2 * (nt + 1) + G;
-			if ((rc = ensure(&m->d_plan, &m->plan_cap, words))) return rc;
-			int32_t* d = m->d_plan;
-			EKG_CUDA(cudaMemcpyAsync(d, seg_units.data(), seg_units.size() * 4, cudaMemcpyHostToDevice, st));
-			EKG_CUDA(cudaMemcpyAsync(d + seg_units.size(), tile_units.data(), tile_units.size() * 4, cudaMemcpyHostToDevice, st));
-			EKG_CUDA(cudaMemcpyAsync(d + seg_units.size() + (nt + 1), piece_first.data(), piece_first.size() * 4, cudaMemcpyHostToDevice, st));
-			EKG_CUDA(cudaMemcpyAsync(d + seg_units.size() + 2 * (nt + 1), piece_base.data(), piece_base.size() * 4, cudaMemcpyHostToDevice, st));
-			EKG_CUDA(cudaStreamSynchronize(st));
-			m->plan_VB = VB; m->plan_T = T_loop; m->plan_S = S; m->plan_G = G_max; m->plan_segs = m->segs_version;
-			m->plan_units = U; m->plan_grid = G; m->plan_pieces = next_piece;
-		}
-		const int64_t ns1 = m->n_segs + 1, nt1 = m->n_tiles + 1;
-		if ((rc = ensure(&m->d_partial, &m->partial_cap, m->plan_pieces * width * kEcgThreads))) return rc;
+		if ((rc = build_segments(m, seg_len, st))) return rc;
+		if (m->n_tiles > 65535) return fail(EKG_E_UNSUPPORTED, "too many (vector, sample) pairs for one launch (B * n_steps <= 16.7 M)");
+
+		const int64_t n_out = B * L * T_loop;
+		if ((rc = ensure(&m->d_partial, &m->partial_cap, m->n_segs * S * n_out))) return rc;
 		if (loop_mode == EKG_MODE_HOISTED) {
 			if ((rc = ensure(&m->d_ftab, &m->ftab_cap, n_bl * 2 * T_loop))) return rc;
 			ecg_ftab_kernel<<<(int)((n_bl * T_loop + 255) / 256), 256, 0, st>>>(d_layer_k, d_t64, m->d_ftab, n_bl, (int)T_loop, (double)(float)m->t0);
@@ -1296,30 +1223,39 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		a.partial = m->d_partial;
 		a.n_segs = (int32_t)m->n_segs; a.B = (int32_t)B; a.L = (int32_t)L; a.T = (int32_t)T_loop; a.n_layers = m->n_layers;
 		a.S = (int32_t)S;
-		a.seg_units = m->d_plan; a.tile_units = m->d_plan + kMaxVecPerTile * ns1; a.piece_base = m->d_plan + kMaxVecPerTile * ns1 + 2 * nt1;
-		a.n_units = m->plan_units; a.n_tiles = (int32_t)m->n_tiles;
-		const int32_t* d_piece_first = m->d_plan + kMaxVecPerTile * ns1 + nt1;
 
-		const dim3 grid((unsigned)m->plan_grid, 1, 1);
+		const dim3 grid((unsigned)m->n_segs, (unsigned)m->n_tiles, 1);
 		const int threads = kEcgThreads;
 		if (need_k0) { EKG_CUDA(cudaEventRecord(m->ev_k0, st)); need_k0 = false; }
 		for (int lead0 = 0; lead0 < L; lead0 += kMaxLeadsPerPass) {
 			a.lead0 = lead0;
+			const int nl = (int)std::min<int64_t>(kMaxLeadsPerPass, L - lead0);
 			if (loop_mode == EKG_MODE_DIRECT) {
-				if (width == 2) rc = launch_ecg<MODE_DIRECT, 2>(a, grid, threads, st);
+				if (nl <= 2) rc = launch_ecg<MODE_DIRECT, 2>(a, grid, threads, st);
 				else rc = launch_ecg<MODE_DIRECT, 4>(a, grid, threads, st);
 				m->last_kernel = "ecg_kernel<DIRECT>";
 			} else {
-				if (width == 2) rc = launch_ecg<MODE_HOISTED, 2>(a, grid, threads, st);
+				if (nl <= 2) rc = launch_ecg<MODE_HOISTED, 2>(a, grid, threads, st);
 				else rc = launch_ecg<MODE_HOISTED, 4>(a, grid, threads, st);
 				m->last_kernel = "ecg_kernel<HOISTED>";
 			}
 			if (rc) return rc;
 			++m->last_launches;
-			if (T_loop == T && timed && lead0 + kMaxLeadsPerPass >= L) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
-			const int64_t n_red = B * std::min<int64_t>(width, L - lead0) * T_loop;
-			ecg_piece_reduce_kernel<<<(unsigned)((n_red + 255) / 256), 256, 0, st>>>(m->d_partial, m->d_tiles, d_piece_first, (int)m->n_tiles, width, lead0,
-			                                                                      (int)B, (int)L, (int)S, (int)T_loop, (int)T, d_ecg);
+		}
+		if (T_loop == T && timed) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
+		{
+			const int64_t n_rows = m->n_segs * S, n_blocks = (n_rows + kRedRows - 1) / kRedRows;
+			const unsigned gx = (unsigned)((n_out + 31) / 32);
+			if (n_blocks > 1) {
+				if (n_blocks > kRedRows) return fail(EKG_E_UNSUPPORTED, "too many partial sums for the two-pass reduction");
+				if ((rc = ensure(&m->d_partial2, &m->partial2_cap, n_blocks * n_out))) return rc;
+				ecg_reduce_kernel<<<dim3(gx, (unsigned)n_blocks), 32 * kRedGroups, 0, st>>>(m->d_partial, m->d_partial2, (int)n_rows, n_out, (int)T_loop, (int)T, 0);
+				EKG_CUDA(cudaGetLastError());
+				++m->last_launches;
+				ecg_reduce_kernel<<<dim3(gx, 1), 32 * kRedGroups, 0, st>>>(m->d_partial2, d_ecg, (int)n_blocks, n_out, (int)T_loop, (int)T, 1);
+			} else {
+				ecg_reduce_kernel<<<dim3(gx, 1), 32 * kRedGroups, 0, st>>>(m->d_partial, d_ecg, (int)n_rows, n_out, (int)T_loop, (int)T, 1);
+			}
 			EKG_CUDA(cudaGetLastError());
 			++m->last_launches;
 		}

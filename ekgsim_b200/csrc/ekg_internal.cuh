@@ -63,12 +63,7 @@ struct EcgArgs {
 	const double* leads;    // [B][L][3] (z,y,x)
 	const float* t_hi;      // [T] time samples, hi/lo split of the f64 value
 	const float* t_lo;
-	double* partial;        // [pieces][NL][kEcgThreads]: one piece per (CTA, tile)
-	const int32_t* seg_units;   // [kMaxVecPerTile][n_segs + 1] chunks of the segments before segment i, per chunk-size class (nb - 1)
-	const int32_t* tile_units;  // [n_tiles + 1] units before tile i
-	const int32_t* piece_base;  // [grid] first piece of every CTA
-	int64_t n_units;
-	int32_t n_tiles;
+	double* partial;        // [n_segs][S][B][L][T]
 	int32_t n_segs, B, L, T, n_layers;
 	int32_t S;              // voxel slices per segment (ecg.cu: pair index = (slice, vector, sample)); 1 = none
 	int32_t lead0;          // first lead handled by this launch (L > kMaxLeadsPerPass -> several passes)
@@ -202,11 +197,6 @@ struct ekg_model {
 
 	// per-call scratch (grown on demand)
 	ekg::Segment* d_segs = nullptr;  int64_t segs_cap = 0;  int64_t n_segs = 0;  int64_t seg_len = 0;
-	std::vector<ekg::Segment> h_segs;  int64_t segs_version = 0;
-	std::vector<ekg::PairTile> h_tiles;
-	// launch plan of the time-loop kernel (ecg.cu): unit / piece tables for (virtual vectors, samples, slices, grid, segments)
-	int32_t* d_plan = nullptr;       int64_t plan_cap = 0;
-	int64_t plan_VB = -1, plan_T = -1, plan_S = -1, plan_G = -1, plan_segs = -1, plan_units = 0, plan_grid = 0, plan_pieces = 0;
 	ekg::PairTile* d_tiles = nullptr; int64_t tiles_cap = 0; int64_t n_tiles = 0; int64_t tiles_B = 0, tiles_T = 0;  // tiles_B = S * B
 	// SEPARABLE path: its own segment table (sized for voxel x vector work, not for the time loop)
 	ekg::Segment* d_msegs = nullptr; int64_t msegs_cap = 0;  int64_t n_msegs = 0;  int64_t mseg_len = 0;
