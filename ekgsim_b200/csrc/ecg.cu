@@ -770,17 +770,17 @@ __global__ void __launch_bounds__(kCombSamples * kCombLanes) ecg_combine_kernel(
 // partial is [n_rows][n_out] (n_rows = segments x slices).  A CTA owns 32 outputs and one block of kRedRows rows
 // (grid.y); its 8 warps each add every 8th row of the block (coalesced 256-byte reads, 8 independent chains instead of
 // one chain of n_rows dependent loads -- a single simulation has only 800 outputs but ~10^4 rows), the 8 sub-sums are
-// added in warp order.  More than one row block: the block sums go to a scratch array and a second launch adds those.
+// added in warp order.  More than one row block: the block sums go to a scratch array and further launches add those.
 // Every order is fixed -> bitwise run-to-run determinism.
 // (the time loop may cover only the first T_loop of T samples: row stride T on the output side of the final pass)
 constexpr int kRedGroups = 8;
-constexpr int kRedRows = 512;
+constexpr int kRedRows = 128;
 __global__ void __launch_bounds__(32 * kRedGroups) ecg_reduce_kernel(const double* __restrict__ partial, double* __restrict__ out, int n_rows,
-                                                                   int64_t n_out, int T_loop, int T, int final_pass) {
+                                                                   int64_t n_out, int T_loop, int T, int final_pass, int rows_per_block) {
 	__shared__ double s_part[kRedGroups][33];
 	const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
 	const int64_t i = (int64_t)blockIdx.x * 32 + o;
-	const int r0 = blockIdx.y * kRedRows, r1 = min(n_rows, r0 + kRedRows);
+	const int r0 = blockIdx.y * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
 	double s = 0.0;
 	if (i < n_out) {
 #pragma unroll 4
@@ -1244,18 +1244,26 @@ static int run_ecg_one(ekg_model* m, const double* d_layer_k, const double* d_le
 		}
 		if (T_loop == T && timed) { EKG_CUDA(cudaEventRecord(m->ev_k1, st)); m->ev_recorded = true; }
 		{
-			const int64_t n_rows = m->n_segs * S, n_blocks = (n_rows + kRedRows - 1) / kRedRows;
+			// row blocks of kRedRows rows are added in parallel, then the block sums, ... until one block is left (ping-pong
+			// between the scratch array and the partial array, whose contents have been consumed by then)
+			int64_t n_rows = m->n_segs * S;
 			const unsigned gx = (unsigned)((n_out + 31) / 32);
-			if (n_blocks > 1) {
-				if (n_blocks > kRedRows) return fail(EKG_E_UNSUPPORTED, "too many partial sums for the two-pass reduction");
-				if ((rc = ensure(&m->d_partial2, &m->partial2_cap, n_blocks * n_out))) return rc;
-				ecg_reduce_kernel<<<dim3(gx, (unsigned)n_blocks), 32 * kRedGroups, 0, st>>>(m->d_partial, m->d_partial2, (int)n_rows, n_out, (int)T_loop, (int)T, 0);
-				EKG_CUDA(cudaGetLastError());
-				++m->last_launches;
-				ecg_reduce_kernel<<<dim3(gx, 1), 32 * kRedGroups, 0, st>>>(m->d_partial2, d_ecg, (int)n_blocks, n_out, (int)T_loop, (int)T, 1);
-			} else {
-				ecg_reduce_kernel<<<dim3(gx, 1), 32 * kRedGroups, 0, st>>>(m->d_partial, d_ecg, (int)n_rows, n_out, (int)T_loop, (int)T, 1);
+			const double* src = m->d_partial;
+			if (n_rows > 4 * kRedRows) {   // a few hundred rows are one pass
+				if ((rc = ensure(&m->d_partial2, &m->partial2_cap, ((n_rows + kRedRows - 1) / kRedRows) * n_out))) return rc;
+				double* dst = m->d_partial2;
+				while (n_rows > 4 * kRedRows) {
+					const int64_t n_blocks = (n_rows + kRedRows - 1) / kRedRows;
+					if (n_blocks > 65535) return fail(EKG_E_UNSUPPORTED, "too many partial sums for the reduction");
+					ecg_reduce_kernel<<<dim3(gx, (unsigned)n_blocks), 32 * kRedGroups, 0, st>>>(src, dst, (int)n_rows, n_out, (int)T_loop, (int)T, 0, kRedRows);
+					EKG_CUDA(cudaGetLastError());
+					++m->last_launches;
+					src = dst;
+					dst = dst == m->d_partial2 ? m->d_partial : m->d_partial2;
+					n_rows = n_blocks;
+				}
 			}
+			ecg_reduce_kernel<<<dim3(gx, 1), 32 * kRedGroups, 0, st>>>(src, d_ecg, (int)n_rows, n_out, (int)T_loop, (int)T, 1, (int)n_rows);
 			EKG_CUDA(cudaGetLastError());
 			++m->last_launches;
 		}
