@@ -370,7 +370,24 @@ def generation_block(n_gpus):
         r = subprocess.run([cli, "-batch", "pop.txt", "-batchout", "crit.txt", "-devices", str(n_gpus)], cwd=d, capture_output=True, text=True, env=env)
         dt = time.time() - t0
         m = re.search(r"batch of (\d+) simulations done in ([0-9.e+-]+) seconds on (\d+) GPU", r.stdout)
-        out["batched_cli"] = {"process_wall_s": dt, "s_per_generation": float(m.group(2)) if m else None, "devices": int(m.group(3)) if m else None}
+        out["batched_cli"] = {"process_wall_s": dt, "s_per_generation_cold": float(m.group(2)) if m else None, "devices": int(m.group(3)) if m else None,
+                              "note": "a fresh process: the one batch it evaluates also pays the first-use allocations (pinned staging, scratch) on every device"}
+        # the same generation inside a resident evaluator (what `ekgSim -serve` or an in-process optimizer sees from the second
+        # generation on): Evaluator::evalBatch on all N devices, best of 5
+        import numpy as np
+        import hostlib
+        genes = np.array([[float(x) for x in ln.replace(",", " ").split()] for ln in vec])
+        os.environ.pop("EKGSIM_B200_DEVICE", None)
+        ev = hostlib.Evaluator(d, devices=str(n_gpus))
+        ev.eval_batch(genes)
+        best = 1e9
+        for _ in range(5):
+            t0 = time.perf_counter()
+            ev.eval_batch(genes)
+            best = min(best, time.perf_counter() - t0)
+        ev.close()
+        out["resident_evaluator"] = {"s_per_generation": best, "sims_per_s": len(genes) / best, "devices": n_gpus,
+                                     "api": "Evaluator::evalBatch (100 individuals, v6 target) on %d device(s), warm" % n_gpus}
         demo = os.path.join(ROOT, "oracle", "_ref", "DEMO_ref")
         if os.path.exists(demo):
             open(os.path.join(d, "settings.ini"), "w").write("[evaluation]\ncommand line = %s -extern\ninput file name = input.txt\n"

@@ -172,10 +172,12 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, t
     if visits_per_round is None:
         # Two slabs: the wave starts next to the cut, both ranks are busy from the first round on -- unbounded rounds are
         # best (measured on the 4x heart, 2 GPUs: 22 ms in 2-3 rounds; 25 ms / 5 rounds bounded to 400 k visits, 35 ms /
-        # 18 rounds bounded to 100 k: a round costs ~0.5 ms of launches, exchange and agreement).  More slabs: a bound
-        # of about a fifth of the slab's brick cells (live bricks are ~40 % of the cells and are visited ~5 times each, so
-        # ~10 rounds per slab) hands the wave on after one round instead of after the slab is finished.
-        visits_per_round = 0 if world <= 2 else max(16384, (z1 - z0) * planes.plane_elems // (64 * 5))
+        # 18 rounds bounded to 100 k: a round costs 0.5-1 ms of launches, exchange and agreement).  More slabs: the wave
+        # would cross them one after the other (8 GPUs, unbounded: 4 rounds of ~10 ms = 43 ms, no faster than one GPU);
+        # a bound hands it on after one round.  Too small a bound multiplies the rounds AND the work (stale halos are
+        # relaxed again: 8 GPUs, 25 k visits: 49 rounds, 41 ms; 50 k: 20 rounds, 27 ms) -- about a third of the slab's
+        # brick cells, at least 50 k.
+        visits_per_round = 0 if world <= 2 else max(50000, (z1 - z0) * planes.plane_elems // (64 * 3))
     t_begin = time.perf_counter()
     planes.begin()
     visits, rounds = 0, 0
