@@ -325,7 +325,38 @@ def heart_block(args, rank, world, local):
     if gold is not None:
         out["ecg_err_of_peak"] = max(out["direct"]["ecg_err_of_peak"], out["default"]["ecg_err_of_peak"])
     if world > 1:
-        # the automaton on the sharded model: plane exchange per round, bits as in the replicated run
+        # the automaton on the sharded model, bits as in the replicated run.  (a) peer-linked: one
+        # kernel per rank, face planes and brick pushes go through the neighbours' memory over NVLink, no host round;
+        # (b) the host-driven rounds (plane exchange through NCCL point-to-point messages + an all-reduce per round).
+        def check_bits(info):
+            if rank == 0 and gold is not None:
+                d2 = model.get_activation()
+                info["bit_exact"] = bool(hashlib.sha256(d2.tobytes()).hexdigest() == gold["sha256_f64_raster"])
+        try:
+            ekdist.link_model(model, slabs, rank, world, dev)
+            linked_ok = True
+        except ek.EkgError as e:
+            linked_ok = False
+            out["automaton_sharded"] = {"linked_unavailable": str(e)}
+        ok_all = ekdist.max_over_ranks(0.0 if linked_ok else 1.0, dev) == 0.0
+        if ok_all:
+            best = None
+            for _ in range(3):
+                tm, cnt = {}, {}
+                _, v = ekdist.linked_activation(model, slabs, rank, world, dev, timings=tm, download=False, info=cnt)
+                run_ms = ekdist.max_over_ranks(tm["run_s"] * 1e3, dev)
+                if best is None or run_ms < best["ms"]:
+                    best = {"ms": run_ms, "kernel_ms_max_over_ranks": ekdist.max_over_ranks(cnt["kernel_ms"], dev),
+                            "ms_gather_over_links": ekdist.max_over_ranks(tm["gather_s"] * 1e3, dev), "brick_visits_rank0": v,
+                            "bricks_queued_at_neighbours_rank0": cnt["bricks_queued_at_neighbours"],
+                            "cells_written_to_neighbours_rank0": cnt["cells_written_to_neighbours"], "host_rounds": 0, "collectives": 0,
+                            "how": "peer-linked: in-kernel plane exchange and brick pushes through NVLink peer memory (CUDA IPC), "
+                                   "global termination detected by rank 0's first warp"}
+            check_bits(best)
+            best["speedup_vs_replicated"] = auto_ms / best["ms"]
+            out["automaton_sharded"] = best
+        if linked_ok:
+            model.activation_unlink()
         planes = ekdist.ModelPlanes(model, dev)
         best, info = None, None
         for _ in range(2):
@@ -339,11 +370,11 @@ def heart_block(args, rank, world, local):
             if best is None or dt < best:
                 best, info = dt, {"ms": dt, "ms_rounds": ekdist.max_over_ranks(tm["rounds_s"] * 1e3, dev),
                                   "ms_gather": ekdist.max_over_ranks(tm["gather_s"] * 1e3, dev), "rounds": rounds, "brick_visits_rank0": v}
-        if rank == 0 and gold is not None:
-            d2 = model.get_activation()
-            info["bit_exact"] = bool(hashlib.sha256(d2.tobytes()).hexdigest() == gold["sha256_f64_raster"])
+        check_bits(info)
         info["speedup_vs_replicated"] = auto_ms / info["ms"]
-        out["automaton_sharded"] = info
+        out["automaton_sharded_host_rounds"] = info
+        if "automaton_sharded" not in out or "ms" not in out["automaton_sharded"]:
+            out["automaton_sharded"] = dict(info, **out.get("automaton_sharded", {}))
     model.close()
     return out
 

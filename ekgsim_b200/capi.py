@@ -22,6 +22,7 @@ FLAG_TIME_KERNEL = 0x100
 FLAG_CORNER_SUM = 0x200   # SEPARABLE: interior voxels by the direct corner sum instead of the series (cross-check)
 FIT_D9 = (0.0, 0.0, 0.0, 0.001, 0.0, 0.00005, 0.0005, 0.01, 0.2)   # sim.cpp:877 `kd`
 START_FLAG = 0x1000
+LINK_INFO_BYTES = 256   # EKG_LINK_INFO_BYTES
 
 # every symbol include/ekgsim_b200.h declares: name -> (restype, argtypes)
 _p, _i64, _d, _int = C.c_void_p, C.c_int64, C.c_double, C.c_int
@@ -47,6 +48,12 @@ SYMBOLS = {
     "ekg_model_activation_merge": (_int, [_p, _i64, _i64, _p, C.POINTER(_i64), _p]),
     "ekg_model_activation_merge_async": (_int, [_p, _i64, _i64, _p, _p, _p]),
     "ekg_model_activation_end": (_int, [_p, _p]),
+    "ekg_model_activation_link_info": (_int, [_p, _p]),
+    "ekg_model_activation_link": (_int, [_p, _int, _int, _p, _p]),
+    "ekg_model_activation_linked_launch": (_int, [_p, _int]),
+    "ekg_model_activation_linked_wait": (_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "ekg_model_activation_linked_gather": (_int, [_p]),
+    "ekg_model_activation_unlink": (_int, [_p]),
     "ekg_model_ap_classes": (_int, [_p, _p, C.POINTER(_i64)]),
     "ekg_simulate": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p]),
     "ekg_simulate_criteria": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _i64, _p, _int, _p, _p]),
@@ -189,6 +196,35 @@ class Model:
         out = np.empty(self.shape, dtype=np.float64) if download else None
         _check(lib().ekg_model_activation_end(self._h, _ptr(out) if download else None))
         return out
+
+    # peer-linked sharded automaton (include/ekgsim_b200.h, "peer-linked")
+    def activation_link_info(self):
+        buf = C.create_string_buffer(LINK_INFO_BYTES)
+        _check(lib().ekg_model_activation_link_info(self._h, buf))
+        return buf.raw
+
+    def activation_link(self, rank, infos, slabs):
+        """infos: every rank's activation_link_info() in rank order; slabs: every rank's (z_begin, z_end)"""
+        blob = b"".join(infos)
+        assert len(blob) == LINK_INFO_BYTES * len(slabs)
+        sl = np.ascontiguousarray(np.asarray(slabs, dtype=np.int64).reshape(-1, 2))
+        _check(lib().ekg_model_activation_link(self._h, int(rank), len(slabs), C.c_char_p(blob), _ptr(sl)))
+
+    def activation_linked_launch(self, max_ctas=0):
+        _check(lib().ekg_model_activation_linked_launch(self._h, int(max_ctas)))
+
+    def activation_linked_wait(self):
+        """-> (brick visits, (bricks queued at other ranks, bricks queued here by others, cells written to other ranks))"""
+        v = _i64(0)
+        rem = (_i64 * 3)()
+        _check(lib().ekg_model_activation_linked_wait(self._h, C.byref(v), rem))
+        return int(v.value), tuple(int(x) for x in rem)
+
+    def activation_linked_gather(self):
+        _check(lib().ekg_model_activation_linked_gather(self._h))
+
+    def activation_unlink(self):
+        _check(lib().ekg_model_activation_unlink(self._h))
 
     def set_activation(self, delay):
         delay = np.ascontiguousarray(delay, dtype=np.float64)

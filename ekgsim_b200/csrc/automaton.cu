@@ -26,6 +26,12 @@
 //  * automaton_kernel (EKGSIM_B200_AUTOMATON=sweep) -- the plain label-correcting sweep over all
 //    occupied voxels, kept as the simple cross-check.
 //
+//  * automaton_brick_kernel<.., LINKED> -- the same kernel on a model sharded into z-slabs over several GPUs: improved
+//    voxels on the slab's first / last plane are also written (64-bit atomicMin, system scope) into the neighbouring
+//    rank's grid through peer-mapped memory, and the neighbour's bricks that can see them are pushed into the
+//    neighbour's ring, all from inside the kernel (NVLink atomics, no host round, no collective).  Rank 0's first warp
+//    detects global termination from every rank's (pending, sent, received) counters, see link_detector.
+//
 // Reads of the time field bypass L1 (ld.global.cg) since other SMs update it; 8-byte accesses do not
 // tear; values only ever decrease, so stale halo reads are harmless (the writer re-queues us).
 // Working set on model_24: 1.6 MB padded u8 layers + 13 MB padded f64 times -> L2 resident.
@@ -34,6 +40,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+
+#include <unistd.h>
 
 #include "ekg_internal.cuh"
 
@@ -90,7 +98,96 @@ __device__ __forceinline__ void brick_push(const BrickArgs& a, int b) {
 	}
 }
 
-template <int NBR>
+__device__ __forceinline__ unsigned long long global_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
+constexpr unsigned long long kLinkTimeoutNs = 12ull * 1000 * 1000 * 1000;   // a linked run that has not ended by then is aborted
+
+// Global termination of a linked run (Mattern's four-counter scheme plus an idle test).  A "message" is a brick queued in
+// another rank's ring.  The sender counts it in its own `sent` BEFORE the peer's `pending` goes up, and in the peer's
+// `received` AFTER that (link_push).  Rank 0's first warp reads (pending, sent, received) of every rank, lane r = rank r,
+// over and over; the run is over when a whole pass saw every rank idle (pending == 0, read before its `sent`) and the sum
+// of `sent` of this pass equals the sum of `received` of the PREVIOUS pass: then nothing was in flight when the previous
+// pass ended, nobody has sent since, and an idle rank only wakes up through a message.  The verdict is written into every
+// rank's counters[7]; waiting warps everywhere watch their own copy.
+__device__ void link_detector(const BrickArgs& a, int lane) {
+	constexpr unsigned kFull = 0xffffffffu;
+	const bool mine = lane < a.link.n_ranks;
+	volatile int* c = mine ? a.link.counters_of[lane] : nullptr;
+	unsigned r_prev = 0;
+	bool have_prev = false;
+	const unsigned long long t0 = global_ns();
+	for (;;) {
+		int pend = 0, gave_up = 0;
+		unsigned sent = 0, recv = 0;
+		if (mine) { pend = c[2]; gave_up = c[3]; }
+		__threadfence_system();
+		if (mine) sent = (unsigned)c[8];
+		__threadfence_system();
+		if (mine) recv = (unsigned)c[9];
+		const bool idle = __all_sync(kFull, pend == 0);
+		const bool broken = __any_sync(kFull, gave_up != 0);
+		const unsigned s_sum = __reduce_add_sync(kFull, sent), r_sum = __reduce_add_sync(kFull, recv);
+		int verdict = 0;
+		if (broken || global_ns() - t0 > kLinkTimeoutNs) verdict = 2;
+		else if (idle && have_prev && s_sum == r_prev) verdict = 1;
+		if (verdict) {
+			if (mine) c[7] = verdict;
+			__threadfence_system();
+			return;
+		}
+		r_prev = r_sum;
+		have_prev = true;
+		__nanosleep(400);
+	}
+}
+
+// the 27 bricks (3x3x3 around ours, bit (dz+1)*9 + (dy+1)*3 + (dx+1), 13 = ours) that hold a cell within one voxel of
+// the cell (cz, cy, cx) of our brick
+__device__ __forceinline__ unsigned reach27(int cz, int cy, int cx) {
+	const unsigned mz = (cz == 0 ? 1u : 0u) | 2u | (cz == kBrick - 1 ? 4u : 0u);
+	const unsigned my = (cy == 0 ? 1u : 0u) | 2u | (cy == kBrick - 1 ? 4u : 0u);
+	const unsigned mx = (cx == 0 ? 1u : 0u) | 2u | (cx == kBrick - 1 ? 4u : 0u);
+	const unsigned zs = ((mz & 1u) ? 0x1ffu : 0u) | ((mz & 2u) ? 0x1ffu << 9 : 0u) | ((mz & 4u) ? 0x1ffu << 18 : 0u);
+	const unsigned ys = (((my & 1u) ? 7u : 0u) | ((my & 2u) ? 7u << 3 : 0u) | ((my & 4u) ? 7u << 6 : 0u)) * ((1u << 18) | (1u << 9) | 1u);
+	const unsigned xs = mx * (((1u << 18) | (1u << 9) | 1u) * ((1u << 6) | (1u << 3) | 1u));
+	return zs & ys & xs;
+}
+
+// Queue, in the ring of the neighbouring rank whose brick state is `pstate`, those of its bricks among `reach` (reach27
+// bits relative to our brick b) that it relaxes.  Our improved times have been written to its grid and fenced before.
+__device__ __forceinline__ void link_push(const BrickArgs& a, int* pstate, unsigned reach, uint8_t owner, int b, int lane) {
+	constexpr unsigned kFull = 0xffffffffu;
+	int* pflag = pstate;
+	int* pring = pstate + 2 * (size_t)a.n_live;
+	int* pcnt = pring + (a.qmask + 1u);
+	int nb = -1;
+	if (lane < 27 && ((reach >> lane) & 1u)) {
+		nb = lane == 13 ? b : __ldg(a.nbr + (size_t)b * 26 + (lane > 13 ? lane - 1 : lane));
+		if (nb >= 0 && !(a.own[nb] & owner)) nb = -1;
+		if (nb >= 0 && atomicExch_system(pflag + nb, 1) != 0) nb = -1;   // already in its ring: whoever pops it reads our times
+	}
+	const unsigned pushers = __ballot_sync(kFull, nb >= 0);
+	const int n_push = __popc(pushers);
+	if (!n_push) return;
+	unsigned base = 0;
+	if (lane == 0) {
+		atomicAdd(a.counters + 8, n_push);                                      // sent -- before the work shows up over there
+		__threadfence_system();
+		atomicAdd_system(pcnt + 2, n_push);                                     // its pending: the rank is busy from here on
+		base = atomicAdd_system((unsigned*)pcnt + 1, (unsigned)n_push);         // its tail
+	}
+	base = __shfl_sync(kFull, base, 0);
+	if (nb >= 0) atomicExch_system(pring + ((base + __popc(pushers & ((1u << lane) - 1u))) & a.qmask), nb);
+	__threadfence_system();
+	__syncwarp();
+	if (lane == 0) atomicAdd_system(pcnt + 9, n_push);                          // received -- after its pending went up
+}
+
+template <int NBR, bool LINKED>
 __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(BrickArgs a) {
 	__shared__ double s_t_all[kBrickWarps][kBrickCells];
 	__shared__ uint8_t s_l_all[kBrickWarps][kBrickCells];
@@ -99,6 +196,10 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 	if (a.w_in_smem) {
 		for (int i = tid; i < a.nl1 * a.nl1 * 3; i += blockDim.x) s_w[i] = __ldg(a.wtab + i);
 		__syncthreads();
+	}
+	if (LINKED && a.link.rank == 0 && blockIdx.x == 0 && warp == 0) {   // no block-wide barrier below this line
+		link_detector(a, lane);
+		return;
 	}
 	const double* __restrict__ wt = a.w_in_smem ? s_w : a.wtab;
 	double* s_t = s_t_all[warp];
@@ -115,27 +216,39 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 	}
 	const double inf = __longlong_as_double(0x7ff0000000000000LL);
 	const int nl3 = a.nl1 * 3;
-	int visits = 0, sweeps = 0;
+	int visits = 0, sweeps = 0, remote_cells = 0;
 	volatile int* vq = a.queue;
 	volatile int* vpending = a.counters + 2;
 	volatile int* vstop = a.counters + 6;
+	volatile int* vverdict = a.counters + 7;
+	unsigned long long t_begin = 0;
+	if (LINKED) t_begin = global_ns();
 
 	for (;;) {   // one warp per brick, no barrier wider than the warp anywhere in here
 		int b = -1;
 		if (lane == 0) {
 			// bounded run: once `budget` ring positions have been claimed nobody claims another one; the bricks still
 			// flagged as queued are carried into the next relaxation by the host (flag[] is authoritative, the ring is rebuilt)
-			if (a.budget && (*(volatile unsigned*)a.counters >= a.budget || vstop[0])) { vstop[0] = 1; b = -2; }
+			if (!LINKED && a.budget && (*(volatile unsigned*)a.counters >= a.budget || vstop[0])) { vstop[0] = 1; b = -2; }
+			if (LINKED && vverdict[0]) b = -2;
 			const unsigned pos = b == -2 ? 0u : atomicAdd((unsigned*)a.counters + 0, 1u);   // head: claim a ring position
+			unsigned nap = 40;
 			for (unsigned spins = 0; b != -2; ++spins) {
 				b = vq[pos & a.qmask];
 				if (b >= 0) { vq[pos & a.qmask] = -1; break; }
-				if (*vpending == 0) { b = -2; break; }                       // nothing queued, nobody working: done
-				if (a.budget && vstop[0]) { b = -2; break; }                 // bounded run over: the producers have left
-				// a warp that found nothing for seconds retires (never spins forever, whatever happens);
-				// the host reports non-convergence if work was still pending when the last warp left
-				if (spins > (1u << 25)) { b = -2; break; }
-				__nanosleep(40);
+				if (LINKED) {
+					// an idle rank waits for work from its neighbours until rank 0 has seen every rank idle with nothing in flight
+					if (vverdict[0]) { b = -2; break; }
+					if ((spins & 255u) == 255u && global_ns() - t_begin > kLinkTimeoutNs) { atomicAdd(a.counters + 3, 1); b = -2; break; }
+					if (spins > 32u && nap < 1000u) nap += nap >> 2;          // long waits poll less often (<= 1 us)
+				} else {
+					if (*vpending == 0) { b = -2; break; }                       // nothing queued, nobody working: done
+					if (a.budget && vstop[0]) { b = -2; break; }                 // bounded run over: the producers have left
+					// a warp that found nothing for seconds retires (never spins forever, whatever happens);
+					// the host reports non-convergence if work was still pending when the last warp left
+					if (spins > (1u << 25)) { b = -2; break; }
+				}
+				__nanosleep(nap);
 			}
 		}
 		b = __shfl_sync(kFull, b, 0);
@@ -187,15 +300,29 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 		// Write back what improved (atomicMin on the bit pattern: positive doubles order like integers, and
 		// two warps may hold the same brick at once).  Queue a neighbouring brick only if one of ITS cells
 		// (our halo copy of it, never smaller than its current value) would improve through a changed voxel.
-		unsigned bits = 0;
+		unsigned bits = 0, reach_dn = 0, reach_up = 0;
+		int vz0 = 0;
+		if (LINKED) vz0 = (int)(origin / a.link.plane) - 1;   // voxel plane of the brick's first cell
 #pragma unroll
 		for (int o = 0; o < kOwn; ++o) {
 			const double tf = s_t[loc[o]];
 			if (lv[o] == 0) continue;
 			const bool improved = tf < t_init[o];
-			if (improved)
-				atomicMin((unsigned long long*)(a.time + origin + (uint32_t)((cz[o] * a.pY + cy[o]) * a.pX + cx[o])),
-				          (unsigned long long)__double_as_longlong(tf));
+			if (improved) {
+				const uint32_t p = origin + (uint32_t)((cz[o] * a.pY + cy[o]) * a.pX + cx[o]);
+				atomicMin((unsigned long long*)(a.time + p), (unsigned long long)__double_as_longlong(tf));
+				if (LINKED) {
+					// our first / last own plane is the halo of the rank below / above: the value goes straight into its grid, and
+					// ITS bricks around the cell get a visit (we cannot test its cells' values from here, so all that can see it)
+					const int z = vz0 + cz[o];
+					const bool dn = z == a.link.z_first && a.link.time_dn != nullptr, up = z == a.link.z_last && a.link.time_up != nullptr;
+					if (dn | up) {
+						const unsigned r27 = reach27(cz[o], cy[o], cx[o]);
+						if (dn) { atomicMin_system((unsigned long long*)(a.link.time_dn + p), (unsigned long long)__double_as_longlong(tf)); reach_dn |= r27; ++remote_cells; }
+						if (up) { atomicMin_system((unsigned long long*)(a.link.time_up + p), (unsigned long long)__double_as_longlong(tf)); reach_up |= r27; ++remote_cells; }
+					}
+				}
+			}
 			const bool on_face = cz[o] == 0 || cz[o] == kBrick - 1 || cy[o] == 0 || cy[o] == kBrick - 1 || cx[o] == 0 || cx[o] == kBrick - 1;
 			if (!on_face || !(improved || (first && tf < inf))) continue;
 #pragma unroll
@@ -216,19 +343,30 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 			}
 		}
 		bits = __reduce_or_sync(kFull, bits);
+		if (LINKED) {
+			reach_dn = __reduce_or_sync(kFull, reach_dn);
+			reach_up = __reduce_or_sync(kFull, reach_up);
+			if (reach_dn | reach_up) {
+				__threadfence_system();   // our times are in the neighbours' grids before their bricks are told to look
+				__syncwarp();
+				if (reach_dn) link_push(a, a.link.state_dn, reach_dn, kOwnBelow, b, lane);
+				if (reach_up) link_push(a, a.link.state_up, reach_up, kOwnAbove, b, lane);
+			}
+		}
 		__threadfence();   // our improved times are visible before anyone is told to look at them
 		// push the neighbours that need a visit: one tail reservation and one pending update per warp
 		// (head, tail and pending are single hot addresses; per-brick atomics on them would serialise)
 		int nb = -1;
 		if (lane < 26 && ((bits >> lane) & 1u)) {
 			nb = __ldg(a.nbr + (size_t)b * 26 + lane);
-			if (nb >= 0 && a.own && !a.own[nb]) nb = -1;               // sharded run: another rank relaxes that brick
+			if (nb >= 0 && a.own && !(a.own[nb] & kOwnMe)) nb = -1;    // sharded run: another rank relaxes that brick
 			if (nb >= 0 && atomicExch(a.flag + nb, 1) != 0) nb = -1;   // already queued
 		}
 		const unsigned pushers = __ballot_sync(kFull, nb >= 0);
 		const int n_push = __popc(pushers);
 		unsigned base = 0;
 		if (lane == 0) {
+			// (linked run: this is where our brick stops counting as work -- after everything it caused elsewhere is accounted for)
 			if (n_push != 1) atomicAdd(a.counters + 2, n_push - 1);        // pending += pushes - (this brick done)
 			if (n_push) base = atomicAdd((unsigned*)a.counters + 1, (unsigned)n_push);
 		}
@@ -236,6 +374,10 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 		if (nb >= 0) atomicExch(a.queue + ((base + __popc(pushers & ((1u << lane) - 1u))) & a.qmask), nb);
 	}
 	if (lane == 0 && visits) { atomicAdd(a.counters + 4, visits); atomicAdd(a.counters + 5, sweeps); }
+	if (LINKED) {
+		remote_cells = __reduce_add_sync(kFull, remote_cells);
+		if (lane == 0 && remote_cells) atomicAdd(a.counters + 10, remote_cells);
+	}
 }
 
 // Negative weights would make "tu >= best -> skip" wrong and Dijkstra itself ill-defined; the
@@ -329,8 +471,8 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
 	const int64_t cap = ring_capacity(n);
-	// state = flag[n] | first_visit[n] | ring[cap] | counters[8]   (allocated as 5n + 8 ints; cap <= 2n)
-	std::vector<int> h((size_t)(2 * n + cap + 8), 0);
+	// state = flag[n] | first_visit[n] | ring[cap] | counters[kBrickCounters]   (allocated as 5n + 32 ints; cap <= max(2n, 2))
+	std::vector<int> h((size_t)(2 * n + cap + kBrickCounters), 0);
 	std::fill(h.begin() + 2 * n, h.begin() + 2 * n + cap, -1);
 	int n0 = 0;
 	for (int32_t b : m->h_start_bricks) { h[(size_t)b] = 1; h[(size_t)(n + b)] = 1; h[(size_t)(2 * n + n0++)] = b; }
@@ -341,17 +483,15 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	return launch_bricks(m, nullptr, rounds_out);
 }
 
-// the frontier kernel over whatever the ring holds; d_own restricts the pushes (sharded run)
-static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out, int64_t budget, int64_t* leftover_out) {
-	cudaStream_t st = m->stream;
+// kernel arguments of the frontier kernel for this model (the link part stays zeroed)
+static void fill_brick_args(ekg_model* m, const uint8_t* d_own, int64_t budget, BrickArgs& a) {
 	const int64_t n = m->n_bricks;
 	const int64_t cap = ring_capacity(n);
 	int* flag = m->d_brick_state;
 	int* first = flag + n;
 	int* ring = first + n;
 	int* counters = ring + cap;
-
-	BrickArgs a{};
+	a = BrickArgs{};
 	a.layer = m->d_layer_pad; a.time = m->d_time_pad; a.wtab = m->d_wtab;
 	a.origin = m->d_brick_origin; a.nbr = m->d_brick_nbr; a.own = d_own;
 	a.flag = flag; a.first_visit = first; a.queue = ring; a.counters = counters; a.qmask = (uint32_t)(cap - 1);
@@ -367,18 +507,26 @@ static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out
 	}
 	const size_t w_bytes = (size_t)a.nl1 * a.nl1 * 3 * sizeof(double);
 	a.w_in_smem = w_bytes <= 32 * 1024;
-	const size_t dyn = a.w_in_smem ? w_bytes : 0;
+}
+
+// the frontier kernel over whatever the ring holds; d_own restricts the pushes (sharded run)
+static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out, int64_t budget, int64_t* leftover_out) {
+	cudaStream_t st = m->stream;
+	const int64_t n = m->n_bricks;
+	BrickArgs a;
+	fill_brick_args(m, d_own, budget, a);
+	const size_t dyn = a.w_in_smem ? (size_t)a.nl1 * a.nl1 * 3 * sizeof(double) : 0;
 	int per_sm = 0;
 	const int threads = 32 * kBrickWarps;
-	void* kfun = a.n_nbr == 26 ? (void*)automaton_brick_kernel<26> : (void*)automaton_brick_kernel<8>;
+	void* kfun = a.n_nbr == 26 ? (void*)automaton_brick_kernel<26, false> : (void*)automaton_brick_kernel<8, false>;
 	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
 	// every CTA must be resident (waiting warps spin on the ring): never launch more than fit
 	const int grid = (int)std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>((n + kBrickWarps - 1) / kBrickWarps, 1));
 	void* kargs[] = {&a};
 	EKG_CUDA(cudaLaunchCooperativeKernel(kfun, dim3(grid), dim3(threads), kargs, dyn, st));
-	int hc[8] = {0};
-	EKG_CUDA(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+	int hc[kBrickCounters] = {0};
+	EKG_CUDA(cudaMemcpyAsync(hc, a.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
 	EKG_CUDA(cudaStreamSynchronize(st));
 	if (rounds_out) *rounds_out = hc[4];   // brick visits (there are no global rounds in the work-queue scheme)
 	m->last_brick_visits = hc[4];
@@ -412,7 +560,7 @@ __global__ void shard_merge_kernel(double* __restrict__ time, const double* __re
 		const int cz = z + dz, cy = y + dy, cx = x + dx;
 		if (cz < 0 || cz >= Z || cy < 0 || cy >= Y || cx < 0 || cx >= X) continue;
 		const int32_t b = bindex[((int64_t)(cz / kBrick) * bY + cy / kBrick) * bX + cx / kBrick];
-		if (b >= 0 && own[b]) mark[b] = 1;
+		if (b >= 0 && (own[b] & kOwnMe)) mark[b] = 1;
 	}
 }
 
@@ -429,18 +577,63 @@ __global__ void shard_enqueue_kernel(int* __restrict__ mark, int n_live, int* __
 	atomicAdd(counters + 2, 1);
 }
 
-__global__ void shard_own_kernel(const uint32_t* __restrict__ origin, int n_live, int64_t plane, int64_t z0, int64_t z1, uint8_t* __restrict__ own,
-                                 int* __restrict__ mark) {
+// which ranks relax brick b: ours if it intersects our slab [z0, z1), the rank below / above if it intersects theirs
+// ([b0, b1) / [a0, a1), empty ranges without a linked neighbour)
+__global__ void shard_own_kernel(const uint32_t* __restrict__ origin, int n_live, int64_t plane, int64_t z0, int64_t z1, int64_t b0, int64_t b1,
+                                 int64_t a0, int64_t a1, uint8_t* __restrict__ own, int* __restrict__ mark) {
 	const int b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= n_live) return;
 	const int64_t z = (int64_t)origin[b] / plane - 1;   // first voxel plane of the brick
-	own[b] = (z < z1 && z + kBrick > z0) ? 1 : 0;
+	own[b] = (uint8_t)(((z < z1 && z + kBrick > z0) ? kOwnMe : 0) | ((z < b1 && z + kBrick > b0) ? kOwnBelow : 0) | ((z < a1 && z + kBrick > a0) ? kOwnAbove : 0));
 	mark[b] = 0;
+}
+
+// our bricks that can see a start voxel (its own brick and those that have it in their halo) are queued at the start
+__global__ void shard_mark_starts_kernel(const uint32_t* __restrict__ starts, int n, int pY, int pX, int Z, int Y, int X,
+                                         const int32_t* __restrict__ bindex, int bY, int bX, const uint8_t* __restrict__ own, int* __restrict__ mark) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t p = starts[i];
+	const int z = (int)(p / ((uint32_t)pY * pX)) - 1, y = (int)((p / pX) % pY) - 1, x = (int)(p % pX) - 1;
+	for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+		const int cz = z + dz, cy = y + dy, cx = x + dx;
+		if (cz < 0 || cz >= Z || cy < 0 || cy >= Y || cx < 0 || cx >= X) continue;
+		const int32_t b = bindex[((int64_t)(cz / kBrick) * bY + cy / kBrick) * bX + cx / kBrick];
+		if (b >= 0 && (own[b] & kOwnMe)) mark[b] = 1;
+	}
 }
 
 static int shard_check(ekg_model* m) {
 	if (m->h_starts.empty()) return fail(EKG_E_NO_START, "Could not find starting point for excitation sequence");
 	if (m->n_layers >= m->t_cols || m->n_layers >= m->t_rows) return fail(EKG_E_TRANSFER, "transfer (conduction) matrix does not define every layer");
+	return EKG_OK;
+}
+
+// bricks a bounded relaxation left flagged as queued -> marked for the next one
+__global__ void shard_carry_kernel(const int* __restrict__ flag, int* __restrict__ mark, int n_live) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b < n_live && flag[b]) mark[b] = 1;
+}
+
+// ring, flags and counters rebuilt from the marked bricks (asynchronous on the model's stream)
+static int shard_fill_ring(ekg_model* m) {
+	cudaStream_t st = m->stream;
+	const int64_t n = m->n_bricks;
+	const int64_t cap = ring_capacity(n);
+	int* flag = m->d_brick_state;
+	int* ring = flag + 2 * n;
+	int* counters = ring + cap;
+	if (n > 0) {
+		shard_carry_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(flag, m->d_brick_mark, (int)n);
+		EKG_CUDA(cudaGetLastError());
+		EKG_CUDA(cudaMemsetAsync(flag, 0, (size_t)(2 * n) * sizeof(int), st));
+	}
+	EKG_CUDA(cudaMemsetAsync(ring, 0xff, (size_t)cap * sizeof(int), st));   // -1 = empty slot
+	EKG_CUDA(cudaMemsetAsync(counters, 0, kBrickCounters * sizeof(int), st));
+	if (n > 0) {
+		shard_enqueue_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_brick_mark, (int)n, flag, flag + n, ring, counters, (uint32_t)(cap - 1));
+		EKG_CUDA(cudaGetLastError());
+	}
 	return EKG_OK;
 }
 
@@ -455,17 +648,19 @@ int shard_begin(ekg_model* m) {
 		EKG_CUDA(cudaMalloc(&m->d_brick_mark, nn * sizeof(int)));
 		EKG_CUDA(cudaMalloc(&m->d_improved, sizeof(unsigned long long)));
 	}
-	// bricks that intersect the slab [slab_z0, slab_z1) (brick bz covers the voxel planes [4 bz, 4 bz + 4)); of those, the
-	// bricks of the start voxels are queued
+	// bricks that intersect the slab [slab_z0, slab_z1) (brick bz covers the voxel planes [4 bz, 4 bz + 4)), and -- linked run --
+	// the slabs of the neighbouring ranks
+	int64_t nb0 = 0, nb1 = 0, na0 = 0, na1 = 0;
+	if (m->link.active) {
+		if (m->link.slabs[2 * (size_t)m->link.rank] != m->slab_z0 || m->link.slabs[2 * (size_t)m->link.rank + 1] != m->slab_z1)
+			return fail(EKG_E_STATE, "the slab has changed since ekg_model_activation_link");
+		if (m->link.below >= 0) { nb0 = m->link.slabs[2 * (size_t)m->link.below]; nb1 = m->link.slabs[2 * (size_t)m->link.below + 1]; }
+		if (m->link.above >= 0) { na0 = m->link.slabs[2 * (size_t)m->link.above]; na1 = m->link.slabs[2 * (size_t)m->link.above + 1]; }
+	}
 	if (n > 0) {
-		shard_own_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_brick_origin, (int)n, m->pY * m->pX, m->slab_z0, m->slab_z1, m->d_brick_own, m->d_brick_mark);
+		shard_own_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_brick_origin, (int)n, m->pY * m->pX, m->slab_z0, m->slab_z1, nb0, nb1, na0, na1,
+		                                                        m->d_brick_own, m->d_brick_mark);
 		EKG_CUDA(cudaGetLastError());
-		static const int one = 1;
-		for (size_t i = 0; i < m->h_start_bricks.size(); ++i) {
-			const int64_t bz = m->h_start_brick_bz[i];
-			if (bz * kBrick < m->slab_z1 && (bz + 1) * kBrick > m->slab_z0)
-				EKG_CUDA(cudaMemcpyAsync(m->d_brick_mark + m->h_start_bricks[i], &one, sizeof(int), cudaMemcpyHostToDevice, st));
-		}
 	}
 	const int64_t npad = m->pZ * m->pY * m->pX;
 	init_time_kernel<<<m->sm_count * 4, 256, 0, st>>>(m->d_time_pad, npad);
@@ -482,19 +677,23 @@ int shard_begin(ekg_model* m) {
 	EKG_CUDA(cudaMemcpyAsync(d_starts, h_starts.data(), h_starts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 	set_start_kernel<<<(int)((h_starts.size() + 127) / 128), 128, 0, st>>>(m->d_time_pad, d_starts, (int)h_starts.size());
 	EKG_CUDA(cudaGetLastError());
+	if (n > 0) {
+		shard_mark_starts_kernel<<<(int)((h_starts.size() + 127) / 128), 128, 0, st>>>(d_starts, (int)h_starts.size(), (int)m->pY, (int)m->pX, (int)m->Z,
+		                                                                                (int)m->Y, (int)m->X, m->d_brick_index, (int)m->bY, (int)m->bX,
+		                                                                                m->d_brick_own, m->d_brick_mark);
+		EKG_CUDA(cudaGetLastError());
+	}
 	EKG_CUDA(cudaStreamSynchronize(st));  // pageable sources
 	EKG_CUDA(cudaFree(d_starts));
 	if (n > 0) EKG_CUDA(cudaMemsetAsync(m->d_brick_state, 0, (size_t)(2 * n) * sizeof(int), st));   // flags: nothing carried over
-	EKG_CUDA(cudaStreamSynchronize(st));
 	m->have_activation = false;
 	m->shard_active = true;
+	m->link.launched = false;
+	// linked run: the neighbours write into our ring as soon as their kernels run, so it is made ready here -- the caller
+	// puts a barrier over all ranks between this call and ekg_model_activation_linked_launch
+	if (m->link.active) { int rc2 = shard_fill_ring(m); if (rc2) return rc2; }
+	EKG_CUDA(cudaStreamSynchronize(st));
 	return EKG_OK;
-}
-
-// bricks a bounded relaxation left flagged as queued -> marked for the next one
-__global__ void shard_carry_kernel(const int* __restrict__ flag, int* __restrict__ mark, int n_live) {
-	const int b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b < n_live && flag[b]) mark[b] = 1;
 }
 
 // max_visits > 0 bounds the relaxation (the wave is handed to the neighbouring slabs before this slab has reached its
@@ -506,17 +705,8 @@ int shard_relax(ekg_model* m, int64_t max_visits, int64_t* visits_out, int64_t* 
 	if (leftover_out) *leftover_out = 0;
 	if (m->merge_pending) { EKG_CUDA(cudaStreamSynchronize(m->merge_stream)); m->merge_pending = false; }   // asynchronous merges have landed
 	if (n == 0) { if (visits_out) *visits_out = 0; return EKG_OK; }
-	const int64_t cap = ring_capacity(n);
-	int* flag = m->d_brick_state;
-	int* ring = flag + 2 * n;
-	int* counters = ring + cap;
-	shard_carry_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(flag, m->d_brick_mark, (int)n);
-	EKG_CUDA(cudaGetLastError());
-	EKG_CUDA(cudaMemsetAsync(flag, 0, (size_t)(2 * n) * sizeof(int), st));
-	EKG_CUDA(cudaMemsetAsync(ring, 0xff, (size_t)cap * sizeof(int), st));   // -1 = empty slot
-	EKG_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(int), st));
-	shard_enqueue_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_brick_mark, (int)n, flag, flag + n, ring, counters, (uint32_t)(cap - 1));
-	EKG_CUDA(cudaGetLastError());
+	int rc0 = shard_fill_ring(m);
+	if (rc0) return rc0;
 	int64_t left = 0;
 	int rc = launch_bricks(m, m->d_brick_own, visits_out, max_visits, &left);
 	if (rc) return rc;
@@ -564,6 +754,191 @@ int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_pl
 		}
 	}
 	if (improved_out) *improved_out = (int64_t)h;
+	return EKG_OK;
+}
+
+// ---- peer-linked sharded automaton ------------------------------------------------------------------------------
+// The ranks of a z-slab sharded model exchange their slab-face planes from inside the frontier kernel (see
+// automaton_brick_kernel<.., LINKED>).  For that every rank maps the other ranks' time grids and brick states: raw
+// pointers + cudaDeviceEnablePeerAccess when the handles live in one process (one host thread per device), CUDA IPC
+// handles between processes (one process per GPU, the torch.distributed layout).  The exchange needs native 64-bit
+// atomics between the devices (NVLink); ekg_model_activation_link refuses anything else and the caller falls back to the
+// host-driven rounds (ekg_model_activation_relax / _export / _merge).
+struct LinkInfo {
+	uint64_t magic;
+	int64_t pid;
+	int32_t device, ipc_ok;
+	uint64_t time_ptr, state_ptr;
+	int64_t n_bricks, npad;
+	cudaIpcMemHandle_t time_h, state_h;
+};
+static_assert(sizeof(LinkInfo) <= EKG_LINK_INFO_BYTES, "EKG_LINK_INFO_BYTES too small");
+constexpr uint64_t kLinkMagic = 0x454b474c494e4b31ull;   // "EKGLINK1"
+
+static int64_t this_pid() { return (int64_t)getpid(); }
+
+int shard_link_info(ekg_model* m, void* info_out) {
+	LinkInfo li;
+	memset(&li, 0, sizeof li);
+	li.magic = kLinkMagic;
+	li.pid = this_pid();
+	li.device = m->device;
+	li.time_ptr = (uint64_t)(uintptr_t)m->d_time_pad;
+	li.state_ptr = (uint64_t)(uintptr_t)m->d_brick_state;
+	li.n_bricks = m->n_bricks;
+	li.npad = m->pZ * m->pY * m->pX;
+	li.ipc_ok = cudaIpcGetMemHandle(&li.time_h, m->d_time_pad) == cudaSuccess && cudaIpcGetMemHandle(&li.state_h, m->d_brick_state) == cudaSuccess;
+	if (!li.ipc_ok) cudaGetLastError();   // same-process links do not need the handles
+	memset(info_out, 0, EKG_LINK_INFO_BYTES);
+	memcpy(info_out, &li, sizeof li);
+	return EKG_OK;
+}
+
+int shard_unlink(ekg_model* m) {
+	if (m->link.launched) { cudaStreamSynchronize(m->stream); m->link.launched = false; }
+	for (void* p : m->link.ipc_opened) cudaIpcCloseMemHandle(p);
+	if (m->link.ev0) cudaEventDestroy(m->link.ev0);
+	if (m->link.ev1) cudaEventDestroy(m->link.ev1);
+	m->link = ekg_model::PeerLink();
+	return EKG_OK;
+}
+
+int shard_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int64_t* slabs) {
+	if (n_ranks < 1 || n_ranks > kMaxLinkRanks || rank < 0 || rank >= n_ranks) return fail(EKG_E_INVALID, "bad rank / number of ranks (at most 16)");
+	shard_unlink(m);
+	ekg_model::PeerLink L;
+	L.rank = rank; L.n_ranks = n_ranks;
+	L.slabs.assign(slabs, slabs + 2 * n_ranks);
+	for (int r = 0; r < n_ranks; ++r) {
+		if (slabs[2 * r] < 0 || slabs[2 * r + 1] > m->Z || slabs[2 * r] > slabs[2 * r + 1]) return fail(EKG_E_INVALID, "bad slab");
+		if (r > 0 && slabs[2 * r] != slabs[2 * r - 1]) return fail(EKG_E_INVALID, "slabs must partition [0, Z) in rank order");
+	}
+	if (slabs[0] != 0 || slabs[2 * n_ranks - 1] != m->Z) return fail(EKG_E_INVALID, "slabs must partition [0, Z) in rank order");
+	if (slabs[2 * rank] != m->slab_z0 || slabs[2 * rank + 1] != m->slab_z1) return fail(EKG_E_STATE, "ekg_model_set_slab has not been called with this rank's slab");
+	const bool live = slabs[2 * rank + 1] > slabs[2 * rank];
+	for (int r = rank - 1; r >= 0 && live; --r) if (slabs[2 * r + 1] > slabs[2 * r]) { L.below = r; break; }
+	for (int r = rank + 1; r < n_ranks && live; ++r) if (slabs[2 * r + 1] > slabs[2 * r]) { L.above = r; break; }
+	L.time.assign((size_t)n_ranks, nullptr);
+	L.state.assign((size_t)n_ranks, nullptr);
+	auto bail = [&](int code, const std::string& msg) { for (void* p : L.ipc_opened) cudaIpcCloseMemHandle(p); return fail(code, msg); };
+	for (int r = 0; r < n_ranks; ++r) {
+		LinkInfo p;
+		memcpy(&p, (const char*)infos + (size_t)r * EKG_LINK_INFO_BYTES, sizeof p);
+		if (p.magic != kLinkMagic) return bail(EKG_E_INVALID, "not a link info record");
+		if (p.n_bricks != m->n_bricks || p.npad != m->pZ * m->pY * m->pX) return bail(EKG_E_INVALID, "the ranks hold different models");
+		if (r == rank) { L.time[(size_t)r] = m->d_time_pad; L.state[(size_t)r] = m->d_brick_state; continue; }
+		if (p.device != m->device || p.pid != this_pid()) {
+			int can = 0, native = 0;
+			int peer_dev = p.device;
+			if (p.device != m->device) {
+				cudaDeviceCanAccessPeer(&can, m->device, peer_dev);
+				if (can) cudaDeviceGetP2PAttribute(&native, cudaDevP2PAttrNativeAtomicSupported, m->device, peer_dev);
+				if (!can || !native) return bail(EKG_E_UNSUPPORTED, "no peer access with native atomics between the devices (the linked automaton needs NVLink)");
+			}
+		}
+		if (p.pid == this_pid()) {
+			if (p.device != m->device) {
+				cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(EKG_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+				cudaGetLastError();
+			}
+			L.time[(size_t)r] = (double*)(uintptr_t)p.time_ptr;
+			L.state[(size_t)r] = (int*)(uintptr_t)p.state_ptr;
+		} else {
+			if (!p.ipc_ok) return bail(EKG_E_UNSUPPORTED, "the peer could not export CUDA IPC handles");
+			void *tp = nullptr, *sp = nullptr;
+			cudaError_t e = cudaIpcOpenMemHandle(&tp, p.time_h, cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) { cudaGetLastError(); return bail(EKG_E_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+			L.ipc_opened.push_back(tp);
+			e = cudaIpcOpenMemHandle(&sp, p.state_h, cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) { cudaGetLastError(); return bail(EKG_E_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+			L.ipc_opened.push_back(sp);
+			L.time[(size_t)r] = (double*)tp;
+			L.state[(size_t)r] = (int*)sp;
+		}
+	}
+	L.active = true;
+	if (cudaEventCreate(&L.ev0) != cudaSuccess || cudaEventCreate(&L.ev1) != cudaSuccess) return bail(EKG_E_CUDA, "cudaEventCreate failed");
+	m->link = L;
+	return EKG_OK;
+}
+
+// Launches the linked frontier kernel and returns at once; all ranks must have passed ekg_model_activation_begin (a
+// barrier is the caller's job).  max_ctas > 0 caps the grid: ranks that share ONE device (tests) must all be resident
+// at the same time, idle ranks wait for their neighbours inside the kernel.
+int shard_linked_launch(ekg_model* m, int max_ctas) {
+	if (!m->link.active) return fail(EKG_E_STATE, "ekg_model_activation_link has not been called");
+	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
+	if (m->link.launched) return fail(EKG_E_STATE, "the linked automaton is already running");
+	cudaStream_t st = m->stream;
+	const int64_t n = m->n_bricks;
+	const int64_t cap = ring_capacity(n);
+	BrickArgs a;
+	fill_brick_args(m, m->d_brick_own, 0, a);
+	const ekg_model::PeerLink& L = m->link;
+	a.link.rank = L.rank; a.link.n_ranks = L.n_ranks;
+	a.link.z_first = (int32_t)m->slab_z0; a.link.z_last = (int32_t)m->slab_z1 - 1;
+	a.link.plane = (uint32_t)(m->pY * m->pX);
+	if (L.below >= 0) { a.link.time_dn = L.time[(size_t)L.below]; a.link.state_dn = L.state[(size_t)L.below]; }
+	if (L.above >= 0) { a.link.time_up = L.time[(size_t)L.above]; a.link.state_up = L.state[(size_t)L.above]; }
+	for (int r = 0; r < L.n_ranks; ++r) a.link.counters_of[r] = L.state[(size_t)r] + 2 * n + cap;
+	const size_t dyn = a.w_in_smem ? (size_t)a.nl1 * a.nl1 * 3 * sizeof(double) : 0;
+	int per_sm = 0;
+	const int threads = 32 * kBrickWarps;
+	void* kfun = a.n_nbr == 26 ? (void*)automaton_brick_kernel<26, true> : (void*)automaton_brick_kernel<8, true>;
+	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
+	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
+	// our own bricks bound the useful grid (a slab is ~1/N of the model); rank 0 gives one warp to the detector
+	int64_t grid = std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>((n + kBrickWarps - 1) / kBrickWarps, 1) + 1);
+	if (max_ctas > 0) grid = std::min<int64_t>(grid, max_ctas);
+	void* kargs[] = {&a};
+	EKG_CUDA(cudaEventRecord(L.ev0, st));
+	EKG_CUDA(cudaLaunchKernel(kfun, dim3((unsigned)grid), dim3(threads), kargs, dyn, st));
+	EKG_CUDA(cudaEventRecord(L.ev1, st));
+	m->link.launched = true;
+	return EKG_OK;
+}
+
+int shard_linked_wait(ekg_model* m, int64_t* visits_out, int64_t* remote_out) {
+	if (!m->link.launched) return fail(EKG_E_STATE, "ekg_model_activation_linked_launch has not been called");
+	cudaStream_t st = m->stream;
+	const int64_t n = m->n_bricks;
+	int* counters = m->d_brick_state + 2 * n + ring_capacity(n);
+	int hc[kBrickCounters] = {0};
+	m->link.launched = false;
+	EKG_CUDA(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+	EKG_CUDA(cudaStreamSynchronize(st));
+	cudaEventElapsedTime(&m->link.kernel_ms, m->link.ev0, m->link.ev1);
+	m->activation_ms = m->link.kernel_ms;
+	m->last_brick_visits = hc[4];
+	if (visits_out) *visits_out = hc[4];
+	if (remote_out) { remote_out[0] = (unsigned)hc[8]; remote_out[1] = (unsigned)hc[9]; remote_out[2] = (unsigned)hc[10]; }
+	if (getenv("EKGSIM_B200_DEBUG"))
+		fprintf(stderr, "linked automaton rank %d: visits %d inner sweeps %d, bricks queued elsewhere %u / here by others %u, cells written to neighbours %d, verdict %d, %.3f ms\n",
+		        m->link.rank, hc[4], hc[5], (unsigned)hc[8], (unsigned)hc[9], hc[10], hc[7], m->link.kernel_ms);
+	if (hc[7] != 1 || hc[2] != 0) {
+		char buf[160];
+		snprintf(buf, sizeof buf, "linked activation automaton did not terminate cleanly (verdict %d, %d bricks pending, %d warps gave up)", hc[7], hc[2], hc[3]);
+		return fail(EKG_E_STATE, buf);
+	}
+	return EKG_OK;
+}
+
+// After every rank's kernel has ended (barrier: the caller's job) the slabs of the other ranks are pulled over the links,
+// so that every rank holds the whole map like after ekg_model_activation.
+int shard_linked_gather(ekg_model* m) {
+	if (!m->link.active) return fail(EKG_E_STATE, "ekg_model_activation_link has not been called");
+	if (m->link.launched) return fail(EKG_E_STATE, "the linked automaton is still running (ekg_model_activation_linked_wait)");
+	const int64_t plane = m->pY * m->pX;
+	// rank r starts with rank r + 1: at any moment every source is read by one rank only (its NVLink egress is the limit)
+	for (int i = 1; i < m->link.n_ranks; ++i) {
+		const int r = (m->link.rank + i) % m->link.n_ranks;
+		const int64_t z0 = m->link.slabs[2 * (size_t)r], z1 = m->link.slabs[2 * (size_t)r + 1];
+		if (z1 <= z0) continue;
+		const size_t off = (size_t)((z0 + 1) * plane), cnt = (size_t)((z1 - z0) * plane);
+		EKG_CUDA(cudaMemcpyAsync(m->d_time_pad + off, m->link.time[(size_t)r] + off, cnt * sizeof(double), cudaMemcpyDefault, m->stream));
+	}
+	EKG_CUDA(cudaStreamSynchronize(m->stream));
 	return EKG_OK;
 }
 

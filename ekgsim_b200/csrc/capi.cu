@@ -68,6 +68,7 @@ static int64_t pad_index(const ekg_model* m, int64_t z, int64_t y, int64_t x) { 
 static void free_model(ekg_model* m) {
 	if (!m) return;
 	cudaSetDevice(m->device);
+	shard_unlink(m);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
 	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_tail, m->d_ftab, m->d_times, m->d_partial, m->d_partial2, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_lmom, m->d_near, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
 	for (void* p : ptrs) if (p) cudaFree(p);
@@ -619,8 +620,8 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		m->n_bricks = nb;
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_origin, (size_t)std::max<int64_t>(nb, 1) * 4));
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_nbr, (size_t)std::max<int64_t>(nb, 1) * 26 * 4));
-		// flag[n] | first_visit[n] | ring[capacity <= max(2n, 2)] | counters[8]   (automaton.cu, run_automaton_bricks)
-		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, ((size_t)nb * 5 + 16) * sizeof(int)));
+		// flag[n] | first_visit[n] | ring[capacity <= max(2n, 2)] | counters[kBrickCounters]   (automaton.cu, run_automaton_bricks)
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, ((size_t)nb * 5 + 32) * sizeof(int)));
 		brick_index_kernel<<<cb, 256, 0, st>>>(d_live, d_scan, n_cells, (int)bY, (int)bX, m->pY, m->pX, m->d_brick_index, m->d_brick_origin);
 		EKG_CREATE_CUDA(cudaGetLastError());
 		brick_nbr_kernel<<<cb, 256, 0, st>>>(m->d_brick_index, n_cells, (int)bZ, (int)bY, (int)bX, m->d_brick_nbr);
@@ -745,6 +746,43 @@ int ekg_model_activation_end(ekg_model* m, double* delay_out) {
 	if (rc) return rc;
 	if (delay_out) return download_activation(m, delay_out);
 	return EKG_OK;
+}
+
+// ---- peer-linked sharded automaton (automaton.cu) --------------------------------------------------------------
+int ekg_model_activation_link_info(ekg_model* m, void* info_out) {
+	if (!m || !info_out) return fail(EKG_E_INVALID, "NULL argument");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_link_info(m, info_out);
+}
+
+int ekg_model_activation_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int64_t* slabs) {
+	if (!m || !infos || !slabs) return fail(EKG_E_INVALID, "NULL argument");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_link(m, rank, n_ranks, infos, slabs);
+}
+
+int ekg_model_activation_linked_launch(ekg_model* m, int max_ctas) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_linked_launch(m, max_ctas);
+}
+
+int ekg_model_activation_linked_wait(ekg_model* m, int64_t* brick_visits_out, int64_t* remote_out) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_linked_wait(m, brick_visits_out, remote_out);
+}
+
+int ekg_model_activation_linked_gather(ekg_model* m) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_linked_gather(m);
+}
+
+int ekg_model_activation_unlink(ekg_model* m) {
+	if (!m) return fail(EKG_E_INVALID, "model is NULL");
+	EKG_CUDA(cudaSetDevice(m->device));
+	return shard_unlink(m);
 }
 
 int ekg_model_set_activation(ekg_model* m, const double* delay) {

@@ -111,6 +111,23 @@ constexpr int kBrickHalo = kBrick + 2;                                // 6
 constexpr int kBrickCells = kBrickHalo * kBrickHalo * kBrickHalo;    // 216 (brick + one-voxel halo)
 constexpr int kBrickWarps = 8;                                        // bricks in flight per CTA
 
+// Linked run (automaton.cu, "peer-linked sharded automaton"): the ranks of a z-slab sharded model write the planes at their
+// slab faces straight into the neighbouring ranks' grids and queue the neighbours' bricks in the neighbours' rings, from
+// inside the frontier kernel, through peer-mapped memory (NVLink); rank 0 detects global termination.
+constexpr int kMaxLinkRanks = 16;
+constexpr int kBrickCounters = 16;   // ints behind the ring, see BrickArgs::counters
+constexpr uint8_t kOwnMe = 1, kOwnBelow = 2, kOwnAbove = 4;
+struct BrickLink {
+	double* time_dn;         // padded time grid of the rank below (same layout as ours), NULL = none
+	double* time_up;
+	int* state_dn;           // its brick state: flag[n] | first_visit[n] | ring[qmask + 1] | counters[kBrickCounters]
+	int* state_up;
+	int* counters_of[kMaxLinkRanks];   // every rank's counters (only rank 0, the termination detector, reads them)
+	int32_t rank, n_ranks;
+	int32_t z_first, z_last; // our first and last own voxel plane (unpadded z)
+	uint32_t plane;          // pY * pX
+};
+
 struct BrickArgs {
 	const uint8_t* layer;    // padded dense grid
 	double* time;            // padded dense grid
@@ -119,15 +136,19 @@ struct BrickArgs {
 	const int32_t* nbr;      // [n_live][26] live index of the neighbouring brick in cube direction k, -1 = none
 	int* flag;               // [n_live] 1 while the brick sits in the ring
 	int* first_visit;        // [n_live] 1 for the bricks of the start voxels until their first visit
-	const uint8_t* own;      // [n_live] sharded run: 1 for the bricks this rank relaxes (NULL = all)
+	const uint8_t* own;      // [n_live] sharded run: kOwnMe for the bricks this rank relaxes (NULL = all), kOwnBelow / kOwnAbove for
+	                         // those the neighbouring ranks relax (a brick that straddles a slab face has several owners)
 	int* queue;              // ring of brick ids, -1 = empty slot, qmask + 1 slots
-	int* counters;           // [0] head, [1] tail, [2] pending (queued or in work), [4] visits, [5] inner sweeps, [6] stop
+	int* counters;           // [0] head, [1] tail, [2] pending (queued or in work), [3] warps that gave up waiting, [4] visits,
+	                         // [5] inner sweeps, [6] stop, linked run: [7] verdict (1 = terminated everywhere, 2 = aborted),
+	                         // [8] bricks queued at other ranks, [9] bricks other ranks queued here, [10] cells written to other ranks
 	uint32_t budget;         // bounded relaxation (sharded run): no further ring position is claimed once `budget` have been; 0 = no bound
 	uint32_t qmask;
 	int32_t n_live, nl1, n_nbr, pY, pX, w_in_smem;
 	int32_t loff[kMaxNbr];   // neighbour offset inside the 10^3 shared-memory cell array
 	int32_t sq[kMaxNbr];     // |dif|^2 - 1
 	int8_t dz[kMaxNbr], dy[kMaxNbr], dx[kMaxNbr];
+	BrickLink link;
 };
 
 }  // namespace ekg
@@ -181,6 +202,18 @@ struct ekg_model {
 	cudaStream_t merge_stream = nullptr;  // stream of the last ekg_model_activation_merge_async (the next relax / end waits for it)
 	bool merge_pending = false;
 	int64_t last_brick_visits = 0;
+	// peer-linked sharded automaton (ekg_model_activation_link / _linked_launch / _linked_wait / _linked_gather)
+	struct PeerLink {
+		bool active = false;
+		int rank = 0, n_ranks = 0, below = -1, above = -1;     // below / above: the nearest ranks with a non-empty slab
+		std::vector<int64_t> slabs;                            // [n_ranks][2]
+		std::vector<double*> time;                             // every rank's d_time_pad as seen from this device (own entry = ours)
+		std::vector<int*> state;                               // every rank's d_brick_state
+		std::vector<void*> ipc_opened;                         // what cudaIpcCloseMemHandle has to release
+		bool launched = false;
+		cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+		float kernel_ms = 0.f;
+	} link;
 
 	// ECG voxel list (layer-sorted, restricted to the slab)
 	int64_t slab_z0 = 0, slab_z1 = 0;
@@ -235,6 +268,12 @@ int shard_relax(ekg_model* m, int64_t max_visits, int64_t* visits_out, int64_t* 
 int shard_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, cudaStream_t st);
 int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, unsigned long long* d_count,
                 cudaStream_t st);
+int shard_link_info(ekg_model* m, void* info_out);
+int shard_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int64_t* slabs);
+int shard_unlink(ekg_model* m);
+int shard_linked_launch(ekg_model* m, int max_ctas);
+int shard_linked_wait(ekg_model* m, int64_t* visits_out, int64_t* remote_out);
+int shard_linked_gather(ekg_model* m);
 // ecg.cu
 // What the caller knows on the host about the coefficients of the batch (all zero: nothing -- the SEPARABLE path
 // then reads both back from the device, one stream synchronisation):

@@ -12,8 +12,12 @@ The path shards in two ways:
   lead-field coefficient of a voxel only needs the *occupancy* of its neighbours, which every rank
   knows from the full layer map, so no halo of potentials is exchanged; the partial ECGs
   [B][L][T] (f64, 6.4 kB per simulation on model_24) are summed with one all-reduce.
-* the activation automaton on such a sharded model (`sharded_activation`): the one place with a real halo exchange --
-  per round one plane each way between neighbouring slabs plus an all-reduce of the "anything improved?" counts.
+* the activation automaton on such a sharded model: the one place with a real halo exchange.  `linked_activation` is the
+  NVLink form -- every rank maps its neighbours' grids (CUDA IPC) and ONE kernel per rank writes improved face voxels
+  into the neighbour's grid and queues the neighbour's bricks itself; torch.distributed only carries the 256-byte link
+  records once and three barriers per run.  `sharded_activation` is the host-driven form (per round one plane each way
+  through point-to-point messages plus an all-reduce of the "anything improved?" counts), the fallback where the devices
+  have no native peer atomics.
 """
 from __future__ import annotations
 
@@ -232,6 +236,83 @@ def sharded_activation(planes, slabs, rank=None, world=None, max_rounds=10000, t
     if timings is not None:
         timings.update(rounds_s=t_rounds - t_begin, gather_s=t_gather - t_rounds, publish_s=time.perf_counter() - t_gather)
     return delay, rounds, visits
+
+
+def barrier(device=None):
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if device is not None and getattr(device, "type", "cpu") == "cuda":
+            dist.barrier(device_ids=[device.index])
+            torch.cuda.synchronize(device)
+        else:
+            dist.barrier()
+
+
+def exchange_link_infos(info: bytes, device=None):
+    """All-gathers the ranks' link records (ekg_model_activation_link_info), rank order."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return [info]
+    world = dist.get_world_size()
+    dev = device if device is not None and getattr(device, "type", "cpu") == "cuda" else "cpu"
+    mine = torch.frombuffer(bytearray(info), dtype=torch.uint8).to(dev)
+    out = torch.empty(world * len(info), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, mine)
+    blob = out.cpu().numpy().tobytes()
+    return [blob[r * len(info):(r + 1) * len(info)] for r in range(world)]
+
+
+def link_model(model, slabs, rank=None, world=None, device=None):
+    """Maps the other ranks' grids into `model` (once per model / slab layout).  Raises EkgError (code -7) where the
+    devices offer no native peer atomics; callers then use sharded_activation."""
+    import torch.distributed as dist
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    infos = exchange_link_infos(model.activation_link_info(), device)
+    assert len(infos) == world == len(slabs)
+    model.activation_link(rank, infos, slabs)
+
+
+def linked_activation(model, slabs, rank=None, world=None, device=None, timings=None, download=True, gather=True, info=None):
+    """The activation automaton of a model sharded into z-slabs, peer-linked (include/ekgsim_b200.h): after
+    `link_model` every rank launches ONE frontier kernel; improved voxels on the slab faces go into the neighbouring
+    rank's grid and the neighbour's bricks into the neighbour's ring from inside the kernel (NVLink atomics), idle ranks
+    wait in the kernel, rank 0's first warp detects global termination.  torch.distributed contributes barriers only:
+    after begin (rings ready before anyone pushes into them), after the kernels (slabs final before anyone copies them),
+    after the gather.  gather=False leaves the map sharded -- outside its slab a rank then holds upper bounds only, which
+    is all the slab's ECG needs, but `end` (range of the activation times) wants the whole map, so gather stays on unless
+    the caller knows better.  Returns (delay or None, brick visits of this rank); `timings` receives wall seconds of the
+    phases and `info` (a dict) the message counters."""
+    import time
+    import torch.distributed as dist
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    assert len(slabs) == world
+    model.activation_begin()
+    barrier(device)
+    t0 = time.perf_counter()
+    model.activation_linked_launch()
+    visits, remote = model.activation_linked_wait()
+    t_local = time.perf_counter()
+    barrier(device)
+    t1 = time.perf_counter()
+    if gather and world > 1:
+        model.activation_linked_gather()
+        barrier(device)
+    t2 = time.perf_counter()
+    delay = model.activation_end(download=download)
+    if timings is not None:
+        timings.update(run_s=t1 - t0, local_s=t_local - t0, gather_s=t2 - t1, publish_s=time.perf_counter() - t2)
+    if info is not None:
+        info.update(bricks_queued_at_neighbours=remote[0], bricks_queued_here_by_neighbours=remote[1], cells_written_to_neighbours=remote[2],
+                    kernel_ms=model.activation_ms)
+    return delay, visits
 
 
 def send_device(planes):

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define EKG_ABI_VERSION 2
+#define EKG_ABI_VERSION 3
 
 enum {
 	EKG_OK = 0,
@@ -149,6 +149,32 @@ int     ekg_model_activation_merge(ekg_model* m, int64_t z_begin, int64_t z_end,
 int     ekg_model_activation_merge_async(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes,
                                          uint64_t* d_improved_accum, void* stream);
 int     ekg_model_activation_end(ekg_model* m, double* delay_out);
+
+/* The same sharded automaton without host rounds ("peer-linked"): every rank maps the neighbouring ranks' grids (NVLink
+ * peer memory: raw pointers inside one process, CUDA IPC between processes) and ONE kernel launch per rank does the whole
+ * run -- a warp that improves a voxel on the first / last plane of its slab also writes it into the neighbour's grid and
+ * queues the neighbour's bricks around it in the neighbour's work ring (system-scope atomics), idle ranks wait inside the
+ * kernel, rank 0 detects global termination from all ranks' message counters.  No collective and no host synchronisation
+ * on the path; the bits are those of ekg_model_activation.  Needs native atomics between the devices (NVLink);
+ * ekg_model_activation_link returns EKG_E_UNSUPPORTED otherwise and the rounds above remain.
+ *   link_info       fills EKG_LINK_INFO_BYTES bytes describing this handle (exchange them between the ranks, rank order)
+ *   link            rank, number of ranks, all ranks' records, all ranks' slabs [n_ranks][2] (a partition of [0, Z) in rank
+ *                   order; this rank's must be what ekg_model_set_slab set).  Ranks with an empty slab take part, idle.
+ *   begin           ekg_model_activation_begin as above (also prepares the work ring); THEN A BARRIER OVER ALL RANKS
+ *   linked_launch   starts the kernel and returns.  max_ctas > 0 caps the grid (ranks sharing one device must all be resident)
+ *   linked_wait     waits for it; brick_visits_out = this rank's brick visits; remote_out[3] (may be NULL) = bricks queued at
+ *                   other ranks, bricks other ranks queued here, cells written into other ranks' grids
+ *   linked_gather   after a barrier over all ranks: copies the other ranks' slabs over the links, so that every rank
+ *                   holds the whole map (optional: the ECG of a slab only needs the slab); then a barrier before the next begin
+ *   end             ekg_model_activation_end as above
+ *   unlink          releases the mappings (also done by ekg_model_destroy) */
+#define EKG_LINK_INFO_BYTES 256
+int     ekg_model_activation_link_info(ekg_model* m, void* info_out);
+int     ekg_model_activation_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int64_t* slabs);
+int     ekg_model_activation_linked_launch(ekg_model* m, int max_ctas);
+int     ekg_model_activation_linked_wait(ekg_model* m, int64_t* brick_visits_out, int64_t* remote_out);
+int     ekg_model_activation_linked_gather(ekg_model* m);
+int     ekg_model_activation_unlink(ekg_model* m);
 int  ekg_model_get_activation(const ekg_model* m, double* delay_out);
 
 /* (layer, delay) class table in first-seen raster order: ap_index_out[Z*Y*X] (-1 = empty);

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     assert sorted(built.SYMBOLS) == names, "ctypes table and header disagree"
-    assert built.lib().ekg_abi_version() == 2
+    assert built.lib().ekg_abi_version() == 3
 
 
 def test_sass_is_sm100a_and_uses_mufu(built):

@@ -611,6 +611,26 @@ def run_sharded(ranks, slabs, budget=0):
     return rounds, visits, [p.end() for p in ranks]
 
 
+def run_linked(models, slabs, gather=True):
+    """The peer-linked sharded automaton with all ranks' handles on ONE device (raw pointers instead of CUDA IPC; every
+    rank's kernel gets an equal share of the SMs so that all of them are resident): link, begin everywhere, launch
+    everywhere, wait everywhere, pull the other slabs, end."""
+    import torch
+    infos = [m.activation_link_info() for m in models]
+    for r, m in enumerate(models):
+        m.activation_link(r, infos, slabs)
+    for m in models:
+        m.activation_begin()
+    cap = max(1, torch.cuda.get_device_properties(0).multi_processor_count * 2 // len(models))
+    for m in models:
+        m.activation_linked_launch(max_ctas=cap)
+    res = [m.activation_linked_wait() for m in models]
+    if gather:
+        for m in models:
+            m.activation_linked_gather()
+    return res, [m.activation_end() for m in models]
+
+
 def test_sharded_automaton_many_crossings(built):
     """A serpentine path crosses the slab faces once per turn: the wave has to be handed back and forth ~10 times, through
     faces that cut bricks in the middle as well as faces on brick boundaries."""
@@ -635,8 +655,54 @@ def test_sharded_automaton_many_crossings(built):
         for d in delays_b:
             assert d.tobytes() == ref.tobytes(), slabs
         assert rounds_b > rounds
+        # peer-linked: no rounds at all, the slabs hand the wave back and forth from inside their kernels
+        res, delays_l = run_linked([p.model for p in ranks], slabs)
+        for d in delays_l:
+            assert d.tobytes() == ref.tobytes(), slabs
+        sent = sum(r[1][0] for r in res)
+        assert sent == sum(r[1][1] for r in res) and sent >= 10, res       # every brick queued elsewhere arrived; >= one per crossing
+        print("  linked: brick visits %s, bricks queued across the faces %d, cells written across %d" % ([r[0] for r in res], sent, sum(r[1][2] for r in res)))
         for p in ranks:
             p.model.close()
+
+
+def test_linked_automaton_empty_slab_and_relink(built):
+    """A rank with an empty slab takes part idle; linking again with other slabs works on the same handles; ranks whose
+    slab is one plane thick send that plane both ways."""
+    layers, transfer = synth.serpentine(n_turns=6, height=12)
+    ref = oracle.activation(layers, transfer)
+    models = [built.Model(layers, transfer, device=0) for _ in range(4)]
+    for slabs in ([(0, 8), (8, 8), (8, 9), (9, 16)], [(0, 3), (3, 4), (4, 5), (5, 16)], [(0, 0), (0, 16), (16, 16), (16, 16)]):
+        for m, (z0, z1) in zip(models, slabs):
+            m.set_slab(z0, z1)
+        res, delays = run_linked(models, slabs)
+        for d in delays:
+            assert d.tobytes() == ref.tobytes(), slabs
+        assert sum(r[1][0] for r in res) == sum(r[1][1] for r in res)
+    # without the gather a rank is only exact on its own slab
+    slabs = [(0, 5), (5, 9), (9, 12), (12, 16)]
+    for m, (z0, z1) in zip(models, slabs):
+        m.set_slab(z0, z1)
+    res, delays = run_linked(models, slabs, gather=False)
+    for d, (z0, z1) in zip(delays, slabs):
+        assert d[z0:z1].tobytes() == ref[z0:z1].tobytes(), (z0, z1)
+    # errors: launch without link / begin, slabs that do not partition
+    lone = built.Model(layers, transfer, device=0)
+    with pytest.raises(built.EkgError):
+        lone.activation_linked_launch()
+    with pytest.raises(built.EkgError):
+        lone.activation_link(0, [lone.activation_link_info()], [(0, 15)])
+    lone.activation_link(0, [lone.activation_link_info()], [(0, 16)])
+    with pytest.raises(built.EkgError):
+        lone.activation_linked_launch()                                    # no begin
+    lone.activation_begin()
+    lone.activation_linked_launch()
+    lone.activation_linked_wait()
+    assert lone.activation_end().tobytes() == ref.tobytes()               # one rank alone: the detector sees itself idle
+    lone.activation_unlink()
+    lone.close()
+    for m in models:
+        m.close()
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -667,6 +733,12 @@ def test_sharded_automaton_entry_points(built, model24, model24_delay, world):
     for delay in delays_b:
         assert delay.tobytes() == model24_delay.tobytes()
     print("  bounded to 4000 visits per round: %d rounds, %d brick visits" % (rounds_b, visits_b))
+    # peer-linked: one kernel per rank, face planes and brick pushes go through the neighbours' memory
+    res, delays_l = run_linked([p.model for p in ranks], slabs)
+    for delay in delays_l:
+        assert delay.tobytes() == model24_delay.tobytes()
+    assert sum(r[1][0] for r in res) == sum(r[1][1] for r in res) > 0
+    print("  linked: brick visits %s, remote (queued there, queued here, cells written) %s" % ([r[0] for r in res], [r[1] for r in res]))
     # the handles are usable afterwards like after ekg_model_activation: slab ECGs add up
     g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
     parts = sum(p.model.simulate(g["layer_k"][:2], g["leads_zyx"][:2], "3D4", 100.0, 1.0, 50.0, mode=3) for p in ranks)

@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--sharded-automaton", action="store_true",
                     help="also run the automaton sharded over the z-slabs (plane exchange over NCCL) and compare with the replicated run")
+    ap.add_argument("--linked-automaton", action="store_true",
+                    help="also run the peer-linked sharded automaton (in-kernel exchange over NVLink peer memory, no host rounds)")
     ap.add_argument("--visits-per-round", type=int, default=-1, help="bound of the sharded automaton's relaxation per round (-1: the driver's default, 0: none)")
     a = ap.parse_args()
     rank, world, local = ekdist.init()
@@ -78,6 +80,26 @@ def main():
                    "visits_per_round": a.visits_per_round,
                    "bit_identical_to_replicated_run": same}
         assert same, "sharded automaton differs from the replicated run"
+    linked = None
+    if a.linked_automaton:
+        slabs = ekdist.slab_ranges(occ_z, world)
+        t0 = time.perf_counter()
+        ekdist.link_model(model, slabs, rank, world, dev)
+        t_link = time.perf_counter() - t0
+        runs = []
+        for _ in range(4):
+            tm, info = {}, {}
+            _, visits = ekdist.linked_activation(model, slabs, rank, world, dev, timings=tm, download=False, info=info)
+            runs.append((ekdist.max_over_ranks(tm["run_s"] * 1e3, dev), ekdist.max_over_ranks(tm["gather_s"] * 1e3, dev),
+                         ekdist.max_over_ranks(info["kernel_ms"], dev), ekdist.max_over_ranks(tm["publish_s"] * 1e3, dev)))
+        d2 = model.get_activation()
+        same = bool(d2.tobytes() == delay.tobytes())
+        best = min(runs)
+        linked = {"ms_run_launch_to_all_ranks_done": best[0], "ms_gather_over_links": best[1], "kernel_ms_max_over_ranks": best[2],
+                  "ms_publish_on_device": best[3], "all_runs_ms": [r[0] for r in runs], "link_setup_ms": t_link * 1e3,
+                  "brick_visits_this_rank": visits, "counters_rank0": info, "bit_identical_to_replicated_run": same}
+        assert same, "linked automaton differs from the replicated run"
+        model.activation_unlink()
     g = np.load(os.path.join(ROOT, "tests", "golden", "golden_glue256.npz"))
     k = np.ascontiguousarray(g["layer_k"][:1])
     lead_b = np.ascontiguousarray(leads[None])
@@ -108,7 +130,7 @@ def main():
     out = {"workload": "configs[3]: %dx heart, %d occupied voxels, z-slab sharded over %d GPU(s)" % (a.factor, n_occ, world),
            "n_gpus": world, "ms_per_sim": ms, "voxel_timesteps_per_s": n_occ * T / (ms * 1e-3), "mode": a.mode,
            "automaton_ms": auto_ms, "automaton_call_ms_map_stays_on_device": t_auto_call * 1e3, "activation_host_copy_ms": t_download * 1e3,
-           "automaton_sweeps": sweeps, "sharded_automaton": sharded, "model_create_s": t_create,
+           "automaton_sweeps": sweeps, "sharded_automaton": sharded, "linked_automaton": linked, "model_create_s": t_create,
            "slab_voxels_rank0": model.num_voxels, "ecg_peak": np.abs(ecg).max(axis=1).tolist()}
     if a.check and rank == 0:
         from oracle import oracle
