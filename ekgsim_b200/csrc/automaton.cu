@@ -827,6 +827,7 @@ int shard_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int
 		if (p.magic != kLinkMagic) return bail(EKG_E_INVALID, "not a link info record");
 		if (p.n_bricks != m->n_bricks || p.npad != m->pZ * m->pY * m->pX) return bail(EKG_E_INVALID, "the ranks hold different models");
 		if (r == rank) { L.time[(size_t)r] = m->d_time_pad; L.state[(size_t)r] = m->d_brick_state; continue; }
+		if (p.device == m->device && p.pid == this_pid()) ++L.colocated;
 		if (p.device != m->device || p.pid != this_pid()) {
 			int can = 0, native = 0;
 			int peer_dev = p.device;
@@ -890,6 +891,8 @@ int shard_linked_launch(ekg_model* m, int max_ctas) {
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
 	// our own bricks bound the useful grid (a slab is ~1/N of the model); rank 0 gives one warp to the detector
 	int64_t grid = std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>((n + kBrickWarps - 1) / kBrickWarps, 1) + 1);
+	// ranks of one process on one device: an equal share of the SMs each, so that every rank's kernel is resident
+	if (max_ctas <= 0 && L.colocated > 1) max_ctas = std::max(1, per_sm * m->sm_count / L.colocated);
 	if (max_ctas > 0) grid = std::min<int64_t>(grid, max_ctas);
 	void* kargs[] = {&a};
 	EKG_CUDA(cudaEventRecord(L.ev0, st));

@@ -206,6 +206,7 @@ struct ekg_model {
 	struct PeerLink {
 		bool active = false;
 		int rank = 0, n_ranks = 0, below = -1, above = -1;     // below / above: the nearest ranks with a non-empty slab
+		int colocated = 1;                                     // ranks of this process on this device (they share its SMs)
 		std::vector<int64_t> slabs;                            // [n_ranks][2]
 		std::vector<double*> time;                             // every rank's d_time_pad as seen from this device (own entry = ours)
 		std::vector<int*> state;                               // every rank's d_brick_state

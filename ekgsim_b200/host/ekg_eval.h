@@ -457,7 +457,7 @@ public:
 		settings.load(ini);
 		sim.reset(new EkgSim);
 		if (withDevice && devices.empty()) if (const char* e = std::getenv("EKGSIM_B200_DEVICES")) devices = parse_device_list(e);
-		if (!devices.empty()) sim->setDevice(devices[0]);
+		if (!devices.empty() && !sim->sharded()) sim->setDevice(devices[0]);
 		sim->loadSettings(ini);
 		sim->loadTransferMatrix();
 		sim->loadMeasuringPoints();
@@ -493,6 +493,10 @@ public:
 			std::cerr << "   endo-epi min delay is also a criterion (" << settings.endoEpiMinCriterionDelay << ")\n";
 		}
 		std::cerr << " total number of criteria = " << deducedNumOfCriteria << "\n\n";
+		if (withDevice && sim->sharded()) {
+			std::cerr << " one model on " << sim->numSlabs() << " z-slabs (" << (sim->slabAutomatonLinked() ? "peer-linked" : "replicated") << " excitation sequence)\n\n";
+			devices.clear();   // slabs and batch devices are alternatives
+		}
 		if (withDevice && devices.size() > 1) {
 			std::vector<std::string> errors(devices.size());
 			std::vector<std::thread> pool;
@@ -827,6 +831,7 @@ private:
 	bool criteriaOnDevice() const {
 		const size_t L = sim->numMeasurements();
 		if (getenv("EKGSIM_B200_HOST_CRITERIA")) return false;
+		if (sim->sharded()) return false;   // z-slabs: the ECG only exists once the partial sums have been added on the host
 		if (settings.criteriaMode != EvalSettings::every_lead || settings.peakPositionIsCriterion) return false;
 		if (targets.size() < L || L == 0) return false;
 		for (size_t m = 1; m < L; ++m) if (targets[m].size() != targets[0].size()) return false;

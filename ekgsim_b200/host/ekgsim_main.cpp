@@ -23,6 +23,10 @@
 //     -devices all|<count>|<id,id,...>   with -batch / -serve: one model replica per GPU, every batch split over them by
 //         one host thread per device (individuals over GPUs, no collective; default EKGSIM_B200_DEVICES, else one GPU:
 //         EKGSIM_B200_DEVICE or 0).  With MPI workers of the reference's optimizer set EKGSIM_B200_DEVICE=<rank % gpus>.
+//     -slabs all|<count>|<id,id,...>     with any mode: ONE model spread over several GPUs as z-slabs (for models too large or
+//         too slow for one GPU): every GPU sums the ECG over its slab, the partial ECGs are added; the excitation sequence is
+//         computed by all GPUs together (peer-linked automaton, NVLink).  Same as EKGSIM_B200_SLABS.  An alternative to
+//         -devices (which replicates the model and splits the batch).
 // The optimizer itself (`ekgSim` without arguments, AMS-DEMO over MPI) is outside the hot path and is
 // not part of this build; use the reference's optimizer with `-extern` or `-batch` as its evaluator.
 
@@ -178,6 +182,7 @@ int main(int argc, char** argv) {
 	try {
 		DashArgs args(argc, argv);
 		std::cerr << "***** parsing program arguments ****************************\n";
+		if (args.is_set("-slabs")) setenv("EKGSIM_B200_SLABS", args.get("-slabs").c_str(), 1);   // read by every EkgSim of this process
 		ekg::OutputSettings out;
 		parse_outputs(args, out);
 		if (args.is_set("-?")) {
@@ -185,6 +190,7 @@ int main(int argc, char** argv) {
 			             "   -out \tspecify outputs of the program; possible values include result, layer_aps, cell_aps <num> [<num>]*\n"
 			             "   -batch \tevaluate every parameter vector of a text file in one GPU batch [-batchout file] [-threads n]\n"
 			             "   -devices \twith -batch / -serve: GPUs to split the batches over: all, a count, or a list 0,1,2 (default: EKGSIM_B200_DEVICES, else one)\n"
+			             "   -slabs \tone model over several GPUs as z-slabs: all, a count, or a list 0,1,2 (default: EKGSIM_B200_SLABS, else off)\n"
 			             "   -extern \tAMS-DEMO ExternalEvaluation protocol: <homeDir>/input.txt -> <homeDir>/output.txt [-server socket]\n"
 			             "   -serve \tresident evaluation server on a unix socket (clients: -extern with -server or EKGSIM_B200_SERVER)\n"
 			             "   -shutdown \task the server on the given socket to exit\n";

@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <cmath>
 #include <memory>
+#include <sstream>
+#include <thread>
 #include <unordered_map>
 
 #include "../../include/ekgsim_b200.h"
@@ -153,6 +155,15 @@ private:
 	int64_t tRows_ = 0, tCols_ = 0;
 	ekg_model* model_ = nullptr;
 	int device_ = 0;
+	/// z-slab mode (new; BASELINE config 4 "single sim z-slab sharded"): ONE large model spread over several GPUs from this
+	/// process.  Every device holds the model and sums the ECG over its slab of voxel planes (ekg_model_set_slab, slabs
+	/// balanced by occupied voxels); run() adds the partial ECGs [leads][T] on the host.  The automaton runs peer-linked
+	/// over the same slabs (ekg_model_activation_link: one kernel per device, face planes exchanged through NVLink peer
+	/// memory); devices without native peer atomics each compute the whole map instead.  slabModels_[0] == model_.
+	std::vector<int> slabDevices_;
+	std::vector<ekg_model*> slabModels_;
+	std::vector<std::pair<int64_t, int64_t>> slabRanges_;
+	bool slabAutomatonLinked_ = false;
 	size_t targetNumOfAps_ = 12;   // Simulation::targetNumOfAps default (simulator.h:556)
 	int nbhd_ = -1;
 	double timeStep_ = 0;
@@ -172,7 +183,92 @@ private:
 		if (model_) return;
 		if (layers_.empty()) throw std::runtime_error("shape not loaded");
 		if (transfer_.empty()) throw std::runtime_error("transfer matrix not loaded");
-		check(ekg_model_create(layers_.data(), Z_, Y_, X_, transfer_.data(), tRows_, tCols_, device_, &model_));
+		if (slabDevices_.size() < 2) {
+			check(ekg_model_create(layers_.data(), Z_, Y_, X_, transfer_.data(), tRows_, tCols_, device_, &model_));
+			return;
+		}
+		// one handle per device, created side by side (each upload + device-side set-up is independent)
+		const size_t n = slabDevices_.size();
+		slabModels_.assign(n, nullptr);
+		std::vector<std::string> errors(n);
+		forEachSlab([&](size_t d) {
+			if (ekg_model_create(layers_.data(), Z_, Y_, X_, transfer_.data(), tRows_, tCols_, slabDevices_[d], &slabModels_[d]) != EKG_OK)
+				throw std::runtime_error(ekg_last_error());
+		});
+		model_ = slabModels_[0];
+		// slabs of (nearly) equal numbers of occupied voxels
+		std::vector<int64_t> cum((size_t)Z_ + 1, 0);
+		for (int64_t z = 0; z < Z_; ++z) {
+			int64_t c = 0;
+			const uint16_t* pl = &layers_[(size_t)(z * Y_ * X_)];
+			for (int64_t i = 0; i < Y_ * X_; ++i) c += (pl[i] & 0x0fff) != 0;
+			cum[(size_t)z + 1] = cum[(size_t)z] + c;
+		}
+		slabRanges_.assign(n, std::make_pair<int64_t, int64_t>(0, 0));
+		int64_t prev = 0;
+		for (size_t d = 0; d < n; ++d) {
+			int64_t cut = Z_;
+			if (d + 1 < n) {
+				const double target = (double)cum[(size_t)Z_] * (double)(d + 1) / (double)n;
+				cut = (int64_t)(std::lower_bound(cum.begin(), cum.end(), (int64_t)std::ceil(target)) - cum.begin());
+				if (cut > 0 && std::fabs((double)cum[(size_t)cut - 1] - target) <= std::fabs((double)cum[(size_t)std::min<int64_t>(cut, Z_)] - target)) --cut;
+				cut = std::min(std::max(cut, prev), Z_);
+			}
+			slabRanges_[d] = std::make_pair(prev, cut);
+			prev = cut;
+		}
+		forEachSlab([&](size_t d) {
+			if (ekg_model_set_slab(slabModels_[d], slabRanges_[d].first, slabRanges_[d].second) != EKG_OK) throw std::runtime_error(ekg_last_error());
+		});
+	}
+
+	/// f(d) for every slab device on its own host thread (the C ABI is one caller per handle; errors are per thread)
+	template <class F>
+	void forEachSlab(F f) {
+		const size_t n = slabDevices_.size();
+		std::vector<std::string> errors(n);
+		std::vector<std::thread> pool;
+		for (size_t d = 0; d < n; ++d)
+			pool.emplace_back([&, d]() { try { f(d); } catch (std::exception& e) { errors[d] = e.what(); if (errors[d].empty()) errors[d] = "error"; } });
+		for (std::thread& t : pool) t.join();
+		for (const std::string& e : errors) if (!e.empty()) throw std::runtime_error(e);
+	}
+
+	void destroyModels() {
+		if (slabModels_.empty()) { if (model_) ekg_model_destroy(model_); }
+		else for (ekg_model* m : slabModels_) if (m) ekg_model_destroy(m);
+		slabModels_.clear();
+		model_ = nullptr;
+		haveActivation_ = false;
+	}
+
+	/// the automaton over the slabs: peer-linked when the devices allow it, else every device computes the whole map
+	void slabActivation() {
+		const size_t n = slabModels_.size();
+		std::vector<unsigned char> infos(n * EKG_LINK_INFO_BYTES);
+		std::vector<int64_t> slabs(2 * n);
+		for (size_t d = 0; d < n; ++d) {
+			check(ekg_model_activation_link_info(slabModels_[d], &infos[d * EKG_LINK_INFO_BYTES]));
+			slabs[2 * d] = slabRanges_[d].first; slabs[2 * d + 1] = slabRanges_[d].second;
+		}
+		bool linked = getenv("EKGSIM_B200_SLAB_AUTOMATON") == nullptr || std::string(getenv("EKGSIM_B200_SLAB_AUTOMATON")) != "replicated";
+		for (size_t d = 0; d < n && linked; ++d) {
+			const int rc = ekg_model_activation_link(slabModels_[d], (int)d, (int)n, infos.data(), slabs.data());
+			if (rc == EKG_E_UNSUPPORTED) linked = false;
+			else check(rc);
+		}
+		slabAutomatonLinked_ = linked;
+		if (!linked) {
+			for (ekg_model* m : slabModels_) ekg_model_activation_unlink(m);
+			forEachSlab([&](size_t d) { if (ekg_model_activation(slabModels_[d], nullptr, nullptr) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
+			return;
+		}
+		// begin everywhere (rings ready) -> launch everywhere -> wait everywhere -> pull the other slabs -> publish
+		forEachSlab([&](size_t d) { if (ekg_model_activation_begin(slabModels_[d]) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
+		for (ekg_model* m : slabModels_) check(ekg_model_activation_linked_launch(m, 0));
+		forEachSlab([&](size_t d) { if (ekg_model_activation_linked_wait(slabModels_[d], nullptr, nullptr) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
+		forEachSlab([&](size_t d) { if (ekg_model_activation_linked_gather(slabModels_[d]) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
+		forEachSlab([&](size_t d) { if (ekg_model_activation_end(slabModels_[d], nullptr) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
 	}
 
 	static PositionVec cross(const PositionVec& a, const PositionVec& b) {
@@ -190,14 +286,36 @@ private:
 public:
 	EkgSim() {
 		if (const char* d = getenv("EKGSIM_B200_DEVICE")) device_ = atoi(d);
+		if (const char* sl = getenv("EKGSIM_B200_SLABS")) setSlabDevices(sl);
 		if (const char* m = getenv("EKGSIM_B200_MODE")) {
 			const std::string s(m);
 			mode_ = s == "direct" ? EKG_MODE_DIRECT : s == "hoisted" ? EKG_MODE_HOISTED : s == "separable" ? EKG_MODE_SEPARABLE : EKG_MODE_DEFAULT;
 		}
 	}
-	~EkgSim() { if (model_) ekg_model_destroy(model_); }
+	~EkgSim() { destroyModels(); }
 
 	void setDevice(int device) { device_ = device; }
+	/// z-slab mode over these GPUs: "all" | "<count>" | "<id>,<id>,..." (an id may repeat: several slabs on one GPU);
+	/// fewer than two devices = off.  Takes effect when the device model is (re)built.
+	void setSlabDevices(const std::string& spec) {
+		std::vector<int> ids;
+		const int have = ekg_device_count();
+		if (spec == "all") for (int i = 0; i < have; ++i) ids.push_back(i);
+		else if (spec.find(',') == std::string::npos) { for (int i = 0; i < atoi(spec.c_str()); ++i) ids.push_back(i); }
+		else {
+			std::istringstream in(spec);
+			for (std::string tok; std::getline(in, tok, ',');) if (!tok.empty()) ids.push_back(atoi(tok.c_str()));
+		}
+		for (int id : ids) if (id < 0 || id >= have) throw std::runtime_error("no such CUDA device in slab list: " + spec);
+		if (ids.size() > 16) throw std::runtime_error("at most 16 slabs");
+		destroyModels();
+		slabDevices_ = ids.size() >= 2 ? ids : std::vector<int>();
+		if (!ids.empty()) device_ = ids[0];
+	}
+	size_t numSlabs() const { return slabDevices_.size() >= 2 ? slabDevices_.size() : 1; }
+	bool sharded() const { return slabDevices_.size() >= 2; }
+	bool slabAutomatonLinked() const { return slabAutomatonLinked_; }
+	const std::vector<std::pair<int64_t, int64_t>>& slabRanges() const { return slabRanges_; }
 	int device() const { return device_; }
 
 	/// A second simulator with the same inputs and settings on another GPU (new; multi-GPU evaluation in one process,
@@ -205,7 +323,9 @@ public:
 	/// main.cpp:301-302): the parsed host state is copied, the device model is created and the activation map
 	/// computed on `device` (bit-identical on every device).  Quiet: the console contract belongs to the primary.
 	std::unique_ptr<EkgSim> replicate(int device) const {
+		if (sharded()) throw std::runtime_error("a z-slab sharded simulator cannot be replicated (slabs and batch devices are alternatives)");
 		std::unique_ptr<EkgSim> r(new EkgSim);
+		r->slabDevices_.clear();
 		r->settings = settings;
 		r->layers_ = layers_; r->Z_ = Z_; r->Y_ = Y_; r->X_ = X_;
 		r->transfer_ = transfer_; r->tRows_ = tRows_; r->tCols_ = tCols_;
@@ -268,7 +388,7 @@ public:
 		ekg::load_double_matrix(settings.inputTransferFilename, transfer_, tRows_, tCols_);
 		// Simulation::loadTransferMatrix checks against the default / previously loaded layer count
 		if ((size_t)tRows_ < targetNumOfAps_ || (size_t)tCols_ < targetNumOfAps_) throw std::runtime_error("loaded transfer matrix too small");
-		if (model_) { ekg_model_destroy(model_); model_ = nullptr; haveActivation_ = false; }
+		destroyModels();
 	}
 
 	void loadMeasuringPoints() {
@@ -330,7 +450,7 @@ public:
 		size_t maxLayer = 0;
 		for (uint16_t l : layers_) maxLayer = std::max<size_t>(maxLayer, l & 0x0fff);
 		targetNumOfAps_ = maxLayer;
-		if (model_) { ekg_model_destroy(model_); model_ = nullptr; haveActivation_ = false; }
+		destroyModels();
 	}
 
 	size_t requiredAps() const { return targetNumOfAps_; }
@@ -339,12 +459,14 @@ public:
 		ensureModel();
 		if (settings.inputExcitationSequenceFilename == "") {
 			ekg::LogTimer tm(std::cerr, "calculating excitation sequence             ");
-			check(ekg_model_activation(model_, nullptr, nullptr));
+			if (sharded()) slabActivation();
+			else check(ekg_model_activation(model_, nullptr, nullptr));
 		} else {
 			ekg::LogTimer tm(std::cerr, "loading excitation sequence                 ");
 			std::vector<double> delay;
 			ekg::load_delay_matrix(settings.inputExcitationSequenceFilename, Z_, Y_, X_, delay);
-			check(ekg_model_set_activation(model_, delay.data()));
+			if (sharded()) forEachSlab([&](size_t d) { if (ekg_model_set_activation(slabModels_[d], delay.data()) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
+			else check(ekg_model_set_activation(model_, delay.data()));
 		}
 		haveActivation_ = true;
 		delayCache_.clear();
@@ -399,8 +521,19 @@ public:
 		const size_t T = (size_t)std::ceil(settings.simulationLength / timeStep_);
 		ecg.assign(B * mps_.size() * T, 0.0);
 		const double t0 = ekg::wall_seconds();
-		check(ekg_simulate(model_, layerK, leadsZyx, (int64_t)B, (int64_t)mps_.size(), nbhd_, (double)settings.simulationStart, timeStep_,
-		                   (double)settings.simulationLength, mode_, ecg.data()));
+		if (!sharded()) {
+			check(ekg_simulate(model_, layerK, leadsZyx, (int64_t)B, (int64_t)mps_.size(), nbhd_, (double)settings.simulationStart, timeStep_,
+			                   (double)settings.simulationLength, mode_, ecg.data()));
+		} else {
+			// every device sums its slab; the partial ECGs are added in slab order (the same sum whatever the thread timing)
+			std::vector<std::vector<double>> part(slabModels_.size(), std::vector<double>(ecg.size()));
+			forEachSlab([&](size_t d) {
+				if (ekg_simulate(slabModels_[d], layerK, leadsZyx, (int64_t)B, (int64_t)mps_.size(), nbhd_, (double)settings.simulationStart, timeStep_,
+				                 (double)settings.simulationLength, mode_, part[d].data()) != EKG_OK)
+					throw std::runtime_error(ekg_last_error());
+			});
+			for (const std::vector<double>& p : part) for (size_t i = 0; i < ecg.size(); ++i) ecg[i] += p[i];
+		}
 		lastRunSeconds_ = ekg::wall_seconds() - t0;
 	}
 
@@ -420,6 +553,13 @@ public:
 		if (!haveActivation_) throw std::runtime_error("excitation sequence missing: call simExcitationSequence() first");
 		if (nbhd_ < 0) throw std::runtime_error("applySettings() must be called before run()");
 		startTime_ = settings.simulationStart;
+		if (sharded()) {   // the fit on the first device, the simulation over the slabs
+			std::vector<double> k;
+			fitLayers(borderK, B, nBorder, mid, d9, step, eps, iterations, k);
+			runBatch(k.data(), leadsZyx, B, ecg);
+			if (layerK) layerK->swap(k);
+			return;
+		}
 		const size_t T = (size_t)std::ceil(settings.simulationLength / timeStep_);
 		ecg.assign(B * mps_.size() * T, 0.0);
 		if (layerK) layerK->assign(B * targetNumOfAps_ * 9, 0.0);
@@ -438,6 +578,7 @@ public:
 		ensureModel();
 		if (!haveActivation_) throw std::runtime_error("excitation sequence missing: call simExcitationSequence() first");
 		if (nbhd_ < 0) throw std::runtime_error("applySettings() must be called before run()");
+		if (sharded()) throw std::runtime_error("evaluateBatchCriteria: not available on a z-slab sharded simulator (use evaluateBatch)");
 		startTime_ = settings.simulationStart;
 		criteria.assign(B * mps_.size(), 0.0);
 		const double t0 = ekg::wall_seconds();

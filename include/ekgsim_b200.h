@@ -161,7 +161,8 @@ int     ekg_model_activation_end(ekg_model* m, double* delay_out);
  *   link            rank, number of ranks, all ranks' records, all ranks' slabs [n_ranks][2] (a partition of [0, Z) in rank
  *                   order; this rank's must be what ekg_model_set_slab set).  Ranks with an empty slab take part, idle.
  *   begin           ekg_model_activation_begin as above (also prepares the work ring); THEN A BARRIER OVER ALL RANKS
- *   linked_launch   starts the kernel and returns.  max_ctas > 0 caps the grid (ranks sharing one device must all be resident)
+ *   linked_launch   starts the kernel and returns.  max_ctas > 0 caps the grid; 0 = the device's capacity, divided by the
+ *                   number of ranks of this process on this device (all of them must be resident at the same time)
  *   linked_wait     waits for it; brick_visits_out = this rank's brick visits; remote_out[3] (may be NULL) = bricks queued at
  *                   other ranks, bricks other ranks queued here, cells written into other ranks' grids
  *   linked_gather   after a barrier over all ranks: copies the other ranks' slabs over the links, so that every rank

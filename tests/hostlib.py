@@ -70,11 +70,15 @@ def load_shape(fname, capacity=1 << 22):
 class Evaluator:
     """Runs in `workdir` (must hold simulator.ini + inputs, like the reference CLI)."""
 
-    def __init__(self, workdir, with_device=True, n_layers=24, n_leads=2, devices=None):
-        """devices: None (one GPU) | "all" | "<count>" | "0,1,..." -- batches are split over them (Evaluator::evalBatch)"""
+    def __init__(self, workdir, with_device=True, n_layers=24, n_leads=2, devices=None, slabs=None):
+        """devices: None (one GPU) | "all" | "<count>" | "0,1,..." -- batches are split over them (Evaluator::evalBatch);
+        slabs: the same spellings -- ONE model as z-slabs over those GPUs (EKGSIM_B200_SLABS, EkgSim::setSlabDevices)"""
         self.workdir, self.n_layers, self.n_leads = workdir, n_layers, n_leads
         cwd = os.getcwd()
         os.chdir(workdir)
+        old = os.environ.pop("EKGSIM_B200_SLABS", None)
+        if slabs is not None:
+            os.environ["EKGSIM_B200_SLABS"] = str(slabs)
         try:
             if devices is not None:
                 self.h = lib().ekg_host_evaluator_create_on(b"simulator.ini", str(devices).encode())
@@ -82,6 +86,9 @@ class Evaluator:
                 self.h = lib().ekg_host_evaluator_create(b"simulator.ini", 1 if with_device else 0)
         finally:
             os.chdir(cwd)
+            os.environ.pop("EKGSIM_B200_SLABS", None)
+            if old is not None:
+                os.environ["EKGSIM_B200_SLABS"] = old
         if not self.h:
             raise RuntimeError(lib().ekg_host_last_error().decode())
         self.n_crit = lib().ekg_host_num_criteria(self.h)

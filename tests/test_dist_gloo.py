@@ -185,3 +185,138 @@ def test_sharded_automaton_driver_gloo(built, cuts):
     got = sorted(q.get() for _ in range(world))
     assert all(ok for _, ok, _ in got), got
     assert got[0][2] >= 2 and len({rounds for _, _, rounds in got}) == 1      # every rank leaves the loop in the same round
+
+
+class LinkedNumpyModel(NumpySlabPlanes):
+    """CPU stand-in for the peer-linked contract of capi.Model (activation_link_info / _link / _begin / _linked_launch /
+    _linked_wait / _linked_gather / _end): the ranks' grids and counters are files mapped into every process (the role
+    CUDA IPC plays on the GPUs).  A rank relaxes its slab, writes its first / last plane into the neighbour's grid and
+    bumps the neighbour's inbox counter; rank 0 detects termination from all ranks' (idle, sent, received) like
+    link_detector in csrc/automaton.cu does (two consecutive passes: everyone idle, sum of sent now == sum of received
+    in the previous pass)."""
+    INFO = 256
+
+    def __init__(self, layers, transfer, tmpdir, rank):
+        super().__init__(layers, transfer, 0, layers.shape[0])
+        self.rank, self.tmpdir = rank, tmpdir
+        self.grid_path = os.path.join(tmpdir, "grid_%d.bin" % rank)
+        self.cnt_path = os.path.join(tmpdir, "cnt_%d.bin" % rank)
+        np.full(self.lay.shape, np.inf).tofile(self.grid_path)
+        np.zeros(8, dtype=np.int64).tofile(self.cnt_path)
+        self.t = np.memmap(self.grid_path, dtype=np.float64, mode="r+", shape=self.lay.shape)
+        self.cnt = np.memmap(self.cnt_path, dtype=np.int64, mode="r+", shape=(8,))   # working, sent, inbox_dn, inbox_up, done_dn, done_up, verdict
+        self.activation_ms = 0.0
+
+    def set_slab(self, z0, z1):
+        self.z0, self.z1 = z0, z1
+
+    def activation_link_info(self):
+        return self.tmpdir.encode().ljust(self.INFO, b"\0")
+
+    def activation_link(self, rank, infos, slabs):
+        assert rank == self.rank and len(infos) == len(slabs) and all(len(i) == self.INFO for i in infos)
+        dirs = [i.rstrip(b"\0").decode() for i in infos]
+        self.slabs = slabs
+        self.grids = [np.memmap(os.path.join(d, "grid_%d.bin" % r), dtype=np.float64, mode="r+", shape=self.lay.shape) for r, d in enumerate(dirs)]
+        self.cnts = [np.memmap(os.path.join(d, "cnt_%d.bin" % r), dtype=np.int64, mode="r+", shape=(8,)) for r, d in enumerate(dirs)]
+        live = [r for r in range(len(slabs)) if slabs[r][1] > slabs[r][0]]
+        self.below = max([r for r in live if r < rank], default=None) if rank in live else None
+        self.above = min([r for r in live if r > rank], default=None) if rank in live else None
+
+    def activation_begin(self):
+        self.t[:] = np.inf
+        self.t[self.start] = 1.0
+        self.cnt[:] = 0
+
+    def activation_linked_launch(self, max_ctas=0):
+        pass
+
+    def _send(self, peer, z, slot):
+        plane = np.array(self.t[z + 1])
+        if not (plane < self.grids[peer][z + 1]).any():
+            return
+        self.cnt[1] += 1                                   # sent, before the neighbour can see the work
+        np.minimum(self.grids[peer][z + 1], plane, out=self.grids[peer][z + 1])
+        self.cnts[peer][slot] += 1                         # its inbox: received
+
+    def activation_linked_wait(self):
+        import time
+        first, r_prev, visits = True, None, 0
+        deadline = time.time() + 120
+        while not self.cnt[6]:
+            assert time.time() < deadline
+            inbox = (int(self.cnt[2]), int(self.cnt[3]))
+            if (first or inbox != (int(self.cnt[4]), int(self.cnt[5]))) and self.z1 > self.z0:
+                self.cnt[0] = 1
+                self.cnt[4], self.cnt[5] = inbox
+                visits += self.relax()[0]
+                if self.below is not None:
+                    self._send(self.below, self.z0, 3)     # my first plane arrives from above, seen from the rank below
+                if self.above is not None:
+                    self._send(self.above, self.z1 - 1, 2)
+                self.cnt[0] = 0
+            else:
+                time.sleep(0.0005)
+            first = False
+            if self.rank == 0:                             # one detector pass
+                idle, sent, recv = True, 0, 0
+                for c in self.cnts:
+                    done = (int(c[4]), int(c[5]))
+                    inbox = (int(c[2]), int(c[3]))
+                    idle = idle and done == inbox and int(c[0]) == 0
+                    sent += int(c[1])
+                    recv += inbox[0] + inbox[1]
+                if idle and r_prev is not None and sent == r_prev:
+                    for c in self.cnts:
+                        c[6] = 1
+                r_prev = recv
+        return visits, (int(self.cnt[1]), int(self.cnt[2] + self.cnt[3]), 0)
+
+    def activation_linked_gather(self):
+        for r, (a, b) in enumerate(self.slabs):
+            if r != self.rank and b > a:
+                self.t[a + 1:b + 1] = self.grids[r][a + 1:b + 1]
+
+    def activation_end(self, download=True):
+        return self.end(download)
+
+
+def _linked_worker(rank, world, port, q, cuts, tmpdir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    r, w, _ = ekdist.init("gloo")
+    layers, transfer, _ = synth.small_heart(seed=6, shape=(14, 13, 12), n_layers=4)
+    slabs = [(cuts[i], cuts[i + 1]) for i in range(w)]
+    model = LinkedNumpyModel(layers, transfer, tmpdir, r)
+    model.set_slab(*slabs[r])
+    dist.barrier()                                         # every rank's files exist
+    ekdist.link_model(model, slabs, r, w)
+    ref = oracle.activation(layers, transfer)
+    ok = True
+    for _ in range(2):                                     # the second run starts from the first one's leftovers
+        info, tm = {}, {}
+        delay, visits = ekdist.linked_activation(model, slabs, r, w, timings=tm, info=info)
+        ok = ok and delay.tobytes() == ref.tobytes() and set(tm) == {"run_s", "local_s", "gather_s", "publish_s"}
+    q.put((r, ok, info["bricks_queued_at_neighbours"], info["bricks_queued_here_by_neighbours"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cuts", [[0, 7, 14], [0, 5, 5, 14], [0, 0, 13, 14]])
+def test_linked_automaton_driver_gloo(built, cuts, tmp_path):
+    """ekgsim_b200.dist.link_model / linked_activation over gloo: the link records are all-gathered in rank order, the
+    barriers sit where the contract wants them (rings ready before anyone pushes, slabs final before anyone copies), and
+    the termination scheme of the linked kernel -- restated on memory-mapped files -- ends every rank with the oracle's
+    bits, also with empty slabs (rank 0, the detector, included)."""
+    world = len(cuts) - 1
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_linked_worker, args=(r, world, port, q, cuts, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    got = sorted(q.get() for _ in range(world))
+    assert all(ok for _, ok, _, _ in got), got
+    assert sum(s for _, _, s, _ in got) == sum(r for _, _, _, r in got) > 0      # every plane sent was received

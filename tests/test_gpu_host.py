@@ -481,3 +481,46 @@ def test_evaluator_splits_batches_over_devices(testrun):
     assert np.abs(got[:, :2] - c1[:5]).max() < 1e-6
     r = subprocess.run([hostlib.CLI, "-batch", "vec5.txt", "-devices", "7,99"], cwd=testrun, capture_output=True, text=True)
     assert "runtime error caught: no such CUDA device in device list" in r.stdout
+
+
+def test_one_model_over_z_slabs_in_the_cxx_host(testrun, golden):
+    """BASELINE config 4's sharding in the product's own C++ host: `EKGSIM_B200_SLABS` / `ekgSim -slabs` spreads ONE model
+    over several GPUs -- every device sums the ECG over its z-slab, the facade adds the partial ECGs, the excitation
+    sequence comes from the peer-linked automaton over the same slabs (one kernel per device, face planes through peer
+    memory).  "0,0,0" puts three slabs on GPU 0, so the whole path runs on a single-GPU box; "all" uses every GPU.
+    Same criteria as the unsharded evaluator, same console contract."""
+    names = list(golden["name"])
+    i = names.index("full1")
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    ev1 = hostlib.Evaluator(testrun, with_device=True)
+    c1, v1 = ev1.eval(golden["params"][i])
+    cb1, vb1 = ev1.eval_batch(g["params"][:9])
+    ev1.close()
+    for spec in ("0,0,0", "all", "0,0"):
+        ev = hostlib.Evaluator(testrun, slabs=spec)
+        c, v = ev.eval(golden["params"][i])
+        cb, vb = ev.eval_batch(g["params"][:9])
+        ev.close()
+        assert np.abs(c - golden["criteria"][i]).max() < 1e-4 and v == v1, (spec, c)
+        assert np.abs(c - c1).max() < 1e-6, (spec, c, c1)
+        assert np.abs(cb - cb1).max() < 1e-6 and (vb == vb1).all(), spec
+    # the CLI spelling; stderr says how the excitation sequence was computed
+    r = subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-out", "result", "-slabs", "0,0,0,0"], cwd=testrun, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "one model on 4 z-slabs (peer-linked excitation sequence)" in r.stderr, r.stderr
+    m = re.search(r" criteria = <([0-9.e+-]+),([0-9.e+-]+)>, violation = ([0-9.e+-]+)\n", r.stdout)
+    assert m, r.stdout
+    assert abs(float(m.group(1)) - golden["criteria"][i][0]) < 1e-4 and abs(float(m.group(2)) - golden["criteria"][i][1]) < 1e-4
+    assert m.group(3) == "240.609"
+    lines = open(os.path.join(testrun, "result.column")).read().split("\n")
+    vals = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in lines[3:]]).T
+    peak = np.abs(golden["ecg"][i]).max(axis=1, keepdims=True)
+    assert (np.abs(vals - golden["ecg"][i]) / peak).max() < 1e-5 + 5e-6
+    # the replicated automaton as the fallback (devices without native peer atomics take this path by themselves)
+    env = dict(os.environ, EKGSIM_B200_SLAB_AUTOMATON="replicated")
+    r = subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-slabs", "2"], cwd=testrun, capture_output=True, text=True, env=env)
+    if "no such CUDA device" not in r.stdout:      # a one-GPU box has no device 1
+        assert "one model on 2 z-slabs (replicated excitation sequence)" in r.stderr, r.stderr
+        assert m.group(0) in r.stdout
+    r = subprocess.run([hostlib.CLI, "test", "-sim", README_VECTOR, "-slabs", "0,99"], cwd=testrun, capture_output=True, text=True)
+    assert "runtime error caught: no such CUDA device in slab list" in r.stdout
