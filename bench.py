@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--ref-length", type=int, default=24, help="time samples per reference sample run")
     ap.add_argument("--ref-full", action="store_true",
                     help="cpu_baseline: additionally time ONE process of the reference at the full 400 samples (~210 s)")
+    ap.add_argument("--no-heart-cli", action="store_true", help="skip the C++-host leg of the config-4 block (ekgSim -slabs N on a text model)")
     ap.add_argument("--no-heart", action="store_true", help="skip the config-4 block (synthetic finer heart, z-slabs + all-reduce)")
     ap.add_argument("--heart-factor", type=int, default=4)
     ap.add_argument("--heart-steps", type=int, default=3)
@@ -376,6 +377,57 @@ def heart_block(args, rank, world, local):
         if "automaton_sharded" not in out or "ms" not in out["automaton_sharded"]:
             out["automaton_sharded"] = dict(info, **out.get("automaton_sharded", {}))
     model.close()
+    if rank == 0 and not args.no_heart_cli:
+        try:
+            out["cxx_host"] = heart_cli_block(f, world)
+        except Exception as e:   # the CLI leg is extra evidence, never a reason to lose the line
+            out["cxx_host"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
+def heart_cli_block(f, n_gpus):
+    """Config 4 as a user of the reference runs it: `ekgSim test -sim <16 params> -out result` in a directory whose
+    simulator.ini names the f-times finer heart (a 208 MB text .matrix at f = 4), with `-slabs N`: the product's C++
+    host spreads the one model over the N GPUs (z-slabs, peer-linked automaton, slab ECGs added).  The reference needs
+    ~114 s for the excitation sequence and ~3.6 h for the simulation of this model on one core."""
+    import ekgio
+    cli = os.path.join(ROOT, "ekgsim_b200", "bin", "ekgSim")
+    vec = "0.00035813,0.0890636,0.0632915,226.183,0.000369406,0.0965625,0.0523254,232.278,0.000710767,0.0720323,0.0187579,200.93,23,22,15,13"
+    out = {"command": "ekgSim test -sim <README vector> -out result -slabs %d" % n_gpus, "factor": f}
+    with tempfile.TemporaryDirectory(prefix="ekg_heart_cli_") as d:
+        t0 = time.time()
+        ekgio.materialise_heart(d, f)
+        out["write_text_model_s"] = time.time() - t0
+        env = dict(os.environ)
+        for k in ("EKGSIM_B200_DEVICE", "EKGSIM_B200_DEVICES", "EKGSIM_B200_SLABS"):
+            env.pop(k, None)
+        env["EKGSIM_B200_CACHE"] = "1"     # the first run leaves a binary side-car of the shape file, the second one uses it
+        runs = []
+        for slabs, label in ((n_gpus, "first_run_text_model"), (n_gpus, "second_run_binary_side_car"), (1, "one_gpu_second_run")):
+            if label == "one_gpu_second_run" and n_gpus == 1:
+                continue
+            t0 = time.time()
+            r = subprocess.run([cli, "test", "-sim", vec, "-out", "result"] + (["-slabs", str(slabs)] if slabs > 1 else []), cwd=d,
+                               capture_output=True, text=True, env=env)
+            wall = time.time() - t0
+            def timer(label_re):
+                m = re.search(label_re + r"\s+done \(([0-9.e+-]+)s\)", r.stderr)
+                return float(m.group(1)) if m else None
+            m = re.search(r" simulation done in ([0-9.e+-]+) seconds", r.stdout)
+            c = re.search(r" criteria = <([0-9.e+-]+),([0-9.e+-]+)>, violation = ([0-9.e+-]+)", r.stdout)
+            k = re.search(r"one model on (\d+) z-slabs \((\S+) excitation sequence\)", r.stderr)
+            runs.append({"run": label, "gpus": slabs, "process_wall_s": wall, "loading_shape_s": timer("loading shape"),
+                         "excitation_sequence_s": timer("calculating excitation sequence"),
+                         "eval_s_fit_plus_simulation_plus_criteria": float(m.group(1)) if m else None,
+                         "criteria": [float(c.group(1)), float(c.group(2))] if c else None,
+                         "slabs": int(k.group(1)) if k else 1, "automaton": k.group(2) if k else "single device",
+                         "ok": bool(r.returncode == 0 and m and c)})
+            if not runs[-1]["ok"]:
+                runs[-1]["tail"] = (r.stdout + r.stderr)[-400:]
+        out["runs"] = runs
+        cs = [x["criteria"] for x in runs if x["criteria"]]
+        if len(cs) > 1:
+            out["criteria_max_abs_diff_between_runs"] = max(abs(a - b) for c in cs[1:] for a, b in zip(c, cs[0]))
     return out
 
 

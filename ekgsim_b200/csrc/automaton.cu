@@ -43,6 +43,10 @@
 
 #include <unistd.h>
 
+#include <algorithm>
+#include <map>
+#include <mutex>
+
 #include "ekg_internal.cuh"
 
 namespace cg = cooperative_groups;
@@ -777,6 +781,34 @@ constexpr uint64_t kLinkMagic = 0x454b474c494e4b31ull;   // "EKGLINK1"
 
 static int64_t this_pid() { return (int64_t)getpid(); }
 
+// Peer access this library switched on, per (device, peer device), counted over the linked handles of the process: with
+// peer access enabled every later cudaMalloc on the device also maps the allocation for the peer (milliseconds each), so
+// the last unlink switches it off again.  Access that was already on (NCCL, the application) is left alone.
+static std::mutex g_peer_mutex;
+static std::map<std::pair<int, int>, int> g_peer_refs;
+
+static cudaError_t peer_acquire(int dev, int peer) {
+	std::lock_guard<std::mutex> lock(g_peer_mutex);
+	int& refs = g_peer_refs[std::make_pair(dev, peer)];
+	if (refs > 0) { ++refs; return cudaSuccess; }
+	const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+	if (e == cudaSuccess) { refs = 1; return e; }
+	cudaGetLastError();
+	g_peer_refs.erase(std::make_pair(dev, peer));
+	return e == cudaErrorPeerAccessAlreadyEnabled ? cudaSuccess : e;   // somebody else's: not ours to switch off
+}
+
+static void peer_release(int dev, int peer) {
+	std::lock_guard<std::mutex> lock(g_peer_mutex);
+	auto it = g_peer_refs.find(std::make_pair(dev, peer));
+	if (it == g_peer_refs.end()) return;
+	if (--it->second == 0) {
+		g_peer_refs.erase(it);
+		cudaDeviceDisablePeerAccess(peer);
+		cudaGetLastError();
+	}
+}
+
 int shard_link_info(ekg_model* m, void* info_out) {
 	LinkInfo li;
 	memset(&li, 0, sizeof li);
@@ -797,6 +829,7 @@ int shard_link_info(ekg_model* m, void* info_out) {
 int shard_unlink(ekg_model* m) {
 	if (m->link.launched) { cudaStreamSynchronize(m->stream); m->link.launched = false; }
 	for (void* p : m->link.ipc_opened) cudaIpcCloseMemHandle(p);
+	for (int peer : m->link.peers_acquired) peer_release(m->device, peer);
 	if (m->link.ev0) cudaEventDestroy(m->link.ev0);
 	if (m->link.ev1) cudaEventDestroy(m->link.ev1);
 	m->link = ekg_model::PeerLink();
@@ -820,7 +853,11 @@ int shard_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int
 	for (int r = rank + 1; r < n_ranks && live; ++r) if (slabs[2 * r + 1] > slabs[2 * r]) { L.above = r; break; }
 	L.time.assign((size_t)n_ranks, nullptr);
 	L.state.assign((size_t)n_ranks, nullptr);
-	auto bail = [&](int code, const std::string& msg) { for (void* p : L.ipc_opened) cudaIpcCloseMemHandle(p); return fail(code, msg); };
+	auto bail = [&](int code, const std::string& msg) {
+		for (void* p : L.ipc_opened) cudaIpcCloseMemHandle(p);
+		for (int peer : L.peers_acquired) peer_release(m->device, peer);
+		return fail(code, msg);
+	};
 	for (int r = 0; r < n_ranks; ++r) {
 		LinkInfo p;
 		memcpy(&p, (const char*)infos + (size_t)r * EKG_LINK_INFO_BYTES, sizeof p);
@@ -838,10 +875,10 @@ int shard_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int
 			}
 		}
 		if (p.pid == this_pid()) {
-			if (p.device != m->device) {
-				cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
-				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(EKG_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
-				cudaGetLastError();
+			if (p.device != m->device && std::find(L.peers_acquired.begin(), L.peers_acquired.end(), p.device) == L.peers_acquired.end()) {
+				const cudaError_t e = peer_acquire(m->device, p.device);
+				if (e != cudaSuccess) return bail(EKG_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+				L.peers_acquired.push_back(p.device);
 			}
 			L.time[(size_t)r] = (double*)(uintptr_t)p.time_ptr;
 			L.state[(size_t)r] = (int*)(uintptr_t)p.state_ptr;

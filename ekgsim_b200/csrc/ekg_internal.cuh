@@ -211,6 +211,7 @@ struct ekg_model {
 		std::vector<double*> time;                             // every rank's d_time_pad as seen from this device (own entry = ours)
 		std::vector<int*> state;                               // every rank's d_brick_state
 		std::vector<void*> ipc_opened;                         // what cudaIpcCloseMemHandle has to release
+		std::vector<int> peers_acquired;                       // devices whose peer access this link holds a reference on
 		bool launched = false;
 		cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 		float kernel_ms = 0.f;

@@ -269,6 +269,9 @@ private:
 		forEachSlab([&](size_t d) { if (ekg_model_activation_linked_wait(slabModels_[d], nullptr, nullptr) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
 		forEachSlab([&](size_t d) { if (ekg_model_activation_linked_gather(slabModels_[d]) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
 		forEachSlab([&](size_t d) { if (ekg_model_activation_end(slabModels_[d], nullptr) != EKG_OK) throw std::runtime_error(ekg_last_error()); });
+		// the mappings are only needed while the automaton runs; with peer access left on, every later allocation on these
+		// devices would be mapped for all the peers as well
+		for (ekg_model* m : slabModels_) ekg_model_activation_unlink(m);
 	}
 
 	static PositionVec cross(const PositionVec& a, const PositionVec& b) {
