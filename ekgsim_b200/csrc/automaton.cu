@@ -91,15 +91,34 @@ __global__ void __launch_bounds__(256) automaton_kernel(AutoArgs a) {
 	(void)inf;
 }
 
-// Work queue of the frontier automaton: a ring of brick ids.  A brick is in the ring at most once
-// (flag[b] = 1 from push to pop), so n_live slots can never overflow.  `pending` counts bricks that
-// are queued or being processed; it can only reach 0 when the whole field is at its fixed point.
-__device__ __forceinline__ void brick_push(const BrickArgs& a, int b) {
-	if (atomicExch(a.flag + b, 1) == 0) {
-		atomicAdd(a.counters + 2, 1);                                   // pending
-		const unsigned pos = atomicAdd((unsigned*)a.counters + 1, 1u);  // tail
-		atomicExch(a.queue + (pos & a.qmask), b);                       // publish (slot was -1)
+// Work queue of the frontier automaton: kBrickBuckets rings of brick ids, one per time bucket (ekg_internal.cuh).  A brick
+// is in the rings at most once (flag[b] = 1 from push to pop), so the qmask + 1 slots of a ring can never overflow.
+// `pending` counts bricks that are queued or being processed; it can only reach 0 when the whole field is at its fixed
+// point.  FIFO mode uses ring 0 alone: consumers claim the next position with one atomicAdd on the head and wait there,
+// producers hand their bricks to the waiting positions.  Time-bucket mode must not bind a warp to a ring that may stay
+// empty for long, so every ring also counts `published - taken`: a consumer first takes one off that count and only
+// with a positive result claims a position (whose slot a producer has filled or is about to); losing the race for the
+// last brick of a bucket costs two atomics on the count and no ring position.
+
+// n bricks (ids in lanes `pushers`) into the ring of time bucket `bucket` of the queue at (ring, cnt): one tail
+// reservation for all of them; SYS = the queue lives in another GPU's memory
+template <bool SYS>
+__device__ __forceinline__ void ring_publish(int* ring, int* cnt, uint32_t qmask, int bucket, int nb, int lane) {
+	constexpr unsigned kFull = 0xffffffffu;
+	const int r = bucket & (kBrickBuckets - 1);
+	int* slots = ring + (size_t)r * (qmask + 1u);
+	const unsigned pushers = __ballot_sync(kFull, nb >= 0);
+	const int n = __popc(pushers);
+	unsigned base = 0;
+	if (lane == 0) base = SYS ? atomicAdd_system((unsigned*)cnt + kCntTail + r, (unsigned)n) : atomicAdd((unsigned*)cnt + kCntTail + r, (unsigned)n);
+	base = __shfl_sync(kFull, base, 0);
+	if (nb >= 0) {
+		int* slot = slots + ((base + __popc(pushers & ((1u << lane) - 1u))) & qmask);
+		if (SYS) atomicExch_system(slot, nb); else atomicExch(slot, nb);
 	}
+	if (SYS) __threadfence_system(); else __threadfence();
+	__syncwarp();
+	if (lane == 0) { if (SYS) atomicAdd_system(cnt + kCntCount + r, n); else atomicAdd(cnt + kCntCount + r, n); }   // takers may come now
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -163,35 +182,36 @@ __device__ __forceinline__ unsigned reach27(int cz, int cy, int cx) {
 
 // Queue, in the ring of the neighbouring rank whose brick state is `pstate`, those of its bricks among `reach` (reach27
 // bits relative to our brick b) that it relaxes.  Our improved times have been written to its grid and fenced before.
-__device__ __forceinline__ void link_push(const BrickArgs& a, int* pstate, unsigned reach, uint8_t owner, int b, int lane) {
+__device__ __forceinline__ void link_push(const BrickArgs& a, int* pstate, unsigned reach, uint8_t owner, int b, int lane, float key) {
 	constexpr unsigned kFull = 0xffffffffu;
 	int* pflag = pstate;
 	int* pring = pstate + 2 * (size_t)a.n_live;
-	int* pcnt = pring + (a.qmask + 1u);
+	int* pcnt = pring + (size_t)kBrickBuckets * (a.qmask + 1u);
 	int nb = -1;
 	if (lane < 27 && ((reach >> lane) & 1u)) {
 		nb = lane == 13 ? b : __ldg(a.nbr + (size_t)b * 26 + (lane > 13 ? lane - 1 : lane));
 		if (nb >= 0 && !(a.own[nb] & owner)) nb = -1;
-		if (nb >= 0 && atomicExch_system(pflag + nb, 1) != 0) nb = -1;   // already in its ring: whoever pops it reads our times
+		if (nb >= 0 && atomicExch_system(pflag + nb, 1) != 0) nb = -1;   // already in its queue: whoever pops it reads our times
 	}
 	const unsigned pushers = __ballot_sync(kFull, nb >= 0);
 	const int n_push = __popc(pushers);
 	if (!n_push) return;
-	unsigned base = 0;
+	int bucket = 0;
 	if (lane == 0) {
 		atomicAdd(a.counters + 8, n_push);                                      // sent -- before the work shows up over there
 		__threadfence_system();
 		atomicAdd_system(pcnt + 2, n_push);                                     // its pending: the rank is busy from here on
-		base = atomicAdd_system((unsigned*)pcnt + 1, (unsigned)n_push);         // its tail
+		const int cur = *(volatile int*)(pcnt + 1);                             // its window of time buckets
+		bucket = min(max((int)(key * a.inv_delta), cur), cur + kBucketsAhead - 1);
 	}
-	base = __shfl_sync(kFull, base, 0);
-	if (nb >= 0) atomicExch_system(pring + ((base + __popc(pushers & ((1u << lane) - 1u))) & a.qmask), nb);
+	bucket = __shfl_sync(kFull, bucket, 0);
+	ring_publish<true>(pring, pcnt, a.qmask, bucket, nb, lane);
 	__threadfence_system();
 	__syncwarp();
 	if (lane == 0) atomicAdd_system(pcnt + 9, n_push);                          // received -- after its pending went up
 }
 
-template <int NBR, bool LINKED>
+template <int NBR, bool LINKED, bool TIMED>
 __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(BrickArgs a) {
 	__shared__ double s_t_all[kBrickWarps][kBrickCells];
 	__shared__ uint8_t s_l_all[kBrickWarps][kBrickCells];
@@ -228,34 +248,104 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 	unsigned long long t_begin = 0;
 	if (LINKED) t_begin = global_ns();
 
+	volatile int* vcur = a.counters + 1;
+	volatile unsigned* vhead = (volatile unsigned*)a.counters + kCntHead;
+	volatile int* vcount = a.counters + kCntCount;
+	int given_up = 0;
+
 	for (;;) {   // one warp per brick, no barrier wider than the warp anywhere in here
 		int b = -1;
-		if (lane == 0) {
-			// bounded run: once `budget` ring positions have been claimed nobody claims another one; the bricks still
-			// flagged as queued are carried into the next relaxation by the host (flag[] is authoritative, the ring is rebuilt)
-			if (!LINKED && a.budget && (*(volatile unsigned*)a.counters >= a.budget || vstop[0])) { vstop[0] = 1; b = -2; }
-			if (LINKED && vverdict[0]) b = -2;
-			const unsigned pos = b == -2 ? 0u : atomicAdd((unsigned*)a.counters + 0, 1u);   // head: claim a ring position
-			unsigned nap = 40;
-			for (unsigned spins = 0; b != -2; ++spins) {
-				b = vq[pos & a.qmask];
-				if (b >= 0) { vq[pos & a.qmask] = -1; break; }
-				if (LINKED) {
-					// an idle rank waits for work from its neighbours until rank 0 has seen every rank idle with nothing in flight
-					if (vverdict[0]) { b = -2; break; }
-					if ((spins & 255u) == 255u && global_ns() - t_begin > kLinkTimeoutNs) { atomicAdd(a.counters + 3, 1); b = -2; break; }
-					if (spins > 32u && nap < 1000u) nap += nap >> 2;          // long waits poll less often (<= 1 us)
-				} else {
-					if (*vpending == 0) { b = -2; break; }                       // nothing queued, nobody working: done
-					if (a.budget && vstop[0]) { b = -2; break; }                 // bounded run over: the producers have left
-					// a warp that found nothing for seconds retires (never spins forever, whatever happens);
-					// the host reports non-convergence if work was still pending when the last warp left
-					if (spins > (1u << 25)) { b = -2; break; }
+		if (!TIMED) {
+			// one FIFO ring: a warp claims the next position and waits there; waiting warps line up behind the tail, whoever
+			// queues a brick hands it to the first of them
+			if (lane == 0) {
+				// bounded run: once `budget` ring positions have been claimed nobody claims another one; the bricks still
+				// flagged as queued are carried into the next relaxation by the host (flag[] is authoritative, the ring is rebuilt)
+				if (!LINKED && a.budget && (vhead[0] >= a.budget || vstop[0])) { vstop[0] = 1; b = -2; }
+				if (LINKED && vverdict[0]) b = -2;
+				const unsigned pos = b == -2 ? 0u : atomicAdd((unsigned*)a.counters + kCntHead, 1u);   // head: claim a ring position
+				unsigned nap = 40;
+				for (unsigned spins = 0; b != -2; ++spins) {
+					b = vq[pos & a.qmask];
+					if (b >= 0) { vq[pos & a.qmask] = -1; break; }
+					if (LINKED) {
+						// an idle rank waits for work from its neighbours until rank 0 has seen every rank idle with nothing in flight
+						if (vverdict[0]) { b = -2; break; }
+						if ((spins & 255u) == 255u && global_ns() - t_begin > kLinkTimeoutNs) { atomicAdd(a.counters + 3, 1); b = -2; break; }
+						if (spins > 32u && nap < 1000u) nap += nap >> 2;          // long waits poll less often (<= 1 us)
+					} else {
+						if (*vpending == 0) { b = -2; break; }                       // nothing queued, nobody working: done
+						if (a.budget && vstop[0]) { b = -2; break; }                 // bounded run over: the producers have left
+						// a warp that found nothing for seconds retires (never spins forever, whatever happens);
+						// the host reports non-convergence if work was still pending when the last warp left
+						if (spins > (1u << 25)) { b = -2; break; }
+					}
+					__nanosleep(nap);
 				}
+			}
+			b = __shfl_sync(kFull, b, 0);
+		} else {
+			// time buckets: take a brick from the earliest bucket that holds one.  Lane i looks at bucket cur - kBucketsBehind + i:
+			// the buckets behind cur catch bricks that were queued with a `cur` read just before the window moved on, new
+			// bricks go into [cur, cur + kBucketsAhead), the rings in between are only ever reached by bricks queued with a
+			// very stale `cur` (taken like any other, but they do not move the window).
+			unsigned nap = 40;
+			for (unsigned spins = 0; b == -1; ++spins) {
+				int quit = 0;
+				if (lane == 0) {
+					if (!LINKED && a.budget && (*(volatile unsigned*)a.counters >= a.budget || vstop[0])) { vstop[0] = 1; quit = 1; }   // bounded run
+					if (LINKED && vverdict[0]) quit = 1;
+				}
+				const int cur = vcur[0];
+				const int bk = cur - kBucketsBehind + lane;
+				bool avail = false;
+				if (lane < kBrickBuckets && bk >= 0) avail = vcount[bk & (kBrickBuckets - 1)] > 0;
+				const unsigned have = __ballot_sync(kFull, avail);
+				quit = __shfl_sync(kFull, quit, 0);
+				const int cur0 = __shfl_sync(kFull, cur, 0);
+				if (quit) { b = -2; break; }
+				if (have) {
+					const int sel = __ffs(have) - 1;
+					const int sbk = __shfl_sync(kFull, bk, sel), r = sbk & (kBrickBuckets - 1);
+					int v = -1;
+					if (lane == 0) {
+						if (atomicSub(a.counters + kCntCount + r, 1) <= 0) {   // others took what there was
+							atomicAdd(a.counters + kCntCount + r, 1);
+							++given_up;
+						} else {
+							const unsigned pos = atomicAdd((unsigned*)a.counters + kCntHead + r, 1u);   // ours: a position of that ring
+							volatile int* slot = vq + (size_t)r * (a.qmask + 1u) + (pos & a.qmask);
+							// as many bricks have been published as positions handed out, ours is there or about to be (a producer
+							// with an earlier reservation may publish after a later one); never wait forever all the same
+							for (unsigned w = 0; (v = *slot) < 0 && w < (1u << 22); ++w) __nanosleep(20);
+							if (v >= 0) {
+								*slot = -1;
+								if (sbk > cur0 && sbk < cur0 + kBucketsAhead) atomicMax(a.counters + 1, sbk);   // nothing earlier is queued: the window moves on
+								if (!LINKED && a.budget) atomicAdd((unsigned*)a.counters, 1u);
+							} else {
+								atomicAdd(a.counters + 3, 1);   // the queue is broken: give up, the host reports it
+								v = -2;
+							}
+						}
+					}
+					b = __shfl_sync(kFull, v, 0);
+					continue;   // b == -1: look again
+				}
+				int idle_quit = 0;
+				if (lane == 0) {
+					if (LINKED) {
+						if ((spins & 255u) == 255u && global_ns() - t_begin > kLinkTimeoutNs) { atomicAdd(a.counters + 3, 1); idle_quit = 1; }
+					} else {
+						if (*vpending == 0) idle_quit = 1;                  // nothing queued, nobody working: done
+						if (a.budget && vstop[0]) idle_quit = 1;            // bounded run over: the producers have left
+						if (spins > (1u << 22)) idle_quit = 1;              // never spin forever (the host reports non-convergence)
+					}
+				}
+				if (__shfl_sync(kFull, idle_quit, 0)) { b = -2; break; }
+				if (spins > 32u && nap < 2000u) nap += nap >> 2;            // long waits poll less often (<= 2 us)
 				__nanosleep(nap);
 			}
 		}
-		b = __shfl_sync(kFull, b, 0);
 		if (b < 0) break;
 		int first_i = 0;   // start bricks: reached voxels count as changed on the first visit
 		if (lane == 0) {
@@ -305,6 +395,7 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 		// two warps may hold the same brick at once).  Queue a neighbouring brick only if one of ITS cells
 		// (our halo copy of it, never smaller than its current value) would improve through a changed voxel.
 		unsigned bits = 0, reach_dn = 0, reach_up = 0;
+		float kmin = 3.0e38f;
 		int vz0 = 0;
 		if (LINKED) vz0 = (int)(origin / a.link.plane) - 1;   // voxel plane of the brick's first cell
 #pragma unroll
@@ -329,6 +420,7 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 			}
 			const bool on_face = cz[o] == 0 || cz[o] == kBrick - 1 || cy[o] == 0 || cy[o] == kBrick - 1 || cx[o] == 0 || cx[o] == kBrick - 1;
 			if (!on_face || !(improved || (first && tf < inf))) continue;
+			if (TIMED) kmin = fminf(kmin, (float)tf);
 #pragma unroll
 			for (int k = 0; k < NBR; ++k) {
 				const int qq = loc[o] - a.loff[k];
@@ -347,14 +439,17 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 			}
 		}
 		bits = __reduce_or_sync(kFull, bits);
+		// the time bucket everything this visit queues goes into: that of the earliest voxel it changed
+		float key = 0.f;
+		if (TIMED) key = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(kmin)));   // positive floats order like their bits
 		if (LINKED) {
 			reach_dn = __reduce_or_sync(kFull, reach_dn);
 			reach_up = __reduce_or_sync(kFull, reach_up);
 			if (reach_dn | reach_up) {
 				__threadfence_system();   // our times are in the neighbours' grids before their bricks are told to look
 				__syncwarp();
-				if (reach_dn) link_push(a, a.link.state_dn, reach_dn, kOwnBelow, b, lane);
-				if (reach_up) link_push(a, a.link.state_up, reach_up, kOwnAbove, b, lane);
+				if (reach_dn) link_push(a, a.link.state_dn, reach_dn, kOwnBelow, b, lane, key);
+				if (reach_up) link_push(a, a.link.state_up, reach_up, kOwnAbove, b, lane, key);
 			}
 		}
 		__threadfence();   // our improved times are visible before anyone is told to look at them
@@ -368,16 +463,21 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 		}
 		const unsigned pushers = __ballot_sync(kFull, nb >= 0);
 		const int n_push = __popc(pushers);
-		unsigned base = 0;
+		int bucket = 0;
 		if (lane == 0) {
 			// (linked run: this is where our brick stops counting as work -- after everything it caused elsewhere is accounted for)
 			if (n_push != 1) atomicAdd(a.counters + 2, n_push - 1);        // pending += pushes - (this brick done)
-			if (n_push) base = atomicAdd((unsigned*)a.counters + 1, (unsigned)n_push);
+			if (TIMED && n_push) {
+				const int cur = vcur[0];
+				bucket = min(max((int)(key * a.inv_delta), cur), cur + kBucketsAhead - 1);
+			}
 		}
-		base = __shfl_sync(kFull, base, 0);
-		if (nb >= 0) atomicExch(a.queue + ((base + __popc(pushers & ((1u << lane) - 1u))) & a.qmask), nb);
+		if (n_push) {
+			if (TIMED) bucket = __shfl_sync(kFull, bucket, 0);
+			ring_publish<false>(a.queue, a.counters, a.qmask, bucket, nb, lane);
+		}
 	}
-	if (lane == 0 && visits) { atomicAdd(a.counters + 4, visits); atomicAdd(a.counters + 5, sweeps); }
+	if (lane == 0 && visits) { atomicAdd(a.counters + 4, visits); atomicAdd(a.counters + 5, sweeps); if (given_up) atomicAdd(a.counters + 11, given_up); }
 	if (LINKED) {
 		remote_cells = __reduce_add_sync(kFull, remote_cells);
 		if (lane == 0 && remote_cells) atomicAdd(a.counters + 10, remote_cells);
@@ -465,25 +565,56 @@ int run_automaton(ekg_model* m, int64_t* sweeps_out) {
 
 static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* visits_out, int64_t budget = 0, int64_t* leftover_out = nullptr);
 
-static int64_t ring_capacity(int64_t n) {
-	int64_t cap = 1;
-	while (cap < std::max<int64_t>(n, 2)) cap <<= 1;
-	return cap;
+static int64_t ring_capacity(int64_t n) { return brick_ring_capacity(n); }
+
+// Time buckets pay off when the frontier is wider than the machine (then the order of the visits is the queue's choice);
+// a small model is bound by the wave's critical path, every queued brick is taken at once, and the FIFO ring's hand-off
+// (waiting warps line up behind the tail) has the shorter latency.  EKGSIM_B200_AUTOMATON_QUEUE=timed|fifo overrides.
+static bool use_time_buckets(const ekg_model* m) {
+	if (!(m->brick_delta > 0.f)) return false;
+	if (const char* e = getenv("EKGSIM_B200_AUTOMATON_QUEUE")) {
+		if (std::string(e) == "timed") return true;
+		if (std::string(e) == "fifo") return false;
+	}
+	return m->n_bricks >= (int64_t)m->sm_count * 2 * kBrickWarps * 12;   // >= 12 bricks per resident warp
+}
+
+// start bricks: flagged, first visit pending, queued in ring 0
+__global__ void brick_seed_kernel(const int32_t* __restrict__ starts, int n0, int n_live, int* __restrict__ flag, int* __restrict__ first,
+                                  int* __restrict__ ring0, int* __restrict__ counters) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n0) {
+		const int b = starts[i];
+		flag[b] = 1;
+		first[b] = 1;
+		ring0[i] = b;
+	}
+	if (i == 0) { counters[kCntTail] = n0; counters[kCntCount] = n0; counters[2] = n0; }
 }
 
 static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
 	const int64_t cap = ring_capacity(n);
-	// state = flag[n] | first_visit[n] | ring[cap] | counters[kBrickCounters]   (allocated as 5n + 32 ints; cap <= max(2n, 2))
-	std::vector<int> h((size_t)(2 * n + cap + kBrickCounters), 0);
-	std::fill(h.begin() + 2 * n, h.begin() + 2 * n + cap, -1);
-	int n0 = 0;
-	for (int32_t b : m->h_start_bricks) { h[(size_t)b] = 1; h[(size_t)(n + b)] = 1; h[(size_t)(2 * n + n0++)] = b; }
-	h[(size_t)(2 * n + cap + 1)] = n0;   // tail
-	h[(size_t)(2 * n + cap + 2)] = n0;   // pending
-	EKG_CUDA(cudaMemcpyAsync(m->d_brick_state, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-	EKG_CUDA(cudaStreamSynchronize(st));  // pageable source
+	// state = flag[n] | first_visit[n] | rings[kBrickBuckets][cap] | counters[kBrickCounters], initialised on the device (the
+	// rings of a 4x heart are 64 MB); the start bricks go into ring 0
+	int* flag = m->d_brick_state;
+	int* ring = flag + 2 * n;
+	int* counters = ring + kBrickBuckets * cap;
+	const int n0 = (int)m->h_start_bricks.size();
+	int32_t* d_sb = nullptr;
+	EKG_CUDA(cudaMalloc(&d_sb, std::max<size_t>(n0, 1) * sizeof(int32_t)));
+	cudaError_t e = cudaMemcpyAsync(d_sb, m->h_start_bricks.data(), (size_t)n0 * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess && n > 0) e = cudaMemsetAsync(flag, 0, (size_t)(2 * n) * sizeof(int), st);
+	if (e == cudaSuccess) e = cudaMemsetAsync(ring, 0xff, (size_t)((use_time_buckets(m) ? kBrickBuckets : 1) * cap) * sizeof(int), st);   // -1 = empty slot
+	if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, kBrickCounters * sizeof(int), st);
+	if (e == cudaSuccess) {
+		brick_seed_kernel<<<(n0 + 127) / 128 + 1, 128, 0, st>>>(d_sb, n0, (int)n, flag, flag + n, ring, counters);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // the start list is a host vector
+	cudaFree(d_sb);
+	if (e != cudaSuccess) return cuda_fail(e, "brick state initialisation", __FILE__, __LINE__);
 	return launch_bricks(m, nullptr, rounds_out);
 }
 
@@ -494,13 +625,14 @@ static void fill_brick_args(ekg_model* m, const uint8_t* d_own, int64_t budget, 
 	int* flag = m->d_brick_state;
 	int* first = flag + n;
 	int* ring = first + n;
-	int* counters = ring + cap;
+	int* counters = ring + kBrickBuckets * cap;
 	a = BrickArgs{};
 	a.layer = m->d_layer_pad; a.time = m->d_time_pad; a.wtab = m->d_wtab;
 	a.origin = m->d_brick_origin; a.nbr = m->d_brick_nbr; a.own = d_own;
 	a.flag = flag; a.first_visit = first; a.queue = ring; a.counters = counters; a.qmask = (uint32_t)(cap - 1);
 	a.n_live = (int32_t)n; a.nl1 = m->n_layers + 1; a.pY = (int32_t)m->pY; a.pX = (int32_t)m->pX;
 	a.budget = (uint32_t)std::min<int64_t>(std::max<int64_t>(budget, 0), 0x7fffffff);
+	a.inv_delta = use_time_buckets(m) ? 1.0f / m->brick_delta : 0.f;
 	NbrTable nb;
 	make_nbr_table(m->Z > 1 ? EKG_NBHD_3D8 : EKG_NBHD_2D8, &nb);  // simulator.cpp:251-254
 	a.n_nbr = nb.n;
@@ -522,7 +654,9 @@ static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out
 	const size_t dyn = a.w_in_smem ? (size_t)a.nl1 * a.nl1 * 3 * sizeof(double) : 0;
 	int per_sm = 0;
 	const int threads = 32 * kBrickWarps;
-	void* kfun = a.n_nbr == 26 ? (void*)automaton_brick_kernel<26, false> : (void*)automaton_brick_kernel<8, false>;
+	const bool timed = a.inv_delta > 0.f;
+	void* kfun = a.n_nbr == 26 ? (timed ? (void*)automaton_brick_kernel<26, false, true> : (void*)automaton_brick_kernel<26, false, false>)
+	                           : (timed ? (void*)automaton_brick_kernel<8, false, true> : (void*)automaton_brick_kernel<8, false, false>);
 	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
 	// every CTA must be resident (waiting warps spin on the ring): never launch more than fit
@@ -534,7 +668,12 @@ static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out
 	EKG_CUDA(cudaStreamSynchronize(st));
 	if (rounds_out) *rounds_out = hc[4];   // brick visits (there are no global rounds in the work-queue scheme)
 	m->last_brick_visits = hc[4];
-	if (getenv("EKGSIM_B200_DEBUG")) fprintf(stderr, "automaton bricks: visits %d inner sweeps %d pushes %d\n", hc[4], hc[5], hc[1]);
+	if (getenv("EKGSIM_B200_DEBUG")) {
+		unsigned pushes = 0;
+		for (int r = 0; r < kBrickBuckets; ++r) pushes += (unsigned)hc[kCntTail + r];
+		fprintf(stderr, "automaton bricks (%s queue, bucket %.3g ms): visits %d inner sweeps %d ring positions %u lost races %d last bucket %d\n",
+		        timed ? "time-bucket" : "fifo", timed ? 1.0 / a.inv_delta : 0.0, hc[4], hc[5], pushes, hc[11], hc[1]);
+	}
 	if (leftover_out) *leftover_out = hc[2];   // bricks still flagged as queued (bounded run)
 	else if (hc[2] != 0) return fail(EKG_E_STATE, "activation automaton did not converge");
 	return EKG_OK;
@@ -576,8 +715,9 @@ __global__ void shard_enqueue_kernel(int* __restrict__ mark, int n_live, int* __
 	mark[b] = 0;
 	flag[b] = 1;
 	first[b] = 1;
-	const unsigned pos = atomicAdd((unsigned*)counters + 1, 1u);
+	const unsigned pos = atomicAdd((unsigned*)counters + kCntTail, 1u);   // ring 0: the earliest bucket
 	ring[pos & qmask] = b;
+	atomicAdd(counters + kCntCount, 1);
 	atomicAdd(counters + 2, 1);
 }
 
@@ -626,13 +766,13 @@ static int shard_fill_ring(ekg_model* m) {
 	const int64_t cap = ring_capacity(n);
 	int* flag = m->d_brick_state;
 	int* ring = flag + 2 * n;
-	int* counters = ring + cap;
+	int* counters = ring + kBrickBuckets * cap;
 	if (n > 0) {
 		shard_carry_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(flag, m->d_brick_mark, (int)n);
 		EKG_CUDA(cudaGetLastError());
 		EKG_CUDA(cudaMemsetAsync(flag, 0, (size_t)(2 * n) * sizeof(int), st));
 	}
-	EKG_CUDA(cudaMemsetAsync(ring, 0xff, (size_t)cap * sizeof(int), st));   // -1 = empty slot
+	EKG_CUDA(cudaMemsetAsync(ring, 0xff, (size_t)(kBrickBuckets * cap) * sizeof(int), st));   // -1 = empty slot
 	EKG_CUDA(cudaMemsetAsync(counters, 0, kBrickCounters * sizeof(int), st));
 	if (n > 0) {
 		shard_enqueue_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(m->d_brick_mark, (int)n, flag, flag + n, ring, counters, (uint32_t)(cap - 1));
@@ -772,6 +912,7 @@ struct LinkInfo {
 	uint64_t magic;
 	int64_t pid;
 	int32_t device, ipc_ok;
+	int32_t timed, pad;       // work-queue mode (all ranks must agree: they push into each other's queues)
 	uint64_t time_ptr, state_ptr;
 	int64_t n_bricks, npad;
 	cudaIpcMemHandle_t time_h, state_h;
@@ -819,6 +960,7 @@ int shard_link_info(ekg_model* m, void* info_out) {
 	li.state_ptr = (uint64_t)(uintptr_t)m->d_brick_state;
 	li.n_bricks = m->n_bricks;
 	li.npad = m->pZ * m->pY * m->pX;
+	li.timed = use_time_buckets(m) ? 1 : 0;
 	li.ipc_ok = cudaIpcGetMemHandle(&li.time_h, m->d_time_pad) == cudaSuccess && cudaIpcGetMemHandle(&li.state_h, m->d_brick_state) == cudaSuccess;
 	if (!li.ipc_ok) cudaGetLastError();   // same-process links do not need the handles
 	memset(info_out, 0, EKG_LINK_INFO_BYTES);
@@ -863,6 +1005,7 @@ int shard_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int
 		memcpy(&p, (const char*)infos + (size_t)r * EKG_LINK_INFO_BYTES, sizeof p);
 		if (p.magic != kLinkMagic) return bail(EKG_E_INVALID, "not a link info record");
 		if (p.n_bricks != m->n_bricks || p.npad != m->pZ * m->pY * m->pX) return bail(EKG_E_INVALID, "the ranks hold different models");
+		if ((p.timed != 0) != use_time_buckets(m)) return bail(EKG_E_INVALID, "the ranks disagree on the work-queue mode (EKGSIM_B200_AUTOMATON_QUEUE / _DELTA)");
 		if (r == rank) { L.time[(size_t)r] = m->d_time_pad; L.state[(size_t)r] = m->d_brick_state; continue; }
 		if (p.device == m->device && p.pid == this_pid()) ++L.colocated;
 		if (p.device != m->device || p.pid != this_pid()) {
@@ -896,6 +1039,7 @@ int shard_link(ekg_model* m, int rank, int n_ranks, const void* infos, const int
 		}
 	}
 	L.active = true;
+	L.timed = use_time_buckets(m);
 	if (cudaEventCreate(&L.ev0) != cudaSuccess || cudaEventCreate(&L.ev1) != cudaSuccess) return bail(EKG_E_CUDA, "cudaEventCreate failed");
 	m->link = L;
 	return EKG_OK;
@@ -919,11 +1063,14 @@ int shard_linked_launch(ekg_model* m, int max_ctas) {
 	a.link.plane = (uint32_t)(m->pY * m->pX);
 	if (L.below >= 0) { a.link.time_dn = L.time[(size_t)L.below]; a.link.state_dn = L.state[(size_t)L.below]; }
 	if (L.above >= 0) { a.link.time_up = L.time[(size_t)L.above]; a.link.state_up = L.state[(size_t)L.above]; }
-	for (int r = 0; r < L.n_ranks; ++r) a.link.counters_of[r] = L.state[(size_t)r] + 2 * n + cap;
+	for (int r = 0; r < L.n_ranks; ++r) a.link.counters_of[r] = L.state[(size_t)r] + 2 * n + kBrickBuckets * cap;
 	const size_t dyn = a.w_in_smem ? (size_t)a.nl1 * a.nl1 * 3 * sizeof(double) : 0;
 	int per_sm = 0;
 	const int threads = 32 * kBrickWarps;
-	void* kfun = a.n_nbr == 26 ? (void*)automaton_brick_kernel<26, true> : (void*)automaton_brick_kernel<8, true>;
+	const bool timed = a.inv_delta > 0.f;
+	if (timed != L.timed) return fail(EKG_E_STATE, "the work-queue mode has changed since ekg_model_activation_link");
+	void* kfun = a.n_nbr == 26 ? (timed ? (void*)automaton_brick_kernel<26, true, true> : (void*)automaton_brick_kernel<26, true, false>)
+	                           : (timed ? (void*)automaton_brick_kernel<8, true, true> : (void*)automaton_brick_kernel<8, true, false>);
 	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
 	// our own bricks bound the useful grid (a slab is ~1/N of the model); rank 0 gives one warp to the detector
@@ -943,7 +1090,7 @@ int shard_linked_wait(ekg_model* m, int64_t* visits_out, int64_t* remote_out) {
 	if (!m->link.launched) return fail(EKG_E_STATE, "ekg_model_activation_linked_launch has not been called");
 	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
-	int* counters = m->d_brick_state + 2 * n + ring_capacity(n);
+	int* counters = m->d_brick_state + 2 * n + kBrickBuckets * ring_capacity(n);
 	int hc[kBrickCounters] = {0};
 	m->link.launched = false;
 	EKG_CUDA(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, st));

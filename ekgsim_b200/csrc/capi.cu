@@ -596,6 +596,14 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		}
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_wtab, w.size() * 8));
 		if (upload(m, m->d_wtab, w.data(), w.size() * 8)) { cleanup(); free_model(m); return EKG_E_CUDA; }
+		// time-bucket width of the automaton's work queue: what the wave needs to cross one brick inside the fastest layer
+		// (any positive value gives the same activation times, this one the fewest brick visits; EKGSIM_B200_AUTOMATON_DELTA
+		// overrides, 0 = plain FIFO)
+		double fastest = INFINITY;
+		for (int l = 1; l < nl1; ++l) { const double v = w[((size_t)l * nl1 + l) * 3]; if (v > 0 && v < fastest) fastest = v; }
+		if (!std::isfinite(fastest)) for (double v : w) if (v > 0 && v < fastest) fastest = v;
+		m->brick_delta = std::isfinite(fastest) ? (float)(fastest * kBrick) : 0.f;
+		if (const char* e = getenv("EKGSIM_B200_AUTOMATON_DELTA")) m->brick_delta = (float)std::max(0.0, atof(e));
 	}
 	// (3) live bricks (kBrick^3 tiles holding at least one occupied voxel) in brick-raster order, their origins and 26 neighbours
 	{
@@ -620,8 +628,8 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 		m->n_bricks = nb;
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_origin, (size_t)std::max<int64_t>(nb, 1) * 4));
 		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_nbr, (size_t)std::max<int64_t>(nb, 1) * 26 * 4));
-		// flag[n] | first_visit[n] | ring[capacity <= max(2n, 2)] | counters[kBrickCounters]   (automaton.cu, run_automaton_bricks)
-		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, ((size_t)nb * 5 + 32) * sizeof(int)));
+		// flag[n] | first_visit[n] | rings | counters   (automaton.cu, run_automaton_bricks)
+		EKG_CREATE_CUDA(cudaMalloc(&m->d_brick_state, (size_t)brick_state_ints(nb) * sizeof(int)));
 		brick_index_kernel<<<cb, 256, 0, st>>>(d_live, d_scan, n_cells, (int)bY, (int)bX, m->pY, m->pX, m->d_brick_index, m->d_brick_origin);
 		EKG_CREATE_CUDA(cudaGetLastError());
 		brick_nbr_kernel<<<cb, 256, 0, st>>>(m->d_brick_index, n_cells, (int)bZ, (int)bY, (int)bX, m->d_brick_nbr);
