@@ -320,7 +320,9 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 							for (unsigned w = 0; (v = *slot) < 0 && w < (1u << 22); ++w) __nanosleep(20);
 							if (v >= 0) {
 								*slot = -1;
-								if (sbk > cur0 && sbk < cur0 + kBucketsAhead) atomicMax(a.counters + 1, sbk);   // nothing earlier is queued: the window moves on
+								// nothing earlier is queued: the window moves on, one bucket per brick taken (a brick queued with a very
+								// stale `cur` shows up in a ring of the future; it must not drag the window along)
+								if (sbk > cur0 && sbk < cur0 + kBucketsAhead) atomicMax(a.counters + 1, cur0 + 1);
 								if (!LINKED && a.budget) atomicAdd((unsigned*)a.counters, 1u);
 							} else {
 								atomicAdd(a.counters + 3, 1);   // the queue is broken: give up, the host reports it
@@ -1101,8 +1103,8 @@ int shard_linked_wait(ekg_model* m, int64_t* visits_out, int64_t* remote_out) {
 	if (visits_out) *visits_out = hc[4];
 	if (remote_out) { remote_out[0] = (unsigned)hc[8]; remote_out[1] = (unsigned)hc[9]; remote_out[2] = (unsigned)hc[10]; }
 	if (getenv("EKGSIM_B200_DEBUG"))
-		fprintf(stderr, "linked automaton rank %d: visits %d inner sweeps %d, bricks queued elsewhere %u / here by others %u, cells written to neighbours %d, verdict %d, %.3f ms\n",
-		        m->link.rank, hc[4], hc[5], (unsigned)hc[8], (unsigned)hc[9], hc[10], hc[7], m->link.kernel_ms);
+		fprintf(stderr, "linked automaton rank %d: visits %d inner sweeps %d, bricks queued elsewhere %u / here by others %u, cells written to neighbours %d, last bucket %d, verdict %d, %.3f ms\n",
+		        m->link.rank, hc[4], hc[5], (unsigned)hc[8], (unsigned)hc[9], hc[10], hc[1], hc[7], m->link.kernel_ms);
 	if (hc[7] != 1 || hc[2] != 0) {
 		char buf[160];
 		snprintf(buf, sizeof buf, "linked activation automaton did not terminate cleanly (verdict %d, %d bricks pending, %d warps gave up)", hc[7], hc[2], hc[3]);
