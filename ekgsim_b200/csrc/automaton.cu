@@ -423,7 +423,9 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 			const bool on_face = cz[o] == 0 || cz[o] == kBrick - 1 || cy[o] == 0 || cy[o] == kBrick - 1 || cx[o] == 0 || cx[o] == kBrick - 1;
 			if (!on_face || !(improved || (first && tf < inf))) continue;
 			if (TIMED) kmin = fminf(kmin, (float)tf);
-#pragma unroll
+			// (rolled: this runs once per visit, and unrolled 2 x 26 times it was 45 of the kernel's 64 KB of code -- the top
+			// stall of the kernel was no_instruction, warps waiting for the instruction cache)
+#pragma unroll 1
 			for (int k = 0; k < NBR; ++k) {
 				const int qq = loc[o] - a.loff[k];
 				const int nz = cz[o] - a.dz[k], ny = cy[o] - a.dy[k], nx = cx[o] - a.dx[k];  // neighbour = index - dif
@@ -512,22 +514,10 @@ int run_automaton(ekg_model* m, int64_t* sweeps_out) {
 	init_time_kernel<<<m->sm_count * 4, 256, 0, st>>>(m->d_time_pad, npad);
 	EKG_CUDA(cudaGetLastError());
 
-	std::vector<uint32_t> h_starts(m->h_starts.size());
-	for (size_t i = 0; i < h_starts.size(); ++i) {
-		int64_t r = m->h_starts[i];
-		int64_t z = r / (m->Y * m->X), y = (r / m->X) % m->Y, x = r % m->X;
-		h_starts[i] = (uint32_t)(((z + 1) * m->pY + (y + 1)) * m->pX + (x + 1));
-	}
-	uint32_t* d_starts = nullptr;
-	EKG_CUDA(cudaMalloc(&d_starts, h_starts.size() * sizeof(uint32_t)));
-	EKG_CUDA(cudaMemcpyAsync(d_starts, h_starts.data(), h_starts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-	set_start_kernel<<<(int)((h_starts.size() + 127) / 128), 128, 0, st>>>(m->d_time_pad, d_starts, (int)h_starts.size());
+	const int n_starts = (int)m->h_starts.size();
+	set_start_kernel<<<(n_starts + 127) / 128, 128, 0, st>>>(m->d_time_pad, m->d_start_pidx, n_starts);
 	EKG_CUDA(cudaGetLastError());
-	if (!sweep) {
-		int rc = run_automaton_bricks(m, sweeps_out);
-		cudaFree(d_starts);
-		return rc;
-	}
+	if (!sweep) return run_automaton_bricks(m, sweeps_out);
 	EKG_CUDA(cudaMemsetAsync(m->d_flags, 0, (size_t)(m->max_sweeps + 1) * sizeof(int), st));
 
 	AutoArgs a{};
@@ -559,7 +549,6 @@ int run_automaton(ekg_model* m, int64_t* sweeps_out) {
 	int sweeps = 0;
 	EKG_CUDA(cudaMemcpyAsync(&sweeps, a.sweeps_out, sizeof(int), cudaMemcpyDeviceToHost, st));
 	EKG_CUDA(cudaStreamSynchronize(st));
-	EKG_CUDA(cudaFree(d_starts));
 	if (sweeps_out) *sweeps_out = sweeps;
 	if (sweeps > m->max_sweeps) return fail(EKG_E_STATE, "activation automaton did not converge");
 	return EKG_OK;
@@ -604,19 +593,11 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	int* ring = flag + 2 * n;
 	int* counters = ring + kBrickBuckets * cap;
 	const int n0 = (int)m->h_start_bricks.size();
-	int32_t* d_sb = nullptr;
-	EKG_CUDA(cudaMalloc(&d_sb, std::max<size_t>(n0, 1) * sizeof(int32_t)));
-	cudaError_t e = cudaMemcpyAsync(d_sb, m->h_start_bricks.data(), (size_t)n0 * sizeof(int32_t), cudaMemcpyHostToDevice, st);
-	if (e == cudaSuccess && n > 0) e = cudaMemsetAsync(flag, 0, (size_t)(2 * n) * sizeof(int), st);
-	if (e == cudaSuccess) e = cudaMemsetAsync(ring, 0xff, (size_t)((use_time_buckets(m) ? kBrickBuckets : 1) * cap) * sizeof(int), st);   // -1 = empty slot
-	if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, kBrickCounters * sizeof(int), st);
-	if (e == cudaSuccess) {
-		brick_seed_kernel<<<(n0 + 127) / 128 + 1, 128, 0, st>>>(d_sb, n0, (int)n, flag, flag + n, ring, counters);
-		e = cudaGetLastError();
-	}
-	if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // the start list is a host vector
-	cudaFree(d_sb);
-	if (e != cudaSuccess) return cuda_fail(e, "brick state initialisation", __FILE__, __LINE__);
+	if (n > 0) EKG_CUDA(cudaMemsetAsync(flag, 0, (size_t)(2 * n) * sizeof(int), st));
+	EKG_CUDA(cudaMemsetAsync(ring, 0xff, (size_t)((use_time_buckets(m) ? kBrickBuckets : 1) * cap) * sizeof(int), st));   // -1 = empty slot
+	EKG_CUDA(cudaMemsetAsync(counters, 0, kBrickCounters * sizeof(int), st));
+	brick_seed_kernel<<<(n0 + 127) / 128 + 1, 128, 0, st>>>(m->d_start_bricks, n0, (int)n, flag, flag + n, ring, counters);
+	EKG_CUDA(cudaGetLastError());
 	return launch_bricks(m, nullptr, rounds_out);
 }
 
@@ -812,25 +793,14 @@ int shard_begin(ekg_model* m) {
 	init_time_kernel<<<m->sm_count * 4, 256, 0, st>>>(m->d_time_pad, npad);
 	EKG_CUDA(cudaGetLastError());
 	// every rank sets every start voxel (simulator.cpp:263); only the owner's bricks relax from it
-	std::vector<uint32_t> h_starts(m->h_starts.size());
-	for (size_t i = 0; i < h_starts.size(); ++i) {
-		const int64_t r = m->h_starts[i];
-		const int64_t z = r / (m->Y * m->X), y = (r / m->X) % m->Y, x = r % m->X;
-		h_starts[i] = (uint32_t)(((z + 1) * m->pY + (y + 1)) * m->pX + (x + 1));
-	}
-	uint32_t* d_starts = nullptr;
-	EKG_CUDA(cudaMalloc(&d_starts, h_starts.size() * sizeof(uint32_t)));
-	EKG_CUDA(cudaMemcpyAsync(d_starts, h_starts.data(), h_starts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-	set_start_kernel<<<(int)((h_starts.size() + 127) / 128), 128, 0, st>>>(m->d_time_pad, d_starts, (int)h_starts.size());
+	const int n_starts = (int)m->h_starts.size();
+	set_start_kernel<<<(n_starts + 127) / 128, 128, 0, st>>>(m->d_time_pad, m->d_start_pidx, n_starts);
 	EKG_CUDA(cudaGetLastError());
 	if (n > 0) {
-		shard_mark_starts_kernel<<<(int)((h_starts.size() + 127) / 128), 128, 0, st>>>(d_starts, (int)h_starts.size(), (int)m->pY, (int)m->pX, (int)m->Z,
-		                                                                                (int)m->Y, (int)m->X, m->d_brick_index, (int)m->bY, (int)m->bX,
-		                                                                                m->d_brick_own, m->d_brick_mark);
+		shard_mark_starts_kernel<<<(n_starts + 127) / 128, 128, 0, st>>>(m->d_start_pidx, n_starts, (int)m->pY, (int)m->pX, (int)m->Z, (int)m->Y, (int)m->X,
+		                                                                 m->d_brick_index, (int)m->bY, (int)m->bX, m->d_brick_own, m->d_brick_mark);
 		EKG_CUDA(cudaGetLastError());
 	}
-	EKG_CUDA(cudaStreamSynchronize(st));  // pageable sources
-	EKG_CUDA(cudaFree(d_starts));
 	if (n > 0) EKG_CUDA(cudaMemsetAsync(m->d_brick_state, 0, (size_t)(2 * n) * sizeof(int), st));   // flags: nothing carried over
 	m->have_activation = false;
 	m->shard_active = true;

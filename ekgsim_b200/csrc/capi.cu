@@ -70,7 +70,7 @@ static void free_model(ekg_model* m) {
 	cudaSetDevice(m->device);
 	shard_unlink(m);
 	void* ptrs[] = {m->d_layer_pad, m->d_time_pad, m->d_auto_pidx, m->d_wtab, m->d_flags, m->d_brick_origin, m->d_brick_nbr, m->d_brick_state, m->d_pos, m->d_mask, m->d_ecg_pidx, m->d_at, m->d_at32,
-	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_tail, m->d_ftab, m->d_times, m->d_partial, m->d_partial2, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_lmom, m->d_near, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range};
+	                m->d_vox, m->d_segs, m->d_tiles, m->d_params, m->d_tail, m->d_ftab, m->d_times, m->d_partial, m->d_partial2, m->d_io_k, m->d_io_leads, m->d_io_ecg, m->d_io_tgt, m->d_io_border, m->d_fit_conn, m->d_msegs, m->d_mseg_first, m->d_mom, m->d_lmom, m->d_near, m->d_k1min, m->d_brick_index, m->d_brick_own, m->d_brick_mark, m->d_improved, m->d_range, m->d_start_pidx, m->d_start_bricks};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (m->h_pin_in) cudaFreeHost(m->h_pin_in);
 	if (m->h_pin_out) cudaFreeHost(m->h_pin_out);
@@ -645,7 +645,19 @@ int ekg_model_create(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X,
 				m->h_start_brick_bz.push_back(z / kBrick);
 			}
 		}
-		EKG_CREATE_CUDA(cudaStreamSynchronize(st));
+		// the start voxels (padded indices) and their bricks stay on the device: every automaton run begins with them
+		{
+			std::vector<uint32_t> sp(m->h_starts.size());
+			for (size_t i = 0; i < sp.size(); ++i) {
+				const int64_t r = m->h_starts[i];
+				sp[i] = (uint32_t)pad_index(m, r / (Y * X), (r / X) % Y, r % X);
+			}
+			EKG_CREATE_CUDA(cudaMalloc(&m->d_start_pidx, std::max<size_t>(sp.size(), 1) * sizeof(uint32_t)));
+			EKG_CREATE_CUDA(cudaMalloc(&m->d_start_bricks, std::max<size_t>(m->h_start_bricks.size(), 1) * sizeof(int32_t)));
+			EKG_CREATE_CUDA(cudaMemcpyAsync(m->d_start_pidx, sp.data(), sp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+			EKG_CREATE_CUDA(cudaMemcpyAsync(m->d_start_bricks, m->h_start_bricks.data(), m->h_start_bricks.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+			EKG_CREATE_CUDA(cudaStreamSynchronize(st));
+		}
 	}
 	cleanup();
 #undef EKG_CREATE_CUDA

@@ -209,6 +209,8 @@ struct ekg_model {
 	int* d_brick_state = nullptr;        // flag[n] | first_visit[n] | rings | counters (brick_state_ints)
 	float brick_delta = 0.f;             // time-bucket width of the work queue (ms), 0 = FIFO
 	std::vector<int32_t> h_start_bricks;
+	uint32_t* d_start_pidx = nullptr;    // padded indices of the start voxels (h_starts)
+	int32_t* d_start_bricks = nullptr;   // h_start_bricks
 	std::vector<int64_t> h_start_brick_bz;   // brick z index of every start brick
 	// z-slab sharded automaton (ekg_model_activation_begin / _relax / _export / _merge / _end)
 	int64_t bZ = 0, bY = 0, bX = 0;

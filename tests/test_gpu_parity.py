@@ -365,6 +365,29 @@ def test_two_gpus_slabs_and_individuals(built, model24, model24_delay):
     parts = m0.simulate(k, leads, "3D4", 100.0, 1.0, 16.0, mode=1) + m1.simulate(k, leads, "3D4", 100.0, 1.0, 16.0, mode=1)
     assert (np.abs(parts - whole) / g["peak_full"][:6, :, None]).max() < 2e-6
     assert (np.abs(parts - g["ecg"][:6]) / g["peak_full"][:6, :, None]).max() < ECG_TOL
+    # the automaton over the same two slabs, peer-linked ACROSS the devices (peer access + native atomics over NVLink; with
+    # both queue disciplines): one kernel per device, no host round, the reference's bits on both
+    for queue in ("fifo", "timed"):
+        os.environ["EKGSIM_B200_AUTOMATON_QUEUE"] = queue
+        try:
+            infos = [m0.activation_link_info(), m1.activation_link_info()]
+            slabs = [(a0, a1), (b0, b1)]
+            m0.activation_link(0, infos, slabs)
+            m1.activation_link(1, infos, slabs)
+            for m in (m0, m1):
+                m.activation_begin()
+            for m in (m0, m1):
+                m.activation_linked_launch()
+            res = [m.activation_linked_wait() for m in (m0, m1)]
+            for m in (m0, m1):
+                m.activation_linked_gather()
+            for m in (m0, m1):
+                assert m.activation_end().tobytes() == model24_delay.tobytes(), queue
+            assert res[0][1][0] == res[1][1][1] > 0 and res[1][1][0] == res[0][1][1] > 0, res
+            for m in (m0, m1):
+                m.activation_unlink()
+        finally:
+            os.environ.pop("EKGSIM_B200_AUTOMATON_QUEUE", None)
     m0.close()
     m1.close()
 

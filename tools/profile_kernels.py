@@ -7,6 +7,7 @@
 
 Workloads (model_24, T = 400, 2 leads, the 256 seeded vectors of the config-3 batch):
     direct256 hoisted256 separable256 cornersum256 direct1 hoisted1 separable1 fit256 fit1 evaluate256 automaton
+    automatonx4 (the same on ekgio.scaled_heart(4): the time-bucket queue; EKGSIM_B200_AUTOMATON_QUEUE=fifo for the FIFO ring)
 """
 import os
 import sys
@@ -22,7 +23,12 @@ import ekgsim_b200 as ek  # noqa: E402
 
 name = sys.argv[1]
 m24 = ekgio.load_model24()
-model = ek.Model(m24["layers"], m24["transfer"], device=0)
+if name == "automatonx4":
+    big, transfer4, _ = ekgio.scaled_heart(4)
+    model = ek.Model(big, transfer4, device=0)
+    name = "automaton"
+else:
+    model = ek.Model(m24["layers"], m24["transfer"], device=0)
 model.activation(download=False)
 g = np.load(os.path.join(ROOT, "tests", "golden", "golden_glue256.npz"))
 dev = torch.device("cuda", 0)
