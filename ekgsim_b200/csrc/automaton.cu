@@ -238,6 +238,15 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 		cz[o] = v / (kBrick * kBrick); cy[o] = (v / kBrick) % kBrick; cx[o] = v % kBrick;
 		loc[o] = ((cz[o] + 1) * kBrickHalo + (cy[o] + 1)) * kBrickHalo + (cx[o] + 1);
 	}
+	// where this lane's cells of the 6^3 staging cube lie relative to the brick's first voxel (the same for every brick)
+	constexpr int kStage = (kBrickCells + 31) / 32;
+	int cell_off[kStage];
+#pragma unroll
+	for (int j = 0; j < kStage; ++j) {
+		const int i = lane + 32 * j;
+		const int lz = i / (kBrickHalo * kBrickHalo), ly = (i / kBrickHalo) % kBrickHalo, lx = i % kBrickHalo;
+		cell_off[j] = ((lz - 1) * a.pY + (ly - 1)) * a.pX + (lx - 1);
+	}
 	const double inf = __longlong_as_double(0x7ff0000000000000LL);
 	const int nl3 = a.nl1 * 3;
 	int visits = 0, sweeps = 0, remote_cells = 0;
@@ -359,11 +368,14 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 		}
 		const bool first = __shfl_sync(kFull, first_i, 0) != 0;
 		const uint32_t origin = __ldg(a.origin + b);
-		for (int i = lane; i < kBrickCells; i += 32) {
-			const int lz = i / (kBrickHalo * kBrickHalo), ly = (i / kBrickHalo) % kBrickHalo, lx = i % kBrickHalo;
-			const uint32_t p = origin + (uint32_t)(((lz - 1) * a.pY + (ly - 1)) * a.pX + (lx - 1));
-			s_l[i] = __ldg(a.layer + p);
-			s_t[i] = __ldcg(a.time + p);
+#pragma unroll
+		for (int j = 0; j < kStage; ++j) {
+			const int i = lane + 32 * j;
+			if (i < kBrickCells) {
+				const uint32_t p = origin + (uint32_t)cell_off[j];
+				s_l[i] = __ldg(a.layer + p);
+				s_t[i] = __ldcg(a.time + p);
+			}
 		}
 		__syncwarp();
 		double t_init[kOwn];
