@@ -265,11 +265,17 @@ def heart_block(args, rank, world, local):
     t0 = time.perf_counter()
     _, visits = model.activation(download=False)
     auto_call_ms = 1e3 * (time.perf_counter() - t0)
-    auto_ms = model.activation_ms
+    auto_first_ms = model.activation_ms
+    auto_all = []
+    for _ in range(3):
+        model.activation(download=False)
+        auto_all.append(model.activation_ms)
+    auto_ms = sorted(auto_all)[1]
     out = {"workload": "configs[3]: %dx heart, %d occupied voxels, one simulation, z-slabs over %d GPU(s) + one all-reduce of the "
                        "[2][400] partial ECGs per simulation" % (f, n_occ, world),
            "factor": f, "voxels": n_occ, "n_gpus": world, "model_create_s": create_s,
-           "automaton": {"ms": auto_ms, "call_ms": auto_call_ms, "brick_visits": visits, "replicated": True}}
+           "automaton": {"ms": auto_ms, "ms_first_call": auto_first_ms, "first_call_wall_ms": auto_call_ms, "ms_all": auto_all, "brick_visits": visits,
+                         "replicated": True, "queue": "time buckets (csrc/automaton.cu)", "timing": "median of 3 calls after the first; device time of the whole call"}}
     if rank == 0 and gold is not None:
         delay = model.get_activation()
         out["automaton_bit_exact"] = bool(hashlib.sha256(delay.tobytes()).hexdigest() == gold["sha256_f64_raster"])
@@ -528,7 +534,12 @@ def run_b200_arm(args):
     m24 = ekgio.load_model24()
     model = ek.Model(m24["layers"], m24["transfer"], device=local)
     delay, sweeps = model.activation()
-    automaton_ms = model.activation_ms
+    automaton_first_ms = model.activation_ms      # the first launch of the process (module load, cold instruction cache)
+    automaton_all = []
+    for _ in range(5):
+        model.activation(download=False)
+        automaton_all.append(model.activation_ms)
+    automaton_ms = sorted(automaton_all)[len(automaton_all) // 2]
     fp = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_activation.json")))
     import hashlib
     act_ok = hashlib.sha256(delay.tobytes()).hexdigest() == fp["sha256_f64_raster"]
@@ -926,7 +937,10 @@ def run_b200_arm(args):
         "launches_per_step": direct_launches,
         "sims_per_s": value / (N_VOX * T_FULL), "e2e_sims_per_s": e2e_value / (N_VOX * T_FULL),
         "roofline": roofline, "clocks": clocks,
-        "automaton": {"ms": automaton_ms, "kernel": "automaton_brick_kernel (4^3-brick frontier, work ring)", "brick_visits": sweeps,
+        "automaton": {"ms": automaton_ms, "ms_first_call_of_the_process": automaton_first_ms, "ms_all": automaton_all,
+                      "timing": "median of 5 calls of ekg_model_activation after the first one; device time (CUDA events) of the whole "
+                                "call: grid and queue initialisation + the frontier kernel",
+                      "kernel": "automaton_brick_kernel (4^3-brick frontier; FIFO work ring on model_24, time-bucket queue on large models)", "brick_visits": sweeps,
                       "bit_exact_vs_reference": bool(act_ok), "edges_per_s": 26 * N_VOX / (automaton_ms * 1e-3),
                       "reference_cpu_s": 2.0},
         "parity_max_err_of_peak": parity,
