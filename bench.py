@@ -383,11 +383,6 @@ def heart_block(args, rank, world, local):
         if "automaton_sharded" not in out or "ms" not in out["automaton_sharded"]:
             out["automaton_sharded"] = dict(info, **out.get("automaton_sharded", {}))
     model.close()
-    if rank == 0 and not args.no_heart_cli:
-        try:
-            out["cxx_host"] = heart_cli_block(f, world)
-        except Exception as e:   # the CLI leg is extra evidence, never a reason to lose the line
-            out["cxx_host"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return out
 
 
@@ -842,6 +837,15 @@ def run_b200_arm(args):
         except Exception as e:
             heart = {"error": repr(e)}
         barrier()
+        # the same configuration through the C++ host alone (rank 0 drives all N GPUs from one child process; the other ranks
+        # wait on the CPU so that no barrier kernel of theirs shares a GPU with it)
+        idle_barrier()
+        if rank == 0 and not args.no_heart_cli and isinstance(heart, dict) and "error" not in heart:
+            try:
+                heart["cxx_host"] = heart_cli_block(args.heart_factor, world)
+            except Exception as e:   # the CLI leg is extra evidence, never a reason to lose the line
+                heart["cxx_host"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        idle_barrier()
 
     # -- BASELINE configs[4]: one AMS-DEMO generation (population 100) through the evaluation boundary, all N GPUs (rank 0)
     generation = None

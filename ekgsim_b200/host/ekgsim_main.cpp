@@ -13,7 +13,8 @@
 // Additions of this build (not in the reference):
 //     ekgSim -batch vectors.txt [-batchout criteria.txt]     evaluate many parameter vectors (one per
 //         line, comma/space separated) in one GPU batch; prints one " criteria = <..>, violation = V"
-//         line per vector.  This is what a population-based optimizer should call per generation.
+//         line per vector.  This is what a population-based optimizer should call per generation.  -evalout <file> also
+//         writes the batch in the format of the reference optimizer's evaluations.txt (AMS-DEMO/Individual.h:361-380).
 //     ekgSim -extern <homeDir>     AMS-DEMO ExternalEvaluation protocol (ExternalEvaluation.h:95-151):
 //         reads <homeDir>/input.txt (one gene per line, '#' comments), writes <homeDir>/output.txt
 //         ("# violation v", then the criteria).  With -server <socket> or EKGSIM_B200_SERVER=<socket> the genes go to a
@@ -107,7 +108,23 @@ void run_single(const std::vector<double>& params, const ekg::OutputSettings& ou
 	std::cout << " criteria = " << ekg::angle_list(result) << ", violation = " << violation << "\n";
 }
 
-void run_batch(const std::string& file, const std::string& outfile, int threads, const std::string& devices) {
+/// the reference optimizer's evaluation log (AMS-DEMO/Individual.h:361-380, `evaluations.txt`): one row per individual,
+/// "evaluation_number \t[input] \t violation \t[properties] \t[output] \t evaluator_rank \t evaluation_time \t life_time",
+/// the chromosome with 26 significant digits (the stream keeps that precision for the rest of the row, like the reference's)
+void write_evaluations(const std::string& fname, const std::vector<std::vector<double>>& sols, const std::vector<std::vector<double>>& results,
+                       const std::vector<double>& violations, double secondsPerEvaluation) {
+	std::ofstream file(fname.c_str());
+	if (!file.is_open()) throw std::runtime_error("could not open " + fname);
+	file << "# format of this file:\n"
+	     << "# evaluation_number \t[function_input_vector] \t violation \t[properties] \t[function_output_vector] \t evaluator_rank \t evaluation_time \t life_time \n";
+	for (size_t i = 0; i < sols.size(); ++i) {
+		file << i << "\t" << std::setprecision(26) << ekg::angle_list(sols[i], 26);
+		file << "\t" << violations[i] << "\t" << "<>" << "\t" << ekg::angle_list(results[i], 26) << "\t" << 0 << "\t" << secondsPerEvaluation << "\t"
+		     << secondsPerEvaluation << "\n";
+	}
+}
+
+void run_batch(const std::string& file, const std::string& outfile, int threads, const std::string& devices, const std::string& evalfile) {
 	std::cerr << "##### Running a batch of simulations ############################\n";
 	std::ifstream in(file.c_str());
 	if (!in.is_open()) throw std::runtime_error("could not open " + file);
@@ -133,6 +150,7 @@ void run_batch(const std::string& file, const std::string& outfile, int threads,
 			of << violations[i] << "\n";
 		}
 	}
+	if (!evalfile.empty()) write_evaluations(evalfile, sols, results, violations, sols.empty() ? 0.0 : secs / (double)sols.size());
 	std::cout << " batch of " << sols.size() << " simulations done in " << secs << " seconds on " << ev.numDevices() << " GPU(s) (GPU part "
 	          << ev.simulator().lastRunSeconds() << " s)\n";
 }
@@ -188,7 +206,7 @@ int main(int argc, char** argv) {
 		if (args.is_set("-?")) {
 			std::cout << "Argument list:\n   -? \tshow this help screen\n   -sim \tjust run single a simulation with parameters provided after -sim\n"
 			             "   -out \tspecify outputs of the program; possible values include result, layer_aps, cell_aps <num> [<num>]*\n"
-			             "   -batch \tevaluate every parameter vector of a text file in one GPU batch [-batchout file] [-threads n]\n"
+			             "   -batch \tevaluate every parameter vector of a text file in one GPU batch [-batchout file] [-evalout evaluations.txt] [-threads n]\n"
 			             "   -devices \twith -batch / -serve: GPUs to split the batches over: all, a count, or a list 0,1,2 (default: EKGSIM_B200_DEVICES, else one)\n"
 			             "   -slabs \tone model over several GPUs as z-slabs: all, a count, or a list 0,1,2 (default: EKGSIM_B200_SLABS, else off)\n"
 			             "   -extern \tAMS-DEMO ExternalEvaluation protocol: <homeDir>/input.txt -> <homeDir>/output.txt [-server socket]\n"
@@ -202,7 +220,7 @@ int main(int argc, char** argv) {
 			run_single(params, out);
 		} else if (args.is_set("-batch")) {
 			std::cerr << "\n";
-			run_batch(args.get("-batch"), args.get("-batchout"), atoi(args.get("-threads").c_str()), args.get("-devices"));
+			run_batch(args.get("-batch"), args.get("-batchout"), atoi(args.get("-threads").c_str()), args.get("-devices"), args.get("-evalout"));
 		} else if (args.is_set("-extern")) {
 			std::cerr << "\n";
 			run_extern(args.get("-extern"), args.get("-server"));

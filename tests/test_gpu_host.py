@@ -475,10 +475,22 @@ def test_evaluator_splits_batches_over_devices(testrun):
     with open(os.path.join(testrun, "vec5.txt"), "w") as f:
         for p in genes[:5]:
             f.write(",".join("%.17g" % x for x in p) + "\n")
-    r = subprocess.run([hostlib.CLI, "-batch", "vec5.txt", "-batchout", "crit5.txt", "-devices", "0,0"], cwd=testrun, capture_output=True, text=True)
+    r = subprocess.run([hostlib.CLI, "-batch", "vec5.txt", "-batchout", "crit5.txt", "-evalout", "evaluations5.txt", "-devices", "0,0"], cwd=testrun,
+                       capture_output=True, text=True)
     assert r.returncode == 0 and "on 2 GPU(s)" in r.stdout, r.stdout + r.stderr
     got = np.loadtxt(os.path.join(testrun, "crit5.txt"))
     assert np.abs(got[:, :2] - c1[:5]).max() < 1e-6
+    # -evalout: the batch in the format of the reference optimizer's evaluations.txt (AMS-DEMO/Individual.h:361-380)
+    lines = open(os.path.join(testrun, "evaluations5.txt")).read().split("\n")
+    assert lines[0] == "# format of this file:" and lines[1].startswith("# evaluation_number \t[function_input_vector] \t violation")
+    rows = [ln.split("\t") for ln in lines[2:] if ln]
+    assert len(rows) == 5 and all(len(rw) == 8 for rw in rows)
+    for i, rw in enumerate(rows):
+        assert int(rw[0]) == i and rw[3] == "<>" and rw[5] == "0"
+        chrom = np.array([float(x) for x in rw[1].strip("<>").split(",")])
+        assert (chrom == genes[i]).all()                                   # 26 significant digits: the genes survive exactly
+        crit = np.array([float(x) for x in rw[4].strip("<>").split(",")])
+        assert np.abs(crit - c1[i]).max() < 1e-6 and float(rw[2]) == v1[i]
     r = subprocess.run([hostlib.CLI, "-batch", "vec5.txt", "-devices", "7,99"], cwd=testrun, capture_output=True, text=True)
     assert "runtime error caught: no such CUDA device in device list" in r.stdout
 
