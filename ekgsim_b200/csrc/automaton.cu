@@ -212,7 +212,7 @@ __device__ __forceinline__ void link_push(const BrickArgs& a, int* pstate, unsig
 }
 
 template <int NBR, bool LINKED, bool TIMED>
-__global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(BrickArgs a) {
+__global__ void __launch_bounds__(32 * kBrickWarps, TIMED ? 3 : 2) automaton_brick_kernel(BrickArgs a) {
 	__shared__ double s_t_all[kBrickWarps][kBrickCells];
 	__shared__ uint8_t s_l_all[kBrickWarps][kBrickCells];
 	extern __shared__ double s_w[];  // edge-weight table [nl1][nl1][3] when it fits (a.w_in_smem)
@@ -246,6 +246,17 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 		const int i = lane + 32 * j;
 		const int lz = i / (kBrickHalo * kBrickHalo), ly = (i / kBrickHalo) % kBrickHalo, lx = i % kBrickHalo;
 		cell_off[j] = ((lz - 1) * a.pY + (ly - 1)) * a.pX + (lx - 1);
+	}
+	// which of a voxel's neighbours lie outside the brick (bit k: neighbour k), the same for every brick
+	unsigned outward[kOwn];
+#pragma unroll
+	for (int o = 0; o < kOwn; ++o) {
+		outward[o] = 0;
+#pragma unroll 1
+		for (int k = 0; k < NBR; ++k) {
+			const int nz = cz[o] - a.dz[k], ny = cy[o] - a.dy[k], nx = cx[o] - a.dx[k];
+			if (nz < 0 || nz >= kBrick || ny < 0 || ny >= kBrick || nx < 0 || nx >= kBrick) outward[o] |= 1u << k;
+		}
 	}
 	const double inf = __longlong_as_double(0x7ff0000000000000LL);
 	const int nl3 = a.nl1 * 3;
@@ -438,17 +449,17 @@ __global__ void __launch_bounds__(32 * kBrickWarps, 2) automaton_brick_kernel(Br
 			// (rolled: this runs once per visit, and unrolled 2 x 26 times it was 45 of the kernel's 64 KB of code -- the top
 			// stall of the kernel was no_instruction, warps waiting for the instruction cache)
 #pragma unroll 1
-			for (int k = 0; k < NBR; ++k) {
+			for (unsigned todo = outward[o]; todo; todo &= todo - 1u) {   // the neighbours of this voxel that lie in another brick
+				const int k = __ffs(todo) - 1;
 				const int qq = loc[o] - a.loff[k];
-				const int nz = cz[o] - a.dz[k], ny = cy[o] - a.dy[k], nx = cx[o] - a.dx[k];  // neighbour = index - dif
-				const int dz = nz < 0 ? -1 : nz >= kBrick ? 1 : 0;
-				const int dy = ny < 0 ? -1 : ny >= kBrick ? 1 : 0;
-				const int dx = nx < 0 ? -1 : nx >= kBrick ? 1 : 0;
-				if (!(dz | dy | dx)) continue;  // interior cell
 				const int lu = s_l[qq];
 				if (lu == 0) continue;
 				const double cand = __dadd_rn(tf, wt[(lv[o] * a.nl1 + lu) * 3 + a.sq[k]]);  // we excite it: T[ours][its]
 				if (cand < s_t[qq]) {
+					const int nz = cz[o] - a.dz[k], ny = cy[o] - a.dy[k], nx = cx[o] - a.dx[k];  // neighbour = index - dif
+					const int dz = nz < 0 ? -1 : nz >= kBrick ? 1 : 0;
+					const int dy = ny < 0 ? -1 : ny >= kBrick ? 1 : 0;
+					const int dx = nx < 0 ? -1 : nx >= kBrick ? 1 : 0;
 					const int id = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
 					bits |= 1u << (id > 13 ? id - 1 : id);
 				}
@@ -570,6 +581,12 @@ static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* visits_out
 
 static int64_t ring_capacity(int64_t n) { return brick_ring_capacity(n); }
 
+static bool use_time_buckets(const ekg_model* m);
+static int brick_ctas_per_sm(const ekg_model* m) {
+	if (const char* e = getenv("EKGSIM_B200_AUTOMATON_CTAS_PER_SM")) return std::max(1, atoi(e));
+	return use_time_buckets(m) ? 3 : 2;
+}
+
 // Time buckets pay off when the frontier is wider than the machine (then the order of the visits is the queue's choice);
 // a small model is bound by the wave's critical path, every queued brick is taken at once, and the FIFO ring's hand-off
 // (waiting warps line up behind the tail) has the shorter latency.  EKGSIM_B200_AUTOMATON_QUEUE=timed|fifo overrides.
@@ -654,7 +671,10 @@ static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out
 	                           : (timed ? (void*)automaton_brick_kernel<8, false, true> : (void*)automaton_brick_kernel<8, false, false>);
 	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
-	// every CTA must be resident (waiting warps spin on the ring): never launch more than fit
+	// every CTA must be resident (waiting warps spin on the ring): never launch more than fit.  The time-bucket kernel (large
+	// models, throughput bound) is built for 3 CTAs per SM at 80 registers, the FIFO kernel (small models, bound by the wave's
+	// critical path: fewer warps polling the queue, fewer instructions per visit) for 2 at 128
+	per_sm = std::min(per_sm, brick_ctas_per_sm(m));
 	const int grid = (int)std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>((n + kBrickWarps - 1) / kBrickWarps, 1));
 	void* kargs[] = {&a};
 	EKG_CUDA(cudaLaunchCooperativeKernel(kfun, dim3(grid), dim3(threads), kargs, dyn, st));
@@ -1058,6 +1078,7 @@ int shard_linked_launch(ekg_model* m, int max_ctas) {
 	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
 	// our own bricks bound the useful grid (a slab is ~1/N of the model); rank 0 gives one warp to the detector
+	per_sm = std::min(per_sm, brick_ctas_per_sm(m));
 	int64_t grid = std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>((n + kBrickWarps - 1) / kBrickWarps, 1) + 1);
 	// ranks of one process on one device: an equal share of the SMs each, so that every rank's kernel is resident
 	if (max_ctas <= 0 && L.colocated > 1) max_ctas = std::max(1, per_sm * m->sm_count / L.colocated);

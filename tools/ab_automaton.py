@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--factors", default="1,2,4")
     ap.add_argument("--deltas", default="")
     ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--ctas", default="", help="comma list of EKGSIM_B200_AUTOMATON_CTAS_PER_SM values to try for every variant")
     a = ap.parse_args()
     out = []
     for f in [int(x) for x in a.factors.split(",")]:
@@ -35,9 +36,14 @@ def main():
             layers, transfer, _ = ekgio.scaled_heart(f)
             g = os.path.join(ROOT, "tests", "golden", "golden_heart%dx.json" % f)
             gold = json.load(open(g))["sha256_f64_raster"] if os.path.exists(g) else None
-        variants = [("fifo", None), ("timed", None)] + [("timed", d) for d in a.deltas.split(",") if d]
-        for queue, delta in variants:
+        variants = [("fifo", None, c) for c in (a.ctas.split(",") if a.ctas else [None])] + [("timed", None, c) for c in (a.ctas.split(",") if a.ctas else [None])] \
+            + [("timed", d, None) for d in a.deltas.split(",") if d]
+        for queue, delta, ctas in variants:
             os.environ["EKGSIM_B200_AUTOMATON_QUEUE"] = queue
+            if ctas is None:
+                os.environ.pop("EKGSIM_B200_AUTOMATON_CTAS_PER_SM", None)
+            else:
+                os.environ["EKGSIM_B200_AUTOMATON_CTAS_PER_SM"] = ctas
             if delta is None:
                 os.environ.pop("EKGSIM_B200_AUTOMATON_DELTA", None)
             else:
@@ -50,7 +56,7 @@ def main():
                 visits.append(v)
             sha = hashlib.sha256(m.get_activation().tobytes()).hexdigest()
             m.close()
-            row = {"factor": f, "queue": queue, "delta_ms": delta or "default", "ms_best": min(ms), "ms_all": [round(x, 3) for x in ms],
+            row = {"factor": f, "queue": queue, "delta_ms": delta or "default", "ctas_per_sm": ctas or "default", "ms_best": min(ms), "ms_all": [round(x, 3) for x in ms],
                    "brick_visits": visits[-1], "bit_exact": (sha == gold) if gold else None}
             print(json.dumps(row), flush=True)
             out.append(row)
