@@ -211,13 +211,29 @@ __device__ __forceinline__ void link_push(const BrickArgs& a, int* pstate, unsig
 	if (lane == 0) atomicAdd_system(pcnt + 9, n_push);                          // received -- after its pending went up
 }
 
-template <int NBR, bool LINKED, bool TIMED>
+// The automaton's neighbourhoods in the order make_nbr_table (ecg.cu) produces them -- (dz, dy, dx) lexicographic over
+// {-1, 0, 1}^3 (NBR = 26) or {0} x {-1, 0, 1}^2 (NBR = 8) without the centre -- as compile-time functions of k, so that the
+// unrolled sweep addresses shared memory with immediate offsets (fill_brick_args checks the table against them).
+template <int NBR> __host__ __device__ constexpr int nb_idx(int k) { return NBR == 26 ? k + (k >= 13 ? 1 : 0) : k + (k >= 4 ? 1 : 0); }
+template <int NBR> __host__ __device__ constexpr int nb_dz(int k) { return NBR == 26 ? nb_idx<NBR>(k) / 9 - 1 : 0; }
+template <int NBR> __host__ __device__ constexpr int nb_dy(int k) { return NBR == 26 ? (nb_idx<NBR>(k) / 3) % 3 - 1 : nb_idx<NBR>(k) / 3 - 1; }
+template <int NBR> __host__ __device__ constexpr int nb_dx(int k) { return nb_idx<NBR>(k) % 3 - 1; }
+template <int NBR> __host__ __device__ constexpr int nb_loff(int k) { return (nb_dz<NBR>(k) * kBrickHalo + nb_dy<NBR>(k)) * kBrickHalo + nb_dx<NBR>(k); }
+template <int NBR> __host__ __device__ constexpr int nb_sq(int k) {
+	return nb_dz<NBR>(k) * nb_dz<NBR>(k) + nb_dy<NBR>(k) * nb_dy<NBR>(k) + nb_dx<NBR>(k) * nb_dx<NBR>(k) - 1;
+}
+
+// WSMEM: the edge-weight table sits in shared memory (it does for up to 36 layers).  A compile-time fact, so that the
+// table is read with LDS and 32-bit address arithmetic -- a pointer that may be shared or global made every lookup a
+// generic 64-bit load with four instructions of address arithmetic, in the innermost loop.
+template <int NBR, bool LINKED, bool TIMED, bool WSMEM>
 __global__ void __launch_bounds__(32 * kBrickWarps, TIMED ? 3 : 2) automaton_brick_kernel(BrickArgs a) {
 	__shared__ double s_t_all[kBrickWarps][kBrickCells];
 	__shared__ uint8_t s_l_all[kBrickWarps][kBrickCells];
+	__shared__ uint16_t s_o_all[kBrickWarps][kBrickCells];   // byte offset of the cell's weight row: layer * nl1 * 3 * 8
 	extern __shared__ double s_w[];  // edge-weight table [nl1][nl1][3] when it fits (a.w_in_smem)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (a.w_in_smem) {
+	if (WSMEM) {
 		for (int i = tid; i < a.nl1 * a.nl1 * 3; i += blockDim.x) s_w[i] = __ldg(a.wtab + i);
 		__syncthreads();
 	}
@@ -225,9 +241,10 @@ __global__ void __launch_bounds__(32 * kBrickWarps, TIMED ? 3 : 2) automaton_bri
 		link_detector(a, lane);
 		return;
 	}
-	const double* __restrict__ wt = a.w_in_smem ? s_w : a.wtab;
+	const double* __restrict__ wt = WSMEM ? (const double*)s_w : a.wtab;
 	double* s_t = s_t_all[warp];
 	uint8_t* s_l = s_l_all[warp];
+	uint16_t* s_o = s_o_all[warp];
 	constexpr int kOwn = kBrick * kBrick * kBrick / 32;  // interior voxels per lane (2)
 	constexpr int kInnerCap = 256;
 	constexpr unsigned kFull = 0xffffffffu;
@@ -384,7 +401,9 @@ __global__ void __launch_bounds__(32 * kBrickWarps, TIMED ? 3 : 2) automaton_bri
 			const int i = lane + 32 * j;
 			if (i < kBrickCells) {
 				const uint32_t p = origin + (uint32_t)cell_off[j];
-				s_l[i] = __ldg(a.layer + p);
+				const int lc = __ldg(a.layer + p);
+				s_l[i] = (uint8_t)lc;
+				s_o[i] = (uint16_t)(lc * nl3 * 8);
 				s_t[i] = __ldcg(a.time + p);
 			}
 		}
@@ -401,14 +420,16 @@ __global__ void __launch_bounds__(32 * kBrickWarps, TIMED ? 3 : 2) automaton_bri
 				if (lv[o] == 0) continue;
 				// branch-free: empty cells have layer 0 whose weight row is +inf, unreached cells hold +inf;
 				// all NBR loads are independent so their latencies overlap
-				const double* __restrict__ wv = wt + lv[o] * 3;
+				const char* __restrict__ wv = (const char*)(wt + lv[o] * 3);
 				const double tv = s_t[loc[o]];
 				double best = tv;
 #pragma unroll
 				for (int k = 0; k < NBR; ++k) {
-					const int qq = loc[o] - a.loff[k];
-					const double cand = __dadd_rn(s_t[qq], wv[(int)s_l[qq] * nl3 + a.sq[k]]);
-					best = fmin(best, cand);
+					// neighbour cell = ours - dif_k; its time, the byte offset of its weight row, the weight w[its layer][ours][|dif|^2]
+					const double tu = (s_t + loc[o])[-nb_loff<NBR>(k)];
+					const int wo = (s_o + loc[o])[-nb_loff<NBR>(k)];
+					const double cand = __dadd_rn(tu, *(const double*)(wv + wo + nb_sq<NBR>(k) * 8));
+					best = cand < best ? cand : best;   // (fmin's NaN rules cost four more instructions; there are no NaNs here)
 				}
 				if (best < tv) { s_t[loc[o]] = best; ch = true; }
 			}
@@ -596,7 +617,7 @@ static bool use_time_buckets(const ekg_model* m) {
 		if (std::string(e) == "timed") return true;
 		if (std::string(e) == "fifo") return false;
 	}
-	return m->n_bricks >= (int64_t)m->sm_count * 2 * kBrickWarps * 12;   // >= 12 bricks per resident warp
+	return m->n_bricks >= (int64_t)m->sm_count * 2 * kBrickWarps * 96;   // >= 96 bricks per resident warp (2x heart: 35, FIFO 1.79 ms / buckets 1.98; 4x: 280, 12.3 / 8.75)
 }
 
 // start bricks: flagged, first visit pending, queued in ring 0
@@ -630,6 +651,16 @@ static int run_automaton_bricks(ekg_model* m, int64_t* rounds_out) {
 	return launch_bricks(m, nullptr, rounds_out);
 }
 
+template <int NBR, bool LINKED>
+static void* pick_brick_kernel2(bool timed, bool wsmem) {
+	if (timed) return wsmem ? (void*)automaton_brick_kernel<NBR, LINKED, true, true> : (void*)automaton_brick_kernel<NBR, LINKED, true, false>;
+	return wsmem ? (void*)automaton_brick_kernel<NBR, LINKED, false, true> : (void*)automaton_brick_kernel<NBR, LINKED, false, false>;
+}
+static void* pick_brick_kernel(bool cube, bool linked, bool timed, bool wsmem) {
+	if (cube) return linked ? pick_brick_kernel2<26, true>(timed, wsmem) : pick_brick_kernel2<26, false>(timed, wsmem);
+	return linked ? pick_brick_kernel2<8, true>(timed, wsmem) : pick_brick_kernel2<8, false>(timed, wsmem);
+}
+
 // kernel arguments of the frontier kernel for this model (the link part stays zeroed)
 static void fill_brick_args(ekg_model* m, const uint8_t* d_own, int64_t budget, BrickArgs& a) {
 	const int64_t n = m->n_bricks;
@@ -652,9 +683,13 @@ static void fill_brick_args(ekg_model* m, const uint8_t* d_own, int64_t budget, 
 		a.loff[k] = (nb.dz[k] * kBrickHalo + nb.dy[k]) * kBrickHalo + nb.dx[k];
 		a.dz[k] = nb.dz[k]; a.dy[k] = nb.dy[k]; a.dx[k] = nb.dx[k];
 		a.sq[k] = nb.dz[k] * nb.dz[k] + nb.dy[k] * nb.dy[k] + nb.dx[k] * nb.dx[k] - 1;
+		// the kernel's unrolled sweep hard-codes this enumeration
+		const bool same = nb.n == 26 ? (a.loff[k] == nb_loff<26>(k) && a.sq[k] == nb_sq<26>(k)) : (a.loff[k] == nb_loff<8>(k) && a.sq[k] == nb_sq<8>(k));
+		if (!same) a.n_nbr = -1;
 	}
 	const size_t w_bytes = (size_t)a.nl1 * a.nl1 * 3 * sizeof(double);
 	a.w_in_smem = w_bytes <= 32 * 1024;
+	if ((int64_t)a.nl1 * a.nl1 * 3 * 8 > 65535) a.n_nbr = -2;   // the staged row offsets are 16 bits (up to 52 layers)
 }
 
 // the frontier kernel over whatever the ring holds; d_own restricts the pushes (sharded run)
@@ -663,12 +698,12 @@ static int launch_bricks(ekg_model* m, const uint8_t* d_own, int64_t* rounds_out
 	const int64_t n = m->n_bricks;
 	BrickArgs a;
 	fill_brick_args(m, d_own, budget, a);
+	if (a.n_nbr < 0) return fail(EKG_E_UNSUPPORTED, a.n_nbr == -2 ? "more than 52 layers: use EKGSIM_B200_AUTOMATON=sweep" : "unexpected neighbour enumeration");
 	const size_t dyn = a.w_in_smem ? (size_t)a.nl1 * a.nl1 * 3 * sizeof(double) : 0;
 	int per_sm = 0;
 	const int threads = 32 * kBrickWarps;
 	const bool timed = a.inv_delta > 0.f;
-	void* kfun = a.n_nbr == 26 ? (timed ? (void*)automaton_brick_kernel<26, false, true> : (void*)automaton_brick_kernel<26, false, false>)
-	                           : (timed ? (void*)automaton_brick_kernel<8, false, true> : (void*)automaton_brick_kernel<8, false, false>);
+	void* kfun = pick_brick_kernel(a.n_nbr == 26, false, timed, a.w_in_smem != 0);
 	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
 	// every CTA must be resident (waiting warps spin on the ring): never launch more than fit.  The time-bucket kernel (large
@@ -1067,14 +1102,14 @@ int shard_linked_launch(ekg_model* m, int max_ctas) {
 	a.link.plane = (uint32_t)(m->pY * m->pX);
 	if (L.below >= 0) { a.link.time_dn = L.time[(size_t)L.below]; a.link.state_dn = L.state[(size_t)L.below]; }
 	if (L.above >= 0) { a.link.time_up = L.time[(size_t)L.above]; a.link.state_up = L.state[(size_t)L.above]; }
+	if (a.n_nbr < 0) return fail(EKG_E_UNSUPPORTED, a.n_nbr == -2 ? "more than 52 layers: use EKGSIM_B200_AUTOMATON=sweep" : "unexpected neighbour enumeration");
 	for (int r = 0; r < L.n_ranks; ++r) a.link.counters_of[r] = L.state[(size_t)r] + 2 * n + kBrickBuckets * cap;
 	const size_t dyn = a.w_in_smem ? (size_t)a.nl1 * a.nl1 * 3 * sizeof(double) : 0;
 	int per_sm = 0;
 	const int threads = 32 * kBrickWarps;
 	const bool timed = a.inv_delta > 0.f;
 	if (timed != L.timed) return fail(EKG_E_STATE, "the work-queue mode has changed since ekg_model_activation_link");
-	void* kfun = a.n_nbr == 26 ? (timed ? (void*)automaton_brick_kernel<26, true, true> : (void*)automaton_brick_kernel<26, true, false>)
-	                           : (timed ? (void*)automaton_brick_kernel<8, true, true> : (void*)automaton_brick_kernel<8, true, false>);
+	void* kfun = pick_brick_kernel(a.n_nbr == 26, true, timed, a.w_in_smem != 0);
 	EKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kfun, threads, dyn));
 	if (per_sm < 1) return fail(EKG_E_CUDA, "automaton kernel does not fit on the device");
 	// our own bricks bound the useful grid (a slab is ~1/N of the model); rank 0 gives one warp to the detector
