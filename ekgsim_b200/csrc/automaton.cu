@@ -555,6 +555,9 @@ int run_automaton(ekg_model* m, int64_t* sweeps_out) {
 	const char* sel = getenv("EKGSIM_B200_AUTOMATON");
 	bool sweep = false;
 	if (sel && std::string(sel) == "sweep") sweep = true;
+	// the frontier kernel stages 16-bit offsets into the (layers + 1)^2 x 3 weight table: up to 51 layers (the reference's
+	// models have 24); anything larger takes the plain sweeps
+	if ((int64_t)(m->n_layers + 1) * (m->n_layers + 1) * 3 * 8 > 65535) sweep = true;
 	init_time_kernel<<<m->sm_count * 4, 256, 0, st>>>(m->d_time_pad, npad);
 	EKG_CUDA(cudaGetLastError());
 

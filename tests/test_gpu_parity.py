@@ -55,6 +55,20 @@ def test_activation_small_bit_exact(built, seed):
     m.close()
 
 
+@pytest.mark.parametrize("n_layers", [30, 40, 60])
+def test_activation_many_layers(built, n_layers):
+    """More layers than the reference's 24: up to 36 the (layers + 1)^2 x 3 weight table sits in shared memory, 40 layers read
+    it from global memory (the kernel variant without the shared table), 60 are beyond the 16-bit row offsets of the
+    frontier kernel and take the plain sweeps by themselves.  Same bits as the oracle in every case."""
+    layers, transfer, _ = synth.small_heart(seed=n_layers, shape=(40, 44, 42), n_layers=n_layers, hole=True)
+    assert int((layers & 0x0FFF).max()) == n_layers
+    ref = oracle.activation(layers, transfer)
+    m = built.Model(layers, transfer)
+    delay, _ = m.activation()
+    assert delay.tobytes() == ref.tobytes()
+    m.close()
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
 def test_activation_random_conduction_and_many_starts(built, seed):
     """Asymmetric random conduction matrices (T[exciting][excited] != T[excited][exciting], three orders of
