@@ -19,10 +19,12 @@
 //    times + 216 u8 layers, two interior voxels per lane), relaxes it to a LOCAL fixed point with
 //    in-place sweeps synchronised by __syncwarp only, writes the improved times back and queues a
 //    neighbouring brick if one of its cells would improve through a changed voxel.  There are no
-//    grid-wide rounds: warps pull brick ids from a lock-free ring (head/tail counters, a `pending`
-//    count of queued + in-work bricks for termination), so the wavefront advances at the pace of
-//    its own dependencies; write-back uses a 64-bit atomicMin because two warps may hold the same
-//    brick at once.
+//    grid-wide rounds: warps pull brick ids from a lock-free queue (a `pending` count of queued +
+//    in-work bricks for termination), so the wavefront advances at the pace of its own
+//    dependencies; write-back uses a 64-bit atomicMin because two warps may hold the same brick at
+//    once.  The queue is one FIFO ring for models whose frontier fits the machine and 16 rings of
+//    time buckets for larger ones (template parameter TIMED, see "Work queue" below): visiting
+//    bricks in the order of their activation times halves the number of visits on a 4x heart.
 //  * automaton_kernel (EKGSIM_B200_AUTOMATON=sweep) -- the plain label-correcting sweep over all
 //    occupied voxels, kept as the simple cross-check.
 //
