@@ -24,6 +24,11 @@
  *   ekg_evaluate              fit + ekg_simulate + curve comparison without leaving the device:
  *                             border APs and lead positions in, criteria out (SimImplementation::eval
  *                             sim.cpp:443-491 minus the gene unpacking, which stays on the host)
+ *   ekg_model_set_slab,       one model over several GPUs (BASELINE config 4; no counterpart in the reference, whose
+ *   ekg_model_activation_*    parallelism is one full model per MPI rank, main.cpp:301): the ECG sum restricted to a z-slab,
+ *                             and calculateExcitationSequence (simulator.cpp:248-286) computed by all GPUs together --
+ *                             peer-linked over NVLink (_link_info / _link / _linked_launch / _linked_wait / _linked_gather)
+ *                             or in host-driven rounds (_begin / _relax_bounded / _export / _merge / _end)
  *
  * Conventions
  *   - voxel arrays are raster z,y,x (x fastest): index (z*Y+y)*X+x          (matrix.h:166-173)
