@@ -502,7 +502,9 @@ __global__ void __launch_bounds__(32 * kBrickWarps, TIMED ? 3 : 2) automaton_bri
 				if (reach_up) link_push(a, a.link.state_up, reach_up, kOwnAbove, b, lane, key);
 			}
 		}
-		__threadfence();   // our improved times are visible before anyone is told to look at them
+		// our improved times are visible before anyone is told to look at them -- also before the flag exchange below: a
+		// neighbour that is queued already reads our times after ITS flag exchange.  (Nobody to tell: no fence.)
+		if (bits) __threadfence();
 		// push the neighbours that need a visit: one tail reservation and one pending update per warp
 		// (head, tail and pending are single hot addresses; per-brick atomics on them would serialise)
 		int nb = -1;
