@@ -890,7 +890,6 @@ int shard_begin(ekg_model* m) {
 // fixed point, so that the ranks work side by side instead of one after the other); *leftover_out = bricks still queued
 int shard_relax(ekg_model* m, int64_t max_visits, int64_t* visits_out, int64_t* leftover_out) {
 	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
-	cudaStream_t st = m->stream;
 	const int64_t n = m->n_bricks;
 	if (leftover_out) *leftover_out = 0;
 	if (m->merge_pending) { EKG_CUDA(cudaStreamSynchronize(m->merge_stream)); m->merge_pending = false; }   // asynchronous merges have landed
@@ -913,7 +912,7 @@ static int plane_range(ekg_model* m, int64_t z_begin, int64_t z_end, int64_t* fi
 }
 
 int shard_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes, cudaStream_t st) {
-	int64_t first, n;
+	int64_t first = 0, n = 0;
 	int rc = plane_range(m, z_begin, z_end, &first, &n);
 	if (rc) return rc;
 	// asynchronous on the caller's stream (the relaxation that produced the values has completed: shard_relax synchronises
@@ -927,7 +926,7 @@ int shard_export(ekg_model* m, int64_t z_begin, int64_t z_end, double* d_planes,
 int shard_merge(ekg_model* m, int64_t z_begin, int64_t z_end, const double* d_planes, int64_t* improved_out, unsigned long long* d_count,
                 cudaStream_t st) {
 	if (!m->shard_active) return fail(EKG_E_STATE, "ekg_model_activation_begin has not been called");
-	int64_t first, n;
+	int64_t first = 0, n = 0;
 	int rc = plane_range(m, z_begin, z_end, &first, &n);
 	if (rc) return rc;
 	unsigned long long h = 0;
