@@ -946,6 +946,10 @@ def run_b200_arm(args):
                                 "call: grid and queue initialisation + the frontier kernel",
                       "kernel": "automaton_brick_kernel (4^3-brick frontier; FIFO work ring on model_24, time-bucket queue on large models)", "brick_visits": sweeps,
                       "bit_exact_vs_reference": bool(act_ok), "edges_per_s": 26 * N_VOX / (automaton_ms * 1e-3),
+                      # 8 B neighbour time + 1 B layer read + 8 B atomicMin per relaxed edge, every edge relaxed once; the
+                      # kernel is bound by the wave's dependency chain, not by bandwidth -- reported for honesty
+                      "hbm": {"algorithmic_bytes": 17 * 26 * N_VOX, "achieved_gbs": 17 * 26 * N_VOX / (automaton_ms * 1e-3) / 1e9,
+                              "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs") if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None},
                       "reference_cpu_s": 2.0},
         "parity_max_err_of_peak": parity,
         "fast_path": fast, "separable_path": separable, "pipeline": pipeline, "single_sim": single,
