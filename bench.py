@@ -302,16 +302,24 @@ def heart_block(args, rank, world, local):
         return ekdist.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
 
     # N = 1 value: the whole model on this rank, no collective
+    k1_min, decay_max = ek.coefficient_hints(k)
+
+    def simulate(md):
+        if md == ek.MODE_DEFAULT:   # the coefficients came from this host: no read-back of their rates inside the call
+            model.simulate_device_hinted(d_k.data_ptr(), d_l.data_ptr(), 1, 2, d_e.data_ptr(), k1_min, decay_max, "3D4", 100.0, 1.0, float(T),
+                                         mode=md, stream=stream)
+        else:
+            model.simulate_device(d_k.data_ptr(), d_l.data_ptr(), 1, 2, d_e.data_ptr(), "3D4", 100.0, 1.0, float(T), mode=md, stream=stream)
+
     one = {}
     for nm, md in modes:
-        one[nm] = timed(lambda: model.simulate_device(d_k.data_ptr(), d_l.data_ptr(), 1, 2, d_e.data_ptr(), "3D4", 100.0, 1.0, float(T),
-                                                      mode=md, stream=stream), args.heart_steps)
+        one[nm] = timed(lambda: simulate(md), args.heart_steps)
     slabs = ekdist.slab_ranges(occ_z, world)
     z0, z1 = slabs[rank]
     model.set_slab(z0, z1)
     for nm, md in modes:
         def step():
-            model.simulate_device(d_k.data_ptr(), d_l.data_ptr(), 1, 2, d_e.data_ptr(), "3D4", 100.0, 1.0, float(T), mode=md, stream=stream)
+            simulate(md)
             ekdist.allreduce_sum_(d_e)
         ms = timed(step, args.heart_steps)
         ecg = d_e.cpu().numpy()[0]
@@ -692,6 +700,24 @@ def run_b200_arm(args):
         sms = float(t.item())
         sep_launches = int(model.last_launch_count)
         sep_kernel = model.last_kernel_name
+        # the same with the caller's knowledge of the coefficients (ekg_simulate_device_hinted): no read-back inside the call
+        sms_hinted = None
+        try:
+            k1_min_b, decay_max_b = ek.coefficient_hints(layer_k)
+            hint_events = []
+            for i in range(2 + args.steps):
+                flush.fill_(1)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                model.simulate_device_hinted(d_k.data_ptr(), d_leads.data_ptr(), B, L, d_ecg.data_ptr(), k1_min_b, decay_max_b, "3D4", 100.0, 1.0,
+                                             float(T_FULL), mode=ek.MODE_SEPARABLE, stream=stream)
+                f1.record()
+                if i >= 2:
+                    hint_events.append((f0, f1))
+            torch.cuda.synchronize()
+            sms_hinted = sum(a.elapsed_time(b) for a, b in hint_events) / len(hint_events)
+        except Exception:
+            sms_hinted = None
         # through the host-buffer C-ABI call in its default mode (what EkgSim::run / runBatch issue)
         for _ in range(2):
             model.simulate(layer_k, leads, "3D4", 100.0, 1.0, float(T_FULL), mode=ek.MODE_DEFAULT)
@@ -727,6 +753,8 @@ def run_b200_arm(args):
         mk_sum = sum(corner_sum_ms) / len(corner_sum_ms)
         ecg_series = d_ecg.cpu().numpy()
         separable = {"kernel": sep_kernel, "ms_per_step": sms, "sims_per_s": world * B / (sms * 1e-3),
+                     "ms_per_step_hinted": sms_hinted, "hinted_note": "ekg_simulate_device_hinted: the caller passes the batch's smallest k1 and largest "
+                     "decay rate, the call does not read them back from the device (this rank's time)",
                      "equivalent_voxel_timesteps_per_s": vts_step_global / (sms * 1e-3),
                      "moment_kernel_ms": mk, "launches_per_step": sep_launches,
                      "interior_voxel_fraction": f_int,
@@ -752,6 +780,25 @@ def run_b200_arm(args):
         s1.record()
         torch.cuda.synchronize()
         single[nm + "_ms"] = s0.elapsed_time(s1) / 20
+    # the default mode once more with the caller's knowledge of the coefficients (ekg_simulate_device_hinted: no read-back of
+    # the batch's rates in the middle of the call -- what ekg_simulate with host buffers does internally)
+    try:
+        k1_min, decay_max = ek.coefficient_hints(layer_k[:1])
+        def hinted():
+            model.simulate_device_hinted(d_k.data_ptr(), d_leads.data_ptr(), 1, L, d_ecg.data_ptr(), k1_min, decay_max, "3D4", 100.0, 1.0,
+                                         float(T_FULL), mode=ek.MODE_SEPARABLE, stream=stream)
+        for _ in range(3):
+            hinted()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(20):
+            hinted()
+        s1.record()
+        torch.cuda.synchronize()
+        single["separable_hinted_ms"] = s0.elapsed_time(s1) / 20
+    except Exception as e:
+        single["separable_hinted_error"] = repr(e)
     single["reference_cpu_s"] = 205.28  # SURVEY.md section 6, measured with the compiled reference on one core
 
     # -- whole pipeline, parameter vectors -> criteria: Evaluator::evalBatch = border APs on the host +

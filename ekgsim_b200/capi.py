@@ -58,6 +58,7 @@ SYMBOLS = {
     "ekg_simulate": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p]),
     "ekg_simulate_criteria": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _i64, _p, _int, _p, _p]),
     "ekg_simulate_device": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _p]),
+    "ekg_simulate_device_hinted": (_int, [_p, _p, _p, _i64, _i64, _int, _d, _d, _d, _int, _d, _d, _p, _p]),
     "ekg_fit_layers": (_int, [_p, _p, _i64, _i64, _i64, _p, _d, _d, _i64, _p]),
     "ekg_fit_layers_device": (_int, [_p, _p, _i64, _i64, _i64, _p, _d, _d, _i64, _p, _p]),
     "ekg_evaluate": (_int, [_p, _p, _i64, _i64, _p, _d, _d, _i64, _p, _i64, _i64, _int, _d, _d, _d, _int, _p, _i64, _p, _int, _p, _p, _p]),
@@ -98,6 +99,13 @@ def _check(rc):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def coefficient_hints(layer_k):
+    """(k1_min, decay_max) of layer coefficients [..., 9] for simulate_device_hinted: the smallest k1, the largest of
+    |k4 + k5| and |k5| (what ekg_simulate derives from its host buffers, capi.cu simulate_host)"""
+    k = np.asarray(layer_k, dtype=np.float64).reshape(-1, 9)
+    return float(k[:, 1].min()), float(np.maximum(np.abs(k[:, 4] + k[:, 5]), np.abs(k[:, 5])).max())
 
 
 def n_steps(total_time, t_step):
@@ -288,6 +296,13 @@ class Model:
         _check(lib().ekg_simulate_device(self._h, C.c_void_p(d_layer_k), C.c_void_p(d_leads), int(B), int(L),
                                          NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd), float(t_start), float(t_step),
                                          float(total_time), int(mode), C.c_void_p(d_ecg), C.c_void_p(stream)))
+
+    def simulate_device_hinted(self, d_layer_k, d_leads, B, L, d_ecg, k1_min, decay_max, nbhd="3D4", t_start=100.0, t_step=1.0,
+                               total_time=400.0, mode=MODE_DEFAULT, stream=0):
+        """simulate_device for a caller who knows the coefficients on the host (`coefficient_hints`): no read-back inside"""
+        _check(lib().ekg_simulate_device_hinted(self._h, C.c_void_p(d_layer_k), C.c_void_p(d_leads), int(B), int(L),
+                                                NBHD[nbhd] if isinstance(nbhd, str) else int(nbhd), float(t_start), float(t_step),
+                                                float(total_time), int(mode), float(k1_min), float(decay_max), C.c_void_p(d_ecg), C.c_void_p(stream)))
 
     def fit_layers(self, border_k, mid=-1, d9=FIT_D9, step=0.5, eps=1e-3, iterations=100):
         """Border APs [B, 2|3, 9] -> layer coefficients [B, n_layers, 9] (sim.cpp:751-916 on the device)."""

@@ -869,6 +869,18 @@ int ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_l
 	return run_ecg(m, d_layer_k, d_leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, d_ecg_out, (cudaStream_t)stream);
 }
 
+int ekg_simulate_device_hinted(ekg_model* m, const double* d_layer_k, const double* d_leads_zyx, int64_t B, int64_t n_leads, int nbhd,
+                               double t_start, double t_step, double total_time, int flags, double k1_min, double decay_max, double* d_ecg_out,
+                               void* stream) {
+	if (!m || !d_layer_k || !d_leads_zyx || !d_ecg_out) return fail(EKG_E_INVALID, "NULL argument");
+	if (!(k1_min > 0) || !std::isfinite(k1_min) || !(decay_max >= 0) || !std::isfinite(decay_max)) return fail(EKG_E_INVALID, "bad coefficient hints");
+	EKG_CUDA(cudaSetDevice(m->device));
+	KHints hints;
+	hints.k1_min = k1_min;
+	hints.decay_max = decay_max;
+	return run_ecg(m, d_layer_k, d_leads_zyx, B, n_leads, nbhd, t_start, t_step, total_time, flags, d_ecg_out, (cudaStream_t)stream, hints);
+}
+
 // border APs + descent settings of the device-side layer fit (ekg_evaluate); border_k == NULL: layer_k is given
 struct FitRequest {
 	const double* border_k = nullptr;

@@ -201,6 +201,17 @@ int  ekg_simulate_device(ekg_model* m, const double* d_layer_k, const double* d_
                          double t_start, double t_step, double total_time,
                          int flags, double* d_ecg_out, void* stream);
 
+/* ekg_simulate_device for a caller who knows the batch's coefficients on the host (it uploaded them): k1_min = the
+ * smallest depolarisation rate k1, decay_max = the largest of |k4 + k5| and |k5|, over all (vector, layer).  The default /
+ * SEPARABLE mode needs both to decide from which sample on the sigmoid is saturated and whether the hoisted exponentials
+ * stay in range; without them ekg_simulate_device reads them back from the device (one stream synchronisation in the
+ * middle of the call).  With them the call is fully asynchronous -- what ekg_simulate (host buffers) does internally.
+ * Hints that do not bound the batch give wrong results. */
+int  ekg_simulate_device_hinted(ekg_model* m, const double* d_layer_k, const double* d_leads_zyx,
+                                int64_t B, int64_t n_leads, int nbhd,
+                                double t_start, double t_step, double total_time,
+                                int flags, double k1_min, double decay_max, double* d_ecg_out, void* stream);
+
 /* ekg_simulate + the reference's curve comparison on the device, so that only B x n_leads criteria
  * have to leave the GPU: criteria_out[b][l] compares ECG[b][l][0..n) with
  * targets[l][0..n), n = min(n_steps, n_target), offset 0, like calculateFitness does (sim.cpp:600-702):

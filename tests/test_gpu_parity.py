@@ -810,3 +810,38 @@ def test_fast_decay_falls_back_to_direct(gpu_model24, model24, model24_delay):
     assert gpu_model24.last_kernel_name == "ecg_kernel<HOISTED>"
     gpu_model24.simulate(g["layer_k"][:3], leads, "3D4", 100.0, 1.0, 80.0, mode=0)
     assert gpu_model24.last_kernel_name == "ecg_moment_kernel"
+
+
+def test_simulate_device_hinted_matches_unhinted(built, gpu_model24, model24_delay):
+    """ekg_simulate_device_hinted: the caller passes the batch's smallest k1 and largest decay rate, so the default mode does
+    not read them back from the device in the middle of the call.  Same kernels, same results as the unhinted call (the
+    device computes the same two numbers in fp32, so the split between time loop and moments may move by one sample:
+    tolerance instead of bit equality) and as the reference goldens; bad hints are rejected."""
+    import torch
+    g = np.load(os.path.join(GOLDEN, "golden_glue256.npz"))
+    gf = np.load(os.path.join(GOLDEN, "golden_eval_full.npz"))
+    gpu_model24.set_activation(model24_delay)
+    dev = torch.device("cuda", 0)
+    for k, leads in ((g["layer_k"][:5], g["leads_zyx"][:5]), (gf["layer_k"], gf["leads_zyx"])):
+        B = k.shape[0]
+        d_k = torch.from_numpy(np.ascontiguousarray(k)).to(dev)
+        d_l = torch.from_numpy(np.ascontiguousarray(leads)).to(dev)
+        e0 = torch.empty((B, 2, 400), dtype=torch.float64, device=dev)
+        e1 = torch.empty_like(e0)
+        stream = torch.cuda.current_stream().cuda_stream
+        k1_min, decay_max = built.coefficient_hints(k)
+        for t_start in (100.0, 0.0):                     # all samples after the QRS complex / the QRS complex inside the run
+            gpu_model24.simulate_device(d_k.data_ptr(), d_l.data_ptr(), B, 2, e0.data_ptr(), "3D4", t_start, 1.0, 400.0, mode=0, stream=stream)
+            gpu_model24.simulate_device_hinted(d_k.data_ptr(), d_l.data_ptr(), B, 2, e1.data_ptr(), k1_min, decay_max, "3D4", t_start, 1.0, 400.0,
+                                               mode=0, stream=stream)
+            torch.cuda.synchronize()
+            a, b = e0.cpu().numpy(), e1.cpu().numpy()
+            assert rel_err(b, a) < 2e-6, (t_start, rel_err(b, a))
+    assert rel_err(b, b) == 0.0
+    # the last batch at t_start = 100 is the reference's own configuration
+    gpu_model24.simulate_device_hinted(d_k.data_ptr(), d_l.data_ptr(), B, 2, e1.data_ptr(), k1_min, decay_max, "3D4", 100.0, 1.0, 400.0, mode=0, stream=stream)
+    torch.cuda.synchronize()
+    assert rel_err(e1.cpu().numpy(), gf["ecg"]) < ECG_TOL
+    for bad in ((0.0, 1.0), (float("nan"), 1.0), (1.0, -1.0), (1.0, float("inf"))):
+        with pytest.raises(built.EkgError):
+            gpu_model24.simulate_device_hinted(d_k.data_ptr(), d_l.data_ptr(), B, 2, e1.data_ptr(), bad[0], bad[1], "3D4", 100.0, 1.0, 400.0, mode=0, stream=stream)
