@@ -63,6 +63,16 @@ int64_t ekg_host_load_shape(const char* fname, uint16_t* layers_out, int64_t cap
 	} catch (std::exception& e) { g_host_error = e.what(); return -1; }
 }
 
+/// EkgSim::balancedSlabs: the z-slab cuts of the C++ host's `-slabs` mode; out = n x (z_begin, z_end).  Host only.
+int ekg_host_balanced_slabs(const uint16_t* layers, int64_t Z, int64_t Y, int64_t X, int n, int64_t* out) {
+	try {
+		std::vector<uint16_t> l(layers, layers + Z * Y * X);
+		const std::vector<std::pair<int64_t, int64_t>> s = SimLib::EkgSim::balancedSlabs(l, Z, Y, X, (size_t)n);
+		for (int i = 0; i < n; ++i) { out[2 * i] = s[(size_t)i].first; out[2 * i + 1] = s[(size_t)i].second; }
+		return 0;
+	} catch (std::exception& e) { g_host_error = e.what(); return -1; }
+}
+
 /// Evaluator over the simulator.ini of the CURRENT directory (like the CLI).  Needs a GPU.
 void* ekg_host_evaluator_create(const char* ini, int with_device) {
 	try { return new ekg::Evaluator(ini, with_device != 0); }

@@ -179,6 +179,35 @@ private:
 
 	static void check(int rc) { if (rc != EKG_OK) throw std::runtime_error(ekg_last_error()); }
 
+public:
+	/// [0, Z) cut into n contiguous z-slabs of (nearly) equal numbers of occupied voxels (the same cuts as
+	/// ekgsim_b200/dist.py::slab_ranges makes for the torchrun layout); slabs may be empty for tiny models
+	static std::vector<std::pair<int64_t, int64_t>> balancedSlabs(const std::vector<uint16_t>& layers, int64_t Z, int64_t Y, int64_t X, size_t n) {
+		std::vector<int64_t> cum((size_t)Z + 1, 0);
+		for (int64_t z = 0; z < Z; ++z) {
+			int64_t c = 0;
+			const uint16_t* pl = &layers[(size_t)(z * Y * X)];
+			for (int64_t i = 0; i < Y * X; ++i) c += (pl[i] & 0x0fff) != 0;
+			cum[(size_t)z + 1] = cum[(size_t)z] + c;
+		}
+		std::vector<std::pair<int64_t, int64_t>> slabs(n, std::make_pair<int64_t, int64_t>(0, 0));
+		int64_t prev = 0;
+		for (size_t d = 0; d < n; ++d) {
+			int64_t cut = Z;
+			if (d + 1 < n) {
+				// the first plane count whose prefix reaches the target, or the one before it if that prefix is at least as close
+				const double target = (double)cum[(size_t)Z] * (double)(d + 1) / (double)n;
+				cut = (int64_t)(std::lower_bound(cum.begin(), cum.end(), target, [](int64_t a, double t) { return (double)a < t; }) - cum.begin());
+				if (cut > 0 && std::fabs((double)cum[(size_t)cut - 1] - target) <= std::fabs((double)cum[(size_t)std::min<int64_t>(cut, Z)] - target)) --cut;
+				cut = std::min(std::max(cut, prev), Z);
+			}
+			slabs[d] = std::make_pair(prev, cut);
+			prev = cut;
+		}
+		return slabs;
+	}
+
+private:
 	void ensureModel() {
 		if (model_) return;
 		if (layers_.empty()) throw std::runtime_error("shape not loaded");
@@ -196,27 +225,7 @@ private:
 				throw std::runtime_error(ekg_last_error());
 		});
 		model_ = slabModels_[0];
-		// slabs of (nearly) equal numbers of occupied voxels
-		std::vector<int64_t> cum((size_t)Z_ + 1, 0);
-		for (int64_t z = 0; z < Z_; ++z) {
-			int64_t c = 0;
-			const uint16_t* pl = &layers_[(size_t)(z * Y_ * X_)];
-			for (int64_t i = 0; i < Y_ * X_; ++i) c += (pl[i] & 0x0fff) != 0;
-			cum[(size_t)z + 1] = cum[(size_t)z] + c;
-		}
-		slabRanges_.assign(n, std::make_pair<int64_t, int64_t>(0, 0));
-		int64_t prev = 0;
-		for (size_t d = 0; d < n; ++d) {
-			int64_t cut = Z_;
-			if (d + 1 < n) {
-				const double target = (double)cum[(size_t)Z_] * (double)(d + 1) / (double)n;
-				cut = (int64_t)(std::lower_bound(cum.begin(), cum.end(), (int64_t)std::ceil(target)) - cum.begin());
-				if (cut > 0 && std::fabs((double)cum[(size_t)cut - 1] - target) <= std::fabs((double)cum[(size_t)std::min<int64_t>(cut, Z_)] - target)) --cut;
-				cut = std::min(std::max(cut, prev), Z_);
-			}
-			slabRanges_[d] = std::make_pair(prev, cut);
-			prev = cut;
-		}
+		slabRanges_ = balancedSlabs(layers_, Z_, Y_, X_, n);
 		forEachSlab([&](size_t d) {
 			if (ekg_model_set_slab(slabModels_[d], slabRanges_[d].first, slabRanges_[d].second) != EKG_OK) throw std::runtime_error(ekg_last_error());
 		});

@@ -203,3 +203,24 @@ def test_run_approximation_matches_oracle(built):
         i = len(got) // 2
         t = start + i * step
         assert got[i] == hostlib.lib().ekg_host_wohlfart_plus(k[0].ctypes.data, t + delay) - hostlib.lib().ekg_host_wohlfart_plus(k[-1].ctypes.data, t)
+
+
+def test_cxx_host_slab_cuts_equal_the_python_driver(built, model24):
+    """`ekgSim -slabs N` (EkgSim::balancedSlabs, sim_lib.h) cuts a model into z-slabs exactly like ekgsim_b200/dist.py::slab_ranges
+    does for the torchrun layout: the two hosts shard one model the same way, also when slabs come out empty."""
+    import ctypes as C
+    from ekgsim_b200 import dist as ekdist
+    rng = np.random.default_rng(5)
+    tiny = np.zeros((3, 4, 5), dtype=np.uint16)
+    tiny[1, 2, 3] = 1
+    sparse = (rng.random((17, 9, 11)) < 0.2).astype(np.uint16) * 3
+    sparse[5:9] = 0
+    for layers in (model24["layers"], tiny, sparse):
+        l = np.ascontiguousarray(layers, dtype=np.uint16)
+        occ = ((l & 0x0FFF) > 0).sum(axis=(1, 2))
+        for n in (1, 2, 3, 4, 8, 16):
+            out = np.zeros((n, 2), dtype=np.int64)
+            rc = hostlib.lib().ekg_host_balanced_slabs(l.ctypes.data_as(C.c_void_p), C.c_int64(l.shape[0]), C.c_int64(l.shape[1]), C.c_int64(l.shape[2]),
+                                                       C.c_int(n), out.ctypes.data_as(C.c_void_p))
+            assert rc == 0
+            assert [tuple(int(v) for v in row) for row in out] == ekdist.slab_ranges(occ, n), (l.shape, n)
